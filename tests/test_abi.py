@@ -1,0 +1,100 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every
+symbol include/x264vfw_cuda.h declares, keeps the reference's geometry and error behaviour,
+and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    syms = set()
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            text = open(os.path.join(ROOT, "include", fn)).read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+            syms |= set(re.findall(r"\b(x264vfw_cuda_[a-z0-9_]+)\s*\(", text))
+    return sorted(syms)
+
+
+def test_library_exports_every_declared_symbol():
+    import x264vfw_b200
+    lib = C.CDLL(x264vfw_b200._lib.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 12
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert "sm_100a" in x264vfw_b200.version()
+
+
+def test_img_fill_matches_codec_c_geometry():
+    from x264vfw_b200 import csp
+    # codec.c:365 BGR stride rounds up to 4 bytes; :359 packed 4:2:2 is 2*w; :371 BGRA 4*w
+    img, n = csp.img_fill(0, csp.X264VFW_CSP_BGR, 66, 48)
+    assert img.i_stride[0] == 200 and n == 200 * 48 and img.i_plane == 1
+    img, n = csp.img_fill(0, csp.X264VFW_CSP_YUYV, 1280, 720)
+    assert img.i_stride[0] == 2560 and n == 1843200
+    img, n = csp.img_fill(0, csp.X264VFW_CSP_BGRA | csp.X264VFW_CSP_VFLIP, 1920, 1080)
+    assert img.i_stride[0] == 7680 and n == 8294400
+    img, n = csp.img_fill(0, csp.X264VFW_CSP_YV12, 64, 48)
+    assert (img.i_plane, img.i_stride[0], img.i_stride[1], n) == (3, 64, 32, 64 * 48 * 3 // 2)
+    img, n = csp.img_fill(0, csp.X264VFW_CSP_NV12, 64, 48)
+    assert (img.i_plane, img.i_stride[1], n) == (2, 64, 64 * 48 * 3 // 2)
+    with pytest.raises(ValueError):
+        csp.img_fill(0, 0, 64, 48)
+
+
+def test_get_csp_and_output_csp_follow_codec_c():
+    from x264vfw_b200 import csp
+    assert csp.get_csp(csp.BI_RGB, 32, 1080) == csp.X264VFW_CSP_BGRA | csp.X264VFW_CSP_VFLIP   # codec.c:220
+    assert csp.get_csp(csp.BI_RGB, 32, -1080) == csp.X264VFW_CSP_BGRA
+    assert csp.get_csp(csp.BI_RGB, 24, 1) == csp.X264VFW_CSP_BGR | csp.X264VFW_CSP_VFLIP
+    assert csp.get_csp(csp.BI_RGB, 16, 1) == csp.X264VFW_CSP_NONE
+    assert csp.get_csp(csp.fourcc("YUY2"), 16, 720) == csp.X264VFW_CSP_YUYV                    # never flipped, :189
+    assert csp.get_csp(csp.fourcc("HDYC"), 16, 720) == csp.X264VFW_CSP_UYVY
+    assert csp.choose_output_csp(csp.X264VFW_CSP_UYVY, False) == csp.X264_CSP_I420
+    assert csp.choose_output_csp(csp.X264VFW_CSP_UYVY, True) == csp.X264_CSP_I422
+    assert csp.choose_output_csp(csp.X264VFW_CSP_BGRA | csp.X264VFW_CSP_VFLIP, True) == csp.X264_CSP_BGRA
+    assert csp.choose_output_csp(csp.X264VFW_CSP_NV12, False) == csp.X264_CSP_NV12
+
+
+def test_unregistered_pairs_return_minus_one_without_touching_the_gpu():
+    """csp.c:443-444: every slot the reference leaves at convert_fail must return -1."""
+    from x264vfw_b200 import csp
+    from x264vfw_b200._lib import Image
+    registered = {
+        csp.X264_CSP_I420: {1, 2, 3, 4, 6, 7, 8, 9}, csp.X264_CSP_NV12: {5}, csp.X264_CSP_I422: {3, 6, 7},
+        csp.X264_CSP_I444: {4}, csp.X264_CSP_BGR: {8}, csp.X264_CSP_BGRA: {9},
+    }
+    a, b = Image(), Image()
+    for out, ok in registered.items():
+        t = csp.csp_init(out, 2, 0)
+        for i in range(csp.X264VFW_CSP_MAX):
+            if i not in ok:
+                assert t.convert[i](C.byref(a), C.byref(b), 64, 48) == -1, (out, i)
+    t = csp.csp_init(0x1234, 2, 0)       # unknown encoder csp: whole table fails
+    assert all(t.convert[i](C.byref(a), C.byref(b), 64, 48) == -1 for i in range(csp.X264VFW_CSP_MAX))
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from x264vfw_b200._lib import Context, CudaError
+    with pytest.raises(CudaError):
+        Context()
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product path (package + csrc + include) must never import/link oracle/."""
+    bad = []
+    for base in ("x264vfw_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c", "Makefile")):
+                    if re.search(r"oracle", open(os.path.join(dp, fn), errors="ignore").read()):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad

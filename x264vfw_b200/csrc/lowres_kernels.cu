@@ -1,0 +1,138 @@
+// Half-resolution ("lowres") plane construction for the lookahead.
+//
+// Replaces, in one pass over the tight luma plane:
+//   [x264] x264_frame_expand_border_mod16 (luma)      -- replicate to 16*mb_w x 16*mb_h
+//   [x264] x264_frame_init_lowres: duplicate last row/column, frame_init_lowres_core
+//          (FILTER(a,b,c,d) = (((a+b+1)>>1)+((c+d+1)>>1)+1)>>1, four phase planes 0/H/V/C)
+//   [x264] x264_frame_expand_border_lowres            -- 32-pixel edge replication
+// (reached in the reference only through codec.c:1693).
+//
+// The mod-16 replication and the duplicated row/column are both "clamp the source
+// coordinate", so they are folded into addressing: P(x,y) = Y(min(x,w-1), min(y,h-1)).
+// The 32-pixel border is "clamp the lowres coordinate", so the grid simply runs over the
+// padded output domain and border threads compute the clamped pixel.  No intermediate
+// padded luma plane, no separate border pass: read luma once, write 4 planes once.
+#include "common.cuh"
+#include "csp_kernels.h"
+
+namespace xv {
+
+#define LOWRES_PAD 32
+
+// gather even / odd bytes of 16 bytes (+1 trailing byte) and form the two horizontal phases
+__device__ __forceinline__ void hphase(const uint4 v, uint32_t tail, uint2 &p0, uint2 &ph)
+{
+    uint32_t e_lo = __byte_perm(v.x, v.y, 0x6420), e_hi = __byte_perm(v.z, v.w, 0x6420);
+    uint32_t o_lo = __byte_perm(v.x, v.y, 0x7531), o_hi = __byte_perm(v.z, v.w, 0x7531);
+    uint32_t n_lo = __funnelshift_r(e_lo, e_hi, 8), n_hi = __funnelshift_r(e_hi, tail, 8);
+    p0 = make_uint2(avg4(e_lo, o_lo), avg4(e_hi, o_hi));
+    ph = make_uint2(avg4(o_lo, n_lo), avg4(o_hi, n_hi));
+}
+
+__device__ __forceinline__ uint4 avg16(uint4 a, uint4 b)
+{
+    return make_uint4(avg4(a.x, b.x), avg4(a.y, b.y), avg4(a.z, b.z), avg4(a.w, b.w));
+}
+
+__device__ __forceinline__ uint32_t filt(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return (((a + b + 1) >> 1) + ((c + d + 1) >> 1) + 1) >> 1;
+}
+
+__global__ void __launch_bounds__(256)
+lowres_init_kernel(LowresJob job)
+{
+    const int chunks = (job.lw + 2 * LOWRES_PAD) >> 3;
+    const int rows = job.lh + 2 * LOWRES_PAD;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= chunks * rows) return;
+    const int prow = idx / chunks;
+    const int pchunk = idx - prow * chunks;
+    const size_t f = blockIdx.y;
+    const uint8_t *Y = job.y + f * job.src_frame_bytes;
+    const int ys = job.y_stride, w = job.w, h = job.h;
+
+    const int ly = min(max(prow - LOWRES_PAD, 0), job.lh - 1);   // clamped lowres row
+    const int lx = (pchunk << 3) - LOWRES_PAD;                    // first lowres x of this chunk
+    const int r0 = min(2 * ly, h - 1), r1 = min(2 * ly + 1, h - 1), r2 = min(2 * ly + 2, h - 1);
+    const uint8_t *s0 = Y + (size_t)r0 * ys, *s1 = Y + (size_t)r1 * ys, *s2 = Y + (size_t)r2 * ys;
+
+    uint2 o0, oh, ov, oc;
+    const int sx = 2 * lx;
+    if (lx >= 0 && lx + 8 <= job.lw && sx + 17 <= w && ((ys | (int)(uintptr_t)Y) & 15) == 0) {
+        // fast path: 16 source bytes per row + the 17th from the next chunk
+        uint4 a = *(const uint4 *)(s0 + sx), b = *(const uint4 *)(s1 + sx), c = *(const uint4 *)(s2 + sx);
+        uint32_t ta = s0[sx + 16], tb = s1[sx + 16], tc = s2[sx + 16];
+        hphase(avg16(a, b), (ta + tb + 1) >> 1, o0, oh);
+        hphase(avg16(b, c), (tb + tc + 1) >> 1, ov, oc);
+    } else {
+        // edge path: per-pixel with clamped coordinates (frame edge, padding, odd geometry)
+        uint32_t r[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        uint32_t last[4] = {0, 0, 0, 0};
+        int last_x = -1 << 30;
+        for (int i = 0; i < 8; i++) {
+            int x = min(max(lx + i, 0), job.lw - 1);
+            if (x != last_x) {
+                int c0 = min(2 * x, w - 1), c1 = min(2 * x + 1, w - 1), c2 = min(2 * x + 2, w - 1);
+                last[0] = filt(s0[c0], s1[c0], s0[c1], s1[c1]);
+                last[1] = filt(s0[c1], s1[c1], s0[c2], s1[c2]);
+                last[2] = filt(s1[c0], s2[c0], s1[c1], s2[c1]);
+                last[3] = filt(s1[c1], s2[c1], s1[c2], s2[c2]);
+                last_x = x;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) r[k][i >> 2] |= last[k] << (8 * (i & 3));
+        }
+        o0 = make_uint2(r[0][0], r[0][1]); oh = make_uint2(r[1][0], r[1][1]);
+        ov = make_uint2(r[2][0], r[2][1]); oc = make_uint2(r[3][0], r[3][1]);
+    }
+    uint8_t *d = job.dst + f * job.dst_frame_bytes + (size_t)prow * job.lstride + (pchunk << 3);
+    *(uint2 *)(d) = o0;
+    *(uint2 *)(d + (size_t)job.lplane_bytes) = oh;
+    *(uint2 *)(d + 2 * (size_t)job.lplane_bytes) = ov;
+    *(uint2 *)(d + 3 * (size_t)job.lplane_bytes) = oc;
+}
+
+int launch_lowres_init(cudaStream_t st, const LowresJob &job, int n_frames)
+{
+    const long long total = (long long)((job.lw + 2 * LOWRES_PAD) >> 3) * (job.lh + 2 * LOWRES_PAD);
+    if (total <= 0 || n_frames <= 0) return 0;
+    dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_frames);
+    lowres_init_kernel<<<grid, 256, 0, st>>>(job);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+// [x264] x264_frame_copy_picture (luma) + x264_frame_expand_border_mod16 + the extra
+// duplicated column/row of x264_frame_init_lowres, as one clamped copy.
+__global__ void __launch_bounds__(256)
+luma_pad_kernel(LumaPadJob job)
+{
+    const int chunks = (job.luma_w + 1 + 15) >> 4;
+    const int rows = job.luma_h + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= chunks * rows) return;
+    const int row = idx / chunks;
+    const int x = (idx - row * chunks) << 4;
+    const size_t f = blockIdx.y;
+    const uint8_t *s = job.y + f * job.src_frame_bytes + (size_t)min(row, job.h - 1) * job.y_stride;
+    uint8_t *d = job.dst + f * job.dst_frame_bytes + (size_t)row * job.dst_stride + x;
+    const int n = min(16, job.luma_w + 1 - x);
+    if (n == 16 && x + 16 <= job.w && ((job.y_stride | job.dst_stride | (int)(uintptr_t)job.y | (int)(uintptr_t)job.dst) & 15) == 0) {
+        *(uint4 *)d = ldg_stream128(s + x);
+    } else {
+        for (int i = 0; i < n; i++) d[i] = s[min(x + i, job.w - 1)];
+    }
+}
+
+int launch_luma_pad(cudaStream_t st, const LumaPadJob &job, int n_frames)
+{
+    const long long total = (long long)((job.luma_w + 1 + 15) >> 4) * (job.luma_h + 1);
+    if (total <= 0 || n_frames <= 0) return 0;
+    dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_frames);
+    luma_pad_kernel<<<grid, 256, 0, st>>>(job);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace xv
