@@ -1,0 +1,113 @@
+/*
+ * lookahead_oracle.h -- CPU restatement of libx264's lookahead cost engine.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED: libx264 is an external,
+ * un-vendored, un-pinned dependency of the reference (reference Makefile:21-23,109); the
+ * only call site is x264_encoder_encode at codec.c:1693.  Every function cites the upstream
+ * libx264 function it follows as "[x264] path: function".
+ */
+#ifndef X264VFW_LOOKAHEAD_ORACLE_H
+#define X264VFW_LOOKAHEAD_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_BFRAME_MAX 16
+#define ORC_LOOKAHEAD_MAX 250
+
+/* frame types: public X264_TYPE_* values of x264.h */
+#define ORC_TYPE_AUTO 0
+#define ORC_TYPE_IDR 1
+#define ORC_TYPE_I 2
+#define ORC_TYPE_P 3
+#define ORC_TYPE_BREF 4
+#define ORC_TYPE_B 5
+#define ORC_TYPE_KEYFRAME 6
+
+/* Plain-int parameter block (x264_param_t subset the lookahead reads).  Field order is
+ * shared with x264vfw_cuda_la_params in include/x264vfw_cuda.h. */
+typedef struct orc_la_params {
+    int   width, height;
+    int   chroma_format;       /* 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (AQ chroma energy)          */
+    int   bframes;             /* i_bframe                                                   */
+    int   b_adapt;             /* i_bframe_adaptive: 0 none, 1 fast, 2 trellis               */
+    int   b_pyramid;           /* i_bframe_pyramid: 0 none, 1 strict, 2 normal               */
+    int   b_bias;              /* i_bframe_bias                                              */
+    int   rc_lookahead;        /* rc.i_lookahead                                             */
+    int   b_mbtree;            /* rc.b_mb_tree                                               */
+    int   scenecut;            /* i_scenecut_threshold                                       */
+    int   keyint_max, keyint_min;
+    int   open_gop;
+    int   weightp;             /* analyse.i_weighted_pred                                    */
+    int   weightb;             /* analyse.b_weighted_bipred                                  */
+    int   subme;               /* analyse.i_subpel_refine of the ENCODER (selects lookahead mode) */
+    int   me_method;           /* analyse.i_me_method (0 dia, 1 hex, ...)                    */
+    int   me_range;            /* analyse.i_me_range                                         */
+    int   mv_range;            /* analyse.i_mv_range after level resolution (512 for level>=3.1) */
+    int   aq_mode;             /* rc.i_aq_mode (0 or 1 supported)                            */
+    float aq_strength;
+    float qcompress;
+    int   frame_reference;     /* i_frame_reference                                          */
+    int   lookahead_threads;   /* i_lookahead_threads (band split of the MB scan)            */
+    int   fps_num, fps_den;
+    int   b_psy;               /* analyse.b_psy (with mbtree: analyse past keyint)           */
+} orc_la_params;
+
+void orc_la_params_preset(orc_la_params *p, const char *preset, int width, int height);
+
+typedef struct orc_la orc_la;
+
+orc_la *orc_la_open(const orc_la_params *p);
+void    orc_la_close(orc_la *la);
+/* Feed one frame in display order (tight planar input in the encoder csp; u/v may be NULL
+ * for luma-only experiments -> chroma energy 0).  Returns number of decided frames now
+ * waiting in the output queue. */
+int orc_la_put_frame(orc_la *la, const uint8_t *y, int y_stride, const uint8_t *u, const uint8_t *v, int c_stride);
+/* End of stream: decide everything still queued ([x264] lookahead flush). */
+int orc_la_flush(orc_la *la);
+
+typedef struct orc_la_decision {
+    int i_frame;        /* display index                                                     */
+    int i_type;         /* ORC_TYPE_IDR/I/P/BREF/B                                           */
+    int b_keyframe;
+    int i_bframes;      /* for the non-B of a mini-GOP: number of B-frames before it         */
+    int i_cost_est;     /* slicetype_frame_cost of the chosen (p0,p1,b); -1 if not computed  */
+    int i_cost_est_aq;
+    int i_intra_mbs;
+    int mb_count;
+} orc_la_decision;
+
+/* Pop the next decided frame (coded order).  qp_offset / qp_offset_aq receive mb_count floats
+ * each when non-NULL (x264_frame_t.f_qp_offset / f_qp_offset_aq).  Returns 1, or 0 if empty. */
+int orc_la_get_decision(orc_la *la, orc_la_decision *d, float *qp_offset, float *qp_offset_aq);
+
+/* ---- white-box access for kernel-level parity tests ------------------------------------- */
+/* All frames ever fed stay addressable by display index until orc_la_close (memory grows
+ * with clip length; the oracle is for short clips). */
+int  orc_la_mb_count(orc_la *la);
+/* run slicetype_frame_cost(p0,p1,b) on explicit display indices (frames[] = identity map) */
+int  orc_la_frame_cost(orc_la *la, int p0, int p1, int b);
+const uint8_t  *orc_la_lowres_planes(orc_la *la, int frame);                 /* 4 padded planes */
+const uint16_t *orc_la_intra_cost(orc_la *la, int frame);
+const uint16_t *orc_la_inv_qscale(orc_la *la, int frame);
+const uint16_t *orc_la_propagate_cost(orc_la *la, int frame);
+const float    *orc_la_qp_offset(orc_la *la, int frame, int aq);
+const int16_t  *orc_la_mvs(orc_la *la, int frame, int list, int dist);       /* [mb][2], dist>=1 */
+const int      *orc_la_mv_costs(orc_la *la, int frame, int list, int dist);
+const uint16_t *orc_la_lowres_costs(orc_la *la, int frame, int d0, int d1);
+int  orc_la_cost_est(orc_la *la, int frame, int d0, int d1, int aq);
+int  orc_la_intra_mbs(orc_la *la, int frame, int d0);
+void orc_la_pixel_stats(orc_la *la, int frame, uint64_t sum[3], uint64_t ssd[3]);
+/* last weight found by the lookahead weight analysis for frame (scale, denom, offset, enabled) */
+void orc_la_weight(orc_la *la, int frame, int out[4]);
+const uint16_t *orc_cost_mv_table(int mv_range, int *half_len);
+/* run one mb-tree pass over explicit display indices with explicit types (for kernel parity) */
+void orc_la_mbtree(orc_la *la, const int *frame_idx, const int *types, int num_frames, int b_intra);
+/* counters: number of MB motion searches / SAD / SATD evaluations performed so far */
+void orc_la_counters(orc_la *la, uint64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
