@@ -150,6 +150,121 @@ int x264vfw_cuda_lowres_init( x264vfw_cuda_ctx *ctx, uint8_t *dst_dev, const uin
                               int y_stride, int i_width, int i_height,
                               size_t src_frame_bytes, size_t dst_frame_bytes, int n_frames );
 
+/* ------------------------------------------------------------------------------------
+ * B2: the lookahead session.  Replaces what happens between x264_encoder_encode receiving
+ * a picture (codec.c:1693) and the frame type / per-MB qp offsets being known:
+ * [x264] x264_adaptive_quant_frame, x264_frame_init_lowres, x264_lookahead_put_frame,
+ * x264_slicetype_decide / x264_slicetype_analyse (scenecut, b-adapt 1/2, mb-tree) with
+ * slicetype_frame_cost on the GPU.  The decisions are handed to the CPU encoder through
+ * x264_picture_t.i_type and .prop.quant_offsets.
+ * ---------------------------------------------------------------------------------- */
+#define X264VFW_CUDA_TYPE_AUTO     0   /* X264_TYPE_* of x264.h */
+#define X264VFW_CUDA_TYPE_IDR      1
+#define X264VFW_CUDA_TYPE_I        2
+#define X264VFW_CUDA_TYPE_P        3
+#define X264VFW_CUDA_TYPE_BREF     4
+#define X264VFW_CUDA_TYPE_B        5
+#define X264VFW_CUDA_BFRAME_MAX    16  /* X264_BFRAME_MAX */
+#define X264VFW_CUDA_LOOKAHEAD_MAX 250 /* X264_LOOKAHEAD_MAX */
+
+/* The x264_param_t fields the lookahead reads, after x264_param_default_preset /
+ * x264_param_parse / level resolution (codec.c:1463,1349,1584). */
+typedef struct x264vfw_cuda_la_params
+{
+    int   width, height;
+    int   chroma_format;       /* 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (of the ENCODER csp)            */
+    int   bframes;             /* i_bframe                                                       */
+    int   b_adapt;             /* i_bframe_adaptive: 0 none, 1 fast, 2 trellis                   */
+    int   b_pyramid;           /* i_bframe_pyramid: 0 none, 1 strict, 2 normal                   */
+    int   b_bias;              /* i_bframe_bias                                                  */
+    int   rc_lookahead;        /* rc.i_lookahead                                                 */
+    int   b_mbtree;            /* rc.b_mb_tree                                                   */
+    int   scenecut;            /* i_scenecut_threshold                                           */
+    int   keyint_max, keyint_min;
+    int   open_gop;
+    int   weightp;             /* analyse.i_weighted_pred                                        */
+    int   weightb;             /* analyse.b_weighted_bipred                                      */
+    int   subme;               /* analyse.i_subpel_refine (selects the lookahead's search mode)  */
+    int   me_method;           /* analyse.i_me_method                                            */
+    int   me_range;            /* analyse.i_me_range                                             */
+    int   mv_range;            /* analyse.i_mv_range after level resolution                      */
+    int   aq_mode;             /* rc.i_aq_mode (0 or 1)                                          */
+    float aq_strength;
+    float qcompress;
+    int   frame_reference;     /* i_frame_reference                                              */
+    int   lookahead_threads;   /* i_lookahead_threads: band split of the MB scan (pin for parity) */
+    int   fps_num, fps_den;
+    int   b_psy;
+} x264vfw_cuda_la_params;
+
+/* x264 defaults + the preset deltas documented at config.c:1460-1498.  Returns 0 / -1. */
+int x264vfw_cuda_la_params_preset( x264vfw_cuda_la_params *p, const char *preset, int width, int height );
+
+typedef struct x264vfw_cuda_la x264vfw_cuda_la;
+
+/* i_in_csp: X264VFW_CUDA_CSP_* (| VFLIP) of the frames passed to put_frame, converted on the
+ * device to i_x264_csp first (stage 1), or X264VFW_CUDA_CSP_NONE when put_frame receives
+ * planar frames already in the encoder csp.  keep_frames != 0 keeps every frame addressable
+ * for x264vfw_cuda_la_read (tests); otherwise frames are recycled as the window slides.
+ * device < 0: current device. */
+int  x264vfw_cuda_la_open( x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *params, int device,
+                           int i_in_csp, int i_x264_csp, int i_colmatrix, int b_fullrange,
+                           int keep_frames );
+void x264vfw_cuda_la_close( x264vfw_cuda_la *la );
+
+/* One input frame in display order == one x264_encoder_encode( pic_in ) call.
+ * src describes the frame like x264vfw_img_fill does; src_on_device selects host or device
+ * pointers.  conv_pic (may be NULL) receives the converted planes in HOST memory -- what
+ * codec->conv_pic holds for the CPU encoder.  Returns the number of decided frames waiting
+ * in the output queue, or -1. */
+int x264vfw_cuda_la_put_frame( x264vfw_cuda_la *la, const x264vfw_cuda_image_t *src, int src_on_device,
+                               x264vfw_cuda_image_t *conv_pic );
+/* End of stream (x264_encoder_encode with pic_in == NULL, codec.c:1755-1758,1848). */
+int x264vfw_cuda_la_flush( x264vfw_cuda_la *la );
+
+typedef struct x264vfw_cuda_la_decision
+{
+    int i_frame;        /* display index                                                        */
+    int i_type;         /* X264VFW_CUDA_TYPE_IDR/I/P/BREF/B -> x264_picture_t.i_type            */
+    int b_keyframe;     /* -> pic_out.b_keyframe (codec.c:1824)                                 */
+    int i_bframes;      /* on the non-B of a mini-GOP: number of B-frames before it             */
+    int i_cost_est;     /* [x264] i_cost_est of the chosen (p0,p1,b); -1 when not computed      */
+    int i_cost_est_aq;
+    int i_intra_mbs;
+    int mb_count;
+} x264vfw_cuda_la_decision;
+
+/* Pops the next decided frame in CODED order.  qp_offset / qp_offset_aq (may be NULL) receive
+ * mb_count floats each: x264_frame_t.f_qp_offset (mb-tree) and .f_qp_offset_aq, the values
+ * x264_picture_t.prop.quant_offsets is built from.  Returns 1, 0 when empty, -1 on error. */
+int x264vfw_cuda_la_get_decision( x264vfw_cuda_la *la, x264vfw_cuda_la_decision *d,
+                                  float *qp_offset, float *qp_offset_aq );
+
+/* ---- B3-shaped white-box entry points (parity tests; frames addressed by display index) --
+ * [x264] slicetype_frame_cost( frames, p0, p1, b ): returns the score, -1 on error. */
+int x264vfw_cuda_la_frame_cost( x264vfw_cuda_la *la, int p0, int p1, int b );
+/* [x264] macroblock_tree over explicit frames/types (frame_idx[0..num_frames]). */
+int x264vfw_cuda_la_mbtree( x264vfw_cuda_la *la, const int *frame_idx, const int *types, int num_frames, int b_intra );
+#define X264VFW_CUDA_LA_LOWRES        1  /* 4 padded planes, uint8                               */
+#define X264VFW_CUDA_LA_INTRA_COST    2  /* uint16[mb]                                           */
+#define X264VFW_CUDA_LA_INV_QSCALE    3  /* uint16[mb]                                           */
+#define X264VFW_CUDA_LA_PROPAGATE     4  /* int32[mb] (unsaturated shadow of i_propagate_cost)   */
+#define X264VFW_CUDA_LA_QP_OFFSET     5  /* float[mb]                                            */
+#define X264VFW_CUDA_LA_QP_OFFSET_AQ  6  /* float[mb]                                            */
+#define X264VFW_CUDA_LA_MVS           7  /* int16[mb][2]; a = list, b = distance (>= 1)          */
+#define X264VFW_CUDA_LA_MV_COSTS      8  /* int32[mb];    a = list, b = distance                 */
+#define X264VFW_CUDA_LA_LOWRES_COSTS  9  /* uint16[mb];   a = b-p0, b = p1-b                     */
+#define X264VFW_CUDA_LA_COST_EST      10 /* int32[3]: cost_est, cost_est_aq, intra_mbs; a,b as 9 */
+#define X264VFW_CUDA_LA_PIXEL_STATS   11 /* uint64[6]: sum[3], ssd[3] (after mean removal)       */
+#define X264VFW_CUDA_LA_WEIGHT        12 /* int32[4]: scale, denom, offset, enabled              */
+#define X264VFW_CUDA_LA_CONV_PLANES   13 /* converted planes of the LAST put frame (tight)       */
+/* Copies the selected array of frame `frame` into dst (capacity dst_bytes).  Returns the
+ * number of bytes written or -1. */
+int64_t x264vfw_cuda_la_read( x264vfw_cuda_la *la, int frame, int what, int a, int b, void *dst, size_t dst_bytes );
+/* [0] slicetype_frame_cost evaluations launched, [1] MB searches (MBs x lists), [2] kernel
+ * launches, [3] host<->device synchronisations */
+void x264vfw_cuda_la_counters( x264vfw_cuda_la *la, uint64_t out[4] );
+
 const char *x264vfw_cuda_last_error( void );
 /* "x264vfw_cuda <version> sm_100a"; also proves the library loaded. */
 const char *x264vfw_cuda_version( void );

@@ -175,3 +175,163 @@ def oracle_luma_pad(y: np.ndarray, w, h):
     o.orc_luma_pad.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
     o.orc_luma_pad(out.ctypes.data, g["luma_stride"], y.ctypes.data, w, w, h)
     return out
+
+
+# ---- stage 2: lookahead oracle -------------------------------------------------------------
+class LaParams(C.Structure):
+    """orc_la_params / x264vfw_cuda_la_params (same field order)."""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("chroma_format", C.c_int), ("bframes", C.c_int),
+                ("b_adapt", C.c_int), ("b_pyramid", C.c_int), ("b_bias", C.c_int), ("rc_lookahead", C.c_int),
+                ("b_mbtree", C.c_int), ("scenecut", C.c_int), ("keyint_max", C.c_int), ("keyint_min", C.c_int),
+                ("open_gop", C.c_int), ("weightp", C.c_int), ("weightb", C.c_int), ("subme", C.c_int),
+                ("me_method", C.c_int), ("me_range", C.c_int), ("mv_range", C.c_int), ("aq_mode", C.c_int),
+                ("aq_strength", C.c_float), ("qcompress", C.c_float), ("frame_reference", C.c_int),
+                ("lookahead_threads", C.c_int), ("fps_num", C.c_int), ("fps_den", C.c_int), ("b_psy", C.c_int)]
+
+
+class LaDecision(C.Structure):
+    _fields_ = [("i_frame", C.c_int), ("i_type", C.c_int), ("b_keyframe", C.c_int), ("i_bframes", C.c_int),
+                ("i_cost_est", C.c_int), ("i_cost_est_aq", C.c_int), ("i_intra_mbs", C.c_int), ("mb_count", C.c_int)]
+
+
+TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "BREF", 5: "B", 6: "KEY"}
+
+
+def la_params(preset, w, h, **over):
+    o = oracle()
+    p = LaParams()
+    o.orc_la_params_preset.argtypes = [C.POINTER(LaParams), C.c_char_p, C.c_int, C.c_int]
+    o.orc_la_params_preset(C.byref(p), preset.encode(), w, h)
+    for k, v in over.items():
+        assert hasattr(p, k), k
+        setattr(p, k, v)
+    return p
+
+
+class OracleLookahead:
+    def __init__(self, params: LaParams):
+        o = self.o = oracle()
+        P = C.POINTER
+        o.orc_la_open.restype = C.c_void_p
+        o.orc_la_open.argtypes = [P(LaParams)]
+        o.orc_la_close.argtypes = [C.c_void_p]
+        o.orc_la_put_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        o.orc_la_flush.argtypes = [C.c_void_p]
+        o.orc_la_get_decision.argtypes = [C.c_void_p, P(LaDecision), C.c_void_p, C.c_void_p]
+        o.orc_la_frame_cost.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        o.orc_la_mb_count.argtypes = [C.c_void_p]
+        for name, res in (("orc_la_lowres_planes", C.c_void_p), ("orc_la_intra_cost", C.c_void_p),
+                          ("orc_la_inv_qscale", C.c_void_p), ("orc_la_propagate_cost", C.c_void_p)):
+            getattr(o, name).restype = res
+            getattr(o, name).argtypes = [C.c_void_p, C.c_int]
+        o.orc_la_qp_offset.restype = C.c_void_p
+        o.orc_la_qp_offset.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        o.orc_la_mvs.restype = C.c_void_p
+        o.orc_la_mvs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        o.orc_la_mv_costs.restype = C.c_void_p
+        o.orc_la_mv_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        o.orc_la_lowres_costs.restype = C.c_void_p
+        o.orc_la_lowres_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        o.orc_la_cost_est.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        o.orc_la_intra_mbs.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        o.orc_la_pixel_stats.argtypes = [C.c_void_p, C.c_int, P(C.c_uint64), P(C.c_uint64)]
+        o.orc_la_weight.argtypes = [C.c_void_p, C.c_int, P(C.c_int)]
+        o.orc_la_mbtree.argtypes = [C.c_void_p, P(C.c_int), P(C.c_int), C.c_int, C.c_int]
+        o.orc_la_counters.argtypes = [C.c_void_p, P(C.c_uint64)]
+        self.p = params
+        self.h = o.orc_la_open(C.byref(params))
+        self.mb_count = o.orc_la_mb_count(self.h)
+        self.g = lowres_geometry(params.width, params.height)
+
+    def close(self):
+        if self.h:
+            self.o.orc_la_close(self.h)
+            self.h = None
+
+    def put_i420(self, buf: np.ndarray):
+        """buf: tight planar frame in the encoder csp (I420 / I422 / I444 by chroma_format)."""
+        w, h = self.p.width, self.p.height
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        cf = self.p.chroma_format
+        cw = w if cf == 3 else w // 2
+        chh = h // 2 if cf == 1 else h
+        base = buf.ctypes.data
+        self._keep = buf
+        return self.o.orc_la_put_frame(self.h, base, w, base + w * h, base + w * h + cw * chh, cw)
+
+    def put_luma(self, y: np.ndarray):
+        y = np.ascontiguousarray(y, dtype=np.uint8)
+        return self.o.orc_la_put_frame(self.h, y.ctypes.data, self.p.width, None, None, 0)
+
+    def flush(self):
+        return self.o.orc_la_flush(self.h)
+
+    def decisions(self):
+        out = []
+        d = LaDecision()
+        while True:
+            q = np.zeros(self.mb_count, dtype=np.float32)
+            qa = np.zeros(self.mb_count, dtype=np.float32)
+            if not self.o.orc_la_get_decision(self.h, C.byref(d), q.ctypes.data, qa.ctypes.data):
+                break
+            out.append(dict(i_frame=d.i_frame, i_type=d.i_type, b_keyframe=d.b_keyframe, i_bframes=d.i_bframes,
+                            i_cost_est=d.i_cost_est, i_cost_est_aq=d.i_cost_est_aq, i_intra_mbs=d.i_intra_mbs,
+                            qp_offset=q, qp_offset_aq=qa))
+        return out
+
+    def frame_cost(self, p0, p1, b):
+        return self.o.orc_la_frame_cost(self.h, p0, p1, b)
+
+    def _arr(self, ptr, n, dtype):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dtype).itemsize,)).view(dtype).copy()
+
+    def lowres_planes(self, f):
+        return self._arr(self.o.orc_la_lowres_planes(self.h, f), 4 * self.g["lplane_bytes"], np.uint8)
+
+    def intra_cost(self, f):
+        return self._arr(self.o.orc_la_intra_cost(self.h, f), self.mb_count, np.uint16)
+
+    def inv_qscale(self, f):
+        return self._arr(self.o.orc_la_inv_qscale(self.h, f), self.mb_count, np.uint16)
+
+    def propagate_cost(self, f):
+        return self._arr(self.o.orc_la_propagate_cost(self.h, f), self.mb_count, np.uint16)
+
+    def qp_offset(self, f, aq=False):
+        return self._arr(self.o.orc_la_qp_offset(self.h, f, int(aq)), self.mb_count, np.float32)
+
+    def mvs(self, f, lst, dist):
+        return self._arr(self.o.orc_la_mvs(self.h, f, lst, dist), 2 * self.mb_count, np.int16).reshape(-1, 2)
+
+    def mv_costs(self, f, lst, dist):
+        return self._arr(self.o.orc_la_mv_costs(self.h, f, lst, dist), self.mb_count, np.int32)
+
+    def lowres_costs(self, f, d0, d1):
+        return self._arr(self.o.orc_la_lowres_costs(self.h, f, d0, d1), self.mb_count, np.uint16)
+
+    def cost_est(self, f, d0, d1, aq=False):
+        return self.o.orc_la_cost_est(self.h, f, d0, d1, int(aq))
+
+    def intra_mbs(self, f, d0):
+        return self.o.orc_la_intra_mbs(self.h, f, d0)
+
+    def pixel_stats(self, f):
+        s, q = (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
+        self.o.orc_la_pixel_stats(self.h, f, s, q)
+        return list(s), list(q)
+
+    def weight(self, f):
+        w = (C.c_int * 4)()
+        self.o.orc_la_weight(self.h, f, w)
+        return dict(scale=w[0], denom=w[1], offset=w[2], on=w[3])
+
+    def mbtree(self, frame_idx, types, b_intra=0):
+        n = len(frame_idx) - 1
+        fi = (C.c_int * (n + 1))(*frame_idx)
+        ty = (C.c_int * (n + 1))(*types)
+        self.o.orc_la_mbtree(self.h, fi, ty, n, b_intra)
+
+    def counters(self):
+        c = (C.c_uint64 * 4)()
+        self.o.orc_la_counters(self.h, c)
+        return dict(mb_cost=c[0], searches=c[1], sad=c[2], satd=c[3])

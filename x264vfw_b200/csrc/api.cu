@@ -146,6 +146,13 @@ static int convert_device(cudaStream_t st, int out_csp, int colmatrix, int fullr
     return launch_planes(st, pj, vec, n_frames);
 }
 
+int convert_device_public(cudaStream_t st, int out_csp, int colmatrix, int fullrange, int ext,
+                          const x264vfw_cuda_image_t *dst, const x264vfw_cuda_image_t *src,
+                          int w, int h, size_t sfb, size_t dfb, int n_frames)
+{
+    return convert_device(st, out_csp, colmatrix, fullrange, ext, dst, src, w, h, sfb, dfb, n_frames);
+}
+
 static int ensure(uint8_t **p, size_t *cap, size_t need, bool pinned)
 {
     if (*cap >= need) return 0;

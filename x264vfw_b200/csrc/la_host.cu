@@ -1,0 +1,1192 @@
+// Lookahead session: host-side control flow around the GPU cost engine.
+//
+// The frame-type decision logic of [x264] encoder/slicetype.c (x264_slicetype_decide,
+// x264_slicetype_analyse, scenecut, slicetype_path(_cost), macroblock_tree) and the queueing
+// of [x264] encoder/lookahead.c are scalar, branchy and tiny, so they stay on the host -- but
+// every slicetype_frame_cost(p0,p1,b) they ask for is a handful of kernel launches on this
+// session's stream.  Results are memoised per frame exactly like upstream (MVs per
+// (list,distance), costs per (b-p0,p1-b)), and the evaluation ORDER is kept identical because
+// it is observable (weights are analysed only on the first P evaluation of a pair; the bidir
+// direct-MV seed exists only once the P search of the later reference has run).
+//
+// Only values the host must branch on force a stream synchronisation (scenecut tests, path
+// cost comparisons, weight scores).  The mb-tree walk and the rate-control precompute only
+// enqueue work; their scalar results are collected at the next synchronisation.
+#include "common.cuh"
+#include "csp_kernels.h"
+#include "la_kernels.h"
+#include "../../include/x264vfw_cuda.h"
+#include <math.h>
+#include <string.h>
+#include <stdlib.h>
+#include <deque>
+#include <vector>
+
+namespace xv {
+
+int convert_device_public(cudaStream_t st, int out_csp, int colmatrix, int fullrange, int ext,
+                          const x264vfw_cuda_image_t *dst, const x264vfw_cuda_image_t *src,
+                          int w, int h, size_t sfb, size_t dfb, int n_frames);
+
+#define BMAX X264VFW_CUDA_BFRAME_MAX
+#define LMAX X264VFW_CUDA_LOOKAHEAD_MAX
+#define T_AUTO X264VFW_CUDA_TYPE_AUTO
+#define T_IDR X264VFW_CUDA_TYPE_IDR
+#define T_I X264VFW_CUDA_TYPE_I
+#define T_P X264VFW_CUDA_TYPE_P
+#define T_BREF X264VFW_CUDA_TYPE_BREF
+#define T_B X264VFW_CUDA_TYPE_B
+#define T_KEYFRAME 6
+#define IS_B(t) ((t) == T_B || (t) == T_BREF)
+#define IS_I(t) ((t) == T_I || (t) == T_IDR || (t) == T_KEYFRAME)
+#define AUTO_OR_I(t) ((t) == T_AUTO || IS_I(t))
+#define AUTO_OR_B(t) ((t) == T_AUTO || IS_B(t))
+#define COST_MAX64 (1ULL << 60)
+#define PENDING (-2)
+
+struct Frame {
+    // host mirror of the x264_frame_t fields the decision logic reads
+    int i_frame = 0, i_type = T_AUTO, i_forced_type = T_AUTO, b_scenecut = 1, b_keyframe = 0, i_bframes = 0;
+    float f_duration = 0;
+    int cost_est[BMAX + 2][BMAX + 2], cost_est_aq[BMAX + 2][BMAX + 2], intra_mbs[BMAX + 2];
+    bool searched[2][BMAX + 1];
+    bool b_intra_calculated = false;
+    bool stats_ready = false;
+    unsigned long long pixel_sum[3], pixel_ssd[3];
+    WeightDev weight = {0, 1, 0, 0};
+    float weighted_cost_delta[BMAX + 2];
+    int rc_d0 = -1, rc_d1 = -1;
+    bool in_use = false;
+    // device side
+    uint8_t *lowres = nullptr;                 // 4 padded planes (+ slack)
+    uint16_t *intra_cost = nullptr, *inv_qscale = nullptr;
+    int *propagate = nullptr;
+    float *qp_offset = nullptr, *qp_offset_aq = nullptr;
+    int *mvs[2][BMAX + 1], *mv_costs[2][BMAX + 1];
+    uint16_t *lowres_costs = nullptr;          // [(B+2)*(B+2)][mb]
+    unsigned long long *stats = nullptr;       // device [6]
+    unsigned long long *h_stats = nullptr;     // pinned [6]
+    uint8_t *arena = nullptr;
+};
+
+struct PendingResult { Frame *f; int d0, d1; int slot; bool is_b; bool intra; };
+
+struct Decision {
+    x264vfw_cuda_la_decision d;
+    Frame *f;
+    float *h_qp, *h_qp_aq;                     // pinned staging, valid after the decide's sync
+};
+
+struct La {
+    x264vfw_cuda_la_params p;
+    LaGeom g;
+    int device;
+    cudaStream_t st;
+    int in_csp, out_csp, colmatrix, fullrange, keep_frames;
+    int la_me_hex, la_subpel_refine, la_satd, do_edges;
+    int slicetype_length, i_last_keyframe;
+    // tables
+    uint16_t *d_cost_mv = nullptr; int cost_mv_half = 0;
+    float *d_log2_lut = nullptr; uint8_t *d_exp2_lut = nullptr;
+    // scratch
+    uint8_t *d_src = nullptr; size_t d_src_bytes = 0;      // packed input staging
+    uint8_t *d_planes = nullptr; size_t d_planes_bytes = 0; // converted planes (tight)
+    x264vfw_cuda_image_t planes_img;
+    uint8_t *d_weight_buf = nullptr;
+    int *d_sync = nullptr;                                  // 2 x (1 + mb_h)
+    int *d_results = nullptr; int *h_results = nullptr;     // ring of 4-int slots
+    int result_head = 0;
+    unsigned *d_wscore = nullptr; unsigned *h_wscore = nullptr;
+    std::vector<PendingResult> pending;
+    // frames
+    std::vector<Frame *> all;            // by display index when keep_frames, else pool
+    std::vector<Frame *> pool;
+    std::vector<Frame *> by_index;       // display index -> frame (null when recycled)
+    std::deque<Frame *> next;
+    Frame *last_nonb = nullptr;
+    std::deque<Decision> outq;
+    std::vector<float *> qp_free;
+    int n_input = 0;
+    uint64_t n_frame_cost = 0, n_mb_search = 0, n_launch = 0, n_sync = 0;
+    bool fail = false;   // set when a device call fails inside the value-returning helpers
+};
+
+static const int RESULT_SLOTS = 1024;
+
+#define LA_CUDA(expr) XV_CUDA_OK(expr)
+
+static int la_sync(La *la);
+
+// ------------------------------------------------------------------------------------------
+// frame slots
+// ------------------------------------------------------------------------------------------
+static Frame *frame_alloc(La *la)
+{
+    Frame *f = new Frame();
+    const int n = la->g.mb_count, B = la->p.bframes;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_lowres = take((size_t)4 * la->g.lplane + 64);
+    const size_t o_intra = take(n * 2), o_invq = take(n * 2), o_prop = take(n * 4), o_qp = take(n * 4), o_qpaq = take(n * 4);
+    size_t o_mvs[2][BMAX + 1], o_mvc[2][BMAX + 1];
+    for (int l = 0; l < 2; l++) for (int d = 0; d <= B; d++) { o_mvs[l][d] = take(n * 4); o_mvc[l][d] = take(n * 4); }
+    const size_t o_lc = take((size_t)(B + 2) * (B + 2) * n * 2);
+    const size_t o_stats = take(64);
+    if (cudaMalloc((void **)&f->arena, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed for a lookahead frame", off); delete f; return nullptr; }
+    if (cudaMallocHost((void **)&f->h_stats, 64) != cudaSuccess) { set_error("cudaMallocHost failed"); cudaFree(f->arena); delete f; return nullptr; }
+    f->lowres = f->arena + o_lowres;
+    f->intra_cost = (uint16_t *)(f->arena + o_intra); f->inv_qscale = (uint16_t *)(f->arena + o_invq);
+    f->propagate = (int *)(f->arena + o_prop);
+    f->qp_offset = (float *)(f->arena + o_qp); f->qp_offset_aq = (float *)(f->arena + o_qpaq);
+    for (int l = 0; l < 2; l++) for (int d = 0; d <= B; d++) { f->mvs[l][d] = (int *)(f->arena + o_mvs[l][d]); f->mv_costs[l][d] = (int *)(f->arena + o_mvc[l][d]); }
+    f->lowres_costs = (uint16_t *)(f->arena + o_lc);
+    f->stats = (unsigned long long *)(f->arena + o_stats);
+    return f;
+}
+
+static void frame_free(Frame *f)
+{
+    if (!f) return;
+    cudaFree(f->arena);
+    cudaFreeHost(f->h_stats);
+    delete f;
+}
+
+static int frame_reset(La *la, Frame *f, int i_frame)
+{
+    const int n = la->g.mb_count, B = la->p.bframes;
+    f->i_frame = i_frame; f->i_type = f->i_forced_type = T_AUTO; f->b_scenecut = 1; f->b_keyframe = 0; f->i_bframes = 0;
+    f->f_duration = 0;
+    for (int a = 0; a < BMAX + 2; a++) { f->intra_mbs[a] = 0; f->weighted_cost_delta[a] = 0; for (int b = 0; b < BMAX + 2; b++) f->cost_est[a][b] = f->cost_est_aq[a][b] = -1; }
+    memset(f->searched, 0, sizeof(f->searched));
+    f->b_intra_calculated = false; f->stats_ready = false;
+    f->weight = WeightDev{0, 1, 0, 0};
+    f->rc_d0 = f->rc_d1 = -1;
+    f->in_use = true;
+    // zero the memo arrays the kernels may read before writing (MV predictors of unscanned
+    // MBs, intra cost of unscanned edge MBs), and the stats accumulators
+    const size_t zero_from = (uint8_t *)f->intra_cost - f->arena;
+    const size_t zero_to = ((uint8_t *)f->stats - f->arena) + 64;
+    (void)n; (void)B;
+    LA_CUDA(cudaMemsetAsync(f->arena + zero_from, 0, zero_to - zero_from, la->st));
+    return 0;
+}
+
+static Frame *frame_get(La *la, int i_frame)
+{
+    Frame *f = nullptr;
+    if (!la->keep_frames) {
+        for (Frame *c : la->pool) if (!c->in_use) { f = c; break; }
+    }
+    if (!f) {
+        f = frame_alloc(la);
+        if (!f) return nullptr;
+        la->pool.push_back(f);
+    }
+    if (frame_reset(la, f, i_frame) < 0) return nullptr;
+    if ((int)la->by_index.size() <= i_frame) la->by_index.resize(i_frame + 1, nullptr);
+    la->by_index[i_frame] = f;
+    return f;
+}
+
+static void frame_release(La *la, Frame *f)
+{
+    if (la->keep_frames || !f) return;
+    f->in_use = false;
+    if (f->i_frame < (int)la->by_index.size() && la->by_index[f->i_frame] == f) la->by_index[f->i_frame] = nullptr;
+}
+
+static inline const uint8_t *plane_org(const La *la, const Frame *f, int k) { return f->lowres + (size_t)k * la->g.lplane + la->g.lorigin; }
+static inline uint16_t *lc_ptr(const La *la, const Frame *f, int d0, int d1) { return f->lowres_costs + ((size_t)d0 * (la->p.bframes + 2) + d1) * la->g.mb_count; }
+
+// ------------------------------------------------------------------------------------------
+// results ring + synchronisation
+// ------------------------------------------------------------------------------------------
+static int result_slot(La *la)
+{
+    if ((int)la->pending.size() >= RESULT_SLOTS - 2) { if (la_sync(la) < 0) return -1; }
+    int s = la->result_head;
+    la->result_head = (la->result_head + 1) % RESULT_SLOTS;
+    return s;
+}
+
+static int la_sync(La *la)
+{
+    if (!la->pending.empty())
+        LA_CUDA(cudaMemcpyAsync(la->h_results, la->d_results, RESULT_SLOTS * 4 * sizeof(int), cudaMemcpyDeviceToHost, la->st));
+    LA_CUDA(cudaStreamSynchronize(la->st));
+    la->n_sync++;
+    for (const PendingResult &r : la->pending) {
+        const int *v = la->h_results + r.slot * 4;
+        Frame *f = r.f;
+        if (r.intra) {
+            f->cost_est[0][0] = v[0]; f->cost_est_aq[0][0] = v[1];
+        } else {
+            int score = v[0];
+            if (r.is_b) score = (int)((uint64_t)score * 100 / (120 + la->p.b_bias));   // [x264] slicetype_frame_cost
+            else f->intra_mbs[r.d0] = v[2];
+            f->cost_est[r.d0][r.d1] = score;
+            f->cost_est_aq[r.d0][r.d1] = v[1];
+        }
+    }
+    la->pending.clear();
+    return 0;
+}
+
+static int ensure_stats(La *la, Frame *f)
+{
+    if (f->stats_ready) return 0;
+    if (la_sync(la) < 0) return -1;     // the AQ kernel + async copy of this frame were enqueued at put time
+    // [x264] x264_adaptive_quant_frame: "Remove mean from SSD calculation"
+    const int cf = la->p.chroma_format;
+    for (int i = 0; i < 3; i++) {
+        unsigned long long sum = f->h_stats[i], ssd = f->h_stats[3 + i];
+        unsigned long long pw = (16 * la->g.mb_w) >> (i && cf != 3), ph = (16 * la->g.mb_h) >> (i && cf == 1);
+        f->pixel_sum[i] = sum;
+        f->pixel_ssd[i] = ssd - (sum * sum + pw * ph / 2) / (pw * ph);
+    }
+    f->stats_ready = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// [x264] slicetype_frame_cost
+// ------------------------------------------------------------------------------------------
+static int launch_intra_for(La *la, Frame *fenc)
+{
+    IntraJob ij;
+    ij.plane0 = plane_org(la, fenc, 0); ij.intra_cost = fenc->intra_cost; ij.full = la->p.subme > 1; ij.satd = la->la_satd;
+    if (launch_intra(la->st, la->g, ij, la->do_edges) < 0) return -1;
+    const int slot = result_slot(la);
+    if (slot < 0) return -1;
+    LA_CUDA(cudaMemsetAsync(la->d_results + slot * 4, 0, 4 * sizeof(int), la->st));
+    IntraSumJob sj;
+    sj.intra_cost = fenc->intra_cost; sj.inv_qscale = fenc->inv_qscale; sj.aq_on = la->p.aq_mode != 0;
+    sj.result = la->d_results + slot * 4; sj.row_satd = nullptr;
+    if (launch_intra_sum(la->st, la->g, sj) < 0) return -1;
+    la->n_launch += 2;
+    la->pending.push_back(PendingResult{fenc, 0, 0, slot, false, true});
+    fenc->cost_est[0][0] = PENDING; fenc->cost_est_aq[0][0] = PENDING;
+    fenc->b_intra_calculated = true;
+    return 0;
+}
+
+static int ue_size(unsigned v) { v += 1; int n = 0; while (v >> (n + 1)) n++; return 2 * n + 1; }
+static int se_size(int v) { int t = 1 - v * 2; if (t < 0) t = v * 2; int n = 0; while (t >> (n + 1)) n++; return 2 * n + 1; }
+
+static int weight_score(La *la, Frame *fenc, Frame *ref, const WeightDev &w, unsigned *score)
+{
+    LA_CUDA(cudaMemsetAsync(la->d_wscore, 0, sizeof(unsigned), la->st));
+    WeightCostJob j;
+    j.fenc = plane_org(la, fenc, 0); j.ref = plane_org(la, ref, 0); j.intra_cost = fenc->intra_cost;
+    j.w = w; j.satd = la->la_satd; j.result = la->d_wscore;
+    if (launch_weight_cost(la->st, la->g, j) < 0) return -1;
+    la->n_launch++;
+    LA_CUDA(cudaMemcpyAsync(la->h_wscore, la->d_wscore, sizeof(unsigned), cudaMemcpyDeviceToHost, la->st));
+    if (la_sync(la) < 0) return -1;
+    unsigned s = *la->h_wscore;
+    if (w.on) s += 1 * 1 * (10 + ue_size(w.denom) * 2 + 2 * (se_size(w.scale) + se_size(w.offset)));   // weight_slice_header_cost
+    *score = s;
+    return 0;
+}
+
+// [x264] x264_weights_analyse( h, fenc, ref, b_lookahead = 1 ): luma only, one candidate
+static int weights_analyse(La *la, Frame *fenc, Frame *ref)
+{
+    const float epsilon = 1.f / 128.f;
+    fenc->weight = WeightDev{0, 1, 0, 0};
+    if (ensure_stats(la, fenc) < 0 || ensure_stats(la, ref) < 0) return -1;
+    const int zero_bias = !ref->pixel_ssd[0];
+    const float fenc_var = fenc->pixel_ssd[0] + zero_bias;
+    const float ref_var = ref->pixel_ssd[0] + zero_bias;
+    const float guess_scale = sqrtf(fenc_var / ref_var);
+    const float fenc_mean = (float)(fenc->pixel_sum[0] + zero_bias) / (la->g.luma_h * la->g.luma_w) / 1;
+    const float ref_mean = (float)(ref->pixel_sum[0] + zero_bias) / (la->g.luma_h * la->g.luma_w) / 1;
+    if (fabsf(ref_mean - fenc_mean) < 0.5f && fabsf(1.f - guess_scale) < epsilon) return 0;
+
+    int scale = (int)round(guess_scale * 128), denom = 7;        // x264_weight_get_h264
+    while (denom > 0 && scale > 127) { denom--; scale >>= 1; }
+    if (scale > 127) scale = 127;
+    int found = 0, mindenom = denom, minscale = scale, minoff = 0;
+
+    if (!fenc->b_intra_calculated && launch_intra_for(la, fenc) < 0) return -1;
+    unsigned origscore, minscore;
+    if (weight_score(la, fenc, ref, WeightDev{0, 1, 0, 0}, &origscore) < 0) return -1;
+    minscore = origscore;
+    if (!minscore) return 0;
+    {
+        int cur_scale = minscale;
+        int cur_offset = (int)(fenc_mean - ref_mean * cur_scale / (1 << mindenom) + 0.5f * 1);
+        if (cur_offset < -128 || cur_offset > 127) {
+            cur_offset = cur_offset < -128 ? -128 : 127;
+            float cs = (1 << mindenom) * (fenc_mean - cur_offset) / ref_mean + 0.5f;
+            cur_scale = (int)(cs < 0 ? 0 : cs > 127 ? 127 : cs);
+        }
+        const int i_off = cur_offset < -128 ? -128 : cur_offset > 127 ? 127 : cur_offset;
+        unsigned s;
+        if (weight_score(la, fenc, ref, WeightDev{1, cur_scale, mindenom, i_off}, &s) < 0) return -1;
+        if (s < minscore) { minscore = s; minscale = cur_scale; minoff = i_off; found = 1; }
+    }
+    while (mindenom > 0 && !(minscale & 1)) { mindenom--; minscale >>= 1; }
+    if (!found || (minscale == 1 << mindenom && minoff == 0) || (float)minscore / origscore > 0.998f) return 0;
+    fenc->weight = WeightDev{1, minscale, mindenom, minoff};
+    // x264_weight_scale_plane: the whole padded plane 0 of the reference
+    if (launch_weight_plane(la->st, la->g, la->d_weight_buf, ref->lowres, fenc->weight) < 0) return -1;
+    la->n_launch++;
+    return 0;
+}
+
+// Enqueues everything slicetype_frame_cost(p0,p1,b) computes.  need_value: synchronise and
+// return the score; otherwise return 0 and leave the result pending.
+static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_value)
+{
+    Frame *fenc = frames[b];
+    const int d0 = b - p0, d1 = p1 - b;
+    if (fenc->cost_est[d0][d1] >= 0) return fenc->cost_est[d0][d1];
+    if (fenc->cost_est[d0][d1] == PENDING) {
+        if (!need_value) return 0;
+        if (la_sync(la) < 0) return -1;
+        return fenc->cost_est[d0][d1];
+    }
+    la->n_frame_cost++;
+    if (p0 == p1) {
+        // intra only
+        if (!fenc->b_intra_calculated) { if (launch_intra_for(la, fenc) < 0) return -1; }
+        else { fenc->cost_est[0][0] = 0; fenc->cost_est_aq[0][0] = 0; }      // unreachable through the memo
+        if (!need_value) return 0;
+        if (la_sync(la) < 0) return -1;
+        return fenc->cost_est[0][0];
+    }
+    Frame *fref0 = frames[p0], *fref1 = frames[p1];
+    bool do_search[2];
+    WeightDev w = {0, 1, 0, 0};
+    do_search[0] = b != p0 && !fenc->searched[0][d0 - 1];
+    do_search[1] = b != p1 && !fenc->searched[1][d1 - 1];
+    if (do_search[0]) {
+        if (la->p.weightp && b == p1) {
+            if (weights_analyse(la, fenc, fref0) < 0) return -1;
+            w = fenc->weight;
+        }
+        fenc->searched[0][d0 - 1] = true;
+    }
+    if (do_search[1]) fenc->searched[1][d1 - 1] = true;
+    const int dist_scale_factor = (((b - p0) << 8) + ((p1 - p0) >> 1)) / (p1 - p0);
+
+    if (!fenc->b_intra_calculated && launch_intra_for(la, fenc) < 0) return -1;
+
+    // ---- searches (wavefront kernel; both lists of a B evaluation share the launch) ----
+    MeParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.bands = la->p.lookahead_threads > 0 ? la->p.lookahead_threads : 1;
+    mp.do_edges = la->do_edges; mp.mv_range2 = 2 * la->p.mv_range; mp.me_hex = la->la_me_hex;
+    mp.subpel_refine = la->la_subpel_refine; mp.satd = la->la_satd; mp.me_range = la->p.me_range;
+    mp.cost_mv = la->d_cost_mv + la->cost_mv_half;
+    for (int l = 0; l < 2; l++) {
+        if (!do_search[l]) continue;
+        MeJob &j = mp.job[mp.njobs];
+        Frame *ref = l ? fref1 : fref0;
+        j.fenc = plane_org(la, fenc, 0);
+        for (int k = 0; k < 4; k++) j.fref[k] = plane_org(la, ref, k);
+        j.fref_w = j.fref[0];
+        j.w = WeightDev{0, 1, 0, 0};
+        if (l == 0 && w.on) { j.w = w; j.fref_w = la->d_weight_buf + la->g.lorigin; }
+        j.mvs = l ? fenc->mvs[1][d1 - 1] : fenc->mvs[0][d0 - 1];
+        j.mv_costs = l ? fenc->mv_costs[1][d1 - 1] : fenc->mv_costs[0][d0 - 1];
+        j.sync = la->d_sync + mp.njobs * (1 + la->g.mb_h);
+        mp.njobs++;
+        la->n_mb_search += la->g.mb_count;
+    }
+    if (mp.njobs) {
+        const size_t words = (size_t)mp.njobs * (1 + la->g.mb_h);
+        LA_CUDA(cudaMemsetAsync(la->d_sync, 0x7f, words * sizeof(int), la->st));
+        for (int k = 0; k < mp.njobs; k++) LA_CUDA(cudaMemsetAsync(la->d_sync + k * (1 + la->g.mb_h), 0, sizeof(int), la->st));
+        if (launch_me(la->st, la->g, mp) < 0) return -1;
+        la->n_launch++;
+    }
+
+    // ---- per-MB selection + accumulators ----
+    const int slot = result_slot(la);
+    if (slot < 0) return -1;
+    LA_CUDA(cudaMemsetAsync(la->d_results + slot * 4, 0, 4 * sizeof(int), la->st));
+    FinalizeJob fj;
+    memset(&fj, 0, sizeof(fj));
+    fj.fenc = plane_org(la, fenc, 0);
+    for (int k = 0; k < 4; k++) { fj.fref0[k] = plane_org(la, fref0, k); fj.fref1[k] = plane_org(la, fref1, k); }
+    fj.mvs0 = b != p0 ? fenc->mvs[0][d0 - 1] : nullptr; fj.mv_costs0 = b != p0 ? fenc->mv_costs[0][d0 - 1] : nullptr;
+    fj.mvs1 = b != p1 ? fenc->mvs[1][d1 - 1] : nullptr; fj.mv_costs1 = b != p1 ? fenc->mv_costs[1][d1 - 1] : nullptr;
+    fj.ref1_mvs = (b < p1 && fref1->searched[0][p1 - p0 - 1]) ? fref1->mvs[0][p1 - p0 - 1] : nullptr;
+    fj.intra_cost = fenc->intra_cost; fj.inv_qscale = fenc->inv_qscale;
+    fj.lowres_costs = lc_ptr(la, fenc, d0, d1);
+    fj.row_satd = nullptr; fj.result = la->d_results + slot * 4;
+    fj.b_bidir = b < p1; fj.b_p = b == p1;
+    fj.dist_scale_factor = dist_scale_factor;
+    fj.bipred_weight = la->p.weightb ? 64 - (dist_scale_factor >> 2) : 32;
+    fj.aq_on = la->p.aq_mode != 0; fj.subme_gt1 = la->p.subme > 1; fj.satd = la->la_satd;
+    fj.mv_range2 = 2 * la->p.mv_range; fj.do_edges = la->do_edges;
+    if (launch_finalize(la->st, la->g, fj) < 0) return -1;
+    la->n_launch++;
+    la->pending.push_back(PendingResult{fenc, d0, d1, slot, b != p1, false});
+    fenc->cost_est[d0][d1] = PENDING; fenc->cost_est_aq[d0][d1] = PENDING;
+    if (!need_value) return 0;
+    if (la_sync(la) < 0) return -1;
+    return fenc->cost_est[d0][d1];
+}
+
+// ------------------------------------------------------------------------------------------
+// [x264] macroblock_tree / macroblock_tree_propagate / macroblock_tree_finish
+// ------------------------------------------------------------------------------------------
+static inline float clip_duration(float f) { return f < 0.01f ? 0.01f : f > 1.00f ? 1.00f : f; }
+#define MBTREE_PRECISION 0.5f
+
+static int tree_finish(La *la, Frame *frame, float average_duration, int ref0_distance)
+{
+    TreeFinishJob j;
+    j.fps_factor = (int)round(clip_duration(average_duration) / clip_duration(frame->f_duration) * 256 / MBTREE_PRECISION);
+    float weightdelta = 0.0;
+    if (ref0_distance && frame->weighted_cost_delta[ref0_distance - 1] > 0)
+        weightdelta = (1.0 - frame->weighted_cost_delta[ref0_distance - 1]);
+    j.weightdelta = weightdelta;
+    j.strength = 5.0f * (1.0f - la->p.qcompress);
+    j.propagate = frame->propagate; j.intra_cost = frame->intra_cost; j.inv_qscale = frame->inv_qscale;
+    j.qp_offset_aq = frame->qp_offset_aq; j.qp_offset = frame->qp_offset; j.log2_lut = la->d_log2_lut;
+    la->n_launch++;
+    return launch_tree_finish(la->st, la->g, j);
+}
+
+static int tree_propagate(La *la, Frame **frames, float average_duration, int p0, int p1, int b, int referenced)
+{
+    PropagateJob j;
+    const int dist_scale_factor = (((b - p0) << 8) + ((p1 - p0) >> 1)) / (p1 - p0);
+    j.bipred_weight = la->p.weightb ? 64 - (dist_scale_factor >> 2) : 32;
+    j.fps_factor = clip_duration(frames[b]->f_duration) / (clip_duration(average_duration) * 256.0f) * MBTREE_PRECISION;
+    j.propagate_in = referenced ? frames[b]->propagate : nullptr;
+    j.intra_cost = frames[b]->intra_cost; j.inv_qscale = frames[b]->inv_qscale;
+    j.lowres_costs = lc_ptr(la, frames[b], b - p0, p1 - b);
+    j.mvs0 = b != p0 ? frames[b]->mvs[0][b - p0 - 1] : nullptr;
+    j.mvs1 = b != p1 ? frames[b]->mvs[1][p1 - b - 1] : nullptr;
+    j.ref0_cost = frames[p0]->propagate; j.ref1_cost = frames[p1]->propagate;
+    j.b_bidir = b != p1;
+    la->n_launch++;
+    return launch_propagate(la->st, la->g, j);
+}
+
+static int zero_propagate(La *la, Frame *f)
+{
+    LA_CUDA(cudaMemsetAsync(f->propagate, 0, la->g.mb_count * sizeof(int), la->st));
+    return 0;
+}
+
+static int macroblock_tree(La *la, Frame **frames, int num_frames, int b_intra)
+{
+    int idx = !b_intra;
+    int last_nonb, cur_nonb = 1, bframes = 0;
+    float total_duration = 0.0;
+    for (int j = 0; j <= num_frames; j++) total_duration += frames[j]->f_duration;
+    const float average_duration = total_duration / (num_frames + 1);
+    int i = num_frames;
+
+    if (b_intra && frame_cost(la, frames, 0, 0, 0, false) < 0) return -1;
+    while (i > 0 && IS_B(frames[i]->i_type)) i--;
+    last_nonb = i;
+    if (last_nonb < idx) return 0;
+    if (zero_propagate(la, frames[last_nonb]) < 0) return -1;
+
+    while (i-- > idx) {
+        cur_nonb = i;
+        while (IS_B(frames[cur_nonb]->i_type) && cur_nonb > 0) cur_nonb--;
+        if (cur_nonb < idx) break;
+        if (frame_cost(la, frames, cur_nonb, last_nonb, last_nonb, false) < 0) return -1;
+        if (zero_propagate(la, frames[cur_nonb]) < 0) return -1;
+        bframes = last_nonb - cur_nonb - 1;
+        if (la->p.b_pyramid && bframes > 1) {
+            const int middle = (bframes + 1) / 2 + cur_nonb;
+            if (frame_cost(la, frames, cur_nonb, last_nonb, middle, false) < 0) return -1;
+            if (zero_propagate(la, frames[middle]) < 0) return -1;
+            while (i > cur_nonb) {
+                const int p0 = i > middle ? middle : cur_nonb;
+                const int p1 = i < middle ? middle : last_nonb;
+                if (i != middle) {
+                    if (frame_cost(la, frames, p0, p1, i, false) < 0) return -1;
+                    if (tree_propagate(la, frames, average_duration, p0, p1, i, 0) < 0) return -1;
+                }
+                i--;
+            }
+            if (tree_propagate(la, frames, average_duration, cur_nonb, last_nonb, middle, 1) < 0) return -1;
+        } else {
+            while (i > cur_nonb) {
+                if (frame_cost(la, frames, cur_nonb, last_nonb, i, false) < 0) return -1;
+                if (tree_propagate(la, frames, average_duration, cur_nonb, last_nonb, i, 0) < 0) return -1;
+                i--;
+            }
+        }
+        if (tree_propagate(la, frames, average_duration, cur_nonb, last_nonb, last_nonb, 1) < 0) return -1;
+        last_nonb = cur_nonb;
+    }
+    if (tree_finish(la, frames[last_nonb], average_duration, last_nonb) < 0) return -1;
+    if (la->p.b_pyramid && bframes > 1)
+        if (tree_finish(la, frames[last_nonb + (bframes + 1) / 2], average_duration, 0) < 0) return -1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// [x264] slicetype_path_cost / slicetype_path / scenecut / x264_slicetype_analyse
+// ------------------------------------------------------------------------------------------
+
+static uint64_t path_cost(La *la, Frame **frames, const char *path, uint64_t threshold)
+{
+    uint64_t cost = 0;
+    int loc = 1, cur_nonb = 0;
+    path--;
+    auto fc = [&](int p0, int p1, int b) -> uint64_t { int v = frame_cost(la, frames, p0, p1, b, true); if (v < 0) { la->fail = true; return 0; } return (uint64_t)v; };
+    while (path[loc]) {
+        int next_nonb = loc;
+        while (path[next_nonb] == 'B') next_nonb++;
+        if (path[next_nonb] == 'P') cost += fc(cur_nonb, next_nonb, next_nonb);
+        else cost += fc(next_nonb, next_nonb, next_nonb);
+        if (cost > threshold) break;
+        if (la->p.b_pyramid && next_nonb - cur_nonb > 2) {
+            const int middle = cur_nonb + (next_nonb - cur_nonb) / 2;
+            cost += fc(cur_nonb, next_nonb, middle);
+            for (int next_b = loc; next_b < middle && cost < threshold; next_b++) cost += fc(cur_nonb, middle, next_b);
+            for (int next_b = middle + 1; next_b < next_nonb && cost < threshold; next_b++) cost += fc(middle, next_nonb, next_b);
+        } else
+            for (int next_b = loc; next_b < next_nonb && cost < threshold; next_b++) cost += fc(cur_nonb, next_nonb, next_b);
+        loc = next_nonb + 1;
+        cur_nonb = next_nonb;
+    }
+    return cost;
+}
+
+static void slicetype_path(La *la, Frame **frames, int length, char (*best_paths)[LMAX + 1])
+{
+    char paths[2][LMAX + 1];
+    const int num_paths = la->p.bframes + 1 < length ? la->p.bframes + 1 : length;
+    uint64_t best_cost = COST_MAX64;
+    int best_possible = 0, idx = 0;
+    for (int path = 0; path < num_paths; path++) {
+        const int len = length - (path + 1);
+        memcpy(paths[idx], best_paths[len % (BMAX + 1)], len);
+        memset(paths[idx] + len, 'B', path);
+        strcpy(paths[idx] + len + path, "P");
+        int possible = 1;
+        for (int i = 1; i <= length; i++) {
+            const int t = frames[i]->i_type;
+            if (t == T_AUTO) continue;
+            if (IS_B(t)) possible = possible && (i < len || i == length || paths[idx][i - 1] == 'B');
+            else {
+                possible = possible && (i < len || paths[idx][i - 1] != 'B');
+                paths[idx][i - 1] = IS_I(t) ? 'I' : 'P';
+            }
+        }
+        if (possible || !best_possible) {
+            if (possible && !best_possible) best_cost = COST_MAX64;
+            const uint64_t cost = path_cost(la, frames, paths[idx], best_cost);
+            if (cost < best_cost) { best_cost = cost; best_possible = possible; idx ^= 1; }
+        }
+    }
+    memcpy(best_paths[length % (BMAX + 1)], paths[idx ^ 1], length);
+}
+
+static int scenecut_internal(La *la, Frame **frames, int p0, int p1)
+{
+    Frame *frame = frames[p1];
+    if (frame_cost(la, frames, p0, p1, p1, true) < 0) { la->fail = true; return 0; }
+    if (frame->cost_est[0][0] == PENDING && la_sync(la) < 0) { la->fail = true; return 0; }
+    const int icost = frame->cost_est[0][0];
+    const int pcost = frame->cost_est[p1 - p0][0];
+    float f_bias;
+    const int i_gop_size = frame->i_frame - la->i_last_keyframe;
+    const float f_thresh_max = la->p.scenecut / 100.0;
+    float f_thresh_min = f_thresh_max * 0.25;
+    if (la->p.keyint_min == la->p.keyint_max) f_thresh_min = f_thresh_max;
+    if (i_gop_size <= la->p.keyint_min / 4) f_bias = f_thresh_min / 4;
+    else if (i_gop_size <= la->p.keyint_min) f_bias = f_thresh_min * i_gop_size / la->p.keyint_min;
+    else f_bias = f_thresh_min + (f_thresh_max - f_thresh_min) * (i_gop_size - la->p.keyint_min) / (la->p.keyint_max - la->p.keyint_min);
+    return pcost >= (1.0 - f_bias) * icost;
+}
+
+static int scenecut(La *la, Frame **frames, int p0, int p1, int real_scenecut, int num_frames, int i_max_search)
+{
+    if (real_scenecut && la->p.bframes) {
+        int origmaxp1 = p0 + 1;
+        if (la->p.b_adapt == 2) origmaxp1 += la->p.bframes;
+        else origmaxp1++;
+        const int maxp1 = origmaxp1 < num_frames ? origmaxp1 : num_frames;
+        for (int curp1 = p1; curp1 <= maxp1; curp1++)
+            if (!scenecut_internal(la, frames, p0, curp1))
+                for (int i = curp1; i > p0; i--) frames[i]->b_scenecut = 0;
+        for (int curp0 = p0; curp0 <= maxp1; curp0++)
+            if (origmaxp1 > i_max_search || (curp0 < maxp1 && scenecut_internal(la, frames, curp0, maxp1)))
+                frames[curp0]->b_scenecut = 0;
+    }
+    if (!frames[p1]->b_scenecut) return 0;
+    return scenecut_internal(la, frames, p0, p1);
+}
+
+static int slicetype_analyse(La *la, int intra_minigop)
+{
+    const x264vfw_cuda_la_params *p = &la->p;
+    Frame *frames[LMAX + 3] = {nullptr};
+    int num_frames, orig_num_frames, keyint_limit, framecnt;
+    int i_max_search = (int)la->next.size() < LMAX ? (int)la->next.size() : LMAX;
+    if (i_max_search > la->slicetype_length + 1 - intra_minigop) i_max_search = la->slicetype_length + 1 - intra_minigop;   // b_deterministic
+    const int keyframe = !!intra_minigop;
+
+    if (!la->last_nonb) return 0;
+    frames[0] = la->last_nonb;
+    for (framecnt = 0; framecnt < i_max_search; framecnt++) frames[framecnt + 1] = la->next[framecnt];
+
+    if (!framecnt) {
+        if (p->b_mbtree) return macroblock_tree(la, frames, 0, keyframe);
+        return 0;
+    }
+    keyint_limit = p->keyint_max - frames[0]->i_frame + la->i_last_keyframe - 1;
+    orig_num_frames = num_frames = framecnt < keyint_limit ? framecnt : keyint_limit;
+    if (p->b_psy && p->b_mbtree) num_frames = framecnt;
+    else if (p->open_gop && num_frames < framecnt) num_frames++;
+    else if (num_frames == 0) { frames[1]->i_type = T_I; return 0; }
+
+    if (AUTO_OR_I(frames[1]->i_type) && p->scenecut && scenecut(la, frames, 0, 1, 1, orig_num_frames, i_max_search)) {
+        if (frames[1]->i_type == T_AUTO) frames[1]->i_type = T_I;
+        return la->fail ? -1 : 0;
+    }
+    for (int j = 1; j <= num_frames; j++)
+        if (frames[j]->i_type == T_KEYFRAME) frames[j]->i_type = p->open_gop ? T_I : T_IDR;
+    for (int j = 2; j <= num_frames; j++)
+        if (frames[j]->i_type == T_IDR && AUTO_OR_B(frames[j - 1]->i_type)) frames[j - 1]->i_type = T_P;
+
+    int num_analysed_frames = num_frames;
+    int reset_start;
+    if (p->bframes) {
+        if (p->b_adapt == 2) {
+            if (num_frames > 1) {
+                char best_paths[BMAX + 1][LMAX + 1];
+                memset(best_paths, 0, sizeof(best_paths));
+                strcpy(best_paths[1], "P");
+                const int best_path_index = num_frames % (BMAX + 1);
+                for (int j = 2; j <= num_frames; j++) slicetype_path(la, frames, j, best_paths);
+                for (int j = 1; j < num_frames; j++) {
+                    if (best_paths[best_path_index][j - 1] != 'B') {
+                        if (AUTO_OR_B(frames[j]->i_type)) frames[j]->i_type = T_P;
+                    } else if (frames[j]->i_type == T_AUTO) frames[j]->i_type = T_B;
+                }
+            }
+        } else if (p->b_adapt == 1) {
+            int last_nonb = 0, num_bframes = p->bframes;
+            char path[LMAX + 1];
+            for (int j = 1; j < num_frames; j++) {
+                if (j - 1 > 0 && IS_B(frames[j - 1]->i_type)) num_bframes--;
+                else { last_nonb = j - 1; num_bframes = p->bframes; }
+                if (!num_bframes) {
+                    if (AUTO_OR_B(frames[j]->i_type)) frames[j]->i_type = T_P;
+                    continue;
+                }
+                if (frames[j]->i_type != T_AUTO) continue;
+                if (IS_B(frames[j + 1]->i_type)) { frames[j]->i_type = T_P; continue; }
+                const int bframes = j - last_nonb - 1;
+                memset(path, 'B', bframes);
+                strcpy(path + bframes, "PP");
+                const uint64_t cost_p = path_cost(la, frames + last_nonb, path, COST_MAX64);
+                strcpy(path + bframes, "BP");
+                const uint64_t cost_b = path_cost(la, frames + last_nonb, path, cost_p);
+                frames[j]->i_type = cost_b < cost_p ? T_B : T_P;
+            }
+        } else {
+            int num_bframes = p->bframes;
+            for (int j = 1; j < num_frames; j++) {
+                if (!num_bframes) {
+                    if (AUTO_OR_B(frames[j]->i_type)) frames[j]->i_type = T_P;
+                } else if (frames[j]->i_type == T_AUTO) {
+                    if (IS_B(frames[j + 1]->i_type)) frames[j]->i_type = T_P;
+                    else frames[j]->i_type = T_B;
+                }
+                if (IS_B(frames[j]->i_type)) num_bframes--;
+                else num_bframes = p->bframes;
+            }
+        }
+        if (AUTO_OR_B(frames[num_frames]->i_type)) frames[num_frames]->i_type = T_P;
+
+        int num_bframes = 0;
+        while (num_bframes < num_frames && IS_B(frames[num_bframes + 1]->i_type)) num_bframes++;
+        for (int j = 1; j < num_bframes + 1; j++) {
+            if (frames[j]->i_forced_type == T_AUTO && AUTO_OR_I(frames[j + 1]->i_forced_type) &&
+                p->scenecut && scenecut(la, frames, j, j + 1, 0, orig_num_frames, i_max_search)) {
+                frames[j]->i_type = T_P;
+                num_analysed_frames = j;
+                break;
+            }
+        }
+        reset_start = keyframe ? 1 : (num_bframes + 2 < num_analysed_frames + 1 ? num_bframes + 2 : num_analysed_frames + 1);
+    } else {
+        for (int j = 1; j <= num_frames; j++)
+            if (AUTO_OR_B(frames[j]->i_type)) frames[j]->i_type = T_P;
+        reset_start = !keyframe + 1;
+    }
+    if (la->fail) return -1;
+
+    if (p->b_mbtree && macroblock_tree(la, frames, num_frames < p->keyint_max ? num_frames : p->keyint_max, keyframe) < 0) return -1;
+
+    {   // enforce keyframe limit
+        int last_keyframe = la->i_last_keyframe, last_possible = 0;
+        for (int j = 1; j <= num_frames; j++) {
+            Frame *frm = frames[j];
+            int keyframe_dist = frm->i_frame - last_keyframe;
+            if (AUTO_OR_I(frm->i_forced_type)) {
+                if (p->open_gop || !IS_B(frames[j - 1]->i_forced_type)) last_possible = j;
+            }
+            if (keyframe_dist >= p->keyint_max) {
+                if (last_possible != 0 && last_possible != j) {
+                    j = last_possible;
+                    frm = frames[j];
+                    keyframe_dist = frm->i_frame - last_keyframe;
+                }
+                last_possible = 0;
+                if (frm->i_type != T_IDR) frm->i_type = p->open_gop ? T_I : T_IDR;
+            }
+            if (frm->i_type == T_I && keyframe_dist >= p->keyint_min) {
+                if (p->open_gop) last_keyframe = frm->i_frame;
+                else if (frm->i_forced_type != T_I) frm->i_type = T_IDR;
+            }
+            if (frm->i_type == T_IDR) {
+                last_keyframe = frm->i_frame;
+                if (j > 1 && IS_B(frames[j - 1]->i_type)) frames[j - 1]->i_type = T_P;
+            }
+        }
+    }
+    for (int j = reset_start; j <= num_frames; j++) frames[j]->i_type = frames[j]->i_forced_type;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// [x264] x264_slicetype_decide + lookahead_slicetype_decide
+// ------------------------------------------------------------------------------------------
+static float *qp_staging(La *la)
+{
+    if (!la->qp_free.empty()) { float *p = la->qp_free.back(); la->qp_free.pop_back(); return p; }
+    float *p = nullptr;
+    if (cudaMallocHost((void **)&p, (size_t)2 * la->g.mb_count * sizeof(float)) != cudaSuccess) { set_error("cudaMallocHost failed"); return nullptr; }
+    return p;
+}
+
+static int decide_and_shift(La *la)
+{
+    const x264vfw_cuda_la_params *p = &la->p;
+    Frame *frames[BMAX + 3];
+    Frame *frm;
+    int bframes, brefs;
+    if (la->next.empty()) return 0;
+    la->fail = false;
+
+    for (Frame *f : la->next) f->f_duration = (float)((double)2 * p->fps_den / ((double)p->fps_num * 2));
+
+    if ((p->bframes && p->b_adapt) || p->scenecut || p->b_mbtree)
+        if (slicetype_analyse(la, 0) < 0) return -1;
+
+    const int n_next = (int)la->next.size();
+    for (bframes = 0, brefs = 0;; bframes++) {
+        frm = la->next[bframes];
+        if (frm->i_type == T_BREF && p->b_pyramid < 2 && brefs == p->b_pyramid) frm->i_type = T_B;
+        else if (frm->i_type == T_BREF && p->b_pyramid == 2 && brefs && p->frame_reference <= (brefs + 3)) frm->i_type = T_B;
+        if (frm->i_type == T_KEYFRAME) frm->i_type = p->open_gop ? T_I : T_IDR;
+        if (frm->i_frame - la->i_last_keyframe >= p->keyint_max) {
+            if (frm->i_type == T_AUTO || frm->i_type == T_I)
+                frm->i_type = p->open_gop && la->i_last_keyframe >= 0 ? T_I : T_IDR;
+            int warn = frm->i_type != T_IDR;
+            if (warn && p->open_gop) warn &= frm->i_type != T_I;
+            if (warn) frm->i_type = p->open_gop && la->i_last_keyframe >= 0 ? T_I : T_IDR;
+        }
+        if (frm->i_type == T_I && frm->i_frame - la->i_last_keyframe >= p->keyint_min) {
+            if (p->open_gop) { la->i_last_keyframe = frm->i_frame; frm->b_keyframe = 1; }
+            else frm->i_type = T_IDR;
+        }
+        if (frm->i_type == T_IDR) {
+            la->i_last_keyframe = frm->i_frame;
+            frm->b_keyframe = 1;
+            if (bframes > 0) { bframes--; la->next[bframes]->i_type = T_P; }
+        }
+        if (bframes == p->bframes || bframes + 1 >= n_next) {
+            if (frm->i_type == T_AUTO || IS_B(frm->i_type)) frm->i_type = T_P;
+        }
+        if (frm->i_type == T_BREF) brefs++;
+        if (frm->i_type == T_AUTO) frm->i_type = T_B;
+        else if (!IS_B(frm->i_type)) break;
+    }
+    la->next[bframes]->i_bframes = bframes;
+    if (p->b_pyramid && bframes > 1 && !brefs) { la->next[(bframes - 1) / 2]->i_type = T_BREF; brefs++; }
+
+    {   // frame cost ratecontrol will ask for (x264_rc_analyse_slice)
+        int p0, p1, b;
+        p1 = b = bframes + 1;
+        frames[0] = la->last_nonb;
+        for (int i = 0; i <= bframes; i++) frames[1 + i] = la->next[i];
+        if (IS_I(la->next[bframes]->i_type)) p0 = bframes + 1;
+        else p0 = 0;
+        if (frame_cost(la, frames, p0, p1, b, false) < 0) return -1;
+        la->next[bframes]->rc_d0 = b - p0; la->next[bframes]->rc_d1 = p1 - b;
+    }
+
+    // coded order: non-B, then BREF, then B
+    std::vector<Frame *> coded;
+    coded.push_back(la->next[bframes]);
+    for (int i = 0; i < bframes; i++) if (la->next[i]->i_type == T_BREF) coded.push_back(la->next[i]);
+    for (int i = 0; i < bframes; i++) if (la->next[i]->i_type != T_BREF) coded.push_back(la->next[i]);
+
+    Frame *old_nonb = la->last_nonb;
+    la->last_nonb = la->next[bframes];
+    const int shift = bframes + 1;
+    for (int i = 0; i < shift; i++) la->next.pop_front();
+
+    if (p->b_mbtree && IS_I(la->last_nonb->i_type))
+        if (slicetype_analyse(la, shift) < 0) return -1;
+
+    // stage the per-MB offsets of the shifted frames, then one synchronisation for the decide
+    for (Frame *f : coded) {
+        Decision d;
+        memset(&d.d, 0, sizeof(d.d));
+        d.f = f;
+        d.h_qp = qp_staging(la);
+        if (!d.h_qp) return -1;
+        d.h_qp_aq = d.h_qp + la->g.mb_count;
+        LA_CUDA(cudaMemcpyAsync(d.h_qp, f->qp_offset, la->g.mb_count * sizeof(float), cudaMemcpyDeviceToHost, la->st));
+        LA_CUDA(cudaMemcpyAsync(d.h_qp_aq, f->qp_offset_aq, la->g.mb_count * sizeof(float), cudaMemcpyDeviceToHost, la->st));
+        la->outq.push_back(d);
+    }
+    if (la_sync(la) < 0) return -1;
+    for (size_t k = la->outq.size() - coded.size(); k < la->outq.size(); k++) {
+        Decision &d = la->outq[k];
+        Frame *f = d.f;
+        d.d.i_frame = f->i_frame; d.d.i_type = f->i_type; d.d.b_keyframe = f->b_keyframe; d.d.i_bframes = f->i_bframes;
+        d.d.mb_count = la->g.mb_count;
+        d.d.i_cost_est = d.d.i_cost_est_aq = d.d.i_intra_mbs = -1;
+        if (f->rc_d0 >= 0) {
+            d.d.i_cost_est = f->cost_est[f->rc_d0][f->rc_d1];
+            d.d.i_cost_est_aq = f->cost_est_aq[f->rc_d0][f->rc_d1];
+            d.d.i_intra_mbs = f->intra_mbs[f->rc_d0];
+        }
+        d.f = nullptr;
+    }
+    // recycle: B-frames are dead once shifted; the previous last_nonb is dead now
+    for (Frame *f : coded) if (f != la->last_nonb) frame_release(la, f);
+    if (old_nonb && old_nonb != la->last_nonb) frame_release(la, old_nonb);
+    return la->fail ? -1 : 0;
+}
+
+} // namespace xv
+
+using namespace xv;
+
+extern "C" {
+
+int x264vfw_cuda_la_params_preset(x264vfw_cuda_la_params *p, const char *preset, int width, int height)
+{
+    // x264 defaults (x264_param_default) + the preset deltas x264vfw documents (config.c:1460-1498)
+    if (!p || !preset) return -1;
+    memset(p, 0, sizeof(*p));
+    p->width = width; p->height = height; p->chroma_format = 1;
+    p->bframes = 3; p->b_adapt = 1; p->b_pyramid = 2; p->b_bias = 0;
+    p->rc_lookahead = 40; p->b_mbtree = 1; p->scenecut = 40;
+    p->keyint_max = 250; p->keyint_min = 25; p->open_gop = 0;
+    p->weightp = 2; p->weightb = 1; p->subme = 7; p->me_method = 1; p->me_range = 16; p->mv_range = 512;
+    p->aq_mode = 1; p->aq_strength = 1.0f; p->qcompress = 0.6f; p->frame_reference = 3;
+    p->lookahead_threads = 1; p->fps_num = 25; p->fps_den = 1; p->b_psy = 1;
+    if (!strcmp(preset, "ultrafast")) {
+        p->frame_reference = 1; p->scenecut = 0; p->bframes = 0; p->b_adapt = 0; p->me_method = 0; p->subme = 0;
+        p->aq_mode = 0; p->b_mbtree = 0; p->rc_lookahead = 0; p->weightp = 0; p->weightb = 0;
+    } else if (!strcmp(preset, "superfast")) {
+        p->me_method = 0; p->subme = 1; p->frame_reference = 1; p->b_mbtree = 0; p->rc_lookahead = 0; p->weightp = 1;
+    } else if (!strcmp(preset, "veryfast")) {
+        p->subme = 2; p->frame_reference = 1; p->weightp = 1; p->rc_lookahead = 10;
+    } else if (!strcmp(preset, "faster")) {
+        p->frame_reference = 2; p->subme = 4; p->weightp = 1; p->rc_lookahead = 20;
+    } else if (!strcmp(preset, "fast")) {
+        p->frame_reference = 2; p->subme = 6; p->weightp = 1; p->rc_lookahead = 30;
+    } else if (!strcmp(preset, "medium")) {
+    } else if (!strcmp(preset, "slow")) {
+        p->subme = 8; p->frame_reference = 5; p->rc_lookahead = 50;
+    } else if (!strcmp(preset, "slower")) {
+        p->me_method = 2; p->subme = 9; p->frame_reference = 8; p->b_adapt = 2; p->rc_lookahead = 60;
+    } else if (!strcmp(preset, "veryslow")) {
+        p->me_method = 2; p->subme = 10; p->me_range = 24; p->frame_reference = 16; p->b_adapt = 2; p->bframes = 8; p->rc_lookahead = 60;
+    } else { set_error("unknown preset %s", preset); return -1; }
+    return 0;
+}
+
+int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *params, int device,
+                         int in_csp, int out_csp, int colmatrix, int fullrange, int keep_frames)
+{
+    if (!pla || !params) { set_error("null argument"); return -1; }
+    *pla = nullptr;
+    int ndev = 0;
+    XV_CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) { set_error("no CUDA device: this library has no CPU fallback"); return -1; }
+    if (device < 0) XV_CUDA_OK(cudaGetDevice(&device));
+    XV_CUDA_OK(cudaSetDevice(device));
+    if (params->width <= 0 || params->height <= 0 || (params->width & 1) || (params->height & 1)) { set_error("width/height must be positive and even"); return -1; }
+    La *la = new La();
+    la->p = *params;
+    x264vfw_cuda_la_params &p = la->p;
+    if (p.bframes > BMAX) p.bframes = BMAX;
+    if (p.bframes < 0) p.bframes = 0;
+    if (p.rc_lookahead > LMAX) p.rc_lookahead = LMAX;
+    if (p.keyint_min <= 0) { int fps = p.fps_num / (p.fps_den > 0 ? p.fps_den : 1); p.keyint_min = p.keyint_max / 10 < fps ? p.keyint_max / 10 : fps; }
+    if (p.chroma_format < 0 || p.chroma_format > 3) { set_error("bad chroma_format"); delete la; return -1; }
+    la->device = device; la->in_csp = in_csp; la->out_csp = out_csp; la->colmatrix = colmatrix; la->fullrange = fullrange;
+    la->keep_frames = keep_frames;
+    x264vfw_cuda_lowres_geom lg;
+    x264vfw_cuda_lowres_geometry(&lg, p.width, p.height);
+    LaGeom &g = la->g;
+    g.width = p.width; g.height = p.height; g.mb_w = lg.mb_w; g.mb_h = lg.mb_h; g.mb_count = lg.mb_w * lg.mb_h;
+    g.luma_w = lg.luma_w; g.luma_h = lg.luma_h; g.lw = lg.lw; g.lh = lg.lh; g.lstride = lg.lstride;
+    g.lplane = lg.lplane_bytes; g.lorigin = lg.lorigin;
+    // [x264] lowres_context_init
+    if (p.subme > 1) { la->la_me_hex = p.me_method >= 1; la->la_subpel_refine = 4; }
+    else { la->la_me_hex = 0; la->la_subpel_refine = 2; }
+    la->la_satd = p.subme > 1;
+    la->do_edges = p.b_mbtree || g.mb_w <= 2 || g.mb_h <= 2;
+    la->slicetype_length = p.bframes > p.rc_lookahead ? p.bframes : p.rc_lookahead;
+    la->i_last_keyframe = -p.keyint_max;
+    if (cudaStreamCreateWithFlags(&la->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete la; return -1; }
+
+    // tables: [x264] x264_analyse_init_costs for X264_LOOKAHEAD_QP (lambda 1), x264_log2_lut, x264_exp2_lut
+    {
+        const int n = 2 * 4 * p.mv_range;
+        std::vector<uint16_t> tab(2 * n + 1);
+        for (int i = 0; i <= n; i++) {
+            float lg2 = i == 0 ? 0.718f : log2f((float)(i + 1)) * 2.0f + 1.718f;
+            int c = (int)(1 * lg2 + .5f);
+            tab[n - i] = tab[n + i] = (uint16_t)(c < 65535 ? c : 65535);
+        }
+        la->cost_mv_half = n;
+        float l2[128]; uint8_t e2[64];
+        for (int i = 0; i < 128; i++) l2[i] = (float)(round(log2(1.0 + i / 128.0) * 100000.0) / 100000.0);
+        for (int i = 0; i < 64; i++) e2[i] = (uint8_t)lround(256.0 * (pow(2.0, i / 64.0) - 1.0));
+        bool ok = cudaMalloc((void **)&la->d_cost_mv, tab.size() * 2) == cudaSuccess &&
+                  cudaMalloc((void **)&la->d_log2_lut, sizeof(l2)) == cudaSuccess &&
+                  cudaMalloc((void **)&la->d_exp2_lut, 64) == cudaSuccess &&
+                  cudaMemcpy(la->d_cost_mv, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(la->d_log2_lut, l2, sizeof(l2), cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(la->d_exp2_lut, e2, 64, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&la->d_weight_buf, g.lplane + 64) == cudaSuccess &&
+             cudaMalloc((void **)&la->d_sync, 2 * (1 + g.mb_h) * sizeof(int)) == cudaSuccess &&
+             cudaMalloc((void **)&la->d_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
+             cudaMallocHost((void **)&la->h_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
+             cudaMalloc((void **)&la->d_wscore, 64) == cudaSuccess &&
+             cudaMallocHost((void **)&la->h_wscore, 64) == cudaSuccess;
+        int64_t pbytes = x264vfw_cuda_picture_layout(&la->planes_img, nullptr, out_csp, p.width, p.height);
+        if (pbytes < 0) { set_error("bad encoder csp %d", out_csp); ok = false; }
+        else {
+            la->d_planes_bytes = (size_t)pbytes;
+            ok = ok && cudaMalloc((void **)&la->d_planes, (size_t)pbytes + 256) == cudaSuccess;
+            if (ok) x264vfw_cuda_picture_layout(&la->planes_img, la->d_planes, out_csp, p.width, p.height);
+        }
+        if (!ok) { if (!*x264vfw_cuda_last_error()) set_error("lookahead allocation failed"); x264vfw_cuda_la_close((x264vfw_cuda_la *)la); return -1; }
+    }
+    *pla = (x264vfw_cuda_la *)la;
+    return 0;
+}
+
+void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
+{
+    La *la = (La *)h;
+    if (!la) return;
+    cudaSetDevice(la->device);
+    if (la->st) cudaStreamSynchronize(la->st);
+    for (Frame *f : la->pool) frame_free(f);
+    for (Decision &d : la->outq) if (d.h_qp) cudaFreeHost(d.h_qp);
+    for (float *q : la->qp_free) cudaFreeHost(q);
+    cudaFree(la->d_cost_mv); cudaFree(la->d_log2_lut); cudaFree(la->d_exp2_lut); cudaFree(la->d_weight_buf);
+    cudaFree(la->d_sync); cudaFree(la->d_results); cudaFree(la->d_wscore); cudaFree(la->d_planes); cudaFree(la->d_src);
+    if (la->h_results) cudaFreeHost(la->h_results);
+    if (la->h_wscore) cudaFreeHost(la->h_wscore);
+    if (la->st) cudaStreamDestroy(la->st);
+    delete la;
+}
+
+int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *src, int src_on_device, x264vfw_cuda_image_t *conv_pic)
+{
+    La *la = (La *)h;
+    if (!la || !src) { set_error("null argument"); return -1; }
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    const int w = la->p.width, hgt = la->p.height;
+    const int in = la->in_csp & X264VFW_CUDA_CSP_MASK;
+    x264vfw_cuda_image_t planes = la->planes_img;           // device, tight, encoder csp
+
+    if (in == X264VFW_CUDA_CSP_NONE) {
+        // planar frame already in the encoder csp: copy rows into the tight device planes
+        x264vfw_cuda_image_t geo;
+        x264vfw_cuda_picture_layout(&geo, nullptr, la->out_csp, w, hgt);
+        for (int i = 0; i < geo.i_plane; i++) {
+            const int rows = (i && (la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_NV12)) ? hgt / 2 : hgt;
+            XV_CUDA_OK(cudaMemcpy2DAsync(planes.plane[i], planes.i_stride[i], src->plane[i], src->i_stride[i], geo.i_stride[i], rows,
+                                         src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, la->st));
+        }
+    } else {
+        x264vfw_cuda_image_t dsrc = *src;
+        dsrc.i_csp = la->in_csp;
+        if (!src_on_device) {
+            x264vfw_cuda_image_t geo;
+            int64_t sbytes = x264vfw_cuda_img_fill(&geo, nullptr, in, w, hgt);
+            if (sbytes < 0) return -1;
+            size_t need = 0, off[4];
+            for (int i = 0; i < geo.i_plane; i++) {
+                const int rows = (i && (in == X264VFW_CUDA_CSP_I420 || in == X264VFW_CUDA_CSP_YV12 || in == X264VFW_CUDA_CSP_NV12)) ? hgt / 2 : hgt;
+                off[i] = need; need += ((size_t)src->i_stride[i] * rows + 255) & ~(size_t)255;
+            }
+            if (la->d_src_bytes < need) {
+                if (la->d_src) { XV_CUDA_OK(cudaStreamSynchronize(la->st)); cudaFree(la->d_src); la->d_src = nullptr; }
+                XV_CUDA_OK(cudaMalloc((void **)&la->d_src, need + 256));
+                la->d_src_bytes = need;
+            }
+            for (int i = 0; i < geo.i_plane; i++) {
+                const int rows = (i && (in == X264VFW_CUDA_CSP_I420 || in == X264VFW_CUDA_CSP_YV12 || in == X264VFW_CUDA_CSP_NV12)) ? hgt / 2 : hgt;
+                dsrc.plane[i] = la->d_src + off[i];
+                XV_CUDA_OK(cudaMemcpyAsync(dsrc.plane[i], src->plane[i], (size_t)src->i_stride[i] * rows, cudaMemcpyHostToDevice, la->st));
+            }
+        }
+        if (convert_device_public(la->st, la->out_csp, la->colmatrix, la->fullrange, X264VFW_CUDA_EXT_NONE, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1;
+        la->n_launch++;
+    }
+    if (conv_pic) {
+        x264vfw_cuda_image_t geo;
+        x264vfw_cuda_picture_layout(&geo, nullptr, la->out_csp, w, hgt);
+        for (int i = 0; i < geo.i_plane; i++) {
+            const int rows = (i && (la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_NV12)) ? hgt / 2 : hgt;
+            XV_CUDA_OK(cudaMemcpy2DAsync(conv_pic->plane[i], conv_pic->i_stride[i], planes.plane[i], planes.i_stride[i], geo.i_stride[i], rows,
+                                         cudaMemcpyDeviceToHost, la->st));
+        }
+    }
+
+    Frame *f = frame_get(la, la->n_input);
+    if (!f) return -1;
+    la->n_input++;
+
+    // [x264] x264_adaptive_quant_frame
+    const bool planar_yuv = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_I422 || la->out_csp == X264VFW_CUDA_OUT_I444;
+    const bool aq_on = la->p.aq_mode != 0 && la->p.aq_strength != 0;
+    AqJob aq;
+    aq.y = planes.plane[0]; aq.y_stride = planes.i_stride[0];
+    aq.u = planar_yuv ? planes.plane[1] : nullptr; aq.v = planar_yuv ? planes.plane[2] : nullptr; aq.c_stride = planes.i_stride[1];
+    aq.chroma_format = planar_yuv ? la->p.chroma_format : 0;
+    aq.aq_on = aq_on; aq.strength = la->p.aq_strength * 1.0397f;
+    aq.qp_offset = f->qp_offset; aq.qp_offset_aq = f->qp_offset_aq; aq.inv_qscale = f->inv_qscale;
+    aq.stats = f->stats; aq.log2_lut = la->d_log2_lut; aq.exp2_lut = la->d_exp2_lut;
+    if (launch_aq(la->st, la->g, aq) < 0) return -1;
+    XV_CUDA_OK(cudaMemcpyAsync(f->h_stats, f->stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, la->st));
+
+    // [x264] x264_frame_init_lowres
+    LowresJob lj;
+    lj.y = planes.plane[0]; lj.y_stride = planes.i_stride[0]; lj.w = w; lj.h = hgt; lj.dst = f->lowres;
+    lj.luma_w = la->g.luma_w; lj.luma_h = la->g.luma_h; lj.lw = la->g.lw; lj.lh = la->g.lh;
+    lj.lstride = la->g.lstride; lj.lplane_bytes = la->g.lplane; lj.lorigin = la->g.lorigin;
+    lj.src_frame_bytes = 0; lj.dst_frame_bytes = 0;
+    if (launch_lowres_init(la->st, lj, 1) < 0) return -1;
+    la->n_launch += 2;
+
+    la->next.push_back(f);      // [x264] x264_lookahead_put_frame
+    while ((int)la->next.size() > la->slicetype_length)
+        if (decide_and_shift(la) < 0) return -1;
+    if (conv_pic || !src_on_device) XV_CUDA_OK(cudaStreamSynchronize(la->st));   // caller's buffers are borrowed for the call only
+    return (int)la->outq.size();
+}
+
+int x264vfw_cuda_la_flush(x264vfw_cuda_la *h)
+{
+    La *la = (La *)h;
+    if (!la) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    while (!la->next.empty())
+        if (decide_and_shift(la) < 0) return -1;
+    return (int)la->outq.size();
+}
+
+int x264vfw_cuda_la_get_decision(x264vfw_cuda_la *h, x264vfw_cuda_la_decision *d, float *qp_offset, float *qp_offset_aq)
+{
+    La *la = (La *)h;
+    if (!la || !d) return -1;
+    if (la->outq.empty()) return 0;
+    Decision &q = la->outq.front();
+    *d = q.d;
+    if (qp_offset) memcpy(qp_offset, q.h_qp, la->g.mb_count * sizeof(float));
+    if (qp_offset_aq) memcpy(qp_offset_aq, q.h_qp_aq, la->g.mb_count * sizeof(float));
+    la->qp_free.push_back(q.h_qp);
+    la->outq.pop_front();
+    return 1;
+}
+
+int x264vfw_cuda_la_frame_cost(x264vfw_cuda_la *h, int p0, int p1, int b)
+{
+    La *la = (La *)h;
+    if (!la) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    if (p0 < 0 || p1 >= (int)la->by_index.size() || b < p0 || b > p1 || b - p0 > la->p.bframes + 1 || p1 - b > la->p.bframes + 1) { set_error("frame_cost: bad indices"); return -1; }
+    for (int i = p0; i <= p1; i++) if (!la->by_index[i]) { set_error("frame %d was recycled (open with keep_frames)", i); return -1; }
+    return frame_cost(la, la->by_index.data(), p0, p1, b, true);
+}
+
+int x264vfw_cuda_la_mbtree(x264vfw_cuda_la *h, const int *frame_idx, const int *types, int num_frames, int b_intra)
+{
+    La *la = (La *)h;
+    if (!la || num_frames > LMAX) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    Frame *frames[LMAX + 3];
+    for (int i = 0; i <= num_frames; i++) {
+        if (frame_idx[i] < 0 || frame_idx[i] >= (int)la->by_index.size() || !la->by_index[frame_idx[i]]) { set_error("mbtree: bad frame"); return -1; }
+        frames[i] = la->by_index[frame_idx[i]];
+        frames[i]->i_type = types[i];
+        frames[i]->f_duration = (float)((double)la->p.fps_den / la->p.fps_num);
+    }
+    if (macroblock_tree(la, frames, num_frames, b_intra) < 0) return -1;
+    return la_sync(la);
+}
+
+int64_t x264vfw_cuda_la_read(x264vfw_cuda_la *h, int frame, int what, int a, int b, void *dst, size_t cap)
+{
+    La *la = (La *)h;
+    if (!la || !dst) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    if (la_sync(la) < 0) return -1;
+    const int n = la->g.mb_count, B = la->p.bframes;
+    if (what == X264VFW_CUDA_LA_CONV_PLANES) {
+        if (cap < la->d_planes_bytes) { set_error("read: buffer too small"); return -1; }
+        XV_CUDA_OK(cudaMemcpy(dst, la->d_planes, la->d_planes_bytes, cudaMemcpyDeviceToHost));
+        return (int64_t)la->d_planes_bytes;
+    }
+    if (frame < 0 || frame >= (int)la->by_index.size() || !la->by_index[frame]) { set_error("read: frame %d not resident", frame); return -1; }
+    Frame *f = la->by_index[frame];
+    const void *src = nullptr; size_t bytes = 0; bool host = false;
+    int tmp[4]; unsigned long long st[6];
+    switch (what) {
+    case X264VFW_CUDA_LA_LOWRES: src = f->lowres; bytes = (size_t)4 * la->g.lplane; break;
+    case X264VFW_CUDA_LA_INTRA_COST: src = f->intra_cost; bytes = n * 2; break;
+    case X264VFW_CUDA_LA_INV_QSCALE: src = f->inv_qscale; bytes = n * 2; break;
+    case X264VFW_CUDA_LA_PROPAGATE: src = f->propagate; bytes = n * 4; break;
+    case X264VFW_CUDA_LA_QP_OFFSET: src = f->qp_offset; bytes = n * 4; break;
+    case X264VFW_CUDA_LA_QP_OFFSET_AQ: src = f->qp_offset_aq; bytes = n * 4; break;
+    case X264VFW_CUDA_LA_MVS: if (a < 0 || a > 1 || b < 1 || b > B + 1) return -1; src = f->mvs[a][b - 1]; bytes = n * 4; break;
+    case X264VFW_CUDA_LA_MV_COSTS: if (a < 0 || a > 1 || b < 1 || b > B + 1) return -1; src = f->mv_costs[a][b - 1]; bytes = n * 4; break;
+    case X264VFW_CUDA_LA_LOWRES_COSTS: if (a < 0 || a > B + 1 || b < 0 || b > B + 1) return -1; src = lc_ptr(la, f, a, b); bytes = n * 2; break;
+    case X264VFW_CUDA_LA_COST_EST:
+        if (a < 0 || a > B + 1 || b < 0 || b > B + 1) return -1;
+        tmp[0] = f->cost_est[a][b]; tmp[1] = f->cost_est_aq[a][b]; tmp[2] = f->intra_mbs[a]; src = tmp; bytes = 12; host = true; break;
+    case X264VFW_CUDA_LA_PIXEL_STATS:
+        if (ensure_stats(la, f) < 0) return -1;
+        for (int i = 0; i < 3; i++) { st[i] = f->pixel_sum[i]; st[3 + i] = f->pixel_ssd[i]; }
+        src = st; bytes = 48; host = true; break;
+    case X264VFW_CUDA_LA_WEIGHT:
+        tmp[0] = f->weight.scale; tmp[1] = f->weight.denom; tmp[2] = f->weight.offset; tmp[3] = f->weight.on; src = tmp; bytes = 16; host = true; break;
+    default: set_error("read: unknown selector %d", what); return -1;
+    }
+    if (cap < bytes) { set_error("read: buffer too small"); return -1; }
+    if (host) memcpy(dst, src, bytes);
+    else XV_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return (int64_t)bytes;
+}
+
+void x264vfw_cuda_la_counters(x264vfw_cuda_la *h, uint64_t out[4])
+{
+    La *la = (La *)h;
+    if (!la) return;
+    out[0] = la->n_frame_cost; out[1] = la->n_mb_search; out[2] = la->n_launch; out[3] = la->n_sync;
+}
+
+} // extern "C"

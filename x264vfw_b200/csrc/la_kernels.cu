@@ -1,0 +1,564 @@
+// Data-parallel lookahead kernels: adaptive-quant statistics, intra cost, per-MB cost
+// selection + frame accumulators, weight scoring, mb-tree propagation.
+//
+// These restate, per macroblock, the upstream libx264 functions the reference reaches only
+// through x264_encoder_encode (reference codec.c:1693):
+//   [x264] encoder/ratecontrol.c  x264_adaptive_quant_frame, ac_energy_mb
+//   [x264] encoder/slicetype.c    slicetype_mb_cost (intra part, bidir part, selection),
+//                                 slicetype_frame_cost accumulators, weight_cost_luma,
+//                                 macroblock_tree_propagate, macroblock_tree_finish
+//   [x264] common/mc.c            mbtree_propagate_cost, mbtree_propagate_list, mc_weight
+//   [x264] common/predict.c       predict_8x8c_{dc,h,v,p}, predict_8x8_filter, predict_8x8_{ddl..hu}
+// Every MB is independent in these kernels (the serial part of the lookahead, the motion
+// search with its spatial MV predictors, lives in la_me_kernel.cu), so each is one thread per
+// MB with warp-shuffle + atomic reductions for the frame sums.  Integer results are bit-exact;
+// float code is compiled with --fmad=false and keeps the reference's operation order.
+#include "la_common.cuh"
+
+namespace xv {
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Adaptive quantisation statistics.  One thread per 16x16 MB; a warp reads 512 contiguous
+// bytes per luma row.  Clamped addressing == the mod-16 replicated frame.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dev_log2(const float *lut, uint32_t x)
+{
+    int lz = __clz(x);
+    return lut[(x << lz >> 24) & 0x7f] + (float)(31 - lz);
+}
+__device__ __forceinline__ int dev_exp2fix8(const uint8_t *lut, float x)
+{
+    int i = (int)(x * (-64.f / 6.f) + 512.5f);
+    if (i < 0) return 0;
+    if (i > 1023) return 0xffff;
+    return (lut[i & 63] + 256) << (i >> 6) >> 8;
+}
+
+__device__ __forceinline__ uint32_t block_var_dev(const uint8_t *p, int stride, int pw, int ph, int x0, int y0,
+                                                  int bw, int bh, int shift, unsigned long long &fsum,
+                                                  unsigned long long &fssd)
+{
+    uint32_t sum = 0, ssd = 0;
+    const bool fast = (x0 + bw <= pw) && (((uintptr_t)p | (unsigned)stride) & 15) == 0 && (x0 & 15) == 0 && (bw & 7) == 0;
+    for (int y = 0; y < bh; y++) {
+        const uint8_t *r = p + (size_t)min(y0 + y, ph - 1) * stride;
+        if (fast) {
+            for (int x = 0; x < bw; x += 8) {
+                uint2 v = *(const uint2 *)(r + x0 + x);
+                sum = __dp4a(v.x, 0x01010101u, sum); sum = __dp4a(v.y, 0x01010101u, sum);
+                ssd = __dp4a(v.x, v.x, ssd); ssd = __dp4a(v.y, v.y, ssd);
+            }
+        } else {
+            for (int x = 0; x < bw; x++) { uint32_t v = r[min(x0 + x, pw - 1)]; sum += v; ssd += v * v; }
+        }
+    }
+    fsum += sum; fssd += ssd;
+    return ssd - (uint32_t)(((unsigned long long)sum * sum) >> shift);
+}
+
+__global__ void __launch_bounds__(128)
+aq_kernel(LaGeom g, AqJob job)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long st[6] = {0, 0, 0, 0, 0, 0};
+    if (idx < g.mb_count) {
+        const int mx = idx % g.mb_w, my = idx / g.mb_w;
+        const int w = g.width, h = g.height, cf = job.chroma_format;
+        uint32_t energy = block_var_dev(job.y, job.y_stride, w, h, 16 * mx, 16 * my, 16, 16, 8, st[0], st[3]);
+        if (cf) {
+            const int cw = cf == 3 ? w : w / 2, ch = cf == 1 ? h / 2 : h;
+            const int cbw = cf == 3 ? 16 : 8, cbh = cf == 1 ? 8 : 16, cshift = cf == 3 ? 8 : cf == 2 ? 7 : 6;
+            energy += block_var_dev(job.u, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, cbh, cshift, st[1], st[4]);
+            energy += block_var_dev(job.v, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, cbh, cshift, st[2], st[5]);
+        }
+        if (job.aq_on) {
+            float qp_adj = job.strength * (dev_log2(job.log2_lut, max(energy, 1u)) - (14.427f + 2 * 0));
+            job.qp_offset[idx] = qp_adj;
+            job.qp_offset_aq[idx] = qp_adj;
+            job.inv_qscale[idx] = (uint16_t)dev_exp2fix8(job.exp2_lut, qp_adj);
+        } else {
+            job.qp_offset[idx] = 0.f; job.qp_offset_aq[idx] = 0.f; job.inv_qscale[idx] = 256;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        unsigned long long s = warp_sum64(st[i]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(job.stats + i, s);
+    }
+}
+
+int launch_aq(cudaStream_t st, const LaGeom &g, const AqJob &job)
+{
+    aq_kernel<<<(g.mb_count + 127) / 128, 128, 0, st>>>(g, job);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Intra cost.  One thread per lowres 8x8 MB.
+// ------------------------------------------------------------------------------------------
+struct Nbr { int tl; int top[16]; int left[8]; };
+struct Edge { int c; int t[16]; int l[8]; };
+
+__device__ __forceinline__ uint32_t splat4(int v) { return (uint32_t)v * 0x01010101u; }
+
+__device__ __forceinline__ void filter_edges_dev(Edge &e, const Nbr &n)
+{
+    e.c = (n.top[0] + 2 * n.tl + n.left[0] + 2) >> 2;
+    e.t[0] = (n.tl + 2 * n.top[0] + n.top[1] + 2) >> 2;
+#pragma unroll
+    for (int x = 1; x < 15; x++) e.t[x] = (n.top[x - 1] + 2 * n.top[x] + n.top[x + 1] + 2) >> 2;
+    e.t[15] = (n.top[14] + 3 * n.top[15] + 2) >> 2;
+    e.l[0] = (n.tl + 2 * n.left[0] + n.left[1] + 2) >> 2;
+#pragma unroll
+    for (int y = 1; y < 7; y++) e.l[y] = (n.left[y - 1] + 2 * n.left[y] + n.left[y + 1] + 2) >> 2;
+    e.l[7] = (n.left[6] + 3 * n.left[7] + 2) >> 2;
+}
+
+// index -1 is the (filtered) corner; the clamps only keep never-selected branches in bounds
+#define ET(i) ((i) < 0 ? e.c : e.t[(i) < 0 ? 0 : (i) > 15 ? 15 : (i)])
+#define EL(i) ((i) < 0 ? e.c : e.l[(i) < 0 ? 0 : (i) > 7 ? 7 : (i)])
+template <int MODE>
+__device__ __forceinline__ int pred8x8_px(const Edge &e, int x, int y)
+{
+    if (MODE == 3) return (x == 7 && y == 7) ? (ET(14) + 3 * ET(15) + 2) >> 2 : (ET(x + y) + 2 * ET(x + y + 1) + ET(x + y + 2) + 2) >> 2;
+    if (MODE == 4) {
+        if (x > y) return (ET(x - y - 2) + 2 * ET(x - y - 1) + ET(x - y) + 2) >> 2;
+        if (x < y) return (EL(y - x - 2) + 2 * EL(y - x - 1) + EL(y - x) + 2) >> 2;
+        return (ET(0) + 2 * e.c + EL(0) + 2) >> 2;
+    }
+    if (MODE == 5) {
+        const int z = 2 * x - y, i = x - (y >> 1);
+        if (z >= 0 && !(z & 1)) return (ET(i - 1) + ET(i) + 1) >> 1;
+        if (z >= 0) return (ET(i - 2) + 2 * ET(i - 1) + ET(i) + 2) >> 2;
+        if (z == -1) return (EL(0) + 2 * e.c + ET(0) + 2) >> 2;
+        return (EL(y - 2 * x - 1) + 2 * EL(y - 2 * x - 2) + EL(y - 2 * x - 3) + 2) >> 2;
+    }
+    if (MODE == 6) {
+        const int z = 2 * y - x, i = y - (x >> 1);
+        if (z >= 0 && !(z & 1)) return (EL(i - 1) + EL(i) + 1) >> 1;
+        if (z >= 0) return (EL(i - 2) + 2 * EL(i - 1) + EL(i) + 2) >> 2;
+        if (z == -1) return (EL(0) + 2 * e.c + ET(0) + 2) >> 2;
+        return (ET(x - 2 * y - 1) + 2 * ET(x - 2 * y - 2) + ET(x - 2 * y - 3) + 2) >> 2;
+    }
+    if (MODE == 7) {
+        const int i = x + (y >> 1);
+        return !(y & 1) ? (ET(i) + ET(i + 1) + 1) >> 1 : (ET(i) + 2 * ET(i + 1) + ET(i + 2) + 2) >> 2;
+    }
+    {   // 8: horizontal-up
+        const int z = x + 2 * y, i = y + (x >> 1);
+        if (z > 13) return EL(7);
+        if (z == 13) return (EL(6) + 3 * EL(7) + 2) >> 2;
+        if (!(z & 1)) return (EL(i) + EL(i + 1) + 1) >> 1;
+        return (EL(i) + 2 * EL(i + 1) + EL(i + 2) + 2) >> 2;
+    }
+}
+#undef ET
+#undef EL
+
+template <int MODE>
+__device__ __forceinline__ int pred8x8_cost(const Edge &e, const uint2 src[8], int satd)
+{
+    uint2 pr[8];
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            lo |= (uint32_t)pred8x8_px<MODE>(e, x, y) << (8 * x);
+            hi |= (uint32_t)pred8x8_px<MODE>(e, x + 4, y) << (8 * x);
+        }
+        pr[y] = make_uint2(lo, hi);
+    }
+    return mbcmp_rows(satd, src, pr);
+}
+
+__global__ void __launch_bounds__(64)
+intra_kernel(LaGeom g, IntraJob job, int do_edges)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.mb_count) return;
+    const int mx = idx % g.mb_w, my = idx / g.mb_w;
+    if (!do_edges && (mx == 0 || my == 0 || mx == g.mb_w - 1 || my == g.mb_h - 1)) return;
+    const int stride = g.lstride;
+    const uint8_t *src = job.plane0 + 8 * (mx + my * stride);
+    uint2 s[8];
+    Nbr n;
+#pragma unroll
+    for (int y = 0; y < 8; y++) { s[y] = load8u(src + y * stride); n.left[y] = src[y * stride - 1]; }
+    n.tl = src[-stride - 1];
+    {
+        uint2 t0 = load8u(src - stride), t1 = load8u(src - stride + 8);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { n.top[i] = px_of(t0, i); n.top[8 + i] = px_of(t1, i); }
+    }
+    uint2 pr[8];
+    int best;
+    {   // predict_8x8c_dc
+        int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { s0 += n.top[i]; s1 += n.top[i + 4]; s2 += n.left[i]; s3 += n.left[i + 4]; }
+        uint32_t d0 = splat4((s0 + s2 + 4) >> 3), d1 = splat4((s1 + 2) >> 2), d2 = splat4((s3 + 2) >> 2), d3 = splat4((s1 + s3 + 4) >> 3);
+#pragma unroll
+        for (int y = 0; y < 8; y++) pr[y] = y < 4 ? make_uint2(d0, d1) : make_uint2(d2, d3);
+        best = mbcmp_rows(job.satd, pr, s);
+    }
+    {   // predict_8x8c_h
+#pragma unroll
+        for (int y = 0; y < 8; y++) pr[y] = make_uint2(splat4(n.left[y]), splat4(n.left[y]));
+        best = min(best, mbcmp_rows(job.satd, pr, s));
+    }
+    {   // predict_8x8c_v
+        uint2 t = load8u(src - stride);
+#pragma unroll
+        for (int y = 0; y < 8; y++) pr[y] = t;
+        best = min(best, mbcmp_rows(job.satd, pr, s));
+    }
+    if (job.full) {
+        {   // predict_8x8c_p
+            int H = 0, V = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int tm = 2 - i < 0 ? n.tl : n.top[2 - i < 0 ? 0 : 2 - i];
+                int lm = 2 - i < 0 ? n.tl : n.left[2 - i < 0 ? 0 : 2 - i];
+                H += (i + 1) * (n.top[4 + i] - tm);
+                V += (i + 1) * (n.left[4 + i] - lm);
+            }
+            int a = 16 * (n.left[7] + n.top[7]);
+            int b = (17 * H + 16) >> 5, c = (17 * V + 16) >> 5;
+            int i00 = a - 3 * b - 3 * c + 16;
+#pragma unroll
+            for (int y = 0; y < 8; y++) {
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    lo |= (uint32_t)clip_px((i00 + c * y + b * x) >> 5) << (8 * x);
+                    hi |= (uint32_t)clip_px((i00 + c * y + b * (x + 4)) >> 5) << (8 * x);
+                }
+                pr[y] = make_uint2(lo, hi);
+            }
+            best = min(best, mbcmp_rows(job.satd, s, pr));
+        }
+        Edge e;
+        filter_edges_dev(e, n);
+        best = min(best, pred8x8_cost<3>(e, s, job.satd));
+        best = min(best, pred8x8_cost<4>(e, s, job.satd));
+        best = min(best, pred8x8_cost<5>(e, s, job.satd));
+        best = min(best, pred8x8_cost<6>(e, s, job.satd));
+        best = min(best, pred8x8_cost<7>(e, s, job.satd));
+        best = min(best, pred8x8_cost<8>(e, s, job.satd));
+    }
+    job.intra_cost[idx] = (uint16_t)(best + 5 + 4);      // + intra_penalty (5*lambda) + lowres_penalty
+}
+
+int launch_intra(cudaStream_t st, const LaGeom &g, const IntraJob &job, int do_edges)
+{
+    intra_kernel<<<(g.mb_count + 63) / 64, 64, 0, st>>>(g, job, do_edges);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+// sums for i_cost_est[0][0] / i_cost_est_aq[0][0] (+ intra row SATDs)
+__global__ void __launch_bounds__(128)
+intra_sum_kernel(LaGeom g, IntraSumJob job, int do_edges)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0, caq = 0;
+    if (idx < g.mb_count) {
+        const int mx = idx % g.mb_w, my = idx / g.mb_w;
+        const bool edge = mx == 0 || my == 0 || mx == g.mb_w - 1 || my == g.mb_h - 1;
+        const bool tiny = g.mb_w <= 2 || g.mb_h <= 2;
+        if (do_edges || !edge) {
+            int ic = job.intra_cost[idx], icaq = ic;
+            if (job.aq_on) icaq = (icaq * job.inv_qscale[idx] + 128) >> 8;
+            if (job.row_satd) atomicAdd(job.row_satd + my, icaq);
+            if (!edge || tiny) { c = ic; caq = icaq; }
+        }
+    }
+    c = warp_sum(c); caq = warp_sum(caq);
+    if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(job.result, c); if (caq) atomicAdd(job.result + 1, caq); }
+}
+
+int launch_intra_sum(cudaStream_t st, const LaGeom &g, const IntraSumJob &job)
+{
+    intra_sum_kernel<<<(g.mb_count + 127) / 128, 128, 0, st>>>(g, job, 1);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-MB cost selection ([x264] slicetype_mb_cost minus the searches).  One thread per MB.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fetch_ref8(uint2 out[8], const uint8_t *const planes[4], int stride, int pel,
+                                           int mvx, int mvy, const WeightDev &w)
+{
+#pragma unroll
+    for (int r = 0; r < 8; r++) out[r] = get_ref_row(planes, stride, pel, mvx, mvy, r, w);
+}
+
+__device__ __forceinline__ uint32_t avg_weighted4(uint32_t a, uint32_t b, int wgt)
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int pa = (a >> (8 * i)) & 0xff, pb = (b >> (8 * i)) & 0xff;
+        r |= (uint32_t)clip_px((pa * wgt + pb * (64 - wgt) + 32) >> 6) << (8 * i);
+    }
+    return r;
+}
+
+__device__ __forceinline__ int bidir_cost(const uint2 fenc[8], uint2 a[8], const uint2 b[8], int wgt, int satd)
+{
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        if (wgt == 32) { a[r].x = __vavgu4(a[r].x, b[r].x); a[r].y = __vavgu4(a[r].y, b[r].y); }
+        else { a[r].x = avg_weighted4(a[r].x, b[r].x, wgt); a[r].y = avg_weighted4(a[r].y, b[r].y, wgt); }
+    }
+    return mbcmp_rows(satd, fenc, a);
+}
+
+__global__ void __launch_bounds__(64)
+finalize_kernel(LaGeom g, FinalizeJob job)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int acc_cost = 0, acc_aq = 0, acc_intra = 0;
+    if (idx < g.mb_count) {
+        const int mx = idx % g.mb_w, my = idx / g.mb_w;
+        const bool edge = mx == 0 || my == 0 || mx == g.mb_w - 1 || my == g.mb_h - 1;
+        const bool tiny = g.mb_w <= 2 || g.mb_h <= 2;
+        if (job.do_edges || !edge) {
+            const int stride = g.lstride, pel = 8 * (mx + my * stride);
+            int bcost = LA_COST_MAX, list_used = 0;
+            int mv0 = 0, mv1 = 0;
+            if (job.b_bidir) {
+                const WeightDev w0 = {0, 1, 0, 0};
+                uint2 fenc[8], ra[8], rb[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) fenc[r] = load8u(job.fenc + pel + r * stride);
+                int min_x, max_x, min_y, max_y;
+                mv_limits(mx, my, g.mb_w, g.mb_h, job.mv_range2, min_x, max_x, min_y, max_y);
+                int d0x = 0, d0y = 0, d1x = 0, d1y = 0;
+                if (job.ref1_mvs) {
+                    const int mvr = job.ref1_mvs[idx];
+                    const int rx = mv_x(mvr), ry = mv_y(mvr);
+                    d0x = (rx * job.dist_scale_factor + 128) >> 8;
+                    d0y = (ry * job.dist_scale_factor + 128) >> 8;
+                    d1x = d0x - rx; d1y = d0y - ry;
+                    d0x = clip3i(d0x, min_x, max_x); d0y = clip3i(d0y, min_y, max_y);
+                    d1x = clip3i(d1x, min_x, max_x); d1y = clip3i(d1y, min_y, max_y);
+                    if (!job.subme_gt1) { d0x &= ~1; d0y &= ~1; d1x &= ~1; d1y &= ~1; }
+                }
+                // TRY_BIDIR(dmv[0], dmv[1], 0)
+                if (job.subme_gt1) {
+                    fetch_ref8(ra, job.fref0, stride, pel, d0x, d0y, w0);
+                    fetch_ref8(rb, job.fref1, stride, pel, d1x, d1y, w0);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        ra[r] = load8u(job.fref0[((d0x & 2) >> 1) + (d0y & 2)] + pel + ((d0y >> 2) + r) * stride + (d0x >> 2));
+                        rb[r] = load8u(job.fref1[((d1x & 2) >> 1) + (d1y & 2)] + pel + ((d1y >> 2) + r) * stride + (d1x >> 2));
+                    }
+                }
+                int c = bidir_cost(fenc, ra, rb, job.bipred_weight, job.satd);
+                if (c < bcost) { bcost = c; list_used = 3; }
+                if (d0x | d0y | d1x | d1y) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) { ra[r] = load8u(job.fref0[0] + pel + r * stride); rb[r] = load8u(job.fref1[0] + pel + r * stride); }
+                    c = bidir_cost(fenc, ra, rb, job.bipred_weight, job.satd);
+                    if (c < bcost) { bcost = c; list_used = 3; }
+                }
+                mv0 = job.mvs0[idx]; mv1 = job.mvs1[idx];
+                const int c0 = job.mv_costs0[idx], c1 = job.mv_costs1[idx];
+                if (c0 < bcost) { bcost = c0; list_used = 1; }
+                if (c1 < bcost) { bcost = c1; list_used = 2; }
+                if (mv0 | mv1) {
+                    // TRY_BIDIR(m[0].mv, m[1].mv, 5)
+                    if (job.subme_gt1) {
+                        fetch_ref8(ra, job.fref0, stride, pel, mv_x(mv0), mv_y(mv0), w0);
+                        fetch_ref8(rb, job.fref1, stride, pel, mv_x(mv1), mv_y(mv1), w0);
+                    } else {
+                        const int ax = mv_x(mv0), ay = mv_y(mv0), bx = mv_x(mv1), by = mv_y(mv1);
+#pragma unroll
+                        for (int r = 0; r < 8; r++) {
+                            ra[r] = load8u(job.fref0[((ax & 2) >> 1) + (ay & 2)] + pel + ((ay >> 2) + r) * stride + (ax >> 2));
+                            rb[r] = load8u(job.fref1[((bx & 2) >> 1) + (by & 2)] + pel + ((by >> 2) + r) * stride + (bx >> 2));
+                        }
+                    }
+                    c = 5 + bidir_cost(fenc, ra, rb, job.bipred_weight, job.satd);
+                    if (c < bcost) { bcost = c; list_used = 3; }
+                }
+            } else if (job.mv_costs0) {
+                const int c0 = job.mv_costs0[idx];
+                if (c0 < bcost) { bcost = c0; list_used = 1; }
+            }
+            bcost += 4;                                      // lowres_penalty
+            if (job.b_p) {
+                const int icost = job.intra_cost[idx];
+                const int b_intra = icost < bcost;
+                if (b_intra) { bcost = icost; list_used = 0; }
+                if (!edge || tiny) acc_intra = b_intra;
+            }
+            int bcost_aq = bcost;
+            if (job.aq_on) bcost_aq = (bcost_aq * job.inv_qscale[idx] + 128) >> 8;
+            if (job.row_satd) atomicAdd(job.row_satd + my, bcost_aq);
+            if (!edge || tiny) { acc_cost = bcost; acc_aq = bcost_aq; }
+            job.lowres_costs[idx] = (uint16_t)(min(bcost, LA_LOWRES_COST_MASK) + (list_used << LA_LOWRES_COST_SHIFT));
+        }
+    }
+    acc_cost = warp_sum(acc_cost); acc_aq = warp_sum(acc_aq); acc_intra = warp_sum(acc_intra);
+    if ((threadIdx.x & 31) == 0) {
+        if (acc_cost) atomicAdd(job.result, acc_cost);
+        if (acc_aq) atomicAdd(job.result + 1, acc_aq);
+        if (acc_intra) atomicAdd(job.result + 2, acc_intra);
+    }
+}
+
+int launch_finalize(cudaStream_t st, const LaGeom &g, const FinalizeJob &job)
+{
+    finalize_kernel<<<(g.mb_count + 63) / 64, 64, 0, st>>>(g, job);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Weights ([x264] weight_cost_luma at mv 0, x264_weight_scale_plane)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+weight_cost_kernel(LaGeom g, WeightCostJob job)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0;
+    if (idx < g.mb_count) {
+        const int mx = idx % g.mb_w, my = idx / g.mb_w;
+        const int pel = 8 * (mx + my * g.lstride);
+        uint2 a[8], f[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            a[r] = load8u(job.ref + pel + r * g.lstride);
+            f[r] = load8u(job.fenc + pel + r * g.lstride);
+            if (job.w.on) { a[r].x = weight_word(job.w, a[r].x); a[r].y = weight_word(job.w, a[r].y); }
+        }
+        c = min(mbcmp_rows(job.satd, a, f), (int)job.intra_cost[idx]);
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(job.result, (unsigned)c);
+}
+
+int launch_weight_cost(cudaStream_t st, const LaGeom &g, const WeightCostJob &job)
+{
+    weight_cost_kernel<<<(g.mb_count + 127) / 128, 128, 0, st>>>(g, job);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+weight_plane_kernel(uint8_t *dst, const uint8_t *src, int nwords, WeightDev w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) ((uint32_t *)dst)[i] = weight_word(w, ((const uint32_t *)src)[i]);
+}
+
+int launch_weight_plane(cudaStream_t st, const LaGeom &g, uint8_t *dst, const uint8_t *src, WeightDev w)
+{
+    const int nwords = g.lplane / 4;
+    weight_plane_kernel<<<(nwords + 255) / 256, 256, 0, st>>>(dst, src, nwords, w);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// MB-tree.  The reference accumulates into uint16 with per-add saturation at 32767; all
+// addends are >= 0, so that equals min(sum, 32767): accumulate with 32-bit atomics into a
+// shadow array and clamp when the value is read.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+propagate_kernel(LaGeom g, PropagateJob job)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.mb_count) return;
+    const int i = idx % g.mb_w, mb_y = idx / g.mb_w;
+    const int lc = job.lowres_costs[idx];
+    const int intra_cost = job.intra_cost[idx];
+    const int inter_cost = min(intra_cost, lc & LA_LOWRES_COST_MASK);
+    const int pin = job.propagate_in ? min(job.propagate_in[idx], 32767) : 0;
+    const float propagate_intra = (float)(intra_cost * (int)job.inv_qscale[idx]);
+    const float propagate_amount = (float)pin + propagate_intra * job.fps_factor;
+    const float propagate_num = (float)(intra_cost - inter_cost);
+    const float propagate_denom = (float)intra_cost;
+    const int amount = min((int)(propagate_amount * propagate_num / propagate_denom + 0.5f), 32767);
+    const int lists_used = lc >> LA_LOWRES_COST_SHIFT;
+    const unsigned width = g.mb_w, height = g.mb_h, stride = g.mb_w;
+#pragma unroll
+    for (int list = 0; list < 2; list++) {
+        if (list == 1 && !job.b_bidir) break;
+        if (!(lists_used & (1 << list))) continue;
+        int *ref = list ? job.ref1_cost : job.ref0_cost;
+        int listamount = amount;
+        if (lists_used == 3) listamount = (listamount * (list ? 64 - job.bipred_weight : job.bipred_weight) + 32) >> 6;
+        const int mv = (list ? job.mvs1 : job.mvs0)[idx];
+        if (!mv) { if (listamount) atomicAdd(ref + mb_y * stride + i, listamount); continue; }
+        int x = mv_x(mv), y = mv_y(mv);
+        const unsigned mbx = (unsigned)((x >> 5) + i), mby = (unsigned)((y >> 5) + mb_y);
+        const unsigned idx0 = mbx + mby * stride, idx2 = idx0 + stride;
+        x &= 31; y &= 31;
+        const int w0 = ((32 - y) * (32 - x) * listamount + 512) >> 10, w1 = ((32 - y) * x * listamount + 512) >> 10;
+        const int w2 = (y * (32 - x) * listamount + 512) >> 10, w3 = (y * x * listamount + 512) >> 10;
+        if (mbx < width - 1 && mby < height - 1) {
+            if (w0) atomicAdd(ref + idx0, w0);
+            if (w1) atomicAdd(ref + idx0 + 1, w1);
+            if (w2) atomicAdd(ref + idx2, w2);
+            if (w3) atomicAdd(ref + idx2 + 1, w3);
+        } else {
+            if (mby < height) {
+                if (mbx < width && w0) atomicAdd(ref + idx0, w0);
+                if (mbx + 1 < width && w1) atomicAdd(ref + idx0 + 1, w1);
+            }
+            if (mby + 1 < height) {
+                if (mbx < width && w2) atomicAdd(ref + idx2, w2);
+                if (mbx + 1 < width && w3) atomicAdd(ref + idx2 + 1, w3);
+            }
+        }
+    }
+}
+
+int launch_propagate(cudaStream_t st, const LaGeom &g, const PropagateJob &job)
+{
+    propagate_kernel<<<(g.mb_count + 127) / 128, 128, 0, st>>>(g, job);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(128)
+tree_finish_kernel(LaGeom g, TreeFinishJob job)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.mb_count) return;
+    const int intra_cost = ((int)job.intra_cost[idx] * (int)job.inv_qscale[idx] + 128) >> 8;
+    if (intra_cost) {
+        const int propagate_cost = (min(job.propagate[idx], 32767) * job.fps_factor + 128) >> 8;
+        const float log2_ratio = dev_log2(job.log2_lut, intra_cost + propagate_cost) - dev_log2(job.log2_lut, intra_cost) + job.weightdelta;
+        job.qp_offset[idx] = job.qp_offset_aq[idx] - job.strength * log2_ratio;
+    }
+}
+
+int launch_tree_finish(cudaStream_t st, const LaGeom &g, const TreeFinishJob &job)
+{
+    tree_finish_kernel<<<(g.mb_count + 127) / 128, 128, 0, st>>>(g, job);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace xv
