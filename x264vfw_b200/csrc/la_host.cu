@@ -274,6 +274,8 @@ static int launch_intra_for(La *la, Frame *fenc)
 static int ue_size(unsigned v) { v += 1; int n = 0; while (v >> (n + 1)) n++; return 2 * n + 1; }
 static int se_size(int v) { int t = 1 - v * 2; if (t < 0) t = v * 2; int n = 0; while (t >> (n + 1)) n++; return 2 * n + 1; }
 
+static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_value);
+
 static int weight_score(La *la, Frame *fenc, Frame *ref, const WeightDev &w, unsigned *score)
 {
     LA_CUDA(cudaMemsetAsync(la->d_wscore, 0, sizeof(unsigned), la->st));
@@ -309,7 +311,11 @@ static int weights_analyse(La *la, Frame *fenc, Frame *ref)
     if (scale > 127) scale = 127;
     int found = 0, mindenom = denom, minscale = scale, minoff = 0;
 
-    if (!fenc->b_intra_calculated && launch_intra_for(la, fenc) < 0) return -1;
+    if (!fenc->b_intra_calculated) {
+        // upstream nests slicetype_frame_cost( fenc, 0, 0, 0 ) here: an intra-only evaluation
+        Frame *one[1] = {fenc};
+        if (frame_cost(la, one, 0, 0, 0, false) < 0) return -1;
+    }
     unsigned origscore, minscore;
     if (weight_score(la, fenc, ref, WeightDev{0, 1, 0, 0}, &origscore) < 0) return -1;
     minscore = origscore;
@@ -351,8 +357,12 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
     la->n_frame_cost++;
     if (p0 == p1) {
         // intra only
-        if (!fenc->b_intra_calculated) { if (launch_intra_for(la, fenc) < 0) return -1; }
-        else { fenc->cost_est[0][0] = 0; fenc->cost_est_aq[0][0] = 0; }      // unreachable through the memo
+        if (!fenc->b_intra_calculated) {
+            if (launch_intra_for(la, fenc) < 0) return -1;
+            // every MB of an intra-only evaluation counts as intra: INTRA_MBS = the scored MBs
+            const bool tiny = la->g.mb_w <= 2 || la->g.mb_h <= 2;
+            fenc->intra_mbs[0] = tiny ? la->g.mb_count : (la->g.mb_w - 2) * (la->g.mb_h - 2);
+        } else { fenc->cost_est[0][0] = 0; fenc->cost_est_aq[0][0] = 0; }    // unreachable through the memo
         if (!need_value) return 0;
         if (la_sync(la) < 0) return -1;
         return fenc->cost_est[0][0];
@@ -459,6 +469,8 @@ static int tree_propagate(La *la, Frame **frames, float average_duration, int p0
     const int dist_scale_factor = (((b - p0) << 8) + ((p1 - p0) >> 1)) / (p1 - p0);
     j.bipred_weight = la->p.weightb ? 64 - (dist_scale_factor >> 2) : 32;
     j.fps_factor = clip_duration(frames[b]->f_duration) / (clip_duration(average_duration) * 256.0f) * MBTREE_PRECISION;
+    // upstream zeroes one row of the unreferenced frame's own array and reads that as its input
+    if (!referenced) LA_CUDA(cudaMemsetAsync(frames[b]->propagate, 0, la->g.mb_w * sizeof(int), la->st));
     j.propagate_in = referenced ? frames[b]->propagate : nullptr;
     j.intra_cost = frames[b]->intra_cost; j.inv_qscale = frames[b]->inv_qscale;
     j.lowres_costs = lc_ptr(la, frames[b], b - p0, p1 - b);

@@ -512,23 +512,24 @@ propagate_kernel(LaGeom g, PropagateJob job)
         if (!mv) { if (listamount) atomicAdd(ref + mb_y * stride + i, listamount); continue; }
         int x = mv_x(mv), y = mv_y(mv);
         const unsigned mbx = (unsigned)((x >> 5) + i), mby = (unsigned)((y >> 5) + mb_y);
+        // unsigned 32-bit index arithmetic on purpose: mbx == -1 wraps so that idx0 + 1 is column 0
         const unsigned idx0 = mbx + mby * stride, idx2 = idx0 + stride;
         x &= 31; y &= 31;
         const int w0 = ((32 - y) * (32 - x) * listamount + 512) >> 10, w1 = ((32 - y) * x * listamount + 512) >> 10;
         const int w2 = (y * (32 - x) * listamount + 512) >> 10, w3 = (y * x * listamount + 512) >> 10;
         if (mbx < width - 1 && mby < height - 1) {
-            if (w0) atomicAdd(ref + idx0, w0);
-            if (w1) atomicAdd(ref + idx0 + 1, w1);
-            if (w2) atomicAdd(ref + idx2, w2);
-            if (w3) atomicAdd(ref + idx2 + 1, w3);
+            if (w0) atomicAdd(&ref[idx0], w0);
+            if (w1) atomicAdd(&ref[idx0 + 1u], w1);
+            if (w2) atomicAdd(&ref[idx2], w2);
+            if (w3) atomicAdd(&ref[idx2 + 1u], w3);
         } else {
             if (mby < height) {
-                if (mbx < width && w0) atomicAdd(ref + idx0, w0);
-                if (mbx + 1 < width && w1) atomicAdd(ref + idx0 + 1, w1);
+                if (mbx < width && w0) atomicAdd(&ref[idx0], w0);
+                if (mbx + 1 < width && w1) atomicAdd(&ref[idx0 + 1u], w1);
             }
             if (mby + 1 < height) {
-                if (mbx < width && w2) atomicAdd(ref + idx2, w2);
-                if (mbx + 1 < width && w3) atomicAdd(ref + idx2 + 1, w3);
+                if (mbx < width && w2) atomicAdd(&ref[idx2], w2);
+                if (mbx + 1 < width && w3) atomicAdd(&ref[idx2 + 1u], w3);
             }
         }
     }
