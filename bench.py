@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p frames/s through csp + lookahead on B200 (BASELINE.json metric).
+
+Workload (config.workload "C5"): per GPU, S concurrent independent 1080p RGB32 bottom-up DIB
+streams, each: BGRA|VFLIP -> I420 (stage 1) -> AQ statistics + lowres planes -> x264 lookahead
+with preset medium (bframes 3, b-adapt 1, rc-lookahead 40, mb-tree, scenecut 40, weightp 2,
+aq-mode 1), one encoder session per stream.  A "step" is one pass of the hot path over one
+batch: every stream consumes F consecutive frames of its synthetic clip and returns the frame
+types / qp offsets decided meanwhile.  Sessions persist across steps (steady state; the
+lookahead window is pre-filled before the warm-up).  N GPUs = N ranks x S streams (weak
+scaling, no collective: streams are independent).
+
+  value : frames/s with the packed inputs already resident in HBM.
+  e2e   : the same through the C-ABI call with HOST (pinned) buffers: H2D of every packed
+          frame and D2H of the converted planes (codec->conv_pic) + decisions inside the timed
+          region.
+  --impl reference : the reference CPU path (reference csp.c object when oracle/_ref exists,
+          plus the CPU restatement of the libx264 lookahead -- libx264 itself is not vendored
+          by the reference) on the host cores, same config, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+PRESET = "medium"
+BGRA_FLIP = 9 | 0x1000
+SRC_BYTES = W * H * 4
+DST_BYTES = W * H * 3 // 2
+CSP_ALGO_BYTES = SRC_BYTES + DST_BYTES          # 11,404,800 B / frame
+LOWRES_ALGO_BYTES = 1920 * 1088 + 4 * 960 * 544   # 4,177,920 B / frame
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=8, help="independent streams per GPU")
+    ap.add_argument("--frames-per-step", type=int, default=16)
+    ap.add_argument("--clip-frames", type=int, default=48)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage1-batch", type=int, default=96, help="frames per launch for the stage-1 roofline probe")
+    return ap.parse_args()
+
+
+def make_clips(n_streams, n_frames, first_stream):
+    """Per-stream packed BGRA clips (numpy, host)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from x264vfw_b200.clipgen import SyntheticClip
+
+    def one(s):
+        clip = SyntheticClip(W, H, n_frames=n_frames, stream_id=first_stream + s, cuts=(n_frames * 5 // 8,), flash=n_frames // 4, flash_len=1)
+        return [clip.packed(n, "bgra") for n in range(n_frames)]
+
+    with ThreadPoolExecutor(max_workers=min(8, n_streams)) as ex:
+        return list(ex.map(one, range(n_streams)))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.sm_max = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=10)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+class StreamWorker(threading.Thread):
+    """One host thread per stream (the reference calls the path on the app thread, codec.c:1728)."""
+
+    def __init__(self, la, frames, on_device, conv_bufs, barrier_in, barrier_out, frames_per_step):
+        super().__init__(daemon=True)
+        self.la, self.frames, self.on_device, self.conv = la, frames, on_device, conv_bufs
+        self.bin, self.bout, self.F = barrier_in, barrier_out, frames_per_step
+        self.pos = 0
+        self.decided = 0
+        self.stop_flag = False
+        self.error = None
+
+    def feed(self, n):
+        for _ in range(n):
+            k = self.pos % len(self.frames)
+            conv = self.conv[self.pos % len(self.conv)] if self.conv else None
+            self.la.put_frame(self.frames[k], on_device=self.on_device, conv_pic=conv)
+            self.decided += len(self.la.decisions(with_offsets=True))
+            self.pos += 1
+
+    def run(self):
+        while True:
+            self.bin.wait()
+            if self.stop_flag:
+                return
+            try:
+                self.feed(self.F)
+            except Exception as e:          # surface, do not hang the barrier
+                self.error = e
+            self.bout.wait()
+
+
+def run_phase(torch, dist, sessions, frames, on_device, conv, args, rank, world, sampler_index, profile=False):
+    """Prefill + warm-up + timed steps.  Returns (ms_per_step_max_over_ranks, clocks, launches, prof)."""
+    import x264vfw_b200 as xv
+    S, F = len(sessions), args.frames_per_step
+    bin_, bout = threading.Barrier(S + 1), threading.Barrier(S + 1)
+    workers = [StreamWorker(sessions[s], frames[s], on_device, conv[s] if conv else None, bin_, bout, F) for s in range(S)]
+    for wkr in workers:
+        wkr.start()
+
+    def step():
+        bin_.wait()
+        bout.wait()
+        for wkr in workers:
+            if wkr.error:
+                raise wkr.error
+
+    # prefill the lookahead window (rc-lookahead 40 + bframes) so that timed steps are steady state
+    prefill = -(-(sessions[0].p.rc_lookahead + sessions[0].p.bframes + 2) // F)
+    for _ in range(prefill):
+        step()
+    for _ in range(args.warmup):
+        step()
+    if profile:
+        for la in sessions:
+            la.profile(1)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(sampler_index)
+    sampler.start()
+    n0 = xv.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    e1.record()
+    e1.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = xv.launch_count() - n0
+    clocks = sampler.stop()
+    prof = None
+    if profile:
+        prof = {}
+        for la in sessions:
+            for k, (t, n) in la.profile(0).items():
+                a = prof.setdefault(k, [0.0, 0])
+                a[0] += t
+                a[1] += n
+    for wkr in workers:
+        wkr.stop_flag = True
+    bin_.wait()
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        l = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(l, op=dist.ReduceOp.SUM)
+        launches = int(l.item())
+    return ms / args.steps, clocks, launches, prof
+
+
+def stage1_roofline(torch, args):
+    """Device-resident batch launches of the stage-1 kernels (the HBM-bound part of the path):
+    CUDA events on the launching stream, inputs larger than L2."""
+    import x264vfw_b200 as xv
+    from x264vfw_b200 import csp, lowres
+    ctx = xv._lib.Context(torch.cuda.current_device())
+    st = torch.cuda.ExternalStream(ctx.stream)
+    nf = args.stage1_batch
+    sfb, dfb = csp.frame_bytes(BGRA_FLIP, 2, W, H)
+    src = torch.randint(0, 256, (nf * sfb,), dtype=torch.uint8, device="cuda")
+    dst = torch.empty(nf * dfb, dtype=torch.uint8, device="cuda")
+    g = lowres.geometry(W, H)
+    lr = torch.empty(nf * 4 * g.lplane_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        ctx.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(iters):
+            fn()
+        b.record(st)
+        b.synchronize()
+        return a.elapsed_time(b) / iters * 1e-3
+
+    t_csp = timeit(lambda: csp.convert_batch(ctx, src.data_ptr(), dst.data_ptr(), BGRA_FLIP, 2, 2, 0, W, H, nf))
+    t_lr = timeit(lambda: lowres.lowres_init(ctx, lr.data_ptr(), dst.data_ptr(), W, W, H, dfb, 4 * g.lplane_bytes, nf))
+    ctx.close()
+    return {"csp_bgra_to_i420": {"frames_per_launch": nf, "ms_per_launch": t_csp * 1e3, "gbs": CSP_ALGO_BYTES * nf / t_csp / 1e9},
+            "lowres_init": {"frames_per_launch": nf, "ms_per_launch": t_lr * 1e3, "gbs": LOWRES_ALGO_BYTES * nf / t_lr / 1e9}}
+
+
+def cpu_reference_run(n_streams, frames_per_stream, clips):
+    """The reference CPU path on host cores: reference csp.c object (oracle/_ref) when present,
+    else the csp port; then the CPU restatement of the libx264 lookahead.  One thread per
+    stream (codec.c:1774 runs on the app thread).  Returns (frames, seconds, kind, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    kind = "reference+port" if ol.have_ref_csp() else "port"
+    conv = ol.ref_convert if ol.have_ref_csp() else ol.oracle_convert
+    ol.oracle()
+    ol.la_params(PRESET, W, H)          # build tables before threading
+    done = [0] * n_streams
+
+    def work(s):
+        la = ol.OracleLookahead(ol.la_params(PRESET, W, H))
+        for n in range(frames_per_stream):
+            planes = conv(clips[s][n % len(clips[s])], BGRA_FLIP, 2, 2, 0, W, H)
+            la.put_i420(planes)
+            done[s] += len(la.decisions())
+        la.flush()
+        done[s] += len(la.decisions())
+        la.close()
+
+    ths = [threading.Thread(target=work, args=(s,)) for s in range(n_streams)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    assert all(d == frames_per_stream for d in done)
+    return n_streams * frames_per_stream, dt, kind, n_streams
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True)
+    cores = os.cpu_count() or 1
+    n_streams = max(1, min(cores, args.streams * max(1, args.gpus)))
+    fps_list = []
+    clips = make_clips(min(n_streams, 8), 12, 0)
+    clips = [clips[i % len(clips)] for i in range(n_streams)]
+    frames_per_stream = 12
+    total_steps = args.warmup + args.steps
+    t_all = []
+    for i in range(total_steps):
+        nfr, dt, kind, used = cpu_reference_run(n_streams, frames_per_stream, clips)
+        if i >= args.warmup:
+            t_all.append(dt)
+            fps_list.append(nfr / dt)
+    fps = sum(fps_list) / len(fps_list)
+    sample = (f"{n_streams} streams x {frames_per_stream} frames of the C5 clip per step, one thread per stream on {cores} host cores; "
+              f"stage 1 = {'unmodified reference csp.c (oracle/_ref)' if 'reference' in kind else 'csp port'}, "
+              "stage 2 = CPU restatement of the libx264 lookahead, scalar C, no asm -- not libx264")
+    line = {"impl": "reference", "metric": "1080p frames/sec through csp+lookahead", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_all) / len(t_all),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C5: 1080p RGB32 bottom-up DIB -> I420 + x264 lookahead preset medium, independent streams",
+                       "preset": PRESET, "width": W, "height": H, "streams": n_streams, "frames_per_step": frames_per_stream},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": n_streams, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+    import torch
+    import x264vfw_b200 as xv
+    from x264vfw_b200 import csp, lookahead
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    n_gpus = world
+    S, F = args.streams, args.frames_per_step
+
+    clips = make_clips(S, args.clip_frames, rank * S)
+    # device-resident copies (value) and pinned host copies (e2e)
+    dev_frames = [[torch.from_numpy(f).cuda() for f in clip] for clip in clips]
+    dev_ptrs = [[t.data_ptr() for t in clip] for clip in dev_frames]
+    torch.cuda.synchronize()
+
+    def open_sessions():
+        return [lookahead.Lookahead(lookahead.params_preset(PRESET, W, H), in_csp=BGRA_FLIP, out_csp=csp.X264_CSP_I420,
+                                    colmatrix=2, fullrange=0, device=local_rank) for _ in range(S)]
+
+    sessions = open_sessions()
+    ms_step, clocks, launches, prof = run_phase(torch, dist, sessions, dev_ptrs, True, None, args, rank, world, local_rank, profile=True)
+    for la in sessions:
+        la.close()
+    frames_per_step_all = S * F * n_gpus
+    value = frames_per_step_all / (ms_step * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        pin_frames = [[torch.from_numpy(f).pin_memory().numpy() for f in clip] for clip in clips]
+        conv = [[torch.empty(DST_BYTES, dtype=torch.uint8).pin_memory().numpy() for _ in range(4)] for _ in range(S)]
+        sessions = open_sessions()
+        ms_e2e, _, _, _ = run_phase(torch, dist, sessions, pin_frames, False, conv, args, rank, world, local_rank)
+        for la in sessions:
+            la.close()
+        mb = sessions[0].mb_count
+        e2e = {"value": frames_per_step_all / (ms_e2e * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": S * F * SRC_BYTES, "d2h_bytes_per_step": S * F * (DST_BYTES + 2 * 4 * mb + 32),
+               "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    stage1 = stage1_roofline(torch, args)
+    # dominant kernel of the step by device time
+    tot = sum(v[0] for v in prof.values()) or 1.0
+    shares = {k: {"ms": v[0], "launches": v[1], "share": v[0] / tot} for k, v in prof.items()}
+    dom = max(prof, key=lambda k: prof[k][0])
+    geom_mb = 120 * 68
+    # algorithmic bytes of one search launch: fenc plane + 4 ref planes + per-MB mv/cost
+    me_bytes_per_search = 960 * 544 * 5 + geom_mb * 8
+    me_ms, me_n = prof["me"]
+    me_avg = me_ms / max(1, me_n)
+    roofline = {"kernel": "me_wavefront_kernel (lowres motion search; latency-bound wavefront on the integer pipe, see DESIGN.md)",
+                "bound": "hbm", "achieved": (me_bytes_per_search * 1.5 / (me_avg * 1e-3) / 1e9) if me_n else None,
+                "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": me_avg, "launches": me_n, "share_of_step_device_time": shares["me"]["share"],
+                "note": "dominant kernel by device time; its bound is neither HBM nor tensor (SURVEY 8(d)): "
+                        "algorithmic traffic is ~2.7 MB per search. The HBM-bound kernels of the path are reported in stage1."}
+    if roofline["achieved"] is not None:
+        roofline["frac"] = roofline["achieved"] / hbm_peak
+    for k in stage1:
+        stage1[k]["frac"] = stage1[k]["gbs"] / hbm_peak
+        stage1[k]["peak"] = hbm_peak
+        stage1[k]["bound"] = "hbm"
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True)
+        cores = os.cpu_count() or 1
+        ns = max(1, min(cores, 8))
+        nfr, dt, kind, used = cpu_reference_run(ns, 12, [c[:12] for c in clips[:ns]] if ns <= len(clips) else [clips[i % len(clips)][:12] for i in range(ns)])
+        cpu_baseline = {"value": nfr / dt, "unit": "frames/s", "cores": used, "kind": "port",
+                        "sample": f"{ns} streams x 12 frames of the same C5 clips, one thread per stream, {cores} host cores available; "
+                                  f"stage 1 = {'unmodified reference csp.c (oracle/_ref)' if 'reference' in kind else 'csp port'}, "
+                                  "stage 2 = CPU restatement of the libx264 lookahead (scalar C, no asm; libx264 is not vendored by the reference)"}
+
+    line = {"metric": "1080p frames/sec through csp+lookahead", "value": value, "unit": "frames/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C5: 1080p RGB32 bottom-up DIB -> I420 + x264 lookahead preset medium, independent streams, one session per stream",
+                       "preset": PRESET, "width": W, "height": H, "streams_per_gpu": S, "frames_per_step_per_stream": F,
+                       "rc_lookahead": 40, "bframes": 3, "b_adapt": 1, "mbtree": 1, "weightp": 2, "aq_mode": 1,
+                       "l2_policy": f"inputs larger than L2: {S * F * SRC_BYTES / 1e6:.0f} MB of packed frames per step per GPU"},
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "stage1": stage1,
+            "kernel_shares": shares, "dominant_kernel_class": dom, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

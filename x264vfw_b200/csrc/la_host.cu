@@ -71,6 +71,18 @@ struct Frame {
 
 struct PendingResult { Frame *f; int d0, d1; int slot; bool is_b; bool intra; };
 
+// Optional per-kernel-class device timing: CUDA events recorded on the session's stream around
+// each launch, resolved at the next synchronisation (bench.py reads the totals).
+enum KClass { K_CSP, K_AQ, K_LOWRES, K_INTRA, K_ME, K_FINALIZE, K_WEIGHT, K_TREE, K_N };
+struct ProfRec { int cls; cudaEvent_t a, b; };
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    std::vector<ProfRec> recs;
+    double ms[K_N] = {0};
+    uint64_t n[K_N] = {0};
+};
+
 struct Decision {
     x264vfw_cuda_la_decision d;
     Frame *f;
@@ -109,6 +121,7 @@ struct La {
     int n_input = 0;
     uint64_t n_frame_cost = 0, n_mb_search = 0, n_launch = 0, n_sync = 0;
     bool fail = false;   // set when a device call fails inside the value-returning helpers
+    Prof prof;
 };
 
 static const int RESULT_SLOTS = 1024;
@@ -116,6 +129,28 @@ static const int RESULT_SLOTS = 1024;
 #define LA_CUDA(expr) XV_CUDA_OK(expr)
 
 static int la_sync(La *la);
+
+static cudaEvent_t prof_event(La *la)
+{
+    if (!la->prof.pool.empty()) { cudaEvent_t e = la->prof.pool.back(); la->prof.pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    La *la; int cls; cudaEvent_t a = nullptr;
+    ProfScope(La *l, int c) : la(l), cls(c) { if (la->prof.on) { a = prof_event(la); cudaEventRecord(a, la->st); } }
+    ~ProfScope() { if (a) { cudaEvent_t b = prof_event(la); cudaEventRecord(b, la->st); la->prof.recs.push_back(ProfRec{cls, a, b}); } }
+};
+static void prof_resolve(La *la)
+{
+    for (const ProfRec &r : la->prof.recs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { la->prof.ms[r.cls] += ms; la->prof.n[r.cls]++; }
+        la->prof.pool.push_back(r.a); la->prof.pool.push_back(r.b);
+    }
+    la->prof.recs.clear();
+}
 
 // ------------------------------------------------------------------------------------------
 // frame slots
@@ -216,6 +251,7 @@ static int la_sync(La *la)
         LA_CUDA(cudaMemcpyAsync(la->h_results, la->d_results, RESULT_SLOTS * 4 * sizeof(int), cudaMemcpyDeviceToHost, la->st));
     LA_CUDA(cudaStreamSynchronize(la->st));
     la->n_sync++;
+    if (!la->prof.recs.empty()) prof_resolve(la);
     for (const PendingResult &r : la->pending) {
         const int *v = la->h_results + r.slot * 4;
         Frame *f = r.f;
@@ -256,14 +292,14 @@ static int launch_intra_for(La *la, Frame *fenc)
 {
     IntraJob ij;
     ij.plane0 = plane_org(la, fenc, 0); ij.intra_cost = fenc->intra_cost; ij.full = la->p.subme > 1; ij.satd = la->la_satd;
-    if (launch_intra(la->st, la->g, ij, la->do_edges) < 0) return -1;
+    { ProfScope ps(la, K_INTRA); if (launch_intra(la->st, la->g, ij, la->do_edges) < 0) return -1; }
     const int slot = result_slot(la);
     if (slot < 0) return -1;
     LA_CUDA(cudaMemsetAsync(la->d_results + slot * 4, 0, 4 * sizeof(int), la->st));
     IntraSumJob sj;
     sj.intra_cost = fenc->intra_cost; sj.inv_qscale = fenc->inv_qscale; sj.aq_on = la->p.aq_mode != 0;
     sj.result = la->d_results + slot * 4; sj.row_satd = nullptr;
-    if (launch_intra_sum(la->st, la->g, sj) < 0) return -1;
+    { ProfScope ps(la, K_INTRA); if (launch_intra_sum(la->st, la->g, sj) < 0) return -1; }
     la->n_launch += 2;
     la->pending.push_back(PendingResult{fenc, 0, 0, slot, false, true});
     fenc->cost_est[0][0] = PENDING; fenc->cost_est_aq[0][0] = PENDING;
@@ -282,7 +318,7 @@ static int weight_score(La *la, Frame *fenc, Frame *ref, const WeightDev &w, uns
     WeightCostJob j;
     j.fenc = plane_org(la, fenc, 0); j.ref = plane_org(la, ref, 0); j.intra_cost = fenc->intra_cost;
     j.w = w; j.satd = la->la_satd; j.result = la->d_wscore;
-    if (launch_weight_cost(la->st, la->g, j) < 0) return -1;
+    { ProfScope ps(la, K_WEIGHT); if (launch_weight_cost(la->st, la->g, j) < 0) return -1; }
     la->n_launch++;
     LA_CUDA(cudaMemcpyAsync(la->h_wscore, la->d_wscore, sizeof(unsigned), cudaMemcpyDeviceToHost, la->st));
     if (la_sync(la) < 0) return -1;
@@ -337,7 +373,7 @@ static int weights_analyse(La *la, Frame *fenc, Frame *ref)
     if (!found || (minscale == 1 << mindenom && minoff == 0) || (float)minscore / origscore > 0.998f) return 0;
     fenc->weight = WeightDev{1, minscale, mindenom, minoff};
     // x264_weight_scale_plane: the whole padded plane 0 of the reference
-    if (launch_weight_plane(la->st, la->g, la->d_weight_buf, ref->lowres, fenc->weight) < 0) return -1;
+    { ProfScope ps(la, K_WEIGHT); if (launch_weight_plane(la->st, la->g, la->d_weight_buf, ref->lowres, fenc->weight) < 0) return -1; }
     la->n_launch++;
     return 0;
 }
@@ -410,7 +446,7 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
         const size_t words = (size_t)mp.njobs * (1 + la->g.mb_h);
         LA_CUDA(cudaMemsetAsync(la->d_sync, 0x7f, words * sizeof(int), la->st));
         for (int k = 0; k < mp.njobs; k++) LA_CUDA(cudaMemsetAsync(la->d_sync + k * (1 + la->g.mb_h), 0, sizeof(int), la->st));
-        if (launch_me(la->st, la->g, mp) < 0) return -1;
+        { ProfScope ps(la, K_ME); if (launch_me(la->st, la->g, mp) < 0) return -1; }
         la->n_launch++;
     }
 
@@ -433,7 +469,7 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
     fj.bipred_weight = la->p.weightb ? 64 - (dist_scale_factor >> 2) : 32;
     fj.aq_on = la->p.aq_mode != 0; fj.subme_gt1 = la->p.subme > 1; fj.satd = la->la_satd;
     fj.mv_range2 = 2 * la->p.mv_range; fj.do_edges = la->do_edges;
-    if (launch_finalize(la->st, la->g, fj) < 0) return -1;
+    { ProfScope ps(la, K_FINALIZE); if (launch_finalize(la->st, la->g, fj) < 0) return -1; }
     la->n_launch++;
     la->pending.push_back(PendingResult{fenc, d0, d1, slot, b != p1, false});
     fenc->cost_est[d0][d1] = PENDING; fenc->cost_est_aq[d0][d1] = PENDING;
@@ -460,6 +496,7 @@ static int tree_finish(La *la, Frame *frame, float average_duration, int ref0_di
     j.propagate = frame->propagate; j.intra_cost = frame->intra_cost; j.inv_qscale = frame->inv_qscale;
     j.qp_offset_aq = frame->qp_offset_aq; j.qp_offset = frame->qp_offset; j.log2_lut = la->d_log2_lut;
     la->n_launch++;
+    ProfScope ps(la, K_TREE);
     return launch_tree_finish(la->st, la->g, j);
 }
 
@@ -479,6 +516,7 @@ static int tree_propagate(La *la, Frame **frames, float average_duration, int p0
     j.ref0_cost = frames[p0]->propagate; j.ref1_cost = frames[p1]->propagate;
     j.b_bidir = b != p1;
     la->n_launch++;
+    ProfScope ps(la, K_TREE);
     return launch_propagate(la->st, la->g, j);
 }
 
@@ -1003,6 +1041,8 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     if (!la) return;
     cudaSetDevice(la->device);
     if (la->st) cudaStreamSynchronize(la->st);
+    prof_resolve(la);
+    for (cudaEvent_t e : la->prof.pool) cudaEventDestroy(e);
     for (Frame *f : la->pool) frame_free(f);
     for (Decision &d : la->outq) if (d.h_qp) cudaFreeHost(d.h_qp);
     for (float *q : la->qp_free) cudaFreeHost(q);
@@ -1055,7 +1095,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
                 XV_CUDA_OK(cudaMemcpyAsync(dsrc.plane[i], src->plane[i], (size_t)src->i_stride[i] * rows, cudaMemcpyHostToDevice, la->st));
             }
         }
-        if (convert_device_public(la->st, la->out_csp, la->colmatrix, la->fullrange, X264VFW_CUDA_EXT_NONE, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1;
+        { ProfScope ps(la, K_CSP); if (convert_device_public(la->st, la->out_csp, la->colmatrix, la->fullrange, X264VFW_CUDA_EXT_NONE, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
         la->n_launch++;
     }
     if (conv_pic) {
@@ -1082,7 +1122,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     aq.aq_on = aq_on; aq.strength = la->p.aq_strength * 1.0397f;
     aq.qp_offset = f->qp_offset; aq.qp_offset_aq = f->qp_offset_aq; aq.inv_qscale = f->inv_qscale;
     aq.stats = f->stats; aq.log2_lut = la->d_log2_lut; aq.exp2_lut = la->d_exp2_lut;
-    if (launch_aq(la->st, la->g, aq) < 0) return -1;
+    { ProfScope ps(la, K_AQ); if (launch_aq(la->st, la->g, aq) < 0) return -1; }
     XV_CUDA_OK(cudaMemcpyAsync(f->h_stats, f->stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, la->st));
 
     // [x264] x264_frame_init_lowres
@@ -1091,7 +1131,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     lj.luma_w = la->g.luma_w; lj.luma_h = la->g.luma_h; lj.lw = la->g.lw; lj.lh = la->g.lh;
     lj.lstride = la->g.lstride; lj.lplane_bytes = la->g.lplane; lj.lorigin = la->g.lorigin;
     lj.src_frame_bytes = 0; lj.dst_frame_bytes = 0;
-    if (launch_lowres_init(la->st, lj, 1) < 0) return -1;
+    { ProfScope ps(la, K_LOWRES); if (launch_lowres_init(la->st, lj, 1) < 0) return -1; }
     la->n_launch += 2;
 
     la->next.push_back(f);      // [x264] x264_lookahead_put_frame
@@ -1192,6 +1232,20 @@ int64_t x264vfw_cuda_la_read(x264vfw_cuda_la *h, int frame, int what, int a, int
     if (host) memcpy(dst, src, bytes);
     else XV_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     return (int64_t)bytes;
+}
+
+int x264vfw_cuda_la_profile(x264vfw_cuda_la *h, int enable, double ms[8], uint64_t count[8])
+{
+    La *la = (La *)h;
+    if (!la) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    if (la_sync(la) < 0) return -1;
+    for (int i = 0; i < K_N; i++) { if (ms) ms[i] = la->prof.ms[i]; if (count) count[i] = la->prof.n[i]; }
+    if (enable >= 0) {
+        la->prof.on = enable != 0;
+        for (int i = 0; i < K_N; i++) { la->prof.ms[i] = 0; la->prof.n[i] = 0; }
+    }
+    return 0;
 }
 
 void x264vfw_cuda_la_counters(x264vfw_cuda_la *h, uint64_t out[4])

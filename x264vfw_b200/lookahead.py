@@ -55,6 +55,11 @@ lib.x264vfw_cuda_la_counters.restype = None
 lib.x264vfw_cuda_la_counters.argtypes = [C.c_void_p, _P(C.c_uint64)]
 
 
+lib.x264vfw_cuda_la_profile.restype = C.c_int
+lib.x264vfw_cuda_la_profile.argtypes = [C.c_void_p, C.c_int, _P(C.c_double), _P(C.c_uint64)]
+KERNEL_CLASSES = ("csp", "aq", "lowres", "intra", "me", "finalize", "weights", "mbtree")
+
+
 def params_preset(preset: str, width: int, height: int, **over) -> LaParams:
     """x264_param_default_preset (codec.c:1463) reduced to the lookahead's fields; keyword
     overrides play the role of the extra command line (codec.c:1349)."""
@@ -181,6 +186,13 @@ class Lookahead:
         return dict(scale=int(v[0]), denom=int(v[1]), offset=int(v[2]), on=int(v[3]))
     def lowres_planes(self, f, nbytes): return self.read(f, LA_LOWRES, dtype=np.uint8, count=nbytes)
     def conv_planes(self, nbytes): return self.read(0, LA_CONV_PLANES, dtype=np.uint8, count=nbytes)
+
+    def profile(self, enable: int = -1):
+        """Per-kernel-class device time (ms) and launch counts since the last reset."""
+        ms, n = (C.c_double * 8)(), (C.c_uint64 * 8)()
+        if lib.x264vfw_cuda_la_profile(self.h, enable, ms, n) < 0:
+            raise CudaError(last_error())
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
 
     def counters(self):
         c = (C.c_uint64 * 4)()
