@@ -49,7 +49,8 @@ struct Frame {
     int i_frame = 0, i_type = T_AUTO, i_forced_type = T_AUTO, b_scenecut = 1, b_keyframe = 0, i_bframes = 0;
     float f_duration = 0;
     int cost_est[BMAX + 2][BMAX + 2], cost_est_aq[BMAX + 2][BMAX + 2], intra_mbs[BMAX + 2];
-    bool searched[2][BMAX + 1];
+    bool searched[2][BMAX + 1];            // logical: what upstream's 0x7FFF sentinel would say
+    bool spec[2][BMAX + 1];                // device arrays already hold the (unweighted) search result
     bool b_intra_calculated = false;
     bool stats_ready = false;
     unsigned long long pixel_sum[3], pixel_ssd[3];
@@ -95,6 +96,7 @@ struct La {
     int device;
     cudaStream_t st;
     int in_csp, out_csp, colmatrix, fullrange, keep_frames;
+    int speculate = 1;
     int la_me_hex, la_subpel_refine, la_satd, do_edges;
     int slicetype_length, i_last_keyframe;
     // tables
@@ -105,7 +107,8 @@ struct La {
     uint8_t *d_planes = nullptr; size_t d_planes_bytes = 0; // converted planes (tight)
     x264vfw_cuda_image_t planes_img;
     uint8_t *d_weight_buf = nullptr;
-    int *d_sync = nullptr;                                  // 2 x (1 + mb_h)
+    int2 *d_rec = nullptr; int *d_ticket = nullptr;         // ME inter-row records / row tickets, per job
+    int me_epoch = 0;
     int *d_results = nullptr; int *h_results = nullptr;     // ring of 4-int slots
     int result_head = 0;
     unsigned *d_wscore = nullptr; unsigned *h_wscore = nullptr;
@@ -194,6 +197,7 @@ static int frame_reset(La *la, Frame *f, int i_frame)
     f->f_duration = 0;
     for (int a = 0; a < BMAX + 2; a++) { f->intra_mbs[a] = 0; f->weighted_cost_delta[a] = 0; for (int b = 0; b < BMAX + 2; b++) f->cost_est[a][b] = f->cost_est_aq[a][b] = -1; }
     memset(f->searched, 0, sizeof(f->searched));
+    memset(f->spec, 0, sizeof(f->spec));
     f->b_intra_calculated = false; f->stats_ready = false;
     f->weight = WeightDev{0, 1, 0, 0};
     f->rc_d0 = f->rc_d1 = -1;
@@ -378,6 +382,70 @@ static int weights_analyse(La *la, Frame *fenc, Frame *ref)
     return 0;
 }
 
+static void me_params_init(La *la, MeParams &mp)
+{
+    memset(&mp, 0, sizeof(mp));
+    mp.bands = la->p.lookahead_threads > 0 ? la->p.lookahead_threads : 1;
+    mp.do_edges = la->do_edges; mp.mv_range2 = 2 * la->p.mv_range; mp.me_hex = la->la_me_hex;
+    mp.subpel_refine = la->la_subpel_refine; mp.satd = la->la_satd; mp.me_range = la->p.me_range;
+    mp.cost_mv = la->d_cost_mv + la->cost_mv_half;
+}
+
+static void me_add_job(La *la, MeParams &mp, Frame *fenc, Frame *ref, int list, int dist, const WeightDev *w)
+{
+    MeJob &j = mp.job[mp.njobs];
+    j.fenc = plane_org(la, fenc, 0);
+    for (int k = 0; k < 4; k++) j.fref[k] = plane_org(la, ref, k);
+    j.fref_w = j.fref[0];
+    j.w = WeightDev{0, 1, 0, 0};
+    if (w) { j.w = *w; j.fref_w = la->d_weight_buf + la->g.lorigin; }
+    j.mvs = fenc->mvs[list][dist - 1];
+    j.mv_costs = fenc->mv_costs[list][dist - 1];
+    j.rec = la->d_rec + (size_t)mp.njobs * la->g.mb_count;
+    j.ticket = la->d_ticket + mp.njobs;
+    mp.njobs++;
+    la->n_mb_search += la->g.mb_count;
+}
+
+static int me_launch(La *la, MeParams &mp)
+{
+    if (!mp.njobs) return 0;
+    LA_CUDA(cudaMemsetAsync(la->d_ticket, 0, XV_ME_MAX_JOBS * sizeof(int), la->st));
+    mp.epoch = ++la->me_epoch;
+    { ProfScope ps(la, K_ME); if (launch_me(la->st, la->g, mp) < 0) return -1; }
+    la->n_launch++;
+    return 0;
+}
+
+// Speculative searches at put time: frame n just arrived, so every (frame, list, distance)
+// pair whose reference is n (list 1 of n-1..n-B) or whose frame is n (list 0 towards
+// n-1..n-B-1) can be searched now, all in ONE launch.  Search results do not depend on when
+// they are computed (each (list,distance) array only reads itself); whether and when upstream
+// would have run them stays tracked by the logical `searched` flags.
+static int speculate_searches(La *la, Frame *fn)
+{
+    if (!la->speculate) return 0;
+    const int n = fn->i_frame, B = la->p.bframes;
+    MeParams mp;
+    me_params_init(la, mp);
+    auto alive = [&](int i) -> Frame * { return (i >= 0 && i < (int)la->by_index.size()) ? la->by_index[i] : nullptr; };
+    auto add = [&](Frame *fenc, Frame *ref, int list, int d) -> int {
+        me_add_job(la, mp, fenc, ref, list, d, nullptr);
+        fenc->spec[list][d - 1] = true;
+        if (mp.njobs == XV_ME_MAX_JOBS) { if (me_launch(la, mp) < 0) return -1; me_params_init(la, mp); }
+        return 0;
+    };
+    for (int d = 1; d <= B + 1; d++) {
+        Frame *ref = alive(n - d);
+        if (ref && !fn->spec[0][d - 1] && add(fn, ref, 0, d) < 0) return -1;
+    }
+    for (int d = 1; d <= B; d++) {
+        Frame *b = alive(n - d);
+        if (b && !b->spec[1][d - 1] && add(b, fn, 1, d) < 0) return -1;
+    }
+    return me_launch(la, mp);
+}
+
 // Enqueues everything slicetype_frame_cost(p0,p1,b) computes.  need_value: synchronise and
 // return the score; otherwise return 0 and leave the result pending.
 static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_value)
@@ -421,33 +489,20 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
     if (!fenc->b_intra_calculated && launch_intra_for(la, fenc) < 0) return -1;
 
     // ---- searches (wavefront kernel; both lists of a B evaluation share the launch) ----
-    MeParams mp;
-    memset(&mp, 0, sizeof(mp));
-    mp.bands = la->p.lookahead_threads > 0 ? la->p.lookahead_threads : 1;
-    mp.do_edges = la->do_edges; mp.mv_range2 = 2 * la->p.mv_range; mp.me_hex = la->la_me_hex;
-    mp.subpel_refine = la->la_subpel_refine; mp.satd = la->la_satd; mp.me_range = la->p.me_range;
-    mp.cost_mv = la->d_cost_mv + la->cost_mv_half;
-    for (int l = 0; l < 2; l++) {
-        if (!do_search[l]) continue;
-        MeJob &j = mp.job[mp.njobs];
-        Frame *ref = l ? fref1 : fref0;
-        j.fenc = plane_org(la, fenc, 0);
-        for (int k = 0; k < 4; k++) j.fref[k] = plane_org(la, ref, k);
-        j.fref_w = j.fref[0];
-        j.w = WeightDev{0, 1, 0, 0};
-        if (l == 0 && w.on) { j.w = w; j.fref_w = la->d_weight_buf + la->g.lorigin; }
-        j.mvs = l ? fenc->mvs[1][d1 - 1] : fenc->mvs[0][d0 - 1];
-        j.mv_costs = l ? fenc->mv_costs[1][d1 - 1] : fenc->mv_costs[0][d0 - 1];
-        j.sync = la->d_sync + mp.njobs * (1 + la->g.mb_h);
-        mp.njobs++;
-        la->n_mb_search += la->g.mb_count;
-    }
-    if (mp.njobs) {
-        const size_t words = (size_t)mp.njobs * (1 + la->g.mb_h);
-        LA_CUDA(cudaMemsetAsync(la->d_sync, 0x7f, words * sizeof(int), la->st));
-        for (int k = 0; k < mp.njobs; k++) LA_CUDA(cudaMemsetAsync(la->d_sync + k * (1 + la->g.mb_h), 0, sizeof(int), la->st));
-        { ProfScope ps(la, K_ME); if (launch_me(la->st, la->g, mp) < 0) return -1; }
-        la->n_launch++;
+    // A list whose unweighted result was already produced speculatively at put time is not
+    // searched again; a weighted P search always runs (it differs from the speculative one).
+    {
+        MeParams mp;
+        me_params_init(la, mp);
+        for (int l = 0; l < 2; l++) {
+            if (!do_search[l]) continue;
+            const int dist = l ? d1 : d0;
+            const bool weighted = l == 0 && w.on;
+            if (fenc->spec[l][dist - 1] && !weighted) continue;
+            me_add_job(la, mp, fenc, l ? fref1 : fref0, l, dist, weighted ? &w : nullptr);
+            if (!weighted) fenc->spec[l][dist - 1] = true;
+        }
+        if (me_launch(la, mp) < 0) return -1;
     }
 
     // ---- per-MB selection + accumulators ----
@@ -1017,7 +1072,9 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
                   cudaMemcpy(la->d_log2_lut, l2, sizeof(l2), cudaMemcpyHostToDevice) == cudaSuccess &&
                   cudaMemcpy(la->d_exp2_lut, e2, 64, cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&la->d_weight_buf, g.lplane + 64) == cudaSuccess &&
-             cudaMalloc((void **)&la->d_sync, 2 * (1 + g.mb_h) * sizeof(int)) == cudaSuccess &&
+             cudaMalloc((void **)&la->d_rec, (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
+             cudaMemset(la->d_rec, 0, (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
+             cudaMalloc((void **)&la->d_ticket, XV_ME_MAX_JOBS * sizeof(int)) == cudaSuccess &&
              cudaMalloc((void **)&la->d_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMallocHost((void **)&la->h_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMalloc((void **)&la->d_wscore, 64) == cudaSuccess &&
@@ -1047,7 +1104,7 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     for (Decision &d : la->outq) if (d.h_qp) cudaFreeHost(d.h_qp);
     for (float *q : la->qp_free) cudaFreeHost(q);
     cudaFree(la->d_cost_mv); cudaFree(la->d_log2_lut); cudaFree(la->d_exp2_lut); cudaFree(la->d_weight_buf);
-    cudaFree(la->d_sync); cudaFree(la->d_results); cudaFree(la->d_wscore); cudaFree(la->d_planes); cudaFree(la->d_src);
+    cudaFree(la->d_rec); cudaFree(la->d_ticket); cudaFree(la->d_results); cudaFree(la->d_wscore); cudaFree(la->d_planes); cudaFree(la->d_src);
     if (la->h_results) cudaFreeHost(la->h_results);
     if (la->h_wscore) cudaFreeHost(la->h_wscore);
     if (la->st) cudaStreamDestroy(la->st);
@@ -1134,6 +1191,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     { ProfScope ps(la, K_LOWRES); if (launch_lowres_init(la->st, lj, 1) < 0) return -1; }
     la->n_launch += 2;
 
+    if (speculate_searches(la, f) < 0) return -1;
     la->next.push_back(f);      // [x264] x264_lookahead_put_frame
     while ((int)la->next.size() > la->slicetype_length)
         if (decide_and_shift(la) < 0) return -1;

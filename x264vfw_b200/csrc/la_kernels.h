@@ -43,11 +43,14 @@ struct MeJob {
     WeightDev w;
     int *mvs;                     // packed int16x2 per MB (x | y<<16)
     int *mv_costs;
-    int *sync;                    // [0] = ticket, [1..mb_h] = per-row progress
+    int2 *rec;                    // per-MB {mv, epoch} records: the inter-row channel of this launch
+    int *ticket;                  // row hand-out counter (zeroed by the launcher)
 };
+#define XV_ME_MAX_JOBS 8
 struct MeParams {
     int njobs;
-    MeJob job[2];
+    int epoch;                    // unique per launch; a record is valid iff its tag equals it
+    MeJob job[XV_ME_MAX_JOBS];
     int bands;                    // lookahead_threads
     int do_edges;
     int mv_range2;                // 2 * analyse.i_mv_range

@@ -8,48 +8,66 @@
 //   diamond, on SAD) and refine_subpel (half-pel diamond on SAD, SATD re-score, quarter-pel
 //   diamond on SATD).  Ties break exactly as upstream (strict <, candidate order).
 //
-// Mapping to the GPU: MB (x,y) depends on (x+1,y) and on row y+1 up to x-1, so every row is
-// a 2-MB-skewed pipeline stage.  One warp owns one MB row; it walks x downwards and spins on
-// the progress counter of the row below (acquire/release through L2).  Rows are handed out
-// by an atomic ticket so a waiting warp only ever waits on warps that already started.
-// Inside an MB the warp evaluates up to 8 candidate positions at once: 4 lanes per
-// candidate, 2 block rows per lane, __vsadu4 for SAD and shuffle butterflies for the 4x4
-// Hadamard of SATD -- all on the integer pipe (this is not a dense contraction).
-// Several searches (both lists of a B evaluation) share one launch via blockIdx.y.
+// Mapping to the GPU
+//   * MB (x,y) depends on (x+1,y) and on row y+1 up to x-1, so every row is a 2-MB-skewed
+//     pipeline stage.  One warp owns one MB row and walks x downwards.  Rows are handed out by
+//     an atomic ticket (bottom row first), so a waiting warp only ever waits on warps that
+//     already started -- no co-residency assumption, no deadlock.
+//   * Rows talk through one 8-byte record per MB {mv, epoch}: a single 64-bit store/load is
+//     atomic, so no fence and no separate progress flag.  The one NEW record an MB needs
+//     (below-left of the next MB) is prefetched while the current MB is being searched, which
+//     takes the L2 round trip off the critical path; so are the next MB's source pixels.
+//   * Inside an MB the warp evaluates up to 8 candidate positions at once: 4 lanes per
+//     candidate, 2 block rows per lane, __vsadu4 for SAD and shuffle butterflies for the 4x4
+//     Hadamard of SATD -- integer pipe only (this is not a dense contraction).
+//   * Reference pixels are staged in shared memory: a 64x48 window of the (weighted) plane 0
+//     around the predictor for all full-pel rounds (hexagon/square/diamond), and a 20x12
+//     window of all four half-pel phase planes around the full-pel winner for the sub-pel
+//     rounds.  A candidate that leaves the full-pel window falls back to global loads, so the
+//     staging never changes a result.
+//   * Several searches (both lists of a B evaluation, or all searches a newly arrived frame
+//     enables) share one launch via blockIdx.y.
 #include "la_common.cuh"
 
 namespace xv {
 
 #define BIG_COST 0x3fffffff
+#define WIN_W 64
+#define WIN_H 48
+#define WIN_R 20
+#define SUB_W 20
+#define SUB_H 12
 
-__device__ __forceinline__ int ld_acquire(const int *p)
+struct __align__(16) MeSmem {
+    uint8_t win[WIN_H * WIN_W];
+    uint8_t sub[4][SUB_H * SUB_W];
+};
+
+__device__ __forceinline__ uint2 ld_rec(const int2 *p)
 {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(int *p, int v)
+__device__ __forceinline__ void st_rec(int2 *p, int mv, int epoch)
 {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_relaxed(const int *p)
-{
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(mv), "r"(epoch) : "memory");
 }
 
 struct WarpMb {
-    // per-lane view of the current MB
     uint2 fe0, fe1;              // fenc rows 2*rp and 2*rp+1
-    int rp, grp, lane;
+    int rp, grp;
     int stride, pel;
+    int px, py;                  // plane coordinates of the MB origin
     const uint8_t *fref[4];
     const uint8_t *fref_w;
     WeightDev w;
     const uint16_t *cost_mv;
     int mvp_x, mvp_y;
     int satd;
+    // shared-memory staging
+    const uint8_t *win; int wx0, wy0;           // full-pel window origin, plane coordinates
+    const uint8_t *sub; int sx0, sy0;           // sub-pel windows origin, plane coordinates
 };
 
 __device__ __forceinline__ int group_sum(int v)
@@ -118,29 +136,72 @@ __device__ __forceinline__ int rows_satd(const WarpMb &m, uint2 a0, uint2 a1)
     return sum;
 }
 
+// 8 bytes at an arbitrary byte offset of a shared-memory window (same 3-word scheme as load8u)
+__device__ __forceinline__ uint2 lds8u(const uint8_t *base, int off)
+{
+    const uint32_t *q = (const uint32_t *)(base + (off & ~3));
+    const unsigned sh = (unsigned)(off & 3) * 8;
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+
 // full-pel candidate on the (possibly weighted) plane 0: SAD + mv cost
 __device__ __forceinline__ int cand_fpel(const WarpMb &m, int mx, int my, bool active)
 {
-    int c = 0;
+    int c = 0, mvc = 0;
     if (active) {
-        const uint8_t *p = m.fref_w + m.pel + (my + 2 * m.rp) * m.stride + mx;
-        c = rows_sad(m, load8u(p), load8u(p + m.stride));
+        mvc = mvcost(m, mx * 4, my * 4);
+        const int X = m.px + mx, Y = m.py + my + 2 * m.rp;
+        const int wx = X - m.wx0, wy = m.py + my - m.wy0;
+        uint2 a0, a1;
+        if (m.win && wx >= 0 && wx + 12 <= WIN_W && wy >= 0 && wy + 8 <= WIN_H) {
+            const int off = (Y - m.wy0) * WIN_W + wx;
+            a0 = lds8u(m.win, off); a1 = lds8u(m.win, off + WIN_W);
+        } else {
+            const uint8_t *p = m.fref_w + m.pel + (my + 2 * m.rp) * m.stride + mx;
+            a0 = load8u(p); a1 = load8u(p + m.stride);
+        }
+        c = rows_sad(m, a0, a1);
     }
     c = group_sum(c);
-    return active ? c + mvcost(m, mx * 4, my * 4) : BIG_COST;
+    return active ? c + mvc : BIG_COST;
 }
+
+// One row (8 px) of get_ref out of the staged sub-pel windows (must cover the position)
+__device__ __forceinline__ uint2 get_ref_row_sub(const WarpMb &m, int mvx, int mvy, int r)
+{
+    const int qidx = ((mvy & 3) << 2) + (mvx & 3);
+    const int X = m.px + (mvx >> 2) - m.sx0, Y = m.py + (mvy >> 2) + r - m.sy0;
+    uint2 a = lds8u(m.sub + c_hpel_ref0[qidx] * (SUB_H * SUB_W), (Y + ((mvy & 3) == 3)) * SUB_W + X);
+    if (qidx & 5) {
+        const uint2 b = lds8u(m.sub + c_hpel_ref1[qidx] * (SUB_H * SUB_W), Y * SUB_W + X + ((mvx & 3) == 3));
+        a.x = __vavgu4(a.x, b.x);
+        a.y = __vavgu4(a.y, b.y);
+    }
+    if (m.w.on) { a.x = weight_word(m.w, a.x); a.y = weight_word(m.w, a.y); }
+    return a;
+}
+
 // quarter-pel candidate through get_ref: SAD or SATD + mv cost
+template <bool SUBWIN>
 __device__ __forceinline__ int cand_qpel(const WarpMb &m, int qx, int qy, bool active, bool use_satd)
 {
     uint2 a0 = make_uint2(0, 0), a1 = a0;
+    int mvc = 0;
     if (active) {
-        a0 = get_ref_row(m.fref, m.stride, m.pel, qx, qy, 2 * m.rp, m.w);
-        a1 = get_ref_row(m.fref, m.stride, m.pel, qx, qy, 2 * m.rp + 1, m.w);
+        mvc = mvcost(m, qx, qy);
+        if (SUBWIN) {
+            a0 = get_ref_row_sub(m, qx, qy, 2 * m.rp);
+            a1 = get_ref_row_sub(m, qx, qy, 2 * m.rp + 1);
+        } else {
+            a0 = get_ref_row(m.fref, m.stride, m.pel, qx, qy, 2 * m.rp, m.w);
+            a1 = get_ref_row(m.fref, m.stride, m.pel, qx, qy, 2 * m.rp + 1, m.w);
+        }
     }
     int c;
     if (use_satd) c = rows_satd(m, a0, a1);
     else c = group_sum(rows_sad(m, a0, a1));
-    return active ? c + mvcost(m, qx, qy) : BIG_COST;
+    return active ? c + mvc : BIG_COST;
 }
 
 __constant__ const signed char c_hex2[8][2] = {{-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0}};
@@ -151,16 +212,64 @@ __constant__ const signed char c_hex_first[6][3] = {{-2, 0, 2}, {-1, 2, 3}, {1, 
 
 struct MeResult { int mvx, mvy, cost; };
 
-__device__ MeResult me_search_mb(WarpMb &m, const MeParams &P, const int mvc[4][2], int i_mvc,
-                                 int min_sx, int max_sx, int min_sy, int max_sy)
+// stage the 64x48 full-pel window of fref_w: 6 x 16-byte loads per lane, issued early
+struct WinRegs { uint4 v[6]; };
+__device__ __forceinline__ void win_issue(const WarpMb &m, const LaGeom &g, int lane, int cx, int cy, WinRegs &r, int &wx0, int &wy0)
+{
+    wx0 = (m.px + cx - WIN_R) & ~15;
+    wx0 = min(max(wx0, -32), g.lstride - 32 - WIN_W);
+    wy0 = min(max(m.py + cy - WIN_R, -32), g.lh + 32 - WIN_H);
+    const uint8_t *base = m.fref_w + wy0 * m.stride + wx0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int c = lane + 32 * k;
+        r.v[k] = __ldg((const uint4 *)(base + (c >> 2) * m.stride + (c & 3) * 16));
+    }
+}
+__device__ __forceinline__ void win_commit(MeSmem &sm, int lane, const WinRegs &r)
+{
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int c = lane + 32 * k;
+        *(uint4 *)(sm.win + (c >> 2) * WIN_W + (c & 3) * 16) = r.v[k];
+    }
+    __syncwarp();
+}
+// stage the four 20x12 sub-pel windows around full-pel position (fx,fy) (MB-relative)
+__device__ __forceinline__ void sub_load(WarpMb &m, MeSmem &sm, int lane, int fx, int fy)
+{
+    m.sx0 = (m.px + fx - 1) & ~3;
+    m.sy0 = m.py + fy - 1;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = lane + 32 * k;                     // 4 planes x 12 rows x 5 words = 240 words
+        if (c < 4 * SUB_H * (SUB_W / 4)) {
+            const int pl = c / (SUB_H * (SUB_W / 4)), rem = c - pl * (SUB_H * (SUB_W / 4));
+            const int row = rem / (SUB_W / 4), wd = rem - row * (SUB_W / 4);
+            const uint32_t v = __ldg((const uint32_t *)(m.fref[pl] + (m.sy0 + row) * m.stride + m.sx0 + 4 * wd));
+            *(uint32_t *)(sm.sub[pl] + row * SUB_W + 4 * wd) = v;
+        }
+    }
+    __syncwarp();
+    m.sub = &sm.sub[0][0];
+}
+
+__device__ MeResult me_search_mb(WarpMb &m, MeSmem &sm, const LaGeom &g, const MeParams &P, const int mvc[4][2], int i_mvc,
+                                 int min_sx, int max_sx, int min_sy, int max_sy, int lane)
 {
     const int mv_x_min = min_sx >> 2, mv_x_max = max_sx >> 2, mv_y_min = min_sy >> 2, mv_y_max = max_sy >> 2;
     const int grp = m.grp;
     int bmx, bmy, bcost, bpred_cost = LA_COST_MAX, bpred_mx = 0, bpred_my = 0;
     int pm_fx = 0, pm_fy = 0;
+    WinRegs wr;
+    m.win = nullptr;
 
     if (P.subpel_refine >= 3) {
         const int pmx = clip3i(m.mvp_x, mv_x_min * 4, mv_x_max * 4), pmy = clip3i(m.mvp_y, mv_y_min * 4, mv_y_max * 4);
+        int wx0, wy0;
+        win_issue(m, g, lane, (pmx + 2) >> 2, (pmy + 2) >> 2, wr, wx0, wy0);
         // slot 0 = clipped mvp, slots 1..n = surviving clipped candidates (x264_predictor_clip)
         int cx = pmx, cy = pmy, n = 0;
         bool active = grp == 0;
@@ -174,7 +283,9 @@ __device__ MeResult me_search_mb(WarpMb &m, const MeParams &P, const int mvc[4][
                 }
             }
         }
-        const int c = cand_qpel(m, cx, cy, active, false);
+        const int c = cand_qpel<false>(m, cx, cy, active, false);
+        win_commit(sm, lane, wr);
+        m.win = sm.win; m.wx0 = wx0; m.wy0 = wy0;
         const int packed = warp_min(active ? (c << 4) + grp : 0x7fffffff);
         const int pmv_cost = __shfl_sync(0xffffffffu, c, 0);
         const int best = packed & 15;
@@ -199,6 +310,8 @@ __device__ MeResult me_search_mb(WarpMb &m, const MeParams &P, const int mvc[4][
         // subme < 3: full-pel predictors; the rounded mvp is scored without its mv cost
         bmx = pm_fx = clip3i((m.mvp_x + 2) >> 2, mv_x_min, mv_x_max);
         bmy = pm_fy = clip3i((m.mvp_y + 2) >> 2, mv_y_min, mv_y_max);
+        int wx0, wy0;
+        win_issue(m, g, lane, bmx, bmy, wr, wx0, wy0);
         int cx = bmx, cy = bmy, n = 0;
         bool active = grp == 0;
 #pragma unroll
@@ -215,6 +328,8 @@ __device__ MeResult me_search_mb(WarpMb &m, const MeParams &P, const int mvc[4][
         const bool zslot = pmv_nz && grp == 7;           // the zero vector rides along in slot 7
         if (zslot) { cx = 0; cy = 0; active = true; }
         int c = cand_fpel(m, cx, cy, active);
+        win_commit(sm, lane, wr);
+        m.win = sm.win; m.wx0 = wx0; m.wy0 = wy0;
         if (grp == 0) c -= mvcost(m, cx * 4, cy * 4);
         const int c_zero = __shfl_sync(0xffffffffu, c, 28);
         const int packed = warp_min((active && !zslot) ? (c << 4) + grp : 0x7fffffff);
@@ -286,13 +401,14 @@ __device__ MeResult me_search_mb(WarpMb &m, const MeParams &P, const int mvc[4][
     if (P.subpel_refine < 3) {
         const int mx = clip3i(m.mvp_x, min_sx + 2, max_sx - 2), my = clip3i(m.mvp_y, min_sy + 2, max_sy - 2);
         if ((mx - bmx) | (my - bmy)) {
-            const int c = __shfl_sync(0xffffffffu, cand_qpel(m, mx, my, grp == 0, false), 0);
+            const int c = __shfl_sync(0xffffffffu, cand_qpel<false>(m, mx, my, grp == 0, false), 0);
             if (c < bcost) { bcost = c; bmx = mx; bmy = my; }
         }
     }
+    sub_load(m, sm, lane, bmx >> 2, bmy >> 2);
     {
         const int dx = grp == 2 ? -2 : grp == 3 ? 2 : 0, dy = grp == 0 ? -2 : grp == 1 ? 2 : 0;
-        const int c = cand_qpel(m, bmx + dx, bmy + dy, grp < 4, false);
+        const int c = cand_qpel<true>(m, bmx + dx, bmy + dy, grp < 4, false);
         const int packed = warp_min(grp < 4 ? (c << 4) + grp + 1 : 0x7fffffff);
         if ((packed >> 4) < bcost) {
             bcost = packed >> 4;
@@ -306,7 +422,7 @@ __device__ MeResult me_search_mb(WarpMb &m, const MeParams &P, const int mvc[4][
         const bool do_qpel = P.subpel_refine >= 4 && !(bmy <= min_sy || bmy >= max_sy || bmx <= min_sx || bmx >= max_sx);
         const int dx = grp == 3 ? -1 : grp == 4 ? 1 : 0, dy = grp == 1 ? -1 : grp == 2 ? 1 : 0;
         const bool active = grp == 0 || (do_qpel && grp < 5);
-        const int c = cand_qpel(m, bmx + dx, bmy + dy, active, true);
+        const int c = cand_qpel<true>(m, bmx + dx, bmy + dy, active, true);
         bcost = __shfl_sync(0xffffffffu, c, 0);
         if (do_qpel) {
             const int packed = warp_min((grp >= 1 && grp < 5) ? (c << 4) + grp : 0x7fffffff);
@@ -325,10 +441,11 @@ __device__ MeResult me_search_mb(WarpMb &m, const MeParams &P, const int mvc[4][
 __global__ void __launch_bounds__(32)
 me_wavefront_kernel(LaGeom g, MeParams P)
 {
+    __shared__ MeSmem sm;
     const MeJob &job = P.job[blockIdx.y];
     const int lane = threadIdx.x;
     int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(job.sync, 1);
+    if (lane == 0) ticket = atomicAdd(job.ticket, 1);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
     const int mb_y = g.mb_h - 1 - ticket;                 // bottom rows start first
     if (mb_y < 0) return;
@@ -338,45 +455,70 @@ me_wavefront_kernel(LaGeom g, MeParams P)
         const int s = (g.mb_h * i + T / 2) / T, e = (g.mb_h * (i + 1) + T / 2) / T;
         if (mb_y >= s && mb_y < e) { slice_start = s; slice_end = e; }
     }
-    int *progress = job.sync + 1;
     const int start_y = min(slice_end - 1, g.mb_h - 2 + P.do_edges), end_y = max(slice_start, 1 - P.do_edges);
     const int start_x = g.mb_w - 2 + P.do_edges, end_x = 1 - P.do_edges;
-    if (mb_y > start_y || mb_y < end_y) {                  // row not scanned (edges without do_edges)
-        if (lane == 0) st_release(progress + mb_y, -1);
-        return;
-    }
+    if (mb_y > start_y || mb_y < end_y) return;            // row not scanned (edges without do_edges)
     const bool has_below = mb_y < slice_end - 1;
     const bool below_scanned = has_below && (mb_y + 1 <= start_y);
+    const int epoch = P.epoch;
+    const int2 *below = job.rec + (mb_y + 1) * g.mb_w;
+    int2 *mine = job.rec + mb_y * g.mb_w;
 
     WarpMb m;
-    m.lane = lane; m.grp = lane >> 2; m.rp = lane & 3;
+    m.grp = lane >> 2; m.rp = lane & 3;
     m.stride = g.lstride;
 #pragma unroll
     for (int k = 0; k < 4; k++) m.fref[k] = job.fref[k];
     m.fref_w = job.fref_w; m.w = job.w; m.cost_mv = P.cost_mv; m.satd = P.satd;
+    m.win = nullptr; m.sub = nullptr;
+
+    // MV of a row-below MB: zero when that position is never scanned, else wait for its record
+    auto below_mv = [&](int x, uint2 pre, bool have_pre) -> int {
+        if (!below_scanned || x < end_x || x > start_x) return 0;
+        uint2 r = have_pre ? pre : ld_rec(below + x);
+        while ((int)r.y != epoch) { __nanosleep(40); r = ld_rec(below + x); }
+        return (int)r.x;
+    };
 
     int right_mv = 0;          // packed mv of (x+1, y); zero before the first MB like the zeroed array
+    int b_m1 = 0, b_0 = 0, b_p1 = 0;                        // below-left, below, below-right of the current MB
+    if (has_below) {
+        const uint2 z = make_uint2(0, 0);
+        if (start_x + 1 < g.mb_w) b_p1 = below_mv(start_x + 1, z, false);
+        b_0 = below_mv(start_x, z, false);
+        if (start_x > 0) b_m1 = below_mv(start_x - 1, z, false);
+    }
+    // source pixels of the first MB
+    uint2 nfe0, nfe1, nr0, nr1;
+    {
+        const int pel = 8 * (start_x + mb_y * g.lstride) + 2 * m.rp * g.lstride;
+        nfe0 = load8u(job.fenc + pel); nfe1 = load8u(job.fenc + pel + g.lstride);
+        nr0 = load8u(job.fref[0] + pel); nr1 = load8u(job.fref[0] + pel + g.lstride);
+    }
+
     for (int mb_x = start_x; mb_x >= end_x; mb_x--) {
         const int mb_xy = mb_x + mb_y * g.mb_w;
         m.pel = 8 * (mb_x + mb_y * g.lstride);
-        {
-            const uint8_t *f = job.fenc + m.pel + 2 * m.rp * g.lstride;
-            m.fe0 = load8u(f); m.fe1 = load8u(f + g.lstride);
+        m.px = 8 * mb_x; m.py = 8 * mb_y;
+        m.fe0 = nfe0; m.fe1 = nfe1;
+        const uint2 r0 = nr0, r1 = nr1;
+        // ---- prefetch for the next MB: its pixels, and the one new record it needs ----
+        uint2 pre = make_uint2(0, 0);
+        const bool want_pre = has_below && below_scanned && mb_x - 2 >= end_x;
+        if (mb_x > end_x) {
+            const int pel = m.pel - 8 + 2 * m.rp * g.lstride;
+            nfe0 = load8u(job.fenc + pel); nfe1 = load8u(job.fenc + pel + g.lstride);
+            nr0 = load8u(job.fref[0] + pel); nr1 = load8u(job.fref[0] + pel + g.lstride);
+            if (want_pre) pre = ld_rec(below + mb_x - 2);
         }
         // ---- reverse-order MV prediction ----
         int mvc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
         int i_mvc = 0;
         if (mb_x < g.mb_w - 1) { mvc[i_mvc][0] = mv_x(right_mv); mvc[i_mvc][1] = mv_y(right_mv); i_mvc++; }
         if (has_below) {
-            if (below_scanned) {
-                const int need = max(mb_x - 1, end_x);     // row below must have finished this x
-                while (ld_acquire(progress + mb_y + 1) > need) __nanosleep(64);
-            }
-            const int *below = job.mvs + mb_xy + g.mb_w;
-            int v = ld_relaxed(below);
-            mvc[i_mvc][0] = mv_x(v); mvc[i_mvc][1] = mv_y(v); i_mvc++;
-            if (mb_x > 0) { v = ld_relaxed(below - 1); mvc[i_mvc][0] = mv_x(v); mvc[i_mvc][1] = mv_y(v); i_mvc++; }
-            if (mb_x < g.mb_w - 1) { v = ld_relaxed(below + 1); mvc[i_mvc][0] = mv_x(v); mvc[i_mvc][1] = mv_y(v); i_mvc++; }
+            mvc[i_mvc][0] = mv_x(b_0); mvc[i_mvc][1] = mv_y(b_0); i_mvc++;
+            if (mb_x > 0) { mvc[i_mvc][0] = mv_x(b_m1); mvc[i_mvc][1] = mv_y(b_m1); i_mvc++; }
+            if (mb_x < g.mb_w - 1) { mvc[i_mvc][0] = mv_x(b_p1); mvc[i_mvc][1] = mv_y(b_p1); i_mvc++; }
         }
         if (i_mvc <= 1) { m.mvp_x = mvc[0][0]; m.mvp_y = mvc[0][1]; }
         else { m.mvp_x = median3i(mvc[0][0], mvc[1][0], mvc[2][0]); m.mvp_y = median3i(mvc[0][1], mvc[1][1], mvc[2][1]); }
@@ -388,14 +530,12 @@ me_wavefront_kernel(LaGeom g, MeParams P)
         bool skip = false;
         if (!(m.mvp_x | m.mvp_y)) {
             // fast skip: mbcmp at mv 0 on the UNWEIGHTED plane 0
-            const uint8_t *p = job.fref[0] + m.pel + 2 * m.rp * g.lstride;
-            const uint2 a0 = load8u(p), a1 = load8u(p + g.lstride);
-            const int c = P.satd ? rows_satd(m, a0, a1) : group_sum(rows_sad(m, a0, a1));
+            const int c = P.satd ? rows_satd(m, r0, r1) : group_sum(rows_sad(m, r0, r1));
             const int c0 = __shfl_sync(0xffffffffu, c, 0);
             if (c0 < 64) { skip = true; out_mv = 0; out_cost = c0; }
         }
         if (!skip) {
-            MeResult r = me_search_mb(m, P, mvc, i_mvc, min_sx, max_sx, min_sy, max_sy);
+            MeResult r = me_search_mb(m, sm, g, P, mvc, i_mvc, min_sx, max_sx, min_sy, max_sy, lane);
             int cost = r.cost - (int)__ldg(P.cost_mv);      // remove mvcost from skip mbs
             if (r.mvx | r.mvy) cost += 5;
             out_mv = mv_pack(r.mvx, r.mvy); out_cost = cost;
@@ -404,8 +544,11 @@ me_wavefront_kernel(LaGeom g, MeParams P)
         if (lane == 0) {
             job.mvs[mb_xy] = out_mv;
             job.mv_costs[mb_xy] = out_cost;
-            st_release(progress + mb_y, mb_x);
+            st_rec(mine + mb_x, out_mv, epoch);
         }
+        // ---- slide the below-row window; resolve the prefetched record ----
+        b_p1 = b_0; b_0 = b_m1;
+        b_m1 = (has_below && mb_x - 2 >= 0) ? below_mv(mb_x - 2, pre, want_pre) : 0;
     }
 }
 
