@@ -331,7 +331,13 @@ def main():
                                     colmatrix=2, fullrange=0, device=local_rank) for _ in range(S)]
 
     sessions = open_sessions()
-    ms_step, clocks, launches, prof = run_phase(torch, dist, sessions, dev_ptrs, True, None, args, rank, world, local_rank, profile=True)
+    ms_step, clocks, launches, _ = run_phase(torch, dist, sessions, dev_ptrs, True, None, args, rank, world, local_rank)
+    host_counters = [la.counters() for la in sessions]
+    for la in sessions:
+        la.close()
+    # same workload once more with per-kernel CUDA-event timing switched on (kernel shares, roofline)
+    sessions = open_sessions()
+    _, _, _, prof = run_phase(torch, dist, sessions, dev_ptrs, True, None, args, rank, world, local_rank, profile=True)
     for la in sessions:
         la.close()
     frames_per_step_all = S * F * n_gpus
@@ -405,7 +411,11 @@ def main():
                        "rc_lookahead": 40, "bframes": 3, "b_adapt": 1, "mbtree": 1, "weightp": 2, "aq_mode": 1,
                        "l2_policy": f"inputs larger than L2: {S * F * SRC_BYTES / 1e6:.0f} MB of packed frames per step per GPU"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "stage1": stage1,
-            "kernel_shares": shares, "dominant_kernel_class": dom, "cpu_baseline": cpu_baseline}
+            "kernel_shares": shares, "dominant_kernel_class": dom, "cpu_baseline": cpu_baseline,
+            "host_us_per_frame": {k: sum(c[k] for c in host_counters) / max(1, sum(c["frames"] for c in host_counters))
+                                  for k in ("put_us", "decide_us", "sync_us")},
+            "per_frame": {k: sum(c[k] for c in host_counters) / max(1, sum(c["frames"] for c in host_counters))
+                          for k in ("frame_costs", "launches", "syncs")}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -262,8 +262,10 @@ int x264vfw_cuda_la_mbtree( x264vfw_cuda_la *la, const int *frame_idx, const int
  * number of bytes written or -1. */
 int64_t x264vfw_cuda_la_read( x264vfw_cuda_la *la, int frame, int what, int a, int b, void *dst, size_t dst_bytes );
 /* [0] slicetype_frame_cost evaluations launched, [1] MB searches (MBs x lists), [2] kernel
- * launches, [3] host<->device synchronisations */
-void x264vfw_cuda_la_counters( x264vfw_cuda_la *la, uint64_t out[4] );
+ * launches, [3] host<->device synchronisations, [4] host microseconds spent enqueueing frame
+ * preparation, [5] in the decision logic (including [6]), [6] blocked in synchronisations,
+ * [7] frames put */
+void x264vfw_cuda_la_counters( x264vfw_cuda_la *la, uint64_t out[8] );
 
 /* Per-kernel-class device time of this session, measured with CUDA events on the session's
  * stream around every launch: [0] csp [1] aq [2] lowres [3] intra [4] motion search

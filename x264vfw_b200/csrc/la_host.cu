@@ -19,6 +19,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <chrono>
 #include <deque>
 #include <vector>
 
@@ -44,6 +45,9 @@ int convert_device_public(cudaStream_t st, int out_csp, int colmatrix, int fullr
 #define COST_MAX64 (1ULL << 60)
 #define PENDING (-2)
 
+#define ME_SIDE 2
+#define ME_EVENTS 64
+
 struct Frame {
     // host mirror of the x264_frame_t fields the decision logic reads
     int i_frame = 0, i_type = T_AUTO, i_forced_type = T_AUTO, b_scenecut = 1, b_keyframe = 0, i_bframes = 0;
@@ -51,6 +55,9 @@ struct Frame {
     int cost_est[BMAX + 2][BMAX + 2], cost_est_aq[BMAX + 2][BMAX + 2], intra_mbs[BMAX + 2];
     bool searched[2][BMAX + 1];            // logical: what upstream's 0x7FFF sentinel would say
     bool spec[2][BMAX + 1];                // device arrays already hold the (unweighted) search result
+    int spec_eng[2][BMAX + 1];             // ... produced by this ME engine
+    uint64_t spec_seq[2][BMAX + 1];        // ... in this launch of it
+    uint64_t touch_seq[1 + ME_SIDE] = {0}; // last launch of each side engine that reads/writes this frame
     bool b_intra_calculated = false;
     bool stats_ready = false;
     unsigned long long pixel_sum[3], pixel_ssd[3];
@@ -107,8 +114,15 @@ struct La {
     uint8_t *d_planes = nullptr; size_t d_planes_bytes = 0; // converted planes (tight)
     x264vfw_cuda_image_t planes_img;
     uint8_t *d_weight_buf = nullptr;
-    int2 *d_rec = nullptr; int *d_ticket = nullptr;         // ME inter-row records / row tickets, per job
-    int me_epoch = 0;
+    // ME engines: [0] runs on the main stream (on-demand searches), [1..ME_SIDE] on side streams
+    // (speculative searches), each with its own inter-row record / ticket scratch.
+    int2 *d_rec[1 + ME_SIDE] = {nullptr}; int *d_ticket[1 + ME_SIDE] = {nullptr};
+    cudaStream_t st_me[1 + ME_SIDE] = {nullptr};
+    cudaEvent_t ev_me[1 + ME_SIDE][ME_EVENTS];              // done-events of the side launches (ring)
+    uint64_t me_seq[1 + ME_SIDE] = {0};                     // launches issued per engine
+    uint64_t me_waited[1 + ME_SIDE] = {0};                  // highest launch the main stream already waits on
+    cudaEvent_t ev_ready = nullptr;                         // main stream -> side stream hand-off
+    int me_epoch = 0, me_rr = 0;
     int *d_results = nullptr; int *h_results = nullptr;     // ring of 4-int slots
     int result_head = 0;
     unsigned *d_wscore = nullptr; unsigned *h_wscore = nullptr;
@@ -124,6 +138,7 @@ struct La {
     int n_input = 0;
     uint64_t n_frame_cost = 0, n_mb_search = 0, n_launch = 0, n_sync = 0;
     bool fail = false;   // set when a device call fails inside the value-returning helpers
+    double t_put = 0, t_decide = 0, t_sync = 0;   // host wall-clock seconds (diagnostics)
     Prof prof;
 };
 
@@ -132,6 +147,7 @@ static const int RESULT_SLOTS = 1024;
 #define LA_CUDA(expr) XV_CUDA_OK(expr)
 
 static int la_sync(La *la);
+static int wait_engine(La *la, int eng, uint64_t seq);
 
 static cudaEvent_t prof_event(La *la)
 {
@@ -141,18 +157,21 @@ static cudaEvent_t prof_event(La *la)
     return e;
 }
 struct ProfScope {
-    La *la; int cls; cudaEvent_t a = nullptr;
-    ProfScope(La *l, int c) : la(l), cls(c) { if (la->prof.on) { a = prof_event(la); cudaEventRecord(a, la->st); } }
-    ~ProfScope() { if (a) { cudaEvent_t b = prof_event(la); cudaEventRecord(b, la->st); la->prof.recs.push_back(ProfRec{cls, a, b}); } }
+    La *la; int cls; cudaStream_t st; cudaEvent_t a = nullptr;
+    ProfScope(La *l, int c, cudaStream_t s = nullptr) : la(l), cls(c), st(s ? s : l->st) { if (la->prof.on) { a = prof_event(la); cudaEventRecord(a, st); } }
+    ~ProfScope() { if (a) { cudaEvent_t b = prof_event(la); cudaEventRecord(b, st); la->prof.recs.push_back(ProfRec{cls, a, b}); } }
 };
 static void prof_resolve(La *la)
 {
+    // records of side-stream launches may still be in flight: keep those for the next round
+    std::vector<ProfRec> keep;
     for (const ProfRec &r : la->prof.recs) {
+        if (cudaEventQuery(r.b) == cudaErrorNotReady) { keep.push_back(r); continue; }
         float ms = 0;
         if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { la->prof.ms[r.cls] += ms; la->prof.n[r.cls]++; }
         la->prof.pool.push_back(r.a); la->prof.pool.push_back(r.b);
     }
-    la->prof.recs.clear();
+    la->prof.recs.swap(keep);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -198,10 +217,17 @@ static int frame_reset(La *la, Frame *f, int i_frame)
     for (int a = 0; a < BMAX + 2; a++) { f->intra_mbs[a] = 0; f->weighted_cost_delta[a] = 0; for (int b = 0; b < BMAX + 2; b++) f->cost_est[a][b] = f->cost_est_aq[a][b] = -1; }
     memset(f->searched, 0, sizeof(f->searched));
     memset(f->spec, 0, sizeof(f->spec));
+    memset(f->spec_eng, 0, sizeof(f->spec_eng));
+    memset(f->spec_seq, 0, sizeof(f->spec_seq));
     f->b_intra_calculated = false; f->stats_ready = false;
     f->weight = WeightDev{0, 1, 0, 0};
     f->rc_d0 = f->rc_d1 = -1;
     f->in_use = true;
+    // a recycled slot may still be in use by speculative searches on the side streams
+    for (int e = 1; e <= ME_SIDE; e++) {
+        if (f->touch_seq[e] && wait_engine(la, e, f->touch_seq[e]) < 0) return -1;
+        f->touch_seq[e] = 0;
+    }
     // zero the memo arrays the kernels may read before writing (MV predictors of unscanned
     // MBs, intra cost of unscanned edge MBs), and the stats accumulators
     const size_t zero_from = (uint8_t *)f->intra_cost - f->arena;
@@ -249,8 +275,12 @@ static int result_slot(La *la)
     return s;
 }
 
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int la_sync(La *la)
 {
+    const double t0 = now_s();
+    struct Acc { La *l; double t; ~Acc() { l->t_sync += now_s() - t; } } acc{la, t0};
     if (!la->pending.empty())
         LA_CUDA(cudaMemcpyAsync(la->h_results, la->d_results, RESULT_SLOTS * 4 * sizeof(int), cudaMemcpyDeviceToHost, la->st));
     LA_CUDA(cudaStreamSynchronize(la->st));
@@ -391,7 +421,7 @@ static void me_params_init(La *la, MeParams &mp)
     mp.cost_mv = la->d_cost_mv + la->cost_mv_half;
 }
 
-static void me_add_job(La *la, MeParams &mp, Frame *fenc, Frame *ref, int list, int dist, const WeightDev *w)
+static void me_add_job(La *la, MeParams &mp, int eng, Frame *fenc, Frame *ref, int list, int dist, const WeightDev *w)
 {
     MeJob &j = mp.job[mp.njobs];
     j.fenc = plane_org(la, fenc, 0);
@@ -401,19 +431,36 @@ static void me_add_job(La *la, MeParams &mp, Frame *fenc, Frame *ref, int list, 
     if (w) { j.w = *w; j.fref_w = la->d_weight_buf + la->g.lorigin; }
     j.mvs = fenc->mvs[list][dist - 1];
     j.mv_costs = fenc->mv_costs[list][dist - 1];
-    j.rec = la->d_rec + (size_t)mp.njobs * la->g.mb_count;
-    j.ticket = la->d_ticket + mp.njobs;
+    j.rec = la->d_rec[eng] + (size_t)mp.njobs * la->g.mb_count;
+    j.ticket = la->d_ticket[eng] + mp.njobs;
     mp.njobs++;
     la->n_mb_search += la->g.mb_count;
 }
 
-static int me_launch(La *la, MeParams &mp)
+// Make the main stream wait for launch `seq` of side engine `eng` (and everything before it).
+static int wait_engine(La *la, int eng, uint64_t seq)
+{
+    if (eng == 0 || seq <= la->me_waited[eng]) return 0;
+    // ring slot of an old launch may have been re-recorded by a newer one: waiting on the newer
+    // one is a superset
+    const uint64_t use = (la->me_seq[eng] - seq >= ME_EVENTS) ? la->me_seq[eng] : seq;
+    LA_CUDA(cudaStreamWaitEvent(la->st, la->ev_me[eng][use % ME_EVENTS], 0));
+    la->me_waited[eng] = use;
+    return 0;
+}
+
+static int me_launch(La *la, MeParams &mp, int eng)
 {
     if (!mp.njobs) return 0;
-    LA_CUDA(cudaMemsetAsync(la->d_ticket, 0, XV_ME_MAX_JOBS * sizeof(int), la->st));
+    cudaStream_t st = la->st_me[eng];
+    LA_CUDA(cudaMemsetAsync(la->d_ticket[eng], 0, XV_ME_MAX_JOBS * sizeof(int), st));
     mp.epoch = ++la->me_epoch;
-    { ProfScope ps(la, K_ME); if (launch_me(la->st, la->g, mp) < 0) return -1; }
+    { ProfScope ps(la, K_ME, st); if (launch_me(st, la->g, mp) < 0) return -1; }
     la->n_launch++;
+    if (eng) {
+        const uint64_t seq = ++la->me_seq[eng];
+        LA_CUDA(cudaEventRecord(la->ev_me[eng][seq % ME_EVENTS], st));
+    }
     return 0;
 }
 
@@ -426,13 +473,21 @@ static int speculate_searches(La *la, Frame *fn)
 {
     if (!la->speculate) return 0;
     const int n = fn->i_frame, B = la->p.bframes;
+    const int eng = 1 + (la->me_rr++ % ME_SIDE);
+    // hand-off: the side stream may start once everything queued so far on the main stream
+    // (this frame's lowres planes, the zeroing of recycled arrays) is done
+    LA_CUDA(cudaEventRecord(la->ev_ready, la->st));
+    LA_CUDA(cudaStreamWaitEvent(la->st_me[eng], la->ev_ready, 0));
     MeParams mp;
     me_params_init(la, mp);
     auto alive = [&](int i) -> Frame * { return (i >= 0 && i < (int)la->by_index.size()) ? la->by_index[i] : nullptr; };
     auto add = [&](Frame *fenc, Frame *ref, int list, int d) -> int {
-        me_add_job(la, mp, fenc, ref, list, d, nullptr);
+        me_add_job(la, mp, eng, fenc, ref, list, d, nullptr);
         fenc->spec[list][d - 1] = true;
-        if (mp.njobs == XV_ME_MAX_JOBS) { if (me_launch(la, mp) < 0) return -1; me_params_init(la, mp); }
+        fenc->spec_eng[list][d - 1] = eng;
+        fenc->spec_seq[list][d - 1] = la->me_seq[eng] + 1;        // the launch this job will be part of
+        fenc->touch_seq[eng] = ref->touch_seq[eng] = la->me_seq[eng] + 1;
+        if (mp.njobs == XV_ME_MAX_JOBS) { if (me_launch(la, mp, eng) < 0) return -1; me_params_init(la, mp); }
         return 0;
     };
     for (int d = 1; d <= B + 1; d++) {
@@ -443,7 +498,7 @@ static int speculate_searches(La *la, Frame *fn)
         Frame *b = alive(n - d);
         if (b && !b->spec[1][d - 1] && add(b, fn, 1, d) < 0) return -1;
     }
-    return me_launch(la, mp);
+    return me_launch(la, mp, eng);
 }
 
 // Enqueues everything slicetype_frame_cost(p0,p1,b) computes.  need_value: synchronise and
@@ -498,11 +553,23 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
             if (!do_search[l]) continue;
             const int dist = l ? d1 : d0;
             const bool weighted = l == 0 && w.on;
-            if (fenc->spec[l][dist - 1] && !weighted) continue;
-            me_add_job(la, mp, fenc, l ? fref1 : fref0, l, dist, weighted ? &w : nullptr);
-            if (!weighted) fenc->spec[l][dist - 1] = true;
+            if (fenc->spec[l][dist - 1]) {
+                // produced (or being produced) by a side engine: order the main stream after it
+                if (wait_engine(la, fenc->spec_eng[l][dist - 1], fenc->spec_seq[l][dist - 1]) < 0) return -1;
+                if (!weighted) continue;
+            }
+            me_add_job(la, mp, 0, fenc, l ? fref1 : fref0, l, dist, weighted ? &w : nullptr);
+            if (!weighted) { fenc->spec[l][dist - 1] = true; fenc->spec_eng[l][dist - 1] = 0; }
         }
-        if (me_launch(la, mp) < 0) return -1;
+        if (me_launch(la, mp, 0) < 0) return -1;
+        // memoised lists are read by the selection kernel as well: same ordering requirement
+        for (int l = 0; l < 2; l++) {
+            const int dist = l ? d1 : d0;
+            if (dist && !do_search[l] && fenc->spec[l][dist - 1])
+                if (wait_engine(la, fenc->spec_eng[l][dist - 1], fenc->spec_seq[l][dist - 1]) < 0) return -1;
+        }
+        if (b < p1 && fref1->searched[0][p1 - p0 - 1] && fref1->spec[0][p1 - p0 - 1])
+            if (wait_engine(la, fref1->spec_eng[0][p1 - p0 - 1], fref1->spec_seq[0][p1 - p0 - 1]) < 0) return -1;
     }
 
     // ---- per-MB selection + accumulators ----
@@ -1028,6 +1095,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     XV_CUDA_OK(cudaSetDevice(device));
     if (params->width <= 0 || params->height <= 0 || (params->width & 1) || (params->height & 1)) { set_error("width/height must be positive and even"); return -1; }
     La *la = new La();
+    memset(la->ev_me, 0, sizeof(la->ev_me));
     la->p = *params;
     x264vfw_cuda_la_params &p = la->p;
     if (p.bframes > BMAX) p.bframes = BMAX;
@@ -1072,13 +1140,20 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
                   cudaMemcpy(la->d_log2_lut, l2, sizeof(l2), cudaMemcpyHostToDevice) == cudaSuccess &&
                   cudaMemcpy(la->d_exp2_lut, e2, 64, cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&la->d_weight_buf, g.lplane + 64) == cudaSuccess &&
-             cudaMalloc((void **)&la->d_rec, (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
-             cudaMemset(la->d_rec, 0, (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
-             cudaMalloc((void **)&la->d_ticket, XV_ME_MAX_JOBS * sizeof(int)) == cudaSuccess &&
+             cudaEventCreateWithFlags(&la->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
              cudaMalloc((void **)&la->d_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMallocHost((void **)&la->h_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMalloc((void **)&la->d_wscore, 64) == cudaSuccess &&
              cudaMallocHost((void **)&la->h_wscore, 64) == cudaSuccess;
+        la->st_me[0] = la->st;
+        for (int e = 0; e <= ME_SIDE && ok; e++) {
+            ok = ok && cudaMalloc((void **)&la->d_rec[e], (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
+                 cudaMemset(la->d_rec[e], 0, (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
+                 cudaMalloc((void **)&la->d_ticket[e], XV_ME_MAX_JOBS * sizeof(int)) == cudaSuccess;
+            if (e) ok = ok && cudaStreamCreateWithFlags(&la->st_me[e], cudaStreamNonBlocking) == cudaSuccess;
+            for (int k = 0; k < ME_EVENTS && ok; k++)
+                ok = ok && cudaEventCreateWithFlags(&la->ev_me[e][k], cudaEventDisableTiming) == cudaSuccess;
+        }
         int64_t pbytes = x264vfw_cuda_picture_layout(&la->planes_img, nullptr, out_csp, p.width, p.height);
         if (pbytes < 0) { set_error("bad encoder csp %d", out_csp); ok = false; }
         else {
@@ -1098,13 +1173,19 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     if (!la) return;
     cudaSetDevice(la->device);
     if (la->st) cudaStreamSynchronize(la->st);
+    for (int e = 1; e <= ME_SIDE; e++) if (la->st_me[e]) cudaStreamSynchronize(la->st_me[e]);
     prof_resolve(la);
     for (cudaEvent_t e : la->prof.pool) cudaEventDestroy(e);
     for (Frame *f : la->pool) frame_free(f);
     for (Decision &d : la->outq) if (d.h_qp) cudaFreeHost(d.h_qp);
     for (float *q : la->qp_free) cudaFreeHost(q);
     cudaFree(la->d_cost_mv); cudaFree(la->d_log2_lut); cudaFree(la->d_exp2_lut); cudaFree(la->d_weight_buf);
-    cudaFree(la->d_rec); cudaFree(la->d_ticket); cudaFree(la->d_results); cudaFree(la->d_wscore); cudaFree(la->d_planes); cudaFree(la->d_src);
+    for (int e = 0; e <= ME_SIDE; e++) {
+        cudaFree(la->d_rec[e]); cudaFree(la->d_ticket[e]);
+        for (int k = 0; k < ME_EVENTS; k++) if (la->ev_me[e][k]) cudaEventDestroy(la->ev_me[e][k]);
+        if (e && la->st_me[e]) cudaStreamDestroy(la->st_me[e]);
+    }
+    if (la->ev_ready) cudaEventDestroy(la->ev_ready); cudaFree(la->d_results); cudaFree(la->d_wscore); cudaFree(la->d_planes); cudaFree(la->d_src);
     if (la->h_results) cudaFreeHost(la->h_results);
     if (la->h_wscore) cudaFreeHost(la->h_wscore);
     if (la->st) cudaStreamDestroy(la->st);
@@ -1115,6 +1196,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
 {
     La *la = (La *)h;
     if (!la || !src) { set_error("null argument"); return -1; }
+    const double t_begin = now_s();
     XV_CUDA_OK(cudaSetDevice(la->device));
     const int w = la->p.width, hgt = la->p.height;
     const int in = la->in_csp & X264VFW_CUDA_CSP_MASK;
@@ -1193,8 +1275,11 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
 
     if (speculate_searches(la, f) < 0) return -1;
     la->next.push_back(f);      // [x264] x264_lookahead_put_frame
+    const double t_mid = now_s();
+    la->t_put += t_mid - t_begin;
     while ((int)la->next.size() > la->slicetype_length)
         if (decide_and_shift(la) < 0) return -1;
+    la->t_decide += now_s() - t_mid;
     if (conv_pic || !src_on_device) XV_CUDA_OK(cudaStreamSynchronize(la->st));   // caller's buffers are borrowed for the call only
     return (int)la->outq.size();
 }
@@ -1255,6 +1340,7 @@ int64_t x264vfw_cuda_la_read(x264vfw_cuda_la *h, int frame, int what, int a, int
     if (!la || !dst) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
     if (la_sync(la) < 0) return -1;
+    for (int e = 1; e <= ME_SIDE; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
     const int n = la->g.mb_count, B = la->p.bframes;
     if (what == X264VFW_CUDA_LA_CONV_PLANES) {
         if (cap < la->d_planes_bytes) { set_error("read: buffer too small"); return -1; }
@@ -1298,6 +1384,8 @@ int x264vfw_cuda_la_profile(x264vfw_cuda_la *h, int enable, double ms[8], uint64
     if (!la) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
     if (la_sync(la) < 0) return -1;
+    for (int e = 1; e <= ME_SIDE; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
+    prof_resolve(la);
     for (int i = 0; i < K_N; i++) { if (ms) ms[i] = la->prof.ms[i]; if (count) count[i] = la->prof.n[i]; }
     if (enable >= 0) {
         la->prof.on = enable != 0;
@@ -1306,11 +1394,12 @@ int x264vfw_cuda_la_profile(x264vfw_cuda_la *h, int enable, double ms[8], uint64
     return 0;
 }
 
-void x264vfw_cuda_la_counters(x264vfw_cuda_la *h, uint64_t out[4])
+void x264vfw_cuda_la_counters(x264vfw_cuda_la *h, uint64_t out[8])
 {
     La *la = (La *)h;
     if (!la) return;
     out[0] = la->n_frame_cost; out[1] = la->n_mb_search; out[2] = la->n_launch; out[3] = la->n_sync;
+    out[4] = (uint64_t)(la->t_put * 1e6); out[5] = (uint64_t)(la->t_decide * 1e6); out[6] = (uint64_t)(la->t_sync * 1e6); out[7] = (uint64_t)la->n_input;
 }
 
 } // extern "C"

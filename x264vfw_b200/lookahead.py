@@ -195,9 +195,10 @@ class Lookahead:
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
 
     def counters(self):
-        c = (C.c_uint64 * 4)()
+        c = (C.c_uint64 * 8)()
         lib.x264vfw_cuda_la_counters(self.h, c)
-        return dict(frame_costs=int(c[0]), mb_searches=int(c[1]), launches=int(c[2]), syncs=int(c[3]))
+        return dict(frame_costs=int(c[0]), mb_searches=int(c[1]), launches=int(c[2]), syncs=int(c[3]),
+                    put_us=int(c[4]), decide_us=int(c[5]), sync_us=int(c[6]), frames=int(c[7]))
 
 
 def smoke_check(ctx=None):
