@@ -53,17 +53,17 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_clips(n_streams, n_frames, first_stream):
+def make_clips(stream_ids, n_frames):
     """Per-stream packed BGRA clips (numpy, host)."""
     from concurrent.futures import ThreadPoolExecutor
     from x264vfw_b200.clipgen import SyntheticClip
 
     def one(s):
-        clip = SyntheticClip(W, H, n_frames=n_frames, stream_id=first_stream + s, cuts=(n_frames * 5 // 8,), flash=n_frames // 4, flash_len=1)
+        clip = SyntheticClip(W, H, n_frames=n_frames, stream_id=s, cuts=(n_frames * 5 // 8,), flash=n_frames // 4, flash_len=1)
         return [clip.packed(n, "bgra") for n in range(n_frames)]
 
-    with ThreadPoolExecutor(max_workers=min(8, n_streams)) as ex:
-        return list(ex.map(one, range(n_streams)))
+    with ThreadPoolExecutor(max_workers=min(8, len(stream_ids))) as ex:
+        return list(ex.map(one, stream_ids))
 
 
 class ClockSampler(threading.Thread):
@@ -188,13 +188,9 @@ def run_phase(torch, dist, sessions, frames, on_device, conv, args, rank, world,
     for wkr in workers:
         wkr.stop_flag = True
     bin_.wait()
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        l = torch.tensor([launches], device="cuda", dtype=torch.int64)
-        dist.all_reduce(l, op=dist.ReduceOp.SUM)
-        launches = int(l.item())
+    from x264vfw_b200.sharding import max_over_ranks, sum_over_ranks
+    ms = max_over_ranks(ms, device="cuda")                  # slowest rank defines the step
+    launches = sum_over_ranks(launches, device="cuda")
     return ms / args.steps, clocks, launches, prof
 
 
@@ -273,7 +269,7 @@ def main_reference(args):
     cores = os.cpu_count() or 1
     n_streams = max(1, min(cores, args.streams * max(1, args.gpus)))
     fps_list = []
-    clips = make_clips(min(n_streams, 8), 12, 0)
+    clips = make_clips(list(range(min(n_streams, 8))), 12)
     clips = [clips[i % len(clips)] for i in range(n_streams)]
     frames_per_stream = 12
     total_steps = args.warmup + args.steps
@@ -320,7 +316,10 @@ def main():
     n_gpus = world
     S, F = args.streams, args.frames_per_step
 
-    clips = make_clips(S, args.clip_frames, rank * S)
+    from x264vfw_b200.sharding import streams_of_rank
+    my_streams = streams_of_rank(S * world, rank, world)   # global stream ids of this rank (S per GPU)
+    assert len(my_streams) == S
+    clips = make_clips(my_streams, args.clip_frames)
     # device-resident copies (value) and pinned host copies (e2e)
     dev_frames = [[torch.from_numpy(f).cuda() for f in clip] for clip in clips]
     dev_ptrs = [[t.data_ptr() for t in clip] for clip in dev_frames]
@@ -353,7 +352,7 @@ def main():
             la.close()
         mb = sessions[0].mb_count
         e2e = {"value": frames_per_step_all / (ms_e2e * 1e-3), "unit": "frames/s",
-               "h2d_bytes_per_step": S * F * SRC_BYTES, "d2h_bytes_per_step": S * F * (DST_BYTES + 2 * 4 * mb + 32),
+               "h2d_bytes_per_step": n_gpus * S * F * SRC_BYTES, "d2h_bytes_per_step": n_gpus * S * F * (DST_BYTES + 2 * 4 * mb + 32),
                "ms_per_step": ms_e2e}
 
     if rank != 0:

@@ -1,0 +1,153 @@
+/*
+ * x264vfw_harness.c -- plain-C host side above the C ABI, mirroring the call order of the
+ * reference's codec session (codec.c:1381-1876) for the hot path only:
+ *
+ *   harness_compress_begin  ~ x264vfw_compress_begin (codec.c:1381): csp from the BITMAPINFOHEADER
+ *                             (get_csp :187-231, choose_output_csp :269-302), x264vfw_csp_init (:1672),
+ *                             conv_pic allocation (:1673), encoder/lookahead open (:1623)
+ *   harness_compress        ~ x264vfw_compress (codec.c:1728): img_fill (:1767), convert (:1774),
+ *                             x264_encoder_encode (:1693) -> here: lookahead put + decisions
+ *   harness_compress_end    ~ x264vfw_compress_end (codec.c:1838): flush (:1848-1854), close (:1857)
+ *
+ * It is a Linux stand-in for the Win32 caller, not a re-implementation of the wrapper: no ICM
+ * messages, no registry, no muxers.  Build: make -C host.  Usage: see main() below.
+ */
+#include "../include/x264vfw_cuda.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    int biWidth, biHeight, biBitCount;
+    unsigned biCompression;              /* 0 = BI_RGB, else FOURCC */
+} harness_bih;
+
+typedef struct {
+    x264vfw_cuda_la *la;
+    x264vfw_cuda_csp_function_t csp;     /* codec->csp */
+    x264vfw_cuda_image_t conv_pic;       /* codec->conv_pic.img */
+    uint8_t *conv_buf;
+    int i_csp, i_x264_csp, width, height, mb_count;
+    int b_encoder_error;                 /* x264vfw.h:193 */
+    float *qp, *qp_aq;
+} harness_codec;
+
+#define FOURCC(a, b, c, d) ((unsigned)(a) | ((unsigned)(b) << 8) | ((unsigned)(c) << 16) | ((unsigned)(d) << 24))
+
+static int get_csp(const harness_bih *h)            /* codec.c:187-231 */
+{
+    switch (h->biCompression) {
+    case FOURCC('I', '4', '2', '0'): case FOURCC('I', 'Y', 'U', 'V'): return X264VFW_CUDA_CSP_I420;
+    case FOURCC('Y', 'V', '1', '2'): return X264VFW_CUDA_CSP_YV12;
+    case FOURCC('Y', 'V', '1', '6'): return X264VFW_CUDA_CSP_YV16;
+    case FOURCC('Y', 'V', '2', '4'): return X264VFW_CUDA_CSP_YV24;
+    case FOURCC('N', 'V', '1', '2'): return X264VFW_CUDA_CSP_NV12;
+    case FOURCC('Y', 'U', 'Y', 'V'): case FOURCC('Y', 'U', 'Y', '2'): return X264VFW_CUDA_CSP_YUYV;
+    case FOURCC('U', 'Y', 'V', 'Y'): case FOURCC('H', 'D', 'Y', 'C'): return X264VFW_CUDA_CSP_UYVY;
+    case 0: {
+        int flip = h->biHeight < 0 ? 0 : X264VFW_CUDA_CSP_VFLIP;
+        if (h->biBitCount == 24) return X264VFW_CUDA_CSP_BGR | flip;
+        if (h->biBitCount == 32) return X264VFW_CUDA_CSP_BGRA | flip;
+    }
+    }
+    return X264VFW_CUDA_CSP_NONE;
+}
+
+static int choose_output_csp(int i_csp, int keep)    /* codec.c:269-302 */
+{
+    switch (i_csp & X264VFW_CUDA_CSP_MASK) {
+    case X264VFW_CUDA_CSP_YV16: return keep ? X264VFW_CUDA_OUT_I422 : X264VFW_CUDA_OUT_I420;
+    case X264VFW_CUDA_CSP_YV24: return keep ? X264VFW_CUDA_OUT_I444 : X264VFW_CUDA_OUT_I420;
+    case X264VFW_CUDA_CSP_NV12: return X264VFW_CUDA_OUT_NV12;
+    case X264VFW_CUDA_CSP_YUYV: case X264VFW_CUDA_CSP_UYVY: return keep ? X264VFW_CUDA_OUT_I422 : X264VFW_CUDA_OUT_I420;
+    case X264VFW_CUDA_CSP_BGR: return keep ? X264VFW_CUDA_OUT_BGR : X264VFW_CUDA_OUT_I420;
+    case X264VFW_CUDA_CSP_BGRA: return keep ? X264VFW_CUDA_OUT_BGRA : X264VFW_CUDA_OUT_I420;
+    default: return X264VFW_CUDA_OUT_I420;
+    }
+}
+
+int harness_compress_begin(harness_codec *c, const harness_bih *in, const char *preset, int keep_input_csp)
+{
+    memset(c, 0, sizeof(*c));
+    c->width = in->biWidth; c->height = abs(in->biHeight);
+    if (c->width <= 0 || c->height <= 0 || (c->width & 1) || (c->height & 1)) return -1;       /* codec.c:639 */
+    c->i_csp = get_csp(in);
+    if (c->i_csp == X264VFW_CUDA_CSP_NONE) return -1;
+    c->i_x264_csp = choose_output_csp(c->i_csp, keep_input_csp);                                /* codec.c:1472 */
+    /* colour matrix / range defaults for YUV targets: undef -> BT.601, TV range (codec.c:1571-1577) */
+    const int colmatrix = 2, fullrange = 0;
+    x264vfw_cuda_la_params p;
+    if (x264vfw_cuda_la_params_preset(&p, preset, c->width, c->height) < 0) return -1;          /* codec.c:1463 */
+    p.chroma_format = c->i_x264_csp == X264VFW_CUDA_OUT_I444 ? 3 : c->i_x264_csp == X264VFW_CUDA_OUT_I422 ? 2 : 1;
+    /* the session converts on the device and mirrors conv_pic back for the CPU encoder */
+    if (x264vfw_cuda_la_open(&c->la, &p, -1, c->i_csp, c->i_x264_csp, colmatrix, fullrange, 0) < 0) return -1;   /* codec.c:1623 */
+    x264vfw_cuda_csp_init(&c->csp, c->i_x264_csp, colmatrix, fullrange);                        /* codec.c:1672 */
+    int64_t n = x264vfw_cuda_picture_layout(&c->conv_pic, NULL, c->i_x264_csp, c->width, c->height);   /* codec.c:1673 */
+    if (n < 0) return -1;
+    c->conv_buf = malloc((size_t)n);
+    x264vfw_cuda_picture_layout(&c->conv_pic, c->conv_buf, c->i_x264_csp, c->width, c->height);
+    c->mb_count = ((c->width + 15) >> 4) * ((c->height + 15) >> 4);
+    c->qp = malloc(sizeof(float) * c->mb_count);
+    c->qp_aq = malloc(sizeof(float) * c->mb_count);
+    return 0;
+}
+
+static void drain(harness_codec *c, FILE *out)
+{
+    x264vfw_cuda_la_decision d;
+    while (x264vfw_cuda_la_get_decision(c->la, &d, c->qp, c->qp_aq) == 1) {
+        /* here the reference would call x264_encoder_encode with pic_in.i_type = d.i_type and
+         * pic_in.prop.quant_offsets = qp - qp_aq */
+        double s = 0;
+        for (int i = 0; i < d.mb_count; i++) s += c->qp[i];
+        if (out) fprintf(out, "frame %d type %d key %d cost %d mean_qp_offset %.4f\n", d.i_frame, d.i_type, d.b_keyframe, d.i_cost_est, s / d.mb_count);
+    }
+}
+
+int harness_compress(harness_codec *c, uint8_t *lpInput, FILE *out)
+{
+    if (c->b_encoder_error) return -1;
+    x264vfw_cuda_image_t pic;
+    if (x264vfw_cuda_img_fill(&pic, lpInput, c->i_csp, c->width, c->height) < 0) { c->b_encoder_error = 1; return -1; }   /* codec.c:1767 */
+    /* codec.c:1774 + :1693 in one call: convert on the device, keep the planes there for the
+     * lookahead, and return them in conv_pic for the CPU encoder */
+    if (x264vfw_cuda_la_put_frame(c->la, &pic, 0, &c->conv_pic) < 0) { c->b_encoder_error = 1; return -1; }              /* codec.c:1776-1778 */
+    drain(c, out);
+    return 0;
+}
+
+int harness_compress_end(harness_codec *c, FILE *out)
+{
+    if (c->la && !c->b_encoder_error) { x264vfw_cuda_la_flush(c->la); drain(c, out); }          /* codec.c:1842-1856 */
+    x264vfw_cuda_la_close(c->la);                                                               /* codec.c:1857 */
+    free(c->conv_buf); free(c->qp); free(c->qp_aq);                                             /* codec.c:1872 */
+    memset(c, 0, sizeof(*c));
+    return 0;
+}
+
+#ifndef HARNESS_NO_MAIN
+/* usage: x264vfw_harness <w> <h> <frames> [preset]   -- encodes a synthetic bottom-up RGB32 clip */
+int main(int argc, char **argv)
+{
+    const int w = argc > 1 ? atoi(argv[1]) : 320, h = argc > 2 ? atoi(argv[2]) : 192, n = argc > 3 ? atoi(argv[3]) : 30;
+    const char *preset = argc > 4 ? argv[4] : "medium";
+    harness_bih bih = {w, h, 32, 0};
+    harness_codec codec;
+    if (harness_compress_begin(&codec, &bih, preset, 0) < 0) { fprintf(stderr, "begin failed: %s\n", x264vfw_cuda_last_error()); return 1; }
+    uint8_t *buf = malloc((size_t)w * h * 4);
+    unsigned s = 0x264;
+    for (int f = 0; f < n; f++) {
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                s = s * 1664525u + 1013904223u;
+                uint8_t *px = buf + ((size_t)y * w + x) * 4;
+                int v = ((x + 2 * f) >> 3 ^ (y + f) >> 3) & 1 ? 180 : 60;
+                px[0] = (uint8_t)(v + (s >> 30)); px[1] = (uint8_t)(v / 2 + (x & 63)); px[2] = (uint8_t)(255 - v); px[3] = 0;
+            }
+        if (harness_compress(&codec, buf, stdout) < 0) { fprintf(stderr, "compress failed: %s\n", x264vfw_cuda_last_error()); return 1; }
+    }
+    harness_compress_end(&codec, stdout);
+    free(buf);
+    return 0;
+}
+#endif
