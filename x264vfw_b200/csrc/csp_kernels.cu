@@ -21,22 +21,31 @@ namespace xv {
 // RGB -> 4:2:0.  One thread = 4 pixels x 2 rows (one 16-byte BGRA load per row, or 12 bytes
 // of BGR24), producing 2x4 Y, 2 U, 2 V.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t luma_px(const RgbCoef &c, uint32_t p)
+// The reference arithmetic is Y = (Y_ADD + Y_R*r + Y_G*g + Y_B*b) >> 20 in uint32 (csp.c:334-337).
+// The kernel is integer-pipe bound if done with per-channel extraction + IMAD, so the three
+// products are evaluated with the integer dot-product unit instead, exactly:
+//   16*coef = hi*256 + lo  (hi < 2^16, lo < 2^8)  =>  16*sum = ((dp2a(hi, px)) << 8) + dp4a(lo, px) + 16*Y_ADD
+// and Y is then the top byte of the 32-bit result (16 * 2^20 = 2^24).  All intermediate values
+// stay below 2^32 (max 16*(524288 + 1048576*255) = 4,286,578,688), so nothing wraps.
+__device__ __forceinline__ uint32_t luma16(const RgbKernelCoef &k, uint32_t p)
 {
-    // p = B | G<<8 | R<<16 | (don't care)<<24          csp.c:334-337
-    uint32_t b = p & 0xff, g = (p >> 8) & 0xff, r = (p >> 16) & 0xff;
-    return ((c.y_add + c.y_r * r + c.y_g * g + c.y_b * b) >> 20) & 0xff;
+    // p = B | G<<8 | R<<16 | X<<24; the X byte meets a zero coefficient
+    const uint32_t t = __dp2a_hi(k.y_rx_hi, p, __dp2a_lo(k.y_bg_hi, p, 0u));
+    return (t << 8) + __dp4a(p, k.y_lo, k.y_add16);
 }
 
-__device__ __forceinline__ void chroma_quad(const RgbCoef &c, uint32_t p00, uint32_t p01,
+// U/V from the sums over the 2x2 quad (csp.c:371-379).  Channel sums are formed two at a
+// time in 16-bit lanes (B|R and G|X); the subtractions are additions of the negated
+// coefficients mod 2^32, which is the same uint32 arithmetic as the reference.
+__device__ __forceinline__ void chroma_quad(const RgbKernelCoef &k, uint32_t p00, uint32_t p01,
                                             uint32_t p10, uint32_t p11, uint32_t &u, uint32_t &v)
 {
-    // sums over the 2x2 quad, then one U and one V            csp.c:371-379
-    uint32_t cb = (p00 & 0xff) + (p01 & 0xff) + (p10 & 0xff) + (p11 & 0xff);
-    uint32_t cg = ((p00 >> 8) & 0xff) + ((p01 >> 8) & 0xff) + ((p10 >> 8) & 0xff) + ((p11 >> 8) & 0xff);
-    uint32_t cr = ((p00 >> 16) & 0xff) + ((p01 >> 16) & 0xff) + ((p10 >> 16) & 0xff) + ((p11 >> 16) & 0xff);
-    u = ((c.u_add + c.u_b * cb - c.u_r * cr - c.u_g * cg) >> 22) & 0xff;
-    v = ((c.v_add + c.v_r * cr - c.v_g * cg - c.v_b * cb) >> 22) & 0xff;
+    const uint32_t br = (p00 & 0x00ff00ffu) + (p01 & 0x00ff00ffu) + (p10 & 0x00ff00ffu) + (p11 & 0x00ff00ffu);
+    const uint32_t gx = __byte_perm(p00, 0, 0x4341) + __byte_perm(p01, 0, 0x4341) +
+                        __byte_perm(p10, 0, 0x4341) + __byte_perm(p11, 0, 0x4341);
+    const uint32_t cb = br & 0xffffu, cr = br >> 16, cg = gx & 0xffffu;
+    u = ((k.u_add + k.u_b * cb + k.u_r_neg * cr + k.u_g_neg * cg) >> 22) & 0xff;
+    v = ((k.v_add + k.v_r * cr + k.v_g_neg * cg + k.v_b_neg * cb) >> 22) & 0xff;
 }
 
 template <int BPP, bool VEC>
@@ -48,9 +57,10 @@ __device__ __forceinline__ void load_px4(const uint8_t *p, int npx, uint32_t px[
             px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
         } else {
             uint32_t w0 = ldg_stream32(p), w1 = ldg_stream32(p + 4), w2 = ldg_stream32(p + 8);
+            // byte 3 of each word is junk: it only ever meets a zero coefficient / an unused lane
             px[0] = w0;
-            px[1] = __byte_perm(w0, w1, 0x0543);
-            px[2] = __byte_perm(w1, w2, 0x0432);
+            px[1] = __byte_perm(w0, w1, 0x3543);
+            px[2] = __byte_perm(w1, w2, 0x3432);
             px[3] = w2 >> 8;
         }
     } else {
@@ -63,76 +73,119 @@ __device__ __forceinline__ void load_px4(const uint8_t *p, int npx, uint32_t px[
     }
 }
 
-template <int BPP, bool NV12, bool VEC>
+// Fast path: width % 4 == 0 and every pointer/stride aligned (checked on the host).  One thread
+// converts a 4-pixel column chunk of TWO row pairs (4 source rows): four independent 128-bit
+// loads in flight per thread, address arithmetic shared between the pairs.
+template <int BPP, bool NV12>
 __global__ void __launch_bounds__(256)
-rgb_to_420_kernel(RgbJob job)
+rgb_to_420_fast_kernel(RgbJob job)
 {
-    const int nchunk = (job.w + 3) >> 2;
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair0 = 2 * (blockIdx.y * blockDim.y + threadIdx.y);
     const int npair = job.h >> 1;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nchunk * npair) return;
-    const int pair = idx / nchunk;
-    const int chunk = idx - pair * nchunk;
+    if (chunk >= (job.w >> 2) || pair0 >= npair) return;
     const int x = chunk << 2;
-    const int npx = min(4, job.w - x);
-    const size_t f = blockIdx.y;
+    const size_t f = blockIdx.z;
+    const bool two = pair0 + 1 < npair;
 
-    const uint8_t *s0 = job.src + f * job.src_frame_bytes + (ptrdiff_t)(2 * pair) * job.src_stride + x * BPP;
-    const uint8_t *s1 = s0 + job.src_stride;
-    uint32_t t[4], b[4];
-    load_px4<BPP, VEC>(s0, npx, t);
-    load_px4<BPP, VEC>(s1, npx, b);
-
-    uint32_t yt = 0, yb = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        yt |= luma_px(job.c, t[i]) << (8 * i);
-        yb |= luma_px(job.c, b[i]) << (8 * i);
+    const uint8_t *s = job.src + f * job.src_frame_bytes + (ptrdiff_t)(2 * pair0) * job.src_stride + x * BPP;
+    uint32_t r[4][4];
+    load_px4<BPP, true>(s, 4, r[0]);
+    load_px4<BPP, true>(s + job.src_stride, 4, r[1]);
+    if (two) {
+        load_px4<BPP, true>(s + 2 * job.src_stride, 4, r[2]);
+        load_px4<BPP, true>(s + 3 * job.src_stride, 4, r[3]);
     }
-    uint32_t u0, v0, u1, v1;
-    chroma_quad(job.c, t[0], b[0], t[1], b[1], u0, v0);
-    chroma_quad(job.c, t[2], b[2], t[3], b[3], u1, v1);
-
-    uint8_t *dy = job.dst_y + f * job.dst_frame_bytes + (size_t)(2 * pair) * job.y_stride + x;
-    uint8_t *du = job.dst_u + f * job.dst_frame_bytes + (size_t)pair * job.u_stride;
-    uint8_t *dv = job.dst_v + f * job.dst_frame_bytes + (size_t)pair * job.v_stride;
-    if (VEC && npx == 4) {
-        *(uint32_t *)dy = yt;
-        *(uint32_t *)(dy + job.y_stride) = yb;
+    uint8_t *dy = job.dst_y + f * job.dst_frame_bytes + (size_t)(2 * pair0) * job.y_stride + x;
+    uint8_t *du = job.dst_u + f * job.dst_frame_bytes + (size_t)pair0 * job.u_stride;
+    uint8_t *dv = job.dst_v + f * job.dst_frame_bytes + (size_t)pair0 * job.v_stride;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        if (p == 1 && !two) break;
+        const uint32_t *t = r[2 * p], *b = r[2 * p + 1];
+        const uint32_t yt = __byte_perm(__byte_perm(luma16(job.k, t[0]), luma16(job.k, t[1]), 0x0073),
+                                        __byte_perm(luma16(job.k, t[2]), luma16(job.k, t[3]), 0x0073), 0x5410);
+        const uint32_t yb = __byte_perm(__byte_perm(luma16(job.k, b[0]), luma16(job.k, b[1]), 0x0073),
+                                        __byte_perm(luma16(job.k, b[2]), luma16(job.k, b[3]), 0x0073), 0x5410);
+        uint32_t u0, v0, u1, v1;
+        chroma_quad(job.k, t[0], b[0], t[1], b[1], u0, v0);
+        chroma_quad(job.k, t[2], b[2], t[3], b[3], u1, v1);
+        *(uint32_t *)(dy + (size_t)(2 * p) * job.y_stride) = yt;
+        *(uint32_t *)(dy + (size_t)(2 * p + 1) * job.y_stride) = yb;
         if (NV12) {
-            *(uint32_t *)(du + x) = u0 | (v0 << 8) | (u1 << 16) | (v1 << 24);
+            *(uint32_t *)(du + (size_t)p * job.u_stride + x) = u0 | (v0 << 8) | (u1 << 16) | (v1 << 24);
         } else {
-            *(uint16_t *)(du + (x >> 1)) = (uint16_t)(u0 | (u1 << 8));
-            *(uint16_t *)(dv + (x >> 1)) = (uint16_t)(v0 | (v1 << 8));
-        }
-    } else {
-        for (int i = 0; i < npx; i++) {
-            dy[i] = (uint8_t)(yt >> (8 * i));
-            dy[job.y_stride + i] = (uint8_t)(yb >> (8 * i));
-        }
-        for (int q = 0; q < (npx >> 1); q++) {
-            uint32_t u = q ? u1 : u0, v = q ? v1 : v0;
-            if (NV12) { du[x + 2 * q] = (uint8_t)u; du[x + 2 * q + 1] = (uint8_t)v; }
-            else      { du[(x >> 1) + q] = (uint8_t)u; dv[(x >> 1) + q] = (uint8_t)v; }
+            *(uint16_t *)(du + (size_t)p * job.u_stride + (x >> 1)) = (uint16_t)(u0 | (u1 << 8));
+            *(uint16_t *)(dv + (size_t)p * job.v_stride + (x >> 1)) = (uint16_t)(v0 | (v1 << 8));
         }
     }
 }
 
-int launch_rgb_to_420(cudaStream_t st, const RgbJob &job, int bpp, bool nv12, bool vec, int n_frames)
+// General path: any even width, any alignment (byte loads/stores).  Same arithmetic.
+template <int BPP, bool NV12>
+__global__ void __launch_bounds__(256)
+rgb_to_420_kernel(RgbJob job)
 {
-    const int nchunk = (job.w + 3) >> 2, npair = job.h >> 1;
-    const long long total = (long long)nchunk * npair;
-    if (total <= 0 || n_frames <= 0) return 0;
-    dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_frames);
-#define XV_RGB(B, N, V) rgb_to_420_kernel<B, N, V><<<grid, 256, 0, st>>>(job)
-    if (bpp == 4) {
-        if (nv12) { if (vec) XV_RGB(4, true, true); else XV_RGB(4, true, false); }
-        else      { if (vec) XV_RGB(4, false, true); else XV_RGB(4, false, false); }
-    } else {
-        if (nv12) { if (vec) XV_RGB(3, true, true); else XV_RGB(3, true, false); }
-        else      { if (vec) XV_RGB(3, false, true); else XV_RGB(3, false, false); }
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair = blockIdx.y * blockDim.y + threadIdx.y;
+    const int nchunk = (job.w + 3) >> 2;
+    if (chunk >= nchunk || pair >= (job.h >> 1)) return;
+    const int x = chunk << 2;
+    const int npx = min(4, job.w - x);
+    const size_t f = blockIdx.z;
+
+    const uint8_t *s0 = job.src + f * job.src_frame_bytes + (ptrdiff_t)(2 * pair) * job.src_stride + x * BPP;
+    const uint8_t *s1 = s0 + job.src_stride;
+    uint32_t t[4], b[4];
+    load_px4<BPP, false>(s0, npx, t);
+    load_px4<BPP, false>(s1, npx, b);
+    const uint32_t yt = __byte_perm(__byte_perm(luma16(job.k, t[0]), luma16(job.k, t[1]), 0x0073),
+                                    __byte_perm(luma16(job.k, t[2]), luma16(job.k, t[3]), 0x0073), 0x5410);
+    const uint32_t yb = __byte_perm(__byte_perm(luma16(job.k, b[0]), luma16(job.k, b[1]), 0x0073),
+                                    __byte_perm(luma16(job.k, b[2]), luma16(job.k, b[3]), 0x0073), 0x5410);
+    uint32_t u0, v0, u1, v1;
+    chroma_quad(job.k, t[0], b[0], t[1], b[1], u0, v0);
+    chroma_quad(job.k, t[2], b[2], t[3], b[3], u1, v1);
+
+    uint8_t *dy = job.dst_y + f * job.dst_frame_bytes + (size_t)(2 * pair) * job.y_stride + x;
+    uint8_t *du = job.dst_u + f * job.dst_frame_bytes + (size_t)pair * job.u_stride;
+    uint8_t *dv = job.dst_v + f * job.dst_frame_bytes + (size_t)pair * job.v_stride;
+    for (int i = 0; i < npx; i++) {
+        dy[i] = (uint8_t)(yt >> (8 * i));
+        dy[job.y_stride + i] = (uint8_t)(yb >> (8 * i));
     }
-#undef XV_RGB
+    for (int q = 0; q < (npx >> 1); q++) {
+        uint32_t u = q ? u1 : u0, v = q ? v1 : v0;
+        if (NV12) { du[x + 2 * q] = (uint8_t)u; du[x + 2 * q + 1] = (uint8_t)v; }
+        else      { du[(x >> 1) + q] = (uint8_t)u; dv[(x >> 1) + q] = (uint8_t)v; }
+    }
+}
+
+int launch_rgb_to_420(cudaStream_t st, const RgbJob &job_in, int bpp, bool nv12, bool vec, int n_frames)
+{
+    RgbJob job = job_in;
+    const int nchunk = (job.w + 3) >> 2, npair = job.h >> 1;
+    if (nchunk <= 0 || npair <= 0 || n_frames <= 0) return 0;
+    // kernel-side coefficient forms (exact re-encodings of csp.c:252-297, see luma16 / chroma_quad)
+    const RgbCoef &c = job.c;
+    RgbKernelCoef &k = job.k;
+    const uint32_t yb = c.y_b << 4, yg = c.y_g << 4, yr = c.y_r << 4;
+    k.y_bg_hi = (yb >> 8) | ((yg >> 8) << 16);
+    k.y_rx_hi = (yr >> 8);
+    k.y_lo = (yb & 0xff) | ((yg & 0xff) << 8) | ((yr & 0xff) << 16);
+    k.y_add16 = c.y_add << 4;
+    k.u_add = c.u_add; k.u_b = c.u_b; k.u_r_neg = 0u - c.u_r; k.u_g_neg = 0u - c.u_g;
+    k.v_add = c.v_add; k.v_r = c.v_r; k.v_g_neg = 0u - c.v_g; k.v_b_neg = 0u - c.v_b;
+    const dim3 block(128, 2);
+    if (vec && (job.w & 3) == 0) {
+        const dim3 grid((unsigned)(((job.w >> 2) + 127) / 128), (unsigned)((npair + 3) / 4), (unsigned)n_frames);
+        if (bpp == 4) { if (nv12) rgb_to_420_fast_kernel<4, true><<<grid, block, 0, st>>>(job); else rgb_to_420_fast_kernel<4, false><<<grid, block, 0, st>>>(job); }
+        else          { if (nv12) rgb_to_420_fast_kernel<3, true><<<grid, block, 0, st>>>(job); else rgb_to_420_fast_kernel<3, false><<<grid, block, 0, st>>>(job); }
+    } else {
+        const dim3 grid((unsigned)((nchunk + 127) / 128), (unsigned)((npair + 1) / 2), (unsigned)n_frames);
+        if (bpp == 4) { if (nv12) rgb_to_420_kernel<4, true><<<grid, block, 0, st>>>(job); else rgb_to_420_kernel<4, false><<<grid, block, 0, st>>>(job); }
+        else          { if (nv12) rgb_to_420_kernel<3, true><<<grid, block, 0, st>>>(job); else rgb_to_420_kernel<3, false><<<grid, block, 0, st>>>(job); }
+    }
     XV_LAUNCH_CHECK();
     return 0;
 }

@@ -13,6 +13,13 @@ struct RgbCoef {
     uint32_t v_r, v_g, v_b, v_add;
 };
 
+// The same coefficients re-encoded for the kernel's dot-product form (launch_rgb_to_420 fills it).
+struct RgbKernelCoef {
+    uint32_t y_bg_hi, y_rx_hi, y_lo, y_add16;
+    uint32_t u_add, u_b, u_r_neg, u_g_neg;
+    uint32_t v_add, v_r, v_g_neg, v_b_neg;
+};
+
 struct RgbJob {
     const uint8_t *src; ptrdiff_t src_stride;     // negative stride = bottom-up DIB
     uint8_t *dst_y, *dst_u, *dst_v;               // NV12: dst_u = interleaved plane, dst_v unused
@@ -20,6 +27,7 @@ struct RgbJob {
     int w, h;
     size_t src_frame_bytes, dst_frame_bytes;
     RgbCoef c;
+    RgbKernelCoef k;
 };
 
 struct PackedJob {

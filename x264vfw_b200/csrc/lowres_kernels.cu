@@ -39,16 +39,13 @@ __device__ __forceinline__ uint32_t filt(uint32_t a, uint32_t b, uint32_t c, uin
     return (((a + b + 1) >> 1) + ((c + d + 1) >> 1) + 1) >> 1;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 lowres_init_kernel(LowresJob job)
 {
-    const int chunks = (job.lw + 2 * LOWRES_PAD) >> 3;
-    const int rows = job.lh + 2 * LOWRES_PAD;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= chunks * rows) return;
-    const int prow = idx / chunks;
-    const int pchunk = idx - prow * chunks;
-    const size_t f = blockIdx.y;
+    const int pchunk = blockIdx.x * blockDim.x + threadIdx.x;       // 8-px chunk of the padded row
+    const int prow = blockIdx.y * blockDim.y + threadIdx.y;          // padded row
+    if (pchunk >= ((job.lw + 2 * LOWRES_PAD) >> 3) || prow >= job.lh + 2 * LOWRES_PAD) return;
+    const size_t f = blockIdx.z;
     const uint8_t *Y = job.y + f * job.src_frame_bytes;
     const int ys = job.y_stride, w = job.w, h = job.h;
 
@@ -59,29 +56,33 @@ lowres_init_kernel(LowresJob job)
 
     uint2 o0, oh, ov, oc;
     const int sx = 2 * lx;
-    if (lx >= 0 && lx + 8 <= job.lw && sx + 17 <= w && ((ys | (int)(uintptr_t)Y) & 15) == 0) {
-        // fast path: 16 source bytes per row + the 17th from the next chunk
-        uint4 a = *(const uint4 *)(s0 + sx), b = *(const uint4 *)(s1 + sx), c = *(const uint4 *)(s2 + sx);
-        uint32_t ta = s0[sx + 16], tb = s1[sx + 16], tc = s2[sx + 16];
+    if (lx >= 0 && lx + 8 <= job.lw && sx + 16 <= w && ((ys | (int)(uintptr_t)Y) & 15) == 0) {
+        // interior: 16 source bytes per row + the 17th column (clamped: it is the duplicated
+        // last column at the right frame edge)
+        const uint4 a = *(const uint4 *)(s0 + sx), b = *(const uint4 *)(s1 + sx), c = *(const uint4 *)(s2 + sx);
+        const int tx = min(sx + 16, w - 1);
+        const uint32_t ta = s0[tx], tb = s1[tx], tc = s2[tx];
         hphase(avg16(a, b), (ta + tb + 1) >> 1, o0, oh);
         hphase(avg16(b, c), (tb + tc + 1) >> 1, ov, oc);
+    } else if (lx + 8 <= 0 || lx >= job.lw) {
+        // left/right padding: the whole chunk replicates the first/last lowres column
+        const int x = lx < 0 ? 0 : job.lw - 1;
+        const int c0 = min(2 * x, w - 1), c1 = min(2 * x + 1, w - 1), c2 = min(2 * x + 2, w - 1);
+        const uint32_t a0 = s0[c0], a1 = s0[c1], a2 = s0[c2], b0 = s1[c0], b1 = s1[c1], b2 = s1[c2];
+        const uint32_t d0 = s2[c0], d1 = s2[c1], d2 = s2[c2];
+        const uint32_t v0 = filt(a0, b0, a1, b1) * 0x01010101u, vh = filt(a1, b1, a2, b2) * 0x01010101u;
+        const uint32_t vv = filt(b0, d0, b1, d1) * 0x01010101u, vc = filt(b1, d1, b2, d2) * 0x01010101u;
+        o0 = make_uint2(v0, v0); oh = make_uint2(vh, vh); ov = make_uint2(vv, vv); oc = make_uint2(vc, vc);
     } else {
-        // edge path: per-pixel with clamped coordinates (frame edge, padding, odd geometry)
+        // odd geometry (width not a multiple of 16, unaligned plane): per-pixel, clamped
         uint32_t r[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-        uint32_t last[4] = {0, 0, 0, 0};
-        int last_x = -1 << 30;
         for (int i = 0; i < 8; i++) {
-            int x = min(max(lx + i, 0), job.lw - 1);
-            if (x != last_x) {
-                int c0 = min(2 * x, w - 1), c1 = min(2 * x + 1, w - 1), c2 = min(2 * x + 2, w - 1);
-                last[0] = filt(s0[c0], s1[c0], s0[c1], s1[c1]);
-                last[1] = filt(s0[c1], s1[c1], s0[c2], s1[c2]);
-                last[2] = filt(s1[c0], s2[c0], s1[c1], s2[c1]);
-                last[3] = filt(s1[c1], s2[c1], s1[c2], s2[c2]);
-                last_x = x;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) r[k][i >> 2] |= last[k] << (8 * (i & 3));
+            const int x = min(max(lx + i, 0), job.lw - 1);
+            const int c0 = min(2 * x, w - 1), c1 = min(2 * x + 1, w - 1), c2 = min(2 * x + 2, w - 1);
+            r[0][i >> 2] |= filt(s0[c0], s1[c0], s0[c1], s1[c1]) << (8 * (i & 3));
+            r[1][i >> 2] |= filt(s0[c1], s1[c1], s0[c2], s1[c2]) << (8 * (i & 3));
+            r[2][i >> 2] |= filt(s1[c0], s2[c0], s1[c1], s2[c1]) << (8 * (i & 3));
+            r[3][i >> 2] |= filt(s1[c1], s2[c1], s1[c2], s2[c2]) << (8 * (i & 3));
         }
         o0 = make_uint2(r[0][0], r[0][1]); oh = make_uint2(r[1][0], r[1][1]);
         ov = make_uint2(r[2][0], r[2][1]); oc = make_uint2(r[3][0], r[3][1]);
@@ -95,10 +96,12 @@ lowres_init_kernel(LowresJob job)
 
 int launch_lowres_init(cudaStream_t st, const LowresJob &job, int n_frames)
 {
-    const long long total = (long long)((job.lw + 2 * LOWRES_PAD) >> 3) * (job.lh + 2 * LOWRES_PAD);
-    if (total <= 0 || n_frames <= 0) return 0;
-    dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_frames);
-    lowres_init_kernel<<<grid, 256, 0, st>>>(job);
+    const int chunks = (job.lw + 2 * LOWRES_PAD) >> 3, rows = job.lh + 2 * LOWRES_PAD;
+    if (chunks <= 0 || rows <= 0 || n_frames <= 0) return 0;
+    // block = (chunks of one row rounded to a warp multiple, up to 128) x (rows to reach 128 threads)
+    const int bx = ((chunks < 128 ? chunks : 128) + 31) & ~31, by = bx >= 128 ? 1 : 128 / bx;
+    dim3 block(bx, by), grid((unsigned)((chunks + bx - 1) / bx), (unsigned)((rows + by - 1) / by), (unsigned)n_frames);
+    lowres_init_kernel<<<grid, block, 0, st>>>(job);
     XV_LAUNCH_CHECK();
     return 0;
 }
