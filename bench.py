@@ -28,6 +28,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware work queue per CUDA stream (8 sessions x 3 streams); must be set before CUDA initialises
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 W, H = 1920, 1080
 PRESET = "medium"

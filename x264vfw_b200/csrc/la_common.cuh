@@ -59,6 +59,23 @@ __device__ __forceinline__ uint2 get_ref_row(const uint8_t *const planes[4], int
     return a;
 }
 
+// Same, for the four phase planes of one frame laid out plane_stride bytes apart (avoids a
+// dynamically indexed pointer array, which would force the caller's state into local memory).
+__device__ __forceinline__ uint2 get_ref_row_ps(const uint8_t *plane0, int plane_stride, int stride, int pel, int mvx, int mvy,
+                                                int r, const WeightDev &w)
+{
+    const int qidx = ((mvy & 3) << 2) + (mvx & 3);
+    const int off = pel + ((mvy >> 2) + r) * stride + (mvx >> 2);
+    uint2 a = load8u(plane0 + (size_t)c_hpel_ref0[qidx] * plane_stride + off + ((mvy & 3) == 3) * stride);
+    if (qidx & 5) {
+        uint2 b = load8u(plane0 + (size_t)c_hpel_ref1[qidx] * plane_stride + off + ((mvx & 3) == 3));
+        a.x = __vavgu4(a.x, b.x);
+        a.y = __vavgu4(a.y, b.y);
+    }
+    if (w.on) { a.x = weight_word(w, a.x); a.y = weight_word(w, a.y); }
+    return a;
+}
+
 // ---- scalar block metrics on 8 rows held as uint2 (thread-per-MB kernels) -------------------
 __device__ __forceinline__ int sad8x8_rows(const uint2 a[8], const uint2 b[8])
 {

@@ -104,6 +104,9 @@ struct La {
     cudaStream_t st;
     int in_csp, out_csp, colmatrix, fullrange, keep_frames;
     int speculate = 1;
+    int me_rows = 0;         // warps per search in the wavefront kernel
+    int decide_lag = 1;      // run the decision due at put(n) during put(n+lag): same decisions, searches overlap
+    bool flushing = false;
     int la_me_hex, la_subpel_refine, la_satd, do_edges;
     int slicetype_length, i_last_keyframe;
     // tables
@@ -419,6 +422,7 @@ static void me_params_init(La *la, MeParams &mp)
     mp.do_edges = la->do_edges; mp.mv_range2 = 2 * la->p.mv_range; mp.me_hex = la->la_me_hex;
     mp.subpel_refine = la->la_subpel_refine; mp.satd = la->la_satd; mp.me_range = la->p.me_range;
     mp.cost_mv = la->d_cost_mv + la->cost_mv_half;
+    mp.rows_in_flight = la->me_rows;
 }
 
 static void me_add_job(La *la, MeParams &mp, int eng, Frame *fenc, Frame *ref, int list, int dist, const WeightDev *w)
@@ -954,7 +958,9 @@ static int decide_and_shift(La *la)
     if ((p->bframes && p->b_adapt) || p->scenecut || p->b_mbtree)
         if (slicetype_analyse(la, 0) < 0) return -1;
 
-    const int n_next = (int)la->next.size();
+    // frames queued beyond the decision's own window (decide_lag) are invisible to it
+    int n_next = (int)la->next.size();
+    if (!la->flushing && n_next > la->slicetype_length + 1) n_next = la->slicetype_length + 1;
     for (bframes = 0, brefs = 0;; bframes++) {
         frm = la->next[bframes];
         if (frm->i_type == T_BREF && p->b_pyramid < 2 && brefs == p->b_pyramid) frm->i_type = T_B;
@@ -1105,12 +1111,22 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (p.chroma_format < 0 || p.chroma_format > 3) { set_error("bad chroma_format"); delete la; return -1; }
     la->device = device; la->in_csp = in_csp; la->out_csp = out_csp; la->colmatrix = colmatrix; la->fullrange = fullrange;
     la->keep_frames = keep_frames;
+    if (const char *e = getenv("X264VFW_CUDA_DECIDE_LAG")) { la->decide_lag = atoi(e); if (la->decide_lag < 0) la->decide_lag = 0; if (la->decide_lag > 4) la->decide_lag = 4; }
+    if (const char *e = getenv("X264VFW_CUDA_SPECULATE")) la->speculate = atoi(e) != 0;
+    if (const char *e = getenv("X264VFW_CUDA_ME_ROWS")) la->me_rows = atoi(e);
+    else la->me_rows = -1;   // resolved below once the geometry is known
     x264vfw_cuda_lowres_geom lg;
     x264vfw_cuda_lowres_geometry(&lg, p.width, p.height);
     LaGeom &g = la->g;
     g.width = p.width; g.height = p.height; g.mb_w = lg.mb_w; g.mb_h = lg.mb_h; g.mb_count = lg.mb_w * lg.mb_h;
     g.luma_w = lg.luma_w; g.luma_h = lg.luma_h; g.lw = lg.lw; g.lh = lg.lh; g.lstride = lg.lstride;
     g.lplane = lg.lplane_bytes; g.lorigin = lg.lorigin;
+    if (la->me_rows < 0) {
+        // at most mb_w/2 rows of a search can be busy at once (a row is mb_w steps long and rows
+        // start 2 steps apart); 2/3 of that keeps the pipeline full with far fewer idle warps
+        const int busy = g.mb_h < (g.mb_w + 1) / 2 ? g.mb_h : (g.mb_w + 1) / 2;
+        la->me_rows = busy * 2 / 3 > 4 ? busy * 2 / 3 : 4;
+    }
     // [x264] lowres_context_init
     if (p.subme > 1) { la->la_me_hex = p.me_method >= 1; la->la_subpel_refine = 4; }
     else { la->la_me_hex = 0; la->la_subpel_refine = 2; }
@@ -1162,6 +1178,16 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
             if (ok) x264vfw_cuda_picture_layout(&la->planes_img, la->d_planes, out_csp, p.width, p.height);
         }
         if (!ok) { if (!*x264vfw_cuda_last_error()) set_error("lookahead allocation failed"); x264vfw_cuda_la_close((x264vfw_cuda_la *)la); return -1; }
+    }
+    // pre-allocate the frame pool: allocation is slow and serialises across sessions
+    if (!keep_frames) {
+        const int want = la->slicetype_length + p.bframes + 6 + la->decide_lag;
+        for (int i = 0; i < want; i++) {
+            Frame *f = frame_alloc(la);
+            if (!f) { x264vfw_cuda_la_close((x264vfw_cuda_la *)la); return -1; }
+            la->pool.push_back(f);
+        }
+        for (int i = 0; i < 4; i++) { float *q = qp_staging(la); if (q) la->qp_free.push_back(q); }
     }
     *pla = (x264vfw_cuda_la *)la;
     return 0;
@@ -1277,7 +1303,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     la->next.push_back(f);      // [x264] x264_lookahead_put_frame
     const double t_mid = now_s();
     la->t_put += t_mid - t_begin;
-    while ((int)la->next.size() > la->slicetype_length)
+    while ((int)la->next.size() > la->slicetype_length + la->decide_lag)
         if (decide_and_shift(la) < 0) return -1;
     la->t_decide += now_s() - t_mid;
     if (conv_pic || !src_on_device) XV_CUDA_OK(cudaStreamSynchronize(la->st));   // caller's buffers are borrowed for the call only
@@ -1289,8 +1315,13 @@ int x264vfw_cuda_la_flush(x264vfw_cuda_la *h)
     La *la = (La *)h;
     if (!la) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
-    while (!la->next.empty())
+    // decisions deferred by decide_lag still see exactly the frames upstream would have had
+    while ((int)la->next.size() > la->slicetype_length)
         if (decide_and_shift(la) < 0) return -1;
+    la->flushing = true;
+    while (!la->next.empty())
+        if (decide_and_shift(la) < 0) { la->flushing = false; return -1; }
+    la->flushing = false;
     return (int)la->outq.size();
 }
 

@@ -50,6 +50,7 @@ struct MeJob {
 struct MeParams {
     int njobs;
     int epoch;                    // unique per launch; a record is valid iff its tag equals it
+    int rows_in_flight;           // warps per search (each walks several rows); 0 = one warp per row
     MeJob job[XV_ME_MAX_JOBS];
     int bands;                    // lookahead_threads
     int do_edges;

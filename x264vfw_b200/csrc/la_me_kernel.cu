@@ -59,7 +59,7 @@ struct WarpMb {
     int rp, grp;
     int stride, pel;
     int px, py;                  // plane coordinates of the MB origin
-    const uint8_t *fref[4];
+    const uint8_t *fref0; int plane_stride;      // four phase planes, plane_stride bytes apart
     const uint8_t *fref_w;
     WeightDev w;
     const uint16_t *cost_mv;
@@ -194,8 +194,8 @@ __device__ __forceinline__ int cand_qpel(const WarpMb &m, int qx, int qy, bool a
             a0 = get_ref_row_sub(m, qx, qy, 2 * m.rp);
             a1 = get_ref_row_sub(m, qx, qy, 2 * m.rp + 1);
         } else {
-            a0 = get_ref_row(m.fref, m.stride, m.pel, qx, qy, 2 * m.rp, m.w);
-            a1 = get_ref_row(m.fref, m.stride, m.pel, qx, qy, 2 * m.rp + 1, m.w);
+            a0 = get_ref_row_ps(m.fref0, m.plane_stride, m.stride, m.pel, qx, qy, 2 * m.rp, m.w);
+            a1 = get_ref_row_ps(m.fref0, m.plane_stride, m.stride, m.pel, qx, qy, 2 * m.rp + 1, m.w);
         }
     }
     int c;
@@ -212,28 +212,37 @@ __constant__ const signed char c_hex_first[6][3] = {{-2, 0, 2}, {-1, 2, 3}, {1, 
 
 struct MeResult { int mvx, mvy, cost; };
 
-// stage the 64x48 full-pel window of fref_w: 6 x 16-byte loads per lane, issued early
-struct WinRegs { uint4 v[6]; };
-__device__ __forceinline__ void win_issue(const WarpMb &m, const LaGeom &g, int lane, int cx, int cy, WinRegs &r, int &wx0, int &wy0)
+// Asynchronous global->shared copies (LDGSTS): no staging registers, no separate store
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// stage the 64x48 full-pel window of fref_w: 6 x 16-byte async copies per lane, issued early
+__device__ __forceinline__ void win_issue(const WarpMb &m, MeSmem &sm, const LaGeom &g, int lane, int cx, int cy, int &wx0, int &wy0)
 {
     wx0 = (m.px + cx - WIN_R) & ~15;
     wx0 = min(max(wx0, -32), g.lstride - 32 - WIN_W);
     wy0 = min(max(m.py + cy - WIN_R, -32), g.lh + 32 - WIN_H);
     const uint8_t *base = m.fref_w + wy0 * m.stride + wx0;
+    __syncwarp();                                        // previous readers of the window are done
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         const int c = lane + 32 * k;
-        r.v[k] = __ldg((const uint4 *)(base + (c >> 2) * m.stride + (c & 3) * 16));
+        cp_async16(sm.win + (c >> 2) * WIN_W + (c & 3) * 16, base + (c >> 2) * m.stride + (c & 3) * 16);
     }
 }
-__device__ __forceinline__ void win_commit(MeSmem &sm, int lane, const WinRegs &r)
+__device__ __forceinline__ void win_commit()
 {
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        const int c = lane + 32 * k;
-        *(uint4 *)(sm.win + (c >> 2) * WIN_W + (c & 3) * 16) = r.v[k];
-    }
+    cp_async_wait_all();
     __syncwarp();
 }
 // stage the four 20x12 sub-pel windows around full-pel position (fx,fy) (MB-relative)
@@ -242,34 +251,36 @@ __device__ __forceinline__ void sub_load(WarpMb &m, MeSmem &sm, int lane, int fx
     m.sx0 = (m.px + fx - 1) & ~3;
     m.sy0 = m.py + fy - 1;
     __syncwarp();
+    // 4 planes x 12 rows x 5 words = 240 words: lane -> plane (lane>>3), 8 lanes x 8 rounds cover 60 words
+    const int pl = lane >> 3, l8 = lane & 7;
+    const uint8_t *src = m.fref0 + (size_t)pl * m.plane_stride + m.sy0 * m.stride + m.sx0;
+    uint8_t *dst = sm.sub[pl];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const int c = lane + 32 * k;                     // 4 planes x 12 rows x 5 words = 240 words
-        if (c < 4 * SUB_H * (SUB_W / 4)) {
-            const int pl = c / (SUB_H * (SUB_W / 4)), rem = c - pl * (SUB_H * (SUB_W / 4));
-            const int row = rem / (SUB_W / 4), wd = rem - row * (SUB_W / 4);
-            const uint32_t v = __ldg((const uint32_t *)(m.fref[pl] + (m.sy0 + row) * m.stride + m.sx0 + 4 * wd));
-            *(uint32_t *)(sm.sub[pl] + row * SUB_W + 4 * wd) = v;
+        const int idx = l8 + 8 * k;                      // 0..63, valid below 60
+        if (idx < SUB_H * (SUB_W / 4)) {
+            const int row = idx / (SUB_W / 4), wd = idx - row * (SUB_W / 4);
+            cp_async4(dst + row * SUB_W + 4 * wd, src + row * m.stride + 4 * wd);
         }
     }
+    cp_async_wait_all();
     __syncwarp();
     m.sub = &sm.sub[0][0];
 }
 
-__device__ MeResult me_search_mb(WarpMb &m, MeSmem &sm, const LaGeom &g, const MeParams &P, const int mvc[4][2], int i_mvc,
+__device__ __forceinline__ MeResult me_search_mb(WarpMb &m, MeSmem &sm, const LaGeom &g, const MeParams &P, const int mvc[4][2], int i_mvc,
                                  int min_sx, int max_sx, int min_sy, int max_sy, int lane)
 {
     const int mv_x_min = min_sx >> 2, mv_x_max = max_sx >> 2, mv_y_min = min_sy >> 2, mv_y_max = max_sy >> 2;
     const int grp = m.grp;
     int bmx, bmy, bcost, bpred_cost = LA_COST_MAX, bpred_mx = 0, bpred_my = 0;
     int pm_fx = 0, pm_fy = 0;
-    WinRegs wr;
     m.win = nullptr;
 
     if (P.subpel_refine >= 3) {
         const int pmx = clip3i(m.mvp_x, mv_x_min * 4, mv_x_max * 4), pmy = clip3i(m.mvp_y, mv_y_min * 4, mv_y_max * 4);
         int wx0, wy0;
-        win_issue(m, g, lane, (pmx + 2) >> 2, (pmy + 2) >> 2, wr, wx0, wy0);
+        win_issue(m, sm, g, lane, (pmx + 2) >> 2, (pmy + 2) >> 2, wx0, wy0);
         // slot 0 = clipped mvp, slots 1..n = surviving clipped candidates (x264_predictor_clip)
         int cx = pmx, cy = pmy, n = 0;
         bool active = grp == 0;
@@ -284,7 +295,7 @@ __device__ MeResult me_search_mb(WarpMb &m, MeSmem &sm, const LaGeom &g, const M
             }
         }
         const int c = cand_qpel<false>(m, cx, cy, active, false);
-        win_commit(sm, lane, wr);
+        win_commit();
         m.win = sm.win; m.wx0 = wx0; m.wy0 = wy0;
         const int packed = warp_min(active ? (c << 4) + grp : 0x7fffffff);
         const int pmv_cost = __shfl_sync(0xffffffffu, c, 0);
@@ -311,7 +322,7 @@ __device__ MeResult me_search_mb(WarpMb &m, MeSmem &sm, const LaGeom &g, const M
         bmx = pm_fx = clip3i((m.mvp_x + 2) >> 2, mv_x_min, mv_x_max);
         bmy = pm_fy = clip3i((m.mvp_y + 2) >> 2, mv_y_min, mv_y_max);
         int wx0, wy0;
-        win_issue(m, g, lane, bmx, bmy, wr, wx0, wy0);
+        win_issue(m, sm, g, lane, bmx, bmy, wx0, wy0);
         int cx = bmx, cy = bmy, n = 0;
         bool active = grp == 0;
 #pragma unroll
@@ -328,7 +339,7 @@ __device__ MeResult me_search_mb(WarpMb &m, MeSmem &sm, const LaGeom &g, const M
         const bool zslot = pmv_nz && grp == 7;           // the zero vector rides along in slot 7
         if (zslot) { cx = 0; cy = 0; active = true; }
         int c = cand_fpel(m, cx, cy, active);
-        win_commit(sm, lane, wr);
+        win_commit();
         m.win = sm.win; m.wx0 = wx0; m.wy0 = wy0;
         if (grp == 0) c -= mvcost(m, cx * 4, cy * 4);
         const int c_zero = __shfl_sync(0xffffffffu, c, 28);
@@ -438,12 +449,19 @@ __device__ MeResult me_search_mb(WarpMb &m, MeSmem &sm, const LaGeom &g, const M
     return r;
 }
 
-__global__ void __launch_bounds__(32)
+#define ME_WARPS 2      // independent rows per block (lifts the 32-blocks-per-SM residency cap)
+__global__ void __launch_bounds__(32 * ME_WARPS, 32 / ME_WARPS)
 me_wavefront_kernel(LaGeom g, MeParams P)
 {
-    __shared__ MeSmem sm;
+    __shared__ MeSmem sm_all[ME_WARPS];
+    MeSmem &sm = sm_all[threadIdx.x >> 5];
     const MeJob &job = P.job[blockIdx.y];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    // Rows are handed out bottom-first by an atomic ticket.  A warp that finishes its row takes
+    // the next ticket, so a search keeps only P.rows_in_flight warps resident instead of one per
+    // row: rows near the top could not start for ~2*(mb_h-1-y) MB steps anyway and would only
+    // hold warp slots while waiting.
+  for (;;) {
     int ticket = 0;
     if (lane == 0) ticket = atomicAdd(job.ticket, 1);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
@@ -457,7 +475,7 @@ me_wavefront_kernel(LaGeom g, MeParams P)
     }
     const int start_y = min(slice_end - 1, g.mb_h - 2 + P.do_edges), end_y = max(slice_start, 1 - P.do_edges);
     const int start_x = g.mb_w - 2 + P.do_edges, end_x = 1 - P.do_edges;
-    if (mb_y > start_y || mb_y < end_y) return;            // row not scanned (edges without do_edges)
+    if (mb_y > start_y || mb_y < end_y) continue;          // row not scanned (edges without do_edges)
     const bool has_below = mb_y < slice_end - 1;
     const bool below_scanned = has_below && (mb_y + 1 <= start_y);
     const int epoch = P.epoch;
@@ -467,8 +485,7 @@ me_wavefront_kernel(LaGeom g, MeParams P)
     WarpMb m;
     m.grp = lane >> 2; m.rp = lane & 3;
     m.stride = g.lstride;
-#pragma unroll
-    for (int k = 0; k < 4; k++) m.fref[k] = job.fref[k];
+    m.fref0 = job.fref[0]; m.plane_stride = g.lplane;      // the phase planes of a frame are contiguous
     m.fref_w = job.fref_w; m.w = job.w; m.cost_mv = P.cost_mv; m.satd = P.satd;
     m.win = nullptr; m.sub = nullptr;
 
@@ -476,7 +493,8 @@ me_wavefront_kernel(LaGeom g, MeParams P)
     auto below_mv = [&](int x, uint2 pre, bool have_pre) -> int {
         if (!below_scanned || x < end_x || x > start_x) return 0;
         uint2 r = have_pre ? pre : ld_rec(below + x);
-        while ((int)r.y != epoch) { __nanosleep(40); r = ld_rec(below + x); }
+        unsigned ns = 32;
+        while ((int)r.y != epoch) { __nanosleep(ns); if (ns < 512) ns <<= 1; r = ld_rec(below + x); }
         return (int)r.x;
     };
 
@@ -511,15 +529,21 @@ me_wavefront_kernel(LaGeom g, MeParams P)
             nr0 = load8u(job.fref[0] + pel); nr1 = load8u(job.fref[0] + pel + g.lstride);
             if (want_pre) pre = ld_rec(below + mb_x - 2);
         }
-        // ---- reverse-order MV prediction ----
-        int mvc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-        int i_mvc = 0;
-        if (mb_x < g.mb_w - 1) { mvc[i_mvc][0] = mv_x(right_mv); mvc[i_mvc][1] = mv_y(right_mv); i_mvc++; }
+        // ---- reverse-order MV prediction: candidates in upstream's order (right, below,
+        // below-left, below-right), compacted without dynamic indexing ----
+        const bool has_r = mb_x < g.mb_w - 1, has_bl = has_below && mb_x > 0, has_br = has_below && has_r;
+        int c0, c1, c2, c3, i_mvc;
         if (has_below) {
-            mvc[i_mvc][0] = mv_x(b_0); mvc[i_mvc][1] = mv_y(b_0); i_mvc++;
-            if (mb_x > 0) { mvc[i_mvc][0] = mv_x(b_m1); mvc[i_mvc][1] = mv_y(b_m1); i_mvc++; }
-            if (mb_x < g.mb_w - 1) { mvc[i_mvc][0] = mv_x(b_p1); mvc[i_mvc][1] = mv_y(b_p1); i_mvc++; }
+            c0 = has_r ? right_mv : b_0;
+            c1 = has_r ? b_0 : (has_bl ? b_m1 : 0);
+            c2 = has_r ? (has_bl ? b_m1 : b_p1) : 0;
+            c3 = (has_r && has_bl) ? b_p1 : 0;
+            i_mvc = (int)has_r + 1 + (int)has_bl + (int)has_br;
+        } else {
+            c0 = has_r ? right_mv : 0; c1 = c2 = c3 = 0;
+            i_mvc = (int)has_r;
         }
+        const int mvc[4][2] = {{mv_x(c0), mv_y(c0)}, {mv_x(c1), mv_y(c1)}, {mv_x(c2), mv_y(c2)}, {mv_x(c3), mv_y(c3)}};
         if (i_mvc <= 1) { m.mvp_x = mvc[0][0]; m.mvp_y = mvc[0][1]; }
         else { m.mvp_x = median3i(mvc[0][0], mvc[1][0], mvc[2][0]); m.mvp_y = median3i(mvc[0][1], mvc[1][1], mvc[2][1]); }
 
@@ -550,13 +574,15 @@ me_wavefront_kernel(LaGeom g, MeParams P)
         b_p1 = b_0; b_0 = b_m1;
         b_m1 = (has_below && mb_x - 2 >= 0) ? below_mv(mb_x - 2, pre, want_pre) : 0;
     }
+  }
 }
 
 int launch_me(cudaStream_t st, const LaGeom &g, const MeParams &p)
 {
     if (p.njobs <= 0) return 0;
-    dim3 grid(g.mb_h, p.njobs);
-    me_wavefront_kernel<<<grid, 32, 0, st>>>(g, p);
+    const int rows = p.rows_in_flight > 0 && p.rows_in_flight < g.mb_h ? p.rows_in_flight : g.mb_h;
+    dim3 grid((rows + ME_WARPS - 1) / ME_WARPS, p.njobs);
+    me_wavefront_kernel<<<grid, 32 * ME_WARPS, 0, st>>>(g, p);
     XV_LAUNCH_CHECK();
     return 0;
 }
