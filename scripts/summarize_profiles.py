@@ -1,0 +1,67 @@
+"""Turns the ncu artefacts in gpurun_out/ into the small text summaries kept under profiles/."""
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+GP = os.path.join(ROOT, "gpurun_out")
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+
+
+def launch_list(src, dst, title):
+    rows = list(csv.reader(open(src)))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    agg = collections.defaultdict(lambda: [0.0, 0])
+    for r in rows[hdr + 1:]:
+        if len(r) < 15:
+            continue
+        name = r[4].split("(")[0].replace("void ", "").replace("xv::", "")
+        agg[name][0] += float(r[-1]); agg[name][1] += 1
+    tot = sum(v[0] for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# {title}\n# gpu__time_duration.sum per launch (ncu --clock-control none; cold-cache, serialised: compare SHARES)\n")
+        f.write(f"{'kernel':46s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            f.write(f"{k:46s} {v[1]:8d} {v[0] / 1e3:12.1f} {v[0] / v[1] / 1e3:10.1f} {v[0] / tot * 100:6.1f}%\n")
+
+
+def raw_metrics(rep, dst, title):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[0]
+    with open(dst, "w") as f:
+        f.write(f"# {title}\n# ncu --set full --clock-control none; one row per captured launch\n")
+        for r in rows[2:]:
+            f.write(f"\n## {r[hdr.index('Kernel Name')]}\n")
+            for k in hdr:
+                if k in KEYS or ("pcsamp_warps_issue_stalled" in k and "not_issued" not in k and r[hdr.index(k)] not in ("0", "")):
+                    f.write(f"{k:78s} {r[hdr.index(k)]} {rows[1][hdr.index(k)]}\n")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    jobs = [("launches_bench_r1.csv", f"launches_bench_{tag}.txt", "bench.py --steps 2 --warmup 3 --streams 2 --frames-per-step 8 (launches 2000..5000)"),
+            ("launches_la_r1a.csv", f"launches_single_stream_{tag}.txt", "scripts/profile_la.py 10 (one 1080p stream, 10 frames)")]
+    for src, dst, title in jobs:
+        if os.path.exists(os.path.join(GP, src)):
+            launch_list(os.path.join(GP, src), os.path.join(OUT, dst), title)
+    reps = [("me_prof_r1c.ncu-rep", f"ncu_me_wavefront_{tag}.txt", "me_wavefront_kernel, 7 searches of one 1080p frame, alone on the GPU"),
+            ("me_prof_r1a.ncu-rep", f"ncu_me_wavefront_{tag}_first_version.txt", "first version of the search kernel (global loads, progress flags) for comparison"),
+            ("s1_bgra_r1a.ncu-rep", f"ncu_csp_bgra_{tag}_before_4row.txt", "rgb_to_420 (dp4a version, before the 4-row fast path), 64 frames per launch"),
+            ("s1_lowres_r1a.ncu-rep", f"ncu_lowres_{tag}_before.txt", "lowres_init before the cheap-border rewrite, 64 frames per launch"),
+            ("s1_bgra_r1b.ncu-rep", f"ncu_csp_bgra_{tag}.txt", "rgb_to_420_fast_kernel<4,false>, 64 frames (730 MB algorithmic) per launch"),
+            ("s1_lowres_r1b.ncu-rep", f"ncu_lowres_{tag}.txt", "lowres_init_kernel, 64 frames per launch")]
+    for src, dst, title in reps:
+        if os.path.exists(os.path.join(GP, src)):
+            raw_metrics(os.path.join(GP, src), os.path.join(OUT, dst), title)
+    print(sorted(os.listdir(OUT)))
