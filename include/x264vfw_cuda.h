@@ -258,6 +258,7 @@ int x264vfw_cuda_la_mbtree( x264vfw_cuda_la *la, const int *frame_idx, const int
 #define X264VFW_CUDA_LA_PIXEL_STATS   11 /* uint64[6]: sum[3], ssd[3] (after mean removal)       */
 #define X264VFW_CUDA_LA_WEIGHT        12 /* int32[4]: scale, denom, offset, enabled              */
 #define X264VFW_CUDA_LA_CONV_PLANES   13 /* converted planes of the LAST put frame (tight)       */
+#define X264VFW_CUDA_LA_ROW_SATDS     14 /* int32[mb_h]: [x264] i_row_satds[a][b] (AQ-weighted)  */
 /* Copies the selected array of frame `frame` into dst (capacity dst_bytes).  Returns the
  * number of bytes written or -1. */
 int64_t x264vfw_cuda_la_read( x264vfw_cuda_la *la, int frame, int what, int a, int b, void *dst, size_t dst_bytes );

@@ -1527,6 +1527,7 @@ const float *orc_la_qp_offset(orc_la *la, int f, int aq) { return aq ? la->all[f
 const int16_t *orc_la_mvs(orc_la *la, int f, int list, int dist) { return (const int16_t *)la->all[f]->mvs[list][dist - 1]; }
 const int *orc_la_mv_costs(orc_la *la, int f, int list, int dist) { return la->all[f]->mv_costs[list][dist - 1]; }
 const uint16_t *orc_la_lowres_costs(orc_la *la, int f, int d0, int d1) { return la->all[f]->lowres_costs[d0][d1]; }
+const int *orc_la_row_satds(orc_la *la, int f, int d0, int d1) { return la->all[f]->row_satds[d0][d1]; }
 int orc_la_cost_est(orc_la *la, int f, int d0, int d1, int aq) { return aq ? la->all[f]->cost_est_aq[d0][d1] : la->all[f]->cost_est[d0][d1]; }
 int orc_la_intra_mbs(orc_la *la, int f, int d0) { return la->all[f]->intra_mbs[d0]; }
 void orc_la_pixel_stats(orc_la *la, int f, uint64_t sum[3], uint64_t ssd[3])

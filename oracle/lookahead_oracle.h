@@ -96,6 +96,7 @@ const float    *orc_la_qp_offset(orc_la *la, int frame, int aq);
 const int16_t  *orc_la_mvs(orc_la *la, int frame, int list, int dist);       /* [mb][2], dist>=1 */
 const int      *orc_la_mv_costs(orc_la *la, int frame, int list, int dist);
 const uint16_t *orc_la_lowres_costs(orc_la *la, int frame, int d0, int d1);
+const int      *orc_la_row_satds(orc_la *la, int frame, int d0, int d1);     /* [mb_h] */
 int  orc_la_cost_est(orc_la *la, int frame, int d0, int d1, int aq);
 int  orc_la_intra_mbs(orc_la *la, int frame, int d0);
 void orc_la_pixel_stats(orc_la *la, int frame, uint64_t sum[3], uint64_t ssd[3]);

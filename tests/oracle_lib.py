@@ -232,6 +232,8 @@ class OracleLookahead:
         o.orc_la_mv_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         o.orc_la_lowres_costs.restype = C.c_void_p
         o.orc_la_lowres_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        o.orc_la_row_satds.restype = C.c_void_p
+        o.orc_la_row_satds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         o.orc_la_cost_est.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         o.orc_la_intra_mbs.argtypes = [C.c_void_p, C.c_int, C.c_int]
         o.orc_la_pixel_stats.argtypes = [C.c_void_p, C.c_int, P(C.c_uint64), P(C.c_uint64)]
@@ -308,6 +310,9 @@ class OracleLookahead:
 
     def lowres_costs(self, f, d0, d1):
         return self._arr(self.o.orc_la_lowres_costs(self.h, f, d0, d1), self.mb_count, np.uint16)
+
+    def row_satds(self, f, d0, d1):
+        return self._arr(self.o.orc_la_row_satds(self.h, f, d0, d1), (self.p.height + 15) >> 4, np.int32)
 
     def cost_est(self, f, d0, d1, aq=False):
         return self.o.orc_la_cost_est(self.h, f, d0, d1, int(aq))

@@ -78,6 +78,8 @@ def compare_cost(orc, gpu, p0, p1, b):
         lg, lo = gpu.lowres_costs(b, d0, d1), orc.lowres_costs(b, d0, d1)
         bad = np.nonzero(lg != lo)[0]
         assert bad.size == 0, ("lowres_costs", p0, p1, b, bad[:5], lg[bad[:5]], lo[bad[:5]])
+    assert np.array_equal(gpu.row_satds(b, d0, d1), orc.row_satds(b, d0, d1)), ("row_satds", p0, p1, b)
+    assert np.array_equal(gpu.row_satds(b, 0, 0), orc.row_satds(b, 0, 0)), ("intra row_satds", b)
     assert gpu.cost_est(b, d0, d1)[:2] == [orc.cost_est(b, d0, d1), orc.cost_est(b, d0, d1, aq=True)]
     if b == p1 and p0 != p1:
         assert gpu.cost_est(b, d0, d1)[2] == orc.intra_mbs(b, d0)

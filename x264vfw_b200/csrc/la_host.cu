@@ -72,6 +72,7 @@ struct Frame {
     float *qp_offset = nullptr, *qp_offset_aq = nullptr;
     int *mvs[2][BMAX + 1], *mv_costs[2][BMAX + 1];
     uint16_t *lowres_costs = nullptr;          // [(B+2)*(B+2)][mb]
+    int *row_satds = nullptr;                  // [(B+2)*(B+2)][mb_h]  ([x264] i_row_satds)
     unsigned long long *stats = nullptr;       // device [6]
     unsigned long long *h_stats = nullptr;     // pinned [6]
     uint8_t *arena = nullptr;
@@ -104,6 +105,7 @@ struct La {
     cudaStream_t st;
     int in_csp, out_csp, colmatrix, fullrange, keep_frames;
     int speculate = 1;
+    int ext = X264VFW_CUDA_EXT_NONE;   // packed 4:2:2 -> I444 uses the documented extension conversion
     int me_rows = 0;         // warps per search in the wavefront kernel
     int decide_lag = 1;      // run the decision due at put(n) during put(n+lag): same decisions, searches overlap
     bool flushing = false;
@@ -191,6 +193,7 @@ static Frame *frame_alloc(La *la)
     size_t o_mvs[2][BMAX + 1], o_mvc[2][BMAX + 1];
     for (int l = 0; l < 2; l++) for (int d = 0; d <= B; d++) { o_mvs[l][d] = take(n * 4); o_mvc[l][d] = take(n * 4); }
     const size_t o_lc = take((size_t)(B + 2) * (B + 2) * n * 2);
+    const size_t o_rs = take((size_t)(B + 2) * (B + 2) * la->g.mb_h * 4);
     const size_t o_stats = take(64);
     if (cudaMalloc((void **)&f->arena, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed for a lookahead frame", off); delete f; return nullptr; }
     if (cudaMallocHost((void **)&f->h_stats, 64) != cudaSuccess) { set_error("cudaMallocHost failed"); cudaFree(f->arena); delete f; return nullptr; }
@@ -200,6 +203,7 @@ static Frame *frame_alloc(La *la)
     f->qp_offset = (float *)(f->arena + o_qp); f->qp_offset_aq = (float *)(f->arena + o_qpaq);
     for (int l = 0; l < 2; l++) for (int d = 0; d <= B; d++) { f->mvs[l][d] = (int *)(f->arena + o_mvs[l][d]); f->mv_costs[l][d] = (int *)(f->arena + o_mvc[l][d]); }
     f->lowres_costs = (uint16_t *)(f->arena + o_lc);
+    f->row_satds = (int *)(f->arena + o_rs);
     f->stats = (unsigned long long *)(f->arena + o_stats);
     return f;
 }
@@ -265,6 +269,7 @@ static void frame_release(La *la, Frame *f)
 }
 
 static inline const uint8_t *plane_org(const La *la, const Frame *f, int k) { return f->lowres + (size_t)k * la->g.lplane + la->g.lorigin; }
+static inline int *rs_ptr(const La *la, const Frame *f, int d0, int d1) { return f->row_satds + ((size_t)d0 * (la->p.bframes + 2) + d1) * la->g.mb_h; }
 static inline uint16_t *lc_ptr(const La *la, const Frame *f, int d0, int d1) { return f->lowres_costs + ((size_t)d0 * (la->p.bframes + 2) + d1) * la->g.mb_count; }
 
 // ------------------------------------------------------------------------------------------
@@ -335,7 +340,7 @@ static int launch_intra_for(La *la, Frame *fenc)
     LA_CUDA(cudaMemsetAsync(la->d_results + slot * 4, 0, 4 * sizeof(int), la->st));
     IntraSumJob sj;
     sj.intra_cost = fenc->intra_cost; sj.inv_qscale = fenc->inv_qscale; sj.aq_on = la->p.aq_mode != 0;
-    sj.result = la->d_results + slot * 4; sj.row_satd = nullptr;
+    sj.result = la->d_results + slot * 4; sj.row_satd = rs_ptr(la, fenc, 0, 0);
     { ProfScope ps(la, K_INTRA); if (launch_intra_sum(la->st, la->g, sj) < 0) return -1; }
     la->n_launch += 2;
     la->pending.push_back(PendingResult{fenc, 0, 0, slot, false, true});
@@ -589,7 +594,7 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
     fj.ref1_mvs = (b < p1 && fref1->searched[0][p1 - p0 - 1]) ? fref1->mvs[0][p1 - p0 - 1] : nullptr;
     fj.intra_cost = fenc->intra_cost; fj.inv_qscale = fenc->inv_qscale;
     fj.lowres_costs = lc_ptr(la, fenc, d0, d1);
-    fj.row_satd = nullptr; fj.result = la->d_results + slot * 4;
+    fj.row_satd = rs_ptr(la, fenc, d0, d1); fj.result = la->d_results + slot * 4;
     fj.b_bidir = b < p1; fj.b_p = b == p1;
     fj.dist_scale_factor = dist_scale_factor;
     fj.bipred_weight = la->p.weightb ? 64 - (dist_scale_factor >> 2) : 32;
@@ -1111,6 +1116,8 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (p.chroma_format < 0 || p.chroma_format > 3) { set_error("bad chroma_format"); delete la; return -1; }
     la->device = device; la->in_csp = in_csp; la->out_csp = out_csp; la->colmatrix = colmatrix; la->fullrange = fullrange;
     la->keep_frames = keep_frames;
+    if (((in_csp & X264VFW_CUDA_CSP_MASK) == X264VFW_CUDA_CSP_YUYV || (in_csp & X264VFW_CUDA_CSP_MASK) == X264VFW_CUDA_CSP_UYVY) && out_csp == X264VFW_CUDA_OUT_I444)
+        la->ext = X264VFW_CUDA_EXT_422_TO_I444;
     if (const char *e = getenv("X264VFW_CUDA_DECIDE_LAG")) { la->decide_lag = atoi(e); if (la->decide_lag < 0) la->decide_lag = 0; if (la->decide_lag > 4) la->decide_lag = 4; }
     if (const char *e = getenv("X264VFW_CUDA_SPECULATE")) la->speculate = atoi(e) != 0;
     if (const char *e = getenv("X264VFW_CUDA_ME_ROWS")) la->me_rows = atoi(e);
@@ -1260,7 +1267,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
                 XV_CUDA_OK(cudaMemcpyAsync(dsrc.plane[i], src->plane[i], (size_t)src->i_stride[i] * rows, cudaMemcpyHostToDevice, la->st));
             }
         }
-        { ProfScope ps(la, K_CSP); if (convert_device_public(la->st, la->out_csp, la->colmatrix, la->fullrange, X264VFW_CUDA_EXT_NONE, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
+        { ProfScope ps(la, K_CSP); if (convert_device_public(la->st, la->out_csp, la->colmatrix, la->fullrange, la->ext, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
         la->n_launch++;
     }
     if (conv_pic) {
@@ -1392,6 +1399,7 @@ int64_t x264vfw_cuda_la_read(x264vfw_cuda_la *h, int frame, int what, int a, int
     case X264VFW_CUDA_LA_MVS: if (a < 0 || a > 1 || b < 1 || b > B + 1) return -1; src = f->mvs[a][b - 1]; bytes = n * 4; break;
     case X264VFW_CUDA_LA_MV_COSTS: if (a < 0 || a > 1 || b < 1 || b > B + 1) return -1; src = f->mv_costs[a][b - 1]; bytes = n * 4; break;
     case X264VFW_CUDA_LA_LOWRES_COSTS: if (a < 0 || a > B + 1 || b < 0 || b > B + 1) return -1; src = lc_ptr(la, f, a, b); bytes = n * 2; break;
+    case X264VFW_CUDA_LA_ROW_SATDS: if (a < 0 || a > B + 1 || b < 0 || b > B + 1) return -1; src = rs_ptr(la, f, a, b); bytes = la->g.mb_h * 4; break;
     case X264VFW_CUDA_LA_COST_EST:
         if (a < 0 || a > B + 1 || b < 0 || b > B + 1) return -1;
         tmp[0] = f->cost_est[a][b]; tmp[1] = f->cost_est_aq[a][b]; tmp[2] = f->intra_mbs[a]; src = tmp; bytes = 12; host = true; break;

@@ -13,7 +13,7 @@ X264_TYPE_AUTO, X264_TYPE_IDR, X264_TYPE_I, X264_TYPE_P, X264_TYPE_BREF, X264_TY
 TYPE_CHAR = {1: "I", 2: "i", 3: "P", 4: "b", 5: "B"}
 
 (LA_LOWRES, LA_INTRA_COST, LA_INV_QSCALE, LA_PROPAGATE, LA_QP_OFFSET, LA_QP_OFFSET_AQ, LA_MVS, LA_MV_COSTS,
- LA_LOWRES_COSTS, LA_COST_EST, LA_PIXEL_STATS, LA_WEIGHT, LA_CONV_PLANES) = range(1, 14)
+ LA_LOWRES_COSTS, LA_COST_EST, LA_PIXEL_STATS, LA_WEIGHT, LA_CONV_PLANES, LA_ROW_SATDS) = range(1, 15)
 
 
 class LaParams(C.Structure):
@@ -177,6 +177,7 @@ class Lookahead:
     def mvs(self, f, lst, dist): return self.read(f, LA_MVS, lst, dist, dtype=np.int16, count=2 * self.mb_count).reshape(-1, 2)
     def mv_costs(self, f, lst, dist): return self.read(f, LA_MV_COSTS, lst, dist, dtype=np.int32, count=self.mb_count)
     def lowres_costs(self, f, d0, d1): return self.read(f, LA_LOWRES_COSTS, d0, d1, dtype=np.uint16, count=self.mb_count)
+    def row_satds(self, f, d0, d1): return self.read(f, LA_ROW_SATDS, d0, d1, dtype=np.int32, count=self.mb_h)
     def cost_est(self, f, d0, d1): return [int(v) for v in self.read(f, LA_COST_EST, d0, d1, dtype=np.int32, count=3)]
     def pixel_stats(self, f):
         v = self.read(f, LA_PIXEL_STATS, dtype=np.uint64, count=6)
