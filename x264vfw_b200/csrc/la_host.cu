@@ -107,6 +107,7 @@ struct La {
     int speculate = 1;
     int ext = X264VFW_CUDA_EXT_NONE;   // packed 4:2:2 -> I444 uses the documented extension conversion
     int me_rows = 0;         // warps per search in the wavefront kernel
+    double spec_threshold = 0.4;   // speculate a (list,distance) pair when at least this share of frames asked for it
     int decide_lag = 1;      // run the decision due at put(n) during put(n+lag): same decisions, searches overlap
     bool flushing = false;
     int la_me_hex, la_subpel_refine, la_satd, do_edges;
@@ -144,6 +145,7 @@ struct La {
     uint64_t n_frame_cost = 0, n_mb_search = 0, n_launch = 0, n_sync = 0;
     bool fail = false;   // set when a device call fails inside the value-returning helpers
     double t_put = 0, t_decide = 0, t_sync = 0;   // host wall-clock seconds (diagnostics)
+    uint64_t n_logical[2][BMAX + 1] = {{0}};      // searches upstream's control flow actually asked for, by list/distance
     Prof prof;
 };
 
@@ -499,13 +501,22 @@ static int speculate_searches(La *la, Frame *fn)
         if (mp.njobs == XV_ME_MAX_JOBS) { if (me_launch(la, mp, eng) < 0) return -1; me_params_init(la, mp); }
         return 0;
     };
+    // Only speculate the (list, distance) pairs the decision logic usually asks for: measured on
+    // this session so far (distance 1 always).  Everything else is searched on demand; results
+    // are identical either way, only the time at which they are computed changes.
+    auto likely = [&](int list, int d) -> bool {
+        if (la->speculate >= 2) return true;
+        if (d == 1) return true;
+        if (la->n_input < 24) return false;
+        return (double)la->n_logical[list][d - 1] >= la->spec_threshold * (double)la->n_input;
+    };
     for (int d = 1; d <= B + 1; d++) {
         Frame *ref = alive(n - d);
-        if (ref && !fn->spec[0][d - 1] && add(fn, ref, 0, d) < 0) return -1;
+        if (ref && !fn->spec[0][d - 1] && likely(0, d) && add(fn, ref, 0, d) < 0) return -1;
     }
     for (int d = 1; d <= B; d++) {
         Frame *b = alive(n - d);
-        if (b && !b->spec[1][d - 1] && add(b, fn, 1, d) < 0) return -1;
+        if (b && !b->spec[1][d - 1] && likely(1, d) && add(b, fn, 1, d) < 0) return -1;
     }
     return me_launch(la, mp, eng);
 }
@@ -548,6 +559,8 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
         fenc->searched[0][d0 - 1] = true;
     }
     if (do_search[1]) fenc->searched[1][d1 - 1] = true;
+    if (do_search[0]) la->n_logical[0][d0 - 1]++;
+    if (do_search[1]) la->n_logical[1][d1 - 1]++;
     const int dist_scale_factor = (((b - p0) << 8) + ((p1 - p0) >> 1)) / (p1 - p0);
 
     if (!fenc->b_intra_calculated && launch_intra_for(la, fenc) < 0) return -1;
@@ -569,6 +582,18 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
             }
             me_add_job(la, mp, 0, fenc, l ? fref1 : fref0, l, dist, weighted ? &w : nullptr);
             if (!weighted) { fenc->spec[l][dist - 1] = true; fenc->spec_eng[l][dist - 1] = 0; }
+            // the decision logic usually asks next for the neighbouring frame against the SAME
+            // reference (path "B..BP" after "B..PP"): search it in the same launch
+            if (la->speculate && mp.njobs < XV_ME_MAX_JOBS) {
+                const int nd = dist + 1;
+                const int ni = l ? fenc->i_frame - 1 : fenc->i_frame + 1;      // display index of the neighbour
+                Frame *nf = (ni >= 0 && ni < (int)la->by_index.size()) ? la->by_index[ni] : nullptr;
+                const int nd_max = l ? la->p.bframes : la->p.bframes + 1;
+                if (nf && nf != (l ? fref1 : fref0) && nd <= nd_max && !nf->spec[l][nd - 1] && !nf->searched[l][nd - 1]) {
+                    me_add_job(la, mp, 0, nf, l ? fref1 : fref0, l, nd, nullptr);
+                    nf->spec[l][nd - 1] = true; nf->spec_eng[l][nd - 1] = 0;
+                }
+            }
         }
         if (me_launch(la, mp, 0) < 0) return -1;
         // memoised lists are read by the selection kernel as well: same ordering requirement
@@ -1120,6 +1145,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
         la->ext = X264VFW_CUDA_EXT_422_TO_I444;
     if (const char *e = getenv("X264VFW_CUDA_DECIDE_LAG")) { la->decide_lag = atoi(e); if (la->decide_lag < 0) la->decide_lag = 0; if (la->decide_lag > 4) la->decide_lag = 4; }
     if (const char *e = getenv("X264VFW_CUDA_SPECULATE")) la->speculate = atoi(e) != 0;
+    if (const char *e = getenv("X264VFW_CUDA_SPEC_THRESHOLD")) la->spec_threshold = atof(e);
     if (const char *e = getenv("X264VFW_CUDA_ME_ROWS")) la->me_rows = atoi(e);
     else la->me_rows = -1;   // resolved below once the geometry is known
     x264vfw_cuda_lowres_geom lg;
@@ -1205,6 +1231,11 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     La *la = (La *)h;
     if (!la) return;
     cudaSetDevice(la->device);
+    if (getenv("X264VFW_CUDA_STATS")) {
+        fprintf(stderr, "[x264vfw_cuda] frames %d searches asked for by (list,dist):", la->n_input);
+        for (int l = 0; l < 2; l++) for (int d = 0; d <= la->p.bframes; d++) fprintf(stderr, " l%d/d%d=%llu", l, d + 1, (unsigned long long)la->n_logical[l][d]);
+        fprintf(stderr, "\n");
+    }
     if (la->st) cudaStreamSynchronize(la->st);
     for (int e = 1; e <= ME_SIDE; e++) if (la->st_me[e]) cudaStreamSynchronize(la->st_me[e]);
     prof_resolve(la);
