@@ -61,7 +61,7 @@ def make_clips(stream_ids, n_frames):
     from x264vfw_b200.clipgen import SyntheticClip
 
     def one(s):
-        clip = SyntheticClip(W, H, n_frames=n_frames, stream_id=s, cuts=(n_frames * 5 // 8,), flash=n_frames // 4, flash_len=1)
+        clip = SyntheticClip(W, H, n_frames=n_frames, stream_id=s, cuts=(n_frames * 5 // 8,), flash=None)
         return [clip.packed(n, "bgra") for n in range(n_frames)]
 
     with ThreadPoolExecutor(max_workers=min(8, len(stream_ids))) as ex:
@@ -118,7 +118,10 @@ class StreamWorker(threading.Thread):
 
     def feed(self, n):
         for _ in range(n):
-            k = self.pos % len(self.frames)
+            # ping-pong playback: the clip loops without a hard cut at the wrap-around
+            n = len(self.frames)
+            k = self.pos % (2 * n - 2)
+            k = k if k < n else 2 * n - 2 - k
             conv = self.conv[self.pos % len(self.conv)] if self.conv else None
             self.la.put_frame(self.frames[k], on_device=self.on_device, conv_pic=conv)
             self.decided += len(self.la.decisions(with_offsets=True))

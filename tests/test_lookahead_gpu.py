@@ -244,3 +244,39 @@ def test_full_size_properties_1080p():
         compare_cost(orc, gpu, 1, 2, 2)
     finally:
         orc.close(); gpu.close()
+
+
+def test_concurrent_sessions_are_deterministic_and_match_oracle():
+    """Eight sessions driven from eight host threads on one GPU (the bench configuration):
+    every one must produce exactly the oracle's decisions, whatever the interleaving of the
+    streams (side-stream searches, adaptive speculation, recycled frame slots)."""
+    import threading
+    from x264vfw_b200 import lookahead
+    w, h, n = 320, 192, 60
+    packed = make_clip(w, h, n, cuts=(25,), flash=40, flash_len=1)
+    i420 = to_i420(packed, w, h)
+    over = {"rc_lookahead": 12, "keyint_max": 50, "keyint_min": 5}
+    orc = ol.OracleLookahead(ol.la_params("medium", w, h, **over))
+    want = run_session(orc, i420, lambda la, f: la.put_i420(f))
+    orc.close()
+    results, errors = {}, []
+
+    def work(k):
+        try:
+            la = lookahead.Lookahead(lookahead.params_preset("medium", w, h, **over), in_csp=BGRA_FLIP, device=0)
+            results[k] = run_session(la, packed, lambda s, f: s.put_frame(f))
+            la.close()
+        except Exception as e:          # noqa: BLE001
+            errors.append(e)
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
+    for k in range(8):
+        got = results[k]
+        assert [(d["i_frame"], d["i_type"], d["i_cost_est"], d["i_cost_est_aq"]) for d in got] == \
+               [(d["i_frame"], d["i_type"], d["i_cost_est"], d["i_cost_est_aq"]) for d in want], k
+        assert all(np.array_equal(a["qp_offset"].view(np.uint32), b["qp_offset"].view(np.uint32)) for a, b in zip(got, want)), k

@@ -65,6 +65,7 @@ struct Frame {
     float weighted_cost_delta[BMAX + 2];
     int rc_d0 = -1, rc_d1 = -1;
     bool in_use = false;
+    bool ready = false;                        // lowres planes / AQ arrays have been enqueued
     // device side
     uint8_t *lowres = nullptr;                 // 4 padded planes (+ slack)
     uint16_t *intra_cost = nullptr, *inv_qscale = nullptr;
@@ -128,6 +129,9 @@ struct La {
     uint64_t me_seq[1 + ME_SIDE] = {0};                     // launches issued per engine
     uint64_t me_waited[1 + ME_SIDE] = {0};                  // highest launch the main stream already waits on
     cudaEvent_t ev_ready = nullptr;                         // main stream -> side stream hand-off
+    cudaEvent_t ev_io = nullptr;                            // caller's buffers are free again (H2D / D2H of this put done)
+    cudaEvent_t ev_h2d = nullptr, ev_csp = nullptr;
+    cudaStream_t st_io = nullptr;                           // host <-> device copies of the borrowed buffers
     int me_epoch = 0, me_rr = 0;
     int *d_results = nullptr; int *h_results = nullptr;     // ring of 4-int slots
     int result_head = 0;
@@ -232,6 +236,7 @@ static int frame_reset(La *la, Frame *f, int i_frame)
     f->weight = WeightDev{0, 1, 0, 0};
     f->rc_d0 = f->rc_d1 = -1;
     f->in_use = true;
+    f->ready = false;
     // a recycled slot may still be in use by speculative searches on the side streams
     for (int e = 1; e <= ME_SIDE; e++) {
         if (f->touch_seq[e] && wait_engine(la, e, f->touch_seq[e]) < 0) return -1;
@@ -589,7 +594,7 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
                 const int ni = l ? fenc->i_frame - 1 : fenc->i_frame + 1;      // display index of the neighbour
                 Frame *nf = (ni >= 0 && ni < (int)la->by_index.size()) ? la->by_index[ni] : nullptr;
                 const int nd_max = l ? la->p.bframes : la->p.bframes + 1;
-                if (nf && nf != (l ? fref1 : fref0) && nd <= nd_max && !nf->spec[l][nd - 1] && !nf->searched[l][nd - 1]) {
+                if (nf && nf->ready && nf != (l ? fref1 : fref0) && nd <= nd_max && !nf->spec[l][nd - 1] && !nf->searched[l][nd - 1]) {
                     me_add_job(la, mp, 0, nf, l ? fref1 : fref0, l, nd, nullptr);
                     nf->spec[l][nd - 1] = true; nf->spec_eng[l][nd - 1] = 0;
                 }
@@ -1167,7 +1172,11 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     la->do_edges = p.b_mbtree || g.mb_w <= 2 || g.mb_h <= 2;
     la->slicetype_length = p.bframes > p.rc_lookahead ? p.bframes : p.rc_lookahead;
     la->i_last_keyframe = -p.keyint_max;
-    if (cudaStreamCreateWithFlags(&la->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete la; return -1; }
+    // the main stream carries the latency-critical chain (the host blocks on it); speculative
+    // searches on the side streams yield to it
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&la->st, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete la; return -1; }
 
     // tables: [x264] x264_analyse_init_costs for X264_LOOKAHEAD_QP (lambda 1), x264_log2_lut, x264_exp2_lut
     {
@@ -1190,6 +1199,10 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
                   cudaMemcpy(la->d_exp2_lut, e2, 64, cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&la->d_weight_buf, g.lplane + 64) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&la->ev_io, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&la->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&la->ev_csp, cudaEventDisableTiming) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&la->st_io, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
              cudaMalloc((void **)&la->d_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMallocHost((void **)&la->h_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMalloc((void **)&la->d_wscore, 64) == cudaSuccess &&
@@ -1199,7 +1212,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
             ok = ok && cudaMalloc((void **)&la->d_rec[e], (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
                  cudaMemset(la->d_rec[e], 0, (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
                  cudaMalloc((void **)&la->d_ticket[e], XV_ME_MAX_JOBS * sizeof(int)) == cudaSuccess;
-            if (e) ok = ok && cudaStreamCreateWithFlags(&la->st_me[e], cudaStreamNonBlocking) == cudaSuccess;
+            if (e) ok = ok && cudaStreamCreateWithPriority(&la->st_me[e], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
             for (int k = 0; k < ME_EVENTS && ok; k++)
                 ok = ok && cudaEventCreateWithFlags(&la->ev_me[e][k], cudaEventDisableTiming) == cudaSuccess;
         }
@@ -1249,7 +1262,11 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
         for (int k = 0; k < ME_EVENTS; k++) if (la->ev_me[e][k]) cudaEventDestroy(la->ev_me[e][k]);
         if (e && la->st_me[e]) cudaStreamDestroy(la->st_me[e]);
     }
-    if (la->ev_ready) cudaEventDestroy(la->ev_ready); cudaFree(la->d_results); cudaFree(la->d_wscore); cudaFree(la->d_planes); cudaFree(la->d_src);
+    if (la->ev_ready) cudaEventDestroy(la->ev_ready);
+    if (la->ev_io) cudaEventDestroy(la->ev_io);
+    if (la->ev_h2d) cudaEventDestroy(la->ev_h2d);
+    if (la->ev_csp) cudaEventDestroy(la->ev_csp);
+    if (la->st_io) { cudaStreamSynchronize(la->st_io); cudaStreamDestroy(la->st_io); } cudaFree(la->d_results); cudaFree(la->d_wscore); cudaFree(la->d_planes); cudaFree(la->d_src);
     if (la->h_results) cudaFreeHost(la->h_results);
     if (la->h_wscore) cudaFreeHost(la->h_wscore);
     if (la->st) cudaStreamDestroy(la->st);
@@ -1265,57 +1282,74 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     const int w = la->p.width, hgt = la->p.height;
     const int in = la->in_csp & X264VFW_CUDA_CSP_MASK;
     x264vfw_cuda_image_t planes = la->planes_img;           // device, tight, encoder csp
-
-    if (in == X264VFW_CUDA_CSP_NONE) {
-        // planar frame already in the encoder csp: copy rows into the tight device planes
-        x264vfw_cuda_image_t geo;
-        x264vfw_cuda_picture_layout(&geo, nullptr, la->out_csp, w, hgt);
-        for (int i = 0; i < geo.i_plane; i++) {
-            const int rows = (i && (la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_NV12)) ? hgt / 2 : hgt;
-            XV_CUDA_OK(cudaMemcpy2DAsync(planes.plane[i], planes.i_stride[i], src->plane[i], src->i_stride[i], geo.i_stride[i], rows,
-                                         src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, la->st));
-        }
-    } else {
-        x264vfw_cuda_image_t dsrc = *src;
-        dsrc.i_csp = la->in_csp;
-        if (!src_on_device) {
-            x264vfw_cuda_image_t geo;
-            int64_t sbytes = x264vfw_cuda_img_fill(&geo, nullptr, in, w, hgt);
-            if (sbytes < 0) return -1;
-            size_t need = 0, off[4];
-            for (int i = 0; i < geo.i_plane; i++) {
-                const int rows = (i && (in == X264VFW_CUDA_CSP_I420 || in == X264VFW_CUDA_CSP_YV12 || in == X264VFW_CUDA_CSP_NV12)) ? hgt / 2 : hgt;
-                off[i] = need; need += ((size_t)src->i_stride[i] * rows + 255) & ~(size_t)255;
-            }
-            if (la->d_src_bytes < need) {
-                if (la->d_src) { XV_CUDA_OK(cudaStreamSynchronize(la->st)); cudaFree(la->d_src); la->d_src = nullptr; }
-                XV_CUDA_OK(cudaMalloc((void **)&la->d_src, need + 256));
-                la->d_src_bytes = need;
-            }
-            for (int i = 0; i < geo.i_plane; i++) {
-                const int rows = (i && (in == X264VFW_CUDA_CSP_I420 || in == X264VFW_CUDA_CSP_YV12 || in == X264VFW_CUDA_CSP_NV12)) ? hgt / 2 : hgt;
-                dsrc.plane[i] = la->d_src + off[i];
-                XV_CUDA_OK(cudaMemcpyAsync(dsrc.plane[i], src->plane[i], (size_t)src->i_stride[i] * rows, cudaMemcpyHostToDevice, la->st));
-            }
-        }
-        { ProfScope ps(la, K_CSP); if (convert_device_public(la->st, la->out_csp, la->colmatrix, la->fullrange, la->ext, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
-        la->n_launch++;
-    }
-    if (conv_pic) {
-        x264vfw_cuda_image_t geo;
-        x264vfw_cuda_picture_layout(&geo, nullptr, la->out_csp, w, hgt);
-        for (int i = 0; i < geo.i_plane; i++) {
-            const int rows = (i && (la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_NV12)) ? hgt / 2 : hgt;
-            XV_CUDA_OK(cudaMemcpy2DAsync(conv_pic->plane[i], conv_pic->i_stride[i], planes.plane[i], planes.i_stride[i], geo.i_stride[i], rows,
-                                         cudaMemcpyDeviceToHost, la->st));
-        }
-    }
+    const bool host_src = !src_on_device && in != X264VFW_CUDA_CSP_NONE;
+    const bool borrowed = conv_pic || !src_on_device;
+    auto chroma_rows = [&](int csp_is_420, int i) { return (i && csp_is_420) ? hgt / 2 : hgt; };
 
     Frame *f = frame_get(la, la->n_input);
     if (!f) return -1;
     la->n_input++;
 
-    // [x264] x264_adaptive_quant_frame
+    // ---- 1. host source: H2D on the I/O stream, so that it overlaps the decision logic below ----
+    x264vfw_cuda_image_t dsrc = *src;
+    dsrc.i_csp = la->in_csp;
+    if (host_src) {
+        x264vfw_cuda_image_t geo;
+        if (x264vfw_cuda_img_fill(&geo, nullptr, in, w, hgt) < 0) return -1;
+        const int in420 = in == X264VFW_CUDA_CSP_I420 || in == X264VFW_CUDA_CSP_YV12 || in == X264VFW_CUDA_CSP_NV12;
+        size_t need = 0, off[4];
+        for (int i = 0; i < geo.i_plane; i++) { off[i] = need; need += ((size_t)src->i_stride[i] * chroma_rows(in420, i) + 255) & ~(size_t)255; }
+        if (la->d_src_bytes < need) {
+            if (la->d_src) { XV_CUDA_OK(cudaStreamSynchronize(la->st)); XV_CUDA_OK(cudaStreamSynchronize(la->st_io)); cudaFree(la->d_src); la->d_src = nullptr; }
+            XV_CUDA_OK(cudaMalloc((void **)&la->d_src, need + 256));
+            la->d_src_bytes = need;
+        }
+        for (int i = 0; i < geo.i_plane; i++) {
+            dsrc.plane[i] = la->d_src + off[i];
+            XV_CUDA_OK(cudaMemcpyAsync(dsrc.plane[i], src->plane[i], (size_t)src->i_stride[i] * chroma_rows(in420, i), cudaMemcpyHostToDevice, la->st_io));
+        }
+        XV_CUDA_OK(cudaEventRecord(la->ev_h2d, la->st_io));
+    }
+
+    // ---- 2. the decision that became due (deferred by decide_lag frames) ----
+    double t_dec = 0;
+    if (la->decide_lag > 0) {
+        la->next.push_back(f);      // [x264] x264_lookahead_put_frame (frame n is outside the window being decided)
+        const double t0 = now_s();
+        while ((int)la->next.size() > la->slicetype_length + la->decide_lag)
+            if (decide_and_shift(la) < 0) return -1;
+        t_dec = now_s() - t0;
+    }
+
+    // ---- 3. stage 1 on the device ----
+    const int out420 = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_NV12;
+    x264vfw_cuda_image_t geo_out;
+    x264vfw_cuda_picture_layout(&geo_out, nullptr, la->out_csp, w, hgt);
+    if (in == X264VFW_CUDA_CSP_NONE) {
+        // planar frame already in the encoder csp: copy rows into the tight device planes
+        for (int i = 0; i < geo_out.i_plane; i++)
+            XV_CUDA_OK(cudaMemcpy2DAsync(planes.plane[i], planes.i_stride[i], src->plane[i], src->i_stride[i], geo_out.i_stride[i], chroma_rows(out420, i),
+                                         src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, la->st));
+    } else {
+        if (host_src) XV_CUDA_OK(cudaStreamWaitEvent(la->st, la->ev_h2d, 0));
+        { ProfScope ps(la, K_CSP); if (convert_device_public(la->st, la->out_csp, la->colmatrix, la->fullrange, la->ext, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
+        la->n_launch++;
+    }
+    // everything that touches the caller's buffers: the converted planes go back on the I/O stream
+    if (conv_pic) {
+        XV_CUDA_OK(cudaEventRecord(la->ev_csp, la->st));
+        XV_CUDA_OK(cudaStreamWaitEvent(la->st_io, la->ev_csp, 0));
+        for (int i = 0; i < geo_out.i_plane; i++)
+            XV_CUDA_OK(cudaMemcpy2DAsync(conv_pic->plane[i], conv_pic->i_stride[i], planes.plane[i], planes.i_stride[i], geo_out.i_stride[i], chroma_rows(out420, i),
+                                         cudaMemcpyDeviceToHost, la->st_io));
+        XV_CUDA_OK(cudaEventRecord(la->ev_io, la->st_io));
+        // the next frame's csp overwrites the planes: order it after this read-back
+        XV_CUDA_OK(cudaStreamWaitEvent(la->st, la->ev_io, 0));
+    } else if (borrowed) {
+        XV_CUDA_OK(cudaEventRecord(la->ev_io, la->st));
+    }
+
+    // ---- 4. [x264] x264_adaptive_quant_frame ----
     const bool planar_yuv = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_I422 || la->out_csp == X264VFW_CUDA_OUT_I444;
     const bool aq_on = la->p.aq_mode != 0 && la->p.aq_strength != 0;
     AqJob aq;
@@ -1328,7 +1362,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     { ProfScope ps(la, K_AQ); if (launch_aq(la->st, la->g, aq) < 0) return -1; }
     XV_CUDA_OK(cudaMemcpyAsync(f->h_stats, f->stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, la->st));
 
-    // [x264] x264_frame_init_lowres
+    // ---- 5. [x264] x264_frame_init_lowres ----
     LowresJob lj;
     lj.y = planes.plane[0]; lj.y_stride = planes.i_stride[0]; lj.w = w; lj.h = hgt; lj.dst = f->lowres;
     lj.luma_w = la->g.luma_w; lj.luma_h = la->g.luma_h; lj.lw = la->g.lw; lj.lh = la->g.lh;
@@ -1337,14 +1371,18 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     { ProfScope ps(la, K_LOWRES); if (launch_lowres_init(la->st, lj, 1) < 0) return -1; }
     la->n_launch += 2;
 
+    f->ready = true;
     if (speculate_searches(la, f) < 0) return -1;
-    la->next.push_back(f);      // [x264] x264_lookahead_put_frame
     const double t_mid = now_s();
-    la->t_put += t_mid - t_begin;
-    while ((int)la->next.size() > la->slicetype_length + la->decide_lag)
-        if (decide_and_shift(la) < 0) return -1;
-    la->t_decide += now_s() - t_mid;
-    if (conv_pic || !src_on_device) XV_CUDA_OK(cudaStreamSynchronize(la->st));   // caller's buffers are borrowed for the call only
+    if (la->decide_lag == 0) {
+        la->next.push_back(f);
+        while ((int)la->next.size() > la->slicetype_length)
+            if (decide_and_shift(la) < 0) return -1;
+        t_dec = now_s() - t_mid;
+    }
+    la->t_decide += t_dec;
+    la->t_put += (la->decide_lag == 0 ? t_mid - t_begin : now_s() - t_begin - t_dec);
+    if (borrowed) XV_CUDA_OK(cudaEventSynchronize(la->ev_io));   // caller's buffers are borrowed for the call only
     return (int)la->outq.size();
 }
 
