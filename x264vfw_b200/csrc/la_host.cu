@@ -22,6 +22,7 @@
 #include <chrono>
 #include <deque>
 #include <vector>
+#include <array>
 
 namespace xv {
 
@@ -76,6 +77,7 @@ struct Frame {
     int *row_satds = nullptr;                  // [(B+2)*(B+2)][mb_h]  ([x264] i_row_satds)
     unsigned long long *stats = nullptr;       // device [6]
     unsigned long long *h_stats = nullptr;     // pinned [6]
+    cudaEvent_t ev_stats = nullptr;            // the async copy of the statistics has landed
     uint8_t *arena = nullptr;
 };
 
@@ -108,6 +110,10 @@ struct La {
     int speculate = 1;
     int ext = X264VFW_CUDA_EXT_NONE;   // packed 4:2:2 -> I444 uses the documented extension conversion
     int me_rows = 0;         // warps per search in the wavefront kernel
+    // searches the decision logic asked for during the current decision, and the ones predicted
+    // for the next decision (same pattern, shifted by the mini-GOP just emitted): {frame, list, dist}
+    std::vector<std::array<int, 3>> asked_now, wanted;
+    int predict = 1;
     double spec_threshold = 0.4;   // speculate a (list,distance) pair when at least this share of frames asked for it
     int decide_lag = 1;      // run the decision due at put(n) during put(n+lag): same decisions, searches overlap
     bool flushing = false;
@@ -149,6 +155,7 @@ struct La {
     uint64_t n_frame_cost = 0, n_mb_search = 0, n_launch = 0, n_sync = 0;
     bool fail = false;   // set when a device call fails inside the value-returning helpers
     double t_put = 0, t_decide = 0, t_sync = 0;   // host wall-clock seconds (diagnostics)
+    uint64_t n_ondemand = 0, n_ondemand_jobs = 0, n_spec_jobs = 0;
     uint64_t n_logical[2][BMAX + 1] = {{0}};      // searches upstream's control flow actually asked for, by list/distance
     Prof prof;
 };
@@ -202,7 +209,7 @@ static Frame *frame_alloc(La *la)
     const size_t o_rs = take((size_t)(B + 2) * (B + 2) * la->g.mb_h * 4);
     const size_t o_stats = take(64);
     if (cudaMalloc((void **)&f->arena, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed for a lookahead frame", off); delete f; return nullptr; }
-    if (cudaMallocHost((void **)&f->h_stats, 64) != cudaSuccess) { set_error("cudaMallocHost failed"); cudaFree(f->arena); delete f; return nullptr; }
+    if (cudaMallocHost((void **)&f->h_stats, 64) != cudaSuccess || cudaEventCreateWithFlags(&f->ev_stats, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaMallocHost failed"); cudaFree(f->arena); delete f; return nullptr; }
     f->lowres = f->arena + o_lowres;
     f->intra_cost = (uint16_t *)(f->arena + o_intra); f->inv_qscale = (uint16_t *)(f->arena + o_invq);
     f->propagate = (int *)(f->arena + o_prop);
@@ -219,6 +226,7 @@ static void frame_free(Frame *f)
     if (!f) return;
     cudaFree(f->arena);
     cudaFreeHost(f->h_stats);
+    if (f->ev_stats) cudaEventDestroy(f->ev_stats);
     delete f;
 }
 
@@ -321,7 +329,8 @@ static int la_sync(La *la)
 static int ensure_stats(La *la, Frame *f)
 {
     if (f->stats_ready) return 0;
-    if (la_sync(la) < 0) return -1;     // the AQ kernel + async copy of this frame were enqueued at put time
+    // the AQ kernel + async copy of this frame were enqueued at put time: wait for that copy only
+    LA_CUDA(cudaEventSynchronize(f->ev_stats));
     // [x264] x264_adaptive_quant_frame: "Remove mean from SSD calculation"
     const int cf = la->p.chroma_format;
     for (int i = 0; i < 3; i++) {
@@ -361,19 +370,24 @@ static int se_size(int v) { int t = 1 - v * 2; if (t < 0) t = v * 2; int n = 0; 
 
 static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_value);
 
-static int weight_score(La *la, Frame *fenc, Frame *ref, const WeightDev &w, unsigned *score)
+// weight_cost_luma for the unweighted reference and for one candidate weight: two kernels, one
+// synchronisation (the candidate only depends on the pixel statistics, not on the first score).
+static int weight_scores(La *la, Frame *fenc, Frame *ref, const WeightDev &w, unsigned *orig, unsigned *cand)
 {
-    LA_CUDA(cudaMemsetAsync(la->d_wscore, 0, sizeof(unsigned), la->st));
+    LA_CUDA(cudaMemsetAsync(la->d_wscore, 0, 2 * sizeof(unsigned), la->st));
     WeightCostJob j;
     j.fenc = plane_org(la, fenc, 0); j.ref = plane_org(la, ref, 0); j.intra_cost = fenc->intra_cost;
-    j.w = w; j.satd = la->la_satd; j.result = la->d_wscore;
+    j.satd = la->la_satd;
+    j.w = WeightDev{0, 1, 0, 0}; j.result = la->d_wscore;
     { ProfScope ps(la, K_WEIGHT); if (launch_weight_cost(la->st, la->g, j) < 0) return -1; }
-    la->n_launch++;
-    LA_CUDA(cudaMemcpyAsync(la->h_wscore, la->d_wscore, sizeof(unsigned), cudaMemcpyDeviceToHost, la->st));
+    j.w = w; j.result = la->d_wscore + 1;
+    { ProfScope ps(la, K_WEIGHT); if (launch_weight_cost(la->st, la->g, j) < 0) return -1; }
+    la->n_launch += 2;
+    LA_CUDA(cudaMemcpyAsync(la->h_wscore, la->d_wscore, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, la->st));
     if (la_sync(la) < 0) return -1;
-    unsigned s = *la->h_wscore;
-    if (w.on) s += 1 * 1 * (10 + ue_size(w.denom) * 2 + 2 * (se_size(w.scale) + se_size(w.offset)));   // weight_slice_header_cost
-    *score = s;
+    *orig = la->h_wscore[0];
+    // + weight_slice_header_cost
+    *cand = la->h_wscore[1] + 1 * 1 * (10 + ue_size(w.denom) * 2 + 2 * (se_size(w.scale) + se_size(w.offset)));
     return 0;
 }
 
@@ -401,10 +415,7 @@ static int weights_analyse(La *la, Frame *fenc, Frame *ref)
         Frame *one[1] = {fenc};
         if (frame_cost(la, one, 0, 0, 0, false) < 0) return -1;
     }
-    unsigned origscore, minscore;
-    if (weight_score(la, fenc, ref, WeightDev{0, 1, 0, 0}, &origscore) < 0) return -1;
-    minscore = origscore;
-    if (!minscore) return 0;
+    unsigned origscore, minscore, candscore;
     {
         int cur_scale = minscale;
         int cur_offset = (int)(fenc_mean - ref_mean * cur_scale / (1 << mindenom) + 0.5f * 1);
@@ -414,9 +425,10 @@ static int weights_analyse(La *la, Frame *fenc, Frame *ref)
             cur_scale = (int)(cs < 0 ? 0 : cs > 127 ? 127 : cs);
         }
         const int i_off = cur_offset < -128 ? -128 : cur_offset > 127 ? 127 : cur_offset;
-        unsigned s;
-        if (weight_score(la, fenc, ref, WeightDev{1, cur_scale, mindenom, i_off}, &s) < 0) return -1;
-        if (s < minscore) { minscore = s; minscale = cur_scale; minoff = i_off; found = 1; }
+        if (weight_scores(la, fenc, ref, WeightDev{1, cur_scale, mindenom, i_off}, &origscore, &candscore) < 0) return -1;
+        minscore = origscore;
+        if (!minscore) return 0;
+        if (candscore < minscore) { minscore = candscore; minscale = cur_scale; minoff = i_off; found = 1; }
     }
     while (mindenom > 0 && !(minscale & 1)) { mindenom--; minscale >>= 1; }
     if (!found || (minscale == 1 << mindenom && minoff == 0) || (float)minscore / origscore > 0.998f) return 0;
@@ -473,6 +485,7 @@ static int me_launch(La *la, MeParams &mp, int eng)
     mp.epoch = ++la->me_epoch;
     { ProfScope ps(la, K_ME, st); if (launch_me(st, la->g, mp) < 0) return -1; }
     la->n_launch++;
+    if (eng) la->n_spec_jobs += mp.njobs; else { la->n_ondemand++; la->n_ondemand_jobs += mp.njobs; }
     if (eng) {
         const uint64_t seq = ++la->me_seq[eng];
         LA_CUDA(cudaEventRecord(la->ev_me[eng][seq % ME_EVENTS], st));
@@ -523,6 +536,17 @@ static int speculate_searches(La *la, Frame *fn)
         Frame *b = alive(n - d);
         if (b && !b->spec[1][d - 1] && likely(1, d) && add(b, fn, 1, d) < 0) return -1;
     }
+    // predicted searches whose two frames are both on the device by now
+    for (size_t k = 0; k < la->wanted.size();) {
+        const int i = la->wanted[k][0], l = la->wanted[k][1], d = la->wanted[k][2];
+        Frame *fe = alive(i), *rf = alive(l ? i + d : i - d);
+        const bool gone = i < n - la->slicetype_length - 8 || (fe && (fe->spec[l][d - 1] || fe->searched[l][d - 1]));
+        if (!gone && fe && rf && fe->ready && rf->ready) {
+            if (add(fe, rf, l, d) < 0) return -1;
+            la->wanted[k] = la->wanted.back(); la->wanted.pop_back();
+        } else if (gone) { la->wanted[k] = la->wanted.back(); la->wanted.pop_back(); }
+        else k++;
+    }
     return me_launch(la, mp, eng);
 }
 
@@ -564,8 +588,8 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
         fenc->searched[0][d0 - 1] = true;
     }
     if (do_search[1]) fenc->searched[1][d1 - 1] = true;
-    if (do_search[0]) la->n_logical[0][d0 - 1]++;
-    if (do_search[1]) la->n_logical[1][d1 - 1]++;
+    if (do_search[0]) { la->n_logical[0][d0 - 1]++; la->asked_now.push_back({fenc->i_frame, 0, d0}); }
+    if (do_search[1]) { la->n_logical[1][d1 - 1]++; la->asked_now.push_back({fenc->i_frame, 1, d1}); }
     const int dist_scale_factor = (((b - p0) << 8) + ((p1 - p0) >> 1)) / (p1 - p0);
 
     if (!fenc->b_intra_calculated && launch_intra_for(la, fenc) < 0) return -1;
@@ -748,6 +772,26 @@ static uint64_t path_cost(La *la, Frame **frames, const char *path, uint64_t thr
     uint64_t cost = 0;
     int loc = 1, cur_nonb = 0;
     path--;
+    if (threshold == COST_MAX64) {
+        // no early termination possible: every evaluation of this path is unconditional, so
+        // enqueue all of them first (same order) and pay one synchronisation instead of one each
+        int l2 = 1, cn = 0;
+        while (path[l2]) {
+            int nn = l2;
+            while (path[nn] == 'B') nn++;
+            if (path[nn] == 'P') frame_cost(la, frames, cn, nn, nn, false);
+            else frame_cost(la, frames, nn, nn, nn, false);
+            if (la->p.b_pyramid && nn - cn > 2) {
+                const int middle = cn + (nn - cn) / 2;
+                frame_cost(la, frames, cn, nn, middle, false);
+                for (int nb = l2; nb < middle; nb++) frame_cost(la, frames, cn, middle, nb, false);
+                for (int nb = middle + 1; nb < nn; nb++) frame_cost(la, frames, middle, nn, nb, false);
+            } else
+                for (int nb = l2; nb < nn; nb++) frame_cost(la, frames, cn, nn, nb, false);
+            l2 = nn + 1;
+            cn = nn;
+        }
+    }
     auto fc = [&](int p0, int p1, int b) -> uint64_t { int v = frame_cost(la, frames, p0, p1, b, true); if (v < 0) { la->fail = true; return 0; } return (uint64_t)v; };
     while (path[loc]) {
         int next_nonb = loc;
@@ -823,6 +867,11 @@ static int scenecut(La *la, Frame **frames, int p0, int p1, int real_scenecut, i
         if (la->p.b_adapt == 2) origmaxp1 += la->p.bframes;
         else origmaxp1++;
         const int maxp1 = origmaxp1 < num_frames ? origmaxp1 : num_frames;
+        // none of the evaluations below depends on another one's value: enqueue them all first
+        // (same order as the loops), synchronise once
+        for (int curp1 = p1; curp1 <= maxp1; curp1++) frame_cost(la, frames, p0, curp1, curp1, false);
+        if (!(origmaxp1 > i_max_search))
+            for (int curp0 = p0; curp0 < maxp1; curp0++) frame_cost(la, frames, curp0, maxp1, maxp1, false);
         for (int curp1 = p1; curp1 <= maxp1; curp1++)
             if (!scenecut_internal(la, frames, p0, curp1))
                 for (int i = curp1; i > p0; i--) frames[i]->b_scenecut = 0;
@@ -987,6 +1036,7 @@ static int decide_and_shift(La *la)
     int bframes, brefs;
     if (la->next.empty()) return 0;
     la->fail = false;
+    la->asked_now.clear();
 
     for (Frame *f : la->next) f->f_duration = (float)((double)2 * p->fps_den / ((double)p->fps_num * 2));
 
@@ -1078,6 +1128,9 @@ static int decide_and_shift(La *la)
         }
         d.f = nullptr;
     }
+    // next decision: most likely the same evaluation pattern, shifted by the mini-GOP just emitted
+    if (la->predict && !la->flushing)
+        for (const auto &a : la->asked_now) la->wanted.push_back({a[0] + shift, a[1], a[2]});
     // recycle: B-frames are dead once shifted; the previous last_nonb is dead now
     for (Frame *f : coded) if (f != la->last_nonb) frame_release(la, f);
     if (old_nonb && old_nonb != la->last_nonb) frame_release(la, old_nonb);
@@ -1151,6 +1204,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_DECIDE_LAG")) { la->decide_lag = atoi(e); if (la->decide_lag < 0) la->decide_lag = 0; if (la->decide_lag > 4) la->decide_lag = 4; }
     if (const char *e = getenv("X264VFW_CUDA_SPECULATE")) la->speculate = atoi(e) != 0;
     if (const char *e = getenv("X264VFW_CUDA_SPEC_THRESHOLD")) la->spec_threshold = atof(e);
+    if (const char *e = getenv("X264VFW_CUDA_PREDICT")) la->predict = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ME_ROWS")) la->me_rows = atoi(e);
     else la->me_rows = -1;   // resolved below once the geometry is known
     x264vfw_cuda_lowres_geom lg;
@@ -1247,7 +1301,8 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     if (getenv("X264VFW_CUDA_STATS")) {
         fprintf(stderr, "[x264vfw_cuda] frames %d searches asked for by (list,dist):", la->n_input);
         for (int l = 0; l < 2; l++) for (int d = 0; d <= la->p.bframes; d++) fprintf(stderr, " l%d/d%d=%llu", l, d + 1, (unsigned long long)la->n_logical[l][d]);
-        fprintf(stderr, "\n");
+        fprintf(stderr, "  | speculative jobs %llu, on-demand launches %llu (%llu jobs)\n", (unsigned long long)la->n_spec_jobs,
+                (unsigned long long)la->n_ondemand, (unsigned long long)la->n_ondemand_jobs);
     }
     if (la->st) cudaStreamSynchronize(la->st);
     for (int e = 1; e <= ME_SIDE; e++) if (la->st_me[e]) cudaStreamSynchronize(la->st_me[e]);
@@ -1361,6 +1416,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     aq.stats = f->stats; aq.log2_lut = la->d_log2_lut; aq.exp2_lut = la->d_exp2_lut;
     { ProfScope ps(la, K_AQ); if (launch_aq(la->st, la->g, aq) < 0) return -1; }
     XV_CUDA_OK(cudaMemcpyAsync(f->h_stats, f->stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, la->st));
+    XV_CUDA_OK(cudaEventRecord(f->ev_stats, la->st));
 
     // ---- 5. [x264] x264_frame_init_lowres ----
     LowresJob lj;
