@@ -80,6 +80,31 @@ class ClockSampler(threading.Thread):
         self._stop_evt = threading.Event()
 
     def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
+    def _run_nvml(self):
+        # same counters as the nvidia-smi clocks line of B200_PROFILING.md, sampled in-process so
+        # that short timed regions still get many samples
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(hnd, pynvml.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_evt.is_set():
+            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM)))
+            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
+            for n, b in bits.items():
+                if r & b:
+                    self.reasons.add(n)
+            self._stop_evt.wait(0.005)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -169,6 +194,7 @@ def run_phase(torch, dist, sessions, frames, on_device, conv, args, rank, world,
     torch.cuda.synchronize()
     sampler = ClockSampler(sampler_index)
     sampler.start()
+    c0 = [la.counters() for la in sessions]
     n0 = xv.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -182,6 +208,8 @@ def run_phase(torch, dist, sessions, frames, on_device, conv, args, rank, world,
     ms = e0.elapsed_time(e1)
     launches = xv.launch_count() - n0
     clocks = sampler.stop()
+    c1 = [la.counters() for la in sessions]
+    run_phase.delta = {k: sum(b[k] - a[k] for a, b in zip(c0, c1)) for k in c1[0]}
     prof = None
     if profile:
         prof = {}
@@ -336,12 +364,13 @@ def main():
 
     sessions = open_sessions()
     ms_step, clocks, launches, _ = run_phase(torch, dist, sessions, dev_ptrs, True, None, args, rank, world, local_rank)
-    host_counters = [la.counters() for la in sessions]
+    host_delta = dict(run_phase.delta)
     for la in sessions:
         la.close()
     # same workload once more with per-kernel CUDA-event timing switched on (kernel shares, roofline)
     sessions = open_sessions()
-    _, _, _, prof = run_phase(torch, dist, sessions, dev_ptrs, True, None, args, rank, world, local_rank, profile=True)
+    ms_prof, _, _, prof = run_phase(torch, dist, sessions, dev_ptrs, True, None, args, rank, world, local_rank, profile=True)
+    prof_delta = dict(run_phase.delta)
     for la in sessions:
         la.close()
     frames_per_step_all = S * F * n_gpus
@@ -383,10 +412,16 @@ def main():
     me_bytes_per_search = 960 * 544 * 5 + geom_mb * 8
     me_ms, me_n = prof["me"]
     me_avg = me_ms / max(1, me_n)
+    searches_per_launch = prof_delta["mb_searches"] / geom_mb / max(1, me_n)
     roofline = {"kernel": "me_wavefront_kernel (lowres motion search; latency-bound wavefront on the integer pipe, see DESIGN.md)",
-                "bound": "hbm", "achieved": (me_bytes_per_search * 1.5 / (me_avg * 1e-3) / 1e9) if me_n else None,
-                "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
-                "avg_launch_ms": me_avg, "launches": me_n, "share_of_step_device_time": shares["me"]["share"],
+                "bound": "hbm", "achieved": (me_bytes_per_search * searches_per_launch / (me_avg * 1e-3) / 1e9) if me_n else None,
+                "peak": hbm_peak, "unit": "GB/s", "frac": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 7-search launch, ncu --set full
+                # (profiles/ncu_me_wavefront_r1.txt): 11.9 MB + 55.3 MB, mostly write-back of earlier kernels' lines
+                "traffic": 67.2e6, "peak_source": peak_src,
+                "avg_launch_ms": me_avg, "launches": me_n, "searches_per_launch": searches_per_launch,
+                "algorithmic_bytes_per_search": me_bytes_per_search, "mb_searches_per_s": prof_delta["mb_searches"] / (ms_prof * args.steps * 1e-3),
+                "share_of_step_device_time": shares["me"]["share"],
                 "note": "dominant kernel by device time; its bound is neither HBM nor tensor (SURVEY 8(d)): "
                         "algorithmic traffic is ~2.7 MB per search. The HBM-bound kernels of the path are reported in stage1."}
     if roofline["achieved"] is not None:
@@ -416,10 +451,8 @@ def main():
                        "l2_policy": f"inputs larger than L2: {S * F * SRC_BYTES / 1e6:.0f} MB of packed frames per step per GPU"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "stage1": stage1,
             "kernel_shares": shares, "dominant_kernel_class": dom, "cpu_baseline": cpu_baseline,
-            "host_us_per_frame": {k: sum(c[k] for c in host_counters) / max(1, sum(c["frames"] for c in host_counters))
-                                  for k in ("put_us", "decide_us", "sync_us")},
-            "per_frame": {k: sum(c[k] for c in host_counters) / max(1, sum(c["frames"] for c in host_counters))
-                          for k in ("frame_costs", "launches", "syncs")}}
+            "host_us_per_frame": {k: host_delta[k] / max(1, host_delta["frames"]) for k in ("put_us", "decide_us", "sync_us")},
+            "per_frame": {k: host_delta[k] / max(1, host_delta["frames"]) for k in ("frame_costs", "launches", "syncs")}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
