@@ -48,6 +48,8 @@ int convert_device_public(cudaStream_t st, int out_csp, int colmatrix, int fullr
 
 #define ME_SIDE 2
 #define ME_EVENTS 64
+#define TREE_RING 4
+#define TREE_MAX_STEPS (2 * LMAX + 16)
 
 struct Frame {
     // host mirror of the x264_frame_t fields the decision logic reads
@@ -142,6 +144,13 @@ struct La {
     int *d_results = nullptr; int *h_results = nullptr;     // ring of 4-int slots
     int result_head = 0;
     unsigned *d_wscore = nullptr; unsigned *h_wscore = nullptr;
+    // mb-tree walks: the step list of a walk is built on the host, copied once and executed by
+    // ONE cluster kernel (ring of staging buffers; a slot is reused only after its copy landed)
+    TreeStep *h_tree[TREE_RING] = {nullptr}, *d_tree[TREE_RING] = {nullptr};
+    cudaEvent_t ev_tree[TREE_RING] = {nullptr};
+    int tree_head = 0, tree_chain = 1;
+    std::vector<TreeStep> tree_zero, tree_steps;
+    bool tree_building = false;
     std::vector<PendingResult> pending;
     // frames
     std::vector<Frame *> all;            // by display index when keep_frames, else pool
@@ -680,9 +689,34 @@ static int tree_finish(La *la, Frame *frame, float average_duration, int ref0_di
     j.strength = 5.0f * (1.0f - la->p.qcompress);
     j.propagate = frame->propagate; j.intra_cost = frame->intra_cost; j.inv_qscale = frame->inv_qscale;
     j.qp_offset_aq = frame->qp_offset_aq; j.qp_offset = frame->qp_offset; j.log2_lut = la->d_log2_lut;
+    if (la->tree_building) {
+        TreeStep s;
+        memset(&s, 0, sizeof(s));
+        s.op = 2; s.sync = 0;       // the finishing steps of a walk touch different frames
+        s.fin_propagate = j.propagate; s.fin_intra = j.intra_cost; s.fin_invq = j.inv_qscale;
+        s.fin_qp_aq = j.qp_offset_aq; s.fin_qp = j.qp_offset;
+        s.fin_fps_factor = j.fps_factor; s.fin_weightdelta = j.weightdelta; s.fin_strength = j.strength;
+        la->tree_steps.push_back(s);
+        return 0;
+    }
     la->n_launch++;
     ProfScope ps(la, K_TREE);
     return launch_tree_finish(la->st, la->g, j);
+}
+
+static int tree_zero(La *la, int *p, int n)
+{
+    if (la->tree_building) {
+        // Every accumulator of a walk is cleared exactly once and before anything is added to it,
+        // so all clears can run first, in one phase.
+        TreeStep s;
+        memset(&s, 0, sizeof(s));
+        s.op = 0; s.n = n; s.zero = p; s.sync = 0;
+        la->tree_zero.push_back(s);
+        return 0;
+    }
+    LA_CUDA(cudaMemsetAsync(p, 0, (size_t)n * sizeof(int), la->st));
+    return 0;
 }
 
 static int tree_propagate(La *la, Frame **frames, float average_duration, int p0, int p1, int b, int referenced)
@@ -692,7 +726,7 @@ static int tree_propagate(La *la, Frame **frames, float average_duration, int p0
     j.bipred_weight = la->p.weightb ? 64 - (dist_scale_factor >> 2) : 32;
     j.fps_factor = clip_duration(frames[b]->f_duration) / (clip_duration(average_duration) * 256.0f) * MBTREE_PRECISION;
     // upstream zeroes one row of the unreferenced frame's own array and reads that as its input
-    if (!referenced) LA_CUDA(cudaMemsetAsync(frames[b]->propagate, 0, la->g.mb_w * sizeof(int), la->st));
+    if (!referenced && tree_zero(la, frames[b]->propagate, la->g.mb_w) < 0) return -1;
     j.propagate_in = referenced ? frames[b]->propagate : nullptr;
     j.intra_cost = frames[b]->intra_cost; j.inv_qscale = frames[b]->inv_qscale;
     j.lowres_costs = lc_ptr(la, frames[b], b - p0, p1 - b);
@@ -700,6 +734,18 @@ static int tree_propagate(La *la, Frame **frames, float average_duration, int p0
     j.mvs1 = b != p1 ? frames[b]->mvs[1][p1 - b - 1] : nullptr;
     j.ref0_cost = frames[p0]->propagate; j.ref1_cost = frames[p1]->propagate;
     j.b_bidir = b != p1;
+    if (la->tree_building) {
+        TreeStep s;
+        memset(&s, 0, sizeof(s));
+        s.op = 1; s.prop = j;
+        // Steps only ADD (integer atomics, order-free) into accumulators of frames earlier in
+        // time, and only a referenced frame READS an accumulator (its own, complete once every
+        // earlier step has landed): a barrier is needed before a referenced step, nowhere else.
+        s.sync = 0;
+        if (referenced && !la->tree_steps.empty()) la->tree_steps.back().sync = 1;
+        la->tree_steps.push_back(s);
+        return 0;
+    }
     la->n_launch++;
     ProfScope ps(la, K_TREE);
     return launch_propagate(la->st, la->g, j);
@@ -707,11 +753,48 @@ static int tree_propagate(La *la, Frame **frames, float average_duration, int p0
 
 static int zero_propagate(La *la, Frame *f)
 {
-    LA_CUDA(cudaMemsetAsync(f->propagate, 0, la->g.mb_count * sizeof(int), la->st));
-    return 0;
+    return tree_zero(la, f->propagate, la->g.mb_count);
 }
 
+// Copy the step list of the walk that was just described and run it as one cluster kernel.
+static int tree_run(La *la)
+{
+    la->tree_building = false;
+    std::vector<TreeStep> &z = la->tree_zero, &t = la->tree_steps;
+    if (t.empty()) { z.clear(); return 0; }
+    if (!z.empty()) z.back().sync = 1;
+    // the finishing steps read accumulators the last propagate steps add to
+    for (size_t k = 0; k < t.size(); k++) if (t[k].op == 2 && k > 0) { t[k - 1].sync = 1; break; }
+    const size_t n = z.size() + t.size();
+    if (n > TREE_MAX_STEPS) { set_error("mb-tree walk too long (%zu steps)", n); return -1; }
+    const int slot = la->tree_head;
+    la->tree_head = (la->tree_head + 1) % TREE_RING;
+    LA_CUDA(cudaEventSynchronize(la->ev_tree[slot]));
+    memcpy(la->h_tree[slot], z.data(), z.size() * sizeof(TreeStep));
+    memcpy(la->h_tree[slot] + z.size(), t.data(), t.size() * sizeof(TreeStep));
+    LA_CUDA(cudaMemcpyAsync(la->d_tree[slot], la->h_tree[slot], n * sizeof(TreeStep), cudaMemcpyHostToDevice, la->st));
+    LA_CUDA(cudaEventRecord(la->ev_tree[slot], la->st));
+    z.clear(); t.clear();
+    la->n_launch++;
+    ProfScope ps(la, K_TREE);
+    return launch_tree_chain(la->st, la->g, la->d_tree[slot], (int)n, la->d_log2_lut);
+}
+
+static int macroblock_tree_walk(La *la, Frame **frames, int num_frames, int b_intra);
+
+// The frame costs a walk asks for are enqueued as they come (they never read an accumulator);
+// the propagate / finish steps are collected and run afterwards in one launch.
 static int macroblock_tree(La *la, Frame **frames, int num_frames, int b_intra)
+{
+    la->tree_building = la->tree_chain != 0;
+    la->tree_zero.clear(); la->tree_steps.clear();
+    const int r = macroblock_tree_walk(la, frames, num_frames, b_intra);
+    if (!la->tree_building) return r;
+    if (r < 0) { la->tree_building = false; return r; }
+    return tree_run(la);
+}
+
+static int macroblock_tree_walk(La *la, Frame **frames, int num_frames, int b_intra)
 {
     int idx = !b_intra;
     int last_nonb, cur_nonb = 1, bframes = 0;
@@ -1205,6 +1288,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_SPECULATE")) la->speculate = atoi(e) != 0;
     if (const char *e = getenv("X264VFW_CUDA_SPEC_THRESHOLD")) la->spec_threshold = atof(e);
     if (const char *e = getenv("X264VFW_CUDA_PREDICT")) la->predict = atoi(e);
+    if (const char *e = getenv("X264VFW_CUDA_TREE_CHAIN")) la->tree_chain = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ME_ROWS")) la->me_rows = atoi(e);
     else la->me_rows = -1;   // resolved below once the geometry is known
     x264vfw_cuda_lowres_geom lg;
@@ -1261,6 +1345,10 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
              cudaMallocHost((void **)&la->h_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMalloc((void **)&la->d_wscore, 64) == cudaSuccess &&
              cudaMallocHost((void **)&la->h_wscore, 64) == cudaSuccess;
+        for (int k = 0; k < TREE_RING && ok; k++)
+            ok = ok && cudaMallocHost((void **)&la->h_tree[k], TREE_MAX_STEPS * sizeof(TreeStep)) == cudaSuccess &&
+                 cudaMalloc((void **)&la->d_tree[k], TREE_MAX_STEPS * sizeof(TreeStep)) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&la->ev_tree[k], cudaEventDisableTiming) == cudaSuccess;
         la->st_me[0] = la->st;
         for (int e = 0; e <= ME_SIDE && ok; e++) {
             ok = ok && cudaMalloc((void **)&la->d_rec[e], (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
@@ -1316,6 +1404,11 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
         cudaFree(la->d_rec[e]); cudaFree(la->d_ticket[e]);
         for (int k = 0; k < ME_EVENTS; k++) if (la->ev_me[e][k]) cudaEventDestroy(la->ev_me[e][k]);
         if (e && la->st_me[e]) cudaStreamDestroy(la->st_me[e]);
+    }
+    for (int k = 0; k < TREE_RING; k++) {
+        if (la->h_tree[k]) cudaFreeHost(la->h_tree[k]);
+        cudaFree(la->d_tree[k]);
+        if (la->ev_tree[k]) cudaEventDestroy(la->ev_tree[k]);
     }
     if (la->ev_ready) cudaEventDestroy(la->ev_ready);
     if (la->ev_io) cudaEventDestroy(la->ev_io);

@@ -484,16 +484,13 @@ int launch_weight_plane(cudaStream_t st, const LaGeom &g, uint8_t *dst, const ui
 // addends are >= 0, so that equals min(sum, 32767): accumulate with 32-bit atomics into a
 // shadow array and clamp when the value is read.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-propagate_kernel(LaGeom g, PropagateJob job)
+__device__ __forceinline__ void propagate_mb(const LaGeom &g, const PropagateJob &job, int idx)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.mb_count) return;
     const int i = idx % g.mb_w, mb_y = idx / g.mb_w;
     const int lc = job.lowres_costs[idx];
     const int intra_cost = job.intra_cost[idx];
     const int inter_cost = min(intra_cost, lc & LA_LOWRES_COST_MASK);
-    const int pin = job.propagate_in ? min(job.propagate_in[idx], 32767) : 0;
+    const int pin = job.propagate_in ? min(__ldcg(job.propagate_in + idx), 32767) : 0;
     const float propagate_intra = (float)(intra_cost * (int)job.inv_qscale[idx]);
     const float propagate_amount = (float)pin + propagate_intra * job.fps_factor;
     const float propagate_num = (float)(intra_cost - inter_cost);
@@ -535,6 +532,13 @@ propagate_kernel(LaGeom g, PropagateJob job)
     }
 }
 
+__global__ void __launch_bounds__(128)
+propagate_kernel(LaGeom g, PropagateJob job)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < g.mb_count) propagate_mb(g, job, idx);
+}
+
 int launch_propagate(cudaStream_t st, const LaGeom &g, const PropagateJob &job)
 {
     propagate_kernel<<<(g.mb_count + 127) / 128, 128, 0, st>>>(g, job);
@@ -542,17 +546,62 @@ int launch_propagate(cudaStream_t st, const LaGeom &g, const PropagateJob &job)
     return 0;
 }
 
+__device__ __forceinline__ void tree_finish_mb(const TreeFinishJob &job, int idx)
+{
+    const int intra_cost = ((int)job.intra_cost[idx] * (int)job.inv_qscale[idx] + 128) >> 8;
+    if (intra_cost) {
+        const int propagate_cost = (min(__ldcg(job.propagate + idx), 32767) * job.fps_factor + 128) >> 8;
+        const float log2_ratio = dev_log2(job.log2_lut, intra_cost + propagate_cost) - dev_log2(job.log2_lut, intra_cost) + job.weightdelta;
+        job.qp_offset[idx] = job.qp_offset_aq[idx] - job.strength * log2_ratio;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 tree_finish_kernel(LaGeom g, TreeFinishJob job)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.mb_count) return;
-    const int intra_cost = ((int)job.intra_cost[idx] * (int)job.inv_qscale[idx] + 128) >> 8;
-    if (intra_cost) {
-        const int propagate_cost = (min(job.propagate[idx], 32767) * job.fps_factor + 128) >> 8;
-        const float log2_ratio = dev_log2(job.log2_lut, intra_cost + propagate_cost) - dev_log2(job.log2_lut, intra_cost) + job.weightdelta;
-        job.qp_offset[idx] = job.qp_offset_aq[idx] - job.strength * log2_ratio;
+    if (idx < g.mb_count) tree_finish_mb(job, idx);
+}
+
+// A whole macroblock_tree walk in ONE launch: the steps are strictly sequential (each
+// propagate reads what the previous ones accumulated), so instead of one tiny kernel per step
+// a single 8-CTA thread-block cluster executes the list and separates the steps with the
+// hardware cluster barrier (release/acquire at cluster scope orders the global atomics).
+#define TREE_CLUSTER 8
+#define TREE_THREADS 1024
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(TREE_CLUSTER, 1, 1) __launch_bounds__(TREE_THREADS)
+tree_chain_kernel(LaGeom g, const TreeStep *steps, int nsteps, const float *log2_lut)
+{
+    const int tid = blockIdx.x * TREE_THREADS + threadIdx.x, nthr = TREE_CLUSTER * TREE_THREADS;
+    for (int s = 0; s < nsteps; s++) {
+        const TreeStep &st = steps[s];          // uniform across the cluster, so is st.sync
+        if (st.op == 0) {
+            for (int i = tid; i < st.n; i += nthr) st.zero[i] = 0;
+        } else if (st.op == 1) {
+            for (int i = tid; i < g.mb_count; i += nthr) propagate_mb(g, st.prop, i);
+        } else {
+            TreeFinishJob fj;
+            fj.propagate = st.fin_propagate; fj.intra_cost = st.fin_intra; fj.inv_qscale = st.fin_invq;
+            fj.qp_offset_aq = st.fin_qp_aq; fj.qp_offset = st.fin_qp; fj.fps_factor = st.fin_fps_factor;
+            fj.weightdelta = st.fin_weightdelta; fj.strength = st.fin_strength; fj.log2_lut = log2_lut;
+            for (int i = tid; i < g.mb_count; i += nthr) tree_finish_mb(fj, i);
+        }
+        if (st.sync) cluster_sync_all();
     }
+}
+
+int launch_tree_chain(cudaStream_t stream, const LaGeom &g, const TreeStep *steps_dev, int nsteps, const float *log2_lut)
+{
+    if (nsteps <= 0) return 0;
+    tree_chain_kernel<<<TREE_CLUSTER, TREE_THREADS, 0, stream>>>(g, steps_dev, nsteps, log2_lut);
+    XV_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_tree_finish(cudaStream_t st, const LaGeom &g, const TreeFinishJob &job)

@@ -113,6 +113,19 @@ struct PropagateJob {
 };
 int launch_propagate(cudaStream_t st, const LaGeom &g, const PropagateJob &job);
 
+// One step of a whole mb-tree walk executed by a single cluster kernel (no launch per step).
+struct TreeStep {
+    int op;                       // 0: zero an accumulator (n ints), 1: propagate, 2: finish
+    int n;                        // op 0: number of ints to clear
+    int sync;                     // cluster barrier after this step (0 when the next step is independent of it)
+    int *zero;                    // op 0
+    PropagateJob prop;            // op 1
+    // op 2 (pointers only; the LUT comes with the launch)
+    const int *fin_propagate; const uint16_t *fin_intra, *fin_invq; const float *fin_qp_aq; float *fin_qp;
+    int fin_fps_factor; float fin_weightdelta, fin_strength;
+};
+int launch_tree_chain(cudaStream_t st, const LaGeom &g, const TreeStep *steps_dev, int nsteps, const float *log2_lut);
+
 struct TreeFinishJob {
     const int *propagate; const uint16_t *intra_cost, *inv_qscale;
     const float *qp_offset_aq; float *qp_offset;
