@@ -270,10 +270,11 @@ void x264vfw_cuda_la_counters( x264vfw_cuda_la *la, uint64_t out[8] );
 
 /* Per-kernel-class device time of this session, measured with CUDA events on the session's
  * stream around every launch: [0] csp [1] aq [2] lowres [3] intra [4] motion search
- * [5] cost selection [6] weights [7] mb-tree.  Returns the totals accumulated so far in
- * ms[8] / count[8] (may be NULL); enable = 1/0 switches measurement on/off and resets the
- * totals, -1 only reads. */
-int x264vfw_cuda_la_profile( x264vfw_cuda_la *la, int enable, double ms[8], uint64_t count[8] );
+ * (ordered part: verification wavefront) [5] cost selection [6] weights [7] mb-tree
+ * [8] motion search (speculative parallel passes) [9..15] reserved.  Returns the totals
+ * accumulated so far in ms[16] / count[16] (may be NULL); enable = 1/0 switches measurement
+ * on/off and resets the totals, -1 only reads. */
+int x264vfw_cuda_la_profile( x264vfw_cuda_la *la, int enable, double ms[16], uint64_t count[16] );
 
 const char *x264vfw_cuda_last_error( void );
 /* "x264vfw_cuda <version> sm_100a"; also proves the library loaded. */

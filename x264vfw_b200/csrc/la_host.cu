@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <chrono>
 #include <deque>
+#include <string>
 #include <vector>
 #include <array>
 
@@ -87,7 +88,7 @@ struct PendingResult { Frame *f; int d0, d1; int slot; bool is_b; bool intra; };
 
 // Optional per-kernel-class device timing: CUDA events recorded on the session's stream around
 // each launch, resolved at the next synchronisation (bench.py reads the totals).
-enum KClass { K_CSP, K_AQ, K_LOWRES, K_INTRA, K_ME, K_FINALIZE, K_WEIGHT, K_TREE, K_N };
+enum KClass { K_CSP, K_AQ, K_LOWRES, K_INTRA, K_ME, K_FINALIZE, K_WEIGHT, K_TREE, K_ME_PASS, K_N };
 struct ProfRec { int cls; cudaEvent_t a, b; };
 struct Prof {
     bool on = false;
@@ -112,6 +113,10 @@ struct La {
     int speculate = 1;
     int ext = X264VFW_CUDA_EXT_NONE;   // packed 4:2:2 -> I444 uses the documented extension conversion
     int me_rows = 0;         // warps per search in the wavefront kernel
+    int me_variant = 1;      // 0: plain wavefront, 1: speculative parallel passes + verification wavefront
+    int me_passes = 2;       // parallel passes of the speculative search
+    int *d_me_stats = nullptr;
+    int stats_verbose = 0; std::string dbg_jobs; int dbg_prev[8] = {0};
     // searches the decision logic asked for during the current decision, and the ones predicted
     // for the next decision (same pattern, shifted by the mini-GOP just emitted): {frame, list, dist}
     std::vector<std::array<int, 3>> asked_now, wanted;
@@ -131,7 +136,7 @@ struct La {
     uint8_t *d_weight_buf = nullptr;
     // ME engines: [0] runs on the main stream (on-demand searches), [1..ME_SIDE] on side streams
     // (speculative searches), each with its own inter-row record / ticket scratch.
-    int2 *d_rec[1 + ME_SIDE] = {nullptr}; int *d_ticket[1 + ME_SIDE] = {nullptr};
+    int2 *d_rec[1 + ME_SIDE] = {nullptr}; int *d_ticket[1 + ME_SIDE] = {nullptr}; int4 *d_assumed[1 + ME_SIDE] = {nullptr};
     cudaStream_t st_me[1 + ME_SIDE] = {nullptr};
     cudaEvent_t ev_me[1 + ME_SIDE][ME_EVENTS];              // done-events of the side launches (ring)
     uint64_t me_seq[1 + ME_SIDE] = {0};                     // launches issued per engine
@@ -140,7 +145,8 @@ struct La {
     cudaEvent_t ev_io = nullptr;                            // caller's buffers are free again (H2D / D2H of this put done)
     cudaEvent_t ev_h2d = nullptr, ev_csp = nullptr;
     cudaStream_t st_io = nullptr;                           // host <-> device copies of the borrowed buffers
-    int me_epoch = 0, me_rr = 0;
+    int me_guess = 1;
+    int me_epoch = 0, me_rr = 0, me_side = ME_SIDE;   // side engines in use (1..ME_SIDE)
     int *d_results = nullptr; int *h_results = nullptr;     // ring of 4-int slots
     int result_head = 0;
     unsigned *d_wscore = nullptr; unsigned *h_wscore = nullptr;
@@ -185,7 +191,7 @@ static cudaEvent_t prof_event(La *la)
 }
 struct ProfScope {
     La *la; int cls; cudaStream_t st; cudaEvent_t a = nullptr;
-    ProfScope(La *l, int c, cudaStream_t s = nullptr) : la(l), cls(c), st(s ? s : l->st) { if (la->prof.on) { a = prof_event(la); cudaEventRecord(a, st); } }
+    ProfScope(La *l, int c, cudaStream_t s = nullptr) : la(l), cls(c), st(s ? s : l->st) { if (la->prof.on && c >= 0) { a = prof_event(la); cudaEventRecord(a, st); } }
     ~ProfScope() { if (a) { cudaEvent_t b = prof_event(la); cudaEventRecord(b, st); la->prof.recs.push_back(ProfRec{cls, a, b}); } }
 };
 static void prof_resolve(La *la)
@@ -456,6 +462,7 @@ static void me_params_init(La *la, MeParams &mp)
     mp.subpel_refine = la->la_subpel_refine; mp.satd = la->la_satd; mp.me_range = la->p.me_range;
     mp.cost_mv = la->d_cost_mv + la->cost_mv_half;
     mp.rows_in_flight = la->me_rows;
+    mp.variant = la->me_variant; mp.npasses = la->me_passes; mp.stats = la->d_me_stats;
 }
 
 static void me_add_job(La *la, MeParams &mp, int eng, Frame *fenc, Frame *ref, int list, int dist, const WeightDev *w)
@@ -470,8 +477,33 @@ static void me_add_job(La *la, MeParams &mp, int eng, Frame *fenc, Frame *ref, i
     j.mv_costs = fenc->mv_costs[list][dist - 1];
     j.rec = la->d_rec[eng] + (size_t)mp.njobs * la->g.mb_count;
     j.ticket = la->d_ticket[eng] + mp.njobs;
+    j.assumed = la->d_assumed[eng] + (size_t)mp.njobs * la->g.mb_count;
+    // first guess of the speculative search: the same (list, distance) field of the previous
+    // frame.  Only a hint: whatever it holds (even a field still being written) is recorded as
+    // "assumed" and checked against the final MVs, so it needs no ordering.
+    j.guess = nullptr; j.guess_num = j.guess_den = 1;
+    if (la->me_guess) {
+        const int pi = fenc->i_frame - 1;
+        Frame *pf = (pi >= 0 && pi < (int)la->by_index.size()) ? la->by_index[pi] : nullptr;
+        if (pf == fenc) pf = nullptr;
+        auto have = [](const Frame *f, int l, int d) { return f->spec[l][d - 1] || f->searched[l][d - 1]; };
+        const int dmax = list ? la->p.bframes : la->p.bframes + 1;
+        if (w && have(fenc, list, dist)) j.guess = j.mvs;                      // weighted re-search: start from the unweighted result (same array)
+        else if (pf && have(pf, list, dist)) j.guess = pf->mvs[list][dist - 1];
+        else {
+            // this frame's (or the previous frame's) field of another distance, rescaled
+            for (int k = 1; k <= dmax && !j.guess; k++)
+                for (int sgn = -1; sgn <= 1 && !j.guess; sgn += 2) {
+                    const int d2 = dist + sgn * k;
+                    if (d2 < 1 || d2 > dmax) continue;
+                    if (have(fenc, list, d2)) { j.guess = fenc->mvs[list][d2 - 1]; j.guess_num = dist; j.guess_den = d2; }
+                    else if (pf && have(pf, list, d2)) { j.guess = pf->mvs[list][d2 - 1]; j.guess_num = dist; j.guess_den = d2; }
+                }
+        }
+    }
     mp.njobs++;
     la->n_mb_search += la->g.mb_count;
+    if (la->stats_verbose) { char b[96]; snprintf(b, sizeof(b), " [f%d l%d d%d%s%s]", fenc->i_frame, list, dist, w ? " W" : "", j.guess ? "" : " noguess"); la->dbg_jobs += b; }
 }
 
 // Make the main stream wait for launch `seq` of side engine `eng` (and everything before it).
@@ -486,13 +518,42 @@ static int wait_engine(La *la, int eng, uint64_t seq)
     return 0;
 }
 
+// One batch of searches: speculative parallel passes + verification wavefront, or the plain
+// wavefront (me_variant 0).
+static int me_kernels(La *la, cudaStream_t st, const MeParams &mp, bool prof)
+{
+    if (!mp.variant) { ProfScope ps(la, prof ? K_ME : -1, st); return launch_me(st, la->g, mp); }
+    {
+        ProfScope ps(la, prof ? K_ME_PASS : -1, st);
+        for (int pass = 0; pass < mp.npasses; pass++)
+            if (launch_me_pass(st, la->g, mp, pass) < 0) return -1;
+    }
+    la->n_launch += mp.npasses;
+    ProfScope ps(la, prof ? K_ME : -1, st);
+    return launch_me_verify(st, la->g, mp);
+}
+
 static int me_launch(La *la, MeParams &mp, int eng)
 {
     if (!mp.njobs) return 0;
     cudaStream_t st = la->st_me[eng];
     LA_CUDA(cudaMemsetAsync(la->d_ticket[eng], 0, XV_ME_MAX_JOBS * sizeof(int), st));
     mp.epoch = ++la->me_epoch;
-    { ProfScope ps(la, K_ME, st); if (launch_me(st, la->g, mp) < 0) return -1; }
+    if (la->stats_verbose && la->d_me_stats) {
+        // diagnostics only: serialises the launch to attribute time and hit rates to it
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaStreamSynchronize(la->st); cudaStreamSynchronize(st);
+        cudaEventRecord(a, st);
+        if (me_kernels(la, st, mp, false) < 0) return -1;
+        cudaEventRecord(b, st); cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        int v[8]; cudaMemcpy(v, la->d_me_stats, sizeof(v), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[me eng%d] %.3f ms kept %d miss %d pass0 %d pass1 %d pass2 %d |%s\n", eng, ms, v[0] - la->dbg_prev[0], v[1] - la->dbg_prev[1],
+                v[2] - la->dbg_prev[2], v[3] - la->dbg_prev[3], v[4] - la->dbg_prev[4], la->dbg_jobs.c_str());
+        memcpy(la->dbg_prev, v, sizeof(v)); la->dbg_jobs.clear();
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    } else
+    { if (me_kernels(la, st, mp, true) < 0) return -1; }
     la->n_launch++;
     if (eng) la->n_spec_jobs += mp.njobs; else { la->n_ondemand++; la->n_ondemand_jobs += mp.njobs; }
     if (eng) {
@@ -511,7 +572,7 @@ static int speculate_searches(La *la, Frame *fn)
 {
     if (!la->speculate) return 0;
     const int n = fn->i_frame, B = la->p.bframes;
-    const int eng = 1 + (la->me_rr++ % ME_SIDE);
+    const int eng = 1 + (la->me_rr++ % la->me_side);
     // hand-off: the side stream may start once everything queued so far on the main stream
     // (this frame's lowres planes, the zeroing of recycled arrays) is done
     LA_CUDA(cudaEventRecord(la->ev_ready, la->st));
@@ -1289,6 +1350,10 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_SPEC_THRESHOLD")) la->spec_threshold = atof(e);
     if (const char *e = getenv("X264VFW_CUDA_PREDICT")) la->predict = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_TREE_CHAIN")) la->tree_chain = atoi(e);
+    if (const char *e = getenv("X264VFW_CUDA_ME_SIDE")) { la->me_side = atoi(e); if (la->me_side < 1) la->me_side = 1; if (la->me_side > ME_SIDE) la->me_side = ME_SIDE; }
+    if (const char *e = getenv("X264VFW_CUDA_ME_VARIANT")) la->me_variant = atoi(e);
+    if (const char *e = getenv("X264VFW_CUDA_ME_PASSES")) { la->me_passes = atoi(e); if (la->me_passes < 1) la->me_passes = 1; if (la->me_passes > 4) la->me_passes = 4; }
+    if (const char *e = getenv("X264VFW_CUDA_ME_GUESS")) la->me_guess = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ME_ROWS")) la->me_rows = atoi(e);
     else la->me_rows = -1;   // resolved below once the geometry is known
     x264vfw_cuda_lowres_geom lg;
@@ -1340,7 +1405,6 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
              cudaEventCreateWithFlags(&la->ev_io, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_csp, cudaEventDisableTiming) == cudaSuccess &&
-             cudaStreamCreateWithPriority(&la->st_io, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
              cudaMalloc((void **)&la->d_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMallocHost((void **)&la->h_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMalloc((void **)&la->d_wscore, 64) == cudaSuccess &&
@@ -1349,11 +1413,15 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
             ok = ok && cudaMallocHost((void **)&la->h_tree[k], TREE_MAX_STEPS * sizeof(TreeStep)) == cudaSuccess &&
                  cudaMalloc((void **)&la->d_tree[k], TREE_MAX_STEPS * sizeof(TreeStep)) == cudaSuccess &&
                  cudaEventCreateWithFlags(&la->ev_tree[k], cudaEventDisableTiming) == cudaSuccess;
+        if (const char *e = getenv("X264VFW_CUDA_STATS")) la->stats_verbose = atoi(e) >= 2;
+        if (getenv("X264VFW_CUDA_STATS"))
+            ok = ok && cudaMalloc((void **)&la->d_me_stats, 8 * sizeof(int)) == cudaSuccess && cudaMemset(la->d_me_stats, 0, 8 * sizeof(int)) == cudaSuccess;
         la->st_me[0] = la->st;
-        for (int e = 0; e <= ME_SIDE && ok; e++) {
+        for (int e = 0; e <= la->me_side && ok; e++) {
             ok = ok && cudaMalloc((void **)&la->d_rec[e], (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
                  cudaMemset(la->d_rec[e], 0, (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int2)) == cudaSuccess &&
-                 cudaMalloc((void **)&la->d_ticket[e], XV_ME_MAX_JOBS * sizeof(int)) == cudaSuccess;
+                 cudaMalloc((void **)&la->d_ticket[e], XV_ME_MAX_JOBS * sizeof(int)) == cudaSuccess &&
+                 cudaMalloc((void **)&la->d_assumed[e], (size_t)XV_ME_MAX_JOBS * g.mb_count * sizeof(int4)) == cudaSuccess;
             if (e) ok = ok && cudaStreamCreateWithPriority(&la->st_me[e], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
             for (int k = 0; k < ME_EVENTS && ok; k++)
                 ok = ok && cudaEventCreateWithFlags(&la->ev_me[e][k], cudaEventDisableTiming) == cudaSuccess;
@@ -1394,6 +1462,13 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     }
     if (la->st) cudaStreamSynchronize(la->st);
     for (int e = 1; e <= ME_SIDE; e++) if (la->st_me[e]) cudaStreamSynchronize(la->st_me[e]);
+    if (la->d_me_stats) {
+        int v[8] = {0};
+        cudaMemcpy(v, la->d_me_stats, sizeof(v), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[x264vfw_cuda] speculative search: kept %d, re-searched in order %d (%.2f%%); searched per pass: %d %d %d %d\n",
+                v[0], v[1], 100.0 * v[1] / (v[0] + v[1] > 0 ? v[0] + v[1] : 1), v[2], v[3], v[4], v[5]);
+        cudaFree(la->d_me_stats);
+    }
     prof_resolve(la);
     for (cudaEvent_t e : la->prof.pool) cudaEventDestroy(e);
     for (Frame *f : la->pool) frame_free(f);
@@ -1401,7 +1476,7 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     for (float *q : la->qp_free) cudaFreeHost(q);
     cudaFree(la->d_cost_mv); cudaFree(la->d_log2_lut); cudaFree(la->d_exp2_lut); cudaFree(la->d_weight_buf);
     for (int e = 0; e <= ME_SIDE; e++) {
-        cudaFree(la->d_rec[e]); cudaFree(la->d_ticket[e]);
+        cudaFree(la->d_rec[e]); cudaFree(la->d_ticket[e]); cudaFree(la->d_assumed[e]);
         for (int k = 0; k < ME_EVENTS; k++) if (la->ev_me[e][k]) cudaEventDestroy(la->ev_me[e][k]);
         if (e && la->st_me[e]) cudaStreamDestroy(la->st_me[e]);
     }
@@ -1434,6 +1509,13 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     const bool borrowed = conv_pic || !src_on_device;
     auto chroma_rows = [&](int csp_is_420, int i) { return (i && csp_is_420) ? hgt / 2 : hgt; };
 
+    if (borrowed && !la->st_io) {
+        // host <-> device copies get their own stream (created on first use: device-resident
+        // sessions keep one hardware queue less busy)
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        XV_CUDA_OK(cudaStreamCreateWithPriority(&la->st_io, cudaStreamNonBlocking, prio_hi));
+    }
     Frame *f = frame_get(la, la->n_input);
     if (!f) return -1;
     la->n_input++;
@@ -1596,7 +1678,7 @@ int64_t x264vfw_cuda_la_read(x264vfw_cuda_la *h, int frame, int what, int a, int
     if (!la || !dst) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
     if (la_sync(la) < 0) return -1;
-    for (int e = 1; e <= ME_SIDE; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
+    for (int e = 1; e <= la->me_side; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
     const int n = la->g.mb_count, B = la->p.bframes;
     if (what == X264VFW_CUDA_LA_CONV_PLANES) {
         if (cap < la->d_planes_bytes) { set_error("read: buffer too small"); return -1; }
@@ -1635,15 +1717,15 @@ int64_t x264vfw_cuda_la_read(x264vfw_cuda_la *h, int frame, int what, int a, int
     return (int64_t)bytes;
 }
 
-int x264vfw_cuda_la_profile(x264vfw_cuda_la *h, int enable, double ms[8], uint64_t count[8])
+int x264vfw_cuda_la_profile(x264vfw_cuda_la *h, int enable, double ms[16], uint64_t count[16])
 {
     La *la = (La *)h;
     if (!la) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
     if (la_sync(la) < 0) return -1;
-    for (int e = 1; e <= ME_SIDE; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
+    for (int e = 1; e <= la->me_side; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
     prof_resolve(la);
-    for (int i = 0; i < K_N; i++) { if (ms) ms[i] = la->prof.ms[i]; if (count) count[i] = la->prof.n[i]; }
+    for (int i = 0; i < 16; i++) { if (ms) ms[i] = i < K_N ? la->prof.ms[i] : 0; if (count) count[i] = i < K_N ? la->prof.n[i] : 0; }
     if (enable >= 0) {
         la->prof.on = enable != 0;
         for (int i = 0; i < K_N; i++) { la->prof.ms[i] = 0; la->prof.n[i] = 0; }

@@ -45,6 +45,9 @@ struct MeJob {
     int *mv_costs;
     int2 *rec;                    // per-MB {mv, epoch} records: the inter-row channel of this launch
     int *ticket;                  // row hand-out counter (zeroed by the launcher)
+    const int *guess;             // speculative search: a similar MV field (e.g. the same search of the previous frame) or null
+    int guess_num, guess_den;     // ... scaled by num/den (a field of another temporal distance)
+    int4 *assumed;                // speculative search: per MB, the four neighbour MVs its current result was computed from
 };
 #define XV_ME_MAX_JOBS 8
 struct MeParams {
@@ -60,8 +63,13 @@ struct MeParams {
     int satd;                     // mbcmp is SATD
     int me_range;
     const uint16_t *cost_mv;      // centred table
+    int variant;                  // 0: plain wavefront (me_wavefront_kernel); 1: speculative parallel passes + verification wavefront
+    int npasses;                  // variant 1: parallel passes before the verification
+    int *stats;                   // optional device counters: [0] kept, [1] re-searched in order, [2..5] searched in pass 0..3
 };
-int launch_me(cudaStream_t st, const LaGeom &g, const MeParams &p);
+int launch_me(cudaStream_t st, const LaGeom &g, const MeParams &p);                    // plain wavefront
+int launch_me_pass(cudaStream_t st, const LaGeom &g, const MeParams &p, int pass);     // one speculative parallel pass
+int launch_me_verify(cudaStream_t st, const LaGeom &g, const MeParams &p);             // exact verification wavefront
 
 // ---- per-MB cost selection + frame accumulators ([x264] rest of slicetype_mb_cost) ---------
 struct FinalizeJob {

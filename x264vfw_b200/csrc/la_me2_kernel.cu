@@ -1,0 +1,677 @@
+// Lowres motion search, parallel part: speculative per-MB searches, several MBs per warp.
+//
+// The sequential definition ([x264] slicetype_mb_cost scanning MBs in reverse raster order,
+// each MB predicted from its right / below / below-left / below-right neighbours) makes one
+// search a chain of mb_w + 2(mb_h-1) dependent MB searches.  But an MB's result is a pure
+// function of its pixels and of those four neighbour MVs, and motion fields are smooth: here
+// every MB is searched AT ONCE from assumed neighbour MVs (the same search of the previous
+// frame as a first guess, then the results of the previous pass), and a cheap verification
+// wavefront (la_me_kernel.cu: me_verify_kernel) keeps a result only if the inputs it assumed
+// are the final MVs of its neighbours -- otherwise it re-runs that MB's search in order.  The
+// output is therefore exactly the sequential scan's (bit-exact incl. tie-breaks); the guess
+// only decides how much of the work happens off the critical path.
+//
+// Mapping: a group of 8 lanes owns one MB and spends ONE lane per candidate position (a lane
+// scores a whole 8x8 candidate: 8 rows of __vsadu4, or an in-register 8x8 SATD), so the
+// control / addressing / reduction instruction stream is shared by the 4 MBs of a warp.
+// The warp never de-converges: groups that are idle, skipped or done with a loop early walk
+// through the same rounds with their candidates predicated off (see FULL below) -- per-group
+// lane masks would let the groups run one after the other (measured: 10.8 active lanes per
+// instruction), which defeats the purpose.
+#include "la_common.cuh"
+
+namespace xv {
+
+#define BIG_COST 0x3fffffff
+#define WIN_W 64
+#define WIN_H 40
+#define WIN_R 16
+#define SUB_W 32
+#define SUB_H 12
+
+struct __align__(16) GroupSmem {
+    uint8_t win[WIN_H * WIN_W];       // full-pel window of the (weighted) plane 0
+    uint8_t sub[4][SUB_H * SUB_W];    // sub-pel windows of the four phase planes
+};
+
+__device__ __forceinline__ uint2 ld_rec2(const int2 *p)
+{
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_rec2(int2 *p, int mv, int epoch)
+{
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(mv), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void cpa16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpa8(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int LPS>
+struct Mb {
+    static constexpr int GL = 8 * LPS;      // lanes of a group
+    static constexpr int RPL = 8 / LPS;     // block rows scored by one lane
+    uint2 fe[RPL];                          // this lane's rows of the source MB
+    int gl, slot, r0;                       // lane within group, candidate slot, first block row
+    int stride, pel, px, py;
+    const uint8_t *fref0; int plane_stride;
+    const uint8_t *fref_w;
+    WeightDev w;
+    const uint16_t *cost_mv;
+    int mvp_x, mvp_y;
+    const uint8_t *win; int wx0, wy0;
+    const uint8_t *sub; int sx0, sy0;
+};
+
+#define FULL 0xffffffffu
+// Every shuffle / warp barrier below is executed by the WHOLE warp at a warp-uniform point;
+// what differs per group is data and predicates only.  (Per-group lane masks would let the
+// groups run de-converged, i.e. one after the other -- measured: 10.8 active lanes per
+// instruction -- which defeats the purpose of sharing the instruction stream.)
+template <int LPS> __device__ __forceinline__ int g_bcast(int v, int slot)
+{
+    return __shfl_sync(FULL, v, slot * LPS, 8 * LPS);
+}
+template <int LPS> __device__ __forceinline__ int g_min(int v)
+{
+    v = min(v, __shfl_xor_sync(FULL, v, LPS));
+    v = min(v, __shfl_xor_sync(FULL, v, 2 * LPS));
+    v = min(v, __shfl_xor_sync(FULL, v, 4 * LPS));
+    return v;
+}
+template <int LPS> __device__ __forceinline__ int part_sum(int v)
+{
+    if (LPS == 2) v += __shfl_xor_sync(FULL, v, 1);
+    return v;
+}
+template <int LPS> __device__ __forceinline__ int mvcost2(const Mb<LPS> &m, int qx, int qy)
+{
+    return (int)__ldg(m.cost_mv + (qx - m.mvp_x)) + (int)__ldg(m.cost_mv + (qy - m.mvp_y));
+}
+
+// ---- SATD of this lane's rows ([x264] x264_pixel_satd_8x4 per 4 rows: two 4x4 Hadamards) ----
+__device__ __forceinline__ int satd_8x4_regs(const uint2 *a, const uint2 *b)
+{
+    int sum = 0;
+#pragma unroll
+    for (int blk = 0; blk < 2; blk++) {
+        int t[4][4];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const uint32_t wa = blk ? a[y].y : a[y].x, wb = blk ? b[y].y : b[y].x;
+            const int d0 = (int)(wa & 0xff) - (int)(wb & 0xff), d1 = (int)((wa >> 8) & 0xff) - (int)((wb >> 8) & 0xff);
+            const int d2 = (int)((wa >> 16) & 0xff) - (int)((wb >> 16) & 0xff), d3 = (int)(wa >> 24) - (int)(wb >> 24);
+            const int s01 = d0 + d1, e01 = d0 - d1, s23 = d2 + d3, e23 = d2 - d3;
+            t[y][0] = s01 + s23; t[y][1] = s01 - s23; t[y][2] = e01 + e23; t[y][3] = e01 - e23;
+        }
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const int s01 = t[0][x] + t[1][x], e01 = t[0][x] - t[1][x], s23 = t[2][x] + t[3][x], e23 = t[2][x] - t[3][x];
+            sum += abs(s01 + s23) + abs(s01 - s23) + abs(e01 + e23) + abs(e01 - e23);
+        }
+    }
+    return sum >> 1;
+}
+template <int LPS> __device__ __forceinline__ int satd_rows(const Mb<LPS> &m, const uint2 *a)
+{
+    if (LPS == 1) {
+        // two 8x4 halves through ONE copy of the butterfly code (rows 4-7 are moved down for
+        // the second trip): code size matters more than 16 register moves here
+        uint2 f[4], r[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++) { f[y] = m.fe[y]; r[y] = a[y]; }
+        int sum = 0;
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            sum += satd_8x4_regs(f, r);
+#pragma unroll
+            for (int y = 0; y < 4; y++) { f[y] = m.fe[4 * (LPS == 1) + y]; r[y] = a[4 * (LPS == 1) + y]; }
+        }
+        return sum;
+    }
+    return part_sum<LPS>(satd_8x4_regs(m.fe, a));
+}
+template <int LPS> __device__ __forceinline__ int sad_rows(const Mb<LPS> &m, const uint2 *a)
+{
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < Mb<LPS>::RPL; r++) c += __vsadu4(a[r].x, m.fe[r].x) + __vsadu4(a[r].y, m.fe[r].y);
+    return c;
+}
+
+// weighted references are rare (fades): keep their per-pixel arithmetic out of line
+__device__ __noinline__ uint32_t weight_word_call(int scale, int denom, int offset, uint32_t v)
+{
+    const WeightDev w = {1, scale, denom, offset};
+    return weight_word(w, v);
+}
+
+// ---- candidates ----------------------------------------------------------------------------
+// full-pel candidate on the (possibly weighted) plane 0: SAD + mv cost
+template <int LPS>
+__device__ __forceinline__ int cand_fpel(const Mb<LPS> &m, int mx, int my, bool active)
+{
+    constexpr int RPL = Mb<LPS>::RPL;
+    int c = 0, mvc = 0;
+    if (active) {
+        mvc = mvcost2(m, mx * 4, my * 4);
+        const int wx = m.px + mx - m.wx0, wy = m.py + my - m.wy0;
+        if (m.win && wx >= 0 && wx + 12 <= WIN_W && wy >= 0 && wy + 8 <= WIN_H) {
+            const int off = (wy + m.r0) * WIN_W + wx;
+            const uint32_t *q = (const uint32_t *)(m.win + (off & ~3));
+            const unsigned sh = (unsigned)(off & 3) * 8;
+#pragma unroll
+            for (int r = 0; r < RPL; r++) {
+                const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                c += __vsadu4(__funnelshift_r(w0, w1, sh), m.fe[r].x) + __vsadu4(__funnelshift_r(w1, w2, sh), m.fe[r].y);
+                q += WIN_W / 4;
+            }
+        } else {
+            const uint8_t *p = m.fref_w + m.pel + (my + m.r0) * m.stride + mx;
+#pragma unroll
+            for (int r = 0; r < RPL; r++) {
+                const uint2 a = load8u(p);
+                c += __vsadu4(a.x, m.fe[r].x) + __vsadu4(a.y, m.fe[r].y);
+                p += m.stride;
+            }
+        }
+    }
+    c = part_sum<LPS>(c);
+    return active ? c + mvc : BIG_COST;
+}
+
+// quarter-pel candidate through get_ref: SAD or SATD + mv cost
+template <int LPS, bool SUBWIN>
+__device__ __forceinline__ int cand_qpel(const Mb<LPS> &m, int qx, int qy, bool active, bool use_satd)
+{
+    constexpr int RPL = Mb<LPS>::RPL;
+    uint2 a[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; r++) a[r] = make_uint2(0, 0);
+    int mvc = 0;
+    if (active) {
+        mvc = mvcost2(m, qx, qy);
+        const int qidx = ((qy & 3) << 2) + (qx & 3);
+        const bool two = (qidx & 5) != 0;
+        if (SUBWIN) {
+            const int X = m.px + (qx >> 2) - m.sx0, Y = m.py + (qy >> 2) + m.r0 - m.sy0;
+            const uint8_t *p0 = m.sub + c_hpel_ref0[qidx] * (SUB_H * SUB_W);
+            const uint8_t *p1 = m.sub + c_hpel_ref1[qidx] * (SUB_H * SUB_W);
+            const int o0 = (Y + ((qy & 3) == 3)) * SUB_W + X, o1 = Y * SUB_W + X + ((qx & 3) == 3);
+            const uint32_t *q0 = (const uint32_t *)(p0 + (o0 & ~3)), *q1 = (const uint32_t *)(p1 + (o1 & ~3));
+            const unsigned s0 = (unsigned)(o0 & 3) * 8, s1 = (unsigned)(o1 & 3) * 8;
+#pragma unroll
+            for (int r = 0; r < RPL; r++) {
+                uint2 v = make_uint2(__funnelshift_r(q0[0], q0[1], s0), __funnelshift_r(q0[1], q0[2], s0));
+                if (two) {
+                    v.x = __vavgu4(v.x, __funnelshift_r(q1[0], q1[1], s1));
+                    v.y = __vavgu4(v.y, __funnelshift_r(q1[1], q1[2], s1));
+                }
+                a[r] = v;
+                q0 += SUB_W / 4; q1 += SUB_W / 4;
+            }
+        } else {
+            const int off = m.pel + ((qy >> 2) + m.r0) * m.stride + (qx >> 2);
+            const uint8_t *p0 = m.fref0 + (size_t)c_hpel_ref0[qidx] * m.plane_stride + off + ((qy & 3) == 3) * m.stride;
+            const uint8_t *p1 = m.fref0 + (size_t)c_hpel_ref1[qidx] * m.plane_stride + off + ((qx & 3) == 3);
+#pragma unroll
+            for (int r = 0; r < RPL; r++) {
+                uint2 v = load8u(p0);
+                if (two) {
+                    const uint2 b = load8u(p1);
+                    v.x = __vavgu4(v.x, b.x); v.y = __vavgu4(v.y, b.y);
+                }
+                a[r] = v;
+                p0 += m.stride; p1 += m.stride;
+            }
+        }
+        if (m.w.on) {
+#pragma unroll
+            for (int r = 0; r < RPL; r++) { a[r].x = weight_word_call(m.w.scale, m.w.denom, m.w.offset, a[r].x); a[r].y = weight_word_call(m.w.scale, m.w.denom, m.w.offset, a[r].y); }
+        }
+    }
+    int c;
+    if (use_satd) c = satd_rows(m, a);
+    else c = part_sum<LPS>(sad_rows(m, a));
+    return active ? c + mvc : BIG_COST;
+}
+
+__constant__ const signed char c2_hex2[8][2] = {{-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0}};
+__constant__ const unsigned char c2_mod6m1[8] = {5, 0, 1, 2, 3, 4, 5, 0};
+__constant__ const signed char c2_square1[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
+__constant__ const signed char c2_hex_first[6][3] = {{-2, 0, 2}, {-1, 2, 3}, {1, 2, 4}, {2, 0, 5}, {1, -2, 6}, {-1, -2, 7}};
+
+struct MeResult2 { int mvx, mvy, cost; };
+
+// stage the 64x40 full-pel window of fref_w around (cx,cy) (MB-relative full-pel): 160 chunks of 16 B
+template <int LPS>
+__device__ __forceinline__ void win_issue(const Mb<LPS> &m, GroupSmem &sm, const LaGeom &g, bool on, int cx, int cy, int &wx0, int &wy0)
+{
+    constexpr int GL = Mb<LPS>::GL;
+    wx0 = (m.px + cx - WIN_R) & ~15;
+    wx0 = min(max(wx0, -32), g.lstride - 32 - WIN_W);
+    wy0 = min(max(m.py + cy - WIN_R, -32), g.lh + 32 - WIN_H);
+    const uint8_t *base = m.fref_w + wy0 * m.stride + wx0;
+    __syncwarp();                                        // previous readers of the window are done
+    if (on) {
+        // lane gl copies chunk (row, col16) = (gl/4 + (GL/4) k, gl%4)
+        const uint8_t *src = base + (m.gl >> 2) * m.stride + (m.gl & 3) * 16;
+        uint8_t *dst = sm.win + (m.gl >> 2) * WIN_W + (m.gl & 3) * 16;
+        const int sstep = (GL / 4) * m.stride;
+#pragma unroll
+        for (int k = 0; k < (WIN_H * 4) / GL; k++) {
+            cpa16(dst, src);
+            src += sstep; dst += (GL / 4) * WIN_W;
+        }
+    }
+}
+__device__ __forceinline__ void win_commit()
+{
+    cpa_wait_all();
+    __syncwarp();
+}
+// stage the four 32x12 sub-pel windows around full-pel position (fx,fy) (MB-relative): 96 chunks of 16 B
+template <int LPS>
+__device__ __forceinline__ void sub_load(Mb<LPS> &m, GroupSmem &sm, bool on, int fx, int fy)
+{
+    constexpr int GL = Mb<LPS>::GL;
+    m.sx0 = (m.px + fx - 1) & ~15;
+    m.sy0 = m.py + fy - 1;
+    __syncwarp();
+    if (on) {
+        // per plane 24 chunks = 12 rows x 2 halves: lane gl copies (row, half) = (gl/2 + (GL/2) j, gl%2)
+        const uint8_t *src = m.fref0 + m.sy0 * m.stride + m.sx0 + (m.gl >> 1) * m.stride + (m.gl & 1) * 16;
+        uint8_t *dst = &sm.sub[0][0] + (m.gl >> 1) * SUB_W + (m.gl & 1) * 16;
+        const int sstep = (GL / 2) * m.stride;
+#pragma unroll
+        for (int pl = 0; pl < 4; pl++) {
+            const uint8_t *s2 = src; uint8_t *d2 = dst;
+#pragma unroll
+            for (int j = 0; j < 24 / GL; j++) {
+                cpa16(d2, s2);
+                s2 += sstep; d2 += (GL / 2) * SUB_W;
+            }
+            src += m.plane_stride; dst += SUB_H * SUB_W;
+        }
+    }
+    cpa_wait_all();
+    __syncwarp();
+    m.sub = &sm.sub[0][0];
+}
+
+// `on`: this group's MB is being searched (group-uniform).
+//
+// The full-pel part is ONE loop around ONE candidate evaluation: every group carries its own
+// state (which round of x264_me_search_ref it is in) and supplies that round's candidates, so
+// groups need not be in the same round -- a group that leaves the hexagon early goes on to
+// the square refine while its neighbours iterate -- and the code stays small (the first
+// version inlined the evaluation at seven call sites: 129 KB of SASS and 23 % of the stall
+// samples waiting for instructions).  The sub-pel part is one loop of two rounds.
+enum { S_PRED, S_RZ, S_HEX1, S_HEXIT, S_SQUARE, S_DIA, S_DONE };
+
+template <int LPS, bool QPRED>
+__device__ __forceinline__ MeResult2 me_search_mb2(Mb<LPS> &m, GroupSmem &sm, const LaGeom &g, const MeParams &P, const bool on,
+                                                   const int mvc[4][2], int i_mvc, int min_sx, int max_sx, int min_sy, int max_sy)
+{
+    const int mv_x_min = min_sx >> 2, mv_x_max = max_sx >> 2, mv_y_min = min_sy >> 2, mv_y_max = max_sy >> 2;
+    const int grp = m.slot;
+    int bmx = 0, bmy = 0, bcost = 0, bpred_cost = LA_COST_MAX, bpred_mx = 0, bpred_my = 0;
+    int pm_fx = 0, pm_fy = 0;
+    int st = S_DONE;
+    // S_PRED (subme < 3): this lane's full-pel predictor candidate
+    int pcx = 0, pcy = 0; bool pact = false, pzslot = false;
+    // S_RZ (subme >= 3): what the predictor round found
+    bool subpel = false, pmv_nz = false, need_zero = false; int pmv_cost = 0;
+    m.win = nullptr;
+
+    if (QPRED) {
+        const int pmx = clip3i(m.mvp_x, mv_x_min * 4, mv_x_max * 4), pmy = clip3i(m.mvp_y, mv_y_min * 4, mv_y_max * 4);
+        int wx0, wy0;
+        win_issue(m, sm, g, on, (pmx + 2) >> 2, (pmy + 2) >> 2, wx0, wy0);
+        // slot 0 = clipped mvp, slots 1..n = surviving clipped candidates (x264_predictor_clip)
+        int cx = pmx, cy = pmy, n = 0;
+        bool active = grp == 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (i < i_mvc) {
+                const int mx = mvc[i][0], my = mvc[i][1];
+                if ((mx | my) && !(mx == pmx && my == pmy)) {
+                    n++;
+                    if (grp == n) { cx = clip3i(mx, mv_x_min * 4, mv_x_max * 4); cy = clip3i(my, mv_y_min * 4, mv_y_max * 4); active = true; }
+                }
+            }
+        }
+        active = active && on;
+        const int c = cand_qpel<LPS, false>(m, cx, cy, active, false);
+        win_commit();
+        m.win = sm.win; m.wx0 = wx0; m.wy0 = wy0;
+        const int packed = g_min<LPS>(active ? (c << 4) + grp : 0x7fffffff);
+        pmv_cost = g_bcast<LPS>(c, 0);
+        const int best = packed & 7;
+        bpred_cost = packed >> 4;
+        bpred_mx = g_bcast<LPS>(cx, best);
+        bpred_my = g_bcast<LPS>(cy, best);
+        bmx = (bpred_mx + 2) >> 2; bmy = (bpred_my + 2) >> 2;
+        subpel = ((bpred_mx | bpred_my) & 3) != 0;
+        pmv_nz = (pmx | pmy) != 0;
+        need_zero = pmv_nz && (bmx | bmy);
+        if (on) {
+            if (subpel || need_zero) st = S_RZ;              // slot 0: rounded best predictor, slot 1: the zero vector
+            else {
+                bcost = bpred_cost;
+                if (!pmv_nz && pmv_cost < bcost) { bcost = pmv_cost; bmx = 0; bmy = 0; }
+                st = P.me_hex ? S_HEX1 : S_DIA;
+            }
+        }
+    } else {
+        // subme < 3: full-pel predictors; the rounded mvp is scored without its mv cost
+        bmx = pm_fx = clip3i((m.mvp_x + 2) >> 2, mv_x_min, mv_x_max);
+        bmy = pm_fy = clip3i((m.mvp_y + 2) >> 2, mv_y_min, mv_y_max);
+        int wx0, wy0;
+        win_issue(m, sm, g, on, bmx, bmy, wx0, wy0);
+        pcx = bmx; pcy = bmy;
+        int n = 0;
+        pact = grp == 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (i < i_mvc) {
+                const int mx = (mvc[i][0] + 2) >> 2, my = (mvc[i][1] + 2) >> 2;
+                if ((mx | my) && !(mx == pm_fx && my == pm_fy)) {
+                    n++;
+                    if (grp == n) { pcx = clip3i(mx, mv_x_min, mv_x_max); pcy = clip3i(my, mv_y_min, mv_y_max); pact = true; }
+                }
+            }
+        }
+        pmv_nz = (pm_fx | pm_fy) != 0;
+        pzslot = pmv_nz && grp == 7;                     // the zero vector rides along in slot 7
+        if (pzslot) { pcx = 0; pcy = 0; pact = true; }
+        win_commit();
+        m.win = sm.win; m.wx0 = wx0; m.wy0 = wy0;
+        if (on) st = S_PRED;
+    }
+
+    // ---- full-pel rounds: predictors (subme < 3), rounded predictor / zero (subme >= 3),
+    //      hexagon + half hexagons + square refine (X264_ME_HEX) or diamond (X264_ME_DIA) ----
+    int dir = 0, iters = P.me_range;
+    while (__any_sync(FULL, st != S_DONE)) {
+        int mx = 0, my = 0, tag = 0; bool a = false;
+        if (st == S_HEX1) { const int k = min(grp, 5); mx = bmx + c2_hex_first[k][0]; my = bmy + c2_hex_first[k][1]; tag = c2_hex_first[k][2]; a = grp < 6; }
+        else if (st == S_HEXIT) { const int kk = min(grp, 2); mx = bmx + c2_hex2[dir + kk][0]; my = bmy + c2_hex2[dir + kk][1]; tag = kk + 1; a = grp < 3; }
+        else if (st == S_SQUARE) { mx = bmx + c2_square1[grp + 1][0]; my = bmy + c2_square1[grp + 1][1]; tag = grp + 1; a = true; }
+        else if (st == S_DIA) { mx = bmx + (grp == 2 ? -1 : grp == 3 ? 1 : 0); my = bmy + (grp == 0 ? -1 : grp == 1 ? 1 : 0); tag = grp + 1; a = grp < 4; }
+        else if (QPRED && st == S_RZ) { mx = grp == 0 ? bmx : 0; my = grp == 0 ? bmy : 0; a = (grp == 0 && subpel) || (grp == 1 && need_zero); }
+        else if (!QPRED && st == S_PRED) { mx = pcx; my = pcy; tag = grp; a = pact; }
+        int c = cand_fpel(m, mx, my, a);
+        if (!QPRED && st == S_PRED) {
+            if (grp == 0) c -= mvcost2(m, mx * 4, my * 4);
+            a = a && !pzslot;
+        }
+        const int packed = g_min<LPS>(a ? (c << 4) + tag : 0x7fffffff);
+        const int c_s0 = g_bcast<LPS>(c, 0), c_s1 = g_bcast<LPS>(c, 1);
+        int c_s7 = 0, px = 0, py = 0;
+        if (!QPRED) { c_s7 = g_bcast<LPS>(c, 7); px = g_bcast<LPS>(pcx, packed & 7); py = g_bcast<LPS>(pcy, packed & 7); }
+        if (st == S_HEX1) {
+            st = S_SQUARE;
+            if (packed < (bcost << 4)) {
+                bcost = packed >> 4;
+                dir = (packed & 15) - 2;
+                bmx += c2_hex2[dir + 1][0]; bmy += c2_hex2[dir + 1][1];
+                iters = (P.me_range >> 1) - 1;
+                if (iters > 0 && bmx >= mv_x_min && bmx <= mv_x_max && bmy >= mv_y_min && bmy <= mv_y_max) st = S_HEXIT;
+            }
+        } else if (st == S_HEXIT) {
+            if (packed >= (bcost << 4)) st = S_SQUARE;
+            else {
+                bcost = packed >> 4;
+                dir += (packed & 15) - 2;
+                dir = c2_mod6m1[dir + 1];
+                bmx += c2_hex2[dir + 1][0]; bmy += c2_hex2[dir + 1][1];
+                iters--;
+                if (!(iters > 0 && bmx >= mv_x_min && bmx <= mv_x_max && bmy >= mv_y_min && bmy <= mv_y_max)) st = S_SQUARE;
+            }
+        } else if (st == S_SQUARE) {
+            if (packed < (bcost << 4)) {
+                bcost = packed >> 4;
+                bmx += c2_square1[packed & 15][0]; bmy += c2_square1[packed & 15][1];
+            }
+            st = S_DONE;
+        } else if (st == S_DIA) {
+            if ((packed >> 4) >= bcost) st = S_DONE;
+            else {
+                bcost = packed >> 4;
+                const int k = (packed & 15) - 1;
+                bmx += k == 2 ? -1 : k == 3 ? 1 : 0;
+                bmy += k == 0 ? -1 : k == 1 ? 1 : 0;
+                if (!(--iters && bmx >= mv_x_min && bmx <= mv_x_max && bmy >= mv_y_min && bmy <= mv_y_max)) st = S_DONE;
+            }
+        } else if (QPRED && st == S_RZ) {
+            bcost = subpel ? c_s0 : bpred_cost;
+            if (pmv_nz) { if (need_zero && c_s1 < bcost) { bcost = c_s1; bmx = 0; bmy = 0; } }
+            else if (pmv_cost < bcost) { bcost = pmv_cost; bmx = 0; bmy = 0; }
+            st = P.me_hex ? S_HEX1 : S_DIA;
+            iters = P.me_range;
+        } else if (!QPRED && st == S_PRED) {
+            bcost = packed >> 4;
+            bmx = px; bmy = py;
+            if (pmv_nz && c_s7 < bcost) { bcost = c_s7; bmx = 0; bmy = 0; }
+            st = P.me_hex ? S_HEX1 : S_DIA;
+            iters = P.me_range;
+        }
+    }
+
+    int mvx, mvy, cost;
+    if (!QPRED) {
+        cost = bcost;
+        if (on && bmx == pm_fx && bmy == pm_fy) cost += mvcost2(m, bmx * 4, bmy * 4);
+        mvx = bmx * 4; mvy = bmy * 4;
+    } else if (bpred_cost < bcost) { mvx = bpred_mx; mvy = bpred_my; cost = bpred_cost; }
+    else { mvx = bmx * 4; mvy = bmy * 4; cost = bcost; }
+    if (!on) { mvx = 0; mvy = 0; cost = 0; }
+
+    // ---- refine_subpel: hpel_iters = 1; qpel_iters = 1 for subme 4, 0 for subme 2 ----
+    bmx = mvx; bmy = mvy; bcost = cost;
+    if (!QPRED) {
+        const int mx = clip3i(m.mvp_x, min_sx + 2, max_sx - 2), my = clip3i(m.mvp_y, min_sy + 2, max_sy - 2);
+        const bool want = on && (((mx - bmx) | (my - bmy)) != 0);
+        if (__any_sync(FULL, want)) {
+            const int c = g_bcast<LPS>(cand_qpel<LPS, false>(m, mx, my, want && grp == 0, false), 0);
+            if (want && c < bcost) { bcost = c; bmx = mx; bmy = my; }
+        }
+    }
+    sub_load(m, sm, on, bmx >> 2, bmy >> 2);
+    // round 0: half-pel diamond on SAD (slots 0-3); round 1 (mbcmp = SATD only): slot 0 re-scores
+    // the half-pel winner with SATD, slots 1-4 are the quarter-pel diamond
+    const int nrounds = P.satd ? 2 : 1;
+    for (int round = 0; round < nrounds; round++) {
+        int dx, dy; bool a, do_qpel = false;
+        if (round == 0) {
+            dx = grp == 2 ? -2 : grp == 3 ? 2 : 0; dy = grp == 0 ? -2 : grp == 1 ? 2 : 0;
+            a = on && grp < 4;
+        } else {
+            do_qpel = on && P.subpel_refine >= 4 && !(bmy <= min_sy || bmy >= max_sy || bmx <= min_sx || bmx >= max_sx);
+            dx = grp == 3 ? -1 : grp == 4 ? 1 : 0; dy = grp == 1 ? -1 : grp == 2 ? 1 : 0;
+            a = on && (grp == 0 || (do_qpel && grp < 5));
+        }
+        const int c = cand_qpel<LPS, true>(m, bmx + dx, bmy + dy, a, round == 1);
+        const int c_s0 = g_bcast<LPS>(c, 0);
+        if (round == 0) {
+            const int packed = g_min<LPS>(a ? (c << 4) + grp + 1 : 0x7fffffff);
+            if (on && (packed >> 4) < bcost) {
+                bcost = packed >> 4;
+                const int k = (packed & 15) - 1;
+                bmx += k == 2 ? -2 : k == 3 ? 2 : 0;
+                bmy += k == 0 ? -2 : k == 1 ? 2 : 0;
+            }
+        } else {
+            const int packed = g_min<LPS>((do_qpel && grp >= 1 && grp < 5) ? (c << 4) + grp : 0x7fffffff);
+            if (on) bcost = c_s0;
+            if (do_qpel && (packed >> 4) < bcost) {
+                bcost = packed >> 4;
+                const int k = packed & 15;
+                bmx += k == 3 ? -1 : k == 4 ? 1 : 0;
+                bmy += k == 1 ? -1 : k == 2 ? 1 : 0;
+            }
+        }
+    }
+    MeResult2 r = {bmx, bmy, bcost};
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Parallel pass: every MB of the frame is searched at once from ASSUMED neighbour MVs (a guess
+// field for the first pass, the previous pass's results afterwards).  A group of 8*LPS lanes
+// owns one MB, NG horizontally adjacent MBs share a warp.  Each MB records the four inputs it
+// used next to its result; the verification wavefront (la_me_kernel.cu: me_verify_kernel)
+// accepts a result only if those inputs equal the final MVs of the neighbours, and re-runs the
+// search otherwise, so the output is exactly the sequential reverse-raster scan's.
+//   pass 0      : inputs from job.guess (or zeros), all MBs
+//   pass 1, 2.. : inputs from the current results; only MBs whose inputs changed are re-run
+// ------------------------------------------------------------------------------------------
+#define PASS_WARPS 2
+// a guess field of another temporal distance, rescaled (any value is a legal guess)
+__device__ __forceinline__ int scale_mv(int mv, int num, int den, int lim)
+{
+    const float f = (float)num / (float)den;
+    const int sx = __float2int_rn((float)mv_x(mv) * f), sy = __float2int_rn((float)mv_y(mv) * f);
+    return mv_pack(clip3i(sx, -lim, lim - 1), clip3i(sy, -lim, lim - 1));     // stay inside the mv cost table
+}
+template <int LPS, bool QPRED>
+__global__ void __launch_bounds__(32 * PASS_WARPS)
+me_pass_kernel(LaGeom g, MeParams P, int pass)
+{
+    constexpr int GL = Mb<LPS>::GL, NG = 32 / GL, RPL = Mb<LPS>::RPL;
+    __shared__ GroupSmem sm_all[PASS_WARPS][NG];
+    const MeJob &job = P.job[blockIdx.y];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gi = lane / GL;
+    GroupSmem &sm = sm_all[warp][gi];
+    const int T = max(1, P.bands);
+    const int start_x = g.mb_w - 2 + P.do_edges, end_x = 1 - P.do_edges;
+    const int ncols = start_x - end_x + 1;
+    const int chunks = (ncols + NG - 1) / NG;
+    const int wid = blockIdx.x * PASS_WARPS + warp;
+    if (wid >= chunks * g.mb_h) return;
+    const int mb_y = wid / chunks, k = (wid - mb_y * chunks) * NG + gi;
+    const int mb_x = start_x - k;
+
+    int slice_start = 0, slice_end = g.mb_h;
+#pragma unroll 1
+    for (int i = 0; i < T; i++) {
+        const int s = (g.mb_h * i + T / 2) / T, e = (g.mb_h * (i + 1) + T / 2) / T;
+        if (mb_y >= s && mb_y < e) { slice_start = s; slice_end = e; }
+    }
+    const int start_y = min(slice_end - 1, g.mb_h - 2 + P.do_edges), end_y = max(slice_start, 1 - P.do_edges);
+    const bool act = mb_y <= start_y && mb_y >= end_y && k < ncols;
+    const bool has_below = mb_y < slice_end - 1;
+    const int mb_xy = mb_x + mb_y * g.mb_w;
+
+    // ---- the four inputs (zero where the neighbour does not exist) ----
+    const bool has_r = mb_x < g.mb_w - 1, has_bl = has_below && mb_x > 0, has_br = has_below && has_r;
+    int4 in = make_int4(0, 0, 0, 0);           // right, below, below-left, below-right
+    const int *src = pass == 0 ? job.guess : job.mvs;
+    if (act && src) {
+        if (has_r) in.x = __ldcg(src + mb_xy + 1);
+        if (has_below) in.y = __ldcg(src + mb_xy + g.mb_w);
+        if (has_bl) in.z = __ldcg(src + mb_xy + g.mb_w - 1);
+        if (has_br) in.w = __ldcg(src + mb_xy + g.mb_w + 1);
+        if (pass == 0 && job.guess_num != job.guess_den) {
+            in.x = scale_mv(in.x, job.guess_num, job.guess_den, P.mv_range2); in.y = scale_mv(in.y, job.guess_num, job.guess_den, P.mv_range2);
+            in.z = scale_mv(in.z, job.guess_num, job.guess_den, P.mv_range2); in.w = scale_mv(in.w, job.guess_num, job.guess_den, P.mv_range2);
+        }
+    }
+    bool need = act;
+    if (pass > 0 && act) {
+        const int4 a = __ldcg(job.assumed + mb_xy);
+        need = a.x != in.x || a.y != in.y || a.z != in.z || a.w != in.w;
+    }
+    if (!__any_sync(FULL, need)) return;
+
+    Mb<LPS> m;
+    m.gl = lane % GL; m.slot = m.gl / LPS; m.r0 = (m.gl % LPS) * RPL;
+    m.stride = g.lstride;
+    m.fref0 = job.fref[0]; m.plane_stride = g.lplane;
+    m.fref_w = job.fref_w; m.w = job.w; m.cost_mv = P.cost_mv;
+    m.win = nullptr; m.sub = nullptr;
+    m.wx0 = m.wy0 = m.sx0 = m.sy0 = 0;
+    m.pel = 8 * (mb_x + mb_y * g.lstride);
+    m.px = 8 * mb_x; m.py = 8 * mb_y;
+#pragma unroll
+    for (int r = 0; r < RPL; r++) m.fe[r] = make_uint2(0, 0);
+    if (need) {
+#pragma unroll
+        for (int r = 0; r < RPL; r++) m.fe[r] = __ldg((const uint2 *)(job.fenc + m.pel + (m.r0 + r) * g.lstride));
+    }
+
+    // ---- reverse-order MV prediction, as in the sequential scan ----
+    int c0, c1, c2, c3, i_mvc;
+    if (has_below) {
+        c0 = has_r ? in.x : in.y;
+        c1 = has_r ? in.y : (has_bl ? in.z : 0);
+        c2 = has_r ? (has_bl ? in.z : in.w) : 0;
+        c3 = (has_r && has_bl) ? in.w : 0;
+        i_mvc = (int)has_r + 1 + (int)has_bl + (int)has_br;
+    } else {
+        c0 = has_r ? in.x : 0; c1 = c2 = c3 = 0;
+        i_mvc = (int)has_r;
+    }
+    if (!need) { c0 = c1 = c2 = c3 = 0; i_mvc = 0; }
+    const int mvc[4][2] = {{mv_x(c0), mv_y(c0)}, {mv_x(c1), mv_y(c1)}, {mv_x(c2), mv_y(c2)}, {mv_x(c3), mv_y(c3)}};
+    if (i_mvc <= 1) { m.mvp_x = mvc[0][0]; m.mvp_y = mvc[0][1]; }
+    else { m.mvp_x = median3i(mvc[0][0], mvc[1][0], mvc[2][0]); m.mvp_y = median3i(mvc[0][1], mvc[1][1], mvc[2][1]); }
+
+    int min_sx, max_sx, min_sy, max_sy;
+    mv_limits(mb_x, mb_y, g.mb_w, g.mb_h, P.mv_range2, min_sx, max_sx, min_sy, max_sy);
+
+    int out_mv = 0, out_cost = 0;
+    bool skip = false;
+    const bool ztest = need && !(m.mvp_x | m.mvp_y);
+    if (__any_sync(FULL, ztest)) {
+        // fast skip: mbcmp at mv 0 on the UNWEIGHTED plane 0 (every lane scores its rows)
+        uint2 a[RPL];
+#pragma unroll
+        for (int r = 0; r < RPL; r++) a[r] = make_uint2(0, 0);
+        if (ztest) {
+#pragma unroll
+            for (int r = 0; r < RPL; r++) a[r] = __ldg((const uint2 *)(job.fref[0] + m.pel + (m.r0 + r) * g.lstride));
+        }
+        const int c = P.satd ? satd_rows(m, a) : part_sum<LPS>(sad_rows(m, a));
+        if (ztest && c < 64) { skip = true; out_mv = 0; out_cost = c; }
+    }
+    const bool on = need && !skip;
+    if (__any_sync(FULL, on)) {
+        MeResult2 r = me_search_mb2<LPS, QPRED>(m, sm, g, P, on, mvc, i_mvc, min_sx, max_sx, min_sy, max_sy);
+        if (on) {
+            int cost = r.cost - (int)__ldg(P.cost_mv);      // remove mvcost from skip mbs
+            if (r.mvx | r.mvy) cost += 5;
+            out_mv = mv_pack(r.mvx, r.mvy); out_cost = cost;
+        }
+    }
+    if (need && m.gl == 0) {
+        job.mvs[mb_xy] = out_mv;
+        job.mv_costs[mb_xy] = out_cost;
+        job.assumed[mb_xy] = in;
+        if (P.stats) atomicAdd(P.stats + 2 + min(pass, 3), 1);
+    }
+}
+
+int launch_me_pass(cudaStream_t st, const LaGeom &g, const MeParams &p, int pass)
+{
+    const int start_x = g.mb_w - 2 + p.do_edges, end_x = 1 - p.do_edges;
+    const int ncols = start_x - end_x + 1;
+    const int chunks = (ncols + 3) / 4;
+    const int warps = chunks * g.mb_h;
+    const dim3 grid((warps + PASS_WARPS - 1) / PASS_WARPS, p.njobs);
+    if (p.subpel_refine >= 3) me_pass_kernel<1, true><<<grid, 32 * PASS_WARPS, 0, st>>>(g, p, pass);
+    else me_pass_kernel<1, false><<<grid, 32 * PASS_WARPS, 0, st>>>(g, p, pass);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace xv

@@ -57,7 +57,7 @@ lib.x264vfw_cuda_la_counters.argtypes = [C.c_void_p, _P(C.c_uint64)]
 
 lib.x264vfw_cuda_la_profile.restype = C.c_int
 lib.x264vfw_cuda_la_profile.argtypes = [C.c_void_p, C.c_int, _P(C.c_double), _P(C.c_uint64)]
-KERNEL_CLASSES = ("csp", "aq", "lowres", "intra", "me", "finalize", "weights", "mbtree")
+KERNEL_CLASSES = ("csp", "aq", "lowres", "intra", "me", "finalize", "weights", "mbtree", "me_pass")
 
 
 def params_preset(preset: str, width: int, height: int, **over) -> LaParams:
@@ -190,7 +190,7 @@ class Lookahead:
 
     def profile(self, enable: int = -1):
         """Per-kernel-class device time (ms) and launch counts since the last reset."""
-        ms, n = (C.c_double * 8)(), (C.c_uint64 * 8)()
+        ms, n = (C.c_double * 16)(), (C.c_uint64 * 16)()
         if lib.x264vfw_cuda_la_profile(self.h, enable, ms, n) < 0:
             raise CudaError(last_error())
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
