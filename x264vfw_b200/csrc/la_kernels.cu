@@ -47,13 +47,13 @@ __device__ __forceinline__ int dev_exp2fix8(const uint8_t *lut, float x)
     return (lut[i & 63] + 256) << (i >> 6) >> 8;
 }
 
-__device__ __forceinline__ uint32_t block_var_dev(const uint8_t *p, int stride, int pw, int ph, int x0, int y0,
-                                                  int bw, int bh, int shift, unsigned long long &fsum,
-                                                  unsigned long long &fssd)
+// sum and sum of squares of rows [ya, yb) of the bw x bh block at (x0, y0)
+__device__ __forceinline__ void block_sums_dev(const uint8_t *p, int stride, int pw, int ph, int x0, int y0,
+                                               int bw, int ya, int yb, uint32_t &sum, uint32_t &ssd)
 {
-    uint32_t sum = 0, ssd = 0;
+    sum = 0; ssd = 0;
     const bool fast = (x0 + bw <= pw) && (((uintptr_t)p | (unsigned)stride) & 15) == 0 && (x0 & 15) == 0 && (bw & 7) == 0;
-    for (int y = 0; y < bh; y++) {
+    for (int y = ya; y < yb; y++) {
         const uint8_t *r = p + (size_t)min(y0 + y, ph - 1) * stride;
         if (fast) {
             for (int x = 0; x < bw; x += 8) {
@@ -65,24 +65,44 @@ __device__ __forceinline__ uint32_t block_var_dev(const uint8_t *p, int stride, 
             for (int x = 0; x < bw; x++) { uint32_t v = r[min(x0 + x, pw - 1)]; sum += v; ssd += v * v; }
         }
     }
-    fsum += sum; fssd += ssd;
-    return ssd - (uint32_t)(((unsigned long long)sum * sum) >> shift);
 }
 
-__global__ void __launch_bounds__(128)
+// A block = 32 consecutive MBs x AQ_PARTS row slices: warp `part` sums rows
+// [part*bh/AQ_PARTS, ...) of every plane block of its 32 MBs (512 contiguous bytes per luma
+// row), the slices meet in shared memory (integer sums: order-free), warp 0 finishes the MB.
+#define AQ_PARTS 8
+__global__ void __launch_bounds__(32 * AQ_PARTS)
 aq_kernel(LaGeom g, AqJob job)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long st[6] = {0, 0, 0, 0, 0, 0};
+    __shared__ uint32_t sh[3][2][AQ_PARTS][32];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 32 + lane;
+    const int w = g.width, h = g.height, cf = job.chroma_format;
+    const int cw = cf == 3 ? w : w / 2, ch = cf == 1 ? h / 2 : h;
+    const int cbw = cf == 3 ? 16 : 8, cbh = cf == 1 ? 8 : 16, cshift = cf == 3 ? 8 : cf == 2 ? 7 : 6;
+    uint32_t s[3] = {0, 0, 0}, q[3] = {0, 0, 0};
     if (idx < g.mb_count) {
         const int mx = idx % g.mb_w, my = idx / g.mb_w;
-        const int w = g.width, h = g.height, cf = job.chroma_format;
-        uint32_t energy = block_var_dev(job.y, job.y_stride, w, h, 16 * mx, 16 * my, 16, 16, 8, st[0], st[3]);
+        block_sums_dev(job.y, job.y_stride, w, h, 16 * mx, 16 * my, 16, part * 16 / AQ_PARTS, (part + 1) * 16 / AQ_PARTS, s[0], q[0]);
         if (cf) {
-            const int cw = cf == 3 ? w : w / 2, ch = cf == 1 ? h / 2 : h;
-            const int cbw = cf == 3 ? 16 : 8, cbh = cf == 1 ? 8 : 16, cshift = cf == 3 ? 8 : cf == 2 ? 7 : 6;
-            energy += block_var_dev(job.u, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, cbh, cshift, st[1], st[4]);
-            energy += block_var_dev(job.v, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, cbh, cshift, st[2], st[5]);
+            block_sums_dev(job.u, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, part * cbh / AQ_PARTS, (part + 1) * cbh / AQ_PARTS, s[1], q[1]);
+            block_sums_dev(job.v, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, part * cbh / AQ_PARTS, (part + 1) * cbh / AQ_PARTS, s[2], q[2]);
+        }
+    }
+#pragma unroll
+    for (int pl = 0; pl < 3; pl++) { sh[pl][0][part][lane] = s[pl]; sh[pl][1][part][lane] = q[pl]; }
+    __syncthreads();
+    if (part) return;
+    unsigned long long st[6] = {0, 0, 0, 0, 0, 0};
+    if (idx < g.mb_count) {
+        uint32_t energy = 0;
+#pragma unroll
+        for (int pl = 0; pl < 3; pl++) {
+            uint32_t sum = 0, ssd = 0;
+#pragma unroll
+            for (int k = 0; k < AQ_PARTS; k++) { sum += sh[pl][0][k][lane]; ssd += sh[pl][1][k][lane]; }
+            st[pl] = sum; st[3 + pl] = ssd;
+            if (pl == 0 || cf) energy += ssd - (uint32_t)(((unsigned long long)sum * sum) >> (pl ? cshift : 8));
         }
         if (job.aq_on) {
             float qp_adj = job.strength * (dev_log2(job.log2_lut, max(energy, 1u)) - (14.427f + 2 * 0));
@@ -95,14 +115,14 @@ aq_kernel(LaGeom g, AqJob job)
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        unsigned long long s = warp_sum64(st[i]);
-        if ((threadIdx.x & 31) == 0 && s) atomicAdd(job.stats + i, s);
+        unsigned long long t = warp_sum64(st[i]);
+        if (lane == 0 && t) atomicAdd(job.stats + i, t);
     }
 }
 
 int launch_aq(cudaStream_t st, const LaGeom &g, const AqJob &job)
 {
-    aq_kernel<<<(g.mb_count + 127) / 128, 128, 0, st>>>(g, job);
+    aq_kernel<<<(g.mb_count + 31) / 32, 32 * AQ_PARTS, 0, st>>>(g, job);
     XV_LAUNCH_CHECK();
     return 0;
 }
@@ -170,9 +190,8 @@ __device__ __forceinline__ int pred8x8_px(const Edge &e, int x, int y)
 #undef EL
 
 template <int MODE>
-__device__ __forceinline__ int pred8x8_cost(const Edge &e, const uint2 src[8], int satd)
+__device__ __forceinline__ void pred8x8_build(const Edge &e, uint2 pr[8])
 {
-    uint2 pr[8];
 #pragma unroll
     for (int y = 0; y < 8; y++) {
         uint32_t lo = 0, hi = 0;
@@ -183,7 +202,6 @@ __device__ __forceinline__ int pred8x8_cost(const Edge &e, const uint2 src[8], i
         }
         pr[y] = make_uint2(lo, hi);
     }
-    return mbcmp_rows(satd, src, pr);
 }
 
 __global__ void __launch_bounds__(64)
@@ -205,30 +223,37 @@ intra_kernel(LaGeom g, IntraJob job, int do_edges)
 #pragma unroll
         for (int i = 0; i < 8; i++) { n.top[i] = px_of(t0, i); n.top[8 + i] = px_of(t1, i); }
     }
-    uint2 pr[8];
-    int best;
-    {   // predict_8x8c_dc
-        int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    Edge e;
+    if (job.full) filter_edges_dev(e, n);
+    // One loop over the modes around ONE copy of the block metric: the SATD butterflies are
+    // most of this kernel's code, and ten inlined copies made it 111 KB of SASS (instruction
+    // cache pressure on everything that runs beside it).
+    int best = 1 << 30;
+    const int nmodes = job.full ? 10 : 3;
+#pragma unroll 1
+    for (int mode = 0; mode < nmodes; mode++) {
+        uint2 pr[8];
+        switch (mode) {
+        case 0: {   // predict_8x8c_dc
+            int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { s0 += n.top[i]; s1 += n.top[i + 4]; s2 += n.left[i]; s3 += n.left[i + 4]; }
-        uint32_t d0 = splat4((s0 + s2 + 4) >> 3), d1 = splat4((s1 + 2) >> 2), d2 = splat4((s3 + 2) >> 2), d3 = splat4((s1 + s3 + 4) >> 3);
+            for (int i = 0; i < 4; i++) { s0 += n.top[i]; s1 += n.top[i + 4]; s2 += n.left[i]; s3 += n.left[i + 4]; }
+            uint32_t d0 = splat4((s0 + s2 + 4) >> 3), d1 = splat4((s1 + 2) >> 2), d2 = splat4((s3 + 2) >> 2), d3 = splat4((s1 + s3 + 4) >> 3);
 #pragma unroll
-        for (int y = 0; y < 8; y++) pr[y] = y < 4 ? make_uint2(d0, d1) : make_uint2(d2, d3);
-        best = mbcmp_rows(job.satd, pr, s);
-    }
-    {   // predict_8x8c_h
+            for (int y = 0; y < 8; y++) pr[y] = y < 4 ? make_uint2(d0, d1) : make_uint2(d2, d3);
+            break;
+        }
+        case 1:     // predict_8x8c_h
 #pragma unroll
-        for (int y = 0; y < 8; y++) pr[y] = make_uint2(splat4(n.left[y]), splat4(n.left[y]));
-        best = min(best, mbcmp_rows(job.satd, pr, s));
-    }
-    {   // predict_8x8c_v
-        uint2 t = load8u(src - stride);
+            for (int y = 0; y < 8; y++) pr[y] = make_uint2(splat4(n.left[y]), splat4(n.left[y]));
+            break;
+        case 2: {   // predict_8x8c_v
+            uint2 t = load8u(src - stride);
 #pragma unroll
-        for (int y = 0; y < 8; y++) pr[y] = t;
-        best = min(best, mbcmp_rows(job.satd, pr, s));
-    }
-    if (job.full) {
-        {   // predict_8x8c_p
+            for (int y = 0; y < 8; y++) pr[y] = t;
+            break;
+        }
+        case 3: {   // predict_8x8c_p
             int H = 0, V = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -250,16 +275,16 @@ intra_kernel(LaGeom g, IntraJob job, int do_edges)
                 }
                 pr[y] = make_uint2(lo, hi);
             }
-            best = min(best, mbcmp_rows(job.satd, s, pr));
+            break;
         }
-        Edge e;
-        filter_edges_dev(e, n);
-        best = min(best, pred8x8_cost<3>(e, s, job.satd));
-        best = min(best, pred8x8_cost<4>(e, s, job.satd));
-        best = min(best, pred8x8_cost<5>(e, s, job.satd));
-        best = min(best, pred8x8_cost<6>(e, s, job.satd));
-        best = min(best, pred8x8_cost<7>(e, s, job.satd));
-        best = min(best, pred8x8_cost<8>(e, s, job.satd));
+        case 4: pred8x8_build<3>(e, pr); break;
+        case 5: pred8x8_build<4>(e, pr); break;
+        case 6: pred8x8_build<5>(e, pr); break;
+        case 7: pred8x8_build<6>(e, pr); break;
+        case 8: pred8x8_build<7>(e, pr); break;
+        default: pred8x8_build<8>(e, pr); break;
+        }
+        best = min(best, mbcmp_rows(job.satd, s, pr));
     }
     job.intra_cost[idx] = (uint16_t)(best + 5 + 4);      // + intra_penalty (5*lambda) + lowres_penalty
 }
@@ -361,44 +386,36 @@ finalize_kernel(LaGeom g, FinalizeJob job)
                     d1x = clip3i(d1x, min_x, max_x); d1y = clip3i(d1y, min_y, max_y);
                     if (!job.subme_gt1) { d0x &= ~1; d0y &= ~1; d1x &= ~1; d1y &= ~1; }
                 }
-                // TRY_BIDIR(dmv[0], dmv[1], 0)
-                if (job.subme_gt1) {
-                    fetch_ref8(ra, job.fref0, stride, pel, d0x, d0y, w0);
-                    fetch_ref8(rb, job.fref1, stride, pel, d1x, d1y, w0);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 8; r++) {
-                        ra[r] = load8u(job.fref0[((d0x & 2) >> 1) + (d0y & 2)] + pel + ((d0y >> 2) + r) * stride + (d0x >> 2));
-                        rb[r] = load8u(job.fref1[((d1x & 2) >> 1) + (d1y & 2)] + pel + ((d1y >> 2) + r) * stride + (d1x >> 2));
-                    }
-                }
-                int c = bidir_cost(fenc, ra, rb, job.bipred_weight, job.satd);
-                if (c < bcost) { bcost = c; list_used = 3; }
-                if (d0x | d0y | d1x | d1y) {
-#pragma unroll
-                    for (int r = 0; r < 8; r++) { ra[r] = load8u(job.fref0[0] + pel + r * stride); rb[r] = load8u(job.fref1[0] + pel + r * stride); }
-                    c = bidir_cost(fenc, ra, rb, job.bipred_weight, job.satd);
-                    if (c < bcost) { bcost = c; list_used = 3; }
-                }
                 mv0 = job.mvs0[idx]; mv1 = job.mvs1[idx];
-                const int c0 = job.mv_costs0[idx], c1 = job.mv_costs1[idx];
-                if (c0 < bcost) { bcost = c0; list_used = 1; }
-                if (c1 < bcost) { bcost = c1; list_used = 2; }
-                if (mv0 | mv1) {
-                    // TRY_BIDIR(m[0].mv, m[1].mv, 5)
-                    if (job.subme_gt1) {
-                        fetch_ref8(ra, job.fref0, stride, pel, mv_x(mv0), mv_y(mv0), w0);
-                        fetch_ref8(rb, job.fref1, stride, pel, mv_x(mv1), mv_y(mv1), w0);
-                    } else {
-                        const int ax = mv_x(mv0), ay = mv_y(mv0), bx = mv_x(mv1), by = mv_y(mv1);
+                // Three bidirectional candidates around ONE copy of the fetch + average + metric
+                // code (code size): k=0 TRY_BIDIR(dmv[0], dmv[1], 0); k=1 the zero vectors, if the
+                // direct vectors were not zero; then the two list costs; k=2 TRY_BIDIR(m[0].mv,
+                // m[1].mv, 5) if either is non-zero.  Same comparison order as upstream.
+#pragma unroll 1
+                for (int k = 0; k < 3; k++) {
+                    int ax, ay, bx, by, pen; bool en;
+                    if (k == 0) { ax = d0x; ay = d0y; bx = d1x; by = d1y; pen = 0; en = true; }
+                    else if (k == 1) { ax = ay = bx = by = 0; pen = 0; en = (d0x | d0y | d1x | d1y) != 0; }
+                    else { ax = mv_x(mv0); ay = mv_y(mv0); bx = mv_x(mv1); by = mv_y(mv1); pen = 5; en = (mv0 | mv1) != 0; }
+                    if (en) {
+                        if (job.subme_gt1) {
+                            fetch_ref8(ra, job.fref0, stride, pel, ax, ay, w0);
+                            fetch_ref8(rb, job.fref1, stride, pel, bx, by, w0);
+                        } else {
 #pragma unroll
-                        for (int r = 0; r < 8; r++) {
-                            ra[r] = load8u(job.fref0[((ax & 2) >> 1) + (ay & 2)] + pel + ((ay >> 2) + r) * stride + (ax >> 2));
-                            rb[r] = load8u(job.fref1[((bx & 2) >> 1) + (by & 2)] + pel + ((by >> 2) + r) * stride + (bx >> 2));
+                            for (int r = 0; r < 8; r++) {
+                                ra[r] = load8u(job.fref0[((ax & 2) >> 1) + (ay & 2)] + pel + ((ay >> 2) + r) * stride + (ax >> 2));
+                                rb[r] = load8u(job.fref1[((bx & 2) >> 1) + (by & 2)] + pel + ((by >> 2) + r) * stride + (bx >> 2));
+                            }
                         }
+                        const int c = pen + bidir_cost(fenc, ra, rb, job.bipred_weight, job.satd);
+                        if (c < bcost) { bcost = c; list_used = 3; }
                     }
-                    c = 5 + bidir_cost(fenc, ra, rb, job.bipred_weight, job.satd);
-                    if (c < bcost) { bcost = c; list_used = 3; }
+                    if (k == 1) {
+                        const int c0 = job.mv_costs0[idx], c1 = job.mv_costs1[idx];
+                        if (c0 < bcost) { bcost = c0; list_used = 1; }
+                        if (c1 < bcost) { bcost = c1; list_used = 2; }
+                    }
                 }
             } else if (job.mv_costs0) {
                 const int c0 = job.mv_costs0[idx];

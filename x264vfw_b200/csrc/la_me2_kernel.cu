@@ -29,9 +29,13 @@ namespace xv {
 #define SUB_W 32
 #define SUB_H 12
 
+// The sub-pel windows reuse the full-pel window's storage (the full-pel rounds are over by
+// then): 2.5 KB per MB in flight, so shared memory allows 20 warps per SM.
 struct __align__(16) GroupSmem {
-    uint8_t win[WIN_H * WIN_W];       // full-pel window of the (weighted) plane 0
-    uint8_t sub[4][SUB_H * SUB_W];    // sub-pel windows of the four phase planes
+    union {
+        uint8_t win[WIN_H * WIN_W];       // full-pel window of the (weighted) plane 0
+        uint8_t sub[4][SUB_H * SUB_W];    // sub-pel windows of the four phase planes
+    };
 };
 
 __device__ __forceinline__ uint2 ld_rec2(const int2 *p)
@@ -88,7 +92,8 @@ template <int LPS> __device__ __forceinline__ int g_min(int v)
 }
 template <int LPS> __device__ __forceinline__ int part_sum(int v)
 {
-    if (LPS == 2) v += __shfl_xor_sync(FULL, v, 1);
+    if (LPS >= 2) v += __shfl_xor_sync(FULL, v, 1);
+    if (LPS >= 4) v += __shfl_xor_sync(FULL, v, 2);
     return v;
 }
 template <int LPS> __device__ __forceinline__ int mvcost2(const Mb<LPS> &m, int qx, int qy)
@@ -119,8 +124,49 @@ __device__ __forceinline__ int satd_8x4_regs(const uint2 *a, const uint2 *b)
     }
     return sum >> 1;
 }
+// LPS = 4: a lane holds two rows.  Rows 0-3 live in lane parts 0,1 and rows 4-7 in parts 2,3:
+// each lane pair forms one 8x4 (horizontal butterflies in the lane, vertical ones across the
+// pair with packed 16-bit shuffles), the two halves add.
+__device__ __forceinline__ int satd_rows4(uint2 fe0, uint2 fe1, uint2 a0, uint2 a1, bool odd)
+{
+    int s[8], d[8];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t f0 = half ? fe0.y : fe0.x, f1 = half ? fe1.y : fe1.x;
+        const uint32_t r0 = half ? a0.y : a0.x, r1 = half ? a1.y : a1.x;
+        int t0[4], t1[4];
+        {
+            int e0 = (int)(f0 & 0xff) - (int)(r0 & 0xff), e1 = (int)((f0 >> 8) & 0xff) - (int)((r0 >> 8) & 0xff);
+            int e2 = (int)((f0 >> 16) & 0xff) - (int)((r0 >> 16) & 0xff), e3 = (int)(f0 >> 24) - (int)(r0 >> 24);
+            int s01 = e0 + e1, d01 = e0 - e1, s23 = e2 + e3, d23 = e2 - e3;
+            t0[0] = s01 + s23; t0[1] = s01 - s23; t0[2] = d01 + d23; t0[3] = d01 - d23;
+        }
+        {
+            int e0 = (int)(f1 & 0xff) - (int)(r1 & 0xff), e1 = (int)((f1 >> 8) & 0xff) - (int)((r1 >> 8) & 0xff);
+            int e2 = (int)((f1 >> 16) & 0xff) - (int)((r1 >> 16) & 0xff), e3 = (int)(f1 >> 24) - (int)(r1 >> 24);
+            int s01 = e0 + e1, d01 = e0 - e1, s23 = e2 + e3, d23 = e2 - e3;
+            t1[0] = s01 + s23; t1[1] = s01 - s23; t1[2] = d01 + d23; t1[3] = d01 - d23;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { s[half * 4 + k] = t0[k] + t1[k]; d[half * 4 + k] = t0[k] - t1[k]; }
+    }
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int mine = (s[k] & 0xffff) | (d[k] << 16);
+        const int other = __shfl_xor_sync(FULL, mine, 1);
+        const int so = (int)(short)(other & 0xffff), dd = other >> 16;
+        sum += odd ? abs(so - s[k]) + abs(dd - d[k]) : abs(s[k] + so) + abs(d[k] + dd);
+    }
+    sum += __shfl_xor_sync(FULL, sum, 1);     // 8x4 total in both lanes of the pair
+    sum >>= 1;
+    sum += __shfl_xor_sync(FULL, sum, 2);     // + the other 8x4
+    return sum;
+}
+
 template <int LPS> __device__ __forceinline__ int satd_rows(const Mb<LPS> &m, const uint2 *a)
 {
+    if (LPS == 4) return satd_rows4(m.fe[0], m.fe[1 % Mb<LPS>::RPL], a[0], a[1 % Mb<LPS>::RPL], m.gl & 1);
     if (LPS == 1) {
         // two 8x4 halves through ONE copy of the butterfly code (rows 4-7 are moved down for
         // the second trip): code size matters more than 16 register moves here
@@ -284,6 +330,7 @@ __device__ __forceinline__ void sub_load(Mb<LPS> &m, GroupSmem &sm, bool on, int
     constexpr int GL = Mb<LPS>::GL;
     m.sx0 = (m.px + fx - 1) & ~15;
     m.sy0 = m.py + fy - 1;
+    m.win = nullptr;                                     // its storage is about to be overwritten
     __syncwarp();
     if (on) {
         // per plane 24 chunks = 12 rows x 2 halves: lane gl copies (row, half) = (gl/2 + (GL/2) j, gl%2)
@@ -294,8 +341,8 @@ __device__ __forceinline__ void sub_load(Mb<LPS> &m, GroupSmem &sm, bool on, int
         for (int pl = 0; pl < 4; pl++) {
             const uint8_t *s2 = src; uint8_t *d2 = dst;
 #pragma unroll
-            for (int j = 0; j < 24 / GL; j++) {
-                cpa16(d2, s2);
+            for (int j = 0; j < (24 + GL - 1) / GL; j++) {
+                if (GL * j + m.gl < 24) cpa16(d2, s2);
                 s2 += sstep; d2 += (GL / 2) * SUB_W;
             }
             src += m.plane_stride; dst += SUB_H * SUB_W;
@@ -543,7 +590,7 @@ __device__ __forceinline__ int scale_mv(int mv, int num, int den, int lim)
     return mv_pack(clip3i(sx, -lim, lim - 1), clip3i(sy, -lim, lim - 1));     // stay inside the mv cost table
 }
 template <int LPS, bool QPRED>
-__global__ void __launch_bounds__(32 * PASS_WARPS)
+__global__ void __launch_bounds__(32 * PASS_WARPS, 10)
 me_pass_kernel(LaGeom g, MeParams P, int pass)
 {
     constexpr int GL = Mb<LPS>::GL, NG = 32 / GL, RPL = Mb<LPS>::RPL;
@@ -670,6 +717,200 @@ int launch_me_pass(cudaStream_t st, const LaGeom &g, const MeParams &p, int pass
     const dim3 grid((warps + PASS_WARPS - 1) / PASS_WARPS, p.njobs);
     if (p.subpel_refine >= 3) me_pass_kernel<1, true><<<grid, 32 * PASS_WARPS, 0, st>>>(g, p, pass);
     else me_pass_kernel<1, false><<<grid, 32 * PASS_WARPS, 0, st>>>(g, p, pass);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Verification wavefront: the exact, ordered half of the speculative search (see
+// la_me2_kernel.cu).  Every MB already holds a result G and the four neighbour MVs A it was
+// computed from.  Rows are walked in dependency order exactly like me_wavefront_kernel, but an
+// MB whose assumed inputs equal the FINAL MVs of its neighbours is simply kept -- and runs of
+// such MBs retire 32 at a time: lane i looks at MB x-i, polls the one new record it needs
+// from the row below, takes its right neighbour's tentative G from lane i-1, and the leading
+// run of matching lanes is final by induction.  Only a mismatching MB pays for a search (the
+// whole warp, 8 candidates x 4 lanes: the same search code as the passes, instantiated with
+// 4 lanes per candidate), with its true inputs.
+// ------------------------------------------------------------------------------------------
+#define VERIFY_WARPS 2
+template <bool QPRED>
+__global__ void __launch_bounds__(32 * VERIFY_WARPS, 8)
+me_verify_kernel(LaGeom g, MeParams P)
+{
+    __shared__ GroupSmem sm_all[VERIFY_WARPS];
+    GroupSmem &sm = sm_all[threadIdx.x >> 5];
+    const MeJob &job = P.job[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const unsigned FULLM = 0xffffffffu;
+  for (;;) {
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(job.ticket, 1);
+    ticket = __shfl_sync(FULLM, ticket, 0);
+    const int mb_y = g.mb_h - 1 - ticket;                 // bottom rows start first
+    if (mb_y < 0) return;
+    const int T = max(1, P.bands);
+    int slice_start = 0, slice_end = g.mb_h;
+    for (int i = 0; i < T; i++) {
+        const int s = (g.mb_h * i + T / 2) / T, e = (g.mb_h * (i + 1) + T / 2) / T;
+        if (mb_y >= s && mb_y < e) { slice_start = s; slice_end = e; }
+    }
+    const int start_y = min(slice_end - 1, g.mb_h - 2 + P.do_edges), end_y = max(slice_start, 1 - P.do_edges);
+    const int start_x = g.mb_w - 2 + P.do_edges, end_x = 1 - P.do_edges;
+    if (mb_y > start_y || mb_y < end_y) continue;          // row not scanned (edges without do_edges)
+    const bool has_below = mb_y < slice_end - 1;
+    const bool below_scanned = has_below && (mb_y + 1 <= start_y);
+    const int epoch = P.epoch;
+    const int2 *below = job.rec + (mb_y + 1) * g.mb_w;
+    int2 *mine = job.rec + mb_y * g.mb_w;
+    const int row0 = mb_y * g.mb_w;
+
+    Mb<4> m;                                               // the whole warp on one MB: 8 candidates x 4 lanes
+    m.gl = lane; m.slot = lane >> 2; m.r0 = (lane & 3) * 2;
+    m.stride = g.lstride;
+    m.fref0 = job.fref[0]; m.plane_stride = g.lplane;
+    m.fref_w = job.fref_w; m.w = job.w; m.cost_mv = P.cost_mv;
+    m.win = nullptr; m.sub = nullptr;
+    m.wx0 = m.wy0 = m.sx0 = m.sy0 = 0;
+
+    // below-row value at column p that needs no record: position absent or never scanned
+    auto below_fixed = [&](int p) -> bool { return !below_scanned || p < end_x || p > start_x || p < 0 || p >= g.mb_w; };
+    auto below_wait = [&](int p) -> int {
+        if (below_fixed(p)) return 0;
+        uint2 r = ld_rec2(below + p);
+        unsigned ns = 32;
+        while ((int)r.y != epoch) { __nanosleep(ns); if (ns < 512) ns <<= 1; r = ld_rec2(below + p); }
+        return (int)r.x;
+    };
+
+    int x = start_x;                // next MB of this row
+    int right_mv = 0;               // final MV of (x+1, y); zero before the first MB
+    int c0 = 0, c1 = 0;             // final MVs of the row below at columns x and x+1
+    if (has_below) { c1 = below_wait(start_x + 1); c0 = below_wait(start_x); }
+    int n_hit = 0, n_miss = 0;
+    unsigned ns = 32;
+    while (x >= end_x) {
+        // ---- load a chunk: lane i examines MB xi = x - i ----
+        const int xi = x - lane;
+        const bool valid = xi >= end_x;
+        int bl = 0; bool rdy = true;                       // row below at column xi-1
+        if (valid && has_below && !below_fixed(xi - 1)) {
+            const uint2 r = ld_rec2(below + xi - 1);
+            rdy = (int)r.y == epoch; bl = (int)r.x;
+        }
+        int4 A = make_int4(0, 0, 0, 0); int G = 0;
+        if (valid) { A = __ldcg(job.assumed + row0 + xi); G = __ldcg(job.mvs + row0 + xi); }
+        const bool has_r = xi < g.mb_w - 1;
+        const bool pollable = valid && has_below && !below_fixed(xi - 1);
+        // ---- walk the chunk: runs of kept MBs retire together, a mismatch is searched in place ----
+        int p = 0;                                         // lanes below p are final
+        int rm = right_mv;                                 // final MV to the right of lane p
+        uint2 nfe0 = make_uint2(0, 0), nfe1 = nfe0; int nfe_x = -1;   // prefetched source rows of MB nfe_x
+        for (;;) {
+            const int bl1 = __shfl_up_sync(FULLM, bl, 1), bl2 = __shfl_up_sync(FULLM, bl, 2);
+            const int rd1 = __shfl_up_sync(FULLM, (int)rdy, 1), rd2 = __shfl_up_sync(FULLM, (int)rdy, 2);
+            const int b0 = lane >= 1 ? bl1 : c0;
+            const int bp1 = lane >= 2 ? bl2 : (lane == 1 ? c0 : c1);
+            const bool cond = valid && rdy && (lane < 1 || rd1) && (lane < 2 || rd2);
+            const int in_b = has_below ? b0 : 0;
+            const int in_bl = (has_below && xi > 0) ? bl : 0;
+            const int in_br = (has_below && has_r) ? bp1 : 0;
+            const bool below_ok = cond && A.y == in_b && A.z == in_bl && A.w == in_br;
+            const int Gr = __shfl_up_sync(FULLM, G, 1);
+            const int in_r = has_r ? (lane == p ? rm : Gr) : 0;
+            const bool hit = lane >= p && below_ok && A.x == in_r;
+            const unsigned hb = __ballot_sync(FULLM, hit) >> p;
+            int n = __ffs(~hb) - 1;
+            if (n < 0) n = 32;
+            if (n > 0) {
+                if (lane >= p && lane < p + n) st_rec2(mine + xi, G, epoch);
+                rm = __shfl_sync(FULLM, G, p + n - 1);
+                p += n; n_hit += n;
+                if (p >= 32) break;
+            }
+            if (!__shfl_sync(FULLM, (int)cond, p)) break;  // end of row, or the row below is not there yet
+            // ---- mismatch at lane p: search MB x-p now, from its true inputs ----
+            n_miss++;
+            const int mb_x = x - p, mb_xy = row0 + mb_x;
+            const int b_m1 = __shfl_sync(FULLM, bl, p), b_0 = __shfl_sync(FULLM, b0, p), b_p1 = __shfl_sync(FULLM, bp1, p);
+            m.pel = 8 * (mb_x + mb_y * g.lstride);
+            m.px = 8 * mb_x; m.py = 8 * mb_y;
+            if (nfe_x == mb_x) { m.fe[0] = nfe0; m.fe[1] = nfe1; }
+            else {
+                const int pel = m.pel + m.r0 * g.lstride;
+                m.fe[0] = load8u(job.fenc + pel); m.fe[1] = load8u(job.fenc + pel + g.lstride);
+            }
+            // while this MB is searched: the lanes still waiting for the row below poll again, and
+            // the next MB's source rows are fetched (it usually mismatches too where this one does)
+            uint2 pre = make_uint2(0, 0);
+            const bool repoll = lane > p && pollable && !rdy;
+            if (repoll) pre = ld_rec2(below + xi - 1);
+            if (mb_x - 1 >= end_x) {
+                const int pel = m.pel - 8 + m.r0 * g.lstride;
+                nfe0 = load8u(job.fenc + pel); nfe1 = load8u(job.fenc + pel + g.lstride);
+                nfe_x = mb_x - 1;
+            }
+            const bool mhas_r = mb_x < g.mb_w - 1, has_bl = has_below && mb_x > 0, has_br = has_below && mhas_r;
+            int k0, k1, k2, k3, i_mvc;
+            if (has_below) {
+                k0 = mhas_r ? rm : b_0;
+                k1 = mhas_r ? b_0 : (has_bl ? b_m1 : 0);
+                k2 = mhas_r ? (has_bl ? b_m1 : b_p1) : 0;
+                k3 = (mhas_r && has_bl) ? b_p1 : 0;
+                i_mvc = (int)mhas_r + 1 + (int)has_bl + (int)has_br;
+            } else {
+                k0 = mhas_r ? rm : 0; k1 = k2 = k3 = 0;
+                i_mvc = (int)mhas_r;
+            }
+            const int mvc[4][2] = {{mv_x(k0), mv_y(k0)}, {mv_x(k1), mv_y(k1)}, {mv_x(k2), mv_y(k2)}, {mv_x(k3), mv_y(k3)}};
+            if (i_mvc <= 1) { m.mvp_x = mvc[0][0]; m.mvp_y = mvc[0][1]; }
+            else { m.mvp_x = median3i(mvc[0][0], mvc[1][0], mvc[2][0]); m.mvp_y = median3i(mvc[0][1], mvc[1][1], mvc[2][1]); }
+            int min_sx, max_sx, min_sy, max_sy;
+            mv_limits(mb_x, mb_y, g.mb_w, g.mb_h, P.mv_range2, min_sx, max_sx, min_sy, max_sy);
+            int out_mv = 0, out_cost = 0;
+            bool skip = false;
+            if (!(m.mvp_x | m.mvp_y)) {
+                const int pel = m.pel + m.r0 * g.lstride;
+                const uint2 a[2] = {load8u(job.fref[0] + pel), load8u(job.fref[0] + pel + g.lstride)};
+                const int cz = P.satd ? satd_rows(m, a) : part_sum<4>(sad_rows(m, a));
+                if (cz < 64) { skip = true; out_mv = 0; out_cost = cz; }
+            }
+            if (!skip) {
+                MeResult2 r = me_search_mb2<4, QPRED>(m, sm, g, P, true, mvc, i_mvc, min_sx, max_sx, min_sy, max_sy);
+                int cost = r.cost - (int)__ldg(P.cost_mv);      // remove mvcost from skip mbs
+                if (r.mvx | r.mvy) cost += 5;
+                out_mv = mv_pack(r.mvx, r.mvy); out_cost = cost;
+            }
+            if (lane == 0) {
+                job.mvs[mb_xy] = out_mv;
+                job.mv_costs[mb_xy] = out_cost;
+                st_rec2(mine + mb_x, out_mv, epoch);
+            }
+            if (lane == p) G = out_mv;                     // the next lane's right neighbour
+            if (repoll && (int)pre.y == epoch) { rdy = true; bl = (int)pre.x; }
+            rm = out_mv;
+            p += 1;
+            if (p >= 32) break;
+        }
+        if (p > 0) {
+            const int nc0 = __shfl_sync(FULLM, bl, p - 1);
+            const int nc1 = p >= 2 ? __shfl_sync(FULLM, bl, p - 2) : c0;
+            c0 = nc0; c1 = nc1;
+            right_mv = rm;
+            x -= p; ns = 32;
+        } else { __nanosleep(ns); if (ns < 512) ns <<= 1; }
+    }
+    if (P.stats && lane == 0) { atomicAdd(P.stats, n_hit); atomicAdd(P.stats + 1, n_miss); }
+  }
+}
+
+
+int launch_me_verify(cudaStream_t st, const LaGeom &g, const MeParams &p)
+{
+    if (p.njobs <= 0) return 0;
+    const int rows = p.rows_in_flight > 0 && p.rows_in_flight < g.mb_h ? p.rows_in_flight : g.mb_h;
+    const dim3 grid((rows + VERIFY_WARPS - 1) / VERIFY_WARPS, p.njobs);
+    if (p.subpel_refine >= 3) me_verify_kernel<true><<<grid, 32 * VERIFY_WARPS, 0, st>>>(g, p);
+    else me_verify_kernel<false><<<grid, 32 * VERIFY_WARPS, 0, st>>>(g, p);
     XV_LAUNCH_CHECK();
     return 0;
 }

@@ -577,171 +577,6 @@ me_wavefront_kernel(LaGeom g, MeParams P)
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Verification wavefront: the exact, ordered half of the speculative search (see
-// la_me2_kernel.cu).  Every MB already holds a result G and the four neighbour MVs A it was
-// computed from.  Rows are walked in dependency order exactly like me_wavefront_kernel, but an
-// MB whose assumed inputs equal the FINAL MVs of its neighbours is simply kept -- and runs of
-// such MBs retire 32 at a time: lane i looks at MB x-i, polls the one new record it needs
-// from the row below, takes its right neighbour's tentative G from lane i-1, and the leading
-// run of matching lanes is final by induction.  Only a mismatching MB pays for a search (the
-// whole warp, 8 candidates x 4 lanes, as in me_wavefront_kernel), with its true inputs.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * ME_WARPS, 32 / ME_WARPS)
-me_verify_kernel(LaGeom g, MeParams P)
-{
-    __shared__ MeSmem sm_all[ME_WARPS];
-    MeSmem &sm = sm_all[threadIdx.x >> 5];
-    const MeJob &job = P.job[blockIdx.y];
-    const int lane = threadIdx.x & 31;
-    const unsigned FULLM = 0xffffffffu;
-  for (;;) {
-    int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(job.ticket, 1);
-    ticket = __shfl_sync(FULLM, ticket, 0);
-    const int mb_y = g.mb_h - 1 - ticket;                 // bottom rows start first
-    if (mb_y < 0) return;
-    const int T = max(1, P.bands);
-    int slice_start = 0, slice_end = g.mb_h;
-    for (int i = 0; i < T; i++) {
-        const int s = (g.mb_h * i + T / 2) / T, e = (g.mb_h * (i + 1) + T / 2) / T;
-        if (mb_y >= s && mb_y < e) { slice_start = s; slice_end = e; }
-    }
-    const int start_y = min(slice_end - 1, g.mb_h - 2 + P.do_edges), end_y = max(slice_start, 1 - P.do_edges);
-    const int start_x = g.mb_w - 2 + P.do_edges, end_x = 1 - P.do_edges;
-    if (mb_y > start_y || mb_y < end_y) continue;          // row not scanned (edges without do_edges)
-    const bool has_below = mb_y < slice_end - 1;
-    const bool below_scanned = has_below && (mb_y + 1 <= start_y);
-    const int epoch = P.epoch;
-    const int2 *below = job.rec + (mb_y + 1) * g.mb_w;
-    int2 *mine = job.rec + mb_y * g.mb_w;
-    const int row0 = mb_y * g.mb_w;
-
-    WarpMb m;
-    m.grp = lane >> 2; m.rp = lane & 3;
-    m.stride = g.lstride;
-    m.fref0 = job.fref[0]; m.plane_stride = g.lplane;
-    m.fref_w = job.fref_w; m.w = job.w; m.cost_mv = P.cost_mv; m.satd = P.satd;
-    m.win = nullptr; m.sub = nullptr;
-
-    // below-row value at column p that needs no record: position absent or never scanned
-    auto below_fixed = [&](int p) -> bool { return !below_scanned || p < end_x || p > start_x || p < 0 || p >= g.mb_w; };
-    auto below_wait = [&](int p) -> int {
-        if (below_fixed(p)) return 0;
-        uint2 r = ld_rec(below + p);
-        unsigned ns = 32;
-        while ((int)r.y != epoch) { __nanosleep(ns); if (ns < 512) ns <<= 1; r = ld_rec(below + p); }
-        return (int)r.x;
-    };
-
-    int x = start_x;                // next MB of this row
-    int right_mv = 0;               // final MV of (x+1, y); zero before the first MB
-    int c0 = 0, c1 = 0;             // final MVs of the row below at columns x and x+1
-    if (has_below) { c1 = below_wait(start_x + 1); c0 = below_wait(start_x); }
-    int n_hit = 0, n_miss = 0;
-    unsigned ns = 32;
-    while (x >= end_x) {
-        // ---- load a chunk: lane i examines MB xi = x - i ----
-        const int xi = x - lane;
-        const bool valid = xi >= end_x;
-        int bl = 0; bool rdy = true;                       // row below at column xi-1
-        if (valid && has_below && !below_fixed(xi - 1)) {
-            const uint2 r = ld_rec(below + xi - 1);
-            rdy = (int)r.y == epoch; bl = (int)r.x;
-        }
-        int4 A = make_int4(0, 0, 0, 0); int G = 0;
-        if (valid) { A = __ldcg(job.assumed + row0 + xi); G = __ldcg(job.mvs + row0 + xi); }
-        const int bl1 = __shfl_up_sync(FULLM, bl, 1), bl2 = __shfl_up_sync(FULLM, bl, 2);
-        const int rd1 = __shfl_up_sync(FULLM, (int)rdy, 1), rd2 = __shfl_up_sync(FULLM, (int)rdy, 2);
-        const int b0 = lane >= 1 ? bl1 : c0;
-        const int bp1 = lane >= 2 ? bl2 : (lane == 1 ? c0 : c1);
-        const bool cond = valid && rdy && (lane < 1 || rd1) && (lane < 2 || rd2);
-        const bool has_r = xi < g.mb_w - 1;
-        const int in_b = has_below ? b0 : 0;
-        const int in_bl = (has_below && xi > 0) ? bl : 0;
-        const int in_br = (has_below && has_r) ? bp1 : 0;
-        const bool below_ok = cond && A.y == in_b && A.z == in_bl && A.w == in_br;
-        // ---- walk the chunk: runs of kept MBs retire together, a mismatch is searched in place ----
-        int p = 0;                                         // lanes below p are final
-        int rm = right_mv;                                 // final MV to the right of lane p
-        for (;;) {
-            const int Gr = __shfl_up_sync(FULLM, G, 1);
-            const int in_r = has_r ? (lane == p ? rm : Gr) : 0;
-            const bool hit = lane >= p && below_ok && A.x == in_r;
-            const unsigned hb = __ballot_sync(FULLM, hit) >> p;
-            int n = __ffs(~hb) - 1;
-            if (n < 0) n = 32;
-            if (n > 0) {
-                if (lane >= p && lane < p + n) st_rec(mine + xi, G, epoch);
-                rm = __shfl_sync(FULLM, G, p + n - 1);
-                p += n; n_hit += n;
-                if (p >= 32) break;
-            }
-            if (!__shfl_sync(FULLM, (int)cond, p)) break;  // end of row, or the row below is not there yet
-            // ---- mismatch at lane p: search MB x-p now, from its true inputs ----
-            n_miss++;
-            const int mb_x = x - p, mb_xy = row0 + mb_x;
-            const int b_m1 = __shfl_sync(FULLM, bl, p), b_0 = __shfl_sync(FULLM, b0, p), b_p1 = __shfl_sync(FULLM, bp1, p);
-            m.pel = 8 * (mb_x + mb_y * g.lstride);
-            m.px = 8 * mb_x; m.py = 8 * mb_y;
-            {
-                const int pel = m.pel + 2 * m.rp * g.lstride;
-                m.fe0 = load8u(job.fenc + pel); m.fe1 = load8u(job.fenc + pel + g.lstride);
-            }
-            const bool mhas_r = mb_x < g.mb_w - 1, has_bl = has_below && mb_x > 0, has_br = has_below && mhas_r;
-            int k0, k1, k2, k3, i_mvc;
-            if (has_below) {
-                k0 = mhas_r ? rm : b_0;
-                k1 = mhas_r ? b_0 : (has_bl ? b_m1 : 0);
-                k2 = mhas_r ? (has_bl ? b_m1 : b_p1) : 0;
-                k3 = (mhas_r && has_bl) ? b_p1 : 0;
-                i_mvc = (int)mhas_r + 1 + (int)has_bl + (int)has_br;
-            } else {
-                k0 = mhas_r ? rm : 0; k1 = k2 = k3 = 0;
-                i_mvc = (int)mhas_r;
-            }
-            const int mvc[4][2] = {{mv_x(k0), mv_y(k0)}, {mv_x(k1), mv_y(k1)}, {mv_x(k2), mv_y(k2)}, {mv_x(k3), mv_y(k3)}};
-            if (i_mvc <= 1) { m.mvp_x = mvc[0][0]; m.mvp_y = mvc[0][1]; }
-            else { m.mvp_x = median3i(mvc[0][0], mvc[1][0], mvc[2][0]); m.mvp_y = median3i(mvc[0][1], mvc[1][1], mvc[2][1]); }
-            int min_sx, max_sx, min_sy, max_sy;
-            mv_limits(mb_x, mb_y, g.mb_w, g.mb_h, P.mv_range2, min_sx, max_sx, min_sy, max_sy);
-            int out_mv = 0, out_cost = 0;
-            bool skip = false;
-            if (!(m.mvp_x | m.mvp_y)) {
-                const int pel = m.pel + 2 * m.rp * g.lstride;
-                const uint2 r0 = load8u(job.fref[0] + pel), r1 = load8u(job.fref[0] + pel + g.lstride);
-                const int c = P.satd ? rows_satd(m, r0, r1) : group_sum(rows_sad(m, r0, r1));
-                const int cz = __shfl_sync(FULLM, c, 0);
-                if (cz < 64) { skip = true; out_mv = 0; out_cost = cz; }
-            }
-            if (!skip) {
-                MeResult r = me_search_mb(m, sm, g, P, mvc, i_mvc, min_sx, max_sx, min_sy, max_sy, lane);
-                int cost = r.cost - (int)__ldg(P.cost_mv);      // remove mvcost from skip mbs
-                if (r.mvx | r.mvy) cost += 5;
-                out_mv = mv_pack(r.mvx, r.mvy); out_cost = cost;
-            }
-            if (lane == 0) {
-                job.mvs[mb_xy] = out_mv;
-                job.mv_costs[mb_xy] = out_cost;
-                st_rec(mine + mb_x, out_mv, epoch);
-            }
-            if (lane == p) G = out_mv;                     // the next lane's right neighbour
-            rm = out_mv;
-            p += 1;
-            if (p >= 32) break;
-        }
-        if (p > 0) {
-            const int nc0 = __shfl_sync(FULLM, bl, p - 1);
-            const int nc1 = p >= 2 ? __shfl_sync(FULLM, bl, p - 2) : c0;
-            c0 = nc0; c1 = nc1;
-            right_mv = rm;
-            x -= p; ns = 32;
-        } else { __nanosleep(ns); if (ns < 512) ns <<= 1; }
-    }
-    if (P.stats && lane == 0) { atomicAdd(P.stats, n_hit); atomicAdd(P.stats + 1, n_miss); }
-  }
-}
-
 static dim3 wavefront_grid(const LaGeom &g, const MeParams &p)
 {
     const int rows = p.rows_in_flight > 0 && p.rows_in_flight < g.mb_h ? p.rows_in_flight : g.mb_h;
@@ -753,15 +588,6 @@ int launch_me(cudaStream_t st, const LaGeom &g, const MeParams &p)
 {
     if (p.njobs <= 0) return 0;
     me_wavefront_kernel<<<wavefront_grid(g, p), 32 * ME_WARPS, 0, st>>>(g, p);
-    XV_LAUNCH_CHECK();
-    return 0;
-}
-
-// exact verification wavefront after the speculative passes (launch_me_pass)
-int launch_me_verify(cudaStream_t st, const LaGeom &g, const MeParams &p)
-{
-    if (p.njobs <= 0) return 0;
-    me_verify_kernel<<<wavefront_grid(g, p), 32 * ME_WARPS, 0, st>>>(g, p);
     XV_LAUNCH_CHECK();
     return 0;
 }
