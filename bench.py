@@ -129,56 +129,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-class StreamWorker(threading.Thread):
-    """One host thread per stream (the reference calls the path on the app thread, codec.c:1728)."""
-
-    def __init__(self, la, frames, on_device, conv_bufs, barrier_in, barrier_out, frames_per_step):
-        super().__init__(daemon=True)
-        self.la, self.frames, self.on_device, self.conv = la, frames, on_device, conv_bufs
-        self.bin, self.bout, self.F = barrier_in, barrier_out, frames_per_step
-        self.pos = 0
-        self.decided = 0
-        self.stop_flag = False
-        self.error = None
-
-    def feed(self, n):
-        for _ in range(n):
-            # ping-pong playback: the clip loops without a hard cut at the wrap-around
-            n = len(self.frames)
-            k = self.pos % (2 * n - 2)
-            k = k if k < n else 2 * n - 2 - k
-            conv = self.conv[self.pos % len(self.conv)] if self.conv else None
-            self.la.put_frame(self.frames[k], on_device=self.on_device, conv_pic=conv)
-            self.decided += len(self.la.decisions(with_offsets=True))
-            self.pos += 1
-
-    def run(self):
-        while True:
-            self.bin.wait()
-            if self.stop_flag:
-                return
-            try:
-                self.feed(self.F)
-            except Exception as e:          # surface, do not hang the barrier
-                self.error = e
-            self.bout.wait()
-
-
 def run_phase(torch, dist, sessions, frames, on_device, conv, args, rank, world, sampler_index, profile=False):
     """Prefill + warm-up + timed steps.  Returns (ms_per_step_max_over_ranks, clocks, launches, prof)."""
     import x264vfw_b200 as xv
+    from x264vfw_b200.harness import StreamSet
     S, F = len(sessions), args.frames_per_step
-    bin_, bout = threading.Barrier(S + 1), threading.Barrier(S + 1)
-    workers = [StreamWorker(sessions[s], frames[s], on_device, conv[s] if conv else None, bin_, bout, F) for s in range(S)]
-    for wkr in workers:
-        wkr.start()
+    # one NATIVE host thread per stream (host/x264vfw_harness.c), like the reference's app threads
+    streams = StreamSet(sessions, frames, on_device, conv)
 
     def step():
-        bin_.wait()
-        bout.wait()
-        for wkr in workers:
-            if wkr.error:
-                raise wkr.error
+        streams.run(F)
 
     # prefill the lookahead window (rc-lookahead 40 + bframes) so that timed steps are steady state
     prefill = -(-(sessions[0].p.rc_lookahead + sessions[0].p.bframes + 2) // F)
@@ -218,9 +178,7 @@ def run_phase(torch, dist, sessions, frames, on_device, conv, args, rank, world,
                 a = prof.setdefault(k, [0.0, 0])
                 a[0] += t
                 a[1] += n
-    for wkr in workers:
-        wkr.stop_flag = True
-    bin_.wait()
+    streams.close()
     from x264vfw_b200.sharding import max_over_ranks, sum_over_ranks
     ms = max_over_ranks(ms, device="cuda")                  # slowest rank defines the step
     launches = sum_over_ranks(launches, device="cuda")
@@ -410,20 +368,31 @@ def main():
     geom_mb = 120 * 68
     # algorithmic bytes of one search launch: fenc plane + 4 ref planes + per-MB mv/cost
     me_bytes_per_search = 960 * 544 * 5 + geom_mb * 8
+    # the motion search = speculative parallel passes (me_pass_kernel, class "me_pass") + the exact
+    # verification wavefront (me_verify_kernel, class "me"); one search batch = one launch of each
     me_ms, me_n = prof["me"]
-    me_avg = me_ms / max(1, me_n)
+    pass_ms, pass_n = prof.get("me_pass", (0.0, 0))
+    me_avg = (me_ms + pass_ms) / max(1, me_n)
     searches_per_launch = prof_delta["mb_searches"] / geom_mb / max(1, me_n)
-    roofline = {"kernel": "me_wavefront_kernel (lowres motion search; latency-bound wavefront on the integer pipe, see DESIGN.md)",
+    # DRAM traffic per search from ncu --set full (profiles/ncu_me_pass_r1.txt, ncu_me_verify_r1.txt):
+    # pass 0 of a 2-search batch reads 4.67 MB and writes ~0 (outputs stay in L2); the
+    # verification of the same batch moves 1.38 MB
+    traffic_per_search = (4.67e6 + 1.38e6) / 2
+    roofline = {"kernel": "motion search: me_pass_kernel (speculative parallel passes) + me_verify_kernel (exact ordered "
+                          "verification); integer pipe / dependent-MB latency, see DESIGN.md 4.1",
                 "bound": "hbm", "achieved": (me_bytes_per_search * searches_per_launch / (me_avg * 1e-3) / 1e9) if me_n else None,
                 "peak": hbm_peak, "unit": "GB/s", "frac": None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one 7-search launch, ncu --set full
-                # (profiles/ncu_me_wavefront_r1.txt): 11.9 MB + 55.3 MB, mostly write-back of earlier kernels' lines
-                "traffic": 67.2e6, "peak_source": peak_src,
+                "traffic": traffic_per_search * searches_per_launch, "peak_source": peak_src,
                 "avg_launch_ms": me_avg, "launches": me_n, "searches_per_launch": searches_per_launch,
+                "avg_pass_ms": pass_ms / max(1, pass_n), "avg_verify_ms": me_ms / max(1, me_n),
                 "algorithmic_bytes_per_search": me_bytes_per_search, "mb_searches_per_s": prof_delta["mb_searches"] / (ms_prof * args.steps * 1e-3),
-                "share_of_step_device_time": shares["me"]["share"],
-                "note": "dominant kernel by device time; its bound is neither HBM nor tensor (SURVEY 8(d)): "
-                        "algorithmic traffic is ~2.7 MB per search. The HBM-bound kernels of the path are reported in stage1."}
+                "share_of_step_device_time": shares["me"]["share"] + shares.get("me_pass", {"share": 0.0})["share"],
+                "issue_slot_utilisation_ncu": {"me_pass_kernel": 0.39, "me_verify_kernel": 0.07,
+                                               "source": "profiles/ncu_me_pass_r1.txt, profiles/ncu_me_verify_r1.txt (kernel alone on the GPU)"},
+                "note": "dominant kernels by device time; their bound is neither HBM nor tensor (SURVEY 8(d)): algorithmic "
+                        "traffic is ~2.7 MB per search against 8160 dependent MB searches, so the GB/s figure is tiny by "
+                        "construction -- the relevant ncu evidence is integer-pipe issue utilisation. The HBM-bound kernels "
+                        "of the path are reported in stage1."}
     if roofline["achieved"] is not None:
         roofline["frac"] = roofline["achieved"] / hbm_peak
     for k in stage1:

@@ -125,6 +125,73 @@ int harness_compress_end(harness_codec *c, FILE *out)
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Several sessions at once, ONE HOST THREAD PER STREAM -- the reference runs the path on
+ * whichever application thread sends ICM_COMPRESS (codec.c:1728), one call in flight per
+ * CODEC, different CODECs concurrently.  bench.py and the tests drive this through ctypes so
+ * that the per-frame loop is native code (Python threads would serialise on the interpreter
+ * lock and measure that instead).
+ * ---------------------------------------------------------------------------------------- */
+#include <pthread.h>
+
+typedef struct harness_stream {
+    x264vfw_cuda_la *la;                 /* open session (x264vfw_cuda_la_open)                    */
+    const uint8_t *const *frames;        /* clip: n_frames packed frames, host (pinned) or device   */
+    int n_frames, on_device;
+    int in_csp, out_csp, width, height;
+    uint8_t *const *conv;                /* n_conv host buffers receiving conv_pic, or NULL         */
+    int n_conv;
+    long pos;                            /* frames fed so far (ping-pong playback position)         */
+    long decided;                        /* decisions drained so far                                */
+    double checksum;                     /* over the drained qp offsets (keeps the copies honest)   */
+    int mb_count, error;
+    float *qp, *qp_aq;                   /* scratch, allocated on first use                         */
+    int count;                           /* frames to feed in this call (set by the runner)         */
+} harness_stream;
+
+static void *stream_thread(void *arg)
+{
+    harness_stream *s = (harness_stream *)arg;
+    if (!s->qp) {
+        s->mb_count = ((s->width + 15) >> 4) * ((s->height + 15) >> 4);
+        s->qp = malloc(sizeof(float) * s->mb_count);
+        s->qp_aq = malloc(sizeof(float) * s->mb_count);
+    }
+    for (int i = 0; i < s->count && !s->error; i++) {
+        /* ping-pong playback: the clip loops without a hard cut at the wrap-around */
+        const int n = s->n_frames;
+        int k = n > 1 ? (int)(s->pos % (2 * n - 2)) : 0;
+        if (k >= n) k = 2 * n - 2 - k;
+        x264vfw_cuda_image_t pic, conv_pic, *cp = NULL;
+        if (x264vfw_cuda_img_fill(&pic, (uint8_t *)s->frames[k], s->in_csp, s->width, s->height) < 0) { s->error = 1; break; }
+        if (s->conv) {
+            x264vfw_cuda_picture_layout(&conv_pic, s->conv[s->pos % s->n_conv], s->out_csp, s->width, s->height);
+            cp = &conv_pic;
+        }
+        if (x264vfw_cuda_la_put_frame(s->la, &pic, s->on_device, cp) < 0) { s->error = 1; break; }
+        x264vfw_cuda_la_decision d;
+        while (x264vfw_cuda_la_get_decision(s->la, &d, s->qp, s->qp_aq) == 1) {
+            s->checksum += s->qp[d.i_frame % s->mb_count] + d.i_type;
+            s->decided++;
+        }
+        s->pos++;
+    }
+    return NULL;
+}
+
+/* Feed `count` frames to each of the n streams concurrently; returns 0, or -1 if any failed. */
+int harness_run_streams(harness_stream *streams, int n, int count)
+{
+    pthread_t th[256];
+    if (n > 256) return -1;
+    for (int i = 0; i < n; i++) { streams[i].count = count; if (pthread_create(&th[i], NULL, stream_thread, &streams[i])) return -1; }
+    int rc = 0;
+    for (int i = 0; i < n; i++) { pthread_join(th[i], NULL); if (streams[i].error) rc = -1; }
+    return rc;
+}
+
+void harness_stream_free(harness_stream *s) { free(s->qp); free(s->qp_aq); s->qp = s->qp_aq = NULL; }
+
 #ifndef HARNESS_NO_MAIN
 /* usage: x264vfw_harness <w> <h> <frames> [preset]   -- encodes a synthetic bottom-up RGB32 clip */
 int main(int argc, char **argv)

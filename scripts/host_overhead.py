@@ -8,17 +8,25 @@ from x264vfw_b200.clipgen import SyntheticClip
 
 W, H, N = 1920, 1080, 24
 clip = SyntheticClip(W, H, n_frames=N, cuts=(15,), flash=None)
-frames = [torch.from_numpy(clip.packed(i, "bgra")).cuda() for i in range(N)]
+HOST = int(os.environ.get("HOST", "0"))      # 1: pinned host frames in, converted planes out (the e2e path)
+if HOST:
+    frames = [torch.from_numpy(clip.packed(i, "bgra")).pin_memory() for i in range(N)]
+else:
+    frames = [torch.from_numpy(clip.packed(i, "bgra")).cuda() for i in range(N)]
 torch.cuda.synchronize()
 
-def run(S, total=120):
+def run(S, total=int(os.environ.get("TOTAL", "120"))):
     las = [lookahead.Lookahead(lookahead.params_preset("medium", W, H), in_csp=9 | 0x1000, device=0) for _ in range(S)]
     base = {}
     def work(la):
+        conv = [torch.empty(W * H * 3 // 2, dtype=torch.uint8).pin_memory().numpy() for _ in range(2)] if HOST else None
         for i in range(total):
             if i == 60:
                 base[id(la)] = (la.counters(), time.perf_counter())
-            la.put_frame(frames[i % N].data_ptr(), on_device=True)
+            if HOST:
+                la.put_frame(frames[i % N].numpy(), on_device=False, conv_pic=conv[i & 1])
+            else:
+                la.put_frame(frames[i % N].data_ptr(), on_device=True)
             la.decisions()
     ths = [threading.Thread(target=work, args=(la,)) for la in las]
     t0 = time.perf_counter()

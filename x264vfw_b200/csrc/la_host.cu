@@ -114,7 +114,7 @@ struct La {
     int ext = X264VFW_CUDA_EXT_NONE;   // packed 4:2:2 -> I444 uses the documented extension conversion
     int me_rows = 0;         // warps per search in the wavefront kernel
     int me_variant = 1;      // 0: plain wavefront, 1: speculative parallel passes + verification wavefront
-    int me_passes = 2;       // parallel passes of the speculative search
+    int me_passes = 3;       // parallel passes of the speculative search
     int *d_me_stats = nullptr;
     int stats_verbose = 0; std::string dbg_jobs; int dbg_prev[8] = {0};
     // searches the decision logic asked for during the current decision, and the ones predicted
@@ -143,7 +143,9 @@ struct La {
     uint64_t me_waited[1 + ME_SIDE] = {0};                  // highest launch the main stream already waits on
     cudaEvent_t ev_ready = nullptr;                         // main stream -> side stream hand-off
     cudaEvent_t ev_io = nullptr;                            // caller's buffers are free again (H2D / D2H of this put done)
-    cudaEvent_t ev_h2d = nullptr, ev_csp = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_csp = nullptr, ev_planes_free = nullptr;
+    cudaEvent_t io_ev[5] = {nullptr}; double io_ms[4] = {0}; uint64_t io_n = 0;   // diagnostics (X264VFW_CUDA_STATS)
+    bool planes_busy = false;                               // ev_planes_free has been recorded at least once
     cudaStream_t st_io = nullptr;                           // host <-> device copies of the borrowed buffers
     int me_guess = 1;
     int me_epoch = 0, me_rr = 0, me_side = ME_SIDE;   // side engines in use (1..ME_SIDE)
@@ -169,7 +171,7 @@ struct La {
     int n_input = 0;
     uint64_t n_frame_cost = 0, n_mb_search = 0, n_launch = 0, n_sync = 0;
     bool fail = false;   // set when a device call fails inside the value-returning helpers
-    double t_put = 0, t_decide = 0, t_sync = 0;   // host wall-clock seconds (diagnostics)
+    double t_put = 0, t_decide = 0, t_sync = 0, t_io = 0;   // host wall-clock seconds (diagnostics)
     uint64_t n_ondemand = 0, n_ondemand_jobs = 0, n_spec_jobs = 0;
     uint64_t n_logical[2][BMAX + 1] = {{0}};      // searches upstream's control flow actually asked for, by list/distance
     Prof prof;
@@ -1405,6 +1407,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
              cudaEventCreateWithFlags(&la->ev_io, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_csp, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&la->ev_planes_free, cudaEventDisableTiming) == cudaSuccess &&
              cudaMalloc((void **)&la->d_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMallocHost((void **)&la->h_results, RESULT_SLOTS * 4 * sizeof(int)) == cudaSuccess &&
              cudaMalloc((void **)&la->d_wscore, 64) == cudaSuccess &&
@@ -1459,6 +1462,11 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
         for (int l = 0; l < 2; l++) for (int d = 0; d <= la->p.bframes; d++) fprintf(stderr, " l%d/d%d=%llu", l, d + 1, (unsigned long long)la->n_logical[l][d]);
         fprintf(stderr, "  | speculative jobs %llu, on-demand launches %llu (%llu jobs)\n", (unsigned long long)la->n_spec_jobs,
                 (unsigned long long)la->n_ondemand, (unsigned long long)la->n_ondemand_jobs);
+        if (la->io_n) fprintf(stderr, "[x264vfw_cuda] I/O stream us per frame: wait for planes %.0f, H2D %.0f, conversion %.0f, D2H %.0f\n",
+                              1e3 * la->io_ms[0] / la->io_n, 1e3 * la->io_ms[1] / la->io_n, 1e3 * la->io_ms[2] / la->io_n, 1e3 * la->io_ms[3] / la->io_n);
+        fprintf(stderr, "[x264vfw_cuda] host us per frame: put %.0f decide %.0f (of which waiting %.0f) final wait for the borrowed buffers %.0f\n",
+                1e6 * la->t_put / (la->n_input ? la->n_input : 1), 1e6 * la->t_decide / (la->n_input ? la->n_input : 1),
+                1e6 * la->t_sync / (la->n_input ? la->n_input : 1), 1e6 * la->t_io / (la->n_input ? la->n_input : 1));
     }
     if (la->st) cudaStreamSynchronize(la->st);
     for (int e = 1; e <= ME_SIDE; e++) if (la->st_me[e]) cudaStreamSynchronize(la->st_me[e]);
@@ -1489,6 +1497,7 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     if (la->ev_io) cudaEventDestroy(la->ev_io);
     if (la->ev_h2d) cudaEventDestroy(la->ev_h2d);
     if (la->ev_csp) cudaEventDestroy(la->ev_csp);
+    if (la->ev_planes_free) cudaEventDestroy(la->ev_planes_free);
     if (la->st_io) { cudaStreamSynchronize(la->st_io); cudaStreamDestroy(la->st_io); } cudaFree(la->d_results); cudaFree(la->d_wscore); cudaFree(la->d_planes); cudaFree(la->d_src);
     if (la->h_results) cudaFreeHost(la->h_results);
     if (la->h_wscore) cudaFreeHost(la->h_wscore);
@@ -1520,26 +1529,62 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     if (!f) return -1;
     la->n_input++;
 
-    // ---- 1. host source: H2D on the I/O stream, so that it overlaps the decision logic below ----
+    const int out420 = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_NV12;
+    x264vfw_cuda_image_t geo_out;
+    x264vfw_cuda_picture_layout(&geo_out, nullptr, la->out_csp, w, hgt);
+    // Stage 1 of a frame whose buffers are borrowed (host source and/or conv_pic) runs entirely
+    // on the I/O stream -- H2D, conversion, D2H of the converted planes -- so that all of it
+    // overlaps the decision logic below, which keeps the main stream to itself.
+    cudaStream_t st1 = borrowed ? la->st_io : la->st;
     x264vfw_cuda_image_t dsrc = *src;
     dsrc.i_csp = la->in_csp;
-    if (host_src) {
-        x264vfw_cuda_image_t geo;
-        if (x264vfw_cuda_img_fill(&geo, nullptr, in, w, hgt) < 0) return -1;
-        const int in420 = in == X264VFW_CUDA_CSP_I420 || in == X264VFW_CUDA_CSP_YV12 || in == X264VFW_CUDA_CSP_NV12;
-        size_t need = 0, off[4];
-        for (int i = 0; i < geo.i_plane; i++) { off[i] = need; need += ((size_t)src->i_stride[i] * chroma_rows(in420, i) + 255) & ~(size_t)255; }
-        if (la->d_src_bytes < need) {
-            if (la->d_src) { XV_CUDA_OK(cudaStreamSynchronize(la->st)); XV_CUDA_OK(cudaStreamSynchronize(la->st_io)); cudaFree(la->d_src); la->d_src = nullptr; }
-            XV_CUDA_OK(cudaMalloc((void **)&la->d_src, need + 256));
-            la->d_src_bytes = need;
+    auto stage1 = [&]() -> int {
+        const bool iop = borrowed && la->d_me_stats;
+        if (iop && !la->io_ev[0]) for (int k = 0; k < 5; k++) cudaEventCreate(&la->io_ev[k]);
+        if (iop) cudaEventRecord(la->io_ev[0], la->st_io);
+        // the previous frame's AQ / lowres kernels read the planes this conversion overwrites
+        if (borrowed && la->planes_busy) XV_CUDA_OK(cudaStreamWaitEvent(la->st_io, la->ev_planes_free, 0));
+        if (iop) cudaEventRecord(la->io_ev[1], la->st_io);
+        if (host_src) {
+            x264vfw_cuda_image_t geo;
+            if (x264vfw_cuda_img_fill(&geo, nullptr, in, w, hgt) < 0) return -1;
+            const int in420 = in == X264VFW_CUDA_CSP_I420 || in == X264VFW_CUDA_CSP_YV12 || in == X264VFW_CUDA_CSP_NV12;
+            size_t need = 0, off[4];
+            for (int i = 0; i < geo.i_plane; i++) { off[i] = need; need += ((size_t)src->i_stride[i] * chroma_rows(in420, i) + 255) & ~(size_t)255; }
+            if (la->d_src_bytes < need) {
+                if (la->d_src) { XV_CUDA_OK(cudaStreamSynchronize(la->st)); XV_CUDA_OK(cudaStreamSynchronize(la->st_io)); cudaFree(la->d_src); la->d_src = nullptr; }
+                XV_CUDA_OK(cudaMalloc((void **)&la->d_src, need + 256));
+                la->d_src_bytes = need;
+            }
+            for (int i = 0; i < geo.i_plane; i++) {
+                dsrc.plane[i] = la->d_src + off[i];
+                XV_CUDA_OK(cudaMemcpyAsync(dsrc.plane[i], src->plane[i], (size_t)src->i_stride[i] * chroma_rows(in420, i), cudaMemcpyHostToDevice, la->st_io));
+            }
         }
-        for (int i = 0; i < geo.i_plane; i++) {
-            dsrc.plane[i] = la->d_src + off[i];
-            XV_CUDA_OK(cudaMemcpyAsync(dsrc.plane[i], src->plane[i], (size_t)src->i_stride[i] * chroma_rows(in420, i), cudaMemcpyHostToDevice, la->st_io));
+        if (iop) cudaEventRecord(la->io_ev[2], la->st_io);
+        if (in == X264VFW_CUDA_CSP_NONE) {
+            // planar frame already in the encoder csp: copy rows into the tight device planes
+            for (int i = 0; i < geo_out.i_plane; i++)
+                XV_CUDA_OK(cudaMemcpy2DAsync(planes.plane[i], planes.i_stride[i], src->plane[i], src->i_stride[i], geo_out.i_stride[i], chroma_rows(out420, i),
+                                             src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st1));
+        } else {
+            { ProfScope ps(la, K_CSP, st1); if (convert_device_public(st1, la->out_csp, la->colmatrix, la->fullrange, la->ext, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
+            la->n_launch++;
         }
-        XV_CUDA_OK(cudaEventRecord(la->ev_h2d, la->st_io));
-    }
+        if (borrowed) {
+            XV_CUDA_OK(cudaEventRecord(la->ev_csp, la->st_io));
+            if (iop) cudaEventRecord(la->io_ev[3], la->st_io);
+            if (conv_pic)
+                for (int i = 0; i < geo_out.i_plane; i++)
+                    XV_CUDA_OK(cudaMemcpy2DAsync(conv_pic->plane[i], conv_pic->i_stride[i], planes.plane[i], planes.i_stride[i], geo_out.i_stride[i], chroma_rows(out420, i),
+                                                 cudaMemcpyDeviceToHost, la->st_io));
+            if (iop) cudaEventRecord(la->io_ev[4], la->st_io);
+            XV_CUDA_OK(cudaEventRecord(la->ev_io, la->st_io));
+        }
+        return 0;
+    };
+    // ---- 1. borrowed buffers: stage 1 goes first, on the I/O stream ----
+    if (borrowed && stage1() < 0) return -1;
 
     // ---- 2. the decision that became due (deferred by decide_lag frames) ----
     double t_dec = 0;
@@ -1551,33 +1596,9 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         t_dec = now_s() - t0;
     }
 
-    // ---- 3. stage 1 on the device ----
-    const int out420 = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_NV12;
-    x264vfw_cuda_image_t geo_out;
-    x264vfw_cuda_picture_layout(&geo_out, nullptr, la->out_csp, w, hgt);
-    if (in == X264VFW_CUDA_CSP_NONE) {
-        // planar frame already in the encoder csp: copy rows into the tight device planes
-        for (int i = 0; i < geo_out.i_plane; i++)
-            XV_CUDA_OK(cudaMemcpy2DAsync(planes.plane[i], planes.i_stride[i], src->plane[i], src->i_stride[i], geo_out.i_stride[i], chroma_rows(out420, i),
-                                         src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, la->st));
-    } else {
-        if (host_src) XV_CUDA_OK(cudaStreamWaitEvent(la->st, la->ev_h2d, 0));
-        { ProfScope ps(la, K_CSP); if (convert_device_public(la->st, la->out_csp, la->colmatrix, la->fullrange, la->ext, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
-        la->n_launch++;
-    }
-    // everything that touches the caller's buffers: the converted planes go back on the I/O stream
-    if (conv_pic) {
-        XV_CUDA_OK(cudaEventRecord(la->ev_csp, la->st));
-        XV_CUDA_OK(cudaStreamWaitEvent(la->st_io, la->ev_csp, 0));
-        for (int i = 0; i < geo_out.i_plane; i++)
-            XV_CUDA_OK(cudaMemcpy2DAsync(conv_pic->plane[i], conv_pic->i_stride[i], planes.plane[i], planes.i_stride[i], geo_out.i_stride[i], chroma_rows(out420, i),
-                                         cudaMemcpyDeviceToHost, la->st_io));
-        XV_CUDA_OK(cudaEventRecord(la->ev_io, la->st_io));
-        // the next frame's csp overwrites the planes: order it after this read-back
-        XV_CUDA_OK(cudaStreamWaitEvent(la->st, la->ev_io, 0));
-    } else if (borrowed) {
-        XV_CUDA_OK(cudaEventRecord(la->ev_io, la->st));
-    }
+    // ---- 3. stage 1 on the main stream (device-resident frame), or its hand-over to it ----
+    if (!borrowed) { if (stage1() < 0) return -1; }
+    else XV_CUDA_OK(cudaStreamWaitEvent(la->st, la->ev_csp, 0));
 
     // ---- 4. [x264] x264_adaptive_quant_frame ----
     const bool planar_yuv = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_I422 || la->out_csp == X264VFW_CUDA_OUT_I444;
@@ -1601,6 +1622,8 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     lj.src_frame_bytes = 0; lj.dst_frame_bytes = 0;
     { ProfScope ps(la, K_LOWRES); if (launch_lowres_init(la->st, lj, 1) < 0) return -1; }
     la->n_launch += 2;
+    XV_CUDA_OK(cudaEventRecord(la->ev_planes_free, la->st));
+    la->planes_busy = true;
 
     f->ready = true;
     if (speculate_searches(la, f) < 0) return -1;
@@ -1613,7 +1636,11 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     }
     la->t_decide += t_dec;
     la->t_put += (la->decide_lag == 0 ? t_mid - t_begin : now_s() - t_begin - t_dec);
-    if (borrowed) XV_CUDA_OK(cudaEventSynchronize(la->ev_io));   // caller's buffers are borrowed for the call only
+    if (borrowed) { const double t0 = now_s(); XV_CUDA_OK(cudaEventSynchronize(la->ev_io)); la->t_io += now_s() - t0; }
+    if (borrowed && la->d_me_stats && la->io_ev[0]) {
+        for (int k = 0; k < 4; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, la->io_ev[k], la->io_ev[k + 1]) == cudaSuccess) la->io_ms[k] += ms; }
+        la->io_n++;
+    }   // caller's buffers are borrowed for the call only
     return (int)la->outq.size();
 }
 
