@@ -258,7 +258,8 @@ def main_reference(args):
         return
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True)
     cores = os.cpu_count() or 1
-    n_streams = max(1, min(cores, args.streams * max(1, args.gpus)))
+    # all the host threads the box has: the streams are independent, one thread each (codec.c:1728)
+    n_streams = max(1, cores)
     fps_list = []
     clips = make_clips(list(range(min(n_streams, 8))), 12)
     clips = [clips[i % len(clips)] for i in range(n_streams)]
@@ -271,7 +272,7 @@ def main_reference(args):
             t_all.append(dt)
             fps_list.append(nfr / dt)
     fps = sum(fps_list) / len(fps_list)
-    sample = (f"{n_streams} streams x {frames_per_stream} frames of the C5 clip per step, one thread per stream on {cores} host cores; "
+    sample = (f"{n_streams} independent C5 streams x {frames_per_stream} frames per step, one thread per stream = all {cores} host cores; "
               f"stage 1 = {'unmodified reference csp.c (oracle/_ref)' if 'reference' in kind else 'csp port'}, "
               "stage 2 = CPU restatement of the libx264 lookahead, scalar C, no asm -- not libx264")
     line = {"impl": "reference", "metric": "1080p frames/sec through csp+lookahead", "value": fps, "unit": "frames/s",

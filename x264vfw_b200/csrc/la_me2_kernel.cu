@@ -6,7 +6,7 @@
 // function of its pixels and of those four neighbour MVs, and motion fields are smooth: here
 // every MB is searched AT ONCE from assumed neighbour MVs (the same search of the previous
 // frame as a first guess, then the results of the previous pass), and a cheap verification
-// wavefront (la_me_kernel.cu: me_verify_kernel) keeps a result only if the inputs it assumed
+// wavefront (me_verify_kernel below) keeps a result only if the inputs it assumed
 // are the final MVs of its neighbours -- otherwise it re-runs that MB's search in order.  The
 // output is therefore exactly the sequential scan's (bit-exact incl. tie-breaks); the guess
 // only decides how much of the work happens off the critical path.
@@ -575,7 +575,7 @@ __device__ __forceinline__ MeResult2 me_search_mb2(Mb<LPS> &m, GroupSmem &sm, co
 // Parallel pass: every MB of the frame is searched at once from ASSUMED neighbour MVs (a guess
 // field for the first pass, the previous pass's results afterwards).  A group of 8*LPS lanes
 // owns one MB, NG horizontally adjacent MBs share a warp.  Each MB records the four inputs it
-// used next to its result; the verification wavefront (la_me_kernel.cu: me_verify_kernel)
+// used next to its result; the verification wavefront (me_verify_kernel below)
 // accepts a result only if those inputs equal the final MVs of the neighbours, and re-runs the
 // search otherwise, so the output is exactly the sequential reverse-raster scan's.
 //   pass 0      : inputs from job.guess (or zeros), all MBs
@@ -732,24 +732,47 @@ int launch_me_pass(cudaStream_t st, const LaGeom &g, const MeParams &p, int pass
 // whole warp, 8 candidates x 4 lanes: the same search code as the passes, instantiated with
 // 4 lanes per candidate), with its true inputs.
 // ------------------------------------------------------------------------------------------
-#define VERIFY_WARPS 2
+// A block owns a BAND of VERIFY_ROWS consecutive rows, one warp per row: inside a band a row
+// hands its MVs to the row above through shared memory (~100 cycles instead of an L2 round
+// trip of ~1500 on the chain), only the top row of a band publishes to global memory for the
+// band above.  Bands are handed out bottom-first by an atomic ticket, so a block only ever
+// waits on bands that already started (no co-residency assumption between blocks).
+#define VERIFY_ROWS 8
+__device__ __forceinline__ uint2 lds_rec(const int2 *p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_rec(int2 *p, int mv, int epoch)
+{
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" :: "r"((unsigned)__cvta_generic_to_shared(p)), "r"(mv), "r"(epoch) : "memory");
+}
+
 template <bool QPRED>
-__global__ void __launch_bounds__(32 * VERIFY_WARPS, 8)
+__global__ void __launch_bounds__(32 * VERIFY_ROWS, 2)
 me_verify_kernel(LaGeom g, MeParams P)
 {
-    __shared__ GroupSmem sm_all[VERIFY_WARPS];
-    GroupSmem &sm = sm_all[threadIdx.x >> 5];
+    extern __shared__ __align__(16) uint8_t vsm[];
+    const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
+    GroupSmem &sm = ((GroupSmem *)vsm)[wrow];
+    int2 *srec = (int2 *)(vsm + VERIFY_ROWS * sizeof(GroupSmem));      // [VERIFY_ROWS][mb_w] {mv, epoch}
+    __shared__ int s_ticket;
     const MeJob &job = P.job[blockIdx.y];
-    const int lane = threadIdx.x & 31;
     const unsigned FULLM = 0xffffffffu;
+    const int nbands = (g.mb_h + VERIFY_ROWS - 1) / VERIFY_ROWS;
   for (;;) {
-    int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(job.ticket, 1);
-    ticket = __shfl_sync(FULLM, ticket, 0);
-    const int mb_y = g.mb_h - 1 - ticket;                 // bottom rows start first
-    if (mb_y < 0) return;
+    __syncthreads();                                       // everybody is done with the previous band's records
+    if (threadIdx.x == 0) s_ticket = atomicAdd(job.ticket, 1);
+    for (int i = lane; i < g.mb_w; i += 32) srec[wrow * g.mb_w + i] = make_int2(0, 0);   // epoch is never 0
+    __syncthreads();
+    const int ticket = s_ticket;
+    if (ticket >= nbands) return;
+    const int mb_y = g.mb_h - 1 - (ticket * VERIFY_ROWS + wrow);   // bottom band first, warp 0 = its bottom row
+    if (mb_y < 0) continue;
     const int T = max(1, P.bands);
     int slice_start = 0, slice_end = g.mb_h;
+#pragma unroll 1
     for (int i = 0; i < T; i++) {
         const int s = (g.mb_h * i + T / 2) / T, e = (g.mb_h * (i + 1) + T / 2) / T;
         if (mb_y >= s && mb_y < e) { slice_start = s; slice_end = e; }
@@ -760,9 +783,14 @@ me_verify_kernel(LaGeom g, MeParams P)
     const bool has_below = mb_y < slice_end - 1;
     const bool below_scanned = has_below && (mb_y + 1 <= start_y);
     const int epoch = P.epoch;
-    const int2 *below = job.rec + (mb_y + 1) * g.mb_w;
+    const bool below_local = wrow > 0;                     // the row below belongs to this block
+    const int2 *below = below_local ? srec + (wrow - 1) * g.mb_w : job.rec + (mb_y + 1) * g.mb_w;
     int2 *mine = job.rec + mb_y * g.mb_w;
+    int2 *mine_s = srec + wrow * g.mb_w;
+    const bool top = wrow == VERIFY_ROWS - 1;              // read by another block: publish to global memory too
     const int row0 = mb_y * g.mb_w;
+    auto ld_below = [&](int p) -> uint2 { return below_local ? lds_rec(below + p) : ld_rec2(below + p); };
+    auto publish = [&](int xcol, int mv) { sts_rec(mine_s + xcol, mv, epoch); if (top) st_rec2(mine + xcol, mv, epoch); };
 
     Mb<4> m;                                               // the whole warp on one MB: 8 candidates x 4 lanes
     m.gl = lane; m.slot = lane >> 2; m.r0 = (lane & 3) * 2;
@@ -776,9 +804,9 @@ me_verify_kernel(LaGeom g, MeParams P)
     auto below_fixed = [&](int p) -> bool { return !below_scanned || p < end_x || p > start_x || p < 0 || p >= g.mb_w; };
     auto below_wait = [&](int p) -> int {
         if (below_fixed(p)) return 0;
-        uint2 r = ld_rec2(below + p);
+        uint2 r = ld_below(p);
         unsigned ns = 32;
-        while ((int)r.y != epoch) { __nanosleep(ns); if (ns < 512) ns <<= 1; r = ld_rec2(below + p); }
+        while ((int)r.y != epoch) { __nanosleep(ns); if (ns < 256) ns <<= 1; r = ld_below(p); }
         return (int)r.x;
     };
 
@@ -794,7 +822,7 @@ me_verify_kernel(LaGeom g, MeParams P)
         const bool valid = xi >= end_x;
         int bl = 0; bool rdy = true;                       // row below at column xi-1
         if (valid && has_below && !below_fixed(xi - 1)) {
-            const uint2 r = ld_rec2(below + xi - 1);
+            const uint2 r = ld_below(xi - 1);
             rdy = (int)r.y == epoch; bl = (int)r.x;
         }
         int4 A = make_int4(0, 0, 0, 0); int G = 0;
@@ -822,7 +850,7 @@ me_verify_kernel(LaGeom g, MeParams P)
             int n = __ffs(~hb) - 1;
             if (n < 0) n = 32;
             if (n > 0) {
-                if (lane >= p && lane < p + n) st_rec2(mine + xi, G, epoch);
+                if (lane >= p && lane < p + n) publish(xi, G);
                 rm = __shfl_sync(FULLM, G, p + n - 1);
                 p += n; n_hit += n;
                 if (p >= 32) break;
@@ -843,7 +871,7 @@ me_verify_kernel(LaGeom g, MeParams P)
             // the next MB's source rows are fetched (it usually mismatches too where this one does)
             uint2 pre = make_uint2(0, 0);
             const bool repoll = lane > p && pollable && !rdy;
-            if (repoll) pre = ld_rec2(below + xi - 1);
+            if (repoll) pre = ld_below(xi - 1);
             if (mb_x - 1 >= end_x) {
                 const int pel = m.pel - 8 + m.r0 * g.lstride;
                 nfe0 = load8u(job.fenc + pel); nfe1 = load8u(job.fenc + pel + g.lstride);
@@ -883,7 +911,7 @@ me_verify_kernel(LaGeom g, MeParams P)
             if (lane == 0) {
                 job.mvs[mb_xy] = out_mv;
                 job.mv_costs[mb_xy] = out_cost;
-                st_rec2(mine + mb_x, out_mv, epoch);
+                publish(mb_x, out_mv);
             }
             if (lane == p) G = out_mv;                     // the next lane's right neighbour
             if (repoll && (int)pre.y == epoch) { rdy = true; bl = (int)pre.x; }
@@ -897,7 +925,7 @@ me_verify_kernel(LaGeom g, MeParams P)
             c0 = nc0; c1 = nc1;
             right_mv = rm;
             x -= p; ns = 32;
-        } else { __nanosleep(ns); if (ns < 512) ns <<= 1; }
+        } else { __nanosleep(below_local ? 20 : ns); if (ns < 256) ns <<= 1; }
     }
     if (P.stats && lane == 0) { atomicAdd(P.stats, n_hit); atomicAdd(P.stats + 1, n_miss); }
   }
@@ -907,10 +935,18 @@ me_verify_kernel(LaGeom g, MeParams P)
 int launch_me_verify(cudaStream_t st, const LaGeom &g, const MeParams &p)
 {
     if (p.njobs <= 0) return 0;
-    const int rows = p.rows_in_flight > 0 && p.rows_in_flight < g.mb_h ? p.rows_in_flight : g.mb_h;
-    const dim3 grid((rows + VERIFY_WARPS - 1) / VERIFY_WARPS, p.njobs);
-    if (p.subpel_refine >= 3) me_verify_kernel<true><<<grid, 32 * VERIFY_WARPS, 0, st>>>(g, p);
-    else me_verify_kernel<false><<<grid, 32 * VERIFY_WARPS, 0, st>>>(g, p);
+    // every band of a search resident at once: the row pipeline is up to mb_w/2 rows deep
+    const dim3 grid((g.mb_h + VERIFY_ROWS - 1) / VERIFY_ROWS, p.njobs);
+    const size_t smem = VERIFY_ROWS * sizeof(GroupSmem) + (size_t)VERIFY_ROWS * g.mb_w * sizeof(int2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(me_verify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(me_verify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_done = true;
+    }
+    if (smem > 160 * 1024) { set_error("frame too wide for the verification kernel (%d MBs)", g.mb_w); return -1; }
+    if (p.subpel_refine >= 3) me_verify_kernel<true><<<grid, 32 * VERIFY_ROWS, smem, st>>>(g, p);
+    else me_verify_kernel<false><<<grid, 32 * VERIFY_ROWS, smem, st>>>(g, p);
     XV_LAUNCH_CHECK();
     return 0;
 }
