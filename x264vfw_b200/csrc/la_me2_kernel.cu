@@ -589,25 +589,12 @@ __device__ __forceinline__ int scale_mv(int mv, int num, int den, int lim)
     const int sx = __float2int_rn((float)mv_x(mv) * f), sy = __float2int_rn((float)mv_y(mv) * f);
     return mv_pack(clip3i(sx, -lim, lim - 1), clip3i(sy, -lim, lim - 1));     // stay inside the mv cost table
 }
-template <int LPS, bool QPRED>
-__global__ void __launch_bounds__(32 * PASS_WARPS, 10)
-me_pass_kernel(LaGeom g, MeParams P, int pass)
+// where an MB sits in the scan: which neighbours exist, whether it is scanned at all
+struct MbPos { int mb_x, mb_y, mb_xy; bool act, has_below, has_r, has_bl, has_br; };
+__device__ __forceinline__ MbPos mb_pos(const LaGeom &g, const MeParams &P, int mb_x, int mb_y, bool in_range)
 {
-    constexpr int GL = Mb<LPS>::GL, NG = 32 / GL, RPL = Mb<LPS>::RPL;
-    __shared__ GroupSmem sm_all[PASS_WARPS][NG];
-    const MeJob &job = P.job[blockIdx.y];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gi = lane / GL;
-    GroupSmem &sm = sm_all[warp][gi];
     const int T = max(1, P.bands);
     const int start_x = g.mb_w - 2 + P.do_edges, end_x = 1 - P.do_edges;
-    const int ncols = start_x - end_x + 1;
-    const int chunks = (ncols + NG - 1) / NG;
-    const int wid = blockIdx.x * PASS_WARPS + warp;
-    if (wid >= chunks * g.mb_h) return;
-    const int mb_y = wid / chunks, k = (wid - mb_y * chunks) * NG + gi;
-    const int mb_x = start_x - k;
-
     int slice_start = 0, slice_end = g.mb_h;
 #pragma unroll 1
     for (int i = 0; i < T; i++) {
@@ -615,31 +602,33 @@ me_pass_kernel(LaGeom g, MeParams P, int pass)
         if (mb_y >= s && mb_y < e) { slice_start = s; slice_end = e; }
     }
     const int start_y = min(slice_end - 1, g.mb_h - 2 + P.do_edges), end_y = max(slice_start, 1 - P.do_edges);
-    const bool act = mb_y <= start_y && mb_y >= end_y && k < ncols;
-    const bool has_below = mb_y < slice_end - 1;
-    const int mb_xy = mb_x + mb_y * g.mb_w;
-
-    // ---- the four inputs (zero where the neighbour does not exist) ----
-    const bool has_r = mb_x < g.mb_w - 1, has_bl = has_below && mb_x > 0, has_br = has_below && has_r;
-    int4 in = make_int4(0, 0, 0, 0);           // right, below, below-left, below-right
-    const int *src = pass == 0 ? job.guess : job.mvs;
-    if (act && src) {
-        if (has_r) in.x = __ldcg(src + mb_xy + 1);
-        if (has_below) in.y = __ldcg(src + mb_xy + g.mb_w);
-        if (has_bl) in.z = __ldcg(src + mb_xy + g.mb_w - 1);
-        if (has_br) in.w = __ldcg(src + mb_xy + g.mb_w + 1);
-        if (pass == 0 && job.guess_num != job.guess_den) {
-            in.x = scale_mv(in.x, job.guess_num, job.guess_den, P.mv_range2); in.y = scale_mv(in.y, job.guess_num, job.guess_den, P.mv_range2);
-            in.z = scale_mv(in.z, job.guess_num, job.guess_den, P.mv_range2); in.w = scale_mv(in.w, job.guess_num, job.guess_den, P.mv_range2);
-        }
+    MbPos q;
+    q.mb_x = mb_x; q.mb_y = mb_y; q.mb_xy = mb_x + mb_y * g.mb_w;
+    q.act = in_range && mb_y <= start_y && mb_y >= end_y && mb_x <= start_x && mb_x >= end_x;
+    q.has_below = mb_y < slice_end - 1;
+    q.has_r = mb_x < g.mb_w - 1; q.has_bl = q.has_below && mb_x > 0; q.has_br = q.has_below && q.has_r;
+    return q;
+}
+// the four inputs (right, below, below-left, below-right; zero where the neighbour does not exist)
+__device__ __forceinline__ int4 mb_inputs(const LaGeom &g, const MbPos &q, const int *src)
+{
+    int4 in = make_int4(0, 0, 0, 0);
+    if (q.act && src) {
+        if (q.has_r) in.x = __ldcg(src + q.mb_xy + 1);
+        if (q.has_below) in.y = __ldcg(src + q.mb_xy + g.mb_w);
+        if (q.has_bl) in.z = __ldcg(src + q.mb_xy + g.mb_w - 1);
+        if (q.has_br) in.w = __ldcg(src + q.mb_xy + g.mb_w + 1);
     }
-    bool need = act;
-    if (pass > 0 && act) {
-        const int4 a = __ldcg(job.assumed + mb_xy);
-        need = a.x != in.x || a.y != in.y || a.z != in.z || a.w != in.w;
-    }
-    if (!__any_sync(FULL, need)) return;
+    return in;
+}
 
+// One MB per group, searched from the inputs `in` (warp-uniform call; `need` is per group).
+template <int LPS, bool QPRED>
+__device__ __forceinline__ void pass_search_store(const LaGeom &g, const MeParams &P, const MeJob &job, GroupSmem &sm, int lane,
+                                                  const MbPos &q, const int4 in, const bool need, int pass)
+{
+    constexpr int GL = Mb<LPS>::GL, RPL = Mb<LPS>::RPL;
+    const int mb_x = q.mb_x, mb_y = q.mb_y;
     Mb<LPS> m;
     m.gl = lane % GL; m.slot = m.gl / LPS; m.r0 = (m.gl % LPS) * RPL;
     m.stride = g.lstride;
@@ -658,15 +647,15 @@ me_pass_kernel(LaGeom g, MeParams P, int pass)
 
     // ---- reverse-order MV prediction, as in the sequential scan ----
     int c0, c1, c2, c3, i_mvc;
-    if (has_below) {
-        c0 = has_r ? in.x : in.y;
-        c1 = has_r ? in.y : (has_bl ? in.z : 0);
-        c2 = has_r ? (has_bl ? in.z : in.w) : 0;
-        c3 = (has_r && has_bl) ? in.w : 0;
-        i_mvc = (int)has_r + 1 + (int)has_bl + (int)has_br;
+    if (q.has_below) {
+        c0 = q.has_r ? in.x : in.y;
+        c1 = q.has_r ? in.y : (q.has_bl ? in.z : 0);
+        c2 = q.has_r ? (q.has_bl ? in.z : in.w) : 0;
+        c3 = (q.has_r && q.has_bl) ? in.w : 0;
+        i_mvc = (int)q.has_r + 1 + (int)q.has_bl + (int)q.has_br;
     } else {
-        c0 = has_r ? in.x : 0; c1 = c2 = c3 = 0;
-        i_mvc = (int)has_r;
+        c0 = q.has_r ? in.x : 0; c1 = c2 = c3 = 0;
+        i_mvc = (int)q.has_r;
     }
     if (!need) { c0 = c1 = c2 = c3 = 0; i_mvc = 0; }
     const int mvc[4][2] = {{mv_x(c0), mv_y(c0)}, {mv_x(c1), mv_y(c1)}, {mv_x(c2), mv_y(c2)}, {mv_x(c3), mv_y(c3)}};
@@ -701,11 +690,45 @@ me_pass_kernel(LaGeom g, MeParams P, int pass)
         }
     }
     if (need && m.gl == 0) {
-        job.mvs[mb_xy] = out_mv;
-        job.mv_costs[mb_xy] = out_cost;
-        job.assumed[mb_xy] = in;
+        job.mvs[q.mb_xy] = out_mv;
+        job.mv_costs[q.mb_xy] = out_cost;
+        job.assumed[q.mb_xy] = in;
         if (P.stats) atomicAdd(P.stats + 2 + min(pass, 3), 1);
     }
+}
+
+// 4 horizontally adjacent MBs per warp.  pass 0: every MB, inputs from the guess field; later
+// passes: inputs from the current results, a warp leaves at once unless one of its MBs saw its
+// inputs change.  (Collecting the MBs to re-search per 256-MB tile and searching them with a
+// small grid was tried: same frame rate within noise, longer when they cluster, so not kept.)
+template <int LPS, bool QPRED>
+__global__ void __launch_bounds__(32 * PASS_WARPS, 10)
+me_pass_kernel(LaGeom g, MeParams P, int pass)
+{
+    constexpr int GL = Mb<LPS>::GL, NG = 32 / GL;
+    __shared__ GroupSmem sm_all[PASS_WARPS][NG];
+    const MeJob &job = P.job[blockIdx.y];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gi = lane / GL;
+    const int start_x = g.mb_w - 2 + P.do_edges, end_x = 1 - P.do_edges;
+    const int ncols = start_x - end_x + 1;
+    const int chunks = (ncols + NG - 1) / NG;
+    const int wid = blockIdx.x * PASS_WARPS + warp;
+    if (wid >= chunks * g.mb_h) return;
+    const int mb_y = wid / chunks, k = (wid - mb_y * chunks) * NG + gi;
+    const MbPos q = mb_pos(g, P, start_x - k, mb_y, k < ncols);
+    int4 in = mb_inputs(g, q, pass == 0 ? job.guess : job.mvs);
+    if (pass == 0 && job.guess_num != job.guess_den) {
+        in.x = scale_mv(in.x, job.guess_num, job.guess_den, P.mv_range2); in.y = scale_mv(in.y, job.guess_num, job.guess_den, P.mv_range2);
+        in.z = scale_mv(in.z, job.guess_num, job.guess_den, P.mv_range2); in.w = scale_mv(in.w, job.guess_num, job.guess_den, P.mv_range2);
+    }
+    bool need = q.act;
+    if (pass > 0 && q.act) {
+        const int4 a = __ldcg(job.assumed + q.mb_xy);
+        need = a.x != in.x || a.y != in.y || a.z != in.z || a.w != in.w;
+    }
+    if (!__any_sync(FULL, need)) return;
+    pass_search_store<LPS, QPRED>(g, P, job, sm_all[warp][gi], lane, q, in, need, pass);
 }
 
 int launch_me_pass(cudaStream_t st, const LaGeom &g, const MeParams &p, int pass)
