@@ -99,6 +99,16 @@ COST_SEQUENCE = [(0, 0, 0), (0, 1, 1), (1, 2, 2), (0, 2, 2), (0, 2, 1), (2, 3, 3
     ("superfast", (320, 192), {"b_mbtree": 1}),
     ("medium", (320, 192), {"weightb": 0, "aq_mode": 0, "weightp": 0}),
     ("medium", (64, 48), {"mv_range": 32}),
+    # geometry corners of the search kernels: 1x1 / 2x2 / 3x2 MB frames (every MB is an edge MB), one
+    # very wide row band, a tall narrow frame (more rows than columns: deep row pipeline, short rows)
+    ("medium", (16, 16), {}),
+    ("medium", (32, 32), {}),
+    ("medium", (48, 32), {}),
+    ("medium", (1280, 48), {}),
+    ("medium", (48, 400), {}),
+    ("veryslow", (320, 192), {}),
+    ("medium", (320, 192), {"b_mbtree": 0}),
+    ("superfast", (330, 186), {"lookahead_threads": 4}),
 ])
 def test_frame_cost_matches_oracle(preset, size, over):
     """slicetype_frame_cost on explicit (p0,p1,b) triples in a fixed order: MVs, MV costs,
@@ -180,6 +190,12 @@ def compare_sessions(preset, w, h, n, clip_kw, over, in_csp=0):
     ("ultrafast", {}),
     ("medium", {"rc_lookahead": 12, "b_pyramid": 0, "b_adapt": 0, "keyint_max": 20, "keyint_min": 2}),
     ("medium", {"rc_lookahead": 10, "open_gop": 1, "keyint_max": 24, "keyint_min": 2, "bframes": 5}),
+    ("veryslow", {"rc_lookahead": 16, "keyint_max": 60, "keyint_min": 5}),
+    ("medium", {"rc_lookahead": 12, "b_pyramid": 1, "keyint_max": 40, "keyint_min": 4}),
+    # tune zerolatency: no lookahead, no B-frames, no mb-tree
+    ("medium", {"rc_lookahead": 0, "bframes": 0, "b_mbtree": 0, "keyint_max": 30, "keyint_min": 3}),
+    ("medium", {"rc_lookahead": 12, "scenecut": 0, "keyint_max": 40, "keyint_min": 4}),
+    ("fast", {"rc_lookahead": 12, "lookahead_threads": 3, "keyint_max": 40, "keyint_min": 4}),
 ])
 def test_session_decisions_match_oracle(preset, over):
     """Whole sessions: frame types, coded order, rate-control costs and per-MB qp offsets."""

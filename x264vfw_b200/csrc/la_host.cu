@@ -1574,10 +1574,23 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         if (borrowed) {
             XV_CUDA_OK(cudaEventRecord(la->ev_csp, la->st_io));
             if (iop) cudaEventRecord(la->io_ev[3], la->st_io);
-            if (conv_pic)
-                for (int i = 0; i < geo_out.i_plane; i++)
-                    XV_CUDA_OK(cudaMemcpy2DAsync(conv_pic->plane[i], conv_pic->i_stride[i], planes.plane[i], planes.i_stride[i], geo_out.i_stride[i], chroma_rows(out420, i),
-                                                 cudaMemcpyDeviceToHost, la->st_io));
+            if (conv_pic) {
+                // tight planes that follow each other on both sides (the usual conv_pic from
+                // x264_picture_alloc / picture_layout) go back as ONE linear copy
+                bool linear = true;
+                size_t total = 0;
+                for (int i = 0; i < geo_out.i_plane; i++) {
+                    const size_t bytes = (size_t)geo_out.i_stride[i] * chroma_rows(out420, i);
+                    linear = linear && conv_pic->i_stride[i] == geo_out.i_stride[i] && planes.i_stride[i] == geo_out.i_stride[i] &&
+                             conv_pic->plane[i] == conv_pic->plane[0] + total && planes.plane[i] == planes.plane[0] + total;
+                    total += bytes;
+                }
+                if (linear) XV_CUDA_OK(cudaMemcpyAsync(conv_pic->plane[0], planes.plane[0], total, cudaMemcpyDeviceToHost, la->st_io));
+                else
+                    for (int i = 0; i < geo_out.i_plane; i++)
+                        XV_CUDA_OK(cudaMemcpy2DAsync(conv_pic->plane[i], conv_pic->i_stride[i], planes.plane[i], planes.i_stride[i], geo_out.i_stride[i], chroma_rows(out420, i),
+                                                     cudaMemcpyDeviceToHost, la->st_io));
+            }
             if (iop) cudaEventRecord(la->io_ev[4], la->st_io);
             XV_CUDA_OK(cudaEventRecord(la->ev_io, la->st_io));
         }
