@@ -188,7 +188,7 @@ typedef struct x264vfw_cuda_la_params
     int   me_method;           /* analyse.i_me_method                                            */
     int   me_range;            /* analyse.i_me_range                                             */
     int   mv_range;            /* analyse.i_mv_range after level resolution                      */
-    int   aq_mode;             /* rc.i_aq_mode (0 or 1)                                          */
+    int   aq_mode;             /* rc.i_aq_mode: 0 off, 1 variance, 2 auto-variance, 3 biased     */
     float aq_strength;
     float qcompress;
     int   frame_reference;     /* i_frame_reference                                              */
@@ -199,6 +199,10 @@ typedef struct x264vfw_cuda_la_params
 
 /* x264 defaults + the preset deltas documented at config.c:1460-1498.  Returns 0 / -1. */
 int x264vfw_cuda_la_params_preset( x264vfw_cuda_la_params *p, const char *preset, int width, int height );
+/* [x264] x264_param_apply_tune reduced to the lookahead's fields; call after _params_preset
+ * (codec.c:1463 applies preset and tuning together).  film/none, animation, grain, stillimage,
+ * psnr, ssim, fastdecode, zerolatency, touhou.  Returns 0, -1 for an unknown name. */
+int x264vfw_cuda_la_params_tune( x264vfw_cuda_la_params *p, const char *tune );
 
 typedef struct x264vfw_cuda_la x264vfw_cuda_la;
 

@@ -877,6 +877,11 @@ static int frame_cost(orc_la *la, frame_t **frames, int p0, int p1, int b)
  * Works on the tight planes with clamped addressing == the mod-16 replicated frame
  * ([x264] x264_frame_expand_border_mod16).
  * ---------------------------------------------------------------------------------------- */
+/* x^(1/8).  [x264] x264_adaptive_quant_frame calls powf(x, 0.125f), whose last bit depends on the C
+ * library; three correctly rounded square roots are the same function up to that bit and are
+ * reproducible everywhere (CPU checker and GPU agree exactly). */
+static inline float pow_1_8(float x) { return sqrtf(sqrtf(sqrtf(x))); }
+
 static uint32_t block_var(const uint8_t *p, int stride, int pw, int ph, int x0, int y0, int bw, int bh, int shift,
                           uint64_t *fsum, uint64_t *fssd)
 {
@@ -903,7 +908,9 @@ static void adaptive_quant_frame(orc_la *la, frame_t *f, const uint8_t *y, int y
         for (int i = 0; i < la->mb_count; i++) { f->qp_offset[i] = f->qp_offset_aq[i] = 0; f->inv_qscale[i] = 256; }
         if (!p->weightp) return;
     }
-    const float strength = p->aq_strength * 1.0397f;
+    const int autovar = aq_on && (p->aq_mode == 2 || p->aq_mode == 3);   /* X264_AQ_AUTOVARIANCE, _BIASED */
+    float strength = p->aq_strength * 1.0397f;
+    float avg_adj = 0.f, avg_adj_pow2 = 0.f, bias_strength = 0.f;
     for (int my = 0; my < la->mb_h; my++)
         for (int mx = 0; mx < la->mb_w; mx++) {
             uint32_t energy = block_var(y, ys, w, h, 16 * mx, 16 * my, 16, 16, 8, &f->pixel_sum[0], &f->pixel_ssd[0]);
@@ -911,13 +918,33 @@ static void adaptive_quant_frame(orc_la *la, frame_t *f, const uint8_t *y, int y
                 energy += block_var(u, cs, cw, ch, cbw * mx, cbh * my, cbw, cbh, cshift, &f->pixel_sum[1], &f->pixel_ssd[1]);
                 energy += block_var(v, cs, cw, ch, cbw * mx, cbh * my, cbw, cbh, cshift, &f->pixel_sum[2], &f->pixel_ssd[2]);
             }
-            if (aq_on) {
+            int xy = mx + my * la->mb_w;
+            if (autovar) {
+                /* first loop of the auto-variance modes: qp_adj = (energy + 1)^(1/8), summed in MB order */
+                float qp_adj = pow_1_8((float)energy * 1.f + 1);
+                f->qp_offset[xy] = qp_adj;
+                avg_adj += qp_adj;
+                avg_adj_pow2 += qp_adj * qp_adj;
+            } else if (aq_on) {
                 float qp_adj = strength * (x264_log2(MAX(energy, 1)) - (14.427f + 2 * 0));
-                int xy = mx + my * la->mb_w;
                 f->qp_offset[xy] = f->qp_offset_aq[xy] = qp_adj;
                 f->inv_qscale[xy] = (uint16_t)x264_exp2fix8(qp_adj);
             }
         }
+    if (autovar) {
+        avg_adj /= la->mb_count;
+        avg_adj_pow2 /= la->mb_count;
+        strength = p->aq_strength * avg_adj;
+        avg_adj = avg_adj - 0.5f * (avg_adj_pow2 - 14.f) / avg_adj;
+        bias_strength = p->aq_strength;
+        for (int xy = 0; xy < la->mb_count; xy++) {
+            float qp_adj = f->qp_offset[xy];
+            if (p->aq_mode == 3) qp_adj = strength * (qp_adj - avg_adj) + bias_strength * (1.f - 14.f / (qp_adj * qp_adj));
+            else qp_adj = strength * (qp_adj - avg_adj);
+            f->qp_offset[xy] = f->qp_offset_aq[xy] = qp_adj;
+            f->inv_qscale[xy] = (uint16_t)x264_exp2fix8(qp_adj);
+        }
+    }
     for (int i = 0; i < 3; i++) {
         uint64_t ssd = f->pixel_ssd[i], sum = f->pixel_sum[i];
         int pw = 16 * la->mb_w >> (i && cf != 3), ph = 16 * la->mb_h >> (i && cf == 1);

@@ -45,7 +45,7 @@ typedef struct orc_la_params {
     int   me_method;           /* analyse.i_me_method (0 dia, 1 hex, ...)                    */
     int   me_range;            /* analyse.i_me_range                                         */
     int   mv_range;            /* analyse.i_mv_range after level resolution (512 for level>=3.1) */
-    int   aq_mode;             /* rc.i_aq_mode (0 or 1 supported)                            */
+    int   aq_mode;             /* rc.i_aq_mode: 0 off, 1 variance, 2 auto-variance, 3 auto-variance biased                            */
     float aq_strength;
     float qcompress;
     int   frame_reference;     /* i_frame_reference                                          */

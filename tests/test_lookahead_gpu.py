@@ -42,12 +42,33 @@ def test_params_presets_agree_with_oracle():
             assert getattr(a, name) == getattr(b, name), (preset, name)
 
 
-@pytest.mark.parametrize("size", [(128, 96), (320, 192), (330, 186)])
-def test_frame_preparation_matches_oracle(size):
-    """AQ statistics, qp offsets, inverse qscale and lowres planes of every put frame."""
+def test_tunes_only_touch_the_documented_fields():
+    from x264vfw_b200 import lookahead
+    base = lookahead.params_preset("medium", 1920, 1080)
+    want = {"film": {}, "animation": {"frame_reference": 6, "aq_strength": 0.6, "bframes": 5},
+            "grain": {"aq_strength": 0.5, "qcompress": 0.8}, "stillimage": {"aq_strength": 1.2},
+            "psnr": {"aq_mode": 0, "b_psy": 0}, "ssim": {"aq_mode": 2, "b_psy": 0},
+            "fastdecode": {"weightb": 0, "weightp": 0}, "zerolatency": {"rc_lookahead": 0, "bframes": 0, "b_mbtree": 0},
+            "touhou": {"frame_reference": 6, "aq_strength": 1.3}}
+    for tune, delta in want.items():
+        p = lookahead.params_tune(lookahead.params_preset("medium", 1920, 1080), tune)
+        for name, _ in p._fields_:
+            exp = delta.get(name, getattr(base, name))
+            got = getattr(p, name)
+            assert (abs(got - exp) < 1e-6) if isinstance(exp, float) else got == exp, (tune, name, got, exp)
+    with pytest.raises(ValueError):
+        lookahead.params_tune(lookahead.params_preset("medium", 64, 64), "nosuchtune")
+
+
+@pytest.mark.parametrize("size,over", [((128, 96), {}), ((320, 192), {}), ((330, 186), {}),
+                                       ((320, 192), {"aq_mode": 2}), ((330, 186), {"aq_mode": 3, "aq_strength": 0.8}),
+                                       ((320, 192), {"aq_mode": 0})])
+def test_frame_preparation_matches_oracle(size, over):
+    """AQ statistics, qp offsets, inverse qscale and lowres planes of every put frame (aq-mode 0, 1
+    and the auto-variance modes 2 / 3, whose frame averages are float sums in MB order)."""
     w, h = size
     frames = to_i420(make_clip(w, h, 4, cuts=(2,), flash=None), w, h)
-    orc, gpu = open_pair("medium", w, h, rc_lookahead=10)
+    orc, gpu = open_pair("medium", w, h, rc_lookahead=10, **over)
     try:
         for f in frames:
             orc.put_i420(f)
@@ -196,6 +217,9 @@ def compare_sessions(preset, w, h, n, clip_kw, over, in_csp=0):
     ("medium", {"rc_lookahead": 0, "bframes": 0, "b_mbtree": 0, "keyint_max": 30, "keyint_min": 3}),
     ("medium", {"rc_lookahead": 12, "scenecut": 0, "keyint_max": 40, "keyint_min": 4}),
     ("fast", {"rc_lookahead": 12, "lookahead_threads": 3, "keyint_max": 40, "keyint_min": 4}),
+    # tune ssim (aq-mode 2, no psy) and the biased auto-variance mode
+    ("medium", {"rc_lookahead": 12, "aq_mode": 2, "b_psy": 0, "keyint_max": 40, "keyint_min": 4}),
+    ("medium", {"rc_lookahead": 12, "aq_mode": 3, "keyint_max": 40, "keyint_min": 4}),
 ])
 def test_session_decisions_match_oracle(preset, over):
     """Whole sessions: frame types, coded order, rate-control costs and per-MB qp offsets."""

@@ -1323,6 +1323,35 @@ int x264vfw_cuda_la_params_preset(x264vfw_cuda_la_params *p, const char *preset,
     return 0;
 }
 
+int x264vfw_cuda_la_params_tune(x264vfw_cuda_la_params *p, const char *tune)
+{
+    // [x264] x264_param_apply_tune reduced to the fields the lookahead reads (the tunings x264vfw
+    // offers in its configuration dialog, config.c "Tuning"); apply after the preset
+    if (!p || !tune) return -1;
+    if (!strcmp(tune, "film") || !strcmp(tune, "none") || !*tune) {
+    } else if (!strcmp(tune, "animation")) {
+        p->frame_reference = p->frame_reference > 1 ? p->frame_reference * 2 : 1;
+        p->aq_strength = 0.6f; p->bframes += 2;
+    } else if (!strcmp(tune, "grain")) {
+        p->aq_strength = 0.5f; p->qcompress = 0.8f;
+    } else if (!strcmp(tune, "stillimage")) {
+        p->aq_strength = 1.2f;
+    } else if (!strcmp(tune, "psnr")) {
+        p->aq_mode = 0; p->b_psy = 0;
+    } else if (!strcmp(tune, "ssim")) {
+        p->aq_mode = 2; p->b_psy = 0;
+    } else if (!strcmp(tune, "fastdecode")) {
+        p->weightb = 0; p->weightp = 0;
+    } else if (!strcmp(tune, "zerolatency")) {
+        p->rc_lookahead = 0; p->bframes = 0; p->b_mbtree = 0;
+    } else if (!strcmp(tune, "touhou")) {
+        p->frame_reference = p->frame_reference > 1 ? p->frame_reference * 2 : 1;
+        p->aq_strength = 1.3f;
+    } else { set_error("unknown tune %s", tune); return -1; }
+    if (p->bframes > BMAX) p->bframes = BMAX;
+    return 0;
+}
+
 int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *params, int device,
                          int in_csp, int out_csp, int colmatrix, int fullrange, int keep_frames)
 {
@@ -1343,6 +1372,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (p.rc_lookahead > LMAX) p.rc_lookahead = LMAX;
     if (p.keyint_min <= 0) { int fps = p.fps_num / (p.fps_den > 0 ? p.fps_den : 1); p.keyint_min = p.keyint_max / 10 < fps ? p.keyint_max / 10 : fps; }
     if (p.chroma_format < 0 || p.chroma_format > 3) { set_error("bad chroma_format"); delete la; return -1; }
+    if (p.aq_mode < 0 || p.aq_mode > 3) { set_error("bad aq_mode %d (0 off, 1 variance, 2 auto-variance, 3 auto-variance biased)", p.aq_mode); delete la; return -1; }
     la->device = device; la->in_csp = in_csp; la->out_csp = out_csp; la->colmatrix = colmatrix; la->fullrange = fullrange;
     la->keep_frames = keep_frames;
     if (((in_csp & X264VFW_CUDA_CSP_MASK) == X264VFW_CUDA_CSP_YUYV || (in_csp & X264VFW_CUDA_CSP_MASK) == X264VFW_CUDA_CSP_UYVY) && out_csp == X264VFW_CUDA_OUT_I444)
@@ -1621,6 +1651,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     aq.u = planar_yuv ? planes.plane[1] : nullptr; aq.v = planar_yuv ? planes.plane[2] : nullptr; aq.c_stride = planes.i_stride[1];
     aq.chroma_format = planar_yuv ? la->p.chroma_format : 0;
     aq.aq_on = aq_on; aq.strength = la->p.aq_strength * 1.0397f;
+    aq.aq_mode = la->p.aq_mode; aq.aq_strength = la->p.aq_strength;
     aq.qp_offset = f->qp_offset; aq.qp_offset_aq = f->qp_offset_aq; aq.inv_qscale = f->inv_qscale;
     aq.stats = f->stats; aq.log2_lut = la->d_log2_lut; aq.exp2_lut = la->d_exp2_lut;
     { ProfScope ps(la, K_AQ); if (launch_aq(la->st, la->g, aq) < 0) return -1; }

@@ -104,7 +104,11 @@ aq_kernel(LaGeom g, AqJob job)
             st[pl] = sum; st[3 + pl] = ssd;
             if (pl == 0 || cf) energy += ssd - (uint32_t)(((unsigned long long)sum * sum) >> (pl ? cshift : 8));
         }
-        if (job.aq_on) {
+        if (job.aq_on && job.aq_mode >= 2) {
+            // auto-variance modes, first loop: (energy + 1)^(1/8) as three correctly rounded square
+            // roots (see the CPU checker); aq_auto_kernel finishes the frame
+            job.qp_offset[idx] = sqrtf(sqrtf(sqrtf((float)energy * 1.f + 1)));
+        } else if (job.aq_on) {
             float qp_adj = job.strength * (dev_log2(job.log2_lut, max(energy, 1u)) - (14.427f + 2 * 0));
             job.qp_offset[idx] = qp_adj;
             job.qp_offset_aq[idx] = qp_adj;
@@ -120,10 +124,50 @@ aq_kernel(LaGeom g, AqJob job)
     }
 }
 
+// [x264] x264_adaptive_quant_frame, X264_AQ_AUTOVARIANCE / _BIASED: the frame averages are float
+// sums taken in MB order, so ONE thread adds them in that order (out of shared memory, 8192 MBs
+// at a time); the second loop over the MBs is elementwise and uses the whole block.
+#define AQ_AUTO_CHUNK 8192
+__global__ void __launch_bounds__(1024)
+aq_auto_kernel(LaGeom g, AqJob job)
+{
+    __shared__ float buf[AQ_AUTO_CHUNK];
+    __shared__ float s_avg, s_strength;
+    float avg_adj = 0.f, avg_adj_pow2 = 0.f;
+    for (int base = 0; base < g.mb_count; base += AQ_AUTO_CHUNK) {
+        const int n = min(AQ_AUTO_CHUNK, g.mb_count - base);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) buf[i] = job.qp_offset[base + i];
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int i = 0; i < n; i++) { const float q = buf[i]; avg_adj += q; avg_adj_pow2 += q * q; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        avg_adj /= g.mb_count;
+        avg_adj_pow2 /= g.mb_count;
+        s_strength = job.aq_strength * avg_adj;
+        s_avg = avg_adj - 0.5f * (avg_adj_pow2 - 14.f) / avg_adj;
+    }
+    __syncthreads();
+    const float strength = s_strength, avg = s_avg, bias_strength = job.aq_strength;
+    for (int i = threadIdx.x; i < g.mb_count; i += blockDim.x) {
+        float qp_adj = job.qp_offset[i];
+        if (job.aq_mode == 3) qp_adj = strength * (qp_adj - avg) + bias_strength * (1.f - 14.f / (qp_adj * qp_adj));
+        else qp_adj = strength * (qp_adj - avg);
+        job.qp_offset[i] = qp_adj;
+        job.qp_offset_aq[i] = qp_adj;
+        job.inv_qscale[i] = (uint16_t)dev_exp2fix8(job.exp2_lut, qp_adj);
+    }
+}
+
 int launch_aq(cudaStream_t st, const LaGeom &g, const AqJob &job)
 {
     aq_kernel<<<(g.mb_count + 31) / 32, 32 * AQ_PARTS, 0, st>>>(g, job);
     XV_LAUNCH_CHECK();
+    if (job.aq_on && job.aq_mode >= 2) {
+        aq_auto_kernel<<<1, 1024, 0, st>>>(g, job);
+        XV_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -19,7 +19,8 @@ struct WeightDev { int on, scale, denom, offset; };
 struct AqJob {
     const uint8_t *y, *u, *v; int y_stride, c_stride;
     int chroma_format;            // 1: 4:2:0, 2: 4:2:2, 3: 4:4:4; 0: luma only
-    int aq_on; float strength;
+    int aq_on; float strength;    // strength: aq-mode 1 (already * 1.0397)
+    int aq_mode; float aq_strength; // aq-mode 2 / 3 (auto-variance): raw rc.f_aq_strength
     float *qp_offset, *qp_offset_aq; uint16_t *inv_qscale;
     unsigned long long *stats;    // [6]: sum[3], ssd[3] (raw, before mean removal)
     const float *log2_lut; const uint8_t *exp2_lut;

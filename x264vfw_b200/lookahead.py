@@ -60,6 +60,17 @@ lib.x264vfw_cuda_la_profile.argtypes = [C.c_void_p, C.c_int, _P(C.c_double), _P(
 KERNEL_CLASSES = ("csp", "aq", "lowres", "intra", "me", "finalize", "weights", "mbtree", "me_pass")
 
 
+lib.x264vfw_cuda_la_params_tune.restype = C.c_int
+lib.x264vfw_cuda_la_params_tune.argtypes = [_P(LaParams), C.c_char_p]
+
+
+def params_tune(p: LaParams, tune: str) -> LaParams:
+    """x264_param_apply_tune (codec.c:1463 passes the dialog's tuning with the preset)."""
+    if lib.x264vfw_cuda_la_params_tune(C.byref(p), tune.encode()) < 0:
+        raise ValueError(last_error())
+    return p
+
+
 def params_preset(preset: str, width: int, height: int, **over) -> LaParams:
     """x264_param_default_preset (codec.c:1463) reduced to the lookahead's fields; keyword
     overrides play the role of the extra command line (codec.c:1349)."""
