@@ -219,8 +219,14 @@ void x264vfw_cuda_la_close( x264vfw_cuda_la *la );
 /* One input frame in display order == one x264_encoder_encode( pic_in ) call.
  * src describes the frame like x264vfw_img_fill does; src_on_device selects host or device
  * pointers.  conv_pic (may be NULL) receives the converted planes in HOST memory -- what
- * codec->conv_pic holds for the CPU encoder.  Returns the number of decided frames waiting
- * in the output queue, or -1. */
+ * codec->conv_pic holds for the CPU encoder.  Both buffers are only borrowed for the call:
+ * the source has been read and conv_pic is complete when it returns.  Returns the number of
+ * decided frames waiting in the output queue, or -1.
+ * Like libx264 behind sync-lookahead, the session works on queued frames in a thread of its
+ * own while the caller moves the next frame: the frames that become decided because of frame n
+ * are published, deterministically, by the call for frame n + 2 (and all of them by _flush);
+ * the sequence of decisions never depends on timing.  X264VFW_CUDA_ASYNC=0 decides inside the
+ * call instead. */
 int x264vfw_cuda_la_put_frame( x264vfw_cuda_la *la, const x264vfw_cuda_image_t *src, int src_on_device,
                                x264vfw_cuda_image_t *conv_pic );
 /* End of stream (x264_encoder_encode with pic_in == NULL, codec.c:1755-1758,1848). */

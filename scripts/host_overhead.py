@@ -11,6 +11,7 @@ clip = SyntheticClip(W, H, n_frames=N, cuts=(15,), flash=None)
 HOST = int(os.environ.get("HOST", "0"))      # 1: pinned host frames in, converted planes out (the e2e path)
 if HOST:
     frames = [torch.from_numpy(clip.packed(i, "bgra")).pin_memory() for i in range(N)]
+    dev_frames = [f.cuda() for f in frames]
 else:
     frames = [torch.from_numpy(clip.packed(i, "bgra")).cuda() for i in range(N)]
 torch.cuda.synchronize()
@@ -23,7 +24,11 @@ def run(S, total=int(os.environ.get("TOTAL", "120"))):
         for i in range(total):
             if i == 60:
                 base[id(la)] = (la.counters(), time.perf_counter())
-            if HOST:
+            if HOST == 2:      # H2D only
+                la.put_frame(frames[i % N].numpy(), on_device=False)
+            elif HOST == 3:    # D2H only
+                la.put_frame(dev_frames[i % N].data_ptr(), on_device=True, conv_pic=conv[i & 1])
+            elif HOST:
                 la.put_frame(frames[i % N].numpy(), on_device=False, conv_pic=conv[i & 1])
             else:
                 la.put_frame(frames[i % N].data_ptr(), on_device=True)

@@ -22,6 +22,10 @@
 #include <chrono>
 #include <deque>
 #include <string>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
 #include <vector>
 #include <array>
 
@@ -166,10 +170,28 @@ struct La {
     std::vector<Frame *> by_index;       // display index -> frame (null when recycled)
     std::deque<Frame *> next;
     Frame *last_nonb = nullptr;
-    std::deque<Decision> outq;
-    std::vector<float *> qp_free;
+    std::deque<Decision> outq;           // produced by the decision logic (worker side)
+    std::deque<Decision> pubq;           // handed over to the caller (x264vfw_cuda_la_get_decision)
+    std::vector<float *> qp_free; std::mutex qp_mu;
+    // The decision that becomes due at put(n) runs on a per-session worker thread and is collected
+    // at put(n+1): the caller's wait for its own H2D / conversion / D2H (frames on which no
+    // decision is due would expose it) then overlaps the decision of the previous mini-GOP.
+    // Same decisions, one put later -- deterministic, like decide_lag.
+    std::thread worker; std::mutex mu; std::condition_variable cv;
+    bool wstop = false;
+    std::deque<std::array<long, 2>> jobs;       // {frame number, planes ring slot} submitted, not yet taken
+    long n_put = 0;                             // frames submitted by the caller
+    long processed = 0;                         // frames the worker is done with (incl. the decisions they made due)
+    std::deque<std::pair<long, Decision>> doneq; // decisions tagged with the frame whose arrival produced them
+    int werr = 0; std::string werr_msg;
+    int async = 1;
+    int io_depth = 2;                           // planes ring: frames the caller may run ahead of the worker
+    uint8_t *d_planes_ring[4] = {nullptr}; x264vfw_cuda_image_t planes_ring[4];
+    cudaEvent_t ev_csp_ring[4] = {nullptr}, ev_free_ring[4] = {nullptr};
+    std::mutex prof_mu;
     int n_input = 0;
-    uint64_t n_frame_cost = 0, n_mb_search = 0, n_launch = 0, n_sync = 0;
+    uint64_t n_frame_cost = 0, n_mb_search = 0, n_sync = 0;
+    std::atomic<uint64_t> n_launch{0};
     bool fail = false;   // set when a device call fails inside the value-returning helpers
     double t_put = 0, t_decide = 0, t_sync = 0, t_io = 0;   // host wall-clock seconds (diagnostics)
     uint64_t n_ondemand = 0, n_ondemand_jobs = 0, n_spec_jobs = 0;
@@ -193,11 +215,12 @@ static cudaEvent_t prof_event(La *la)
 }
 struct ProfScope {
     La *la; int cls; cudaStream_t st; cudaEvent_t a = nullptr;
-    ProfScope(La *l, int c, cudaStream_t s = nullptr) : la(l), cls(c), st(s ? s : l->st) { if (la->prof.on && c >= 0) { a = prof_event(la); cudaEventRecord(a, st); } }
-    ~ProfScope() { if (a) { cudaEvent_t b = prof_event(la); cudaEventRecord(b, st); la->prof.recs.push_back(ProfRec{cls, a, b}); } }
+    ProfScope(La *l, int c, cudaStream_t s = nullptr) : la(l), cls(c), st(s ? s : l->st) { if (la->prof.on && c >= 0) { std::lock_guard<std::mutex> lk(la->prof_mu); a = prof_event(la); cudaEventRecord(a, st); } }
+    ~ProfScope() { if (a) { std::lock_guard<std::mutex> lk(la->prof_mu); cudaEvent_t b = prof_event(la); cudaEventRecord(b, st); la->prof.recs.push_back(ProfRec{cls, a, b}); } }
 };
 static void prof_resolve(La *la)
 {
+    std::lock_guard<std::mutex> lk(la->prof_mu);
     // records of side-stream launches may still be in flight: keep those for the next round
     std::vector<ProfRec> keep;
     for (const ProfRec &r : la->prof.recs) {
@@ -1168,7 +1191,10 @@ static int slicetype_analyse(La *la, int intra_minigop)
 // ------------------------------------------------------------------------------------------
 static float *qp_staging(La *la)
 {
-    if (!la->qp_free.empty()) { float *p = la->qp_free.back(); la->qp_free.pop_back(); return p; }
+    {
+        std::lock_guard<std::mutex> lk(la->qp_mu);
+        if (!la->qp_free.empty()) { float *p = la->qp_free.back(); la->qp_free.pop_back(); return p; }
+    }
     float *p = nullptr;
     if (cudaMallocHost((void **)&p, (size_t)2 * la->g.mb_count * sizeof(float)) != cudaSuccess) { set_error("cudaMallocHost failed"); return nullptr; }
     return p;
@@ -1283,6 +1309,103 @@ static int decide_and_shift(La *la)
     return la->fail ? -1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Session worker.  put_frame only moves the caller's buffers (H2D, conversion, D2H on the I/O
+// stream) and queues the frame; everything that touches the lookahead state -- frame slot, AQ,
+// lowres planes, speculative searches, the decisions that become due -- runs here, in arrival
+// order.  The caller may run io_depth frames ahead (ring of converted-plane buffers), so its
+// wait for its own copies overlaps the decision of an earlier mini-GOP instead of adding to
+// it.  Decisions are published deterministically: put(n) returns what frames <= n - io_depth
+// made due, like [x264]'s own lookahead thread behind sync-lookahead.
+// ------------------------------------------------------------------------------------------
+// Frame f has been converted into `planes` (signalled by ev_csp on the I/O stream): [x264]
+// x264_adaptive_quant_frame, x264_frame_init_lowres, then the searches this frame enables.
+static int process_frame(La *la, Frame *f, const x264vfw_cuda_image_t &planes, cudaEvent_t ev_csp, cudaEvent_t ev_free)
+{
+    const int w = la->p.width, hgt = la->p.height;
+    if (ev_csp) XV_CUDA_OK(cudaStreamWaitEvent(la->st, ev_csp, 0));
+    // ---- [x264] x264_adaptive_quant_frame ----
+    const bool planar_yuv = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_I422 || la->out_csp == X264VFW_CUDA_OUT_I444;
+    const bool aq_on = la->p.aq_mode != 0 && la->p.aq_strength != 0;
+    AqJob aq;
+    aq.y = planes.plane[0]; aq.y_stride = planes.i_stride[0];
+    aq.u = planar_yuv ? planes.plane[1] : nullptr; aq.v = planar_yuv ? planes.plane[2] : nullptr; aq.c_stride = planes.i_stride[1];
+    aq.chroma_format = planar_yuv ? la->p.chroma_format : 0;
+    aq.aq_on = aq_on; aq.strength = la->p.aq_strength * 1.0397f;
+    aq.aq_mode = la->p.aq_mode; aq.aq_strength = la->p.aq_strength;
+    aq.qp_offset = f->qp_offset; aq.qp_offset_aq = f->qp_offset_aq; aq.inv_qscale = f->inv_qscale;
+    aq.stats = f->stats; aq.log2_lut = la->d_log2_lut; aq.exp2_lut = la->d_exp2_lut;
+    { ProfScope ps(la, K_AQ); if (launch_aq(la->st, la->g, aq) < 0) return -1; }
+    XV_CUDA_OK(cudaMemcpyAsync(f->h_stats, f->stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, la->st));
+    XV_CUDA_OK(cudaEventRecord(f->ev_stats, la->st));
+    // ---- [x264] x264_frame_init_lowres ----
+    LowresJob lj;
+    lj.y = planes.plane[0]; lj.y_stride = planes.i_stride[0]; lj.w = w; lj.h = hgt; lj.dst = f->lowres;
+    lj.luma_w = la->g.luma_w; lj.luma_h = la->g.luma_h; lj.lw = la->g.lw; lj.lh = la->g.lh;
+    lj.lstride = la->g.lstride; lj.lplane_bytes = la->g.lplane; lj.lorigin = la->g.lorigin;
+    lj.src_frame_bytes = 0; lj.dst_frame_bytes = 0;
+    { ProfScope ps(la, K_LOWRES); if (launch_lowres_init(la->st, lj, 1) < 0) return -1; }
+    la->n_launch += 2;
+    XV_CUDA_OK(cudaEventRecord(ev_free, la->st));           // the planes may be overwritten again
+    f->ready = true;
+    return speculate_searches(la, f);
+}
+
+static int run_due_decisions(La *la)
+{
+    const double t0 = now_s();
+    int rc = 0;
+    while ((int)la->next.size() > la->slicetype_length + la->decide_lag)
+        if (decide_and_shift(la) < 0) { rc = -1; break; }
+    la->t_decide += now_s() - t0;
+    return rc;
+}
+
+static void worker_main(La *la)
+{
+    cudaSetDevice(la->device);
+    for (;;) {
+        std::array<long, 2> job;
+        {
+            std::unique_lock<std::mutex> lk(la->mu);
+            la->cv.wait(lk, [&] { return la->wstop || !la->jobs.empty(); });
+            if (la->jobs.empty()) return;
+            job = la->jobs.front(); la->jobs.pop_front();
+        }
+        const int slot = (int)job[1];
+        // The decision that becomes due with frame n only looks at frames < n (decide_lag >= 1):
+        // run it first, and enqueue this frame's AQ / lowres / searches afterwards -- by then its
+        // conversion on the I/O stream has finished, so the main stream never waits for a copy.
+        // (When the conversion is already done -- device-resident sources -- the frame goes first,
+        // so that its searches start as early as possible.)
+        int rc = 0;
+        Frame *f = frame_get(la, (int)job[0]);
+        if (!f) rc = -1;
+        const bool converted = rc == 0 && cudaEventQuery(la->ev_csp_ring[slot]) == cudaSuccess;
+        if (rc == 0 && converted) rc = process_frame(la, f, la->planes_ring[slot], la->ev_csp_ring[slot], la->ev_free_ring[slot]);
+        if (rc == 0) { la->n_input = (int)job[0] + 1; la->next.push_back(f); rc = run_due_decisions(la); }
+        if (rc == 0 && !converted) rc = process_frame(la, f, la->planes_ring[slot], la->ev_csp_ring[slot], la->ev_free_ring[slot]);
+        std::lock_guard<std::mutex> lk(la->mu);
+        if (rc < 0 && !la->werr) { la->werr = -1; la->werr_msg = x264vfw_cuda_last_error(); }
+        while (!la->outq.empty()) { la->doneq.emplace_back(job[0], la->outq.front()); la->outq.pop_front(); }
+        la->processed = job[0] + 1;
+        la->cv.notify_all();
+    }
+}
+
+// Wait until the worker is done with `count` frames; then publish what frames <= upto made due.
+static int worker_wait(La *la, long count, long upto)
+{
+    if (!la->worker.joinable()) return 0;
+    std::unique_lock<std::mutex> lk(la->mu);
+    la->cv.wait(lk, [&] { return la->processed >= count; });
+    while (!la->doneq.empty() && la->doneq.front().first <= upto) { la->pubq.push_back(la->doneq.front().second); la->doneq.pop_front(); }
+    if (la->werr) { set_error("%s", la->werr_msg.c_str()); return -1; }
+    return 0;
+}
+// everything submitted so far is processed and published (white-box calls, flush, close)
+static int worker_join(La *la) { return worker_wait(la, la->n_put, la->n_put); }
+
 } // namespace xv
 
 using namespace xv;
@@ -1386,6 +1509,8 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_ME_VARIANT")) la->me_variant = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ME_PASSES")) { la->me_passes = atoi(e); if (la->me_passes < 1) la->me_passes = 1; if (la->me_passes > 4) la->me_passes = 4; }
     if (const char *e = getenv("X264VFW_CUDA_ME_GUESS")) la->me_guess = atoi(e);
+    if (const char *e = getenv("X264VFW_CUDA_ASYNC")) la->async = atoi(e);
+    if (const char *e = getenv("X264VFW_CUDA_IO_DEPTH")) { la->io_depth = atoi(e); if (la->io_depth < 1) la->io_depth = 1; if (la->io_depth > 4) la->io_depth = 4; }
     if (const char *e = getenv("X264VFW_CUDA_ME_ROWS")) la->me_rows = atoi(e);
     else la->me_rows = -1;   // resolved below once the geometry is known
     x264vfw_cuda_lowres_geom lg;
@@ -1434,7 +1559,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
                   cudaMemcpy(la->d_exp2_lut, e2, 64, cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&la->d_weight_buf, g.lplane + 64) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&la->ev_io, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&la->ev_io, cudaEventDisableTiming | (getenv("X264VFW_CUDA_BLOCKING_IO") ? cudaEventBlockingSync : 0)) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_csp, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_planes_free, cudaEventDisableTiming) == cudaSuccess &&
@@ -1478,6 +1603,17 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
         }
         for (int i = 0; i < 4; i++) { float *q = qp_staging(la); if (q) la->qp_free.push_back(q); }
     }
+    if (la->async && la->decide_lag >= 1 && !keep_frames) {
+        bool ok = cudaStreamCreateWithPriority(&la->st_io, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        for (int k = 0; k < la->io_depth && ok; k++) {
+            ok = cudaMalloc((void **)&la->d_planes_ring[k], la->d_planes_bytes + 256) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&la->ev_csp_ring[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&la->ev_free_ring[k], cudaEventDisableTiming) == cudaSuccess;
+            if (ok) x264vfw_cuda_picture_layout(&la->planes_ring[k], la->d_planes_ring[k], out_csp, p.width, p.height);
+        }
+        if (!ok) { set_error("lookahead allocation failed"); x264vfw_cuda_la_close((x264vfw_cuda_la *)la); return -1; }
+        la->worker = std::thread(worker_main, la);
+    }
     *pla = (x264vfw_cuda_la *)la;
     return 0;
 }
@@ -1487,6 +1623,11 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     La *la = (La *)h;
     if (!la) return;
     cudaSetDevice(la->device);
+    if (la->worker.joinable()) {
+        worker_join(la);
+        { std::lock_guard<std::mutex> lk(la->mu); la->wstop = true; la->cv.notify_all(); }
+        la->worker.join();
+    }
     if (getenv("X264VFW_CUDA_STATS")) {
         fprintf(stderr, "[x264vfw_cuda] frames %d searches asked for by (list,dist):", la->n_input);
         for (int l = 0; l < 2; l++) for (int d = 0; d <= la->p.bframes; d++) fprintf(stderr, " l%d/d%d=%llu", l, d + 1, (unsigned long long)la->n_logical[l][d]);
@@ -1511,6 +1652,9 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     for (cudaEvent_t e : la->prof.pool) cudaEventDestroy(e);
     for (Frame *f : la->pool) frame_free(f);
     for (Decision &d : la->outq) if (d.h_qp) cudaFreeHost(d.h_qp);
+    for (Decision &d : la->pubq) if (d.h_qp) cudaFreeHost(d.h_qp);
+    for (auto &pd : la->doneq) if (pd.second.h_qp) cudaFreeHost(pd.second.h_qp);
+    for (int k = 0; k < 4; k++) { cudaFree(la->d_planes_ring[k]); if (la->ev_csp_ring[k]) cudaEventDestroy(la->ev_csp_ring[k]); if (la->ev_free_ring[k]) cudaEventDestroy(la->ev_free_ring[k]); }
     for (float *q : la->qp_free) cudaFreeHost(q);
     cudaFree(la->d_cost_mv); cudaFree(la->d_log2_lut); cudaFree(la->d_exp2_lut); cudaFree(la->d_weight_buf);
     for (int e = 0; e <= ME_SIDE; e++) {
@@ -1555,9 +1699,21 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         XV_CUDA_OK(cudaStreamCreateWithPriority(&la->st_io, cudaStreamNonBlocking, prio_hi));
     }
-    Frame *f = frame_get(la, la->n_input);
-    if (!f) return -1;
-    la->n_input++;
+    const bool async = la->worker.joinable();
+    const long n = la->n_put;
+    const int slot = async ? (int)(n % la->io_depth) : 0;
+    if (async) {
+        planes = la->planes_ring[slot];
+        // the worker must be done with the frame that used this slot (its AQ / lowres kernels are
+        // then at least enqueued, ev_free_ring orders the conversion after them on the device)
+        if (n >= la->io_depth && worker_wait(la, n - la->io_depth + 1, n - la->io_depth) < 0) return -1;
+    }
+    Frame *f = nullptr;
+    if (!async) {
+        f = frame_get(la, la->n_input);
+        if (!f) return -1;
+        la->n_input++;
+    }
 
     const int out420 = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_NV12;
     x264vfw_cuda_image_t geo_out;
@@ -1565,7 +1721,9 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     // Stage 1 of a frame whose buffers are borrowed (host source and/or conv_pic) runs entirely
     // on the I/O stream -- H2D, conversion, D2H of the converted planes -- so that all of it
     // overlaps the decision logic below, which keeps the main stream to itself.
-    cudaStream_t st1 = borrowed ? la->st_io : la->st;
+    cudaStream_t st1 = (borrowed || async) ? la->st_io : la->st;
+    cudaEvent_t ev_free = async ? la->ev_free_ring[slot] : la->ev_planes_free, ev_csp = async ? la->ev_csp_ring[slot] : la->ev_csp;
+    const bool planes_in_use = async ? n >= la->io_depth : la->planes_busy;
     x264vfw_cuda_image_t dsrc = *src;
     dsrc.i_csp = la->in_csp;
     auto stage1 = [&]() -> int {
@@ -1573,7 +1731,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         if (iop && !la->io_ev[0]) for (int k = 0; k < 5; k++) cudaEventCreate(&la->io_ev[k]);
         if (iop) cudaEventRecord(la->io_ev[0], la->st_io);
         // the previous frame's AQ / lowres kernels read the planes this conversion overwrites
-        if (borrowed && la->planes_busy) XV_CUDA_OK(cudaStreamWaitEvent(la->st_io, la->ev_planes_free, 0));
+        if ((borrowed || async) && planes_in_use) XV_CUDA_OK(cudaStreamWaitEvent(la->st_io, ev_free, 0));
         if (iop) cudaEventRecord(la->io_ev[1], la->st_io);
         if (host_src) {
             x264vfw_cuda_image_t geo;
@@ -1601,8 +1759,8 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
             { ProfScope ps(la, K_CSP, st1); if (convert_device_public(st1, la->out_csp, la->colmatrix, la->fullrange, la->ext, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
             la->n_launch++;
         }
-        if (borrowed) {
-            XV_CUDA_OK(cudaEventRecord(la->ev_csp, la->st_io));
+        if (borrowed || async) {
+            XV_CUDA_OK(cudaEventRecord(ev_csp, la->st_io));
             if (iop) cudaEventRecord(la->io_ev[3], la->st_io);
             if (conv_pic) {
                 // tight planes that follow each other on both sides (the usual conv_pic from
@@ -1627,7 +1785,23 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         return 0;
     };
     // ---- 1. borrowed buffers: stage 1 goes first, on the I/O stream ----
-    if (borrowed && stage1() < 0) return -1;
+    if ((borrowed || async) && stage1() < 0) return -1;
+    if (async) {
+        // hand the frame to the session worker; wait for the borrowed buffers only
+        {
+            std::lock_guard<std::mutex> lk(la->mu);
+            la->jobs.push_back({n, (long)slot});
+            la->cv.notify_all();
+        }
+        la->n_put++;
+        la->t_put += now_s() - t_begin;
+        if (borrowed) { const double t0 = now_s(); XV_CUDA_OK(cudaEventSynchronize(la->ev_io)); la->t_io += now_s() - t0; }
+        if (borrowed && la->d_me_stats && la->io_ev[0]) {
+            for (int k = 0; k < 4; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, la->io_ev[k], la->io_ev[k + 1]) == cudaSuccess) la->io_ms[k] += ms; }
+            la->io_n++;
+        }
+        return (int)la->pubq.size();
+    }
 
     // ---- 2. the decision that became due (deferred by decide_lag frames) ----
     double t_dec = 0;
@@ -1685,7 +1859,9 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         for (int k = 0; k < 4; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, la->io_ev[k], la->io_ev[k + 1]) == cudaSuccess) la->io_ms[k] += ms; }
         la->io_n++;
     }   // caller's buffers are borrowed for the call only
-    return (int)la->outq.size();
+    la->n_put++;
+    while (!la->outq.empty()) { la->pubq.push_back(la->outq.front()); la->outq.pop_front(); }
+    return (int)la->pubq.size();
 }
 
 int x264vfw_cuda_la_flush(x264vfw_cuda_la *h)
@@ -1693,6 +1869,7 @@ int x264vfw_cuda_la_flush(x264vfw_cuda_la *h)
     La *la = (La *)h;
     if (!la) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
+    if (worker_join(la) < 0) return -1;
     // decisions deferred by decide_lag still see exactly the frames upstream would have had
     while ((int)la->next.size() > la->slicetype_length)
         if (decide_and_shift(la) < 0) return -1;
@@ -1700,20 +1877,21 @@ int x264vfw_cuda_la_flush(x264vfw_cuda_la *h)
     while (!la->next.empty())
         if (decide_and_shift(la) < 0) { la->flushing = false; return -1; }
     la->flushing = false;
-    return (int)la->outq.size();
+    while (!la->outq.empty()) { la->pubq.push_back(la->outq.front()); la->outq.pop_front(); }
+    return (int)la->pubq.size();
 }
 
 int x264vfw_cuda_la_get_decision(x264vfw_cuda_la *h, x264vfw_cuda_la_decision *d, float *qp_offset, float *qp_offset_aq)
 {
     La *la = (La *)h;
     if (!la || !d) return -1;
-    if (la->outq.empty()) return 0;
-    Decision &q = la->outq.front();
+    if (la->pubq.empty()) return 0;
+    Decision &q = la->pubq.front();
     *d = q.d;
     if (qp_offset) memcpy(qp_offset, q.h_qp, la->g.mb_count * sizeof(float));
     if (qp_offset_aq) memcpy(qp_offset_aq, q.h_qp_aq, la->g.mb_count * sizeof(float));
-    la->qp_free.push_back(q.h_qp);
-    la->outq.pop_front();
+    { std::lock_guard<std::mutex> lk(la->qp_mu); la->qp_free.push_back(q.h_qp); }
+    la->pubq.pop_front();
     return 1;
 }
 
@@ -1722,6 +1900,7 @@ int x264vfw_cuda_la_frame_cost(x264vfw_cuda_la *h, int p0, int p1, int b)
     La *la = (La *)h;
     if (!la) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
+    if (worker_join(la) < 0) return -1;
     if (p0 < 0 || p1 >= (int)la->by_index.size() || b < p0 || b > p1 || b - p0 > la->p.bframes + 1 || p1 - b > la->p.bframes + 1) { set_error("frame_cost: bad indices"); return -1; }
     for (int i = p0; i <= p1; i++) if (!la->by_index[i]) { set_error("frame %d was recycled (open with keep_frames)", i); return -1; }
     return frame_cost(la, la->by_index.data(), p0, p1, b, true);
@@ -1732,6 +1911,7 @@ int x264vfw_cuda_la_mbtree(x264vfw_cuda_la *h, const int *frame_idx, const int *
     La *la = (La *)h;
     if (!la || num_frames > LMAX) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
+    if (worker_join(la) < 0) return -1;
     Frame *frames[LMAX + 3];
     for (int i = 0; i <= num_frames; i++) {
         if (frame_idx[i] < 0 || frame_idx[i] >= (int)la->by_index.size() || !la->by_index[frame_idx[i]]) { set_error("mbtree: bad frame"); return -1; }
@@ -1748,12 +1928,15 @@ int64_t x264vfw_cuda_la_read(x264vfw_cuda_la *h, int frame, int what, int a, int
     La *la = (La *)h;
     if (!la || !dst) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
+    if (worker_join(la) < 0) return -1;
     if (la_sync(la) < 0) return -1;
     for (int e = 1; e <= la->me_side; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
     const int n = la->g.mb_count, B = la->p.bframes;
     if (what == X264VFW_CUDA_LA_CONV_PLANES) {
         if (cap < la->d_planes_bytes) { set_error("read: buffer too small"); return -1; }
-        XV_CUDA_OK(cudaMemcpy(dst, la->d_planes, la->d_planes_bytes, cudaMemcpyDeviceToHost));
+        const uint8_t *last = la->worker.joinable() ? la->d_planes_ring[(la->n_put + la->io_depth - 1) % la->io_depth] : la->d_planes;
+        if (la->st_io) XV_CUDA_OK(cudaStreamSynchronize(la->st_io));
+        XV_CUDA_OK(cudaMemcpy(dst, last, la->d_planes_bytes, cudaMemcpyDeviceToHost));
         return (int64_t)la->d_planes_bytes;
     }
     if (frame < 0 || frame >= (int)la->by_index.size() || !la->by_index[frame]) { set_error("read: frame %d not resident", frame); return -1; }
@@ -1793,6 +1976,7 @@ int x264vfw_cuda_la_profile(x264vfw_cuda_la *h, int enable, double ms[16], uint6
     La *la = (La *)h;
     if (!la) return -1;
     XV_CUDA_OK(cudaSetDevice(la->device));
+    if (worker_join(la) < 0) return -1;
     if (la_sync(la) < 0) return -1;
     for (int e = 1; e <= la->me_side; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
     prof_resolve(la);
