@@ -16,6 +16,20 @@ else:
     frames = [torch.from_numpy(clip.packed(i, "bgra")).cuda() for i in range(N)]
 torch.cuda.synchronize()
 
+BG = int(os.environ.get("BGCOPY", "0"))     # 1: a background thread keeps the H2D link busy (diagnostics)
+if BG:
+    bg_h = torch.empty(8294400, dtype=torch.uint8).pin_memory(); bg_d = torch.empty(8294400, dtype=torch.uint8, device="cuda")
+    bg_stop = False
+    def bg():
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            while not bg_stop:
+                for _ in range(BG):
+                    bg_d.copy_(bg_h, non_blocking=True)
+                st.synchronize()
+                time.sleep(0.0002 if BG < 8 else 0)
+    threading.Thread(target=bg, daemon=True).start()
+
 def run(S, total=int(os.environ.get("TOTAL", "120"))):
     las = [lookahead.Lookahead(lookahead.params_preset("medium", W, H), in_csp=9 | 0x1000, device=0) for _ in range(S)]
     base = {}

@@ -193,7 +193,7 @@ struct La {
     uint64_t n_frame_cost = 0, n_mb_search = 0, n_sync = 0;
     std::atomic<uint64_t> n_launch{0};
     bool fail = false;   // set when a device call fails inside the value-returning helpers
-    double t_put = 0, t_decide = 0, t_sync = 0, t_io = 0;   // host wall-clock seconds (diagnostics)
+    double t_put = 0, t_decide = 0, t_sync = 0, t_io = 0, t_csp_wait = 0;   // host wall-clock seconds (diagnostics)
     uint64_t n_ondemand = 0, n_ondemand_jobs = 0, n_spec_jobs = 0;
     uint64_t n_logical[2][BMAX + 1] = {{0}};      // searches upstream's control flow actually asked for, by list/distance
     Prof prof;
@@ -1323,7 +1323,12 @@ static int decide_and_shift(La *la)
 static int process_frame(La *la, Frame *f, const x264vfw_cuda_image_t &planes, cudaEvent_t ev_csp, cudaEvent_t ev_free)
 {
     const int w = la->p.width, hgt = la->p.height;
-    if (ev_csp) XV_CUDA_OK(cudaStreamWaitEvent(la->st, ev_csp, 0));
+    if (ev_csp) {
+        // Wait for the conversion HERE, on the host, not in the main stream: a stream-side wait
+        // would make the next decision's synchronisation wait for this frame's copies as well.
+        if (cudaEventQuery(ev_csp) != cudaSuccess) { const double t0 = now_s(); XV_CUDA_OK(cudaEventSynchronize(ev_csp)); la->t_csp_wait += now_s() - t0; }
+        XV_CUDA_OK(cudaStreamWaitEvent(la->st, ev_csp, 0));
+    }
     // ---- [x264] x264_adaptive_quant_frame ----
     const bool planar_yuv = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_I422 || la->out_csp == X264VFW_CUDA_OUT_I444;
     const bool aq_on = la->p.aq_mode != 0 && la->p.aq_strength != 0;
@@ -1635,9 +1640,9 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
                 (unsigned long long)la->n_ondemand, (unsigned long long)la->n_ondemand_jobs);
         if (la->io_n) fprintf(stderr, "[x264vfw_cuda] I/O stream us per frame: wait for planes %.0f, H2D %.0f, conversion %.0f, D2H %.0f\n",
                               1e3 * la->io_ms[0] / la->io_n, 1e3 * la->io_ms[1] / la->io_n, 1e3 * la->io_ms[2] / la->io_n, 1e3 * la->io_ms[3] / la->io_n);
-        fprintf(stderr, "[x264vfw_cuda] host us per frame: put %.0f decide %.0f (of which waiting %.0f) final wait for the borrowed buffers %.0f\n",
+        fprintf(stderr, "[x264vfw_cuda] host us per frame: put %.0f decide %.0f (of which waiting %.0f) final wait for the borrowed buffers %.0f, worker waiting for a conversion %.0f\n",
                 1e6 * la->t_put / (la->n_input ? la->n_input : 1), 1e6 * la->t_decide / (la->n_input ? la->n_input : 1),
-                1e6 * la->t_sync / (la->n_input ? la->n_input : 1), 1e6 * la->t_io / (la->n_input ? la->n_input : 1));
+                1e6 * la->t_sync / (la->n_input ? la->n_input : 1), 1e6 * la->t_io / (la->n_input ? la->n_input : 1), 1e6 * la->t_csp_wait / (la->n_input ? la->n_input : 1));
     }
     if (la->st) cudaStreamSynchronize(la->st);
     for (int e = 1; e <= ME_SIDE; e++) if (la->st_me[e]) cudaStreamSynchronize(la->st_me[e]);
