@@ -66,6 +66,13 @@ __device__ __forceinline__ uint32_t ldg_stream32(const void *p)
 }
 
 // rounding byte-wise average (a+b+1)>>1 on 4 packed bytes
-__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) { return __vavgu4(a, b); }
+// = __vavgu4, which the compiler expands to five integer operations (xor, shift, and, or, sub);
+// folding the mask into the xor with one LOP3 leaves four -- these kernels are ALU-pipe bound
+__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b)
+{
+    uint32_t t;
+    asm("lop3.b32 %0, %1, %2, 0xfefefefe, 0x28;" : "=r"(t) : "r"(a), "r"(b));      // (a ^ b) & 0xfefefefe
+    return (a | b) - (t >> 1);
+}
 
 } // namespace xv

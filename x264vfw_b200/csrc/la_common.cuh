@@ -52,8 +52,8 @@ __device__ __forceinline__ uint2 get_ref_row(const uint8_t *const planes[4], int
     uint2 a = load8u(planes[c_hpel_ref0[qidx]] + off + ((mvy & 3) == 3) * stride);
     if (qidx & 5) {
         uint2 b = load8u(planes[c_hpel_ref1[qidx]] + off + ((mvx & 3) == 3));
-        a.x = __vavgu4(a.x, b.x);
-        a.y = __vavgu4(a.y, b.y);
+        a.x = avg4(a.x, b.x);
+        a.y = avg4(a.y, b.y);
     }
     if (w.on) { a.x = weight_word(w, a.x); a.y = weight_word(w, a.y); }
     return a;
@@ -69,8 +69,8 @@ __device__ __forceinline__ uint2 get_ref_row_ps(const uint8_t *plane0, int plane
     uint2 a = load8u(plane0 + (size_t)c_hpel_ref0[qidx] * plane_stride + off + ((mvy & 3) == 3) * stride);
     if (qidx & 5) {
         uint2 b = load8u(plane0 + (size_t)c_hpel_ref1[qidx] * plane_stride + off + ((mvx & 3) == 3));
-        a.x = __vavgu4(a.x, b.x);
-        a.y = __vavgu4(a.y, b.y);
+        a.x = avg4(a.x, b.x);
+        a.y = avg4(a.y, b.y);
     }
     if (w.on) { a.x = weight_word(w, a.x); a.y = weight_word(w, a.y); }
     return a;

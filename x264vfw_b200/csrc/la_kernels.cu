@@ -393,7 +393,7 @@ __device__ __forceinline__ int bidir_cost(const uint2 fenc[8], uint2 a[8], const
 {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        if (wgt == 32) { a[r].x = __vavgu4(a[r].x, b[r].x); a[r].y = __vavgu4(a[r].y, b[r].y); }
+        if (wgt == 32) { a[r].x = avg4(a[r].x, b[r].x); a[r].y = avg4(a[r].y, b[r].y); }
         else { a[r].x = avg_weighted4(a[r].x, b[r].x, wgt); a[r].y = avg_weighted4(a[r].y, b[r].y, wgt); }
     }
     return mbcmp_rows(satd, fenc, a);

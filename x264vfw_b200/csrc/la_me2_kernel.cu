@@ -257,8 +257,8 @@ __device__ __forceinline__ int cand_qpel(const Mb<LPS> &m, int qx, int qy, bool 
             for (int r = 0; r < RPL; r++) {
                 uint2 v = make_uint2(__funnelshift_r(q0[0], q0[1], s0), __funnelshift_r(q0[1], q0[2], s0));
                 if (two) {
-                    v.x = __vavgu4(v.x, __funnelshift_r(q1[0], q1[1], s1));
-                    v.y = __vavgu4(v.y, __funnelshift_r(q1[1], q1[2], s1));
+                    v.x = avg4(v.x, __funnelshift_r(q1[0], q1[1], s1));
+                    v.y = avg4(v.y, __funnelshift_r(q1[1], q1[2], s1));
                 }
                 a[r] = v;
                 q0 += SUB_W / 4; q1 += SUB_W / 4;
@@ -272,7 +272,7 @@ __device__ __forceinline__ int cand_qpel(const Mb<LPS> &m, int qx, int qy, bool 
                 uint2 v = load8u(p0);
                 if (two) {
                     const uint2 b = load8u(p1);
-                    v.x = __vavgu4(v.x, b.x); v.y = __vavgu4(v.y, b.y);
+                    v.x = avg4(v.x, b.x); v.y = avg4(v.y, b.y);
                 }
                 a[r] = v;
                 p0 += m.stride; p1 += m.stride;

@@ -175,8 +175,8 @@ __device__ __forceinline__ uint2 get_ref_row_sub(const WarpMb &m, int mvx, int m
     uint2 a = lds8u(m.sub + c_hpel_ref0[qidx] * (SUB_H * SUB_W), (Y + ((mvy & 3) == 3)) * SUB_W + X);
     if (qidx & 5) {
         const uint2 b = lds8u(m.sub + c_hpel_ref1[qidx] * (SUB_H * SUB_W), Y * SUB_W + X + ((mvx & 3) == 3));
-        a.x = __vavgu4(a.x, b.x);
-        a.y = __vavgu4(a.y, b.y);
+        a.x = avg4(a.x, b.x);
+        a.y = avg4(a.y, b.y);
     }
     if (m.w.on) { a.x = weight_word(m.w, a.x); a.y = weight_word(m.w, a.y); }
     return a;
