@@ -191,8 +191,7 @@ int launch_rgb_to_420(cudaStream_t st, const RgbJob &job_in, int bpp, bool nv12,
 }
 
 // ------------------------------------------------------------------------------------------
-// Packed 4:2:2 (YUYV / UYVY) -> planar.  One thread = 8 pixels (16 source bytes) of one row
-// (I422/I444) or of a row pair (I420).
+// Packed 4:2:2 (YUYV / UYVY) -> planar.  One thread = 8 pixels (16 source bytes) of a row pair.
 //   MODE 0: I420 (chroma = (top+bottom+1)>>1, csp.c:185-186)
 //   MODE 1: I422 (copy, csp.c:239-240)
 //   MODE 2: I444 extension (I422 samples, each chroma sample written twice)
@@ -231,8 +230,10 @@ template <bool UYVY, int MODE, bool VEC>
 __global__ void __launch_bounds__(256)
 packed422_kernel(PackedJob job)
 {
+    // every mode works on a ROW PAIR per thread (height is even): two independent 128-bit loads in
+    // flight, address arithmetic shared; only MODE 0 combines the two rows
     const int nchunk = (job.w + 7) >> 3;
-    const int nrow = MODE == 0 ? (job.h >> 1) : job.h;
+    const int nrow = job.h >> 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nchunk * nrow) return;
     const int row = idx / nchunk;
@@ -242,43 +243,58 @@ packed422_kernel(PackedJob job)
     const size_t f = blockIdx.y;
     const bool vec = VEC;
 
-    const int srow = MODE == 0 ? 2 * row : row;
+    const int srow = 2 * row;
     const uint8_t *s0 = job.src + f * job.src_frame_bytes + (ptrdiff_t)srow * job.src_stride + 2 * x;
-    uint2 y0, y1 = make_uint2(0, 0);
-    uint32_t u, v;
-    split422<UYVY>(load_422_row<UYVY>(s0, npx, vec), y0, u, v);
+    uint2 y0, y1;
+    uint32_t u, v, ub, vb;
+    const uint4 in0 = load_422_row<UYVY>(s0, npx, vec), in1 = load_422_row<UYVY>(s0 + job.src_stride, npx, vec);
+    split422<UYVY>(in0, y0, u, v);
+    split422<UYVY>(in1, y1, ub, vb);
     if (MODE == 0) {
-        uint32_t ub, vb;
-        split422<UYVY>(load_422_row<UYVY>(s0 + job.src_stride, npx, vec), y1, ub, vb);
         u = avg4(u, ub);
         v = avg4(v, vb);
     }
 
+    const int crow = MODE == 0 ? row : srow;               // first chroma row written by this thread
     uint8_t *dy = job.dst_y + f * job.dst_frame_bytes + (size_t)srow * job.y_stride + x;
-    uint8_t *du = job.dst_u + f * job.dst_frame_bytes + (size_t)row * job.u_stride;
-    uint8_t *dv = job.dst_v + f * job.dst_frame_bytes + (size_t)row * job.v_stride;
+    uint8_t *du = job.dst_u + f * job.dst_frame_bytes + (size_t)crow * job.u_stride;
+    uint8_t *dv = job.dst_v + f * job.dst_frame_bytes + (size_t)crow * job.v_stride;
     if (vec && npx == 8) {
         *(uint2 *)dy = y0;
-        if (MODE == 0) *(uint2 *)(dy + job.y_stride) = y1;
+        *(uint2 *)(dy + job.y_stride) = y1;
         if (MODE == 2) {
             uint2 uu, v2;
             uu.x = __byte_perm(u, 0, 0x1100); uu.y = __byte_perm(u, 0, 0x3322);
             v2.x = __byte_perm(v, 0, 0x1100); v2.y = __byte_perm(v, 0, 0x3322);
             *(uint2 *)(du + x) = uu;
             *(uint2 *)(dv + x) = v2;
+            uu.x = __byte_perm(ub, 0, 0x1100); uu.y = __byte_perm(ub, 0, 0x3322);
+            v2.x = __byte_perm(vb, 0, 0x1100); v2.y = __byte_perm(vb, 0, 0x3322);
+            *(uint2 *)(du + job.u_stride + x) = uu;
+            *(uint2 *)(dv + job.v_stride + x) = v2;
         } else {
             *(uint32_t *)(du + (x >> 1)) = u;
             *(uint32_t *)(dv + (x >> 1)) = v;
+            if (MODE == 1) {
+                *(uint32_t *)(du + job.u_stride + (x >> 1)) = ub;
+                *(uint32_t *)(dv + job.v_stride + (x >> 1)) = vb;
+            }
         }
     } else {
         for (int i = 0; i < npx; i++) {
             dy[i] = (uint8_t)((i < 4 ? y0.x : y0.y) >> (8 * (i & 3)));
-            if (MODE == 0) dy[job.y_stride + i] = (uint8_t)((i < 4 ? y1.x : y1.y) >> (8 * (i & 3)));
+            dy[job.y_stride + i] = (uint8_t)((i < 4 ? y1.x : y1.y) >> (8 * (i & 3)));
         }
         for (int i = 0; i < (npx >> 1); i++) {
-            uint8_t ub = (uint8_t)(u >> (8 * i)), vb = (uint8_t)(v >> (8 * i));
-            if (MODE == 2) { du[x + 2 * i] = du[x + 2 * i + 1] = ub; dv[x + 2 * i] = dv[x + 2 * i + 1] = vb; }
-            else           { du[(x >> 1) + i] = ub; dv[(x >> 1) + i] = vb; }
+            const uint8_t u0 = (uint8_t)(u >> (8 * i)), v0 = (uint8_t)(v >> (8 * i));
+            const uint8_t u1 = (uint8_t)(ub >> (8 * i)), v1 = (uint8_t)(vb >> (8 * i));
+            if (MODE == 2) {
+                du[x + 2 * i] = du[x + 2 * i + 1] = u0; dv[x + 2 * i] = dv[x + 2 * i + 1] = v0;
+                du[job.u_stride + x + 2 * i] = du[job.u_stride + x + 2 * i + 1] = u1; dv[job.v_stride + x + 2 * i] = dv[job.v_stride + x + 2 * i + 1] = v1;
+            } else {
+                du[(x >> 1) + i] = u0; dv[(x >> 1) + i] = v0;
+                if (MODE == 1) { du[job.u_stride + (x >> 1) + i] = u1; dv[job.v_stride + (x >> 1) + i] = v1; }
+            }
         }
     }
 }
@@ -286,7 +302,7 @@ packed422_kernel(PackedJob job)
 int launch_packed422(cudaStream_t st, const PackedJob &job, bool uyvy, int mode, bool vec, int n_frames)
 {
     const int nchunk = (job.w + 7) >> 3;
-    const int nrow = mode == 0 ? (job.h >> 1) : job.h;
+    const int nrow = job.h >> 1;                        // a row pair per thread in every mode
     const long long total = (long long)nchunk * nrow;
     if (total <= 0 || n_frames <= 0) return 0;
     dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_frames);
