@@ -487,9 +487,102 @@ finalize_kernel(LaGeom g, FinalizeJob job)
     }
 }
 
+// B evaluations: the three bidirectional candidates are most of the work (six block fetches and
+// three SATDs per MB), and the host usually waits for this kernel.  Four lanes share an MB (two
+// rows each; the SATD butterflies cross lanes with shuffles), which makes the kernel four times
+// wider and its per-thread chain four times shorter.  Same arithmetic, same comparison order.
+__global__ void __launch_bounds__(128)
+finalize_bidir4_kernel(LaGeom g, FinalizeJob job)
+{
+    const unsigned FULLM = 0xffffffffu;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = tid >> 2, part = tid & 3;
+    const bool in_range = idx < g.mb_count;
+    const int mx = in_range ? idx % g.mb_w : 0, my = in_range ? idx / g.mb_w : 0;
+    const bool edge = mx == 0 || my == 0 || mx == g.mb_w - 1 || my == g.mb_h - 1;
+    const bool tiny = g.mb_w <= 2 || g.mb_h <= 2;
+    const bool act = in_range && (job.do_edges || !edge);
+    const int stride = g.lstride, pel = 8 * (mx + my * stride), r0 = 2 * part;
+    const WeightDev w0 = {0, 1, 0, 0};
+    int acc_cost = 0, acc_aq = 0;
+    int bcost = LA_COST_MAX, list_used = 0;
+    uint2 f0 = make_uint2(0, 0), f1 = f0;
+    int d0x = 0, d0y = 0, d1x = 0, d1y = 0, mv0 = 0, mv1 = 0;
+    if (act) {
+        f0 = load8u(job.fenc + pel + r0 * stride); f1 = load8u(job.fenc + pel + (r0 + 1) * stride);
+        int min_x, max_x, min_y, max_y;
+        mv_limits(mx, my, g.mb_w, g.mb_h, job.mv_range2, min_x, max_x, min_y, max_y);
+        if (job.ref1_mvs) {
+            const int mvr = job.ref1_mvs[idx];
+            const int rx = mv_x(mvr), ry = mv_y(mvr);
+            d0x = (rx * job.dist_scale_factor + 128) >> 8;
+            d0y = (ry * job.dist_scale_factor + 128) >> 8;
+            d1x = d0x - rx; d1y = d0y - ry;
+            d0x = clip3i(d0x, min_x, max_x); d0y = clip3i(d0y, min_y, max_y);
+            d1x = clip3i(d1x, min_x, max_x); d1y = clip3i(d1y, min_y, max_y);
+            if (!job.subme_gt1) { d0x &= ~1; d0y &= ~1; d1x &= ~1; d1y &= ~1; }
+        }
+        mv0 = job.mvs0[idx]; mv1 = job.mvs1[idx];
+    }
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        int ax, ay, bx, by, pen; bool en;
+        if (k == 0) { ax = d0x; ay = d0y; bx = d1x; by = d1y; pen = 0; en = act; }
+        else if (k == 1) { ax = ay = bx = by = 0; pen = 0; en = act && (d0x | d0y | d1x | d1y) != 0; }
+        else { ax = mv_x(mv0); ay = mv_y(mv0); bx = mv_x(mv1); by = mv_y(mv1); pen = 5; en = act && (mv0 | mv1) != 0; }
+        if (__any_sync(FULLM, en)) {
+            uint2 a0 = make_uint2(0, 0), a1 = a0, b0 = a0, b1 = a0;
+            if (en) {
+                if (job.subme_gt1) {
+                    a0 = get_ref_row(job.fref0, stride, pel, ax, ay, r0, w0); a1 = get_ref_row(job.fref0, stride, pel, ax, ay, r0 + 1, w0);
+                    b0 = get_ref_row(job.fref1, stride, pel, bx, by, r0, w0); b1 = get_ref_row(job.fref1, stride, pel, bx, by, r0 + 1, w0);
+                } else {
+                    const uint8_t *pa = job.fref0[((ax & 2) >> 1) + (ay & 2)] + pel + ((ay >> 2) + r0) * stride + (ax >> 2);
+                    const uint8_t *pb = job.fref1[((bx & 2) >> 1) + (by & 2)] + pel + ((by >> 2) + r0) * stride + (bx >> 2);
+                    a0 = load8u(pa); a1 = load8u(pa + stride); b0 = load8u(pb); b1 = load8u(pb + stride);
+                }
+                if (job.bipred_weight == 32) {
+                    a0.x = avg4(a0.x, b0.x); a0.y = avg4(a0.y, b0.y); a1.x = avg4(a1.x, b1.x); a1.y = avg4(a1.y, b1.y);
+                } else {
+                    a0.x = avg_weighted4(a0.x, b0.x, job.bipred_weight); a0.y = avg_weighted4(a0.y, b0.y, job.bipred_weight);
+                    a1.x = avg_weighted4(a1.x, b1.x, job.bipred_weight); a1.y = avg_weighted4(a1.y, b1.y, job.bipred_weight);
+                }
+            }
+            int c;
+            if (job.satd) c = satd_rows4(f0, f1, a0, a1, part & 1);
+            else {
+                c = __vsadu4(a0.x, f0.x) + __vsadu4(a0.y, f0.y) + __vsadu4(a1.x, f1.x) + __vsadu4(a1.y, f1.y);
+                c += __shfl_xor_sync(FULLM, c, 1);
+                c += __shfl_xor_sync(FULLM, c, 2);
+            }
+            c += pen;
+            if (en && c < bcost) { bcost = c; list_used = 3; }
+        }
+        if (k == 1 && act) {
+            const int c0 = job.mv_costs0[idx], c1 = job.mv_costs1[idx];
+            if (c0 < bcost) { bcost = c0; list_used = 1; }
+            if (c1 < bcost) { bcost = c1; list_used = 2; }
+        }
+    }
+    if (act && part == 0) {
+        bcost += 4;                                      // lowres_penalty
+        int bcost_aq = bcost;
+        if (job.aq_on) bcost_aq = (bcost_aq * job.inv_qscale[idx] + 128) >> 8;
+        if (job.row_satd) atomicAdd(job.row_satd + my, bcost_aq);
+        if (!edge || tiny) { acc_cost = bcost; acc_aq = bcost_aq; }
+        job.lowres_costs[idx] = (uint16_t)(min(bcost, LA_LOWRES_COST_MASK) + (list_used << LA_LOWRES_COST_SHIFT));
+    }
+    acc_cost = warp_sum(acc_cost); acc_aq = warp_sum(acc_aq);
+    if ((threadIdx.x & 31) == 0) {
+        if (acc_cost) atomicAdd(job.result, acc_cost);
+        if (acc_aq) atomicAdd(job.result + 1, acc_aq);
+    }
+}
+
 int launch_finalize(cudaStream_t st, const LaGeom &g, const FinalizeJob &job)
 {
-    finalize_kernel<<<(g.mb_count + 63) / 64, 64, 0, st>>>(g, job);
+    if (job.b_bidir) finalize_bidir4_kernel<<<(4 * g.mb_count + 127) / 128, 128, 0, st>>>(g, job);
+    else finalize_kernel<<<(g.mb_count + 63) / 64, 64, 0, st>>>(g, job);
     XV_LAUNCH_CHECK();
     return 0;
 }

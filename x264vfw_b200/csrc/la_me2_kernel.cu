@@ -124,46 +124,6 @@ __device__ __forceinline__ int satd_8x4_regs(const uint2 *a, const uint2 *b)
     }
     return sum >> 1;
 }
-// LPS = 4: a lane holds two rows.  Rows 0-3 live in lane parts 0,1 and rows 4-7 in parts 2,3:
-// each lane pair forms one 8x4 (horizontal butterflies in the lane, vertical ones across the
-// pair with packed 16-bit shuffles), the two halves add.
-__device__ __forceinline__ int satd_rows4(uint2 fe0, uint2 fe1, uint2 a0, uint2 a1, bool odd)
-{
-    int s[8], d[8];
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const uint32_t f0 = half ? fe0.y : fe0.x, f1 = half ? fe1.y : fe1.x;
-        const uint32_t r0 = half ? a0.y : a0.x, r1 = half ? a1.y : a1.x;
-        int t0[4], t1[4];
-        {
-            int e0 = (int)(f0 & 0xff) - (int)(r0 & 0xff), e1 = (int)((f0 >> 8) & 0xff) - (int)((r0 >> 8) & 0xff);
-            int e2 = (int)((f0 >> 16) & 0xff) - (int)((r0 >> 16) & 0xff), e3 = (int)(f0 >> 24) - (int)(r0 >> 24);
-            int s01 = e0 + e1, d01 = e0 - e1, s23 = e2 + e3, d23 = e2 - e3;
-            t0[0] = s01 + s23; t0[1] = s01 - s23; t0[2] = d01 + d23; t0[3] = d01 - d23;
-        }
-        {
-            int e0 = (int)(f1 & 0xff) - (int)(r1 & 0xff), e1 = (int)((f1 >> 8) & 0xff) - (int)((r1 >> 8) & 0xff);
-            int e2 = (int)((f1 >> 16) & 0xff) - (int)((r1 >> 16) & 0xff), e3 = (int)(f1 >> 24) - (int)(r1 >> 24);
-            int s01 = e0 + e1, d01 = e0 - e1, s23 = e2 + e3, d23 = e2 - e3;
-            t1[0] = s01 + s23; t1[1] = s01 - s23; t1[2] = d01 + d23; t1[3] = d01 - d23;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) { s[half * 4 + k] = t0[k] + t1[k]; d[half * 4 + k] = t0[k] - t1[k]; }
-    }
-    int sum = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int mine = (s[k] & 0xffff) | (d[k] << 16);
-        const int other = __shfl_xor_sync(FULL, mine, 1);
-        const int so = (int)(short)(other & 0xffff), dd = other >> 16;
-        sum += odd ? abs(so - s[k]) + abs(dd - d[k]) : abs(s[k] + so) + abs(d[k] + dd);
-    }
-    sum += __shfl_xor_sync(FULL, sum, 1);     // 8x4 total in both lanes of the pair
-    sum >>= 1;
-    sum += __shfl_xor_sync(FULL, sum, 2);     // + the other 8x4
-    return sum;
-}
-
 template <int LPS> __device__ __forceinline__ int satd_rows(const Mb<LPS> &m, const uint2 *a)
 {
     if (LPS == 4) return satd_rows4(m.fe[0], m.fe[1 % Mb<LPS>::RPL], a[0], a[1 % Mb<LPS>::RPL], m.gl & 1);
