@@ -67,6 +67,7 @@ struct Frame {
     uint64_t spec_seq[2][BMAX + 1];        // ... in this launch of it
     uint64_t touch_seq[1 + ME_SIDE] = {0}; // last launch of each side engine that reads/writes this frame
     bool b_intra_calculated = false;
+    bool intra_dev = false;                    // intra_cost[] already computed on the device (at arrival)
     bool stats_ready = false;
     unsigned long long pixel_sum[3], pixel_ssd[3];
     WeightDev weight = {0, 1, 0, 0};
@@ -280,7 +281,7 @@ static int frame_reset(La *la, Frame *f, int i_frame)
     memset(f->spec, 0, sizeof(f->spec));
     memset(f->spec_eng, 0, sizeof(f->spec_eng));
     memset(f->spec_seq, 0, sizeof(f->spec_seq));
-    f->b_intra_calculated = false; f->stats_ready = false;
+    f->b_intra_calculated = false; f->intra_dev = false; f->stats_ready = false;
     f->weight = WeightDev{0, 1, 0, 0};
     f->rc_d0 = f->rc_d1 = -1;
     f->in_use = true;
@@ -390,7 +391,11 @@ static int launch_intra_for(La *la, Frame *fenc)
 {
     IntraJob ij;
     ij.plane0 = plane_org(la, fenc, 0); ij.intra_cost = fenc->intra_cost; ij.full = la->p.subme > 1; ij.satd = la->la_satd;
-    { ProfScope ps(la, K_INTRA); if (launch_intra(la->st, la->g, ij, la->do_edges) < 0) return -1; }
+    if (!fenc->intra_dev) {   // normally done when the frame arrived (process_frame): the costs do not depend on when
+        ProfScope ps(la, K_INTRA);
+        if (launch_intra(la->st, la->g, ij, la->do_edges) < 0) return -1;
+        fenc->intra_dev = true;
+    }
     const int slot = result_slot(la);
     if (slot < 0) return -1;
     LA_CUDA(cudaMemsetAsync(la->d_results + slot * 4, 0, 4 * sizeof(int), la->st));
@@ -1352,6 +1357,14 @@ static int process_frame(La *la, Frame *f, const x264vfw_cuda_image_t &planes, c
     { ProfScope ps(la, K_LOWRES); if (launch_lowres_init(la->st, lj, 1) < 0) return -1; }
     la->n_launch += 2;
     XV_CUDA_OK(cudaEventRecord(ev_free, la->st));           // the planes may be overwritten again
+    {   // every frame's intra costs are needed sooner or later and only depend on its lowres plane
+        IntraJob ij;
+        ij.plane0 = plane_org(la, f, 0); ij.intra_cost = f->intra_cost; ij.full = la->p.subme > 1; ij.satd = la->la_satd;
+        ProfScope ps(la, K_INTRA);
+        if (launch_intra(la->st, la->g, ij, la->do_edges) < 0) return -1;
+        f->intra_dev = true;
+        la->n_launch++;
+    }
     f->ready = true;
     return speculate_searches(la, f);
 }
