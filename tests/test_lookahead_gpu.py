@@ -320,3 +320,20 @@ def test_concurrent_sessions_are_deterministic_and_match_oracle():
         assert [(d["i_frame"], d["i_type"], d["i_cost_est"], d["i_cost_est_aq"]) for d in got] == \
                [(d["i_frame"], d["i_type"], d["i_cost_est"], d["i_cost_est_aq"]) for d in want], k
         assert all(np.array_equal(a["qp_offset"].view(np.uint32), b["qp_offset"].view(np.uint32)) for a, b in zip(got, want)), k
+
+
+def _golden_cases():
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lookahead_golden.json")))
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=[c["name"] for c in _golden_cases()])
+def test_device_path_matches_the_committed_fingerprints(case):
+    """The whole device path (packed BGRA in, csp + lookahead) against tests/golden/lookahead_golden.json,
+    without the checker in the loop."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_lookahead_golden as mk
+    fp = mk.fingerprint(case["preset"], case["w"], case["h"], case["frames"], case["over"], backend="gpu")
+    for k in ("types", "coded_order", "costs", "qp_offset_fnv", "qp_offset_aq_fnv"):
+        assert fp[k] == case[k], (case["name"], k)
