@@ -56,7 +56,11 @@ __device__ __forceinline__ void load_px4(const uint8_t *p, int npx, uint32_t px[
             uint4 v = ldg_stream128(p);
             px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
         } else {
-            uint32_t w0 = ldg_stream32(p), w1 = ldg_stream32(p + 4), w2 = ldg_stream32(p + 8);
+            // three 32-bit loads at stride 12: each touches every sector of the warp's 384-byte span, so
+            // these go THROUGH L1 (the second and third hit there) instead of fetching the span from L2
+            // three times
+            const uint32_t *q = (const uint32_t *)p;
+            uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
             // byte 3 of each word is junk: it only ever meets a zero coefficient / an unused lane
             px[0] = w0;
             px[1] = __byte_perm(w0, w1, 0x3543);
