@@ -720,7 +720,7 @@ int launch_me_pass(cudaStream_t st, const LaGeom &g, const MeParams &p, int pass
 // trip of ~1500 on the chain), only the top row of a band publishes to global memory for the
 // band above.  Bands are handed out bottom-first by an atomic ticket, so a block only ever
 // waits on bands that already started (no co-residency assumption between blocks).
-#define VERIFY_ROWS 8
+#define VERIFY_ROWS 16
 __device__ __forceinline__ uint2 lds_rec(const int2 *p)
 {
     uint2 v;
@@ -733,7 +733,7 @@ __device__ __forceinline__ void sts_rec(int2 *p, int mv, int epoch)
 }
 
 template <bool QPRED>
-__global__ void __launch_bounds__(32 * VERIFY_ROWS, 2)
+__global__ void __launch_bounds__(32 * VERIFY_ROWS, 1)
 me_verify_kernel(LaGeom g, MeParams P)
 {
     extern __shared__ __align__(16) uint8_t vsm[];
