@@ -194,7 +194,10 @@ struct La {
     uint64_t n_frame_cost = 0, n_mb_search = 0, n_sync = 0;
     std::atomic<uint64_t> n_launch{0};
     bool fail = false;   // set when a device call fails inside the value-returning helpers
-    double t_put = 0, t_decide = 0, t_sync = 0, t_io = 0, t_csp_wait = 0;   // host wall-clock seconds (diagnostics)
+    double t_put = 0, t_decide = 0, t_sync = 0, t_io = 0, t_csp_wait = 0;
+    // what the host was waiting for at each synchronisation (diagnostics): [0] only light kernels,
+    // [1] a speculative search batch still in flight, [2] an on-demand search batch
+    int sync_kind = 0; double t_sync_kind[3] = {0, 0, 0}; uint64_t n_sync_kind[3] = {0, 0, 0};   // host wall-clock seconds (diagnostics)
     uint64_t n_ondemand = 0, n_ondemand_jobs = 0, n_spec_jobs = 0;
     uint64_t n_logical[2][BMAX + 1] = {{0}};      // searches upstream's control flow actually asked for, by list/distance
     Prof prof;
@@ -349,6 +352,7 @@ static int la_sync(La *la)
         LA_CUDA(cudaMemcpyAsync(la->h_results, la->d_results, RESULT_SLOTS * 4 * sizeof(int), cudaMemcpyDeviceToHost, la->st));
     LA_CUDA(cudaStreamSynchronize(la->st));
     la->n_sync++;
+    la->t_sync_kind[la->sync_kind] += now_s() - t0; la->n_sync_kind[la->sync_kind]++; la->sync_kind = 0;
     if (!la->prof.recs.empty()) prof_resolve(la);
     for (const PendingResult &r : la->pending) {
         const int *v = la->h_results + r.slot * 4;
@@ -545,6 +549,7 @@ static int wait_engine(La *la, int eng, uint64_t seq)
     const uint64_t use = (la->me_seq[eng] - seq >= ME_EVENTS) ? la->me_seq[eng] : seq;
     LA_CUDA(cudaStreamWaitEvent(la->st, la->ev_me[eng][use % ME_EVENTS], 0));
     la->me_waited[eng] = use;
+    if (la->d_me_stats && cudaEventQuery(la->ev_me[eng][use % ME_EVENTS]) != cudaSuccess && la->sync_kind < 1) la->sync_kind = 1;
     return 0;
 }
 
@@ -585,7 +590,7 @@ static int me_launch(La *la, MeParams &mp, int eng)
     } else
     { if (me_kernels(la, st, mp, true) < 0) return -1; }
     la->n_launch++;
-    if (eng) la->n_spec_jobs += mp.njobs; else { la->n_ondemand++; la->n_ondemand_jobs += mp.njobs; }
+    if (eng) la->n_spec_jobs += mp.njobs; else { la->n_ondemand++; la->n_ondemand_jobs += mp.njobs; la->sync_kind = 2; }
     if (eng) {
         const uint64_t seq = ++la->me_seq[eng];
         LA_CUDA(cudaEventRecord(la->ev_me[eng][seq % ME_EVENTS], st));
@@ -1653,6 +1658,10 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
                 (unsigned long long)la->n_ondemand, (unsigned long long)la->n_ondemand_jobs);
         if (la->io_n) fprintf(stderr, "[x264vfw_cuda] I/O stream us per frame: wait for planes %.0f, H2D %.0f, conversion %.0f, D2H %.0f\n",
                               1e3 * la->io_ms[0] / la->io_n, 1e3 * la->io_ms[1] / la->io_n, 1e3 * la->io_ms[2] / la->io_n, 1e3 * la->io_ms[3] / la->io_n);
+        fprintf(stderr, "[x264vfw_cuda] waits: light kernels only %llu x %.0f us, speculative search in flight %llu x %.0f us, on-demand search %llu x %.0f us\n",
+                (unsigned long long)la->n_sync_kind[0], 1e6 * la->t_sync_kind[0] / (la->n_sync_kind[0] ? la->n_sync_kind[0] : 1),
+                (unsigned long long)la->n_sync_kind[1], 1e6 * la->t_sync_kind[1] / (la->n_sync_kind[1] ? la->n_sync_kind[1] : 1),
+                (unsigned long long)la->n_sync_kind[2], 1e6 * la->t_sync_kind[2] / (la->n_sync_kind[2] ? la->n_sync_kind[2] : 1));
         fprintf(stderr, "[x264vfw_cuda] host us per frame: put %.0f decide %.0f (of which waiting %.0f) final wait for the borrowed buffers %.0f, worker waiting for a conversion %.0f\n",
                 1e6 * la->t_put / (la->n_input ? la->n_input : 1), 1e6 * la->t_decide / (la->n_input ? la->n_input : 1),
                 1e6 * la->t_sync / (la->n_input ? la->n_input : 1), 1e6 * la->t_io / (la->n_input ? la->n_input : 1), 1e6 * la->t_csp_wait / (la->n_input ? la->n_input : 1));
