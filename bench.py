@@ -43,7 +43,7 @@ LOWRES_ALGO_BYTES = 1920 * 1088 + 4 * 960 * 544   # 4,177,920 B / frame
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=8, help="independent streams per GPU")

@@ -50,7 +50,7 @@ def raw_metrics(rep, dst, title):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
-    jobs = [("launches_bench_r1d.csv", f"launches_bench_{tag}.txt", "bench.py --steps 2 --warmup 3 --streams 2 --frames-per-step 8 --no-e2e --no-cpu-baseline (launches 3000..6000)"),
+    jobs = [("launches_bench_r1e.csv", f"launches_bench_{tag}.txt", "bench.py --steps 2 --warmup 3 --streams 2 --frames-per-step 8 --no-e2e --no-cpu-baseline (launches 3000..6000)"),
             ("launches_bench_r1.csv", f"launches_bench_{tag}_wavefront_version.txt", "same command, earlier build (plain wavefront search, one kernel per mb-tree step)"),
             ("launches_la_r1a.csv", f"launches_single_stream_{tag}.txt", "scripts/profile_la.py 10 (one 1080p stream, 10 frames)")]
     for src, dst, title in jobs:
@@ -58,7 +58,7 @@ if __name__ == "__main__":
             launch_list(os.path.join(GP, src), os.path.join(OUT, dst), title)
     reps = [("me_pass_d.ncu-rep", f"ncu_me_pass_{tag}.txt", "me_pass_kernel<1,true>, pass 0 of a 2-search batch (16320 MB searches), alone on the GPU"),
             ("me_pass_a.ncu-rep", f"ncu_me_pass_{tag}_first_version.txt", "me_pass_kernel before the state-machine / code-size work (129 KB of SASS, 167 registers)"),
-            ("me_verify_d.ncu-rep", f"ncu_me_verify_{tag}.txt", "me_verify_kernel<true>, verification wavefront of a 2-search batch, alone on the GPU"),
+            ("me_verify_e.ncu-rep", f"ncu_me_verify_{tag}.txt", "me_verify_kernel<true>, verification wavefront of a 2-search batch, alone on the GPU"),
             ("me2_b.ncu-rep", f"ncu_me_band_{tag}_rejected.txt", "rejected design: 4 MB rows per warp in lockstep (me_band_kernel), 2 searches"),
             ("me_prof_r1c.ncu-rep", f"ncu_me_wavefront_{tag}.txt", "me_wavefront_kernel (plain wavefront, now the fallback), 7 searches of one 1080p frame, alone on the GPU"),
             ("me_prof_r1a.ncu-rep", f"ncu_me_wavefront_{tag}_first_version.txt", "first version of the search kernel (global loads, progress flags) for comparison"),
