@@ -418,7 +418,7 @@ def main():
             "config": {"workload": "C5: 1080p RGB32 bottom-up DIB -> I420 + x264 lookahead preset medium, independent streams, one session per stream",
                        "preset": PRESET, "width": W, "height": H, "streams_per_gpu": S, "frames_per_step_per_stream": F,
                        "rc_lookahead": 40, "bframes": 3, "b_adapt": 1, "mbtree": 1, "weightp": 2, "aq_mode": 1,
-                       "l2_policy": f"inputs larger than L2: {S * F * SRC_BYTES / 1e6:.0f} MB of packed frames per step per GPU"},
+                       "host_wait": os.environ.get("X264VFW_CUDA_SYNC", "spin"), "l2_policy": f"inputs larger than L2: {S * F * SRC_BYTES / 1e6:.0f} MB of packed frames per step per GPU"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "stage1": stage1,
             "kernel_shares": shares, "dominant_kernel_class": dom, "cpu_baseline": cpu_baseline,
             "host_us_per_frame": {k: host_delta[k] / max(1, host_delta["frames"]) for k in ("put_us", "decide_us", "sync_us")},

@@ -186,6 +186,9 @@ struct La {
     std::deque<std::pair<long, Decision>> doneq; // decisions tagged with the frame whose arrival produced them
     int werr = 0; std::string werr_msg;
     int async = 1;
+    // host waits: spin (lowest latency; one busy core per waiting thread) or block on an interrupt
+    // (X264VFW_CUDA_SYNC=block: for hosts with fewer cores than session threads)
+    bool blocking = false; int spin_us = 60; cudaEvent_t ev_sync = nullptr;   // default: spin; hybrid: spin for spin_us, then block
     int io_depth = 2;                           // planes ring: frames the caller may run ahead of the worker
     uint8_t *d_planes_ring[4] = {nullptr}; x264vfw_cuda_image_t planes_ring[4];
     cudaEvent_t ev_csp_ring[4] = {nullptr}, ev_free_ring[4] = {nullptr};
@@ -209,6 +212,25 @@ static const int RESULT_SLOTS = 1024;
 
 static int la_sync(La *la);
 static int wait_engine(La *la, int eng, uint64_t seq);
+
+static inline double now_s();
+// Host wait for an event: poll for a short while (most waits are for a few light kernels), then
+// block on the interrupt so that long waits (a search batch, a frame's copies) do not hold a core
+// -- a node runs 2 threads per stream, usually more than it has cores once several GPUs are used.
+static int wait_event(La *la, cudaEvent_t ev)
+{
+    if (la->blocking && la->spin_us > 0) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(ev);
+            if (q == cudaSuccess) return 0;
+            if (q != cudaErrorNotReady) { set_error("cudaEventQuery failed: %s", cudaGetErrorString(q)); return -1; }
+            if (std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() > la->spin_us) break;
+        }
+    }
+    LA_CUDA(cudaEventSynchronize(ev));
+    return 0;
+}
 
 static cudaEvent_t prof_event(La *la)
 {
@@ -253,7 +275,7 @@ static Frame *frame_alloc(La *la)
     const size_t o_rs = take((size_t)(B + 2) * (B + 2) * la->g.mb_h * 4);
     const size_t o_stats = take(64);
     if (cudaMalloc((void **)&f->arena, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed for a lookahead frame", off); delete f; return nullptr; }
-    if (cudaMallocHost((void **)&f->h_stats, 64) != cudaSuccess || cudaEventCreateWithFlags(&f->ev_stats, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaMallocHost failed"); cudaFree(f->arena); delete f; return nullptr; }
+    if (cudaMallocHost((void **)&f->h_stats, 64) != cudaSuccess || cudaEventCreateWithFlags(&f->ev_stats, cudaEventDisableTiming | (la->blocking ? cudaEventBlockingSync : 0)) != cudaSuccess) { set_error("cudaMallocHost failed"); cudaFree(f->arena); delete f; return nullptr; }
     f->lowres = f->arena + o_lowres;
     f->intra_cost = (uint16_t *)(f->arena + o_intra); f->inv_qscale = (uint16_t *)(f->arena + o_invq);
     f->propagate = (int *)(f->arena + o_prop);
@@ -350,7 +372,8 @@ static int la_sync(La *la)
     struct Acc { La *l; double t; ~Acc() { l->t_sync += now_s() - t; } } acc{la, t0};
     if (!la->pending.empty())
         LA_CUDA(cudaMemcpyAsync(la->h_results, la->d_results, RESULT_SLOTS * 4 * sizeof(int), cudaMemcpyDeviceToHost, la->st));
-    LA_CUDA(cudaStreamSynchronize(la->st));
+    if (la->blocking) { LA_CUDA(cudaEventRecord(la->ev_sync, la->st)); if (wait_event(la, la->ev_sync) < 0) return -1; }
+    else LA_CUDA(cudaStreamSynchronize(la->st));
     la->n_sync++;
     la->t_sync_kind[la->sync_kind] += now_s() - t0; la->n_sync_kind[la->sync_kind]++; la->sync_kind = 0;
     if (!la->prof.recs.empty()) prof_resolve(la);
@@ -375,7 +398,7 @@ static int ensure_stats(La *la, Frame *f)
 {
     if (f->stats_ready) return 0;
     // the AQ kernel + async copy of this frame were enqueued at put time: wait for that copy only
-    LA_CUDA(cudaEventSynchronize(f->ev_stats));
+    if (wait_event(la, f->ev_stats) < 0) return -1;
     // [x264] x264_adaptive_quant_frame: "Remove mean from SSD calculation"
     const int cf = la->p.chroma_format;
     for (int i = 0; i < 3; i++) {
@@ -1336,7 +1359,7 @@ static int process_frame(La *la, Frame *f, const x264vfw_cuda_image_t &planes, c
     if (ev_csp) {
         // Wait for the conversion HERE, on the host, not in the main stream: a stream-side wait
         // would make the next decision's synchronisation wait for this frame's copies as well.
-        if (cudaEventQuery(ev_csp) != cudaSuccess) { const double t0 = now_s(); XV_CUDA_OK(cudaEventSynchronize(ev_csp)); la->t_csp_wait += now_s() - t0; }
+        if (cudaEventQuery(ev_csp) != cudaSuccess) { const double t0 = now_s(); if (wait_event(la, ev_csp) < 0) return -1; la->t_csp_wait += now_s() - t0; }
         XV_CUDA_OK(cudaStreamWaitEvent(la->st, ev_csp, 0));
     }
     // ---- [x264] x264_adaptive_quant_frame ----
@@ -1533,6 +1556,11 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_ME_PASSES")) { la->me_passes = atoi(e); if (la->me_passes < 1) la->me_passes = 1; if (la->me_passes > 4) la->me_passes = 4; }
     if (const char *e = getenv("X264VFW_CUDA_ME_GUESS")) la->me_guess = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ASYNC")) la->async = atoi(e);
+    if (const char *e = getenv("X264VFW_CUDA_SYNC")) {      // spin (default) | block | hybrid | hybrid:<microseconds>
+        la->blocking = strcmp(e, "spin") != 0;
+        if (!strcmp(e, "block")) la->spin_us = 0;
+        else if (!strncmp(e, "hybrid:", 7)) la->spin_us = atoi(e + 7);
+    }
     if (const char *e = getenv("X264VFW_CUDA_IO_DEPTH")) { la->io_depth = atoi(e); if (la->io_depth < 1) la->io_depth = 1; if (la->io_depth > 4) la->io_depth = 4; }
     if (const char *e = getenv("X264VFW_CUDA_ME_ROWS")) la->me_rows = atoi(e);
     else la->me_rows = -1;   // resolved below once the geometry is known
@@ -1582,7 +1610,8 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
                   cudaMemcpy(la->d_exp2_lut, e2, 64, cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&la->d_weight_buf, g.lplane + 64) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&la->ev_io, cudaEventDisableTiming | (getenv("X264VFW_CUDA_BLOCKING_IO") ? cudaEventBlockingSync : 0)) == cudaSuccess &&
+             cudaEventCreateWithFlags(&la->ev_io, cudaEventDisableTiming | (la->blocking ? cudaEventBlockingSync : 0)) == cudaSuccess &&
+             cudaEventCreateWithFlags(&la->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_csp, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_planes_free, cudaEventDisableTiming) == cudaSuccess &&
@@ -1630,7 +1659,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
         bool ok = cudaStreamCreateWithPriority(&la->st_io, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
         for (int k = 0; k < la->io_depth && ok; k++) {
             ok = cudaMalloc((void **)&la->d_planes_ring[k], la->d_planes_bytes + 256) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&la->ev_csp_ring[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&la->ev_csp_ring[k], cudaEventDisableTiming | (la->blocking ? cudaEventBlockingSync : 0)) == cudaSuccess &&
                  cudaEventCreateWithFlags(&la->ev_free_ring[k], cudaEventDisableTiming) == cudaSuccess;
             if (ok) x264vfw_cuda_picture_layout(&la->planes_ring[k], la->d_planes_ring[k], out_csp, p.width, p.height);
         }
@@ -1696,6 +1725,7 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     }
     if (la->ev_ready) cudaEventDestroy(la->ev_ready);
     if (la->ev_io) cudaEventDestroy(la->ev_io);
+    if (la->ev_sync) cudaEventDestroy(la->ev_sync);
     if (la->ev_h2d) cudaEventDestroy(la->ev_h2d);
     if (la->ev_csp) cudaEventDestroy(la->ev_csp);
     if (la->ev_planes_free) cudaEventDestroy(la->ev_planes_free);
@@ -1822,7 +1852,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         }
         la->n_put++;
         la->t_put += now_s() - t_begin;
-        if (borrowed) { const double t0 = now_s(); XV_CUDA_OK(cudaEventSynchronize(la->ev_io)); la->t_io += now_s() - t0; }
+        if (borrowed) { const double t0 = now_s(); if (wait_event(la, la->ev_io) < 0) return -1; la->t_io += now_s() - t0; }
         if (borrowed && la->d_me_stats && la->io_ev[0]) {
             for (int k = 0; k < 4; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, la->io_ev[k], la->io_ev[k + 1]) == cudaSuccess) la->io_ms[k] += ms; }
             la->io_n++;
@@ -1881,7 +1911,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     }
     la->t_decide += t_dec;
     la->t_put += (la->decide_lag == 0 ? t_mid - t_begin : now_s() - t_begin - t_dec);
-    if (borrowed) { const double t0 = now_s(); XV_CUDA_OK(cudaEventSynchronize(la->ev_io)); la->t_io += now_s() - t0; }
+    if (borrowed) { const double t0 = now_s(); if (wait_event(la, la->ev_io) < 0) return -1; la->t_io += now_s() - t0; }
     if (borrowed && la->d_me_stats && la->io_ev[0]) {
         for (int k = 0; k < 4; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, la->io_ev[k], la->io_ev[k + 1]) == cudaSuccess) la->io_ms[k] += ms; }
         la->io_n++;
