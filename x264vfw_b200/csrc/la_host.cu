@@ -23,6 +23,7 @@
 #include <deque>
 #include <string>
 #include <thread>
+#include <sched.h>
 #include <mutex>
 #include <condition_variable>
 #include <atomic>
@@ -188,7 +189,7 @@ struct La {
     int async = 1;
     // host waits: spin (lowest latency; one busy core per waiting thread) or block on an interrupt
     // (X264VFW_CUDA_SYNC=block: for hosts with fewer cores than session threads)
-    bool blocking = false; int spin_us = 60; cudaEvent_t ev_sync = nullptr;   // default: spin; hybrid: spin for spin_us, then block
+    bool blocking = false, yielding = false; int spin_us = 60; cudaEvent_t ev_sync = nullptr;   // default: spin; hybrid: spin for spin_us, then block
     int io_depth = 2;                           // planes ring: frames the caller may run ahead of the worker
     uint8_t *d_planes_ring[4] = {nullptr}; x264vfw_cuda_image_t planes_ring[4];
     cudaEvent_t ev_csp_ring[4] = {nullptr}, ev_free_ring[4] = {nullptr};
@@ -219,6 +220,15 @@ static inline double now_s();
 // -- a node runs 2 threads per stream, usually more than it has cores once several GPUs are used.
 static int wait_event(La *la, cudaEvent_t ev)
 {
+    if (la->yielding) {
+        // poll, but give the core away between polls: for nodes with more session threads than cores
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(ev);
+            if (q == cudaSuccess) return 0;
+            if (q != cudaErrorNotReady) { set_error("cudaEventQuery failed: %s", cudaGetErrorString(q)); return -1; }
+            sched_yield();
+        }
+    }
     if (la->blocking && la->spin_us > 0) {
         const auto t0 = std::chrono::steady_clock::now();
         for (;;) {
@@ -372,7 +382,7 @@ static int la_sync(La *la)
     struct Acc { La *l; double t; ~Acc() { l->t_sync += now_s() - t; } } acc{la, t0};
     if (!la->pending.empty())
         LA_CUDA(cudaMemcpyAsync(la->h_results, la->d_results, RESULT_SLOTS * 4 * sizeof(int), cudaMemcpyDeviceToHost, la->st));
-    if (la->blocking) { LA_CUDA(cudaEventRecord(la->ev_sync, la->st)); if (wait_event(la, la->ev_sync) < 0) return -1; }
+    if (la->blocking || la->yielding) { LA_CUDA(cudaEventRecord(la->ev_sync, la->st)); if (wait_event(la, la->ev_sync) < 0) return -1; }
     else LA_CUDA(cudaStreamSynchronize(la->st));
     la->n_sync++;
     la->t_sync_kind[la->sync_kind] += now_s() - t0; la->n_sync_kind[la->sync_kind]++; la->sync_kind = 0;
@@ -1556,8 +1566,9 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_ME_PASSES")) { la->me_passes = atoi(e); if (la->me_passes < 1) la->me_passes = 1; if (la->me_passes > 4) la->me_passes = 4; }
     if (const char *e = getenv("X264VFW_CUDA_ME_GUESS")) la->me_guess = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ASYNC")) la->async = atoi(e);
-    if (const char *e = getenv("X264VFW_CUDA_SYNC")) {      // spin (default) | block | hybrid | hybrid:<microseconds>
-        la->blocking = strcmp(e, "spin") != 0;
+    if (const char *e = getenv("X264VFW_CUDA_SYNC")) {      // spin (default) | yield | block | hybrid | hybrid:<microseconds>
+        la->yielding = !strcmp(e, "yield");
+        la->blocking = strcmp(e, "spin") != 0 && !la->yielding;
         if (!strcmp(e, "block")) la->spin_us = 0;
         else if (!strncmp(e, "hybrid:", 7)) la->spin_us = atoi(e + 7);
     }
