@@ -142,6 +142,16 @@ int x264vfw_cuda_luma_pad( x264vfw_cuda_ctx *ctx, uint8_t *dst_dev, const uint8_
                            int y_stride, int i_width, int i_height,
                            size_t src_frame_bytes, size_t dst_frame_bytes, int n_frames );
 
+/* [x264] x264_frame_copy_picture (chroma part of a 4:2:0 frame: planar U, V interleaved into the
+ * encoder's internal NV12 plane) + x264_frame_expand_border_mod16 for that plane: (w/2)x(h/2) U
+ * and V -> dst_stride x (luma_h/2) bytes, the last U/V pair and the last row replicated out to
+ * the mod-16 size.  Together with _luma_pad this is the internal frame libx264 builds from
+ * conv_pic (codec.c:1673,1774 produce it; entered via codec.c:1693).  n_frames frames per launch. */
+int x264vfw_cuda_chroma_nv12_pad( x264vfw_cuda_ctx *ctx, uint8_t *dst_dev, int dst_stride,
+                                  const uint8_t *u_dev, const uint8_t *v_dev, int c_stride,
+                                  int i_width, int i_height,
+                                  size_t src_frame_bytes, size_t dst_frame_bytes, int n_frames );
+
 /* [x264] x264_frame_init_lowres = frame_init_lowres_core + x264_frame_expand_border_lowres:
  * writes the four padded half-pel phase planes (0,H,V,C), consecutive in dst_dev
  * (4*lplane_bytes per frame).  src_dev is the TIGHT w*h luma; the mod-16 replication is

@@ -41,6 +41,23 @@ void orc_luma_pad(uint8_t *dst, int dst_stride, const uint8_t *y, int y_stride, 
     memcpy(dst + (size_t)lh * dst_stride, dst + (size_t)(lh - 1) * dst_stride, lw + 1);
 }
 
+/* [x264] common/frame.c: x264_frame_copy_picture, 4:2:0 chroma (common/mc.c: plane_copy_interleave)
+ * followed by x264_frame_expand_border_mod16 for the chroma plane: the last U/V pair is repeated to
+ * the right, the last row downwards.  dst: dst_stride x (luma_h/2), luma_w bytes per row used. */
+void orc_chroma_nv12_pad(uint8_t *dst, int dst_stride, const uint8_t *u, const uint8_t *v, int c_stride, int w, int h)
+{
+    int g[10];
+    orc_lowres_geometry(w, h, g);
+    const int lw = g[2], lh = g[3];
+    const int cw = w / 2, ch = h / 2;
+    for (int r = 0; r < ch; r++) {
+        uint8_t *d = dst + (size_t)r * dst_stride;
+        for (int x = 0; x < cw; x++) { d[2 * x] = u[(size_t)r * c_stride + x]; d[2 * x + 1] = v[(size_t)r * c_stride + x]; }
+        for (int x = cw; x < lw / 2; x++) { d[2 * x] = d[2 * cw - 2]; d[2 * x + 1] = d[2 * cw - 1]; }
+    }
+    for (int r = ch; r < lh / 2; r++) memcpy(dst + (size_t)r * dst_stride, dst + (size_t)(ch - 1) * dst_stride, lw);
+}
+
 static inline int filt(int a, int b, int c, int d) { return (((a + b + 1) >> 1) + ((c + d + 1) >> 1) + 1) >> 1; }
 
 /* step 2+3: frame_init_lowres_core over the padded luma, then 32-px edge replication.

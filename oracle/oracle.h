@@ -49,6 +49,7 @@ void orc_lcg_fill(uint8_t *p, size_t n, int w, int h);
  * luma_stride lw lh lstride lplane_bytes lorigin (same geometry as the CUDA library). */
 void orc_lowres_geometry(int w, int h, int g[10]);
 void orc_luma_pad(uint8_t *dst, int dst_stride, const uint8_t *y, int y_stride, int w, int h);
+void orc_chroma_nv12_pad(uint8_t *dst, int dst_stride, const uint8_t *u, const uint8_t *v, int c_stride, int w, int h);
 void orc_lowres_init(uint8_t *dst4planes, const uint8_t *y, int y_stride, int w, int h);
 
 #ifdef __cplusplus

@@ -178,6 +178,15 @@ def oracle_luma_pad(y: np.ndarray, w, h):
 
 
 # ---- stage 2: lookahead oracle -------------------------------------------------------------
+def oracle_chroma_nv12_pad(u: np.ndarray, v: np.ndarray, w, h):
+    g = lowres_geometry(w, h)
+    o = oracle()
+    out = np.zeros(g["luma_w"] * (g["luma_h"] // 2), dtype=np.uint8)
+    o.orc_chroma_nv12_pad.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    o.orc_chroma_nv12_pad(out.ctypes.data, g["luma_w"], u.ctypes.data, v.ctypes.data, w // 2, w, h)
+    return out
+
+
 class LaParams(C.Structure):
     """orc_la_params / x264vfw_cuda_la_params (same field order)."""
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("chroma_format", C.c_int), ("bframes", C.c_int),

@@ -56,3 +56,23 @@ def test_luma_pad_matches_oracle(ctx, size):
     got = d_out.cpu().numpy().reshape(g.luma_h + 1, g.luma_stride)[:, :g.luma_w + 1]
     want = ol.oracle_luma_pad(y, w, h).reshape(g.luma_h + 1, g.luma_stride)[:, :g.luma_w + 1]
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("size", [(64, 48), (66, 50), (34, 18), (1920, 1080)])
+def test_chroma_nv12_pad_matches_oracle(ctx, size):
+    """[x264] x264_frame_copy_picture chroma (planar U, V -> NV12) + expand_border_mod16 on the device."""
+    import torch
+    from x264vfw_b200 import lowres
+    w, h = size
+    g = lowres.geometry(w, h)
+    rng = np.random.default_rng(w + 7 * h)
+    u = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+    v = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+    d_u, d_v = torch.from_numpy(u).cuda(), torch.from_numpy(v).cuda()
+    d_out = torch.zeros(g.luma_w * (g.luma_h // 2), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    lowres.chroma_nv12_pad(ctx, d_out.data_ptr(), g.luma_w, d_u.data_ptr(), d_v.data_ptr(), w // 2, w, h)
+    ctx.sync()
+    got = d_out.cpu().numpy()
+    want = ol.oracle_chroma_nv12_pad(u, v, w, h)
+    assert np.array_equal(got, want)

@@ -56,3 +56,20 @@ def test_lowres_constant_and_padding_properties():
     for k in range(4):
         inner = out[k, 32:32 + g["lh"], 32:32 + g["lw"]]
         assert np.array_equal(out[k, :, :g["lw"] + 64], np.pad(inner, 32, mode="edge"))
+
+
+@pytest.mark.parametrize("size", [(64, 48), (66, 50), (34, 18), (1920, 1080)])
+def test_chroma_nv12_pad_oracle_against_numpy(size):
+    """x264_frame_copy_picture (4:2:0 chroma -> NV12) + expand_border_mod16, independent numpy formulation."""
+    w, h = size
+    g = ol.lowres_geometry(w, h)
+    rng = np.random.default_rng(w * 31 + h)
+    u = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+    v = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+    got = ol.oracle_chroma_nv12_pad(u, v, w, h).reshape(g["luma_h"] // 2, g["luma_w"])
+    rows = np.minimum(np.arange(g["luma_h"] // 2), h // 2 - 1)
+    cols = np.minimum(np.arange(g["luma_w"] // 2), w // 2 - 1)
+    want = np.empty_like(got)
+    want[:, 0::2] = u[rows][:, cols]
+    want[:, 1::2] = v[rows][:, cols]
+    assert np.array_equal(got, want)

@@ -55,6 +55,8 @@ def _load():
         "x264vfw_cuda_lowres_geometry": (None, [P(LowresGeom), C.c_int, C.c_int]),
         "x264vfw_cuda_luma_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                             C.c_size_t, C.c_size_t, C.c_int]),
+        "x264vfw_cuda_chroma_nv12_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                   C.c_size_t, C.c_size_t, C.c_int]),
         "x264vfw_cuda_lowres_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                C.c_size_t, C.c_size_t, C.c_int]),
     }

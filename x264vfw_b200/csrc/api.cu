@@ -431,4 +431,20 @@ int x264vfw_cuda_luma_pad(x264vfw_cuda_ctx *ctx, uint8_t *dst, const uint8_t *y,
     return launch_luma_pad(c->stream, j, n_frames);
 }
 
+int x264vfw_cuda_chroma_nv12_pad(x264vfw_cuda_ctx *ctx, uint8_t *dst, int dst_stride, const uint8_t *u, const uint8_t *v,
+                                 int c_stride, int w, int h, size_t sfb, size_t dfb, int n_frames)
+{
+    if (!ctx || !dst || !u || !v) { set_error("null argument"); return -1; }
+    if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) { set_error("width/height must be positive and even"); return -1; }
+    Ctx *c = (Ctx *)ctx;
+    XV_CUDA_OK(cudaSetDevice(c->device));
+    x264vfw_cuda_lowres_geom g;
+    x264vfw_cuda_lowres_geometry(&g, w, h);
+    if (dst_stride < g.luma_w) { set_error("chroma plane stride %d < %d", dst_stride, g.luma_w); return -1; }
+    ChromaPadJob j;
+    j.u = u; j.v = v; j.c_stride = c_stride; j.w = w; j.h = h; j.dst = dst; j.dst_stride = dst_stride;
+    j.luma_w = g.luma_w; j.luma_h = g.luma_h; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
+    return launch_chroma_nv12_pad(c->stream, j, n_frames);
+}
+
 } // extern "C"

@@ -73,4 +73,11 @@ struct LumaPadJob {
 };
 int launch_luma_pad(cudaStream_t st, const LumaPadJob &job, int n_frames);
 
+struct ChromaPadJob {
+    const uint8_t *u, *v; int c_stride; int w, h;     // planar 4:2:0 chroma, (w/2) x (h/2) each; w, h = luma size
+    uint8_t *dst; int dst_stride; int luma_w, luma_h;  // interleaved plane, luma_w bytes x luma_h/2 rows
+    size_t src_frame_bytes, dst_frame_bytes;
+};
+int launch_chroma_nv12_pad(cudaStream_t st, const ChromaPadJob &job, int n_frames);
+
 } // namespace xv

@@ -138,4 +138,45 @@ int launch_luma_pad(cudaStream_t st, const LumaPadJob &job, int n_frames)
     return 0;
 }
 
+// [x264] x264_frame_copy_picture, chroma of a 4:2:0 frame (plane_copy_interleave: planar U, V ->
+// the encoder's interleaved NV12 plane) + x264_frame_expand_border_mod16 for that plane (the last
+// U/V PAIR replicated to the right, the last row downwards): one clamped gather, 4 pairs per thread.
+__global__ void __launch_bounds__(256)
+chroma_nv12_pad_kernel(ChromaPadJob job)
+{
+    const int chunks = (job.luma_w / 2 + 3) >> 2;          // 4 UV pairs (8 bytes) per thread
+    const int rows = job.luma_h / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= chunks * rows) return;
+    const int row = idx / chunks;
+    const int p0 = (idx - row * chunks) << 2;               // first pair of this thread
+    const size_t f = blockIdx.y;
+    const int cw = job.w / 2, ch = job.h / 2;
+    const int srow = min(row, ch - 1);
+    const uint8_t *u = job.u + f * job.src_frame_bytes + (size_t)srow * job.c_stride;
+    const uint8_t *v = job.v + f * job.src_frame_bytes + (size_t)srow * job.c_stride;
+    uint8_t *d = job.dst + f * job.dst_frame_bytes + (size_t)row * job.dst_stride + 2 * p0;
+    const int npairs = min(4, job.luma_w / 2 - p0);
+    if (npairs == 4 && p0 + 4 <= cw && (((uintptr_t)u | (uintptr_t)v | (uintptr_t)job.c_stride) & 3) == 0 && (p0 & 3) == 0 &&
+        (((uintptr_t)d | (uintptr_t)job.dst_stride) & 7) == 0) {
+        const uint32_t uu = ldg_stream32(u + p0), vv = ldg_stream32(v + p0);
+        *(uint2 *)d = make_uint2(__byte_perm(uu, vv, 0x5140), __byte_perm(uu, vv, 0x7362));
+    } else {
+        for (int i = 0; i < npairs; i++) {
+            const int sp = min(p0 + i, cw - 1);
+            d[2 * i] = u[sp]; d[2 * i + 1] = v[sp];
+        }
+    }
+}
+
+int launch_chroma_nv12_pad(cudaStream_t st, const ChromaPadJob &job, int n_frames)
+{
+    const long long total = (long long)((job.luma_w / 2 + 3) >> 2) * (job.luma_h / 2);
+    if (total <= 0 || n_frames <= 0) return 0;
+    dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_frames);
+    chroma_nv12_pad_kernel<<<grid, 256, 0, st>>>(job);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
 } // namespace xv

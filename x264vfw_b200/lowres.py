@@ -27,3 +27,12 @@ def luma_pad(ctx: Context, d_dst: int, d_y: int, y_stride: int, width: int, heig
                                    src_frame_bytes, dst_frame_bytes, n_frames)
     if rc < 0:
         raise CudaError(last_error())
+
+
+def chroma_nv12_pad(ctx: Context, d_dst: int, dst_stride: int, d_u: int, d_v: int, c_stride: int, width: int, height: int,
+                    src_frame_bytes: int = 0, dst_frame_bytes: int = 0, n_frames: int = 1):
+    """[x264] x264_frame_copy_picture chroma (planar U, V -> NV12) + x264_frame_expand_border_mod16."""
+    rc = lib.x264vfw_cuda_chroma_nv12_pad(ctx.handle, C.c_void_p(d_dst), dst_stride, C.c_void_p(d_u), C.c_void_p(d_v), c_stride,
+                                          width, height, src_frame_bytes, dst_frame_bytes, n_frames)
+    if rc < 0:
+        raise CudaError(last_error())
