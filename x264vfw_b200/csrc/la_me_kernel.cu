@@ -1,4 +1,7 @@
-// Lowres motion search: the serial core of the lookahead, as a row-pipelined wavefront.
+// Lowres motion search, PLAIN WAVEFRONT: the whole search in dependency order, one warp per MB row.
+// This was the round's first design and is now the fallback (X264VFW_CUDA_ME_VARIANT=0); sessions
+// use the speculative passes + verification wavefront of la_me2_kernel.cu, which
+// produce the same MVs and costs bit for bit.
 //
 // Restates, for one (frame, reference, list) pair, the search that [x264]
 // encoder/slicetype.c: slicetype_mb_cost runs per 8x8 lowres MB in reverse raster order:
