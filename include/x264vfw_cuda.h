@@ -160,6 +160,29 @@ int x264vfw_cuda_lowres_init( x264vfw_cuda_ctx *ctx, uint8_t *dst_dev, const uin
                               int y_stride, int i_width, int i_height,
                               size_t src_frame_bytes, size_t dst_frame_bytes, int n_frames );
 
+/* ---- half-pel reference planes of a reconstructed frame ------------------
+ * [x264] x264_frame_expand_border + x264_frame_filter (x264_mc_functions_t.hpel_filter) +
+ * x264_frame_expand_border_filtered for a progressive 8-bit luma plane: what libx264 runs on every
+ * reconstructed reference frame inside x264_encoder_encode (codec.c:1693) before the next frame's
+ * motion search can read frame->filtered[0][0..3].  Geometry of one padded plane: */
+typedef struct x264vfw_cuda_hpel_geom
+{
+    int stride;              /* bytes per row: (w + 2*32) rounded up to 64                */
+    int plane_bytes;         /* stride * (h + 2*32)                                       */
+    int origin;              /* offset of pixel (0,0) inside a padded plane               */
+} x264vfw_cuda_hpel_geom;
+
+void x264vfw_cuda_hpel_geometry( x264vfw_cuda_hpel_geom *g, int i_width, int i_height );
+
+/* src_dev: tight i_width x i_height plane (upstream: 16*mb_w x 16*mb_h; i_width % 4 == 0 required).
+ * dst_dev: four padded planes per frame, consecutive (4*plane_bytes): [0] the frame with its 32-pixel
+ * replicated border, [1] H, [2] V, [3] centre half-pel planes, each complete including the border
+ * (the filter is evaluated 8 pixels beyond the frame and replicated from 4 columns / 8 rows outside,
+ * exactly as upstream).  Bit-exact to upstream's C hpel_filter.  n_frames frames per launch. */
+int x264vfw_cuda_hpel_filter( x264vfw_cuda_ctx *ctx, uint8_t *dst_dev, const uint8_t *src_dev,
+                              int src_stride, int i_width, int i_height,
+                              size_t src_frame_bytes, size_t dst_frame_bytes, int n_frames );
+
 /* ------------------------------------------------------------------------------------
  * B2: the lookahead session.  Replaces what happens between x264_encoder_encode receiving
  * a picture (codec.c:1693) and the frame type / per-MB qp offsets being known:

@@ -52,6 +52,10 @@ void orc_luma_pad(uint8_t *dst, int dst_stride, const uint8_t *y, int y_stride, 
 void orc_chroma_nv12_pad(uint8_t *dst, int dst_stride, const uint8_t *u, const uint8_t *v, int c_stride, int w, int h);
 void orc_lowres_init(uint8_t *dst4planes, const uint8_t *y, int y_stride, int w, int h);
 
+/* ---- next row f3: half-pel reference planes (hpel_oracle.c).  g[3] = stride plane_bytes origin. */
+void orc_hpel_geometry(int w, int h, int g[3]);
+void orc_hpel_planes(uint8_t *dst4planes, const uint8_t *src, int src_stride, int w, int h);
+
 #ifdef __cplusplus
 }
 #endif

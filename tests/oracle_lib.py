@@ -177,6 +177,49 @@ def oracle_luma_pad(y: np.ndarray, w, h):
     return out
 
 
+# ---- next row f3: half-pel reference planes ---------------------------------------------------
+def hpel_geometry(w, h):
+    g = (C.c_int * 3)()
+    o = oracle()
+    o.orc_hpel_geometry.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    o.orc_hpel_geometry(w, h, g)
+    return dict(zip(("stride", "plane_bytes", "origin"), list(g)))
+
+
+def oracle_hpel_planes(y: np.ndarray, w, h):
+    """y: tight (h, w) uint8 reconstructed plane.  Returns (4, h+64, stride): P0, H, V, C, all padded."""
+    g = hpel_geometry(w, h)
+    y = np.ascontiguousarray(y, dtype=np.uint8)
+    out = np.zeros(4 * g["plane_bytes"], dtype=np.uint8)
+    o = oracle()
+    o.orc_hpel_planes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    o.orc_hpel_planes(out.ctypes.data, y.ctypes.data, w, w, h)
+    return out.reshape(4, h + 64, g["stride"])
+
+
+def numpy_hpel_planes(y: np.ndarray):
+    """Independent formulation of the same planes (no borders materialised, no loops over pixels):
+    Pi(x,y) = Fi(clamp(x,-4,w+3), clamp(y,-8,h+7)) with Fi the 6-tap filter on the edge-clamped frame."""
+    h, w = y.shape
+    P = 32
+    ext = np.pad(y.astype(np.int64), P + 8, mode="edge")        # frame with an (ample) replicated border
+    o = P + 8                                                    # index of pixel (0,0) in ext
+
+    def tap(a, axis):
+        r = lambda k: np.roll(a, -k, axis=axis)
+        return r(-2) + r(3) - 5 * (r(-1) + r(2)) + 20 * (r(0) + r(1))
+
+    v16 = tap(ext, 0)
+    fh = np.clip((tap(ext, 1) + 16) >> 5, 0, 255)
+    fv = np.clip((v16 + 16) >> 5, 0, 255)
+    fc = np.clip((tap(v16, 1) + 512) >> 10, 0, 255)
+    ys = np.clip(np.arange(-P, h + P), -8, h + 7) + o
+    xs = np.clip(np.arange(-P, w + P), -4, w + 3) + o
+    out = [ext[o - P:o + h + P, o - P:o + w + P]]
+    out += [f[np.ix_(ys, xs)] for f in (fh, fv, fc)]
+    return np.stack(out).astype(np.uint8)                        # (4, h+64, w+64)
+
+
 # ---- stage 2: lookahead oracle -------------------------------------------------------------
 def oracle_chroma_nv12_pad(u: np.ndarray, v: np.ndarray, w, h):
     g = lowres_geometry(w, h)

@@ -1,0 +1,98 @@
+"""GPU parity: the half-pel reference plane kernel through the C ABI vs the CPU checker,
+bit-exact on all four padded planes including every border byte."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from x264vfw_b200._lib import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _content(w, h, kind, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, (h, w), dtype=np.uint8)
+    if kind == "extreme":                      # drives every 6-tap sum and the centre intermediate to its limits
+        return (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)
+    return np.tile((np.arange(w) % 2 * 255).astype(np.uint8), (h, 1))
+
+
+@pytest.mark.parametrize("size", [(16, 16), (64, 48), (112, 18), (240, 64), (1280, 720), (1920, 1088), (3840, 2160), (20, 6)])
+@pytest.mark.parametrize("kind", ["noise", "extreme"])
+def test_hpel_filter_matches_checker(ctx, size, kind):
+    import torch
+    from x264vfw_b200 import hpel
+    w, h = size
+    nf = 2 if w * h < 4_000_000 else 1
+    g = hpel.geometry(w, h)
+    og = ol.hpel_geometry(w, h)
+    assert (g.stride, g.plane_bytes, g.origin) == (og["stride"], og["plane_bytes"], og["origin"])
+    sfb = (w * h + 255) // 256 * 256
+    dfb = 4 * g.plane_bytes
+    frames = [_content(w, h, kind, 11 * w + h + f) for f in range(nf)]
+    host = np.zeros(nf * sfb, dtype=np.uint8)
+    for f, y in enumerate(frames):
+        host[f * sfb:f * sfb + w * h] = y.reshape(-1)
+    d_src = torch.from_numpy(host).cuda()
+    d_out = torch.full((nf * dfb,), 0x5A, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    hpel.hpel_filter(ctx, d_out.data_ptr(), d_src.data_ptr(), w, w, h, sfb, dfb, nf)
+    ctx.sync()
+    got = d_out.cpu().numpy().reshape(nf, 4, h + 64, g.stride)
+    for f, y in enumerate(frames):
+        want = ol.oracle_hpel_planes(y, w, h)
+        for p in range(4):
+            assert np.array_equal(got[f, p, :, :w + 64], want[p, :, :w + 64]), (size, kind, f, p)
+    assert np.all(got[:, :, :, w + 64:] == 0x5A)
+
+
+def test_hpel_filter_unaligned_source_and_big_batch(ctx):
+    """Source plane at an odd address / odd stride (byte gathers) and a batch large enough for 24-row strips."""
+    import torch
+    from x264vfw_b200 import hpel
+    w, h, ss, off = 64, 32, 67, 1
+    g = hpel.geometry(w, h)
+    nf = 40
+    sfb = ss * h + 5
+    rng = np.random.default_rng(3)
+    host = rng.integers(0, 256, nf * sfb + 8, dtype=np.uint8)
+    d_src = torch.from_numpy(host).cuda()
+    d_out = torch.zeros(nf * 4 * g.plane_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    hpel.hpel_filter(ctx, d_out.data_ptr(), d_src.data_ptr() + off, ss, w, h, sfb, 4 * g.plane_bytes, nf)
+    ctx.sync()
+    got = d_out.cpu().numpy().reshape(nf, 4, h + 64, g.stride)
+    for f in (0, 17, nf - 1):
+        y = np.stack([host[off + f * sfb + r * ss: off + f * sfb + r * ss + w] for r in range(h)])
+        want = ol.oracle_hpel_planes(y, w, h)
+        assert np.array_equal(got[f, :, :, :w + 64], want[:, :, :w + 64]), f
+
+    # 1080p batch: 24-row strips
+    w, h = 1920, 1088
+    g = hpel.geometry(w, h)
+    nf = 8
+    sfb = w * h
+    host = rng.integers(0, 256, nf * sfb, dtype=np.uint8)
+    d_src = torch.from_numpy(host).cuda()
+    d_out = torch.zeros(nf * 4 * g.plane_bytes, dtype=torch.uint8, device="cuda")
+    hpel.hpel_filter(ctx, d_out.data_ptr(), d_src.data_ptr(), w, w, h, sfb, 4 * g.plane_bytes, nf)
+    ctx.sync()
+    got = d_out.cpu().numpy().reshape(nf, 4, h + 64, g.stride)
+    for f in (0, nf - 1):
+        want = ol.oracle_hpel_planes(host[f * sfb:(f + 1) * sfb].reshape(h, w), w, h)
+        assert np.array_equal(got[f, :, :, :w + 64], want[:, :, :w + 64]), f
+
+
+def test_hpel_filter_rejects_bad_geometry(ctx):
+    from x264vfw_b200 import hpel
+    from x264vfw_b200._lib import CudaError
+    with pytest.raises(CudaError):
+        hpel.hpel_filter(ctx, 256, 256, 18, 18, 16)

@@ -1,0 +1,87 @@
+"""Half-pel reference planes, CPU side:
+ * the C checker (oracle/hpel_oracle.c: upstream's literal sequence) against an independent numpy formulation
+   (clamped coordinates, no materialised borders);
+ * the CUDA warp program itself (x264vfw_b200/csrc/hpel_kernel.cuh), compiled by g++ against the lockstep warp
+   shim in tests/sim/ and run on the CPU, against the checker -- same source as the sm_100a build, so index
+   arithmetic, packed-lane biases and border ownership are verified before the kernel reaches a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _frames(w, h, seed):
+    rng = np.random.default_rng(seed)
+    noise = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    # saturating content: 0/255 blocks drive the 6-tap sums to both clip() limits and the centre
+    # plane's intermediate to its extremes
+    extreme = (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)
+    cols = np.tile((np.arange(w) % 2 * 255).astype(np.uint8), (h, 1))
+    return [noise, extreme, cols]
+
+
+@pytest.mark.parametrize("size", [(16, 16), (64, 48), (128, 32), (240, 64), (20, 6)])
+def test_checker_matches_numpy_formulation(size):
+    w, h = size
+    for i, y in enumerate(_frames(w, h, 7 * w + h)):
+        want = ol.numpy_hpel_planes(y)
+        got = ol.oracle_hpel_planes(y, w, h)[:, :, :w + 64]
+        assert np.array_equal(got, want), (size, i)
+
+
+def test_checker_plane0_is_the_border_expanded_frame():
+    w, h = 32, 16
+    y = np.arange(w * h, dtype=np.uint32).astype(np.uint8).reshape(h, w)
+    p0 = ol.oracle_hpel_planes(y, w, h)[0, :, :w + 64]
+    assert np.array_equal(p0, np.pad(y, 32, mode="edge"))
+
+
+@pytest.fixture(scope="module")
+def sim():
+    so = os.path.join(ROOT, "tests", "sim", "_build", "libhpel_sim.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    srcs = [os.path.join(ROOT, "tests", "sim", "hpel_sim.cpp"), os.path.join(ROOT, "tests", "sim", "warp_sim.h"),
+            os.path.join(ROOT, "x264vfw_b200", "csrc", "hpel_kernel.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, srcs[0],
+                        "-lpthread"], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.sim_hpel.restype = C.c_int
+    lib.sim_hpel.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int,
+                             C.c_size_t, C.c_size_t, C.c_int]
+    return lib
+
+
+# (w, h, rows_per_strip, source stride, source offset): one tile, two tiles with the right edge in the second,
+# the right edge exactly at lane 30, strips that end inside / beyond the frame, unaligned source (byte gathers)
+@pytest.mark.parametrize("case", [(16, 16, 12, 16, 0), (64, 48, 12, 64, 0), (112, 18, 6, 112, 0),
+                                  (128, 32, 24, 128, 0), (240, 20, 12, 240, 0), (64, 16, 12, 67, 1),
+                                  (20, 6, 12, 20, 0)])
+def test_warp_program_on_cpu_matches_checker(sim, case):
+    w, h, rps, ss, off = case
+    g = ol.hpel_geometry(w, h)
+    nf = 2
+    frames = _frames(w, h, w + 3 * h)[:nf]
+    sfb = ss * h + 16
+    src = np.zeros(nf * sfb + 8, dtype=np.uint8)
+    for f, y in enumerate(frames):
+        for r in range(h):
+            src[off + f * sfb + r * ss: off + f * sfb + r * ss + w] = y[r]
+    dfb = 4 * g["plane_bytes"]
+    dst = np.full(nf * dfb, 0x5A, dtype=np.uint8)
+    units = sim.sim_hpel(dst.ctypes.data, src.ctypes.data + off, ss, w, h, g["stride"], g["plane_bytes"], rps,
+                         sfb, dfb, nf)
+    assert units > 0
+    got = dst.reshape(nf, 4, h + 64, g["stride"])
+    for f, y in enumerate(frames):
+        want = ol.oracle_hpel_planes(y, w, h)
+        for p in range(4):
+            assert np.array_equal(got[f, p, :, :w + 64], want[p, :, :w + 64]), (case, f, p)
+        # nothing outside the w+64 columns is touched
+        assert np.all(got[f, :, :, w + 64:] == 0x5A)

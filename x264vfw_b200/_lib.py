@@ -29,6 +29,10 @@ class LowresGeom(C.Structure):
                                        "lw", "lh", "lstride", "lplane_bytes", "lorigin")]
 
 
+class HpelGeom(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("stride", "plane_bytes", "origin")]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise LibraryMissing(
@@ -57,6 +61,9 @@ def _load():
                                             C.c_size_t, C.c_size_t, C.c_int]),
         "x264vfw_cuda_chroma_nv12_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                    C.c_size_t, C.c_size_t, C.c_int]),
+        "x264vfw_cuda_hpel_geometry": (None, [P(HpelGeom), C.c_int, C.c_int]),
+        "x264vfw_cuda_hpel_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_size_t, C.c_size_t, C.c_int]),
         "x264vfw_cuda_lowres_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                C.c_size_t, C.c_size_t, C.c_int]),
     }

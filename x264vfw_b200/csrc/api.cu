@@ -6,6 +6,9 @@
 // (codec.c:1673).  Here the same decisions select a CUDA kernel + launch descriptor.
 #include "common.cuh"
 #include "csp_kernels.h"
+#define XV_DEVICE static inline      /* host view of hpel_kernel.cuh: the job descriptor only */
+#define XV_HPEL_HOST_ONLY
+#include "hpel_kernel.cuh"
 #include "../../include/x264vfw_cuda.h"
 #include <stdarg.h>
 #include <string.h>
@@ -445,6 +448,32 @@ int x264vfw_cuda_chroma_nv12_pad(x264vfw_cuda_ctx *ctx, uint8_t *dst, int dst_st
     j.u = u; j.v = v; j.c_stride = c_stride; j.w = w; j.h = h; j.dst = dst; j.dst_stride = dst_stride;
     j.luma_w = g.luma_w; j.luma_h = g.luma_h; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
     return launch_chroma_nv12_pad(c->stream, j, n_frames);
+}
+
+void x264vfw_cuda_hpel_geometry(x264vfw_cuda_hpel_geom *g, int w, int h)
+{
+    g->stride = (w + 64 + 63) & ~63;
+    g->plane_bytes = g->stride * (h + 64);
+    g->origin = 32 * g->stride + 32;
+}
+
+int x264vfw_cuda_hpel_filter(x264vfw_cuda_ctx *ctx, uint8_t *dst, const uint8_t *src, int src_stride, int w, int h,
+                             size_t sfb, size_t dfb, int n_frames)
+{
+    if (!ctx || !dst || !src) { set_error("null argument"); return -1; }
+    if (w <= 0 || h <= 0 || (w & 3)) { set_error("hpel: width must be a positive multiple of 4 (upstream: 16*mb_w)"); return -1; }
+    Ctx *c = (Ctx *)ctx;
+    XV_CUDA_OK(cudaSetDevice(c->device));
+    x264vfw_cuda_hpel_geom g;
+    x264vfw_cuda_hpel_geometry(&g, w, h);
+    if (!al(dst, 4) || !als((long long)dfb, 4)) { set_error("hpel dst must be 4-byte aligned"); return -1; }
+    if (n_frames > 1 && dfb < 4 * (size_t)g.plane_bytes) { set_error("hpel: dst_frame_bytes %zu < %zu", dfb, 4 * (size_t)g.plane_bytes); return -1; }
+    HpelJob j;
+    j.src = src; j.src_stride = src_stride; j.w = w; j.h = h;
+    j.dst = dst; j.stride = g.stride; j.plane_bytes = (size_t)g.plane_bytes;
+    j.rows_per_strip = 0;
+    j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
+    return launch_hpel(c->stream, j, n_frames);
 }
 
 } // extern "C"

@@ -80,4 +80,8 @@ struct ChromaPadJob {
 };
 int launch_chroma_nv12_pad(cudaStream_t st, const ChromaPadJob &job, int n_frames);
 
+// hpel_kernels.cu (the job descriptor is in hpel_kernel.cuh, shared with the CPU lockstep simulation)
+struct HpelJob;
+int launch_hpel(cudaStream_t st, HpelJob &job, int n_frames);
+
 } // namespace xv

@@ -1,0 +1,68 @@
+// Launcher of the half-pel reference plane kernel (hpel_kernel.cuh holds the warp program and its
+// description).  sm_100a device versions of the helpers the program uses.
+#include "common.cuh"
+#include "csp_kernels.h"
+
+#define XV_DEVICE __device__ __forceinline__
+
+namespace xv {
+
+__device__ __forceinline__ uint32_t xv_ld_u32(const uint8_t *p) { return __ldg((const uint32_t *)p); }
+__device__ __forceinline__ uint32_t xv_ld_u8(const uint8_t *p) { return __ldg(p); }
+__device__ __forceinline__ void xv_st_u32(uint8_t *p, uint32_t v) { asm volatile("st.global.b32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+// keeps the compiler from folding the frame's base back into every address computation
+__device__ __forceinline__ uint8_t *xv_opaque(uint8_t *p) { asm volatile("" : "+l"(p)); return p; }
+__device__ __forceinline__ uint32_t xv_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+__device__ __forceinline__ uint32_t xv_shfl_up1(uint32_t v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ uint32_t xv_shfl_down1(uint32_t v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ uint32_t xv_shfl_idx(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// per 16-bit lane: max(min(a + b, c), 0)  (DPX, VIADDMNMX-class on sm_90+)
+__device__ __forceinline__ uint32_t xv_addmin_relu_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
+// c + sum of four (unsigned byte of a) * (signed byte of b)
+__device__ __forceinline__ int xv_dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// c + (signed low half of a) * (signed byte 0 of b) + (signed high half of a) * (signed byte 1 of b)
+__device__ __forceinline__ int xv_dp2a_lo(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// bytes (sat(v0), sat(v1), sat(v2), sat(v3)), v0 in the low byte; sat = clamp to [0, 255]
+__device__ __forceinline__ uint32_t xv_pack_sat_u8(int v0, int v1, int v2, int v3)
+{
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(t) : "r"(v3), "r"(v2));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(t));
+    return d;
+}
+
+} // namespace xv
+
+#include "hpel_kernel.cuh"
+
+namespace xv {
+
+__global__ void __launch_bounds__(128)
+hpel_kernel(HpelJob job)
+{
+    const int unit = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (unit >= job.ntiles * job.nstrips) return;               // warp-uniform
+    hpel_unit(job, unit, blockIdx.y, threadIdx.x & 31);
+}
+
+int launch_hpel(cudaStream_t st, HpelJob &job, int n_frames)
+{
+    if (job.w <= 0 || job.h <= 0 || n_frames <= 0) return 0;
+    const long long units = hpel_plan(job, n_frames);
+    dim3 grid((unsigned)((units + 3) / 4), (unsigned)n_frames);
+    hpel_kernel<<<grid, 128, 0, st>>>(job);
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace xv
