@@ -38,6 +38,7 @@ SRC_BYTES = W * H * 4
 DST_BYTES = W * H * 3 // 2
 CSP_ALGO_BYTES = SRC_BYTES + DST_BYTES          # 11,404,800 B / frame
 LOWRES_ALGO_BYTES = 1920 * 1088 + 4 * 960 * 544   # 4,177,920 B / frame
+HPEL_ALGO_BYTES = 5 * 1920 * 1088                 # reconstructed plane in, 4 reference planes out: 10,444,800 B / frame
 
 
 def parse_args():
@@ -189,7 +190,7 @@ def stage1_roofline(torch, args):
     """Device-resident batch launches of the stage-1 kernels (the HBM-bound part of the path):
     CUDA events on the launching stream, inputs larger than L2."""
     import x264vfw_b200 as xv
-    from x264vfw_b200 import csp, lowres
+    from x264vfw_b200 import csp, lowres, hpel
     ctx = xv._lib.Context(torch.cuda.current_device())
     st = torch.cuda.ExternalStream(ctx.stream)
     nf = args.stage1_batch
@@ -214,8 +215,16 @@ def stage1_roofline(torch, args):
 
     t_csp = timeit(lambda: csp.convert_batch(ctx, src.data_ptr(), dst.data_ptr(), BGRA_FLIP, 2, 2, 0, W, H, nf))
     t_lr = timeit(lambda: lowres.lowres_init(ctx, lr.data_ptr(), dst.data_ptr(), W, W, H, dfb, 4 * g.lplane_bytes, nf))
+    # half-pel reference planes: a mod-16 reconstructed plane per frame, half the batch (4 padded
+    # output planes of 2.3 MB each per frame)
+    hg = hpel.geometry(W, 1088)
+    hn = max(1, nf // 2)
+    rec = torch.randint(0, 256, (hn * W * 1088,), dtype=torch.uint8, device="cuda")
+    hp = torch.empty(hn * 4 * hg.plane_bytes, dtype=torch.uint8, device="cuda")
+    t_hp = timeit(lambda: hpel.hpel_filter(ctx, hp.data_ptr(), rec.data_ptr(), W, W, 1088, W * 1088, 4 * hg.plane_bytes, hn))
     ctx.close()
-    return {"csp_bgra_to_i420": {"frames_per_launch": nf, "ms_per_launch": t_csp * 1e3, "gbs": CSP_ALGO_BYTES * nf / t_csp / 1e9},
+    return {"hpel_filter": {"frames_per_launch": hn, "ms_per_launch": t_hp * 1e3, "gbs": HPEL_ALGO_BYTES * hn / t_hp / 1e9},
+            "csp_bgra_to_i420": {"frames_per_launch": nf, "ms_per_launch": t_csp * 1e3, "gbs": CSP_ALGO_BYTES * nf / t_csp / 1e9},
             "lowres_init": {"frames_per_launch": nf, "ms_per_launch": t_lr * 1e3, "gbs": LOWRES_ALGO_BYTES * nf / t_lr / 1e9}}
 
 

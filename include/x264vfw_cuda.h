@@ -174,7 +174,7 @@ typedef struct x264vfw_cuda_hpel_geom
 
 void x264vfw_cuda_hpel_geometry( x264vfw_cuda_hpel_geom *g, int i_width, int i_height );
 
-/* src_dev: tight i_width x i_height plane (upstream: 16*mb_w x 16*mb_h; i_width % 4 == 0 required).
+/* src_dev: tight i_width x i_height plane (upstream: 16*mb_w x 16*mb_h; i_width % 8 == 0 required).
  * dst_dev: four padded planes per frame, consecutive (4*plane_bytes): [0] the frame with its 32-pixel
  * replicated border, [1] H, [2] V, [3] centre half-pel planes, each complete including the border
  * (the filter is evaluated 8 pixels beyond the frame and replicated from 4 columns / 8 rows outside,

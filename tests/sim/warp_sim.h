@@ -50,6 +50,16 @@ static inline void xv_st_u32(uint8_t *p, uint32_t v)
     if ((uintptr_t)p & 3) abort();                      // the device store needs 4-byte alignment
     memcpy(p, &v, 4);
 }
+static inline void xv_ld_u64(const uint8_t *p, uint32_t &x, uint32_t &y)
+{
+    if ((uintptr_t)p & 7) abort();                      // the device load needs 8-byte alignment
+    memcpy(&x, p, 4); memcpy(&y, p + 4, 4);
+}
+static inline void xv_st_u64(uint8_t *p, uint32_t x, uint32_t y)
+{
+    if ((uintptr_t)p & 7) abort();
+    memcpy(p, &x, 4); memcpy(p + 4, &y, 4);
+}
 static inline uint8_t *xv_opaque(uint8_t *p) { return p; }
 
 static inline uint32_t xv_prmt(uint32_t a, uint32_t b, uint32_t sel)

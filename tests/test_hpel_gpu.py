@@ -25,7 +25,7 @@ def _content(w, h, kind, seed):
     return np.tile((np.arange(w) % 2 * 255).astype(np.uint8), (h, 1))
 
 
-@pytest.mark.parametrize("size", [(16, 16), (64, 48), (112, 18), (240, 64), (1280, 720), (1920, 1088), (3840, 2160), (20, 6)])
+@pytest.mark.parametrize("size", [(16, 16), (64, 48), (112, 18), (240, 64), (1280, 720), (1920, 1088), (3840, 2160), (248, 12), (24, 6)])
 @pytest.mark.parametrize("kind", ["noise", "extreme"])
 def test_hpel_filter_matches_checker(ctx, size, kind):
     import torch
@@ -95,4 +95,4 @@ def test_hpel_filter_rejects_bad_geometry(ctx):
     from x264vfw_b200 import hpel
     from x264vfw_b200._lib import CudaError
     with pytest.raises(CudaError):
-        hpel.hpel_filter(ctx, 256, 256, 18, 18, 16)
+        hpel.hpel_filter(ctx, 256, 256, 20, 20, 16)

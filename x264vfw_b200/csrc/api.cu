@@ -461,12 +461,12 @@ int x264vfw_cuda_hpel_filter(x264vfw_cuda_ctx *ctx, uint8_t *dst, const uint8_t 
                              size_t sfb, size_t dfb, int n_frames)
 {
     if (!ctx || !dst || !src) { set_error("null argument"); return -1; }
-    if (w <= 0 || h <= 0 || (w & 3)) { set_error("hpel: width must be a positive multiple of 4 (upstream: 16*mb_w)"); return -1; }
+    if (w <= 0 || h <= 0 || (w & 7)) { set_error("hpel: width must be a positive multiple of 8 (upstream: 16*mb_w)"); return -1; }
     Ctx *c = (Ctx *)ctx;
     XV_CUDA_OK(cudaSetDevice(c->device));
     x264vfw_cuda_hpel_geom g;
     x264vfw_cuda_hpel_geometry(&g, w, h);
-    if (!al(dst, 4) || !als((long long)dfb, 4)) { set_error("hpel dst must be 4-byte aligned"); return -1; }
+    if (!al(dst, 8) || !als((long long)dfb, 8)) { set_error("hpel dst must be 8-byte aligned"); return -1; }
     if (n_frames > 1 && dfb < 4 * (size_t)g.plane_bytes) { set_error("hpel: dst_frame_bytes %zu < %zu", dfb, 4 * (size_t)g.plane_bytes); return -1; }
     HpelJob j;
     j.src = src; j.src_stride = src_stride; j.w = w; j.h = h;

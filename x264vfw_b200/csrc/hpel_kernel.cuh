@@ -12,16 +12,20 @@
 // so the kernel walks the domain [-4,w+4) x [-8,h+8) once, and the units that own its first / last
 // column or row also write the replicated border.  Read the frame once, write four padded planes once.
 //
-// Mapping.  A warp owns 30 32-bit words (120 pixels) of a strip of rows; lanes 0 and 31 carry the
-// neighbouring words (halo) so that everything horizontal is a shuffle.  The six source rows of the
-// vertical filter slide through registers (two packed 16-bit pairs per row, loop unrolled by six so
-// the rotation is register renaming).  Arithmetic per 4 pixels:
+// Mapping.  A lane owns 8 pixels (two 32-bit words) of a strip of rows, a warp 30 such lanes (240 pixels);
+// lanes 0 and 31 carry the neighbouring words (halo) so that everything horizontal is a shuffle, and the
+// shuffle's "no such lane -> own value" is exactly the clamped neighbour at the frame's left / right edge.
+// Tiles cover [0,w); the two words just outside ([-8,0) and [w,w+8)) are the halo lanes of the first /
+// last tile, which also own the replicated border.  The six source rows of the vertical filter slide
+// through registers (four packed 16-bit pairs per row, loop unrolled by six so the rotation is register
+// renaming).  Arithmetic:
 //   V  : packed 16-bit lanes, biased by 2576 = 80*32 + 16 so that lanes never go negative (no borrow between
 //        lanes) and the bias supplies the rounding term; >>5, per-lane add/min/relu (DPX) gives clip().
-//   H  : two dp4a per pixel on byte windows cut out of (left, own, right) words with PRMT.
+//   H  : two dp4a per pixel on byte windows cut out of (left, own, own, right) words with PRMT.
 //   C  : three dp2a per pixel on pairs of the biased 16-bit vertical sums (own + neighbours' by shuffle),
 //        32-bit accumulation as upstream's C code (the 16-bit trick of upstream's asm can overflow).
 //   clip + pack of H and C: cvt.pack.sat.u8.s32.
+// About 19 issued instructions per pixel for 5 bytes of traffic per pixel.
 //
 // This header is compiled by nvcc (hpel_kernels.cu) and, with the lockstep warp shim in tests/sim/, by g++:
 // the CPU suite runs this very code against the CPU checker.  The shim is test infrastructure; the product has no
@@ -33,46 +37,66 @@
 namespace xv {
 
 struct HpelJob {
-    const uint8_t *src; int src_stride; int w, h;     // tight plane, w % 4 == 0
+    const uint8_t *src; int src_stride; int w, h;     // tight plane, w % 8 == 0
     uint8_t *dst;                                     // 4 padded planes per frame: P0, H, V, C
     int stride; size_t plane_bytes;                   // stride >= w + 64, plane_bytes = stride * (h + 64)
     int rows_per_strip;                               // multiple of 6
-    int ntiles, nstrips;                              // ceil((w+8)/4 / 30), ceil((h+16) / rows_per_strip)
+    int ntiles, nstrips;                              // ceil(w/8 / 30), ceil((h+16) / rows_per_strip)
     size_t src_frame_bytes, dst_frame_bytes;
 };
 
 #define HPEL_PAD   32
-#define HPEL_TILE  30          // words per warp that are stored (lanes 1..30)
+#define HPEL_TILE  30          // 8-pixel words per warp that lie inside the frame (lanes 1..30)
 
 // launch plan: fills ntiles / rows_per_strip / nstrips; returns the number of warps (units) per frame
 static inline long long hpel_plan(HpelJob &job, int n_frames)
 {
-    const int nwords = (job.w + 8) >> 2;
-    job.ntiles = (nwords + HPEL_TILE - 1) / HPEL_TILE;
+    const int nw8 = job.w >> 3;
+    job.ntiles = (nw8 + HPEL_TILE - 1) / HPEL_TILE;
     // enough warps for every SM even with one frame: strips of 12 rows; 24 once a batch fills the GPU
     if (job.rows_per_strip <= 0)
-        job.rows_per_strip = (long long)job.ntiles * ((job.h + 16 + 23) / 24) * n_frames >= 148 * 32 ? 24 : 12;
+        job.rows_per_strip = (long long)job.ntiles * ((job.h + 16 + 23) / 24) * n_frames >= 148 * 24 ? 24 : 12;
     job.nstrips = (job.h + 16 + job.rows_per_strip - 1) / job.rows_per_strip;
     return (long long)job.ntiles * job.nstrips;
 }
 
 #ifndef XV_HPEL_HOST_ONLY
-XV_DEVICE uint32_t hpel_load_word(const uint8_t *row, int fx, int w, bool direct)
+struct HpelWord { uint32_t x, y; };                    // 8 pixels: x = the first four
+
+XV_DEVICE HpelWord hpel_load_word(const uint8_t *row, int fx, int w, bool direct)
 {
-    if (direct) return xv_ld_u32(row + fx);
-    const int x0 = min(max(fx, 0), w - 1), x1 = min(max(fx + 1, 0), w - 1);
-    const int x2 = min(max(fx + 2, 0), w - 1), x3 = min(max(fx + 3, 0), w - 1);
-    return (uint32_t)xv_ld_u8(row + x0) | ((uint32_t)xv_ld_u8(row + x1) << 8) |
-           ((uint32_t)xv_ld_u8(row + x2) << 16) | ((uint32_t)xv_ld_u8(row + x3) << 24);
+    HpelWord r;
+    if (direct) { xv_ld_u64(row + fx, r.x, r.y); return r; }
+    uint32_t b[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = xv_ld_u8(row + min(max(fx + i, 0), w - 1));
+    r.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    r.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+    return r;
 }
 
-XV_DEVICE void hpel_store4(uint8_t *D, uint32_t o, uint32_t pb, const uint32_t v[4])
+XV_DEVICE void hpel_store4(uint8_t *D, uint32_t o, uint32_t pb, const HpelWord v[4])
 {
     uint8_t *d = D + o;
-    xv_st_u32(d, v[0]); d += pb;
-    xv_st_u32(d, v[1]); d += pb;
-    xv_st_u32(d, v[2]); d += pb;
-    xv_st_u32(d, v[3]);
+    xv_st_u64(d, v[0].x, v[0].y); d += pb;
+    xv_st_u64(d, v[1].x, v[1].y); d += pb;
+    xv_st_u64(d, v[2].x, v[2].y); d += pb;
+    xv_st_u64(d, v[3].x, v[3].y);
+}
+
+XV_DEVICE uint32_t hpel_clip_v(uint32_t v)            // packed (V16 + 2576): ((V16+16)>>5) clipped to [0,255]
+{
+    return xv_addmin_relu_s16x2((v >> 5) & 0x07FF07FFu, 0xFFB0FFB0u, 0x00FF00FFu);
+}
+
+XV_DEVICE int hpel_tap_h(uint32_t win_m2, uint32_t win_p2)   // bytes x-2..x+1 and x+2..x+5 (the last two unused)
+{
+    return xv_dp4a_us(win_m2, 0x1414FB01u, xv_dp4a_us(win_p2, 0x000001FBu, 16)) >> 5;
+}
+
+XV_DEVICE int hpel_tap_c(uint32_t qm2, uint32_t q0, uint32_t qp2)   // pairs (V[x-2],V[x-1]) (V[x],V[x+1]) (V[x+2],V[x+3])
+{
+    return xv_dp2a_lo(qm2, 0xFB01u, xv_dp2a_lo(q0, 0x1414u, xv_dp2a_lo(qp2, 0x01FBu, 512 - 32 * 2576))) >> 10;
 }
 
 // one warp: tile `unit % ntiles` of strip `unit / ntiles` of frame `frame`
@@ -80,32 +104,36 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
 {
     const int tile = unit % job.ntiles, strip = unit / job.ntiles;
     const int w = job.w, h = job.h;
-    const int nwords = (w + 8) >> 2;                          // words of the filtered domain [-4, w+4)
-    const int wj = tile * HPEL_TILE + lane - 1;               // this lane's word (lanes 0, 31: halo)
-    const int fx = 4 * wj - 4;                                // frame x of its first pixel
+    const int nw8 = w >> 3;                                   // 8-pixel words inside the frame
+    const int wj = tile * HPEL_TILE + lane - 1;               // this lane's word; -1 and nw8 = the words just outside
+    const int fx = 8 * wj;                                    // frame x of its first pixel
     const uint8_t *S = job.src + (size_t)frame * job.src_frame_bytes;
     const int ss = job.src_stride;
-    const bool direct = fx >= 0 && fx + 3 < w && ((((uintptr_t)S) | (uintptr_t)(uint32_t)ss) & 3) == 0;
+    const bool direct = fx >= 0 && fx + 7 < w && ((((uintptr_t)S) | (uintptr_t)(uint32_t)ss) & 7) == 0;
     const int fy0 = strip * job.rows_per_strip - 8;
 
     uint8_t *D = xv_opaque(job.dst + (size_t)frame * job.dst_frame_bytes);
-    const bool store_lane = lane >= 1 && lane <= HPEL_TILE && wj < nwords;
-    const int last_lane = nwords - tile * HPEL_TILE;          // lane that holds the last word of the row
-    const bool left_tile = tile == 0, right_tile = last_lane >= 1 && last_lane <= HPEL_TILE;
+    // who stores: lanes 1..30 up to and including the word just right of the frame; lane 0 only as the word
+    // just left of the frame; lane 31 only as the word just right of it
+    const bool left_word = wj == -1, right_word = wj == nw8;
+    const bool store_lane = (lane >= 1 && lane <= HPEL_TILE && wj <= nw8) || left_word || right_word;
+    const int right_lane = nw8 - tile * HPEL_TILE + 1;        // lane of the word just right of the frame
+    const bool left_tile = tile == 0, right_tile = right_lane >= 1 && right_lane <= 31;
     const uint32_t pb = (uint32_t)job.plane_bytes, own_off = (uint32_t)(fx + HPEL_PAD);
-    // lanes 0..6 of the first tile write the left border (columns 0..27), lanes 7..13 of the last tile the
-    // right border (columns w+36 .. w+63): the first / last pixel of the row, replicated
+    // the rest of the border: columns 0..23 (lanes 1..3 of the first tile) and w+40..w+63 (lanes 4..6 of the
+    // last tile) repeat the first / last filtered pixel of the row
     const bool edge_tile = left_tile || right_tile;
-    const bool edge_lane = lane < 7 ? left_tile : (lane < 14 && right_tile);
-    const uint32_t edge_off = lane < 7 ? 4u * lane : (uint32_t)(w + HPEL_PAD + 4) + 4u * (lane - 7);
+    const bool edge_lane = lane >= 1 && lane <= 6 && (lane <= 3 ? left_tile : right_tile);
+    const uint32_t edge_off = lane <= 3 ? 8u * (lane - 1) : (uint32_t)(w + HPEL_PAD + 8) + 8u * (lane - 4);
 
-    // sliding window: row fy-2+k of the (clamped) frame lives in lo/hi[(j+k)%6], widened to 16-bit pairs
-    uint32_t lo[6], hi[6];
+    // sliding window: row fy-2+k of the (clamped) frame lives in s[(j+k)%6], widened to 16-bit pairs
+    uint32_t s[6][4];
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const int sy = min(max(fy0 - 2 + k, 0), h - 1);
-        const uint32_t word = hpel_load_word(S + (size_t)sy * ss, fx, w, direct);
-        lo[k] = xv_prmt(word, 0u, 0x4140); hi[k] = xv_prmt(word, 0u, 0x4342);
+        const HpelWord wd = hpel_load_word(S + (size_t)sy * ss, fx, w, direct);
+        s[k][0] = xv_prmt(wd.x, 0u, 0x4140); s[k][1] = xv_prmt(wd.x, 0u, 0x4342);
+        s[k][2] = xv_prmt(wd.y, 0u, 0x4140); s[k][3] = xv_prmt(wd.y, 0u, 0x4342);
     }
 
 #pragma unroll 1
@@ -116,53 +144,56 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
             if (fy >= h + 8) return;                          // warp-uniform
             {
                 const int sy = min(max(fy + 3, 0), h - 1);
-                const uint32_t word = hpel_load_word(S + (size_t)sy * ss, fx, w, direct);
-                lo[(j + 5) % 6] = xv_prmt(word, 0u, 0x4140); hi[(j + 5) % 6] = xv_prmt(word, 0u, 0x4342);
+                const HpelWord wd = hpel_load_word(S + (size_t)sy * ss, fx, w, direct);
+                uint32_t *n = s[(j + 5) % 6];
+                n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);
+                n[2] = xv_prmt(wd.y, 0u, 0x4140); n[3] = xv_prmt(wd.y, 0u, 0x4342);
             }
             // ---- vertical 6-tap on packed pairs, lanes biased by 2576 --------------------------------
-            uint32_t vlo = lo[j % 6] + lo[(j + 5) % 6] + 0x0A100A10u;
-            uint32_t vhi = hi[j % 6] + hi[(j + 5) % 6] + 0x0A100A10u;
-            vlo += 20u * (lo[(j + 2) % 6] + lo[(j + 3) % 6]);
-            vhi += 20u * (hi[(j + 2) % 6] + hi[(j + 3) % 6]);
-            vlo -= 5u * (lo[(j + 1) % 6] + lo[(j + 4) % 6]);
-            vhi -= 5u * (hi[(j + 1) % 6] + hi[(j + 4) % 6]);
-            uint32_t out[4];
-            {   // V plane: ((v+16)>>5) + 80 per lane, then max(min(. - 80, 255), 0)
-                const uint32_t rlo = xv_addmin_relu_s16x2((vlo >> 5) & 0x07FF07FFu, 0xFFB0FFB0u, 0x00FF00FFu);
-                const uint32_t rhi = xv_addmin_relu_s16x2((vhi >> 5) & 0x07FF07FFu, 0xFFB0FFB0u, 0x00FF00FFu);
-                out[2] = xv_prmt(rlo, rhi, 0x6420);
+            uint32_t v[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t t = s[j % 6][i] + s[(j + 5) % 6][i] + 0x0A100A10u;
+                t += 20u * (s[(j + 2) % 6][i] + s[(j + 3) % 6][i]);
+                t -= 5u * (s[(j + 1) % 6][i] + s[(j + 4) % 6][i]);
+                v[i] = t;
             }
-            {   // P0 and H plane: byte windows of (left, own, right)
-                const uint32_t raw = xv_prmt(lo[(j + 2) % 6], hi[(j + 2) % 6], 0x6420);
-                const uint32_t L = xv_shfl_up1(raw), R = xv_shfl_down1(raw);
-                const uint32_t a0 = xv_prmt(L, raw, 0x5432), a1 = xv_prmt(L, raw, 0x6543), a3 = xv_prmt(raw, R, 0x4321);
-                const uint32_t b0 = xv_prmt(raw, R, 0x5432), b1 = xv_prmt(raw, R, 0x6543), b3 = R >> 8;
-                const int h0 = xv_dp4a_us(a0, 0x1414FB01u, xv_dp4a_us(b0, 0x000001FBu, 16)) >> 5;
-                const int h1 = xv_dp4a_us(a1, 0x1414FB01u, xv_dp4a_us(b1, 0x000001FBu, 16)) >> 5;
-                const int h2 = xv_dp4a_us(raw, 0x1414FB01u, xv_dp4a_us(R, 0x000001FBu, 16)) >> 5;
-                const int h3 = xv_dp4a_us(a3, 0x1414FB01u, xv_dp4a_us(b3, 0x000001FBu, 16)) >> 5;
-                out[0] = raw;
-                out[1] = xv_pack_sat_u8(h0, h1, h2, h3);
+            HpelWord out[4];
+            // V plane
+            out[2].x = xv_prmt(hpel_clip_v(v[0]), hpel_clip_v(v[1]), 0x6420);
+            out[2].y = xv_prmt(hpel_clip_v(v[2]), hpel_clip_v(v[3]), 0x6420);
+            {   // P0 and H plane: byte windows of the 16-byte span (L, w0, w1, R), span offset 4 = own pixel 0
+                const uint32_t w0 = xv_prmt(s[(j + 2) % 6][0], s[(j + 2) % 6][1], 0x6420);
+                const uint32_t w1 = xv_prmt(s[(j + 2) % 6][2], s[(j + 2) % 6][3], 0x6420);
+                const uint32_t L = xv_shfl_up1(w1), R = xv_shfl_down1(w0);
+                const uint32_t o2 = xv_prmt(L, w0, 0x5432), o3 = xv_prmt(L, w0, 0x6543), o5 = xv_prmt(w0, w1, 0x4321);
+                const uint32_t o6 = xv_prmt(w0, w1, 0x5432), o7 = xv_prmt(w0, w1, 0x6543), o9 = xv_prmt(w1, R, 0x4321);
+                const uint32_t o10 = xv_prmt(w1, R, 0x5432), o11 = xv_prmt(w1, R, 0x6543), o13 = R >> 8;
+                out[0].x = w0; out[0].y = w1;
+                out[1].x = xv_pack_sat_u8(hpel_tap_h(o2, o6), hpel_tap_h(o3, o7), hpel_tap_h(w0, w1), hpel_tap_h(o5, o9));
+                out[1].y = xv_pack_sat_u8(hpel_tap_h(o6, o10), hpel_tap_h(o7, o11), hpel_tap_h(w1, R), hpel_tap_h(o9, o13));
             }
-            {   // C plane: horizontal 6-tap over the vertical sums; the bias contributes 32 * 2576
-                const uint32_t Lhi = xv_shfl_up1(vhi), Rlo = xv_shfl_down1(vlo), Rhi = xv_shfl_down1(vhi);
-                const uint32_t qm1 = xv_prmt(Lhi, vlo, 0x5432), q1 = xv_prmt(vlo, vhi, 0x5432);
-                const uint32_t q3 = xv_prmt(vhi, Rlo, 0x5432), q5 = xv_prmt(Rlo, Rhi, 0x5432);
-                const int cb = 512 - 32 * 2576;
-                const int c0 = xv_dp2a_lo(Lhi, 0xFB01u, xv_dp2a_lo(vlo, 0x1414u, xv_dp2a_lo(vhi, 0x01FBu, cb))) >> 10;
-                const int c1 = xv_dp2a_lo(qm1, 0xFB01u, xv_dp2a_lo(q1, 0x1414u, xv_dp2a_lo(q3, 0x01FBu, cb))) >> 10;
-                const int c2 = xv_dp2a_lo(vlo, 0xFB01u, xv_dp2a_lo(vhi, 0x1414u, xv_dp2a_lo(Rlo, 0x01FBu, cb))) >> 10;
-                const int c3 = xv_dp2a_lo(q1, 0xFB01u, xv_dp2a_lo(q3, 0x1414u, xv_dp2a_lo(q5, 0x01FBu, cb))) >> 10;
-                out[3] = xv_pack_sat_u8(c0, c1, c2, c3);
+            {   // C plane: horizontal 6-tap over the vertical sums (pairs q[k] = (V[k], V[k+1]), k = -2..9)
+                const uint32_t Lv3 = xv_shfl_up1(v[3]), R0 = xv_shfl_down1(v[0]), R1 = xv_shfl_down1(v[1]);
+                const uint32_t qm1 = xv_prmt(Lv3, v[0], 0x5432), q1 = xv_prmt(v[0], v[1], 0x5432);
+                const uint32_t q3 = xv_prmt(v[1], v[2], 0x5432), q5 = xv_prmt(v[2], v[3], 0x5432);
+                const uint32_t q7 = xv_prmt(v[3], R0, 0x5432), q9 = xv_prmt(R0, R1, 0x5432);
+                out[3].x = xv_pack_sat_u8(hpel_tap_c(Lv3, v[0], v[1]), hpel_tap_c(qm1, q1, q3),
+                                          hpel_tap_c(v[0], v[1], v[2]), hpel_tap_c(q1, q3, q5));
+                out[3].y = xv_pack_sat_u8(hpel_tap_c(v[1], v[2], v[3]), hpel_tap_c(q3, q5, q7),
+                                          hpel_tap_c(v[2], v[3], R0), hpel_tap_c(q5, q7, q9));
             }
-            // ---- stores: own word, plus the replicated border where this unit owns an edge ------------
-            // (32-bit offsets from the frame's base: four planes of a frame stay below 4 GB)
-            uint32_t e[4] = {0, 0, 0, 0};
+            // ---- the words just outside the frame: 4 filtered pixels next to the frame, the other 4 already
+            //      border (= the outermost filtered pixel); the rest of the border goes to the edge lanes -----
+            HpelWord e[4];
             if (edge_tile) {                                  // warp-uniform
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
-                    const uint32_t bl = xv_shfl_idx(out[p], 1), br = xv_shfl_idx(out[p], last_lane & 31);
-                    e[p] = (lane < 7 ? bl & 0xFFu : br >> 24) * 0x01010101u;
+                    const uint32_t repl = (out[p].y & 0xFFu) * 0x01010101u, repr = (out[p].x >> 24) * 0x01010101u;
+                    if (left_word) out[p].x = repl;
+                    if (right_word) out[p].y = repr;
+                    const uint32_t bl = xv_shfl_idx(repl, 0), br = xv_shfl_idx(repr, right_lane & 31);
+                    e[p].x = e[p].y = lane <= 3 ? bl : br;
                 }
             }
             const uint32_t ro = (uint32_t)(fy + HPEL_PAD) * (uint32_t)job.stride;

@@ -8,8 +8,10 @@
 namespace xv {
 
 __device__ __forceinline__ uint32_t xv_ld_u32(const uint8_t *p) { return __ldg((const uint32_t *)p); }
+__device__ __forceinline__ void xv_ld_u64(const uint8_t *p, uint32_t &x, uint32_t &y) { const uint2 v = __ldg((const uint2 *)p); x = v.x; y = v.y; }
 __device__ __forceinline__ uint32_t xv_ld_u8(const uint8_t *p) { return __ldg(p); }
 __device__ __forceinline__ void xv_st_u32(uint8_t *p, uint32_t v) { asm volatile("st.global.b32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void xv_st_u64(uint8_t *p, uint32_t x, uint32_t y) { asm volatile("st.global.v2.b32 [%0], {%1, %2};" :: "l"(p), "r"(x), "r"(y) : "memory"); }
 // keeps the compiler from folding the frame's base back into every address computation
 __device__ __forceinline__ uint8_t *xv_opaque(uint8_t *p) { asm volatile("" : "+l"(p)); return p; }
 __device__ __forceinline__ uint32_t xv_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
