@@ -61,6 +61,7 @@ static inline void xv_st_u64(uint8_t *p, uint32_t x, uint32_t y)
     memcpy(p, &x, 4); memcpy(p + 4, &y, 4);
 }
 static inline uint8_t *xv_opaque(uint8_t *p) { return p; }
+static inline const uint8_t *xv_opaque(const uint8_t *p) { return p; }
 
 static inline uint32_t xv_prmt(uint32_t a, uint32_t b, uint32_t sel)
 {

@@ -75,9 +75,8 @@ XV_DEVICE HpelWord hpel_load_word(const uint8_t *row, int fx, int w, bool direct
     return r;
 }
 
-XV_DEVICE void hpel_store4(uint8_t *D, uint32_t o, uint32_t pb, const HpelWord v[4])
+XV_DEVICE void hpel_store4(uint8_t *d, uint32_t pb, const HpelWord v[4])
 {
-    uint8_t *d = D + o;
     xv_st_u64(d, v[0].x, v[0].y); d += pb;
     xv_st_u64(d, v[1].x, v[1].y); d += pb;
     xv_st_u64(d, v[2].x, v[2].y); d += pb;
@@ -136,6 +135,14 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
         s[k][2] = xv_prmt(wd.y, 0u, 0x4140); s[k][3] = xv_prmt(wd.y, 0u, 0x4342);
     }
 
+    // the next two rows are always in flight: a row is requested two iterations before it is widened
+    HpelWord pre[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) pre[k] = hpel_load_word(S + (size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss, fx, w, direct);
+    // running store address of row fy (own word; the border word is edge_delta away)
+    uint8_t *dp = D + ((size_t)(fy0 + HPEL_PAD) * job.stride + own_off);
+    const ptrdiff_t edge_delta = (ptrdiff_t)edge_off - (ptrdiff_t)own_off;
+
 #pragma unroll 1
     for (int base = 0; base < job.rows_per_strip; base += 6) {
 #pragma unroll
@@ -143,11 +150,11 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
             const int fy = fy0 + base + j;
             if (fy >= h + 8) return;                          // warp-uniform
             {
-                const int sy = min(max(fy + 3, 0), h - 1);
-                const HpelWord wd = hpel_load_word(S + (size_t)sy * ss, fx, w, direct);
+                const HpelWord wd = pre[j & 1];
                 uint32_t *n = s[(j + 5) % 6];
                 n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);
                 n[2] = xv_prmt(wd.y, 0u, 0x4140); n[3] = xv_prmt(wd.y, 0u, 0x4342);
+                pre[j & 1] = hpel_load_word(S + (size_t)min(max(fy + 5, 0), h - 1) * ss, fx, w, direct);
             }
             // ---- vertical 6-tap on packed pairs, lanes biased by 2576 --------------------------------
             uint32_t v[4];
@@ -196,16 +203,16 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
                     e[p].x = e[p].y = lane <= 3 ? bl : br;
                 }
             }
-            const uint32_t ro = (uint32_t)(fy + HPEL_PAD) * (uint32_t)job.stride;
-            if (store_lane) hpel_store4(D, ro + own_off, pb, out);
-            if (edge_lane) hpel_store4(D, ro + edge_off, pb, e);
+            if (store_lane) hpel_store4(dp, pb, out);
+            if (edge_lane) hpel_store4(dp + edge_delta, pb, e);
+            dp += job.stride;
             if (fy == -8 || fy == h + 7) {                    // top / bottom border: 24 more copies of this row
                 const int rb = fy == -8 ? 0 : h + HPEL_PAD + 8;
 #pragma unroll 1
                 for (int r = rb; r < rb + 24; r++) {
-                    const uint32_t rr = (uint32_t)r * (uint32_t)job.stride;
-                    if (store_lane) hpel_store4(D, rr + own_off, pb, out);
-                    if (edge_lane) hpel_store4(D, rr + edge_off, pb, e);
+                    const size_t rr = (size_t)r * job.stride;
+                    if (store_lane) hpel_store4(D + (rr + own_off), pb, out);
+                    if (edge_lane) hpel_store4(D + (rr + edge_off), pb, e);
                 }
             }
         }

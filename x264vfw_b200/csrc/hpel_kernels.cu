@@ -2,6 +2,7 @@
 // description).  sm_100a device versions of the helpers the program uses.
 #include "common.cuh"
 #include "csp_kernels.h"
+#include <stdlib.h>
 
 #define XV_DEVICE __device__ __forceinline__
 
@@ -14,6 +15,7 @@ __device__ __forceinline__ void xv_st_u32(uint8_t *p, uint32_t v) { asm volatile
 __device__ __forceinline__ void xv_st_u64(uint8_t *p, uint32_t x, uint32_t y) { asm volatile("st.global.v2.b32 [%0], {%1, %2};" :: "l"(p), "r"(x), "r"(y) : "memory"); }
 // keeps the compiler from folding the frame's base back into every address computation
 __device__ __forceinline__ uint8_t *xv_opaque(uint8_t *p) { asm volatile("" : "+l"(p)); return p; }
+__device__ __forceinline__ const uint8_t *xv_opaque(const uint8_t *p) { asm volatile("" : "+l"(p)); return p; }
 __device__ __forceinline__ uint32_t xv_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 __device__ __forceinline__ uint32_t xv_shfl_up1(uint32_t v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ uint32_t xv_shfl_down1(uint32_t v) { return __shfl_down_sync(0xffffffffu, v, 1); }
@@ -49,7 +51,8 @@ __device__ __forceinline__ uint32_t xv_pack_sat_u8(int v0, int v1, int v2, int v
 
 namespace xv {
 
-__global__ void __launch_bounds__(128)
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS)
 hpel_kernel(HpelJob job)
 {
     const int unit = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -62,7 +65,14 @@ int launch_hpel(cudaStream_t st, HpelJob &job, int n_frames)
     if (job.w <= 0 || job.h <= 0 || n_frames <= 0) return 0;
     const long long units = hpel_plan(job, n_frames);
     dim3 grid((unsigned)((units + 3) / 4), (unsigned)n_frames);
-    hpel_kernel<<<grid, 128, 0, st>>>(job);
+    // register budget: 7 blocks per SM = 72 registers (no spills); the other budgets are tuning variants for
+    // scripts/probe_hpel.py
+    const char *ev = getenv("X264VFW_CUDA_HPEL_VARIANT");
+    const int variant = ev ? atoi(ev) : 7;
+    if (variant == 8) hpel_kernel<8><<<grid, 128, 0, st>>>(job);
+    else if (variant == 7) hpel_kernel<7><<<grid, 128, 0, st>>>(job);
+    else if (variant == 5) hpel_kernel<5><<<grid, 128, 0, st>>>(job);
+    else hpel_kernel<6><<<grid, 128, 0, st>>>(job);
     XV_LAUNCH_CHECK();
     return 0;
 }
