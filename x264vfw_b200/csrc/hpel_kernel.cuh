@@ -17,8 +17,7 @@
 // shuffle's "no such lane -> own value" is exactly the clamped neighbour at the frame's left / right edge.
 // Tiles cover [0,w); the two words just outside ([-8,0) and [w,w+8)) are the halo lanes of the first /
 // last tile, which also own the replicated border.  The six source rows of the vertical filter slide
-// through registers (four packed 16-bit pairs per row, loop unrolled by six so the rotation is register
-// renaming).  Arithmetic:
+// through registers (four packed 16-bit pairs per row; one row per loop trip, see the note at the loop).  Arithmetic:
 //   V  : packed 16-bit lanes, biased by 2576 = 80*32 + 16 so that lanes never go negative (no borrow between
 //        lanes) and the bias supplies the rounding term; >>5, per-lane add/min/relu (DPX) gives clip().
 //   H  : two dp4a per pixel on byte windows cut out of (left, own, own, right) words with PRMT.
@@ -40,7 +39,7 @@ struct HpelJob {
     const uint8_t *src; int src_stride; int w, h;     // tight plane, w % 8 == 0
     uint8_t *dst;                                     // 4 padded planes per frame: P0, H, V, C
     int stride; size_t plane_bytes;                   // stride >= w + 64, plane_bytes = stride * (h + 64)
-    int rows_per_strip;                               // multiple of 6
+    int rows_per_strip;
     int ntiles, nstrips;                              // ceil(w/8 / 30), ceil((h+16) / rows_per_strip)
     size_t src_frame_bytes, dst_frame_bytes;
 };
@@ -125,7 +124,7 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     const bool edge_lane = lane >= 1 && lane <= 6 && (lane <= 3 ? left_tile : right_tile);
     const uint32_t edge_off = lane <= 3 ? 8u * (lane - 1) : (uint32_t)(w + HPEL_PAD + 8) + 8u * (lane - 4);
 
-    // sliding window: row fy-2+k of the (clamped) frame lives in s[(j+k)%6], widened to 16-bit pairs
+    // sliding window: row fy-2+k of the (clamped) frame lives in s[k], widened to 16-bit pairs
     uint32_t s[6][4];
 #pragma unroll
     for (int k = 0; k < 5; k++) {
@@ -143,26 +142,29 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     uint8_t *dp = D + ((size_t)(fy0 + HPEL_PAD) * job.stride + own_off);
     const ptrdiff_t edge_delta = (ptrdiff_t)edge_off - (ptrdiff_t)own_off;
 
+    // One row per trip, NOT unrolled: the window moves by register copies (20 of ~230 instructions) so that
+    // the loop body stays a few KB -- unrolled by six (rotation by renaming) it was 55 KB, beyond the 32 KB
+    // L1.5 instruction cache, and a quarter of the stall samples were "no instruction".
 #pragma unroll 1
-    for (int base = 0; base < job.rows_per_strip; base += 6) {
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-            const int fy = fy0 + base + j;
+    for (int i = 0; i < job.rows_per_strip; i++) {
+        {
+            const int fy = fy0 + i;
             if (fy >= h + 8) return;                          // warp-uniform
             {
-                const HpelWord wd = pre[j & 1];
-                uint32_t *n = s[(j + 5) % 6];
+                const HpelWord wd = pre[0];
+                uint32_t *n = s[5];
                 n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);
                 n[2] = xv_prmt(wd.y, 0u, 0x4140); n[3] = xv_prmt(wd.y, 0u, 0x4342);
-                pre[j & 1] = hpel_load_word(S + (size_t)min(max(fy + 5, 0), h - 1) * ss, fx, w, direct);
+                pre[0] = pre[1];
+                pre[1] = hpel_load_word(S + (size_t)min(max(fy + 5, 0), h - 1) * ss, fx, w, direct);
             }
             // ---- vertical 6-tap on packed pairs, lanes biased by 2576 --------------------------------
             uint32_t v[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                uint32_t t = s[j % 6][i] + s[(j + 5) % 6][i] + 0x0A100A10u;
-                t += 20u * (s[(j + 2) % 6][i] + s[(j + 3) % 6][i]);
-                t -= 5u * (s[(j + 1) % 6][i] + s[(j + 4) % 6][i]);
+                uint32_t t = s[0][i] + s[5][i] + 0x0A100A10u;
+                t += 20u * (s[2][i] + s[3][i]);
+                t -= 5u * (s[1][i] + s[4][i]);
                 v[i] = t;
             }
             HpelWord out[4];
@@ -170,8 +172,8 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
             out[2].x = xv_prmt(hpel_clip_v(v[0]), hpel_clip_v(v[1]), 0x6420);
             out[2].y = xv_prmt(hpel_clip_v(v[2]), hpel_clip_v(v[3]), 0x6420);
             {   // P0 and H plane: byte windows of the 16-byte span (L, w0, w1, R), span offset 4 = own pixel 0
-                const uint32_t w0 = xv_prmt(s[(j + 2) % 6][0], s[(j + 2) % 6][1], 0x6420);
-                const uint32_t w1 = xv_prmt(s[(j + 2) % 6][2], s[(j + 2) % 6][3], 0x6420);
+                const uint32_t w0 = xv_prmt(s[2][0], s[2][1], 0x6420);
+                const uint32_t w1 = xv_prmt(s[2][2], s[2][3], 0x6420);
                 const uint32_t L = xv_shfl_up1(w1), R = xv_shfl_down1(w0);
                 const uint32_t o2 = xv_prmt(L, w0, 0x5432), o3 = xv_prmt(L, w0, 0x6543), o5 = xv_prmt(w0, w1, 0x4321);
                 const uint32_t o6 = xv_prmt(w0, w1, 0x5432), o7 = xv_prmt(w0, w1, 0x6543), o9 = xv_prmt(w1, R, 0x4321);
@@ -214,6 +216,11 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
                     if (store_lane) hpel_store4(D + (rr + own_off), pb, out);
                     if (edge_lane) hpel_store4(D + (rr + edge_off), pb, e);
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) s[k][q] = s[k + 1][q];
             }
         }
     }

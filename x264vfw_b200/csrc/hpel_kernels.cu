@@ -51,28 +51,20 @@ __device__ __forceinline__ uint32_t xv_pack_sat_u8(int v0, int v1, int v2, int v
 
 namespace xv {
 
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(128, MIN_BLOCKS)
+// one warp per block: tiles at the frame's edges do more work (border), a block of several warps would
+// hold its slot until the slowest one is done
+__global__ void __launch_bounds__(32, 28)
 hpel_kernel(HpelJob job)
 {
-    const int unit = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (unit >= job.ntiles * job.nstrips) return;               // warp-uniform
-    hpel_unit(job, unit, blockIdx.y, threadIdx.x & 31);
+    hpel_unit(job, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
 int launch_hpel(cudaStream_t st, HpelJob &job, int n_frames)
 {
     if (job.w <= 0 || job.h <= 0 || n_frames <= 0) return 0;
     const long long units = hpel_plan(job, n_frames);
-    dim3 grid((unsigned)((units + 3) / 4), (unsigned)n_frames);
-    // register budget: 7 blocks per SM = 72 registers (no spills); the other budgets are tuning variants for
-    // scripts/probe_hpel.py
-    const char *ev = getenv("X264VFW_CUDA_HPEL_VARIANT");
-    const int variant = ev ? atoi(ev) : 7;
-    if (variant == 8) hpel_kernel<8><<<grid, 128, 0, st>>>(job);
-    else if (variant == 7) hpel_kernel<7><<<grid, 128, 0, st>>>(job);
-    else if (variant == 5) hpel_kernel<5><<<grid, 128, 0, st>>>(job);
-    else hpel_kernel<6><<<grid, 128, 0, st>>>(job);
+    dim3 grid((unsigned)units, (unsigned)n_frames);
+    hpel_kernel<<<grid, 32, 0, st>>>(job);
     XV_LAUNCH_CHECK();
     return 0;
 }
