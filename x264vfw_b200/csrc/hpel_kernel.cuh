@@ -62,16 +62,27 @@ static inline long long hpel_plan(HpelJob &job, int n_frames)
 #ifndef XV_HPEL_HOST_ONLY
 struct HpelWord { uint32_t x, y; };                    // 8 pixels: x = the first four
 
-XV_DEVICE HpelWord hpel_load_word(const uint8_t *row, int fx, int w, bool direct)
+// A lane's 8 pixels of one row.  Aligned planes (the normal case): every lane issues one 64-bit load; the lanes
+// whose word lies left / right of the frame read the frame's first / last word instead and hpel_fix_word turns
+// it into the replicated edge pixel when the row is consumed (two trips later) -- nothing depends on the load
+// when it is issued.  Unaligned planes: eight clamped byte loads.
+XV_DEVICE HpelWord hpel_load_word(const uint8_t *row, int fx, int cfx, int w, bool aligned)
 {
     HpelWord r;
-    if (direct) { xv_ld_u64(row + fx, r.x, r.y); return r; }
+    if (aligned) { xv_ld_u64(row + cfx, r.x, r.y); return r; }
     uint32_t b[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) b[i] = xv_ld_u8(row + min(max(fx + i, 0), w - 1));
     r.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
     r.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
     return r;
+}
+
+XV_DEVICE HpelWord hpel_fix_word(HpelWord wd, int side)      // side: -1 left of the frame, +1 right of it, 0 inside
+{
+    if (side < 0) wd.x = wd.y = (wd.x & 0xFFu) * 0x01010101u;
+    if (side > 0) wd.x = wd.y = (wd.y >> 24) * 0x01010101u;
+    return wd;
 }
 
 XV_DEVICE void hpel_store4(uint8_t *d, uint32_t pb, const HpelWord v[4])
@@ -107,7 +118,9 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     const int fx = 8 * wj;                                    // frame x of its first pixel
     const uint8_t *S = job.src + (size_t)frame * job.src_frame_bytes;
     const int ss = job.src_stride;
-    const bool direct = fx >= 0 && fx + 7 < w && ((((uintptr_t)S) | (uintptr_t)(uint32_t)ss) & 7) == 0;
+    const bool aligned = ((((uintptr_t)S) | (uintptr_t)(uint32_t)ss) & 7) == 0;   // warp-uniform
+    const int cfx = min(max(fx, 0), w - 8);                   // column actually loaded (aligned planes)
+    const int side = !aligned ? 0 : fx < 0 ? -1 : fx >= w ? 1 : 0;
     const int fy0 = strip * job.rows_per_strip - 8;
 
     uint8_t *D = xv_opaque(job.dst + (size_t)frame * job.dst_frame_bytes);
@@ -129,7 +142,7 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const int sy = min(max(fy0 - 2 + k, 0), h - 1);
-        const HpelWord wd = hpel_load_word(S + (size_t)sy * ss, fx, w, direct);
+        const HpelWord wd = hpel_fix_word(hpel_load_word(S + (size_t)sy * ss, fx, cfx, w, aligned), side);
         s[k][0] = xv_prmt(wd.x, 0u, 0x4140); s[k][1] = xv_prmt(wd.x, 0u, 0x4342);
         s[k][2] = xv_prmt(wd.y, 0u, 0x4140); s[k][3] = xv_prmt(wd.y, 0u, 0x4342);
     }
@@ -137,7 +150,7 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     // the next two rows are always in flight: a row is requested two iterations before it is widened
     HpelWord pre[2];
 #pragma unroll
-    for (int k = 0; k < 2; k++) pre[k] = hpel_load_word(S + (size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss, fx, w, direct);
+    for (int k = 0; k < 2; k++) pre[k] = hpel_load_word(S + (size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss, fx, cfx, w, aligned);
     // running store address of row fy (own word; the border word is edge_delta away)
     uint8_t *dp = D + ((size_t)(fy0 + HPEL_PAD) * job.stride + own_off);
     const ptrdiff_t edge_delta = (ptrdiff_t)edge_off - (ptrdiff_t)own_off;
@@ -145,18 +158,19 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     // One row per trip, NOT unrolled: the window moves by register copies (20 of ~230 instructions) so that
     // the loop body stays a few KB -- unrolled by six (rotation by renaming) it was 55 KB, beyond the 32 KB
     // L1.5 instruction cache, and a quarter of the stall samples were "no instruction".
+    // (no exit inside the loop: an EXIT, even predicated off, waits for the loads in flight)
+    const int ntrips = min(job.rows_per_strip, h + 8 - fy0);
 #pragma unroll 1
-    for (int i = 0; i < job.rows_per_strip; i++) {
+    for (int i = 0; i < ntrips; i++) {
         {
             const int fy = fy0 + i;
-            if (fy >= h + 8) return;                          // warp-uniform
             {
-                const HpelWord wd = pre[0];
+                const HpelWord wd = edge_tile ? hpel_fix_word(pre[0], side) : pre[0];
                 uint32_t *n = s[5];
                 n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);
                 n[2] = xv_prmt(wd.y, 0u, 0x4140); n[3] = xv_prmt(wd.y, 0u, 0x4342);
                 pre[0] = pre[1];
-                pre[1] = hpel_load_word(S + (size_t)min(max(fy + 5, 0), h - 1) * ss, fx, w, direct);
+                pre[1] = hpel_load_word(S + (size_t)min(max(fy + 5, 0), h - 1) * ss, fx, cfx, w, aligned);
             }
             // ---- vertical 6-tap on packed pairs, lanes biased by 2576 --------------------------------
             uint32_t v[4];
@@ -195,14 +209,21 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
             // ---- the words just outside the frame: 4 filtered pixels next to the frame, the other 4 already
             //      border (= the outermost filtered pixel); the rest of the border goes to the edge lanes -----
             HpelWord e[4];
-            if (edge_tile) {                                  // warp-uniform
+            if (left_tile) {                                  // warp-uniform
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
-                    const uint32_t repl = (out[p].y & 0xFFu) * 0x01010101u, repr = (out[p].x >> 24) * 0x01010101u;
-                    if (left_word) out[p].x = repl;
-                    if (right_word) out[p].y = repr;
-                    const uint32_t bl = xv_shfl_idx(repl, 0), br = xv_shfl_idx(repr, right_lane & 31);
-                    e[p].x = e[p].y = lane <= 3 ? bl : br;
+                    const uint32_t rep = (out[p].y & 0xFFu) * 0x01010101u;
+                    if (left_word) out[p].x = rep;
+                    e[p].x = e[p].y = xv_shfl_idx(rep, 0);
+                }
+            }
+            if (right_tile) {                                 // warp-uniform
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const uint32_t rep = (out[p].x >> 24) * 0x01010101u;
+                    if (right_word) out[p].y = rep;
+                    const uint32_t br = xv_shfl_idx(rep, right_lane & 31);
+                    if (lane > 3) e[p].x = e[p].y = br;
                 }
             }
             if (store_lane) hpel_store4(dp, pb, out);
