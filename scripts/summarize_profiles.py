@@ -14,7 +14,8 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "smsp__average_warp_latency_per_inst_issued.ratio"]
 
 
 def launch_list(src, dst, title):
@@ -65,7 +66,10 @@ if __name__ == "__main__":
             ("s1_bgra_r1a.ncu-rep", f"ncu_csp_bgra_{tag}_before_4row.txt", "rgb_to_420 (dp4a version, before the 4-row fast path), 64 frames per launch"),
             ("s1_lowres_r1a.ncu-rep", f"ncu_lowres_{tag}_before.txt", "lowres_init before the cheap-border rewrite, 64 frames per launch"),
             ("s1_bgra_r1b.ncu-rep", f"ncu_csp_bgra_{tag}.txt", "rgb_to_420_fast_kernel<4,false>, 64 frames (730 MB algorithmic) per launch"),
-            ("s1_lowres_r1b.ncu-rep", f"ncu_lowres_{tag}.txt", "lowres_init_kernel, 64 frames per launch")]
+            ("s1_lowres_r1b.ncu-rep", f"ncu_lowres_{tag}.txt", "lowres_init_kernel, 64 frames per launch"),
+            ("hpel_a.ncu-rep", f"ncu_hpel_{tag}_first_version.txt", "hpel_kernel, first version (row loop unrolled by six: 57 KB of SASS, load consumed in the trip that issues it), 48 frames of 1920x1088 per launch"),
+            ("hpel_b.ncu-rep", f"ncu_hpel_{tag}_prefetch_unrolled.txt", "hpel_kernel with rows prefetched two trips ahead, still unrolled by six (62 KB of SASS): the stall moves from the load to the instruction cache"),
+            ("hpel_c.ncu-rep", f"ncu_hpel_{tag}.txt", "hpel_kernel, one row per loop trip (6 KB loop body), one warp per block; 48 frames of 1920x1088 per launch (before the EXIT was taken out of the loop)")]
     for src, dst, title in reps:
         if os.path.exists(os.path.join(GP, src)):
             raw_metrics(os.path.join(GP, src), os.path.join(OUT, dst), title)

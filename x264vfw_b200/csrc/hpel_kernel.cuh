@@ -66,13 +66,13 @@ struct HpelWord { uint32_t x, y; };                    // 8 pixels: x = the firs
 // whose word lies left / right of the frame read the frame's first / last word instead and hpel_fix_word turns
 // it into the replicated edge pixel when the row is consumed (two trips later) -- nothing depends on the load
 // when it is issued.  Unaligned planes: eight clamped byte loads.
-XV_DEVICE HpelWord hpel_load_word(const uint8_t *row, int fx, int cfx, int w, bool aligned)
+XV_DEVICE HpelWord hpel_load_word(const uint8_t *rowc, int fx, int cfx, int w, bool aligned)   // rowc = row + cfx
 {
     HpelWord r;
-    if (aligned) { xv_ld_u64(row + cfx, r.x, r.y); return r; }
+    if (aligned) { xv_ld_u64(rowc, r.x, r.y); return r; }
     uint32_t b[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) b[i] = xv_ld_u8(row + min(max(fx + i, 0), w - 1));
+    for (int i = 0; i < 8; i++) b[i] = xv_ld_u8(rowc + (min(max(fx + i, 0), w - 1) - cfx));
     r.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
     r.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
     return r;
@@ -142,7 +142,7 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const int sy = min(max(fy0 - 2 + k, 0), h - 1);
-        const HpelWord wd = hpel_fix_word(hpel_load_word(S + (size_t)sy * ss, fx, cfx, w, aligned), side);
+        const HpelWord wd = hpel_fix_word(hpel_load_word(S + ((size_t)sy * ss + cfx), fx, cfx, w, aligned), side);
         s[k][0] = xv_prmt(wd.x, 0u, 0x4140); s[k][1] = xv_prmt(wd.x, 0u, 0x4342);
         s[k][2] = xv_prmt(wd.y, 0u, 0x4140); s[k][3] = xv_prmt(wd.y, 0u, 0x4342);
     }
@@ -150,9 +150,11 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     // the next two rows are always in flight: a row is requested two iterations before it is widened
     HpelWord pre[2];
 #pragma unroll
-    for (int k = 0; k < 2; k++) pre[k] = hpel_load_word(S + (size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss, fx, cfx, w, aligned);
+    for (int k = 0; k < 2; k++) pre[k] = hpel_load_word(S + ((size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss + cfx), fx, cfx, w, aligned);
     // running store address of row fy (own word; the border word is edge_delta away)
     uint8_t *dp = D + ((size_t)(fy0 + HPEL_PAD) * job.stride + own_off);
+    // running load address: row clamp(fy+5) of the frame, this lane's column; it moves down while inside the frame
+    const uint8_t *rp = S + ((size_t)min(max(fy0 + 5, 0), h - 1) * ss + cfx);
     const ptrdiff_t edge_delta = (ptrdiff_t)edge_off - (ptrdiff_t)own_off;
 
     // One row per trip, NOT unrolled: the window moves by register copies (20 of ~230 instructions) so that
@@ -170,7 +172,8 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
                 n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);
                 n[2] = xv_prmt(wd.y, 0u, 0x4140); n[3] = xv_prmt(wd.y, 0u, 0x4342);
                 pre[0] = pre[1];
-                pre[1] = hpel_load_word(S + (size_t)min(max(fy + 5, 0), h - 1) * ss, fx, cfx, w, aligned);
+                pre[1] = hpel_load_word(rp, fx, cfx, w, aligned);
+                if ((unsigned)(fy + 5) < (unsigned)(h - 1)) rp += ss;
             }
             // ---- vertical 6-tap on packed pairs, lanes biased by 2576 --------------------------------
             uint32_t v[4];
