@@ -60,7 +60,7 @@ static inline long long hpel_plan(HpelJob &job, int n_frames)
 }
 
 #ifndef XV_HPEL_HOST_ONLY
-struct HpelWord { uint32_t x, y; };                    // 8 pixels: x = the first four
+struct alignas(8) HpelWord { uint32_t x, y; };         // 8 pixels: x = the first four
 
 // A lane's 8 pixels of one row.  Aligned planes (the normal case): every lane issues one 64-bit load; the lanes
 // whose word lies left / right of the frame read the frame's first / last word instead and hpel_fix_word turns
@@ -83,6 +83,17 @@ XV_DEVICE HpelWord hpel_fix_word(HpelWord wd, int side)      // side: -1 left of
     if (side < 0) wd.x = wd.y = (wd.x & 0xFFu) * 0x01010101u;
     if (side > 0) wd.x = wd.y = (wd.y >> 24) * 0x01010101u;
     return wd;
+}
+
+#define HPEL_DIST  3            // rows in flight per lane
+#define HPEL_RING  4            // ring slots (power of two > HPEL_DIST)
+
+// request a lane's 8 pixels of one row into its ring slot (one cp.async group per call)
+XV_DEVICE void hpel_fetch_row(HpelWord *slot, const uint8_t *rowc, int fx, int cfx, int w, bool aligned)
+{
+    if (aligned) xv_cp_async8(slot, rowc);
+    else { const HpelWord wd = hpel_load_word(rowc, fx, cfx, w, false); xv_sts_u64(slot, wd.x, wd.y); }
+    xv_cp_async_commit();
 }
 
 XV_DEVICE void hpel_store4(uint8_t *d, uint32_t pb, const HpelWord v[4])
@@ -147,14 +158,18 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
         s[k][2] = xv_prmt(wd.y, 0u, 0x4140); s[k][3] = xv_prmt(wd.y, 0u, 0x4342);
     }
 
-    // the next two rows are always in flight: a row is requested two iterations before it is widened
-    HpelWord pre[2];
+    // The next HPEL_DIST rows are always in flight, through a per-lane ring in shared memory filled by cp.async:
+    // the copy has no destination register, so nothing in the loop waits on it until the row is due (a register
+    // double buffer needs either an unrolled loop or a copy of a register that is still being filled, and that
+    // copy waits for the load -- it held 25 % of the stall samples).
+    XV_SHARED HpelWord ring[HPEL_RING][32];
 #pragma unroll
-    for (int k = 0; k < 2; k++) pre[k] = hpel_load_word(S + ((size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss + cfx), fx, cfx, w, aligned);
+    for (int k = 0; k < HPEL_DIST; k++)
+        hpel_fetch_row(&ring[k][lane], S + ((size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss + cfx), fx, cfx, w, aligned);
     // running store address of row fy (own word; the border word is edge_delta away)
     uint8_t *dp = D + ((size_t)(fy0 + HPEL_PAD) * job.stride + own_off);
-    // running load address: row clamp(fy+5) of the frame, this lane's column; it moves down while inside the frame
-    const uint8_t *rp = S + ((size_t)min(max(fy0 + 5, 0), h - 1) * ss + cfx);
+    // running load address: row clamp(fy+3+HPEL_DIST) of the frame, this lane's column; it moves down while inside the frame
+    const uint8_t *rp = S + ((size_t)min(max(fy0 + 3 + HPEL_DIST, 0), h - 1) * ss + cfx);
     const ptrdiff_t edge_delta = (ptrdiff_t)edge_off - (ptrdiff_t)own_off;
 
     // One row per trip, NOT unrolled: the window moves by register copies (20 of ~230 instructions) so that
@@ -167,13 +182,15 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
         {
             const int fy = fy0 + i;
             {
-                const HpelWord wd = edge_tile ? hpel_fix_word(pre[0], side) : pre[0];
+                hpel_fetch_row(&ring[(i + HPEL_DIST) & (HPEL_RING - 1)][lane], rp, fx, cfx, w, aligned);   // row fy+3+DIST
+                if ((unsigned)(fy + 3 + HPEL_DIST) < (unsigned)(h - 1)) rp += ss;
+                xv_cp_async_wait<HPEL_DIST>();                                                       // row fy+3 has landed
+                HpelWord wd;
+                xv_lds_u64(&ring[i & (HPEL_RING - 1)][lane], wd.x, wd.y);
+                if (edge_tile) wd = hpel_fix_word(wd, side);
                 uint32_t *n = s[5];
                 n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);
                 n[2] = xv_prmt(wd.y, 0u, 0x4140); n[3] = xv_prmt(wd.y, 0u, 0x4342);
-                pre[0] = pre[1];
-                pre[1] = hpel_load_word(rp, fx, cfx, w, aligned);
-                if ((unsigned)(fy + 5) < (unsigned)(h - 1)) rp += ss;
             }
             // ---- vertical 6-tap on packed pairs, lanes biased by 2576 --------------------------------
             uint32_t v[4];
