@@ -67,9 +67,11 @@ if __name__ == "__main__":
             ("s1_lowres_r1a.ncu-rep", f"ncu_lowres_{tag}_before.txt", "lowres_init before the cheap-border rewrite, 64 frames per launch"),
             ("s1_bgra_r1b.ncu-rep", f"ncu_csp_bgra_{tag}.txt", "rgb_to_420_fast_kernel<4,false>, 64 frames (730 MB algorithmic) per launch"),
             ("s1_lowres_r1b.ncu-rep", f"ncu_lowres_{tag}.txt", "lowres_init_kernel, 64 frames per launch"),
-            ("hpel_a.ncu-rep", f"ncu_hpel_{tag}_first_version.txt", "hpel_kernel, first version (row loop unrolled by six: 57 KB of SASS, load consumed in the trip that issues it), 48 frames of 1920x1088 per launch"),
-            ("hpel_b.ncu-rep", f"ncu_hpel_{tag}_prefetch_unrolled.txt", "hpel_kernel with rows prefetched two trips ahead, still unrolled by six (62 KB of SASS): the stall moves from the load to the instruction cache"),
-            ("hpel_c.ncu-rep", f"ncu_hpel_{tag}.txt", "hpel_kernel, one row per loop trip (6 KB loop body), one warp per block; 48 frames of 1920x1088 per launch (before the EXIT was taken out of the loop)")]
+            ("hpel_a.ncu-rep", f"ncu_hpel_{tag}_v1_unrolled.txt", "hpel_kernel, first version (row loop unrolled by six: 57 KB of SASS, a row's load consumed in the trip that issues it), 48 frames of 1920x1088 per launch"),
+            ("hpel_b.ncu-rep", f"ncu_hpel_{tag}_v2_prefetch_unrolled.txt", "hpel_kernel with rows prefetched two trips ahead, still unrolled by six (62 KB of SASS): the stall moves from the load to the instruction cache"),
+            ("hpel_c.ncu-rep", f"ncu_hpel_{tag}_v3_compact_loop.txt", "hpel_kernel, one row per loop trip (6 KB loop body), one warp per block; an EXIT inside the loop still waits for the prefetched loads"),
+            ("hpel_e.ncu-rep", f"ncu_hpel_{tag}_v4_no_exit.txt", "hpel_kernel without the EXIT in the loop, register double buffer: the copy pre[0]=pre[1] of a register still being loaded holds 25 % of the stall samples"),
+            ("hpel_f.ncu-rep", f"ncu_hpel_{tag}.txt", "hpel_kernel as measured at the end of the round: rows prefetched three trips ahead through a per-lane cp.async ring in shared memory; 48 frames of 1920x1088 per launch")]
     for src, dst, title in reps:
         if os.path.exists(os.path.join(GP, src)):
             raw_metrics(os.path.join(GP, src), os.path.join(OUT, dst), title)

@@ -62,15 +62,18 @@ static inline void xv_st_u64(uint8_t *p, uint32_t x, uint32_t y)
     memcpy(p, &x, 4); memcpy(p + 4, &y, 4);
 }
 // cp.async: modelled as an immediate copy (the real one lands no later than the matching wait_group)
-static inline void xv_cp_async8(void *smem, const void *gmem)
+typedef uint8_t *xv_saddr;
+static inline xv_saddr xv_saddr_of(void *smem) { return (uint8_t *)smem; }
+static inline void xv_cp_async8(xv_saddr smem, const void *gmem)
 {
     if (((uintptr_t)smem | (uintptr_t)gmem) & 7) abort();
     memcpy(smem, gmem, 8);
 }
 static inline void xv_cp_async_commit() {}
 template <int N> static inline void xv_cp_async_wait() {}
-static inline void xv_lds_u64(const void *smem, uint32_t &x, uint32_t &y) { memcpy(&x, smem, 4); memcpy(&y, (const uint8_t *)smem + 4, 4); }
-static inline void xv_sts_u64(void *smem, uint32_t x, uint32_t y) { memcpy(smem, &x, 4); memcpy((uint8_t *)smem + 4, &y, 4); }
+static inline void xv_lds_u64(xv_saddr smem, uint32_t &x, uint32_t &y) { memcpy(&x, smem, 4); memcpy(&y, smem + 4, 4); }
+static inline void xv_sts_u64(xv_saddr smem, uint32_t x, uint32_t y) { memcpy(smem, &x, 4); memcpy(smem + 4, &y, 4); }
+static inline uint32_t xv_opaque_u32(uint32_t v) { return v; }
 static inline uint8_t *xv_opaque(uint8_t *p) { return p; }
 static inline const uint8_t *xv_opaque(const uint8_t *p) { return p; }
 

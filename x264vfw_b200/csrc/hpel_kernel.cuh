@@ -89,7 +89,7 @@ XV_DEVICE HpelWord hpel_fix_word(HpelWord wd, int side)      // side: -1 left of
 #define HPEL_RING  4            // ring slots (power of two > HPEL_DIST)
 
 // request a lane's 8 pixels of one row into its ring slot (one cp.async group per call)
-XV_DEVICE void hpel_fetch_row(HpelWord *slot, const uint8_t *rowc, int fx, int cfx, int w, bool aligned)
+XV_DEVICE void hpel_fetch_row(xv_saddr slot, const uint8_t *rowc, int fx, int cfx, int w, bool aligned)
 {
     if (aligned) xv_cp_async8(slot, rowc);
     else { const HpelWord wd = hpel_load_word(rowc, fx, cfx, w, false); xv_sts_u64(slot, wd.x, wd.y); }
@@ -129,7 +129,12 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     const int fx = 8 * wj;                                    // frame x of its first pixel
     const uint8_t *S = job.src + (size_t)frame * job.src_frame_bytes;
     const int ss = job.src_stride;
-    const bool aligned = ((((uintptr_t)S) | (uintptr_t)(uint32_t)ss) & 7) == 0;   // warp-uniform
+    const int right_lane = (w >> 3) - tile * HPEL_TILE + 1;   // lane of the word just right of the frame
+    // warp-uniform facts, kept in one register (recomputing them from the kernel parameters cost a dozen issue
+    // slots per row): 1 = 8-byte aligned plane, 2 = first tile of the row, 4 = last tile of the row
+    const uint32_t flags = xv_opaque_u32((((((uintptr_t)S) | (uintptr_t)(uint32_t)ss) & 7) == 0 ? 1u : 0u) |
+                                         (tile == 0 ? 2u : 0u) | (right_lane >= 1 && right_lane <= 31 ? 4u : 0u));
+    const bool aligned = (flags & 1u) != 0;
     const int cfx = min(max(fx, 0), w - 8);                   // column actually loaded (aligned planes)
     const int side = !aligned ? 0 : fx < 0 ? -1 : fx >= w ? 1 : 0;
     const int fy0 = strip * job.rows_per_strip - 8;
@@ -139,23 +144,31 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     // just left of the frame; lane 31 only as the word just right of it
     const bool left_word = wj == -1, right_word = wj == nw8;
     const bool store_lane = (lane >= 1 && lane <= HPEL_TILE && wj <= nw8) || left_word || right_word;
-    const int right_lane = nw8 - tile * HPEL_TILE + 1;        // lane of the word just right of the frame
-    const bool left_tile = tile == 0, right_tile = right_lane >= 1 && right_lane <= 31;
+    const bool left_tile = (flags & 2u) != 0, right_tile = (flags & 4u) != 0;
     const uint32_t pb = (uint32_t)job.plane_bytes, own_off = (uint32_t)(fx + HPEL_PAD);
     // the rest of the border: columns 0..23 (lanes 1..3 of the first tile) and w+40..w+63 (lanes 4..6 of the
     // last tile) repeat the first / last filtered pixel of the row
-    const bool edge_tile = left_tile || right_tile;
+    const bool edge_tile = (flags & 6u) != 0;
     const bool edge_lane = lane >= 1 && lane <= 6 && (lane <= 3 ? left_tile : right_tile);
     const uint32_t edge_off = lane <= 3 ? 8u * (lane - 1) : (uint32_t)(w + HPEL_PAD + 8) + 8u * (lane - 4);
 
     // sliding window: row fy-2+k of the (clamped) frame lives in s[k], widened to 16-bit pairs
     uint32_t s[6][4];
+    {
+        HpelWord first[5];                                    // all five requests go out before the first is used
+        if (aligned) {
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const int sy = min(max(fy0 - 2 + k, 0), h - 1);
-        const HpelWord wd = hpel_fix_word(hpel_load_word(S + ((size_t)sy * ss + cfx), fx, cfx, w, aligned), side);
-        s[k][0] = xv_prmt(wd.x, 0u, 0x4140); s[k][1] = xv_prmt(wd.x, 0u, 0x4342);
-        s[k][2] = xv_prmt(wd.y, 0u, 0x4140); s[k][3] = xv_prmt(wd.y, 0u, 0x4342);
+            for (int k = 0; k < 5; k++) xv_ld_u64(S + ((size_t)min(max(fy0 - 2 + k, 0), h - 1) * ss + cfx), first[k].x, first[k].y);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 5; k++) first[k] = hpel_load_word(S + ((size_t)min(max(fy0 - 2 + k, 0), h - 1) * ss + cfx), fx, cfx, w, false);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const HpelWord wd = hpel_fix_word(first[k], side);
+            s[k][0] = xv_prmt(wd.x, 0u, 0x4140); s[k][1] = xv_prmt(wd.x, 0u, 0x4342);
+            s[k][2] = xv_prmt(wd.y, 0u, 0x4140); s[k][3] = xv_prmt(wd.y, 0u, 0x4342);
+        }
     }
 
     // The next HPEL_DIST rows are always in flight, through a per-lane ring in shared memory filled by cp.async:
@@ -163,9 +176,10 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     // double buffer needs either an unrolled loop or a copy of a register that is still being filled, and that
     // copy waits for the load -- it held 25 % of the stall samples).
     XV_SHARED HpelWord ring[HPEL_RING][32];
+    const xv_saddr ring0 = xv_saddr_of(&ring[0][lane]);       // slot k of this lane = ring0 + 256 k
 #pragma unroll
     for (int k = 0; k < HPEL_DIST; k++)
-        hpel_fetch_row(&ring[k][lane], S + ((size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss + cfx), fx, cfx, w, aligned);
+        hpel_fetch_row(ring0 + 256u * k, S + ((size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss + cfx), fx, cfx, w, aligned);
     // running store address of row fy (own word; the border word is edge_delta away)
     uint8_t *dp = D + ((size_t)(fy0 + HPEL_PAD) * job.stride + own_off);
     // running load address: row clamp(fy+3+HPEL_DIST) of the frame, this lane's column; it moves down while inside the frame
@@ -176,17 +190,16 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     // the loop body stays a few KB -- unrolled by six (rotation by renaming) it was 55 KB, beyond the 32 KB
     // L1.5 instruction cache, and a quarter of the stall samples were "no instruction".
     // (no exit inside the loop: an EXIT, even predicated off, waits for the loads in flight)
-    const int ntrips = min(job.rows_per_strip, h + 8 - fy0);
 #pragma unroll 1
-    for (int i = 0; i < ntrips; i++) {
+    for (int fy = fy0, i = 0, left = min(job.rows_per_strip, h + 8 - fy0); left > 0;
+         left--, fy++, i = (i + 1) & (HPEL_RING - 1)) {                              // i = ring slot of row fy+3
         {
-            const int fy = fy0 + i;
             {
-                hpel_fetch_row(&ring[(i + HPEL_DIST) & (HPEL_RING - 1)][lane], rp, fx, cfx, w, aligned);   // row fy+3+DIST
+                hpel_fetch_row(ring0 + 256u * ((i + HPEL_DIST) & (HPEL_RING - 1)), rp, fx, cfx, w, aligned);   // row fy+3+DIST
                 if ((unsigned)(fy + 3 + HPEL_DIST) < (unsigned)(h - 1)) rp += ss;
                 xv_cp_async_wait<HPEL_DIST>();                                                       // row fy+3 has landed
                 HpelWord wd;
-                xv_lds_u64(&ring[i & (HPEL_RING - 1)][lane], wd.x, wd.y);
+                xv_lds_u64(ring0 + 256u * (i & (HPEL_RING - 1)), wd.x, wd.y);
                 if (edge_tile) wd = hpel_fix_word(wd, side);
                 uint32_t *n = s[5];
                 n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);

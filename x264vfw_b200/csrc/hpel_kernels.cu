@@ -14,21 +14,25 @@ __device__ __forceinline__ void xv_ld_u64(const uint8_t *p, uint32_t &x, uint32_
 __device__ __forceinline__ uint32_t xv_ld_u8(const uint8_t *p) { return __ldg(p); }
 __device__ __forceinline__ void xv_st_u32(uint8_t *p, uint32_t v) { asm volatile("st.global.b32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void xv_st_u64(uint8_t *p, uint32_t x, uint32_t y) { asm volatile("st.global.v2.b32 [%0], {%1, %2};" :: "l"(p), "r"(x), "r"(y) : "memory"); }
+// shared-memory addresses are carried as 32-bit shared-window offsets
+typedef uint32_t xv_saddr;
+__device__ __forceinline__ xv_saddr xv_saddr_of(const void *smem) { return (uint32_t)__cvta_generic_to_shared(smem); }
 // 8 bytes global -> shared without a destination register; groups complete in order
-__device__ __forceinline__ void xv_cp_async8(void *smem, const void *gmem)
+__device__ __forceinline__ void xv_cp_async8(xv_saddr smem, const void *gmem)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void xv_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void xv_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-__device__ __forceinline__ void xv_lds_u64(const void *smem, uint32_t &x, uint32_t &y)
+__device__ __forceinline__ void xv_lds_u64(xv_saddr smem, uint32_t &x, uint32_t &y)
 {
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"((unsigned)__cvta_generic_to_shared(smem)) : "memory");
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(smem) : "memory");
 }
-__device__ __forceinline__ void xv_sts_u64(void *smem, uint32_t x, uint32_t y)
+__device__ __forceinline__ void xv_sts_u64(xv_saddr smem, uint32_t x, uint32_t y)
 {
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "r"(x), "r"(y) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(smem), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ uint32_t xv_opaque_u32(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 // keeps the compiler from folding the frame's base back into every address computation
 __device__ __forceinline__ uint8_t *xv_opaque(uint8_t *p) { asm volatile("" : "+l"(p)); return p; }
 __device__ __forceinline__ const uint8_t *xv_opaque(const uint8_t *p) { asm volatile("" : "+l"(p)); return p; }
@@ -69,7 +73,7 @@ namespace xv {
 
 // one warp per block: tiles at the frame's edges do more work (border), a block of several warps would
 // hold its slot until the slowest one is done
-__global__ void __launch_bounds__(32, 28)
+__global__ void __launch_bounds__(32, 25)
 hpel_kernel(HpelJob job)
 {
     hpel_unit(job, blockIdx.x, blockIdx.y, threadIdx.x);
