@@ -86,3 +86,31 @@ def test_warp_program_on_cpu_matches_checker(sim, case):
             assert np.array_equal(got[f, p, :, :w + 64], want[p, :, :w + 64]), (case, f, p)
         # nothing outside the w+64 columns is touched
         assert np.all(got[f, :, :, w + 64:] == 0x5A)
+
+
+def test_warp_program_on_cpu_random_geometry(sim):
+    """Random widths (multiples of 8, up to three tiles), heights, strip lengths and source alignments."""
+    rng = np.random.default_rng(20261017)
+    for _ in range(24):
+        w = 8 * int(rng.integers(1, 66))
+        h = int(rng.integers(1, 40))
+        rps = int(rng.integers(1, 30))
+        off = int(rng.choice([0, 0, 0, 8, 3]))
+        ss = w + int(rng.choice([0, 0, 8, 24, 5]))
+        if off % 8 or ss % 8:
+            w = min(w, 96)                      # the byte-gather path is slow in the simulation
+        g = ol.hpel_geometry(w, h)
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        if rng.integers(0, 3) == 0:
+            y = (y > 127).astype(np.uint8) * 255
+        src = np.zeros(ss * h + 32, dtype=np.uint8)
+        base = src.ctypes.data
+        pad = (-base) % 8                       # make the buffer itself 8-byte aligned, then apply `off`
+        for r in range(h):
+            src[pad + off + r * ss: pad + off + r * ss + w] = y[r]
+        dst = np.full(4 * g["plane_bytes"], 0x5A, dtype=np.uint8)
+        sim.sim_hpel(dst.ctypes.data, base + pad + off, ss, w, h, g["stride"], g["plane_bytes"], rps, ss * h, 4 * g["plane_bytes"], 1)
+        got = dst.reshape(4, h + 64, g["stride"])
+        want = ol.oracle_hpel_planes(y, w, h)
+        assert np.array_equal(got[:, :, :w + 64], want[:, :, :w + 64]), (w, h, rps, off, ss)
+        assert np.all(got[:, :, w + 64:] == 0x5A)

@@ -186,96 +186,94 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     const uint8_t *rp = S + ((size_t)min(max(fy0 + 3 + HPEL_DIST, 0), h - 1) * ss + cfx);
     const ptrdiff_t edge_delta = (ptrdiff_t)edge_off - (ptrdiff_t)own_off;
 
-    // One row per trip, NOT unrolled: the window moves by register copies (20 of ~230 instructions) so that
+    // One row per trip, NOT unrolled: the window moves by register copies (20 of ~250 instructions) so that
     // the loop body stays a few KB -- unrolled by six (rotation by renaming) it was 55 KB, beyond the 32 KB
-    // L1.5 instruction cache, and a quarter of the stall samples were "no instruction".
-    // (no exit inside the loop: an EXIT, even predicated off, waits for the loads in flight)
+    // L1.5 instruction cache, and a quarter of the stall samples were "no instruction".  The trip count is
+    // computed up front: an EXIT inside the loop, even predicated off, waits for every load in flight.
 #pragma unroll 1
     for (int fy = fy0, i = 0, left = min(job.rows_per_strip, h + 8 - fy0); left > 0;
          left--, fy++, i = (i + 1) & (HPEL_RING - 1)) {                              // i = ring slot of row fy+3
-        {
-            {
-                hpel_fetch_row(ring0 + 256u * ((i + HPEL_DIST) & (HPEL_RING - 1)), rp, fx, cfx, w, aligned);   // row fy+3+DIST
-                if ((unsigned)(fy + 3 + HPEL_DIST) < (unsigned)(h - 1)) rp += ss;
-                xv_cp_async_wait<HPEL_DIST>();                                                       // row fy+3 has landed
-                HpelWord wd;
-                xv_lds_u64(ring0 + 256u * (i & (HPEL_RING - 1)), wd.x, wd.y);
-                if (edge_tile) wd = hpel_fix_word(wd, side);
-                uint32_t *n = s[5];
-                n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);
-                n[2] = xv_prmt(wd.y, 0u, 0x4140); n[3] = xv_prmt(wd.y, 0u, 0x4342);
-            }
-            // ---- vertical 6-tap on packed pairs, lanes biased by 2576 --------------------------------
-            uint32_t v[4];
+        {   // request row fy+3+DIST, take delivery of row fy+3
+            hpel_fetch_row(ring0 + 256u * ((i + HPEL_DIST) & (HPEL_RING - 1)), rp, fx, cfx, w, aligned);   // row fy+3+DIST
+            if ((unsigned)(fy + 3 + HPEL_DIST) < (unsigned)(h - 1)) rp += ss;
+            xv_cp_async_wait<HPEL_DIST>();                                                       // row fy+3 has landed
+            HpelWord wd;
+            xv_lds_u64(ring0 + 256u * (i & (HPEL_RING - 1)), wd.x, wd.y);
+            if (edge_tile) wd = hpel_fix_word(wd, side);
+            uint32_t *n = s[5];
+            n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);
+            n[2] = xv_prmt(wd.y, 0u, 0x4140); n[3] = xv_prmt(wd.y, 0u, 0x4342);
+        }
+        // ---- vertical 6-tap on packed pairs, lanes biased by 2576 --------------------------------
+        uint32_t v[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint32_t t = s[0][i] + s[5][i] + 0x0A100A10u;
-                t += 20u * (s[2][i] + s[3][i]);
-                t -= 5u * (s[1][i] + s[4][i]);
-                v[i] = t;
-            }
-            HpelWord out[4];
-            // V plane
-            out[2].x = xv_prmt(hpel_clip_v(v[0]), hpel_clip_v(v[1]), 0x6420);
-            out[2].y = xv_prmt(hpel_clip_v(v[2]), hpel_clip_v(v[3]), 0x6420);
-            {   // P0 and H plane: byte windows of the 16-byte span (L, w0, w1, R), span offset 4 = own pixel 0
-                const uint32_t w0 = xv_prmt(s[2][0], s[2][1], 0x6420);
-                const uint32_t w1 = xv_prmt(s[2][2], s[2][3], 0x6420);
-                const uint32_t L = xv_shfl_up1(w1), R = xv_shfl_down1(w0);
-                const uint32_t o2 = xv_prmt(L, w0, 0x5432), o3 = xv_prmt(L, w0, 0x6543), o5 = xv_prmt(w0, w1, 0x4321);
-                const uint32_t o6 = xv_prmt(w0, w1, 0x5432), o7 = xv_prmt(w0, w1, 0x6543), o9 = xv_prmt(w1, R, 0x4321);
-                const uint32_t o10 = xv_prmt(w1, R, 0x5432), o11 = xv_prmt(w1, R, 0x6543), o13 = R >> 8;
-                out[0].x = w0; out[0].y = w1;
-                out[1].x = xv_pack_sat_u8(hpel_tap_h(o2, o6), hpel_tap_h(o3, o7), hpel_tap_h(w0, w1), hpel_tap_h(o5, o9));
-                out[1].y = xv_pack_sat_u8(hpel_tap_h(o6, o10), hpel_tap_h(o7, o11), hpel_tap_h(w1, R), hpel_tap_h(o9, o13));
-            }
-            {   // C plane: horizontal 6-tap over the vertical sums (pairs q[k] = (V[k], V[k+1]), k = -2..9)
-                const uint32_t Lv3 = xv_shfl_up1(v[3]), R0 = xv_shfl_down1(v[0]), R1 = xv_shfl_down1(v[1]);
-                const uint32_t qm1 = xv_prmt(Lv3, v[0], 0x5432), q1 = xv_prmt(v[0], v[1], 0x5432);
-                const uint32_t q3 = xv_prmt(v[1], v[2], 0x5432), q5 = xv_prmt(v[2], v[3], 0x5432);
-                const uint32_t q7 = xv_prmt(v[3], R0, 0x5432), q9 = xv_prmt(R0, R1, 0x5432);
-                out[3].x = xv_pack_sat_u8(hpel_tap_c(Lv3, v[0], v[1]), hpel_tap_c(qm1, q1, q3),
-                                          hpel_tap_c(v[0], v[1], v[2]), hpel_tap_c(q1, q3, q5));
-                out[3].y = xv_pack_sat_u8(hpel_tap_c(v[1], v[2], v[3]), hpel_tap_c(q3, q5, q7),
-                                          hpel_tap_c(v[2], v[3], R0), hpel_tap_c(q5, q7, q9));
-            }
-            // ---- the words just outside the frame: 4 filtered pixels next to the frame, the other 4 already
-            //      border (= the outermost filtered pixel); the rest of the border goes to the edge lanes -----
-            HpelWord e[4];
-            if (left_tile) {                                  // warp-uniform
+        for (int q = 0; q < 4; q++) {
+            uint32_t t = s[0][q] + s[5][q] + 0x0A100A10u;
+            t += 20u * (s[2][q] + s[3][q]);
+            t -= 5u * (s[1][q] + s[4][q]);
+            v[q] = t;
+        }
+        HpelWord out[4];
+        // V plane
+        out[2].x = xv_prmt(hpel_clip_v(v[0]), hpel_clip_v(v[1]), 0x6420);
+        out[2].y = xv_prmt(hpel_clip_v(v[2]), hpel_clip_v(v[3]), 0x6420);
+        {   // P0 and H plane: byte windows of the 16-byte span (L, w0, w1, R), span offset 4 = own pixel 0
+            const uint32_t w0 = xv_prmt(s[2][0], s[2][1], 0x6420);
+            const uint32_t w1 = xv_prmt(s[2][2], s[2][3], 0x6420);
+            const uint32_t L = xv_shfl_up1(w1), R = xv_shfl_down1(w0);
+            const uint32_t o2 = xv_prmt(L, w0, 0x5432), o3 = xv_prmt(L, w0, 0x6543), o5 = xv_prmt(w0, w1, 0x4321);
+            const uint32_t o6 = xv_prmt(w0, w1, 0x5432), o7 = xv_prmt(w0, w1, 0x6543), o9 = xv_prmt(w1, R, 0x4321);
+            const uint32_t o10 = xv_prmt(w1, R, 0x5432), o11 = xv_prmt(w1, R, 0x6543), o13 = R >> 8;
+            out[0].x = w0; out[0].y = w1;
+            out[1].x = xv_pack_sat_u8(hpel_tap_h(o2, o6), hpel_tap_h(o3, o7), hpel_tap_h(w0, w1), hpel_tap_h(o5, o9));
+            out[1].y = xv_pack_sat_u8(hpel_tap_h(o6, o10), hpel_tap_h(o7, o11), hpel_tap_h(w1, R), hpel_tap_h(o9, o13));
+        }
+        {   // C plane: horizontal 6-tap over the vertical sums (pairs q[k] = (V[k], V[k+1]), k = -2..9)
+            const uint32_t Lv3 = xv_shfl_up1(v[3]), R0 = xv_shfl_down1(v[0]), R1 = xv_shfl_down1(v[1]);
+            const uint32_t qm1 = xv_prmt(Lv3, v[0], 0x5432), q1 = xv_prmt(v[0], v[1], 0x5432);
+            const uint32_t q3 = xv_prmt(v[1], v[2], 0x5432), q5 = xv_prmt(v[2], v[3], 0x5432);
+            const uint32_t q7 = xv_prmt(v[3], R0, 0x5432), q9 = xv_prmt(R0, R1, 0x5432);
+            out[3].x = xv_pack_sat_u8(hpel_tap_c(Lv3, v[0], v[1]), hpel_tap_c(qm1, q1, q3),
+                                      hpel_tap_c(v[0], v[1], v[2]), hpel_tap_c(q1, q3, q5));
+            out[3].y = xv_pack_sat_u8(hpel_tap_c(v[1], v[2], v[3]), hpel_tap_c(q3, q5, q7),
+                                      hpel_tap_c(v[2], v[3], R0), hpel_tap_c(q5, q7, q9));
+        }
+        // ---- the words just outside the frame: 4 filtered pixels next to the frame, the other 4 already
+        //      border (= the outermost filtered pixel); the rest of the border goes to the edge lanes -----
+        HpelWord e[4];
+        if (left_tile) {                                  // warp-uniform
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    const uint32_t rep = (out[p].y & 0xFFu) * 0x01010101u;
-                    if (left_word) out[p].x = rep;
-                    e[p].x = e[p].y = xv_shfl_idx(rep, 0);
-                }
+            for (int p = 0; p < 4; p++) {
+                const uint32_t rep = (out[p].y & 0xFFu) * 0x01010101u;
+                if (left_word) out[p].x = rep;
+                e[p].x = e[p].y = xv_shfl_idx(rep, 0);
             }
-            if (right_tile) {                                 // warp-uniform
+        }
+        if (right_tile) {                                 // warp-uniform
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    const uint32_t rep = (out[p].x >> 24) * 0x01010101u;
-                    if (right_word) out[p].y = rep;
-                    const uint32_t br = xv_shfl_idx(rep, right_lane & 31);
-                    if (lane > 3) e[p].x = e[p].y = br;
-                }
+            for (int p = 0; p < 4; p++) {
+                const uint32_t rep = (out[p].x >> 24) * 0x01010101u;
+                if (right_word) out[p].y = rep;
+                const uint32_t br = xv_shfl_idx(rep, right_lane & 31);
+                if (lane > 3) e[p].x = e[p].y = br;
             }
-            if (store_lane) hpel_store4(dp, pb, out);
-            if (edge_lane) hpel_store4(dp + edge_delta, pb, e);
-            dp += job.stride;
-            if (fy == -8 || fy == h + 7) {                    // top / bottom border: 24 more copies of this row
-                const int rb = fy == -8 ? 0 : h + HPEL_PAD + 8;
+        }
+        if (store_lane) hpel_store4(dp, pb, out);
+        if (edge_lane) hpel_store4(dp + edge_delta, pb, e);
+        dp += job.stride;
+        if (fy == -8 || fy == h + 7) {                    // top / bottom border: 24 more copies of this row
+            const int rb = fy == -8 ? 0 : h + HPEL_PAD + 8;
 #pragma unroll 1
-                for (int r = rb; r < rb + 24; r++) {
-                    const size_t rr = (size_t)r * job.stride;
-                    if (store_lane) hpel_store4(D + (rr + own_off), pb, out);
-                    if (edge_lane) hpel_store4(D + (rr + edge_off), pb, e);
-                }
+            for (int r = rb; r < rb + 24; r++) {
+                const size_t rr = (size_t)r * job.stride;
+                if (store_lane) hpel_store4(D + (rr + own_off), pb, out);
+                if (edge_lane) hpel_store4(D + (rr + edge_off), pb, e);
             }
+        }
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
+        for (int k = 0; k < 5; k++) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) s[k][q] = s[k + 1][q];
-            }
+            for (int q = 0; q < 4; q++) s[k][q] = s[k + 1][q];
         }
     }
 }
