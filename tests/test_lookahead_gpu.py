@@ -322,6 +322,35 @@ def test_concurrent_sessions_are_deterministic_and_match_oracle():
         assert all(np.array_equal(a["qp_offset"].view(np.uint32), b["qp_offset"].view(np.uint32)) for a, b in zip(got, want)), k
 
 
+def test_gop_segmented_clip_equals_one_reference_session_per_segment():
+    """a single clip shards only as GOP segments, each through its own session (closed GOP, own IDR).
+    Two 'ranks' share the device here; the stitched result must be what one CPU reference session per segment gives."""
+    from x264vfw_b200 import lookahead, sharding
+    w, h, n, seg = 192, 128, 30, 12
+    packed = make_clip(w, h, n, cuts=(17,))
+    i420 = to_i420(packed, w, h)
+    po, pg = params_pair("medium", w, h, rc_lookahead=8, keyint_max=50, keyint_min=5)
+    parts = {}
+    for rank in range(2):
+        parts.update(sharding.run_clip_segments(lambda: lookahead.Lookahead(pg, device=0), i420, seg, rank, 2))
+    got = sharding.stitch_segments(parts)
+    want = []
+    for a, b in sharding.gop_segments(n, seg):
+        orc = ol.OracleLookahead(po)
+        try:
+            want += [dict(d, i_frame=d["i_frame"] + a) for d in run_session(orc, i420[a:b], lambda la, f: la.put_i420(f))]
+        finally:
+            orc.close()
+    assert [d["i_frame"] for d in got] == [d["i_frame"] for d in want]
+    assert sorted(d["i_frame"] for d in got) == list(range(n))
+    for a, b in zip(got, want):
+        for k in ("i_type", "b_keyframe", "i_bframes", "i_cost_est", "i_cost_est_aq", "i_intra_mbs"):
+            assert a[k] == b[k], (k, a["i_frame"], a[k], b[k])
+        assert np.array_equal(a["qp_offset"].view(np.uint32), b["qp_offset"].view(np.uint32)), a["i_frame"]
+    starts = {a for a, _ in sharding.gop_segments(n, seg)}
+    assert all(d["i_type"] == 1 and d["b_keyframe"] for d in got if d["i_frame"] in starts)   # X264_TYPE_IDR
+
+
 def _golden_cases():
     import json, os
     return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lookahead_golden.json")))
