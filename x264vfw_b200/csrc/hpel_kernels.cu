@@ -2,7 +2,6 @@
 // description).  sm_100a device versions of the helpers the program uses.
 #include "common.cuh"
 #include "csp_kernels.h"
-#include <stdlib.h>
 
 #define XV_DEVICE __device__ __forceinline__
 #define XV_SHARED __shared__
@@ -72,7 +71,8 @@ __device__ __forceinline__ uint32_t xv_pack_sat_u8(int v0, int v1, int v2, int v
 namespace xv {
 
 // one warp per block: tiles at the frame's edges do more work (border), a block of several warps would
-// hold its slot until the slowest one is done
+// hold its slot until the slowest one is done.  Register budget: asking for 25 blocks (cap 80) lets ptxas settle
+// on 72 registers without a spill -- 28 warps per SM all the same; asking for 28 (cap 72) spills the trip counter.
 __global__ void __launch_bounds__(32, 25)
 hpel_kernel(HpelJob job)
 {
