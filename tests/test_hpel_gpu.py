@@ -91,6 +91,30 @@ def test_hpel_filter_unaligned_source_and_big_batch(ctx):
         assert np.array_equal(got[f, :, :, :w + 64], want[:, :, :w + 64]), f
 
 
+def test_device_path_matches_the_committed_fingerprints(ctx):
+    """The device path against tests/golden/hpel_golden.json, without the checker in the loop."""
+    import importlib.util
+    import json
+    import os
+    import torch
+    from x264vfw_b200 import hpel
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_hpel_golden", os.path.join(gdir, "make_hpel_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    for case in json.load(open(os.path.join(gdir, "hpel_golden.json"))):
+        w, h = case["w"], case["h"]
+        y = mg.source_plane(w, h)
+        g = hpel.geometry(w, h)
+        d_src = torch.from_numpy(y.reshape(-1)).cuda()
+        d_out = torch.zeros(4 * g.plane_bytes, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        hpel.hpel_filter(ctx, d_out.data_ptr(), d_src.data_ptr(), w, w, h)
+        ctx.sync()
+        got = d_out.cpu().numpy().reshape(4, h + 64, g.stride)
+        assert mg.fingerprint(got, w) == case["planes_fnv"], (w, h)
+
+
 def test_hpel_filter_rejects_bad_geometry(ctx):
     from x264vfw_b200 import hpel
     from x264vfw_b200._lib import CudaError

@@ -42,6 +42,21 @@ def test_checker_plane0_is_the_border_expanded_frame():
     assert np.array_equal(p0, np.pad(y, 32, mode="edge"))
 
 
+def test_checker_matches_the_committed_fingerprints():
+    """tests/golden/hpel_golden.json freezes the checker (it is not a reference output: libx264 is absent)."""
+    import json
+    sys_path = os.path.join(ROOT, "tests", "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_hpel_golden", os.path.join(sys_path, "make_hpel_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    for case in json.load(open(os.path.join(sys_path, "hpel_golden.json"))):
+        w, h = case["w"], case["h"]
+        y = mg.source_plane(w, h)
+        assert mg.fnv(y) == case["src_fnv"], (w, h)
+        assert mg.fingerprint(ol.oracle_hpel_planes(y, w, h), w) == case["planes_fnv"], (w, h)
+
+
 @pytest.fixture(scope="module")
 def sim():
     so = os.path.join(ROOT, "tests", "sim", "_build", "libhpel_sim.so")
