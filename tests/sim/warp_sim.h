@@ -74,6 +74,7 @@ template <int N> static inline void xv_cp_async_wait() {}
 static inline void xv_lds_u64(xv_saddr smem, uint32_t &x, uint32_t &y) { memcpy(&x, smem, 4); memcpy(&y, smem + 4, 4); }
 static inline void xv_sts_u64(xv_saddr smem, uint32_t x, uint32_t y) { memcpy(smem, &x, 4); memcpy(smem + 4, &y, 4); }
 static inline uint32_t xv_opaque_u32(uint32_t v) { return v; }
+static inline xv_saddr xv_opaque_saddr(xv_saddr v) { return v; }
 static inline uint8_t *xv_opaque(uint8_t *p) { return p; }
 static inline const uint8_t *xv_opaque(const uint8_t *p) { return p; }
 

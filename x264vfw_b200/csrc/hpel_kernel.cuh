@@ -41,6 +41,7 @@ struct HpelJob {
     int stride; size_t plane_bytes;                   // stride >= w + 64, plane_bytes = stride * (h + 64)
     int rows_per_strip;
     int ntiles, nstrips;                              // ceil(w/8 / 30), ceil((h+16) / rows_per_strip)
+    int h_m1, h_p7;                                   // h - 1, h + 7: compared every trip, read straight from the parameter bank
     size_t src_frame_bytes, dst_frame_bytes;
 };
 
@@ -56,6 +57,7 @@ static inline long long hpel_plan(HpelJob &job, int n_frames)
     if (job.rows_per_strip <= 0)
         job.rows_per_strip = (long long)job.ntiles * ((job.h + 16 + 23) / 24) * n_frames >= 148 * 24 ? 24 : 12;
     job.nstrips = (job.h + 16 + job.rows_per_strip - 1) / job.rows_per_strip;
+    job.h_m1 = job.h - 1; job.h_p7 = job.h + 7;
     return (long long)job.ntiles * job.nstrips;
 }
 
@@ -96,7 +98,7 @@ XV_DEVICE void hpel_fetch_row(xv_saddr slot, const uint8_t *rowc, int fx, int cf
     xv_cp_async_commit();
 }
 
-XV_DEVICE void hpel_store4(uint8_t *d, uint32_t pb, const HpelWord v[4])
+XV_DEVICE void hpel_store4(uint8_t *d, size_t pb, const HpelWord v[4])
 {
     xv_st_u64(d, v[0].x, v[0].y); d += pb;
     xv_st_u64(d, v[1].x, v[1].y); d += pb;
@@ -130,27 +132,32 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     const uint8_t *S = job.src + (size_t)frame * job.src_frame_bytes;
     const int ss = job.src_stride;
     const int right_lane = (w >> 3) - tile * HPEL_TILE + 1;   // lane of the word just right of the frame
-    // warp-uniform facts, kept in one register (recomputing them from the kernel parameters cost a dozen issue
-    // slots per row): 1 = 8-byte aligned plane, 2 = first tile of the row, 4 = last tile of the row
-    const uint32_t flags = xv_opaque_u32((((((uintptr_t)S) | (uintptr_t)(uint32_t)ss) & 7) == 0 ? 1u : 0u) |
-                                         (tile == 0 ? 2u : 0u) | (right_lane >= 1 && right_lane <= 31 ? 4u : 0u));
+    // who stores: lanes 1..30 up to and including the word just right of the frame; lane 0 only as the word
+    // just left of the frame; lane 31 only as the word just right of it.  The rest of the border: columns 0..23
+    // (lanes 1..3 of the first tile) and w+40..w+63 (lanes 4..6 of the last tile) repeat the first / last
+    // filtered pixel of the row.
+    // Facts that never change, kept in two registers (recomputing them from the kernel parameters and the lane
+    // number cost two dozen issue slots per row).  `flags` is warp-uniform (branches on it hold shuffles):
+    // 1 = 8-byte aligned plane, 2 = first tile of the row, 4 = last tile of the row.  `lflags` is per lane:
+    // 1 = stores its own word, 2 = stores a border word, 4 = owns the word just left of the frame, 8 = the word
+    // just right of it, 16 = lane > 3.
+    const bool lt = tile == 0, rt = right_lane >= 1 && right_lane <= 31;
+    const uint32_t flags = xv_opaque_u32((((((uintptr_t)S) | (uintptr_t)(uint32_t)ss) & 7) == 0 ? 1u : 0u) | (lt ? 2u : 0u) | (rt ? 4u : 0u));
+    const uint32_t lflags = xv_opaque_u32(((lane >= 1 && lane <= HPEL_TILE && wj <= nw8) || wj == -1 || wj == nw8 ? 1u : 0u) |
+                                          (lane >= 1 && lane <= 6 && (lane <= 3 ? lt : rt) ? 2u : 0u) |
+                                          (wj == -1 ? 4u : 0u) | (wj == nw8 ? 8u : 0u) | (lane > 3 ? 16u : 0u));
     const bool aligned = (flags & 1u) != 0;
     const int cfx = min(max(fx, 0), w - 8);                   // column actually loaded (aligned planes)
     const int side = !aligned ? 0 : fx < 0 ? -1 : fx >= w ? 1 : 0;
     const int fy0 = strip * job.rows_per_strip - 8;
 
     uint8_t *D = xv_opaque(job.dst + (size_t)frame * job.dst_frame_bytes);
-    // who stores: lanes 1..30 up to and including the word just right of the frame; lane 0 only as the word
-    // just left of the frame; lane 31 only as the word just right of it
-    const bool left_word = wj == -1, right_word = wj == nw8;
-    const bool store_lane = (lane >= 1 && lane <= HPEL_TILE && wj <= nw8) || left_word || right_word;
-    const bool left_tile = (flags & 2u) != 0, right_tile = (flags & 4u) != 0;
-    const uint32_t pb = (uint32_t)job.plane_bytes, own_off = (uint32_t)(fx + HPEL_PAD);
-    // the rest of the border: columns 0..23 (lanes 1..3 of the first tile) and w+40..w+63 (lanes 4..6 of the
-    // last tile) repeat the first / last filtered pixel of the row
-    const bool edge_tile = (flags & 6u) != 0;
-    const bool edge_lane = lane >= 1 && lane <= 6 && (lane <= 3 ? left_tile : right_tile);
+    const uint32_t own_off = (uint32_t)(fx + HPEL_PAD);
     const uint32_t edge_off = lane <= 3 ? 8u * (lane - 1) : (uint32_t)(w + HPEL_PAD + 8) + 8u * (lane - 4);
+    const bool left_tile = (flags & 2u) != 0, right_tile = (flags & 4u) != 0, edge_tile = (flags & 6u) != 0;
+    const bool store_lane = (lflags & 1u) != 0, edge_lane = (lflags & 2u) != 0;
+    const bool left_word = (lflags & 4u) != 0, right_word = (lflags & 8u) != 0;
+    const size_t pb = job.plane_bytes;
 
     // sliding window: row fy-2+k of the (clamped) frame lives in s[k], widened to 16-bit pairs
     uint32_t s[6][4];
@@ -176,7 +183,8 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     // double buffer needs either an unrolled loop or a copy of a register that is still being filled, and that
     // copy waits for the load -- it held 25 % of the stall samples).
     XV_SHARED HpelWord ring[HPEL_RING][32];
-    const xv_saddr ring0 = xv_saddr_of(&ring[0][lane]);       // slot k of this lane = ring0 + 256 k
+    const xv_saddr ring0 = xv_opaque_saddr(xv_saddr_of(&ring[0][lane]));   // slot k of this lane = ring0 + 256 k; opaque: otherwise
+                                                                         // it is rematerialised (two S2R + five more) every trip
 #pragma unroll
     for (int k = 0; k < HPEL_DIST; k++)
         hpel_fetch_row(ring0 + 256u * k, S + ((size_t)min(max(fy0 + 3 + k, 0), h - 1) * ss + cfx), fx, cfx, w, aligned);
@@ -195,7 +203,7 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
          left--, fy++, i = (i + 1) & (HPEL_RING - 1)) {                              // i = ring slot of row fy+3
         {   // request row fy+3+DIST, take delivery of row fy+3
             hpel_fetch_row(ring0 + 256u * ((i + HPEL_DIST) & (HPEL_RING - 1)), rp, fx, cfx, w, aligned);   // row fy+3+DIST
-            if ((unsigned)(fy + 3 + HPEL_DIST) < (unsigned)(h - 1)) rp += ss;
+            if ((unsigned)(fy + 3 + HPEL_DIST) < (unsigned)job.h_m1) rp += ss;
             xv_cp_async_wait<HPEL_DIST>();                                                       // row fy+3 has landed
             HpelWord wd;
             xv_lds_u64(ring0 + 256u * (i & (HPEL_RING - 1)), wd.x, wd.y);
@@ -255,13 +263,13 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
                 const uint32_t rep = (out[p].x >> 24) * 0x01010101u;
                 if (right_word) out[p].y = rep;
                 const uint32_t br = xv_shfl_idx(rep, right_lane & 31);
-                if (lane > 3) e[p].x = e[p].y = br;
+                if (lflags & 16u) e[p].x = e[p].y = br;
             }
         }
         if (store_lane) hpel_store4(dp, pb, out);
         if (edge_lane) hpel_store4(dp + edge_delta, pb, e);
         dp += job.stride;
-        if (fy == -8 || fy == h + 7) {                    // top / bottom border: 24 more copies of this row
+        if (fy == -8 || fy == job.h_p7) {                 // top / bottom border: 24 more copies of this row
             const int rb = fy == -8 ? 0 : h + HPEL_PAD + 8;
 #pragma unroll 1
             for (int r = rb; r < rb + 24; r++) {

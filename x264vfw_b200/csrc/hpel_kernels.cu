@@ -32,6 +32,7 @@ __device__ __forceinline__ void xv_sts_u64(xv_saddr smem, uint32_t x, uint32_t y
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(smem), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ uint32_t xv_opaque_u32(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ xv_saddr xv_opaque_saddr(xv_saddr v) { asm volatile("" : "+r"(v)); return v; }
 // keeps the compiler from folding the frame's base back into every address computation
 __device__ __forceinline__ uint8_t *xv_opaque(uint8_t *p) { asm volatile("" : "+l"(p)); return p; }
 __device__ __forceinline__ const uint8_t *xv_opaque(const uint8_t *p) { asm volatile("" : "+l"(p)); return p; }
