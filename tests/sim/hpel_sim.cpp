@@ -14,6 +14,9 @@ extern "C" int sim_hpel(uint8_t *dst, const uint8_t *src, int src_stride, int w,
     const long long units = xv::hpel_plan(job, n_frames);
     for (int f = 0; f < n_frames; f++)
         for (long long u = 0; u < units; u++)
-            xv::sim_run_warp([&](int lane) { xv::hpel_unit(job, (int)u, f, lane); });
+            xv::sim_run_warp([&](int lane) {
+                if (job.aligned) xv::hpel_unit<true>(job, (int)u, f, lane);
+                else xv::hpel_unit<false>(job, (int)u, f, lane);
+            });
     return (int)units;
 }

@@ -42,6 +42,7 @@ struct HpelJob {
     int rows_per_strip;
     int ntiles, nstrips;                              // ceil(w/8 / 30), ceil((h+16) / rows_per_strip)
     int h_m1, h_p7;                                   // h - 1, h + 7: compared every trip, read straight from the parameter bank
+    int aligned;                                      // every frame's plane and the stride are 8-byte aligned: picks the instantiation
     size_t src_frame_bytes, dst_frame_bytes;
 };
 
@@ -58,6 +59,7 @@ static inline long long hpel_plan(HpelJob &job, int n_frames)
         job.rows_per_strip = (long long)job.ntiles * ((job.h + 16 + 23) / 24) * n_frames >= 148 * 24 ? 24 : 12;
     job.nstrips = (job.h + 16 + job.rows_per_strip - 1) / job.rows_per_strip;
     job.h_m1 = job.h - 1; job.h_p7 = job.h + 7;
+    job.aligned = ((((uintptr_t)job.src) | (uintptr_t)(uint32_t)job.src_stride | (n_frames > 1 ? (uintptr_t)job.src_frame_bytes : 0)) & 7) == 0;
     return (long long)job.ntiles * job.nstrips;
 }
 
@@ -89,6 +91,7 @@ XV_DEVICE HpelWord hpel_fix_word(HpelWord wd, int side)      // side: -1 left of
 
 #define HPEL_DIST  3            // rows in flight per lane
 #define HPEL_RING  4            // ring slots (power of two > HPEL_DIST)
+#define HPEL_UNROLL 2           // rows per loop trip (divides HPEL_RING)
 
 // request a lane's 8 pixels of one row into its ring slot (one cp.async group per call)
 XV_DEVICE void hpel_fetch_row(xv_saddr slot, const uint8_t *rowc, int fx, int cfx, int w, bool aligned)
@@ -121,7 +124,9 @@ XV_DEVICE int hpel_tap_c(uint32_t qm2, uint32_t q0, uint32_t qp2)   // pairs (V[
     return xv_dp2a_lo(qm2, 0xFB01u, xv_dp2a_lo(q0, 0x1414u, xv_dp2a_lo(qp2, 0x01FBu, 512 - 32 * 2576))) >> 10;
 }
 
-// one warp: tile `unit % ntiles` of strip `unit / ntiles` of frame `frame`
+// one warp: tile `unit % ntiles` of strip `unit / ntiles` of frame `frame`.  ALIGNED (= job.aligned, decided by
+// hpel_plan) selects 64-bit loads / cp.async; otherwise bytes are gathered.
+template <bool ALIGNED>
 XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
 {
     const int tile = unit % job.ntiles, strip = unit / job.ntiles;
@@ -138,15 +143,15 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     // filtered pixel of the row.
     // Facts that never change, kept in two registers (recomputing them from the kernel parameters and the lane
     // number cost two dozen issue slots per row).  `flags` is warp-uniform (branches on it hold shuffles):
-    // 1 = 8-byte aligned plane, 2 = first tile of the row, 4 = last tile of the row.  `lflags` is per lane:
+    // 2 = first tile of the row, 4 = last tile of the row.  `lflags` is per lane:
     // 1 = stores its own word, 2 = stores a border word, 4 = owns the word just left of the frame, 8 = the word
     // just right of it, 16 = lane > 3.
     const bool lt = tile == 0, rt = right_lane >= 1 && right_lane <= 31;
-    const uint32_t flags = xv_opaque_u32((((((uintptr_t)S) | (uintptr_t)(uint32_t)ss) & 7) == 0 ? 1u : 0u) | (lt ? 2u : 0u) | (rt ? 4u : 0u));
+    const uint32_t flags = xv_opaque_u32((lt ? 2u : 0u) | (rt ? 4u : 0u));
     const uint32_t lflags = xv_opaque_u32(((lane >= 1 && lane <= HPEL_TILE && wj <= nw8) || wj == -1 || wj == nw8 ? 1u : 0u) |
                                           (lane >= 1 && lane <= 6 && (lane <= 3 ? lt : rt) ? 2u : 0u) |
                                           (wj == -1 ? 4u : 0u) | (wj == nw8 ? 8u : 0u) | (lane > 3 ? 16u : 0u));
-    const bool aligned = (flags & 1u) != 0;
+    constexpr bool aligned = ALIGNED;
     const int cfx = min(max(fx, 0), w - 8);                   // column actually loaded (aligned planes)
     const int side = !aligned ? 0 : fx < 0 ? -1 : fx >= w ? 1 : 0;
     const int fy0 = strip * job.rows_per_strip - 8;
@@ -160,7 +165,7 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     const size_t pb = job.plane_bytes;
 
     // sliding window: row fy-2+k of the (clamped) frame lives in s[k], widened to 16-bit pairs
-    uint32_t s[6][4];
+    uint32_t s[5 + HPEL_UNROLL][4];
     {
         HpelWord first[5];                                    // all five requests go out before the first is used
         if (aligned) {
@@ -194,21 +199,26 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     const uint8_t *rp = S + ((size_t)min(max(fy0 + 3 + HPEL_DIST, 0), h - 1) * ss + cfx);
     const ptrdiff_t edge_delta = (ptrdiff_t)edge_off - (ptrdiff_t)own_off;
 
-    // One row per trip, NOT unrolled: the window moves by register copies (20 of ~250 instructions) so that
-    // the loop body stays a few KB -- unrolled by six (rotation by renaming) it was 55 KB, beyond the 32 KB
-    // L1.5 instruction cache, and a quarter of the stall samples were "no instruction".  The trip count is
-    // computed up front: an EXIT inside the loop, even predicated off, waits for every load in flight.
+    // Two rows per trip (HPEL_UNROLL): the window rotates by renaming inside a trip and moves by register copies
+    // between trips (10 copies per row instead of 20); the loop body stays ~7 KB on the interior path -- unrolled
+    // by six (no copies at all) it was 55 KB, beyond the 32 KB L1.5 instruction cache, and a quarter of the stall
+    // samples were "no instruction".  The trip count is computed up front: an EXIT inside the loop, even
+    // predicated off, waits for every load in flight.  An odd row count runs one row too many: it is computed
+    // from clamped (valid) source rows and not stored.
 #pragma unroll 1
     for (int fy = fy0, i = 0, left = min(job.rows_per_strip, h + 8 - fy0); left > 0;
-         left--, fy++, i = (i + 1) & (HPEL_RING - 1)) {                              // i = ring slot of row fy+3
-        {   // request row fy+3+DIST, take delivery of row fy+3
-            hpel_fetch_row(ring0 + 256u * ((i + HPEL_DIST) & (HPEL_RING - 1)), rp, fx, cfx, w, aligned);   // row fy+3+DIST
-            if ((unsigned)(fy + 3 + HPEL_DIST) < (unsigned)job.h_m1) rp += ss;
-            xv_cp_async_wait<HPEL_DIST>();                                                       // row fy+3 has landed
+         left -= HPEL_UNROLL, fy += HPEL_UNROLL, i = (i + HPEL_UNROLL) & (HPEL_RING - 1)) {   // i = ring slot of row fy+3
+#pragma unroll
+      for (int u = 0; u < HPEL_UNROLL; u++) {             // row fy+u: window s[u] .. s[u+5]
+        const bool live = u == 0 || left > u;             // warp-uniform
+        {   // request row fy+u+3+DIST, take delivery of row fy+u+3
+            hpel_fetch_row(ring0 + 256u * ((i + u + HPEL_DIST) & (HPEL_RING - 1)), rp, fx, cfx, w, aligned);
+            if ((unsigned)(fy + u + 3 + HPEL_DIST) < (unsigned)job.h_m1) rp += ss;
+            xv_cp_async_wait<HPEL_DIST>();                                                       // row fy+u+3 has landed
             HpelWord wd;
-            xv_lds_u64(ring0 + 256u * (i & (HPEL_RING - 1)), wd.x, wd.y);
+            xv_lds_u64(ring0 + 256u * ((i + u) & (HPEL_RING - 1)), wd.x, wd.y);
             if (edge_tile) wd = hpel_fix_word(wd, side);
-            uint32_t *n = s[5];
+            uint32_t *n = s[u + 5];
             n[0] = xv_prmt(wd.x, 0u, 0x4140); n[1] = xv_prmt(wd.x, 0u, 0x4342);
             n[2] = xv_prmt(wd.y, 0u, 0x4140); n[3] = xv_prmt(wd.y, 0u, 0x4342);
         }
@@ -216,9 +226,9 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
         uint32_t v[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            uint32_t t = s[0][q] + s[5][q] + 0x0A100A10u;
-            t += 20u * (s[2][q] + s[3][q]);
-            t -= 5u * (s[1][q] + s[4][q]);
+            uint32_t t = s[u][q] + s[u + 5][q] + 0x0A100A10u;
+            t += 20u * (s[u + 2][q] + s[u + 3][q]);
+            t -= 5u * (s[u + 1][q] + s[u + 4][q]);
             v[q] = t;
         }
         HpelWord out[4];
@@ -226,8 +236,8 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
         out[2].x = xv_prmt(hpel_clip_v(v[0]), hpel_clip_v(v[1]), 0x6420);
         out[2].y = xv_prmt(hpel_clip_v(v[2]), hpel_clip_v(v[3]), 0x6420);
         {   // P0 and H plane: byte windows of the 16-byte span (L, w0, w1, R), span offset 4 = own pixel 0
-            const uint32_t w0 = xv_prmt(s[2][0], s[2][1], 0x6420);
-            const uint32_t w1 = xv_prmt(s[2][2], s[2][3], 0x6420);
+            const uint32_t w0 = xv_prmt(s[u + 2][0], s[u + 2][1], 0x6420);
+            const uint32_t w1 = xv_prmt(s[u + 2][2], s[u + 2][3], 0x6420);
             const uint32_t L = xv_shfl_up1(w1), R = xv_shfl_down1(w0);
             const uint32_t o2 = xv_prmt(L, w0, 0x5432), o3 = xv_prmt(L, w0, 0x6543), o5 = xv_prmt(w0, w1, 0x4321);
             const uint32_t o6 = xv_prmt(w0, w1, 0x5432), o7 = xv_prmt(w0, w1, 0x6543), o9 = xv_prmt(w1, R, 0x4321);
@@ -266,22 +276,25 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
                 if (lflags & 16u) e[p].x = e[p].y = br;
             }
         }
-        if (store_lane) hpel_store4(dp, pb, out);
-        if (edge_lane) hpel_store4(dp + edge_delta, pb, e);
-        dp += job.stride;
-        if (fy == -8 || fy == job.h_p7) {                 // top / bottom border: 24 more copies of this row
-            const int rb = fy == -8 ? 0 : h + HPEL_PAD + 8;
+        if (live) {
+            if (store_lane) hpel_store4(dp, pb, out);
+            if (edge_lane) hpel_store4(dp + edge_delta, pb, e);
+            if (fy + u == -8 || fy + u == job.h_p7) {     // top / bottom border: 24 more copies of this row
+                const int rb = fy + u == -8 ? 0 : h + HPEL_PAD + 8;
 #pragma unroll 1
-            for (int r = rb; r < rb + 24; r++) {
-                const size_t rr = (size_t)r * job.stride;
-                if (store_lane) hpel_store4(D + (rr + own_off), pb, out);
-                if (edge_lane) hpel_store4(D + (rr + edge_off), pb, e);
+                for (int r = rb; r < rb + 24; r++) {
+                    const size_t rr = (size_t)r * job.stride;
+                    if (store_lane) hpel_store4(D + (rr + own_off), pb, out);
+                    if (edge_lane) hpel_store4(D + (rr + edge_off), pb, e);
+                }
             }
         }
+        dp += job.stride;
+      }
 #pragma unroll
         for (int k = 0; k < 5; k++) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) s[k][q] = s[k + 1][q];
+            for (int q = 0; q < 4; q++) s[k][q] = s[k + HPEL_UNROLL][q];
         }
     }
 }

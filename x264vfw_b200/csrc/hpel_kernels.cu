@@ -74,10 +74,11 @@ namespace xv {
 // one warp per block: tiles at the frame's edges do more work (border), a block of several warps would
 // hold its slot until the slowest one is done.  Register budget: asking for 25 blocks (cap 80) lets ptxas settle
 // on 72 registers without a spill -- 28 warps per SM all the same; asking for 28 (cap 72) spills the trip counter.
+template <bool ALIGNED>
 __global__ void __launch_bounds__(32, 25)
 hpel_kernel(HpelJob job)
 {
-    hpel_unit(job, blockIdx.x, blockIdx.y, threadIdx.x);
+    hpel_unit<ALIGNED>(job, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
 int launch_hpel(cudaStream_t st, HpelJob &job, int n_frames)
@@ -85,7 +86,8 @@ int launch_hpel(cudaStream_t st, HpelJob &job, int n_frames)
     if (job.w <= 0 || job.h <= 0 || n_frames <= 0) return 0;
     const long long units = hpel_plan(job, n_frames);
     dim3 grid((unsigned)units, (unsigned)n_frames);
-    hpel_kernel<<<grid, 32, 0, st>>>(job);
+    if (job.aligned) hpel_kernel<true><<<grid, 32, 0, st>>>(job);
+    else hpel_kernel<false><<<grid, 32, 0, st>>>(job);
     XV_LAUNCH_CHECK();
     return 0;
 }
