@@ -103,9 +103,10 @@ XV_DEVICE void hpel_fetch_row(xv_saddr slot, const uint8_t *rowc, int fx, int cf
 
 XV_DEVICE void hpel_store4(uint8_t *d, size_t pb, const HpelWord v[4])
 {
-    xv_st_u64(d, v[0].x, v[0].y); d += pb;
-    xv_st_u64(d, v[1].x, v[1].y); d += pb;
-    xv_st_u64(d, v[2].x, v[2].y); d += pb;
+    // a chain of three 64-bit adds (opaque: otherwise 2*pb and 3*pb are built with wide multiplies, 10 instructions)
+    xv_st_u64(d, v[0].x, v[0].y); d = xv_opaque(d + pb);
+    xv_st_u64(d, v[1].x, v[1].y); d = xv_opaque(d + pb);
+    xv_st_u64(d, v[2].x, v[2].y); d = xv_opaque(d + pb);
     xv_st_u64(d, v[3].x, v[3].y);
 }
 
