@@ -1,4 +1,5 @@
-"""GPU parity: the half-pel reference plane kernel through the C ABI vs the CPU checker,
+"""(SURVEY 8f rows run after the main path: this file sorts behind test_lowres_gpu / test_lookahead_gpu.)
+GPU parity: the half-pel reference plane kernel through the C ABI vs the CPU checker,
 bit-exact on all four padded planes including every border byte."""
 import numpy as np
 import pytest
