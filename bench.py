@@ -226,7 +226,10 @@ def stage1_roofline(torch, args):
         hp_line = {"frames_per_launch": hn, "ms_per_launch": t_hp * 1e3, "gbs": HPEL_ALGO_BYTES * hn / t_hp / 1e9}
     except Exception as e:          # reported in the line, never hidden: the headline numbers above are already measured
         hp_line = {"error": f"{type(e).__name__}: {e}"}
-    ctx.close()
+    try:
+        ctx.close()
+    except Exception:
+        pass
     return {"hpel_filter": hp_line,
             "csp_bgra_to_i420": {"frames_per_launch": nf, "ms_per_launch": t_csp * 1e3, "gbs": CSP_ALGO_BYTES * nf / t_csp / 1e9},
             "lowres_init": {"frames_per_launch": nf, "ms_per_launch": t_lr * 1e3, "gbs": LOWRES_ALGO_BYTES * nf / t_lr / 1e9}}
