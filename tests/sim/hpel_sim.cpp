@@ -15,8 +15,8 @@ extern "C" int sim_hpel(uint8_t *dst, const uint8_t *src, int src_stride, int w,
     for (int f = 0; f < n_frames; f++)
         for (long long u = 0; u < units; u++)
             xv::sim_run_warp([&](int lane) {
-                if (job.aligned) xv::hpel_unit<true>(job, (int)u, f, lane);
-                else xv::hpel_unit<false>(job, (int)u, f, lane);
+                if (job.aligned) xv::hpel_unit_any<true>(job, (int)u, f, lane);
+                else xv::hpel_unit_any<false>(job, (int)u, f, lane);
             });
     return (int)units;
 }

@@ -75,10 +75,12 @@ def sim():
 
 # (w, h, rows_per_strip, source stride, source offset): one tile; the word right of the frame exactly in the halo
 # lane 31 (240, 480); a second tile that holds one word (248); strips that end inside / beyond the frame; an
-# unaligned source (byte gathers); frames smaller than the filter's support
+# unaligned source (byte gathers); frames smaller than the filter's support; three tiles (the middle one runs the
+# interior-tile loop) with odd heights / strip lengths (the two-rows-per-trip loop computes one row too many)
 @pytest.mark.parametrize("case", [(16, 16, 12, 16, 0), (64, 48, 12, 64, 0), (112, 18, 6, 112, 0),
                                   (128, 32, 24, 128, 0), (240, 20, 12, 240, 0), (248, 12, 12, 248, 0),
-                                  (480, 8, 6, 480, 0), (64, 16, 12, 67, 1), (24, 6, 12, 24, 0), (8, 3, 12, 8, 0)])
+                                  (480, 8, 6, 480, 0), (64, 16, 12, 67, 1), (24, 6, 12, 24, 0), (8, 3, 12, 8, 0),
+                                  (600, 10, 12, 600, 0), (720, 9, 5, 720, 0), (520, 7, 24, 523, 3)])
 def test_warp_program_on_cpu_matches_checker(sim, case):
     w, h, rps, ss, off = case
     g = ol.hpel_geometry(w, h)

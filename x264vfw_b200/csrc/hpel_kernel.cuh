@@ -43,6 +43,8 @@ struct HpelJob {
     int ntiles, nstrips;                              // ceil(w/8 / 30), ceil((h+16) / rows_per_strip)
     int h_m1, h_p7;                                   // h - 1, h + 7: compared every trip, read straight from the parameter bank
     int aligned;                                      // every frame's plane and the stride are 8-byte aligned: picks the instantiation
+    // filter constants, read as parameter-bank operands (as literals each is rebuilt by a move in every row)
+    uint32_t k_h_lo, k_h_hi, k_c_m2, k_c_0, k_c_p2, k_clip;
     size_t src_frame_bytes, dst_frame_bytes;
 };
 
@@ -59,6 +61,9 @@ static inline long long hpel_plan(HpelJob &job, int n_frames)
         job.rows_per_strip = (long long)job.ntiles * ((job.h + 16 + 23) / 24) * n_frames >= 148 * 24 ? 24 : 12;
     job.nstrips = (job.h + 16 + job.rows_per_strip - 1) / job.rows_per_strip;
     job.h_m1 = job.h - 1; job.h_p7 = job.h + 7;
+    job.k_h_lo = 0x1414FB01u; job.k_h_hi = 0x000001FBu;       // H: bytes x-2..x+1 and x+2..x+5 times (1,-5,20,20) (-5,1,0,0)
+    job.k_c_m2 = 0xFB01u; job.k_c_0 = 0x1414u; job.k_c_p2 = 0x01FBu;   // centre: 16-bit pairs times (1,-5) (20,20) (-5,1)
+    job.k_clip = 0xFFB0FFB0u;                                 // packed -80: removes the bias of the vertical sums after >>5
     job.aligned = ((((uintptr_t)job.src) | (uintptr_t)(uint32_t)job.src_stride | (n_frames > 1 ? (uintptr_t)job.src_frame_bytes : 0)) & 7) == 0;
     return (long long)job.ntiles * job.nstrips;
 }
@@ -110,25 +115,26 @@ XV_DEVICE void hpel_store4(uint8_t *d, size_t pb, const HpelWord v[4])
     xv_st_u64(d, v[3].x, v[3].y);
 }
 
-XV_DEVICE uint32_t hpel_clip_v(uint32_t v)            // packed (V16 + 2576): ((V16+16)>>5) clipped to [0,255]
+XV_DEVICE uint32_t hpel_clip_v(uint32_t v, const HpelJob &k)   // packed (V16 + 2576): ((V16+16)>>5) clipped to [0,255]
 {
-    return xv_addmin_relu_s16x2((v >> 5) & 0x07FF07FFu, 0xFFB0FFB0u, 0x00FF00FFu);
+    return xv_addmin_relu_s16x2((v >> 5) & 0x07FF07FFu, k.k_clip, 0x00FF00FFu);
 }
 
-XV_DEVICE int hpel_tap_h(uint32_t win_m2, uint32_t win_p2)   // bytes x-2..x+1 and x+2..x+5 (the last two unused)
+XV_DEVICE int hpel_tap_h(uint32_t win_m2, uint32_t win_p2, const HpelJob &k)   // bytes x-2..x+1 and x+2..x+5 (the last two unused)
 {
-    return xv_dp4a_us(win_m2, 0x1414FB01u, xv_dp4a_us(win_p2, 0x000001FBu, 16)) >> 5;
+    return xv_dp4a_us(win_m2, k.k_h_lo, xv_dp4a_us(win_p2, k.k_h_hi, 16)) >> 5;
 }
 
-XV_DEVICE int hpel_tap_c(uint32_t qm2, uint32_t q0, uint32_t qp2)   // pairs (V[x-2],V[x-1]) (V[x],V[x+1]) (V[x+2],V[x+3])
+XV_DEVICE int hpel_tap_c(uint32_t qm2, uint32_t q0, uint32_t qp2, const HpelJob &k)   // pairs (V[x-2],V[x-1]) (V[x],V[x+1]) (V[x+2],V[x+3])
 {
-    return xv_dp2a_lo(qm2, 0xFB01u, xv_dp2a_lo(q0, 0x1414u, xv_dp2a_lo(qp2, 0x01FBu, 512 - 32 * 2576))) >> 10;
+    return xv_dp2a_lo(qm2, k.k_c_m2, xv_dp2a_lo(q0, k.k_c_0, xv_dp2a_lo(qp2, k.k_c_p2, 512 - 32 * 2576))) >> 10;
 }
 
 // one warp: tile `unit % ntiles` of strip `unit / ntiles` of frame `frame`.  ALIGNED (= job.aligned, decided by
-// hpel_plan) selects 64-bit loads / cp.async; otherwise bytes are gathered.
-template <bool ALIGNED>
-XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
+// hpel_plan) selects 64-bit loads / cp.async; otherwise bytes are gathered.  EDGE = the tile holds the frame's first
+// or last column (hpel_unit_any decides): interior tiles run a loop without any of the border work.
+template <bool ALIGNED, bool EDGE>
+XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane, HpelWord (*ring)[32])
 {
     const int tile = unit % job.ntiles, strip = unit / job.ntiles;
     const int w = job.w, h = job.h;
@@ -160,8 +166,8 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     uint8_t *D = xv_opaque(job.dst + (size_t)frame * job.dst_frame_bytes);
     const uint32_t own_off = (uint32_t)(fx + HPEL_PAD);
     const uint32_t edge_off = lane <= 3 ? 8u * (lane - 1) : (uint32_t)(w + HPEL_PAD + 8) + 8u * (lane - 4);
-    const bool left_tile = (flags & 2u) != 0, right_tile = (flags & 4u) != 0, edge_tile = (flags & 6u) != 0;
-    const bool store_lane = (lflags & 1u) != 0, edge_lane = (lflags & 2u) != 0;
+    const bool left_tile = EDGE && (flags & 2u) != 0, right_tile = EDGE && (flags & 4u) != 0, edge_tile = EDGE;
+    const bool store_lane = (lflags & 1u) != 0, edge_lane = EDGE && (lflags & 2u) != 0;
     const bool left_word = (lflags & 4u) != 0, right_word = (lflags & 8u) != 0;
     const size_t pb = job.plane_bytes;
 
@@ -188,7 +194,6 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
     // the copy has no destination register, so nothing in the loop waits on it until the row is due (a register
     // double buffer needs either an unrolled loop or a copy of a register that is still being filled, and that
     // copy waits for the load -- it held 25 % of the stall samples).
-    XV_SHARED HpelWord ring[HPEL_RING][32];
     const xv_saddr ring0 = xv_opaque_saddr(xv_saddr_of(&ring[0][lane]));   // slot k of this lane = ring0 + 256 k; opaque: otherwise
                                                                          // it is rematerialised (two S2R + five more) every trip
 #pragma unroll
@@ -234,8 +239,8 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
         }
         HpelWord out[4];
         // V plane
-        out[2].x = xv_prmt(hpel_clip_v(v[0]), hpel_clip_v(v[1]), 0x6420);
-        out[2].y = xv_prmt(hpel_clip_v(v[2]), hpel_clip_v(v[3]), 0x6420);
+        out[2].x = xv_prmt(hpel_clip_v(v[0], job), hpel_clip_v(v[1], job), 0x6420);
+        out[2].y = xv_prmt(hpel_clip_v(v[2], job), hpel_clip_v(v[3], job), 0x6420);
         {   // P0 and H plane: byte windows of the 16-byte span (L, w0, w1, R), span offset 4 = own pixel 0
             const uint32_t w0 = xv_prmt(s[u + 2][0], s[u + 2][1], 0x6420);
             const uint32_t w1 = xv_prmt(s[u + 2][2], s[u + 2][3], 0x6420);
@@ -244,18 +249,18 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
             const uint32_t o6 = xv_prmt(w0, w1, 0x5432), o7 = xv_prmt(w0, w1, 0x6543), o9 = xv_prmt(w1, R, 0x4321);
             const uint32_t o10 = xv_prmt(w1, R, 0x5432), o11 = xv_prmt(w1, R, 0x6543), o13 = R >> 8;
             out[0].x = w0; out[0].y = w1;
-            out[1].x = xv_pack_sat_u8(hpel_tap_h(o2, o6), hpel_tap_h(o3, o7), hpel_tap_h(w0, w1), hpel_tap_h(o5, o9));
-            out[1].y = xv_pack_sat_u8(hpel_tap_h(o6, o10), hpel_tap_h(o7, o11), hpel_tap_h(w1, R), hpel_tap_h(o9, o13));
+            out[1].x = xv_pack_sat_u8(hpel_tap_h(o2, o6, job), hpel_tap_h(o3, o7, job), hpel_tap_h(w0, w1, job), hpel_tap_h(o5, o9, job));
+            out[1].y = xv_pack_sat_u8(hpel_tap_h(o6, o10, job), hpel_tap_h(o7, o11, job), hpel_tap_h(w1, R, job), hpel_tap_h(o9, o13, job));
         }
         {   // C plane: horizontal 6-tap over the vertical sums (pairs q[k] = (V[k], V[k+1]), k = -2..9)
             const uint32_t Lv3 = xv_shfl_up1(v[3]), R0 = xv_shfl_down1(v[0]), R1 = xv_shfl_down1(v[1]);
             const uint32_t qm1 = xv_prmt(Lv3, v[0], 0x5432), q1 = xv_prmt(v[0], v[1], 0x5432);
             const uint32_t q3 = xv_prmt(v[1], v[2], 0x5432), q5 = xv_prmt(v[2], v[3], 0x5432);
             const uint32_t q7 = xv_prmt(v[3], R0, 0x5432), q9 = xv_prmt(R0, R1, 0x5432);
-            out[3].x = xv_pack_sat_u8(hpel_tap_c(Lv3, v[0], v[1]), hpel_tap_c(qm1, q1, q3),
-                                      hpel_tap_c(v[0], v[1], v[2]), hpel_tap_c(q1, q3, q5));
-            out[3].y = xv_pack_sat_u8(hpel_tap_c(v[1], v[2], v[3]), hpel_tap_c(q3, q5, q7),
-                                      hpel_tap_c(v[2], v[3], R0), hpel_tap_c(q5, q7, q9));
+            out[3].x = xv_pack_sat_u8(hpel_tap_c(Lv3, v[0], v[1], job), hpel_tap_c(qm1, q1, q3, job),
+                                      hpel_tap_c(v[0], v[1], v[2], job), hpel_tap_c(q1, q3, q5, job));
+            out[3].y = xv_pack_sat_u8(hpel_tap_c(v[1], v[2], v[3], job), hpel_tap_c(q3, q5, q7, job),
+                                      hpel_tap_c(v[2], v[3], R0, job), hpel_tap_c(q5, q7, q9, job));
         }
         // ---- the words just outside the frame: 4 filtered pixels next to the frame, the other 4 already
         //      border (= the outermost filtered pixel); the rest of the border goes to the edge lanes -----
@@ -298,6 +303,15 @@ XV_DEVICE void hpel_unit(const HpelJob &job, int unit, int frame, int lane)
             for (int q = 0; q < 4; q++) s[k][q] = s[k + HPEL_UNROLL][q];
         }
     }
+}
+template <bool ALIGNED>
+XV_DEVICE void hpel_unit_any(const HpelJob &job, int unit, int frame, int lane)
+{
+    XV_SHARED HpelWord ring[HPEL_RING][32];               // the prefetch ring of this warp (one warp per block)
+    const int tile = unit % job.ntiles;
+    const int right_lane = (job.w >> 3) - tile * HPEL_TILE + 1;
+    if (tile == 0 || (right_lane >= 1 && right_lane <= 31)) hpel_unit<ALIGNED, true>(job, unit, frame, lane, ring);
+    else hpel_unit<ALIGNED, false>(job, unit, frame, lane, ring);
 }
 #endif // XV_HPEL_HOST_ONLY
 

@@ -78,7 +78,7 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__(32, 25)
 hpel_kernel(HpelJob job)
 {
-    hpel_unit<ALIGNED>(job, blockIdx.x, blockIdx.y, threadIdx.x);
+    hpel_unit_any<ALIGNED>(job, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
 int launch_hpel(cudaStream_t st, HpelJob &job, int n_frames)
