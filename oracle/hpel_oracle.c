@@ -1,7 +1,12 @@
 /*
  * hpel_oracle.c -- scalar restatement of libx264's half-pel reference planes.
- * TEST INFRASTRUCTURE (see oracle.h).  PARITY UNPINNED: upstream libx264 is not in the
- * reference tree; this follows upstream's published C algorithm by function name:
+ * TEST INFRASTRUCTURE (see oracle.h).  Upstream libx264 is not in the reference tree, so this is NOT pinned
+ * against libx264; it IS pinned against the H.264 standard's fractional sample interpolation as libavcodec's
+ * decoder evaluates it (tests/test_h264_pins.py, fixtures tests/golden/h264_pins.json: all quarter-sample
+ * phases, vectors up to 22 samples outside the picture, random and 0/255 content) -- an encoder's reference
+ * planes have to give the decoder's prediction.  What that leaves unpinned: the layout (stride, 32-sample
+ * border) and the planes' bytes further than 22 samples outside the frame.
+ * It follows upstream's published C algorithm by function name:
  *   [x264] common/frame.c  x264_frame_expand_border (plane_expand_border), x264_frame_expand_border_filtered
  *   [x264] common/mc.c     hpel_filter (C version, 8-bit: pad = 0), x264_frame_filter (progressive)
  * It goes through upstream's literal sequence (materialised 32-pixel border, filter over the frame plus

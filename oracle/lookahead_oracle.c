@@ -5,6 +5,9 @@
  *
  * TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see lookahead_oracle.h): written from the
  * published upstream algorithm; function-by-function citations are "[x264] file: function".
+ * Two pieces are pinned all the same, against libavcodec's H.264 decoder, because the standard fixes them
+ * (tests/test_h264_pins.py): get_ref_8x8 (which planes a quarter-sample position averages) and the ten intra
+ * predictors (pred_8x8c_*, filter_edges, pred_8x8_mode).  Search order, costs, decisions and mb-tree are not.
  * The 8-bit, progressive, non-VBV, single-pass paths are restated (the only ones the
  * reference's presets reach through codec.c:1693 for the BASELINE configs).
  */
@@ -1577,3 +1580,28 @@ void orc_la_mbtree(orc_la *la, const int *frame_idx, const int *types, int num_f
     macroblock_tree(la, frames, num_frames, b_intra);
 }
 void orc_la_counters(orc_la *la, uint64_t out[4]) { out[0] = la->n_mbcost; out[1] = la->n_search; out[2] = la->n_sad; out[3] = la->n_satd; }
+
+/* ---- test hooks (see lookahead_oracle.h) ---- */
+void orc_test_get_ref_8x8(uint8_t dst[64], const uint8_t *p0, const uint8_t *p1, const uint8_t *p2, const uint8_t *p3,
+                          int stride, int mvx, int mvy)
+{
+    uint8_t *const planes[4] = {(uint8_t *)p0, (uint8_t *)p1, (uint8_t *)p2, (uint8_t *)p3};
+    get_ref_8x8(dst, planes, stride, mvx, mvy, NULL);
+}
+
+void orc_test_intra_pred_8x8(uint8_t dst[64], int kind, const uint8_t *src, int stride)
+{
+    nbr_t n;
+    n.tl = src[-stride - 1];
+    for (int i = 0; i < 16; i++) n.top[i] = src[-stride + i];
+    for (int i = 0; i < 8; i++) n.left[i] = src[i * stride - 1];
+    if (kind == 0) pred_8x8c_dc(dst, &n);
+    else if (kind == 1) pred_8x8c_h(dst, &n);
+    else if (kind == 2) pred_8x8c_v(dst, &n);
+    else if (kind == 3) pred_8x8c_p(dst, &n);
+    else {
+        edge_t e;
+        filter_edges(&e, &n);
+        pred_8x8_mode(dst, &e, kind - 10);
+    }
+}

@@ -108,6 +108,17 @@ void orc_la_mbtree(orc_la *la, const int *frame_idx, const int *types, int num_f
 /* counters: number of MB motion searches / SAD / SATD evaluations performed so far */
 void orc_la_counters(orc_la *la, uint64_t out[4]);
 
+/* Test hooks on two restated [x264] pieces that a standard H.264 DECODER must reproduce, so that they can be
+ * pinned against one (tests/golden/make_h264_pins.py, tests/test_h264_pins.py):
+ *  - get_ref ([x264] common/mc.c): the 8x8 block at quarter-sample vector (mvx, mvy) from four half-pel planes
+ *    (full, H, V, centre), each pointer already at the block's integer position;
+ *  - the intra predictors of the lookahead ([x264] common/predict.c): kind 0..3 = predict_8x8c_{dc,h,v,p},
+ *    kind 13..18 = predict_8x8_{ddl,ddr,vr,hd,vl,hu} after predict_8x8_filter; src = the block's top-left sample
+ *    inside a plane that holds its neighbours (row above incl. 8 samples to the right, column to the left). */
+void orc_test_get_ref_8x8(uint8_t dst[64], const uint8_t *p0, const uint8_t *p1, const uint8_t *p2, const uint8_t *p3,
+                          int stride, int mvx, int mvy);
+void orc_test_intra_pred_8x8(uint8_t dst[64], int kind, const uint8_t *src, int stride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,140 @@
+"""Shared by tests/golden/make_h264_pins.py (generator) and tests/test_h264_pins.py: the pictures, motion vectors
+and intra test layout of the H.264-decoder pins, and the checker-side evaluation of the same predictions.
+
+What is pinned: three restated [x264] pieces whose results the H.264 standard fixes, because an encoder's
+prediction must be the decoder's -- (1) the half-pel planes (oracle/hpel_oracle.c: border expansion, 6-tap H / V /
+centre), (2) get_ref's choice and averaging of two planes per quarter-sample position (oracle/lookahead_oracle.c),
+(3) the ten intra predictors the lookahead scores (predict_8x8c_{dc,h,v,p}, predict_8x8_filter +
+predict_8x8_{ddl,ddr,vr,hd,vl,hu}).  The reference is libavcodec's H.264 decoder (the FFmpeg build inside this
+image's opencv wheel), driven by bitstreams from tests/golden/h264_mini.py; its outputs are frozen as FNV-1a-64
+hashes in tests/golden/h264_pins.json.  libx264 itself stays absent: everything else in the lookahead checker
+(search order, costs, decisions, mb-tree) remains unpinned."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import oracle_lib as ol  # noqa: E402
+
+MC_W, MC_H = 64, 48
+# every quarter-sample phase at the origin, then vectors that reach up to 22 samples outside the picture (the
+# decoder clamps coordinates; the planes carry a 32-sample replicated border)
+MC_MVS = [(fx, fy) for fy in range(4) for fx in range(4)] + [(-37, 22), (50, -61), (3, -90), (-85, 1), (-6, -7), (83, 86)]
+MC_KINDS = ("noise", "extreme")
+INTRA_MBW, INTRA_MBH = 4, 24
+
+
+def _lcg(n, w, h):
+    buf = np.zeros(n, dtype=np.uint8)
+    ol.oracle().orc_lcg_fill(buf.ctypes.data, buf.size, w, h)        # SURVEY A.4 generator, seeded by (w, h)
+    return buf
+
+
+def mc_picture(kind):
+    w, h = MC_W, MC_H
+    b = _lcg(w * h * 3 // 2, w + (7 if kind == "extreme" else 0), h)
+    if kind == "extreme":                                   # 0 / 255 only: every tap sum reaches its limits
+        b = np.where(b > 127, 255, 0).astype(np.uint8)
+    return b[:w * h].reshape(h, w), b[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), b[w * h * 5 // 4:].reshape(h // 2, w // 2)
+
+
+def intra_picture():
+    w, h = 16 * INTRA_MBW, 16 * INTRA_MBH
+    b = _lcg(w * h * 3 // 2, w, h)
+    return b[:w * h].reshape(h, w), b[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), b[w * h * 5 // 4:].reshape(h // 2, w // 2)
+
+
+def intra_tests():
+    """{(mbx, mby): (Intra_8x8 luma mode 3..8, chroma mode 0..3)}: odd rows, odd columns; every neighbour I_PCM."""
+    t, k = {}, 0
+    for mby in range(1, INTRA_MBH, 2):
+        for mbx in (1, 3):
+            t[(mbx, mby)] = (3 + k % 6, (k // 2) % 4)
+            k += 1
+    return t
+
+
+def mc_stream(kind):
+    import h264_mini as hm
+    y, u, v = mc_picture(kind)
+    aus = [hm.sps(MC_W // 16, MC_H // 16) + hm.pps() + hm.idr_pcm_picture(y, u, v)]
+    for k, (mx, my) in enumerate(MC_MVS):
+        aus.append(hm.p_picture_uniform_mv(MC_W // 16, MC_H // 16, mx, my, 1, 2 * (k + 1)))
+    return aus
+
+
+def intra_stream():
+    import h264_mini as hm
+    y, u, v = intra_picture()
+    return [hm.sps(INTRA_MBW, INTRA_MBH) + hm.pps() + hm.idr_pcm_picture(y, u, v, intra_tests())]
+
+
+def fnv(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return f"{ol.oracle().orc_fnv1a64(a.ctypes.data, a.size):016x}"
+
+
+def predict_from_planes(planes, w, h, stride, mvx, mvy):
+    """The whole picture predicted with one quarter-sample vector: get_ref (checker's own code) per 8x8 block on
+    four padded half-pel planes of shape (4, h + 64, stride) -- the checker's or the device's."""
+    o = ol.oracle()
+    planes = np.ascontiguousarray(planes)
+    out = np.zeros((h, w), dtype=np.uint8)
+    blk = np.zeros(64, dtype=np.uint8)
+    base, pb = planes.ctypes.data, planes.shape[1] * stride
+    for by in range(0, h, 8):
+        for bx in range(0, w, 8):
+            off = (by + 32) * stride + bx + 32
+            o.orc_test_get_ref_8x8(blk.ctypes.data, *[C.c_void_p(base + p * pb + off) for p in range(4)], stride, mvx, mvy)
+            out[by:by + 8, bx:bx + 8] = blk.reshape(8, 8)
+    return out
+
+
+def checker_mc_hashes(kind, planes=None):
+    y, _, _ = mc_picture(kind)
+    g = ol.hpel_geometry(MC_W, MC_H)
+    if planes is None:
+        planes = ol.oracle_hpel_planes(y, MC_W, MC_H)
+    return [fnv(predict_from_planes(planes, MC_W, MC_H, g["stride"], mx, my)) for mx, my in MC_MVS]
+
+
+def checker_intra_hashes():
+    """Per test macroblock: hashes of the predicted top-left luma 8x8 and of the two chroma 8x8 blocks, from the
+    SOURCE picture's neighbours (I_PCM neighbours decode to the source)."""
+    o = ol.oracle()
+    y, u, v = [np.ascontiguousarray(p) for p in intra_picture()]
+    w = y.shape[1]
+    blk = np.zeros(64, dtype=np.uint8)
+    out = []
+    for (mbx, mby), (m, c) in sorted(intra_tests().items()):
+        o.orc_test_intra_pred_8x8(blk.ctypes.data, 10 + m, C.c_void_p(y.ctypes.data + 16 * mby * w + 16 * mbx), w)
+        hy = fnv(blk)
+        hc = []
+        for pl in (u, v):
+            o.orc_test_intra_pred_8x8(blk.ctypes.data, c, C.c_void_p(pl.ctypes.data + 8 * mby * (w // 2) + 8 * mbx), w // 2)
+            hc.append(fnv(blk))
+        out.append({"mb": [mbx, mby], "luma_mode": m, "chroma_mode": c, "luma": hy, "u": hc[0], "v": hc[1]})
+    return out
+
+
+def decoder_mc_hashes(kind):
+    import avdec
+    pics = avdec.decode_h264(mc_stream(kind))
+    y, _, _ = mc_picture(kind)
+    assert len(pics) == 1 + len(MC_MVS) and np.array_equal(pics[0][0], y)
+    return [fnv(p[0]) for p in pics[1:]]
+
+
+def decoder_intra_hashes():
+    import avdec
+    (Y, U, V), = avdec.decode_h264(intra_stream())
+    out = []
+    for (mbx, mby), (m, c) in sorted(intra_tests().items()):
+        out.append({"mb": [mbx, mby], "luma_mode": m, "chroma_mode": c,
+                    "luma": fnv(Y[16 * mby:16 * mby + 8, 16 * mbx:16 * mbx + 8]),
+                    "u": fnv(U[8 * mby:8 * mby + 8, 8 * mbx:8 * mbx + 8]), "v": fnv(V[8 * mby:8 * mby + 8, 8 * mbx:8 * mbx + 8])})
+    return out

@@ -131,3 +131,19 @@ def test_warp_program_on_cpu_random_geometry(sim):
         want = ol.oracle_hpel_planes(y, w, h)
         assert np.array_equal(got[:, :, :w + 64], want[:, :, :w + 64]), (w, h, rps, off, ss)
         assert np.all(got[:, :, w + 64:] == 0x5A)
+
+
+@pytest.mark.parametrize("kind", ["noise", "extreme"])
+def test_warp_program_on_cpu_reproduces_the_h264_decoders_motion_compensation(sim, kind):
+    """The kernel's source, run in lockstep on the CPU, against libavcodec's H.264 decoder (tests/golden/h264_pins.json):
+    its four planes read at every quarter-sample phase give the decoder's motion-compensated pictures."""
+    import json
+    import h264_pins as hp
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "h264_pins.json")))
+    w, h = hp.MC_W, hp.MC_H
+    y, _, _ = hp.mc_picture(kind)
+    y = np.ascontiguousarray(y)
+    g = ol.hpel_geometry(w, h)
+    dst = np.zeros(4 * g["plane_bytes"], dtype=np.uint8)
+    sim.sim_hpel(dst.ctypes.data, y.ctypes.data, w, w, h, g["stride"], g["plane_bytes"], 12, w * h, 4 * g["plane_bytes"], 1)
+    assert hp.checker_mc_hashes(kind, planes=dst.reshape(4, h + 64, g["stride"])) == gold["mc"]["pictures"][kind]

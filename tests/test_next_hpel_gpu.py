@@ -116,6 +116,29 @@ def test_device_path_matches_the_committed_fingerprints(ctx):
         assert mg.fingerprint(got, w) == case["planes_fnv"], (w, h)
 
 
+@pytest.mark.parametrize("kind", ["noise", "extreme"])
+def test_device_planes_reproduce_the_h264_decoders_motion_compensation(ctx, kind):
+    """The device's four half-pel planes, read at every quarter-sample phase (get_ref), against the pictures
+    libavcodec's H.264 decoder produced from the same source (tests/golden/h264_pins.json): a reference that is
+    not the checker."""
+    import json
+    import os
+    import torch
+    import h264_pins as hp
+    from x264vfw_b200 import hpel
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h264_pins.json")))
+    w, h = hp.MC_W, hp.MC_H
+    y, _, _ = hp.mc_picture(kind)
+    g = hpel.geometry(w, h)
+    d_src = torch.from_numpy(np.ascontiguousarray(y).reshape(-1)).cuda()
+    d_out = torch.zeros(4 * g.plane_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    hpel.hpel_filter(ctx, d_out.data_ptr(), d_src.data_ptr(), w, w, h)
+    ctx.sync()
+    planes = d_out.cpu().numpy().reshape(4, h + 64, g.stride)
+    assert hp.checker_mc_hashes(kind, planes=planes) == gold["mc"]["pictures"][kind]
+
+
 def test_hpel_filter_rejects_bad_geometry(ctx):
     from x264vfw_b200 import hpel
     from x264vfw_b200._lib import CudaError
