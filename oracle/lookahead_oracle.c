@@ -5,8 +5,9 @@
  *
  * TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see lookahead_oracle.h): written from the
  * published upstream algorithm; function-by-function citations are "[x264] file: function".
- * Two pieces are pinned all the same, against libavcodec's H.264 decoder, because the standard fixes them
- * (tests/test_h264_pins.py): get_ref_8x8 (which planes a quarter-sample position averages) and the ten intra
+ * Four pieces are pinned all the same, against libavcodec's H.264 decoder, because the standard fixes them
+ * (tests/test_h264_pins.py): get_ref_8x8 (which planes a quarter-sample position averages), weight_px (explicit
+ * weighted prediction), pixel_avg_8x8 with la_bipred_weight (implicit bidirectional weights) and the ten intra
  * predictors (pred_8x8c_*, filter_edges, pred_8x8_mode).  Search order, costs, decisions and mb-tree are not.
  * The 8-bit, progressive, non-VBV, single-pass paths are restated (the only ones the
  * reference's presets reach through codec.c:1693 for the BASELINE configs).
@@ -216,6 +217,11 @@ static void get_ref_8x8(uint8_t *dst, uint8_t *const planes[4], int stride, int 
     if (w && w->on)
         for (int i = 0; i < 64; i++) dst[i] = weight_px(w, dst[i]);
 }
+
+/* [x264] encoder/slicetype.c: the lookahead's own distance scale (slicetype_frame_cost, macroblock_tree_propagate)
+ * and the weight of the list-0 block in a bidirectional average (weightb: implicit weights of H.264 8.4.2.3.1) */
+static inline int la_dist_scale_factor(int p0, int p1, int b) { return (((b - p0) << 8) + ((p1 - p0) >> 1)) / (p1 - p0); }
+static inline int la_bipred_weight(int weightb, int dist_scale_factor) { return weightb ? 64 - (dist_scale_factor >> 2) : 32; }
 
 static void pixel_avg_8x8(uint8_t *dst, const uint8_t *a, int sa, const uint8_t *b, int sb, int weight)
 {
@@ -593,7 +599,7 @@ static void mb_cost(orc_la *la, slice_ctx *s, int mb_x, int mb_y)
     const int mb_stride = la->mb_w, mb_xy = mb_x + mb_y * mb_stride;
     const int stride = la->lstride;
     const int pel = 8 * (mb_x + mb_y * stride);
-    const int bipred_weight = la->p.weightb ? 64 - (s->dist_scale_factor >> 2) : 32;
+    const int bipred_weight = la_bipred_weight(la->p.weightb, s->dist_scale_factor);
     int16_t (*fenc_mvs[2])[2] = {b != p0 ? &fenc->mvs[0][b - p0 - 1][mb_xy] : NULL, b != p1 ? &fenc->mvs[1][p1 - b - 1][mb_xy] : NULL};
     int *fenc_costs[2] = {b != p0 ? &fenc->mv_costs[0][b - p0 - 1][mb_xy] : NULL, b != p1 ? &fenc->mv_costs[1][p1 - b - 1][mb_xy] : NULL};
     const int b_frame_score_mb = (mb_x > 0 && mb_x < la->mb_w - 1 && mb_y > 0 && mb_y < la->mb_h - 1) || la->mb_w <= 2 || la->mb_h <= 2;
@@ -835,7 +841,7 @@ static int frame_cost(orc_la *la, frame_t **frames, int p0, int p1, int b)
         fenc->mvs_searched[0][b - p0 - 1] = 1;
     }
     if (s.do_search[1]) fenc->mvs_searched[1][p1 - b - 1] = 1;
-    if (p1 != p0) s.dist_scale_factor = (((b - p0) << 8) + ((p1 - p0) >> 1)) / (p1 - p0);
+    if (p1 != p0) s.dist_scale_factor = la_dist_scale_factor(p0, p1, b);
 
     int *row_inter = calloc(la->mb_h, sizeof(int)), *row_intra = calloc(la->mb_h, sizeof(int));
     s.row_inter = row_inter; s.row_intra = row_intra;
@@ -1017,8 +1023,8 @@ static void mbtree_finish(orc_la *la, frame_t *frame, float average_duration, in
 static void mbtree_propagate(orc_la *la, frame_t **frames, float average_duration, int p0, int p1, int b, int referenced)
 {
     uint16_t *ref_costs[2] = {frames[p0]->propagate_cost, frames[p1]->propagate_cost};
-    int dist_scale_factor = (((b - p0) << 8) + ((p1 - p0) >> 1)) / (p1 - p0);
-    int bipred_weight = la->p.weightb ? 64 - (dist_scale_factor >> 2) : 32;
+    int dist_scale_factor = la_dist_scale_factor(p0, p1, b);
+    int bipred_weight = la_bipred_weight(la->p.weightb, dist_scale_factor);
     int16_t (*mvs[2])[2] = {b != p0 ? frames[b]->mvs[0][b - p0 - 1] : NULL, b != p1 ? frames[b]->mvs[1][p1 - b - 1] : NULL};
     int bipred_weights[2] = {bipred_weight, 64 - bipred_weight};
     int16_t *buf = la->scratch_amount;
@@ -1604,4 +1610,22 @@ void orc_test_intra_pred_8x8(uint8_t dst[64], int kind, const uint8_t *src, int 
         filter_edges(&e, &n);
         pred_8x8_mode(dst, &e, kind - 10);
     }
+}
+
+void orc_test_get_ref_8x8_weighted(uint8_t dst[64], const uint8_t *p0, const uint8_t *p1, const uint8_t *p2, const uint8_t *p3,
+                                   int stride, int mvx, int mvy, int scale, int denom, int offset)
+{
+    uint8_t *const planes[4] = {(uint8_t *)p0, (uint8_t *)p1, (uint8_t *)p2, (uint8_t *)p3};
+    const weight_t w = {1, scale, denom, offset};
+    get_ref_8x8(dst, planes, stride, mvx, mvy, &w);
+}
+
+int orc_test_bipred_weight(int p0, int p1, int b, int weightb)
+{
+    return la_bipred_weight(weightb, la_dist_scale_factor(p0, p1, b));
+}
+
+void orc_test_pixel_avg_8x8(uint8_t dst[64], const uint8_t a[64], const uint8_t b[64], int weight)
+{
+    pixel_avg_8x8(dst, a, 8, b, 8, weight);
 }

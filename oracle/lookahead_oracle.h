@@ -118,6 +118,14 @@ void orc_la_counters(orc_la *la, uint64_t out[4]);
 void orc_test_get_ref_8x8(uint8_t dst[64], const uint8_t *p0, const uint8_t *p1, const uint8_t *p2, const uint8_t *p3,
                           int stride, int mvx, int mvy);
 void orc_test_intra_pred_8x8(uint8_t dst[64], int kind, const uint8_t *src, int stride);
+/* get_ref followed by the explicit weight (mc_weight: ((p * scale + 2^(denom-1)) >> denom) + offset, clipped),
+ * the decoder's explicit weighted sample prediction (H.264 8.4.2.3) */
+void orc_test_get_ref_8x8_weighted(uint8_t dst[64], const uint8_t *p0, const uint8_t *p1, const uint8_t *p2, const uint8_t *p3,
+                                   int stride, int mvx, int mvy, int scale, int denom, int offset);
+/* the bidirectional average of the lookahead: weight of the list-0 block for frames (p0, b, p1) in display order
+ * (weightb = implicit weights, H.264 8.4.2.3.1/2) and pixel_avg with that weight */
+int orc_test_bipred_weight(int p0, int p1, int b, int weightb);
+void orc_test_pixel_avg_8x8(uint8_t dst[64], const uint8_t a[64], const uint8_t b[64], int weight);
 
 #ifdef __cplusplus
 }

@@ -71,7 +71,7 @@ def nal(ref_idc, unit_type, rbsp: bytes) -> bytes:
     return bytes(out)
 
 
-def sps(mb_w, mb_h) -> bytes:
+def sps(mb_w, mb_h, num_ref_frames=1, reorder=0) -> bytes:
     b = Bits()
     b.u(8, 100)                  # profile_idc: High (transform 8x8 for the Intra_8x8 pictures)
     b.u(8, 0)                    # constraint flags + reserved
@@ -84,25 +84,36 @@ def sps(mb_w, mb_h) -> bytes:
     b.ue(0)                      # log2_max_frame_num_minus4 -> 4 bits
     b.ue(0)                      # pic_order_cnt_type 0
     b.ue(4)                      # log2_max_pic_order_cnt_lsb_minus4 -> 8 bits
-    b.ue(1)                      # max_num_ref_frames
+    b.ue(num_ref_frames)         # max_num_ref_frames
     b.u(1, 0)                    # gaps_in_frame_num_value_allowed_flag
     b.ue(mb_w - 1); b.ue(mb_h - 1)
     b.u(1, 1)                    # frame_mbs_only_flag
     b.u(1, 1)                    # direct_8x8_inference_flag
     b.u(1, 0)                    # frame_cropping_flag
-    b.u(1, 0)                    # vui_parameters_present_flag
+    if not reorder:
+        b.u(1, 0)                # vui_parameters_present_flag
+    else:                        # VUI with nothing but the bitstream restriction: tells the decoder its reorder depth
+        b.u(1, 1)
+        for _ in range(9):       # aspect_ratio, overscan, video_signal_type, chroma_loc, timing, nal_hrd, vcl_hrd,
+            b.u(1, 0)            # pic_struct: all absent ... and bitstream_restriction_flag next
+        b.bits[-1] = 1           # bitstream_restriction_flag
+        b.u(1, 1)                # motion_vectors_over_pic_boundaries_flag
+        b.ue(0); b.ue(0)         # max_bytes_per_pic_denom, max_bits_per_mb_denom
+        b.ue(16); b.ue(16)       # log2_max_mv_length_horizontal / vertical
+        b.ue(reorder)            # max_num_reorder_frames
+        b.ue(num_ref_frames)     # max_dec_frame_buffering
     b.trailing()
     return nal(3, 7, b.bytes())
 
 
-def pps() -> bytes:
+def pps(pps_id=0, weighted_pred=0, weighted_bipred_idc=0) -> bytes:
     b = Bits()
-    b.ue(0); b.ue(0)             # pic_parameter_set_id, seq_parameter_set_id
+    b.ue(pps_id); b.ue(0)        # pic_parameter_set_id, seq_parameter_set_id
     b.u(1, 0)                    # entropy_coding_mode_flag: CAVLC
     b.u(1, 0)                    # bottom_field_pic_order_in_frame_present_flag
     b.ue(0)                      # num_slice_groups_minus1
     b.ue(0); b.ue(0)             # num_ref_idx_l0/l1_default_active_minus1
-    b.u(1, 0); b.u(2, 0)         # weighted_pred_flag, weighted_bipred_idc
+    b.u(1, weighted_pred); b.u(2, weighted_bipred_idc)     # weighted_pred_flag, weighted_bipred_idc (2 = implicit)
     b.se(0); b.se(0); b.se(0)    # pic_init_qp_minus26, pic_init_qs_minus26, chroma_qp_index_offset
     b.u(1, 1)                    # deblocking_filter_control_present_flag (slices switch the filter off)
     b.u(1, 0)                    # constrained_intra_pred_flag
@@ -114,17 +125,27 @@ def pps() -> bytes:
     return nal(3, 8, b.bytes())
 
 
-def _slice_header(b: Bits, idr: bool, slice_type: int, frame_num: int, poc_lsb: int, ref: bool):
+def _slice_header(b: Bits, idr: bool, slice_type: int, frame_num: int, poc_lsb: int, ref: bool, pps_id=0, weight=None):
     b.ue(0)                      # first_mb_in_slice
-    b.ue(slice_type)             # 0 = P, 2 = I
-    b.ue(0)                      # pic_parameter_set_id
+    b.ue(slice_type)             # 0 = P, 1 = B, 2 = I
+    b.ue(pps_id)                 # pic_parameter_set_id
     b.u(4, frame_num)
     if idr:
         b.ue(0)                  # idr_pic_id
     b.u(8, poc_lsb)
+    if slice_type == 1:
+        b.u(1, 1)                # direct_spatial_mv_pred_flag
+        b.u(1, 0)                # num_ref_idx_active_override_flag
+        b.u(1, 0); b.u(1, 0)     # ref_pic_list_modification_flag_l0 / _l1
     if slice_type == 0:
         b.u(1, 0)                # num_ref_idx_active_override_flag
         b.u(1, 0)                # ref_pic_list_modification_flag_l0
+        if weight is not None:   # pred_weight_table (7.3.3.2), the PPS has weighted_pred_flag
+            denom, scale, offset = weight
+            b.ue(denom)          # luma_log2_weight_denom
+            b.ue(0)              # chroma_log2_weight_denom
+            b.u(1, 1); b.se(scale); b.se(offset)     # luma_weight_l0_flag, luma_weight_l0, luma_offset_l0
+            b.u(1, 0)            # chroma_weight_l0_flag
     if ref:
         if idr:
             b.u(1, 0); b.u(1, 0)     # no_output_of_prior_pics_flag, long_term_reference_flag
@@ -174,17 +195,48 @@ def idr_pcm_picture(y, u, v, intra_tests=None) -> bytes:
     return nal(3, 5, b.bytes())
 
 
-def p_picture_uniform_mv(mb_w, mb_h, mvx, mvy, frame_num, poc_lsb) -> bytes:
+def p_picture_uniform_mv(mb_w, mb_h, mvx, mvy, frame_num, poc_lsb, weight=None) -> bytes:
     """A non-reference P picture: every macroblock P_L0_16x16 with the quarter-sample vector (mvx, mvy), no
-    residual.  With one vector everywhere the median predictor (8.4.1.3) equals it for every macroblock but the
+    residual.  weight = (log2 denominator, scale, offset): explicit weighted prediction of luma (needs pps(1, 1),
+    selected here by pps id 1).  With one vector everywhere the median predictor (8.4.1.3) equals it for every macroblock but the
     first, whose neighbours are all unavailable (predictor 0)."""
     b = Bits()
-    _slice_header(b, False, 0, frame_num, poc_lsb, False)
+    _slice_header(b, False, 0, frame_num, poc_lsb, False, pps_id=1 if weight is not None else 0, weight=weight)
     for i in range(mb_w * mb_h):
         b.ue(0)                  # mb_skip_run
         b.ue(0)                  # mb_type P_L0_16x16
         b.se(mvx if i == 0 else 0)
         b.se(mvy if i == 0 else 0)
         b.ue(0)                  # coded_block_pattern me(v): codeNum 0 = Inter cbp 0
+    b.trailing()
+    return nal(0, 1, b.bytes())
+
+
+def p_pcm_reference_picture(y, u, v, frame_num, poc_lsb) -> bytes:
+    """A P picture made of I_PCM macroblocks, kept as a reference: a second reference with pixels we choose."""
+    mb_h, mb_w = y.shape[0] // 16, y.shape[1] // 16
+    b = Bits()
+    _slice_header(b, False, 0, frame_num, poc_lsb, True)
+    for mby in range(mb_h):
+        for mbx in range(mb_w):
+            b.ue(0)              # mb_skip_run
+            _pcm_mb(b, 30, y, u, v, mbx, mby)
+    b.trailing()
+    return nal(2, 1, b.bytes())
+
+
+def b_picture_uniform_mvs(mb_w, mb_h, mv0, mv1, frame_num, poc_lsb, pps_id) -> bytes:
+    """A non-reference B picture: every macroblock B_Bi_16x16 (list 0 = the nearest earlier reference, list 1 = the
+    nearest later one) with one vector per list, no residual: the decoded picture is the (pps: default or implicitly
+    weighted) average of the two interpolated predictions."""
+    b = Bits()
+    _slice_header(b, False, 1, frame_num, poc_lsb, False, pps_id=pps_id)
+    for i in range(mb_w * mb_h):
+        b.ue(0)                  # mb_skip_run
+        b.ue(3)                  # mb_type B_Bi_16x16
+        for mv in (mv0, mv1):    # mvd_l0 then mvd_l1; per list the median predictor is the uniform vector
+            b.se(mv[0] if i == 0 else 0)
+            b.se(mv[1] if i == 0 else 0)
+        b.ue(0)                  # coded_block_pattern: Inter 0
     b.trailing()
     return nal(0, 1, b.bytes())

@@ -1,11 +1,13 @@
 """Shared by tests/golden/make_h264_pins.py (generator) and tests/test_h264_pins.py: the pictures, motion vectors
 and intra test layout of the H.264-decoder pins, and the checker-side evaluation of the same predictions.
 
-What is pinned: three restated [x264] pieces whose results the H.264 standard fixes, because an encoder's
+What is pinned: five restated [x264] pieces whose results the H.264 standard fixes, because an encoder's
 prediction must be the decoder's -- (1) the half-pel planes (oracle/hpel_oracle.c: border expansion, 6-tap H / V /
 centre), (2) get_ref's choice and averaging of two planes per quarter-sample position (oracle/lookahead_oracle.c),
 (3) the ten intra predictors the lookahead scores (predict_8x8c_{dc,h,v,p}, predict_8x8_filter +
-predict_8x8_{ddl,ddr,vr,hd,vl,hu}).  The reference is libavcodec's H.264 decoder (the FFmpeg build inside this
+predict_8x8_{ddl,ddr,vr,hd,vl,hu}), (4) mc_weight, the explicit weighted prediction of a weighted reference,
+(5) the bidirectional average: pixel_avg and the lookahead's bipred weight for every (p0, b, p1) up to 16 B-frames
+(implicit weights).  The reference is libavcodec's H.264 decoder (the FFmpeg build inside this
 image's opencv wheel), driven by bitstreams from tests/golden/h264_mini.py; its outputs are frozen as FNV-1a-64
 hashes in tests/golden/h264_pins.json.  libx264 itself stays absent: everything else in the lookahead checker
 (search order, costs, decisions, mb-tree) remains unpinned."""
@@ -25,6 +27,15 @@ MC_W, MC_H = 64, 48
 # decoder clamps coordinates; the planes carry a 32-sample replicated border)
 MC_MVS = [(fx, fy) for fy in range(4) for fx in range(4)] + [(-37, 22), (50, -61), (3, -90), (-85, 1), (-6, -7), (83, 86)]
 MC_KINDS = ("noise", "extreme")
+# explicit weighted prediction (mc_weight): (vector, (log2 denominator, scale, offset))
+WP_CASES = [((0, 0), (0, 1, 5)), ((0, 0), (5, 40, -3)), ((2, 1), (6, 100, 20)), ((3, 3), (7, 127, -128)), ((1, 2), (2, 7, 127)),
+            ((0, 0), (0, 2, -100)), ((-37, 22), (5, 31, 0)), ((2, 2), (7, 127, 1)), ((0, 0), (1, 1, 0)), ((1, 0), (6, 64, -1))]
+# bidirectional prediction: (distance p1 - p0, position b - p0, list-0 vector, list-1 vector, weighted_bipred_idc);
+# idc 2 = implicit weights (x264's weightb), 0 = plain average.  Then every (distance, position) the lookahead can
+# meet with up to 16 B-frames, to pin its own distance scale against the standard's.
+BI_CASES = [(2, 1, (0, 0), (0, 0), 0), (2, 1, (0, 0), (0, 0), 2), (3, 1, (2, 1), (-3, 2), 2), (4, 1, (5, -6), (1, 1), 2),
+            (4, 3, (3, 3), (-9, 7), 2), (4, 3, (3, 3), (-9, 7), 0), (5, 2, (-37, 22), (50, -61), 2), (8, 7, (1, 2), (3, 0), 2)]
+BI_CASES += [(d, b, (1, 0), (0, 1), 2) for d in range(2, 18) for b in range(1, d)]
 INTRA_MBW, INTRA_MBH = 4, 24
 
 
@@ -67,6 +78,26 @@ def mc_stream(kind):
     return aus
 
 
+def wp_stream():
+    import h264_mini as hm
+    y, u, v = mc_picture("noise")
+    aus = [hm.sps(MC_W // 16, MC_H // 16) + hm.pps() + hm.pps(1, 1) + hm.idr_pcm_picture(y, u, v)]
+    for k, ((mx, my), wt) in enumerate(WP_CASES):
+        aus.append(hm.p_picture_uniform_mv(MC_W // 16, MC_H // 16, mx, my, 1, 2 * (k + 1), weight=wt))
+    return aus
+
+
+def bi_stream(case):
+    import h264_mini as hm
+    d, b, mv0, mv1, idc = case
+    ya, ua, va = mc_picture("noise")
+    yb, ub, vb = mc_picture("extreme")
+    mw, mh = MC_W // 16, MC_H // 16
+    return [hm.sps(mw, mh, 2, 1) + hm.pps() + hm.pps(2, 0, 2) + hm.idr_pcm_picture(ya, ua, va),
+            hm.p_pcm_reference_picture(yb, ub, vb, 1, 2 * d),
+            hm.b_picture_uniform_mvs(mw, mh, mv0, mv1, 2, 2 * b, 2 if idc else 0)]
+
+
 def intra_stream():
     import h264_mini as hm
     y, u, v = intra_picture()
@@ -78,9 +109,10 @@ def fnv(a):
     return f"{ol.oracle().orc_fnv1a64(a.ctypes.data, a.size):016x}"
 
 
-def predict_from_planes(planes, w, h, stride, mvx, mvy):
+def predict_from_planes(planes, w, h, stride, mvx, mvy, weight=None):
     """The whole picture predicted with one quarter-sample vector: get_ref (checker's own code) per 8x8 block on
-    four padded half-pel planes of shape (4, h + 64, stride) -- the checker's or the device's."""
+    four padded half-pel planes of shape (4, h + 64, stride) -- the checker's or the device's.  weight = (log2
+    denominator, scale, offset) applies mc_weight after the interpolation, as get_ref does for a weighted reference."""
     o = ol.oracle()
     planes = np.ascontiguousarray(planes)
     out = np.zeros((h, w), dtype=np.uint8)
@@ -89,7 +121,11 @@ def predict_from_planes(planes, w, h, stride, mvx, mvy):
     for by in range(0, h, 8):
         for bx in range(0, w, 8):
             off = (by + 32) * stride + bx + 32
-            o.orc_test_get_ref_8x8(blk.ctypes.data, *[C.c_void_p(base + p * pb + off) for p in range(4)], stride, mvx, mvy)
+            ptrs = [C.c_void_p(base + p * pb + off) for p in range(4)]
+            if weight is None:
+                o.orc_test_get_ref_8x8(blk.ctypes.data, *ptrs, stride, mvx, mvy)
+            else:
+                o.orc_test_get_ref_8x8_weighted(blk.ctypes.data, *ptrs, stride, mvx, mvy, weight[1], weight[0], weight[2])
             out[by:by + 8, bx:bx + 8] = blk.reshape(8, 8)
     return out
 
@@ -100,6 +136,57 @@ def checker_mc_hashes(kind, planes=None):
     if planes is None:
         planes = ol.oracle_hpel_planes(y, MC_W, MC_H)
     return [fnv(predict_from_planes(planes, MC_W, MC_H, g["stride"], mx, my)) for mx, my in MC_MVS]
+
+
+def checker_wp_hashes():
+    y, _, _ = mc_picture("noise")
+    g = ol.hpel_geometry(MC_W, MC_H)
+    planes = ol.oracle_hpel_planes(y, MC_W, MC_H)
+    return [fnv(predict_from_planes(planes, MC_W, MC_H, g["stride"], mx, my, wt)) for (mx, my), wt in WP_CASES]
+
+
+def decoder_wp_hashes():
+    import avdec
+    pics = avdec.decode_h264(wp_stream())
+    assert len(pics) == 1 + len(WP_CASES)
+    return [fnv(p[0]) for p in pics[1:]]
+
+
+def checker_bi_hashes():
+    """get_ref on both references, the lookahead's bipred weight for (p0, b, p1) = (0, b, d), pixel_avg."""
+    o = ol.oracle()
+    g = ol.hpel_geometry(MC_W, MC_H)
+    pa = ol.oracle_hpel_planes(mc_picture("noise")[0], MC_W, MC_H)
+    pb = ol.oracle_hpel_planes(mc_picture("extreme")[0], MC_W, MC_H)
+    cache, out = {}, []
+    blk = np.zeros(64, dtype=np.uint8)
+    for d, b, mv0, mv1, idc in BI_CASES:
+        if (0, mv0) not in cache:
+            cache[(0, mv0)] = predict_from_planes(pa, MC_W, MC_H, g["stride"], *mv0)
+        if (1, mv1) not in cache:
+            cache[(1, mv1)] = predict_from_planes(pb, MC_W, MC_H, g["stride"], *mv1)
+        a, c = cache[(0, mv0)], cache[(1, mv1)]
+        wt = o.orc_test_bipred_weight(0, d, b, 1 if idc else 0)
+        pr = np.zeros((MC_H, MC_W), dtype=np.uint8)
+        for by in range(0, MC_H, 8):
+            for bx in range(0, MC_W, 8):
+                x = np.ascontiguousarray(a[by:by + 8, bx:bx + 8]).reshape(-1)
+                z = np.ascontiguousarray(c[by:by + 8, bx:bx + 8]).reshape(-1)
+                o.orc_test_pixel_avg_8x8(blk.ctypes.data, x.ctypes.data, z.ctypes.data, wt)
+                pr[by:by + 8, bx:bx + 8] = blk.reshape(8, 8)
+        out.append(fnv(pr))
+    return out
+
+
+def decoder_bi_hashes(cases=None):
+    import avdec
+    ya, yb = mc_picture("noise")[0], mc_picture("extreme")[0]
+    out = []
+    for case in (BI_CASES if cases is None else cases):
+        pics = avdec.decode_h264(bi_stream(case))        # output order: the IDR, the B picture, the later reference
+        assert len(pics) == 3 and np.array_equal(pics[0][0], ya) and np.array_equal(pics[2][0], yb), case
+        out.append(fnv(pics[1][0]))
+    return out
 
 
 def checker_intra_hashes():

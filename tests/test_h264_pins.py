@@ -31,6 +31,23 @@ def test_checker_hpel_planes_and_get_ref_equal_the_decoders_motion_compensation(
     assert not bad, bad
 
 
+def test_checker_weighted_get_ref_equals_the_decoders_explicit_weighted_prediction():
+    """get_ref + mc_weight (a weighted reference of the lookahead) against P pictures with a pred_weight_table:
+    denominators 0..7, scales 1..127, offsets -128..127, integer and fractional vectors."""
+    assert [[list(m), list(w)] for m, w in hp.WP_CASES] == GOLD["wp"]["cases"]
+    assert hp.checker_wp_hashes() == GOLD["wp"]["pictures"]
+
+
+def test_checker_bidirectional_average_equals_the_decoders():
+    """pixel_avg with the lookahead's bipred weight against B pictures (plain and implicitly weighted), incl. every
+    (distance, position) the lookahead can meet with up to 16 B-frames: its own distance scale gives the
+    standard's implicit weights."""
+    assert [[c[0], c[1], list(c[2]), list(c[3]), c[4]] for c in hp.BI_CASES] == GOLD["bi"]["cases"]
+    got, want = hp.checker_bi_hashes(), GOLD["bi"]["pictures"]
+    bad = [hp.BI_CASES[i] for i in range(len(want)) if got[i] != want[i]]
+    assert not bad, bad
+
+
 def test_checker_intra_predictors_equal_the_decoders():
     """predict_8x8c_{dc,h,v,p} (as the decoder's intra chroma prediction) and predict_8x8_filter +
     predict_8x8_{ddl,ddr,vr,hd,vl,hu} (as its Intra_8x8 prediction), neighbours from I_PCM macroblocks."""
@@ -61,3 +78,5 @@ def test_live_decoder_reproduces_the_fixture():
         pytest.skip("no loadable libavcodec")
     assert hp.decoder_mc_hashes("noise") == GOLD["mc"]["pictures"]["noise"]
     assert hp.decoder_intra_hashes() == GOLD["intra"]
+    assert hp.decoder_wp_hashes() == GOLD["wp"]["pictures"]
+    assert hp.decoder_bi_hashes(hp.BI_CASES[:8]) == GOLD["bi"]["pictures"][:8]
