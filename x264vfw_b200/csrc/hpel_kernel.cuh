@@ -17,14 +17,20 @@
 // shuffle's "no such lane -> own value" is exactly the clamped neighbour at the frame's left / right edge.
 // Tiles cover [0,w); the two words just outside ([-8,0) and [w,w+8)) are the halo lanes of the first /
 // last tile, which also own the replicated border.  The six source rows of the vertical filter slide
-// through registers (four packed 16-bit pairs per row; one row per loop trip, see the note at the loop).  Arithmetic:
+// through registers (four packed 16-bit pairs per row; two rows per loop trip, see the note at the loop).  Arithmetic:
 //   V  : packed 16-bit lanes, biased by 2576 = 80*32 + 16 so that lanes never go negative (no borrow between
 //        lanes) and the bias supplies the rounding term; >>5, per-lane add/min/relu (DPX) gives clip().
 //   H  : two dp4a per pixel on byte windows cut out of (left, own, own, right) words with PRMT.
 //   C  : three dp2a per pixel on pairs of the biased 16-bit vertical sums (own + neighbours' by shuffle),
 //        32-bit accumulation as upstream's C code (the 16-bit trick of upstream's asm can overflow).
 //   clip + pack of H and C: cvt.pack.sat.u8.s32.
-// About 19 issued instructions per pixel for 5 bytes of traffic per pixel.
+// About 23 issued instructions per pixel of an interior tile (182 per lane and row, 124 of them the filter) for
+// 5 bytes of traffic per pixel.  Specialisations: ALIGNED (64-bit loads / cp.async vs byte gathers, decided on the
+// host by hpel_plan) and EDGE (tiles that hold the frame's first or last column do the border work; the others run
+// a loop without it, hpel_unit_any).
+// Pinned beyond the checker: the four planes, read at every quarter-sample position, reproduce the motion-
+// compensated pictures of an independent H.264 decoder (tests/golden/h264_pins.json; tests/test_hpel_oracle.py
+// for this source on the CPU, tests/test_next_hpel_gpu.py for the device).
 //
 // This header is compiled by nvcc (hpel_kernels.cu) and, with the lockstep warp shim in tests/sim/, by g++:
 // the CPU suite runs this very code against the CPU checker.  The shim is test infrastructure; the product has no
