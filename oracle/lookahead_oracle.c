@@ -1629,3 +1629,17 @@ void orc_test_pixel_avg_8x8(uint8_t dst[64], const uint8_t a[64], const uint8_t 
 {
     pixel_avg_8x8(dst, a, 8, b, 8, weight);
 }
+
+void orc_test_predict_picture(uint8_t *dst, const uint8_t *planes, int stride, size_t plane_bytes, int w, int h,
+                              int mvx, int mvy, int scale, int denom, int offset)
+{
+    const weight_t wt = {1, scale, denom, offset};
+    uint8_t blk[64];
+    for (int by = 0; by < h; by += 8)
+        for (int bx = 0; bx < w; bx += 8) {
+            uint8_t *pl[4];
+            for (int p = 0; p < 4; p++) pl[p] = (uint8_t *)planes + p * plane_bytes + (size_t)(by + PAD) * stride + bx + PAD;
+            get_ref_8x8(blk, pl, stride, mvx, mvy, scale < 0 ? NULL : &wt);
+            for (int y = 0; y < 8; y++) memcpy(dst + (size_t)(by + y) * w + bx, blk + 8 * y, 8);
+        }
+}

@@ -7,6 +7,7 @@
  */
 #ifndef X264VFW_LOOKAHEAD_ORACLE_H
 #define X264VFW_LOOKAHEAD_ORACLE_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -124,6 +125,10 @@ void orc_test_get_ref_8x8_weighted(uint8_t dst[64], const uint8_t *p0, const uin
                                    int stride, int mvx, int mvy, int scale, int denom, int offset);
 /* the bidirectional average of the lookahead: weight of the list-0 block for frames (p0, b, p1) in display order
  * (weightb = implicit weights, H.264 8.4.2.3.1/2) and pixel_avg with that weight */
+/* a whole w x h picture (multiples of 8) predicted with one vector from four padded planes (32-sample border,
+ * plane p at planes + p * plane_bytes): get_ref per 8x8 block; scale < 0 = unweighted */
+void orc_test_predict_picture(uint8_t *dst, const uint8_t *planes, int stride, size_t plane_bytes, int w, int h,
+                              int mvx, int mvy, int scale, int denom, int offset);
 int orc_test_bipred_weight(int p0, int p1, int b, int weightb);
 void orc_test_pixel_avg_8x8(uint8_t dst[64], const uint8_t a[64], const uint8_t b[64], int weight);
 

@@ -14,12 +14,20 @@ syntax tables."""
 
 
 class Bits:
+    """MSB-first bit writer; whole bytes go in at byte speed once aligned (I_PCM samples)."""
+
     def __init__(self):
-        self.bits = []
+        self.buf = bytearray()
+        self.acc = 0
+        self.n = 0
 
     def u(self, n, v):
-        for i in range(n - 1, -1, -1):
-            self.bits.append((v >> i) & 1)
+        self.acc = (self.acc << n) | (v & ((1 << n) - 1))
+        self.n += n
+        while self.n >= 8:
+            self.n -= 8
+            self.buf.append((self.acc >> self.n) & 0xFF)
+        self.acc &= (1 << self.n) - 1
 
     def ue(self, v):
         v += 1
@@ -31,44 +39,30 @@ class Bits:
         self.ue(2 * v - 1 if v > 0 else -2 * v)
 
     def aligned(self):
-        return len(self.bits) % 8 == 0
+        return self.n == 0
 
     def align_zero(self):
-        while not self.aligned():
-            self.bits.append(0)
+        if self.n:
+            self.u(8 - self.n, 0)
 
     def raw(self, data: bytes):
         assert self.aligned()
-        for b in data:
-            self.u(8, b)
+        self.buf += data
 
     def trailing(self):                     # rbsp_trailing_bits
-        self.bits.append(1)
+        self.u(1, 1)
         self.align_zero()
 
     def bytes(self):
         assert self.aligned()
-        out = bytearray()
-        for i in range(0, len(self.bits), 8):
-            b = 0
-            for k in range(8):
-                b = (b << 1) | self.bits[i + k]
-            out.append(b)
-        return bytes(out)
+        return bytes(self.buf)
 
 
 def nal(ref_idc, unit_type, rbsp: bytes) -> bytes:
-    """Start code + header + payload with emulation prevention (7.4.1)."""
-    out = bytearray(b"\x00\x00\x00\x01")
-    out.append((ref_idc << 5) | unit_type)
-    zeros = 0
-    for b in rbsp:
-        if zeros >= 2 and b <= 3:
-            out.append(3)
-            zeros = 0
-        out.append(b)
-        zeros = zeros + 1 if b == 0 else 0
-    return bytes(out)
+    """Start code + header + payload with emulation prevention (7.4.1): 03 after two zero bytes when the next
+    byte is 00..03 (the zero run starts again at that byte)."""
+    import re
+    return b"\x00\x00\x00\x01" + bytes([(ref_idc << 5) | unit_type]) + re.sub(b"\x00\x00(?=[\x00-\x03])", b"\x00\x00\x03", rbsp)
 
 
 def sps(mb_w, mb_h, num_ref_frames=1, reorder=0) -> bytes:
@@ -94,9 +88,9 @@ def sps(mb_w, mb_h, num_ref_frames=1, reorder=0) -> bytes:
         b.u(1, 0)                # vui_parameters_present_flag
     else:                        # VUI with nothing but the bitstream restriction: tells the decoder its reorder depth
         b.u(1, 1)
-        for _ in range(9):       # aspect_ratio, overscan, video_signal_type, chroma_loc, timing, nal_hrd, vcl_hrd,
-            b.u(1, 0)            # pic_struct: all absent ... and bitstream_restriction_flag next
-        b.bits[-1] = 1           # bitstream_restriction_flag
+        for _ in range(8):       # aspect_ratio, overscan, video_signal_type, chroma_loc, timing, nal_hrd, vcl_hrd,
+            b.u(1, 0)            # pic_struct: all absent
+        b.u(1, 1)                # bitstream_restriction_flag
         b.u(1, 1)                # motion_vectors_over_pic_boundaries_flag
         b.ue(0); b.ue(0)         # max_bytes_per_pic_denom, max_bits_per_mb_denom
         b.ue(16); b.ue(16)       # log2_max_mv_length_horizontal / vertical
@@ -158,9 +152,9 @@ def _slice_header(b: Bits, idr: bool, slice_type: int, frame_num: int, poc_lsb: 
 def _pcm_mb(b: Bits, mb_type_code: int, y, u, v, mbx, mby):
     b.ue(mb_type_code)           # I_PCM: 25 in I slices, 5 + 25 in P slices
     b.align_zero()               # pcm_alignment_zero_bit
-    b.raw(bytes(y[16 * mby:16 * mby + 16, 16 * mbx:16 * mbx + 16].reshape(-1).tolist()))
-    b.raw(bytes(u[8 * mby:8 * mby + 8, 8 * mbx:8 * mbx + 8].reshape(-1).tolist()))
-    b.raw(bytes(v[8 * mby:8 * mby + 8, 8 * mbx:8 * mbx + 8].reshape(-1).tolist()))
+    b.raw(y[16 * mby:16 * mby + 16, 16 * mbx:16 * mbx + 16].tobytes())
+    b.raw(u[8 * mby:8 * mby + 8, 8 * mbx:8 * mbx + 8].tobytes())
+    b.raw(v[8 * mby:8 * mby + 8, 8 * mbx:8 * mbx + 8].tobytes())
 
 
 def idr_pcm_picture(y, u, v, intra_tests=None) -> bytes:

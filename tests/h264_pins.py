@@ -27,6 +27,9 @@ MC_W, MC_H = 64, 48
 # decoder clamps coordinates; the planes carry a 32-sample replicated border)
 MC_MVS = [(fx, fy) for fy in range(4) for fx in range(4)] + [(-37, 22), (50, -61), (3, -90), (-85, 1), (-6, -7), (83, 86)]
 MC_KINDS = ("noise", "extreme")
+# the same at BASELINE's frame size (1080p padded to whole macroblocks): the kernel's tiles and strips
+HD_W, HD_H = 1920, 1088
+HD_MVS = [(1, 1), (2, 2), (3, 1), (2, 0), (0, 2), (-61, 30)]
 # explicit weighted prediction (mc_weight): (vector, (log2 denominator, scale, offset))
 WP_CASES = [((0, 0), (0, 1, 5)), ((0, 0), (5, 40, -3)), ((2, 1), (6, 100, 20)), ((3, 3), (7, 127, -128)), ((1, 2), (2, 7, 127)),
             ((0, 0), (0, 2, -100)), ((-37, 22), (5, 31, 0)), ((2, 2), (7, 127, 1)), ((0, 0), (1, 1, 0)), ((1, 0), (6, 64, -1))]
@@ -67,6 +70,35 @@ def intra_tests():
             t[(mbx, mby)] = (3 + k % 6, (k // 2) % 4)
             k += 1
     return t
+
+
+def hd_picture():
+    b = _lcg(HD_W * HD_H, HD_W, HD_H)
+    return b.reshape(HD_H, HD_W)
+
+
+def hd_stream():
+    import h264_mini as hm
+    y = hd_picture()
+    c = np.full((HD_H // 2, HD_W // 2), 128, dtype=np.uint8)
+    aus = [hm.sps(HD_W // 16, HD_H // 16) + hm.pps() + hm.idr_pcm_picture(y, c, c)]
+    for k, (mx, my) in enumerate(HD_MVS):
+        aus.append(hm.p_picture_uniform_mv(HD_W // 16, HD_H // 16, mx, my, 1, 2 * (k + 1)))
+    return aus
+
+
+def checker_hd_hashes(planes=None):
+    g = ol.hpel_geometry(HD_W, HD_H)
+    if planes is None:
+        planes = ol.oracle_hpel_planes(hd_picture(), HD_W, HD_H)
+    return [fnv(predict_from_planes(planes, HD_W, HD_H, g["stride"], mx, my)) for mx, my in HD_MVS]
+
+
+def decoder_hd_hashes():
+    import avdec
+    pics = avdec.decode_h264(hd_stream())
+    assert len(pics) == 1 + len(HD_MVS) and np.array_equal(pics[0][0], hd_picture())
+    return [fnv(p[0]) for p in pics[1:]]
 
 
 def mc_stream(kind):
@@ -114,19 +146,11 @@ def predict_from_planes(planes, w, h, stride, mvx, mvy, weight=None):
     four padded half-pel planes of shape (4, h + 64, stride) -- the checker's or the device's.  weight = (log2
     denominator, scale, offset) applies mc_weight after the interpolation, as get_ref does for a weighted reference."""
     o = ol.oracle()
+    o.orc_test_predict_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t] + [C.c_int] * 7
     planes = np.ascontiguousarray(planes)
     out = np.zeros((h, w), dtype=np.uint8)
-    blk = np.zeros(64, dtype=np.uint8)
-    base, pb = planes.ctypes.data, planes.shape[1] * stride
-    for by in range(0, h, 8):
-        for bx in range(0, w, 8):
-            off = (by + 32) * stride + bx + 32
-            ptrs = [C.c_void_p(base + p * pb + off) for p in range(4)]
-            if weight is None:
-                o.orc_test_get_ref_8x8(blk.ctypes.data, *ptrs, stride, mvx, mvy)
-            else:
-                o.orc_test_get_ref_8x8_weighted(blk.ctypes.data, *ptrs, stride, mvx, mvy, weight[1], weight[0], weight[2])
-            out[by:by + 8, bx:bx + 8] = blk.reshape(8, 8)
+    dn, sc, of = weight if weight is not None else (0, -1, 0)
+    o.orc_test_predict_picture(out.ctypes.data, planes.ctypes.data, stride, planes.shape[1] * stride, w, h, mvx, mvy, sc, dn, of)
     return out
 
 

@@ -31,6 +31,12 @@ def test_checker_hpel_planes_and_get_ref_equal_the_decoders_motion_compensation(
     assert not bad, bad
 
 
+def test_checker_equals_the_decoder_at_1080p():
+    """1920x1088 (BASELINE's frame padded to whole macroblocks), six vectors."""
+    assert (GOLD["hd"]["w"], GOLD["hd"]["h"], [tuple(m) for m in GOLD["hd"]["mvs"]]) == (hp.HD_W, hp.HD_H, hp.HD_MVS)
+    assert hp.checker_hd_hashes() == GOLD["hd"]["pictures"]
+
+
 def test_checker_weighted_get_ref_equals_the_decoders_explicit_weighted_prediction():
     """get_ref + mc_weight (a weighted reference of the lookahead) against P pictures with a pred_weight_table:
     denominators 0..7, scales 1..127, offsets -128..127, integer and fractional vectors."""

@@ -139,6 +139,26 @@ def test_device_planes_reproduce_the_h264_decoders_motion_compensation(ctx, kind
     assert hp.checker_mc_hashes(kind, planes=planes) == gold["mc"]["pictures"][kind]
 
 
+def test_device_planes_reproduce_the_h264_decoder_at_1080p(ctx):
+    """1920x1088, six vectors: every tile and strip of the kernel at BASELINE's frame size against the decoder's
+    pictures (tests/golden/h264_pins.json)."""
+    import json
+    import os
+    import torch
+    import h264_pins as hp
+    from x264vfw_b200 import hpel
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h264_pins.json")))
+    w, h = hp.HD_W, hp.HD_H
+    g = hpel.geometry(w, h)
+    d_src = torch.from_numpy(np.ascontiguousarray(hp.hd_picture()).reshape(-1)).cuda()
+    d_out = torch.zeros(4 * g.plane_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    hpel.hpel_filter(ctx, d_out.data_ptr(), d_src.data_ptr(), w, w, h)
+    ctx.sync()
+    planes = d_out.cpu().numpy().reshape(4, h + 64, g.stride)
+    assert hp.checker_hd_hashes(planes=planes) == gold["hd"]["pictures"]
+
+
 def test_hpel_filter_rejects_bad_geometry(ctx):
     from x264vfw_b200 import hpel
     from x264vfw_b200._lib import CudaError
