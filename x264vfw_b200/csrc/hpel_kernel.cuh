@@ -29,7 +29,7 @@
 // host by hpel_plan) and EDGE (tiles that hold the frame's first or last column do the border work; the others run
 // a loop without it, hpel_unit_any).
 // Pinned beyond the checker: the four planes, read at every quarter-sample position, reproduce the motion-
-// compensated pictures of an independent H.264 decoder (tests/golden/h264_pins.json; tests/test_hpel_oracle.py
+// compensated pictures of an independent H.264 decoder (tests/golden/h264_pins.json; the lockstep run in the CPU suite
 // for this source on the CPU, tests/test_next_hpel_gpu.py for the device).
 //
 // This header is compiled by nvcc (hpel_kernels.cu) and, with the lockstep warp shim in tests/sim/, by g++:
