@@ -1643,3 +1643,6 @@ void orc_test_predict_picture(uint8_t *dst, const uint8_t *planes, int stride, s
             for (int y = 0; y < 8; y++) memcpy(dst + (size_t)(by + y) * w + bx, blk + 8 * y, 8);
         }
 }
+
+int orc_test_sad_8x8(const uint8_t a[64], const uint8_t b[64]) { return sad_8x8(a, 8, b, 8); }
+int orc_test_satd_8x8(const uint8_t a[64], const uint8_t b[64]) { return satd_8x8(a, 8, b, 8); }

@@ -130,6 +130,9 @@ void orc_test_get_ref_8x8_weighted(uint8_t dst[64], const uint8_t *p0, const uin
 void orc_test_predict_picture(uint8_t *dst, const uint8_t *planes, int stride, size_t plane_bytes, int w, int h,
                               int mvx, int mvy, int scale, int denom, int offset);
 int orc_test_bipred_weight(int p0, int p1, int b, int weightb);
+/* the two block metrics of the search ([x264] common/pixel.c: sad 8x8, satd 8x8), strides 8 */
+int orc_test_sad_8x8(const uint8_t a[64], const uint8_t b[64]);
+int orc_test_satd_8x8(const uint8_t a[64], const uint8_t b[64]);
 void orc_test_pixel_avg_8x8(uint8_t dst[64], const uint8_t a[64], const uint8_t b[64], int weight);
 
 #ifdef __cplusplus
