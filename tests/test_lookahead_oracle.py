@@ -45,3 +45,51 @@ def test_block_metrics_against_a_matrix_formulation():
             satd += s >> 1
         assert o.orc_test_sad_8x8(a.ctypes.data, b.ctypes.data) == sad
         assert o.orc_test_satd_8x8(a.ctypes.data, b.ctypes.data) == satd
+
+
+def test_intra_costs_of_a_session_rebuilt_from_pinned_pieces():
+    """Row a11 end to end on the CPU: the checker's per-MB intra costs of a frame against a Python restatement of
+    [x264] slicetype_mb_cost's intra part -- neighbours from the padded lowres plane, the ten predictions through
+    the decoder-pinned hook (tests/test_h264_pins.py), SATD through the matrix formulation (SAD and three modes only
+    at subme <= 1), min + 5*lambda + 4."""
+    import ctypes as C
+    import numpy as np
+    import oracle_lib as ol
+    o = ol.oracle()
+    H = np.array([[1, 1, 1, 1], [1, 1, -1, -1], [1, -1, -1, 1], [1, -1, 1, -1]], dtype=np.int64)
+
+    def satd(a, b):
+        d = a.astype(np.int64) - b.astype(np.int64)
+        return sum(sum(int(np.abs(H @ d[4 * hf:4 * hf + 4, 4 * bl:4 * bl + 4] @ H.T).sum()) for bl in range(2)) >> 1 for hf in range(2))
+
+    w, h = 112, 80                                      # 7 x 5 macroblocks, lowres 56 x 40
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:h, 0:w]
+    y = ((xx * 3 + yy * 2) % 200 + rng.integers(0, 40, (h, w))).astype(np.uint8)     # gradients + noise: several modes win
+    for subme, modes in ((7, [0, 1, 2, 3, 13, 14, 15, 16, 17, 18]), (1, [0, 1, 2])):
+        la = ol.OracleLookahead(ol.la_params("medium", w, h, subme=subme))
+        try:
+            la.put_luma(y)
+            la.frame_cost(0, 0, 0)
+            got = la.intra_cost(0)
+            g = la.g
+            plane = np.ascontiguousarray(la.lowres_planes(0)[:g["lplane_bytes"]])
+            st, org = g["lstride"], g["lorigin"]
+            blk = np.zeros(64, dtype=np.uint8)
+            winners = set()
+            for mby in range(g["mb_h"]):
+                for mbx in range(g["mb_w"]):
+                    off = org + 8 * mby * st + 8 * mbx
+                    src = np.stack([plane[off + r * st:off + r * st + 8] for r in range(8)])
+                    best = None
+                    for m in modes:
+                        o.orc_test_intra_pred_8x8(blk.ctypes.data, m, C.c_void_p(plane.ctypes.data + off), st)
+                        # [x264] mbcmp_init: SATD when subme > 1, SAD otherwise
+                        c = satd(blk.reshape(8, 8), src) if subme > 1 else int(np.abs(blk.reshape(8, 8).astype(np.int64) - src).sum())
+                        if best is None or c < best[0]:
+                            best = (c, m)
+                    winners.add(best[1])
+                    assert got[mby * g["mb_w"] + mbx] == best[0] + 5 + 4, (subme, mbx, mby)
+            assert len(winners) >= (3 if subme > 1 else 2)   # the picture exercises more than one predictor
+        finally:
+            la.close()
