@@ -93,3 +93,81 @@ def test_intra_costs_of_a_session_rebuilt_from_pinned_pieces():
             assert len(winners) >= (3 if subme > 1 else 2)   # the picture exercises more than one predictor
         finally:
             la.close()
+
+
+def test_inter_costs_at_the_chosen_vectors_rebuilt_from_pinned_pieces():
+    """Row a12, the part that is arithmetic rather than search order: for every MB of a P search the checker's stored
+    cost must be SATD(source, get_ref(reference planes, chosen vector)) + cost_mv(vector - predictor) - cost_mv(0)
+    [+ 5 when the vector is not zero], with the predictor rebuilt here from the final vector field (right, below,
+    below-left, below-right neighbours of the reverse-raster scan) -- get_ref through the decoder-pinned hook, SATD
+    through the matrix formulation, cost_mv from its defining formula.  Zero-predictor MBs whose co-located SATD is
+    below 64 keep the zero vector and that SATD."""
+    import ctypes as C
+    import math
+    import numpy as np
+    import oracle_lib as ol
+    o = ol.oracle()
+    H = np.array([[1, 1, 1, 1], [1, 1, -1, -1], [1, -1, -1, 1], [1, -1, 1, -1]], dtype=np.int64)
+
+    def satd(a, b):
+        d = a.astype(np.int64) - b.astype(np.int64)
+        return sum(sum(int(np.abs(H @ d[4 * hf:4 * hf + 4, 4 * bl:4 * bl + 4] @ H.T).sum()) for bl in range(2)) >> 1 for hf in range(2))
+
+    def cost_mv(d):                                     # [x264] x264_analyse_init_costs at lambda 1
+        d = abs(d)
+        return int(np.float32(0.718) + np.float32(0.5)) if d == 0 else \
+            int(np.float32(np.float32(math.log2(d + 1)) * np.float32(2.0) + np.float32(1.718)) + np.float32(0.5))
+
+    def median3(a, b, c):
+        return sorted((a, b, c))[1]
+
+    w, h = 160, 96                                      # 10 x 6 macroblocks
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (h + 32, w + 32), dtype=np.uint8)
+    base = ((base.astype(np.int32) + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4).astype(np.uint8)
+    f0, f1 = base[8:8 + h, 8:8 + w], base[5:5 + h, 11:11 + w]          # a global shift of (+3, -3) full-res pixels
+    la = ol.OracleLookahead(ol.la_params("medium", w, h, weightp=0))
+    try:
+        la.put_luma(np.ascontiguousarray(f0))
+        la.put_luma(np.ascontiguousarray(f1))
+        la.frame_cost(0, 1, 1)
+        g = la.g
+        mvs, costs = la.mvs(1, 0, 1), la.mv_costs(1, 0, 1)
+        st, org, pb = g["lstride"], g["lorigin"], g["lplane_bytes"]
+        ref = np.ascontiguousarray(la.lowres_planes(0))
+        cur = np.ascontiguousarray(la.lowres_planes(1)[:pb])
+        mbw, mbh = g["mb_w"], g["mb_h"]
+        blk = np.zeros(64, dtype=np.uint8)
+        moved = 0
+        for mby in range(mbh):
+            for mbx in range(mbw):
+                i = mby * mbw + mbx
+                cand = []
+                if mbx < mbw - 1:
+                    cand.append(mvs[i + 1])
+                if mby < mbh - 1:
+                    cand.append(mvs[i + mbw])
+                    if mbx > 0:
+                        cand.append(mvs[i + mbw - 1])
+                    if mbx < mbw - 1:
+                        cand.append(mvs[i + mbw + 1])
+                cand = [(int(c[0]), int(c[1])) for c in cand] + [(0, 0)] * 4
+                n = sum(1 for _ in cand) - 4
+                mvp = cand[0] if n <= 1 else (median3(cand[0][0], cand[1][0], cand[2][0]), median3(cand[0][1], cand[1][1], cand[2][1]))
+                off = org + 8 * mby * st + 8 * mbx
+                src = np.stack([cur[off + r * st:off + r * st + 8] for r in range(8)])
+                mx, my = int(mvs[i][0]), int(mvs[i][1])
+                o.orc_test_get_ref_8x8(blk.ctypes.data, *[C.c_void_p(ref.ctypes.data + p * pb + off) for p in range(4)], st, mx, my)
+                s = satd(src, blk.reshape(8, 8))
+                if mvp == (0, 0):
+                    o.orc_test_get_ref_8x8(blk.ctypes.data, *[C.c_void_p(ref.ctypes.data + p * pb + off) for p in range(4)], st, 0, 0)
+                    s0 = satd(src, blk.reshape(8, 8))
+                    if s0 < 64:
+                        assert (mx, my) == (0, 0) and costs[i] == s0, (mbx, mby)
+                        continue
+                want = s + cost_mv(mx - mvp[0]) + cost_mv(my - mvp[1]) - cost_mv(0) + (5 if (mx or my) else 0)
+                assert costs[i] == want, (mbx, mby, (mx, my), mvp, int(costs[i]), want)
+                moved += (mx, my) != (0, 0)
+        assert moved > mbw * mbh // 2                    # the clip really moves: most MBs carry a vector
+    finally:
+        la.close()
