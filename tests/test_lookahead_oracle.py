@@ -171,3 +171,70 @@ def test_inter_costs_at_the_chosen_vectors_rebuilt_from_pinned_pieces():
         assert moved > mbw * mbh // 2                    # the clip really moves: most MBs carry a vector
     finally:
         la.close()
+
+
+def test_behavioural_anchors_of_the_decision_logic():
+    """What any x264 does on these clips, whatever its version (documented behaviour, not a reference pin): the
+    first frame is an IDR; a hard scene cut starts with an I-frame that is not a keyframe-interval IDR; a short
+    white flash is not mistaken for a cut (how short depends on b-adapt); a static clip uses its B-frames; keyint forces an IDR; with bframes 0
+    there are no B-frames; decisions come out in coded order (every B after the P/I that closes its mini-GOP)."""
+    import numpy as np
+    import oracle_lib as ol
+    from x264vfw_b200.clipgen import SyntheticClip
+    BGRA_FLIP = 9 | 0x1000
+    w, h = 128, 96
+
+    def run(n, over, **clip_kw):
+        clip = SyntheticClip(w, h, n_frames=n, **clip_kw)
+        la = ol.OracleLookahead(ol.la_params("medium", w, h, **over))
+        out = []
+        try:
+            for i in range(n):
+                la.put_i420(ol.oracle_convert(clip.packed(i, "bgra"), BGRA_FLIP, 2, 2, 0, w, h))
+                out += la.decisions()
+            la.flush()
+            out += la.decisions()
+        finally:
+            la.close()
+        assert sorted(d["i_frame"] for d in out) == list(range(n))
+        types = {d["i_frame"]: d["i_type"] for d in out}
+        # coded order: a B-frame follows the next non-B frame in display order
+        pos = {d["i_frame"]: k for k, d in enumerate(out)}
+        for f, t in types.items():
+            if t in (4, 5):
+                nxt = min(g for g, tg in types.items() if g > f and tg not in (4, 5))
+                assert pos[nxt] < pos[f], (f, nxt)
+        return types, {d["i_frame"]: d["b_keyframe"] for d in out}
+
+    IDR, I, P, BREF, B = 1, 2, 3, 4, 5
+    base = dict(rc_lookahead=10, keyint_max=250, keyint_min=5)
+    types, key = run(24, base, cuts=(13,), flash=None)
+    assert types[0] == IDR and key[0]
+    assert types[13] in (I, IDR), types                                  # the cut
+    assert all(types[f] not in (I, IDR) for f in range(1, 24) if f != 13), types
+    # flash rejection looks ahead to p0 + 2 with b-adapt 1 and to p0 + 1 + bframes with b-adapt 2 ([x264] scenecut):
+    # a one-frame flash is never a cut, a two-frame flash is none under b-adapt 2 (and is one under b-adapt 1)
+    types, _ = run(24, base, cuts=(), flash=11, flash_len=1)
+    assert all(types[f] not in (I, IDR) for f in range(1, 24)), types
+    types, _ = run(24, dict(base, b_adapt=2), cuts=(), flash=11, flash_len=2)
+    assert all(types[f] not in (I, IDR) for f in range(1, 24)), types
+    types, _ = run(24, base, cuts=(), flash=11, flash_len=2)
+    assert types[11] in (I, IDR), types
+    types, _ = run(16, dict(base, keyint_max=8, keyint_min=2), cuts=(), flash=None)
+    assert types[0] == IDR and types[8] == IDR, types                    # keyint
+    types, _ = run(12, dict(base, bframes=0), cuts=(), flash=None)
+    assert all(t in (IDR, I, P) for t in types.values()), types
+    still = SyntheticClip(w, h, n_frames=1, cuts=(), flash=None).packed(0, "bgra")
+    la = ol.OracleLookahead(ol.la_params("medium", w, h, **base))
+    out = []
+    try:
+        f = ol.oracle_convert(still, BGRA_FLIP, 2, 2, 0, w, h)
+        for _ in range(14):
+            la.put_i420(f)
+            out += la.decisions()
+        la.flush()
+        out += la.decisions()
+    finally:
+        la.close()
+    nb = sum(d["i_type"] in (BREF, B) for d in out)
+    assert nb >= 6, [d["i_type"] for d in sorted(out, key=lambda d: d["i_frame"])]      # a static clip is mostly B-frames
