@@ -238,3 +238,36 @@ def test_behavioural_anchors_of_the_decision_logic():
         la.close()
     nb = sum(d["i_type"] in (BREF, B) for d in out)
     assert nb >= 6, [d["i_type"] for d in sorted(out, key=lambda d: d["i_frame"])]      # a static clip is mostly B-frames
+
+
+def test_behavioural_anchors_of_the_qp_offsets():
+    """Without mb-tree the offsets handed to the encoder are the AQ offsets; without AQ and mb-tree they are zero;
+    with mb-tree on a static clip every MB of an early frame is referenced by the whole window, so its offset is well
+    below the AQ offset, and the last P-frame of the clip (nothing references it) keeps the AQ offset."""
+    import numpy as np
+    import oracle_lib as ol
+    from x264vfw_b200.clipgen import SyntheticClip
+    w, h, n = 128, 96, 12
+    f = ol.oracle_convert(SyntheticClip(w, h, n_frames=1, cuts=(), flash=None).packed(0, "bgra"), 9 | 0x1000, 2, 2, 0, w, h)
+
+    def run(**over):
+        la = ol.OracleLookahead(ol.la_params("medium", w, h, rc_lookahead=8, keyint_max=250, keyint_min=5, **over))
+        out = []
+        try:
+            for _ in range(n):
+                la.put_i420(f)
+                out += la.decisions()
+            la.flush()
+            out += la.decisions()
+        finally:
+            la.close()
+        return {d["i_frame"]: d for d in out}
+
+    d = run(b_mbtree=0)
+    assert all(np.array_equal(x["qp_offset"].view(np.uint32), x["qp_offset_aq"].view(np.uint32)) for x in d.values())
+    d = run(b_mbtree=0, aq_mode=0)
+    assert all(not x["qp_offset"].any() and not x["qp_offset_aq"].any() for x in d.values())
+    d = run()
+    assert float((d[0]["qp_offset"] - d[0]["qp_offset_aq"]).max()) < -1.0        # importance raises quality: lower qp
+    last_ref = max(k for k, x in d.items() if x["i_type"] in (1, 2, 3))
+    assert np.array_equal(d[last_ref]["qp_offset"].view(np.uint32), d[last_ref]["qp_offset_aq"].view(np.uint32))
