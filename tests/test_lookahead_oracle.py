@@ -271,3 +271,25 @@ def test_behavioural_anchors_of_the_qp_offsets():
     assert float((d[0]["qp_offset"] - d[0]["qp_offset_aq"]).max()) < -1.0        # importance raises quality: lower qp
     last_ref = max(k for k, x in d.items() if x["i_type"] in (1, 2, 3))
     assert np.array_equal(d[last_ref]["qp_offset"].view(np.uint32), d[last_ref]["qp_offset_aq"].view(np.uint32))
+
+
+def test_the_search_recovers_a_global_translation():
+    """A picture shifted by (dx, dy) full-resolution pixels is found at (2 dx, 2 dy) quarter samples of the lowres
+    plane by (almost) every macroblock: whole-, half- and odd shifts."""
+    from collections import Counter
+    import numpy as np
+    import oracle_lib as ol
+    w, h = 160, 96
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (h + 32, w + 32), dtype=np.uint8)
+    base = ((base.astype(np.int32) + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4).astype(np.uint8)
+    for dx, dy in ((3, -3), (4, 0), (0, -2), (0, 0), (-6, 5)):
+        la = ol.OracleLookahead(ol.la_params("medium", w, h, weightp=0))
+        try:
+            la.put_luma(np.ascontiguousarray(base[8:8 + h, 8:8 + w]))
+            la.put_luma(np.ascontiguousarray(base[8 + dy:8 + dy + h, 8 + dx:8 + dx + w]))
+            la.frame_cost(0, 1, 1)
+            (mv, cnt), = Counter(map(tuple, la.mvs(1, 0, 1).tolist())).most_common(1)
+            assert mv == (2 * dx, 2 * dy) and cnt >= 0.9 * la.mb_count, ((dx, dy), mv, cnt)
+        finally:
+            la.close()
