@@ -293,3 +293,27 @@ def test_the_search_recovers_a_global_translation():
             assert mv == (2 * dx, 2 * dy) and cnt >= 0.9 * la.mb_count, ((dx, dy), mv, cnt)
         finally:
             la.close()
+
+
+def test_the_weight_analysis_recovers_a_fade():
+    """frame1 = frame0 * scale + offset: the lookahead's weight analysis finds scale / 2^denom and the offset (to
+    within one level), with the smallest denominator; an unchanged frame gets no weight."""
+    import numpy as np
+    import oracle_lib as ol
+    w, h = 160, 96
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    base = ((base.astype(np.int32) + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4).astype(np.uint8)
+    for sc, of, want in ((0.75, 10, (3, 2)), (0.5, 0, (1, 1)), (1.0, 20, (1, 0)), (1.25, -20, (5, 2)), (1.0, 0, None)):
+        la = ol.OracleLookahead(ol.la_params("medium", w, h))
+        try:
+            la.put_luma(base)
+            la.put_luma(np.clip(base.astype(np.float64) * sc + of + 0.5, 0, 255).astype(np.uint8))
+            la.frame_cost(0, 1, 1)
+            wt = la.weight(1)
+            if want is None:
+                assert not wt["on"], wt
+            else:
+                assert wt["on"] and (wt["scale"], wt["denom"]) == want and abs(wt["offset"] - of) <= 1, ((sc, of), wt)
+        finally:
+            la.close()
