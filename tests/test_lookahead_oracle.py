@@ -317,3 +317,41 @@ def test_the_weight_analysis_recovers_a_fade():
                 assert wt["on"] and (wt["scale"], wt["denom"]) == want and abs(wt["offset"] - of) <= 1, ((sc, of), wt)
         finally:
             la.close()
+
+
+def test_aq_offsets_against_a_numpy_formulation():
+    """f1 (adaptive quant, aq-mode 1): per MB, energy = AC energy of the 16x16 luma block + both 8x8 chroma blocks
+    (ssd - sum^2 >> 8 resp. >> 6) on the frame replicated out to whole macroblocks; offset = 1.0397 * strength * (log2(max(
+    energy, 1)) - 14.427).  [x264] x264_log2 is a 128-entry table, so the comparison allows its 0.0113 step; the
+    point is the energy (blocks, replication, chroma) rather than the last bit."""
+    import numpy as np
+    import oracle_lib as ol
+    from x264vfw_b200.clipgen import SyntheticClip
+    w, h = 136, 88                                      # not multiples of 16: the replicated part counts
+    f = ol.oracle_convert(SyntheticClip(w, h, n_frames=1, cuts=(), flash=None).packed(0, "bgra"), 9 | 0x1000, 2, 2, 0, w, h)
+    p = ol.la_params("medium", w, h)
+    la = ol.OracleLookahead(p)
+    try:
+        la.put_i420(f)
+        got = la.qp_offset(0, aq=True)
+    finally:
+        la.close()
+    y = f[:w * h].reshape(h, w).astype(np.int64)
+    u = f[w * h:w * h * 5 // 4].reshape(h // 2, w // 2).astype(np.int64)
+    v = f[w * h * 5 // 4:].reshape(h // 2, w // 2).astype(np.int64)
+    mbw, mbh = (w + 15) // 16, (h + 15) // 16
+    y = np.pad(y, ((0, 16 * mbh - h), (0, 16 * mbw - w)), mode="edge")
+    u = np.pad(u, ((0, 8 * mbh - h // 2), (0, 8 * mbw - w // 2)), mode="edge")
+    v = np.pad(v, ((0, 8 * mbh - h // 2), (0, 8 * mbw - w // 2)), mode="edge")
+
+    def ac(b, shift):
+        s, q = int(b.sum()), int((b * b).sum())
+        return q - ((s * s) >> shift)
+
+    strength = float(np.float32(p.aq_strength) * np.float32(1.0397))       # [x264] aq-mode 1: f_aq_strength * 1.0397f
+    for mby in range(mbh):
+        for mbx in range(mbw):
+            e = ac(y[16 * mby:16 * mby + 16, 16 * mbx:16 * mbx + 16], 8) + ac(u[8 * mby:8 * mby + 8, 8 * mbx:8 * mbx + 8], 6) + \
+                ac(v[8 * mby:8 * mby + 8, 8 * mbx:8 * mbx + 8], 6)
+            want = strength * (np.log2(max(e, 1)) - 14.427)
+            assert abs(float(got[mby * mbw + mbx]) - want) <= strength * 0.0115 + 1e-4, (mbx, mby, float(got[mby * mbw + mbx]), want)
