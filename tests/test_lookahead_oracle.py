@@ -355,3 +355,70 @@ def test_aq_offsets_against_a_numpy_formulation():
                 ac(v[8 * mby:8 * mby + 8, 8 * mbx:8 * mbx + 8], 6)
             want = strength * (np.log2(max(e, 1)) - 14.427)
             assert abs(float(got[mby * mbw + mbx]) - want) <= strength * 0.0115 + 1e-4, (mbx, mby, float(got[mby * mbw + mbx]), want)
+
+
+def test_one_mbtree_step_against_a_python_formulation():
+    """Row a16: frames (I, P, P); the tree walk propagates frame 2 into frame 1 once and finishes frame 1.  The
+    propagated amounts ([x264] mbtree_propagate_cost, float32 in C's order) and their split over up to four MBs
+    along the lowres vector ([x264] mbtree_propagate_list: x>>5, 32-step bilinear weights, +512 >> 10, saturating
+    add, frame-edge cases) are recomputed here from the checker's own inputs; the finished qp offsets are compared
+    within the step of the log2 table."""
+    import numpy as np
+    import oracle_lib as ol
+    f32 = np.float32
+    w, h = 160, 96
+    rng = np.random.default_rng(9)
+    base = rng.integers(0, 256, (h + 32, w + 64), dtype=np.uint8)
+    base = ((base.astype(np.int32) + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4).astype(np.uint8)
+    p = ol.la_params("medium", w, h, weightp=0)
+    la = ol.OracleLookahead(p)
+    try:
+        for k in range(3):                               # a pan of (+5, -3) pixels per frame: vectors (10, -6), a 4-way split
+            la.put_luma(np.ascontiguousarray(base[8 + 3 * (2 - k):8 + 3 * (2 - k) + h, 8 + 5 * k:8 + 5 * k + w]))
+        la.mbtree([0, 1, 2], [2, 3, 3], 0)               # I, P, P
+        got = la.propagate_cost(1).astype(np.int64)
+        intra, invq = la.intra_cost(2).astype(np.int64), la.inv_qscale(2).astype(np.int64)
+        lc, mvs = la.lowres_costs(2, 1, 0).astype(np.int64), la.mvs(2, 0, 1).astype(np.int64)
+        mbw, mbh = la.g["mb_w"], la.g["mb_h"]
+        fps_factor = f32(f32(p.fps_den) / f32(p.fps_num)) / (f32(f32(p.fps_den) / f32(p.fps_num)) * f32(256.0)) * f32(0.5)
+        want = np.zeros(mbw * mbh, dtype=np.int64)
+
+        def add(idx, v):
+            want[idx] = min(want[idx] + v, 32767)
+
+        split = 0
+        for mby in range(mbh):
+            for i in range(mbw):
+                k = mby * mbw + i
+                if not (lc[k] >> 14) & 1 or not intra[k]:
+                    continue
+                inter = min(intra[k], lc[k] & 16383)
+                amount = f32(0) + f32(intra[k] * invq[k]) * fps_factor
+                amount = min(int(amount * f32(intra[k] - inter) / f32(intra[k]) + f32(0.5)), 32767)
+                x, y = int(mvs[k][0]), int(mvs[k][1])
+                if not (x or y):
+                    add(k, amount)
+                    continue
+                mbx, mby2 = (x >> 5) + i, (y >> 5) + mby
+                x &= 31
+                y &= 31
+                ws = [(32 - y) * (32 - x), (32 - y) * x, y * (32 - x), y * x]
+                ws = [(v * amount + 512) >> 10 for v in ws]
+                split += all(ws)
+                for (dx, dy), v in zip(((0, 0), (1, 0), (0, 1), (1, 1)), ws):
+                    if 0 <= mbx + dx < mbw and 0 <= mby2 + dy < mbh:
+                        add((mby2 + dy) * mbw + mbx + dx, v)
+        assert split > mbw * mbh // 3                    # the clip exercises the 4-way split
+        assert np.array_equal(got, want), np.argwhere(got != want)[:5]
+        # finish: qp_offset = qp_offset_aq - 5 (1 - qcomp) (log2(intra' + propagate') - log2(intra'))
+        i1, q1 = la.intra_cost(1).astype(np.int64), la.inv_qscale(1).astype(np.int64)
+        qp, qa = la.qp_offset(1), la.qp_offset(1, aq=True)
+        strength = 5.0 * (1.0 - float(p.qcompress))
+        for k in range(mbw * mbh):
+            ic = (i1[k] * q1[k] + 128) >> 8
+            if ic:
+                pc = (got[k] * 512 + 128) >> 8          # fps_factor of the finish = 256 / MBTREE_PRECISION
+                ratio = np.log2(ic + pc) - np.log2(ic)
+                assert abs(float(qp[k]) - (float(qa[k]) - strength * ratio)) <= strength * 0.0115 + 1e-4, k
+    finally:
+        la.close()
