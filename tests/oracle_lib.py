@@ -34,6 +34,24 @@ def oracle():
         o.orc_fnv1a64.restype = C.c_uint64
         o.orc_fnv1a64.argtypes = [C.c_void_p, C.c_size_t]
         o.orc_lcg_fill.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        # test hooks of the lookahead checker (pointers must never travel as default C ints)
+        V, I = C.c_void_p, C.c_int
+        o.orc_test_get_ref_8x8.argtypes = [V, V, V, V, V, I, I, I]
+        o.orc_test_get_ref_8x8.restype = None
+        o.orc_test_get_ref_8x8_weighted.argtypes = [V, V, V, V, V, I, I, I, I, I, I]
+        o.orc_test_get_ref_8x8_weighted.restype = None
+        o.orc_test_intra_pred_8x8.argtypes = [V, I, V, I]
+        o.orc_test_intra_pred_8x8.restype = None
+        o.orc_test_pixel_avg_8x8.argtypes = [V, V, V, I]
+        o.orc_test_pixel_avg_8x8.restype = None
+        o.orc_test_bipred_weight.argtypes = [I, I, I, I]
+        o.orc_test_bipred_weight.restype = I
+        o.orc_test_sad_8x8.argtypes = [V, V]
+        o.orc_test_sad_8x8.restype = I
+        o.orc_test_satd_8x8.argtypes = [V, V]
+        o.orc_test_satd_8x8.restype = I
+        o.orc_test_predict_picture.argtypes = [V, V, I, C.c_size_t] + [I] * 7
+        o.orc_test_predict_picture.restype = None
         _orc = o
     return _orc
 
