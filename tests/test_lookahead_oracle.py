@@ -422,3 +422,32 @@ def test_one_mbtree_step_against_a_python_formulation():
                 assert abs(float(qp[k]) - (float(qa[k]) - strength * ratio)) <= strength * 0.0115 + 1e-4, k
     finally:
         la.close()
+
+
+def test_frame_sums_are_the_sums_of_the_per_mb_results():
+    """Row a13: [x264] slicetype_slice_cost / slicetype_frame_cost accumulators rebuilt from the per-MB results --
+    cost estimate and intra-MB count over the interior macroblocks (the frame's border MBs are not scored), the AQ
+    cost with each MB scaled by its inv_qscale (+128 >> 8), row sums over all macroblocks."""
+    import numpy as np
+    import oracle_lib as ol
+    from x264vfw_b200.clipgen import SyntheticClip
+    w, h = 160, 112
+    clip = SyntheticClip(w, h, n_frames=2, cuts=(), flash=None)
+    la = ol.OracleLookahead(ol.la_params("medium", w, h))
+    try:
+        for i in range(2):
+            la.put_i420(ol.oracle_convert(clip.packed(i, "bgra"), 9 | 0x1000, 2, 2, 0, w, h))
+        score = la.frame_cost(0, 1, 1)
+        mbw, mbh = la.g["mb_w"], la.g["mb_h"]
+        lc = la.lowres_costs(1, 1, 0).astype(np.int64).reshape(mbh, mbw)
+        invq = la.inv_qscale(1).astype(np.int64).reshape(mbh, mbw)
+        cost, used = lc & 16383, lc >> 14
+        cost_aq = (cost * invq + 128) >> 8
+        inner = (slice(1, mbh - 1), slice(1, mbw - 1))
+        assert la.cost_est(1, 1, 0) == int(cost[inner].sum()) == score
+        assert la.cost_est(1, 1, 0, aq=True) == int(cost_aq[inner].sum())
+        assert la.intra_mbs(1, 1) == int((used[inner] == 0).sum())
+        assert np.array_equal(la.row_satds(1, 1, 0), cost_aq.sum(axis=1))
+        assert 0 < (used == 0).sum() < mbw * mbh or (used == 1).all()
+    finally:
+        la.close()
