@@ -59,7 +59,8 @@ def parse_args():
 def make_clips(stream_ids, n_frames):
     """Per-stream packed BGRA clips (numpy, host)."""
     from concurrent.futures import ThreadPoolExecutor
-    from x264vfw_b200.clipgen import SyntheticClip
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from clipgen import SyntheticClip        # test / bench infrastructure, not part of the product package
 
     def one(s):
         clip = SyntheticClip(W, H, n_frames=n_frames, stream_id=s, cuts=(n_frames * 5 // 8,), flash=None)
@@ -344,13 +345,13 @@ def main():
                                     colmatrix=2, fullrange=0, device=local_rank) for _ in range(S)]
 
     sessions = open_sessions()
-    ms_step, clocks, launches, _ = run_phase(torch, dist, sessions, dev_ptrs, True, None, args, rank, world, local_rank)
+    ms_step, clocks, launches, _ = run_phase(torch, dist, sessions, dev_ptrs, 2, None, args, rank, world, local_rank)
     host_delta = dict(run_phase.delta)
     for la in sessions:
         la.close()
     # same workload once more with per-kernel CUDA-event timing switched on (kernel shares, roofline)
     sessions = open_sessions()
-    ms_prof, _, _, prof = run_phase(torch, dist, sessions, dev_ptrs, True, None, args, rank, world, local_rank, profile=True)
+    ms_prof, _, _, prof = run_phase(torch, dist, sessions, dev_ptrs, 2, None, args, rank, world, local_rank, profile=True)
     prof_delta = dict(run_phase.delta)
     for la in sessions:
         la.close()

@@ -147,7 +147,37 @@ typedef struct harness_stream {
     int mb_count, error;
     float *qp, *qp_aq;                   /* scratch, allocated on first use                         */
     int count;                           /* frames to feed in this call (set by the runner)         */
+    /* optional decision log (parity tests): log_cap records; qp arrays are kept as FNV-1a-64 hashes */
+    struct harness_logrec *log; int log_cap, log_n;
 } harness_stream;
+
+typedef struct harness_logrec {
+    x264vfw_cuda_la_decision d;
+    uint64_t qp_fnv, qp_aq_fnv;
+} harness_logrec;
+
+static uint64_t fnv1a64(const void *p, size_t n)
+{
+    const uint8_t *b = (const uint8_t *)p;
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ULL; }
+    return h;
+}
+
+static void stream_drain(harness_stream *s)
+{
+    x264vfw_cuda_la_decision d;
+    while (x264vfw_cuda_la_get_decision(s->la, &d, s->qp, s->qp_aq) == 1) {
+        s->checksum += s->qp[d.i_frame % s->mb_count] + d.i_type;
+        if (s->log && s->log_n < s->log_cap) {
+            harness_logrec *r = &s->log[s->log_n++];
+            r->d = d;
+            r->qp_fnv = fnv1a64(s->qp, sizeof(float) * s->mb_count);
+            r->qp_aq_fnv = fnv1a64(s->qp_aq, sizeof(float) * s->mb_count);
+        }
+        s->decided++;
+    }
+}
 
 static void *stream_thread(void *arg)
 {
@@ -169,11 +199,7 @@ static void *stream_thread(void *arg)
             cp = &conv_pic;
         }
         if (x264vfw_cuda_la_put_frame(s->la, &pic, s->on_device, cp) < 0) { s->error = 1; break; }
-        x264vfw_cuda_la_decision d;
-        while (x264vfw_cuda_la_get_decision(s->la, &d, s->qp, s->qp_aq) == 1) {
-            s->checksum += s->qp[d.i_frame % s->mb_count] + d.i_type;
-            s->decided++;
-        }
+        stream_drain(s);
         s->pos++;
     }
     return NULL;
@@ -187,6 +213,19 @@ int harness_run_streams(harness_stream *streams, int n, int count)
     for (int i = 0; i < n; i++) { streams[i].count = count; if (pthread_create(&th[i], NULL, stream_thread, &streams[i])) return -1; }
     int rc = 0;
     for (int i = 0; i < n; i++) { pthread_join(th[i], NULL); if (streams[i].error) rc = -1; }
+    return rc;
+}
+
+/* End of stream for every session (x264vfw_cuda_la_flush), decisions drained like in harness_run_streams. */
+int harness_flush_streams(harness_stream *streams, int n)
+{
+    int rc = 0;
+    for (int i = 0; i < n; i++) {
+        harness_stream *s = &streams[i];
+        if (!s->qp) continue;
+        if (x264vfw_cuda_la_flush(s->la) < 0) { s->error = 1; rc = -1; continue; }
+        stream_drain(s);
+    }
     return rc;
 }
 

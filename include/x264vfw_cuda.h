@@ -250,16 +250,23 @@ int  x264vfw_cuda_la_open( x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *
 void x264vfw_cuda_la_close( x264vfw_cuda_la *la );
 
 /* One input frame in display order == one x264_encoder_encode( pic_in ) call.
- * src describes the frame like x264vfw_img_fill does; src_on_device selects host or device
- * pointers.  conv_pic (may be NULL) receives the converted planes in HOST memory -- what
- * codec->conv_pic holds for the CPU encoder.  Both buffers are only borrowed for the call:
- * the source has been read and conv_pic is complete when it returns.  Returns the number of
- * decided frames waiting in the output queue, or -1.
+ * src describes the frame like x264vfw_img_fill does; src_on_device selects host (0) or device
+ * (X264VFW_CUDA_SRC_DEVICE, X264VFW_CUDA_SRC_RESIDENT) pointers.  conv_pic (may be NULL) receives
+ * the converted planes in HOST memory -- what codec->conv_pic holds for the CPU encoder.  Both
+ * buffers are only borrowed for the call: the source has been read and conv_pic is complete when
+ * it returns (for X264VFW_CUDA_SRC_DEVICE the call waits for the device-side conversion that reads
+ * it).  The one exception is X264VFW_CUDA_SRC_RESIDENT: the caller promises that the device buffer
+ * stays unmodified until x264vfw_cuda_la_flush / _close (a clip that lives in HBM), and the call
+ * returns without waiting for its reader.  Returns the number of decided frames waiting in the
+ * output queue, or -1.
  * Like libx264 behind sync-lookahead, the session works on queued frames in a thread of its
  * own while the caller moves the next frame: the frames that become decided because of frame n
  * are published, deterministically, by the call for frame n + 2 (and all of them by _flush);
  * the sequence of decisions never depends on timing.  X264VFW_CUDA_ASYNC=0 decides inside the
  * call instead. */
+#define X264VFW_CUDA_SRC_HOST     0
+#define X264VFW_CUDA_SRC_DEVICE   1
+#define X264VFW_CUDA_SRC_RESIDENT 2
 int x264vfw_cuda_la_put_frame( x264vfw_cuda_la *la, const x264vfw_cuda_image_t *src, int src_on_device,
                                x264vfw_cuda_image_t *conv_pic );
 /* End of stream (x264_encoder_encode with pic_in == NULL, codec.c:1755-1758,1848). */

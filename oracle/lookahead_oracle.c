@@ -815,6 +815,10 @@ static void weights_analyse(orc_la *la, frame_t *fenc, frame_t *ref)
     while (mindenom > 0 && !(minscale & 1)) { mindenom--; minscale >>= 1; }
     if (!found || (minscale == 1 << mindenom && minoff == 0) || (float)minscore / origscore > 0.998f) return;
     wt->on = 1; wt->scale = minscale; wt->denom = mindenom; wt->offset = minoff;
+    /* X264_WEIGHTP_FAKE: the weight is only used inside the lookahead; what it gained is kept for
+     * macroblock_tree_finish ([x264] x264_weights_analyse: f_weighted_cost_delta[i_delta_index]) */
+    if (la->p.weightp == ORC_WEIGHTP_FAKE)
+        fenc->weighted_cost_delta[fenc->i_frame - ref->i_frame - 1] = (float)minscore / origscore;
 
     /* x264_weight_scale_plane over the whole padded lowres[0] of the reference */
     const uint8_t *src = ref->lowres_buf;
@@ -1477,6 +1481,8 @@ void orc_la_params_preset(orc_la_params *p, const char *preset, int width, int h
         p->me_method = 2; p->subme = 9; p->frame_reference = 8; p->b_adapt = 2; p->rc_lookahead = 60;
     } else if (!strcmp(preset, "veryslow")) {
         p->me_method = 2; p->subme = 10; p->me_range = 24; p->frame_reference = 16; p->b_adapt = 2; p->bframes = 8; p->rc_lookahead = 60;
+    } else if (!strcmp(preset, "placebo")) {
+        p->me_method = 4; p->subme = 11; p->me_range = 24; p->frame_reference = 16; p->b_adapt = 2; p->bframes = 16; p->rc_lookahead = 60;
     }
 }
 
@@ -1488,6 +1494,9 @@ orc_la *orc_la_open(const orc_la_params *p)
     if (la->p.bframes > ORC_BFRAME_MAX) la->p.bframes = ORC_BFRAME_MAX;
     if (la->p.rc_lookahead > ORC_LOOKAHEAD_MAX) la->p.rc_lookahead = ORC_LOOKAHEAD_MAX;
     if (la->p.keyint_min <= 0) la->p.keyint_min = MIN(la->p.keyint_max / 10, la->p.fps_num / MAX(1, la->p.fps_den));
+    /* [x264] encoder/encoder.c validate_parameters: weightp off + mb-tree + psy => X264_WEIGHTP_FAKE (-1):
+     * the lookahead still analyses (and uses) luma weights and records f_weighted_cost_delta */
+    if (!la->p.weightp && la->p.b_mbtree && la->p.b_psy) la->p.weightp = ORC_WEIGHTP_FAKE;
     int g[10];
     orc_lowres_geometry(p->width, p->height, g);
     la->mb_w = g[0]; la->mb_h = g[1]; la->mb_count = g[0] * g[1];

@@ -25,6 +25,7 @@ extern "C" {
 #define ORC_TYPE_BREF 4
 #define ORC_TYPE_B 5
 #define ORC_TYPE_KEYFRAME 6
+#define ORC_WEIGHTP_FAKE (-1)   /* X264_WEIGHTP_FAKE of x264.h */
 
 /* Plain-int parameter block (x264_param_t subset the lookahead reads).  Field order is
  * shared with x264vfw_cuda_la_params in include/x264vfw_cuda.h. */

@@ -5,7 +5,8 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from x264vfw_b200 import lookahead
-from x264vfw_b200.clipgen import SyntheticClip
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from clipgen import SyntheticClip
 from x264vfw_b200.harness import StreamSet
 
 FLIP = 0x1000

@@ -4,7 +4,8 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from x264vfw_b200 import lookahead
-from x264vfw_b200.clipgen import SyntheticClip
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from clipgen import SyntheticClip
 
 W, H, N = 1920, 1080, 24
 clip = SyntheticClip(W, H, n_frames=N, cuts=(15,), flash=None)

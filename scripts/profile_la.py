@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from x264vfw_b200 import lookahead, csp
-from x264vfw_b200.clipgen import SyntheticClip
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from clipgen import SyntheticClip
 
 W, H = 1920, 1080
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10

@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from x264vfw_b200 import lookahead
-from x264vfw_b200.clipgen import SyntheticClip
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from clipgen import SyntheticClip
 
 w, h, n = 336, 192, 22
 clip = SyntheticClip(w, h, n_frames=n, cuts=(12,), flash=None)

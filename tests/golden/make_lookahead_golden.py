@@ -15,7 +15,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle_lib as ol  # noqa: E402
-from x264vfw_b200.clipgen import SyntheticClip  # noqa: E402
+from clipgen import SyntheticClip  # noqa: E402
 
 BGRA_FLIP = 9 | 0x1000
 CASES = [

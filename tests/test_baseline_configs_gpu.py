@@ -1,7 +1,14 @@
-"""GPU parity at the BASELINE.json configurations (full frame sizes, shortened clips): the whole
-path -- packed input -> device csp -> AQ/lowres -> lookahead decisions -- against the CPU oracle
-fed with oracle-converted planes.  Frame types, coded order, rate-control costs and per-MB qp
-offsets must be identical."""
+"""GPU parity at the BASELINE.json configurations, run to STEADY STATE (full frame sizes, the lookahead
+window full for most of the clip, key-frame interval small enough to fire, cut and flash inside a
+full window): the whole path -- packed input -> device csp -> AQ/lowres -> lookahead decisions --
+against the CPU oracle fed with oracle-converted planes.  Frame types, coded order, rate-control
+costs and per-MB qp offsets must be identical.
+
+The checker runs in a thread of its own beside the device session (ctypes releases the interpreter
+lock), so a case costs max(checker, device) + clip generation."""
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 import pytest
 
@@ -11,53 +18,97 @@ pytestmark = pytest.mark.gpu
 
 FLIP = 0x1000
 YUYV, UYVY, BGR, BGRA = 6, 7, 8, 9
+TYPE_CH = {1: "I", 2: "i", 3: "P", 4: "b", 5: "B"}
 
 
-def run_config(w, h, n_frames, fmt, in_csp, out_csp, chroma_format, preset, over, ext=0, cuts=None):
-    from x264vfw_b200 import lookahead
-    from x264vfw_b200.clipgen import SyntheticClip
-    clip = SyntheticClip(w, h, n_frames=n_frames, cuts=cuts if cuts is not None else (n_frames * 5 // 8,), flash=n_frames // 3, flash_len=1)
-    over = dict(over, chroma_format=chroma_format)
-    po, pg = ol.la_params(preset, w, h, **over), lookahead.params_preset(preset, w, h, **over)
-    orc = ol.OracleLookahead(po)
-    gpu = lookahead.Lookahead(pg, in_csp=in_csp, out_csp=out_csp, device=0)
-    do, dg = [], []
+def make_packed(w, h, n_frames, fmt, stream_id=0, **clip_kw):
+    from clipgen import SyntheticClip
+    clip = SyntheticClip(w, h, n_frames=n_frames, stream_id=stream_id, **clip_kw)
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        return list(ex.map(lambda n: clip.packed(n, fmt), range(n_frames)))
+
+
+def oracle_session(params, planes):
+    orc = ol.OracleLookahead(params)
+    out = []
     try:
-        for n in range(n_frames):
-            packed = clip.packed(n, fmt)
-            planes = ol.oracle_convert(packed, in_csp, out_csp, 2, 0, w, h, ext=ext)
-            assert planes is not None
-            orc.put_i420(planes)
-            do += orc.decisions()
-            gpu.put_frame(packed)
-            dg += gpu.decisions()
-        orc.flush(); do += orc.decisions()
-        gpu.flush(); dg += gpu.decisions()
+        for p in planes:
+            orc.put_i420(p)
+            out += orc.decisions()
+        orc.flush()
+        out += orc.decisions()
     finally:
-        orc.close(); gpu.close()
-    assert len(dg) == n_frames
-    assert [d["i_frame"] for d in dg] == [d["i_frame"] for d in do]
+        orc.close()
+    return out
+
+
+def compare_decisions(dg, do, n_frames, tag=""):
+    assert len(dg) == n_frames, (tag, len(dg))
+    assert [d["i_frame"] for d in dg] == [d["i_frame"] for d in do], tag
     for a, b in zip(dg, do):
         for k in ("i_type", "b_keyframe", "i_bframes", "i_cost_est", "i_cost_est_aq", "i_intra_mbs"):
-            assert a[k] == b[k], (k, a["i_frame"], a[k], b[k])
-        assert np.array_equal(a["qp_offset"].view(np.uint32), b["qp_offset"].view(np.uint32)), a["i_frame"]
-        assert np.array_equal(a["qp_offset_aq"].view(np.uint32), b["qp_offset_aq"].view(np.uint32)), a["i_frame"]
-    return "".join({1: "I", 2: "i", 3: "P", 4: "b", 5: "B"}[d["i_type"]] for d in sorted(dg, key=lambda d: d["i_frame"]))
+            assert a[k] == b[k], (tag, k, a["i_frame"], a[k], b[k])
+        assert np.array_equal(a["qp_offset"].view(np.uint32), b["qp_offset"].view(np.uint32)), (tag, a["i_frame"])
+        assert np.array_equal(a["qp_offset_aq"].view(np.uint32), b["qp_offset_aq"].view(np.uint32)), (tag, a["i_frame"])
+    return "".join(TYPE_CH[d["i_type"]] for d in sorted(dg, key=lambda d: d["i_frame"]))
 
 
-def test_config1_1080p_rgb32_bottom_up_to_i420_medium():
-    types = run_config(1920, 1080, 46, "bgra", BGRA | FLIP, 2, 1, "medium", {})
-    assert types[0] == "I" and len(types) == 46
+def run_config(w, h, n_frames, fmt, in_csp, out_csp, chroma_format, preset, over, ext=0, nv12_oracle_i420=False, **clip_kw):
+    from x264vfw_b200 import lookahead
+    packed = make_packed(w, h, n_frames, fmt, **clip_kw)
+    over = dict(over, chroma_format=chroma_format)
+    po, pg = ol.la_params(preset, w, h, **over), lookahead.params_preset(preset, w, h, **over)
+    # the checker is fed planar frames: an NV12 session is checked against the I420 planes of the same samples
+    o_csp, o_ext = (2, 0) if nv12_oracle_i420 else (out_csp, ext)
+    planes = [ol.oracle_convert(p, in_csp, o_csp, 2, 0, w, h, ext=o_ext) for p in packed]
+    assert all(p is not None for p in planes)
+    res = {}
+    th = threading.Thread(target=lambda: res.setdefault("do", oracle_session(po, planes)))
+    th.start()
+    gpu = lookahead.Lookahead(pg, in_csp=in_csp, out_csp=out_csp, device=0)
+    dg = []
+    try:
+        for p in packed:
+            gpu.put_frame(p)
+            dg += gpu.decisions()
+        gpu.flush()
+        dg += gpu.decisions()
+    finally:
+        gpu.close()
+        th.join()
+    return compare_decisions(dg, res["do"], n_frames)
+
+
+def test_config1_1080p_rgb32_bottom_up_to_i420_medium_300_frames():
+    """BASELINE config 1 on the clip SURVEY 8(d) pins: 300 frames, hard cuts at 100 and 200, a two-frame white
+    flash at 150, rc-lookahead 40 full from frame 40 on, keyint 250 reached."""
+    types = run_config(1920, 1080, 300, "bgra", BGRA | FLIP, 2, 1, "medium", {}, cuts=(100, 200), flash=150, flash_len=2)
+    assert len(types) == 300 and types[0] == "I"
+    assert types[100] in "Ii" and types[200] in "Ii", types            # both hard cuts
+    assert types[150] not in "Ii" and types[152] not in "Ii", types    # the flash is rejected as a scene cut
+    assert "B" in types and "P" in types
 
 
 def test_config2_720p_yuy2_to_i420_veryfast_lookahead20():
-    types = run_config(1280, 720, 40, "yuyv", YUYV, 2, 1, "veryfast", {"rc_lookahead": 20})
-    assert types[0] == "I"
+    types = run_config(1280, 720, 96, "yuyv", YUYV, 2, 1, "veryfast", {"rc_lookahead": 20, "keyint_max": 60, "keyint_min": 6},
+                       cuts=(50,), flash=70, flash_len=2)
+    assert types[0] == "I" and types[50] in "Ii"
 
 
-def test_config3_1080p_rgb24_to_i420_slow_badapt2_lookahead60():
-    """The lookahead of config 3 on the reference-defined I420 planes (b-adapt 2 trellis)."""
-    types = run_config(1920, 1080, 24, "bgr", BGR | FLIP, 2, 1, "slow", {"b_adapt": 2, "rc_lookahead": 60})
+def test_config3_1080p_rgb24_to_i420_slow_badapt2_lookahead60_steady_state():
+    """The lookahead of config 3 on the reference-defined I420 planes: b-adapt 2 (Viterbi over a FULL 60-frame
+    window for 36 decisions), key-frame interval 48 so that the keyint logic fires twice."""
+    types = run_config(1920, 1080, 96, "bgr", BGR | FLIP, 2, 1, "slow", {"b_adapt": 2, "rc_lookahead": 60, "keyint_max": 48, "keyint_min": 4},
+                       cuts=(70,), flash=30, flash_len=2)
+    assert types[0] == "I" and types.count("I") >= 3, types
+
+
+def test_config3_1080p_rgb24_to_nv12_session():
+    """'RGB24 -> NV12' as BASELINE names it: the extension conversion (reference I420 arithmetic, U/V interleaved)
+    feeding an NV12 session -- libx264 computes 4:2:0 AQ energies on its internal NV12 frame, so the decisions
+    must be those of the I420 session on the same samples."""
+    types = run_config(1920, 1080, 30, "bgr", BGR | FLIP, 4, 1, "slow", {"b_adapt": 2, "rc_lookahead": 20, "keyint_max": 48, "keyint_min": 4},
+                       nv12_oracle_i420=True, cuts=(17,), flash=None)
     assert types[0] == "I"
 
 
@@ -66,7 +117,7 @@ def test_config3_rgb24_to_nv12_layout_is_the_interleaved_reference_i420():
     the reference I420 result with U/V interleaved (x264_frame_copy_picture)."""
     from x264vfw_b200 import csp
     from x264vfw_b200._lib import Context
-    from x264vfw_b200.clipgen import SyntheticClip
+    from clipgen import SyntheticClip
     w, h = 1920, 1080
     src = SyntheticClip(w, h, n_frames=1).packed(0, "bgr")
     ctx = Context(0)
@@ -80,13 +131,80 @@ def test_config3_rgb24_to_nv12_layout_is_the_interleaved_reference_i420():
     assert np.array_equal(nv12[w * h::2], u) and np.array_equal(nv12[w * h + 1::2], v)
 
 
-def test_config4_2160p_uyvy_to_i422_medium():
-    """Reference-defined 4:2:2 target of config 4 (UYVY -> I422, csp.c:498), High 4:2:2 AQ chroma."""
-    types = run_config(3840, 2160, 12, "uyvy", UYVY, 6, 2, "medium", {})
-    assert types[0] == "I"
+def test_config4_2160p_uyvy_to_i422_medium_steady_state():
+    """Reference-defined 4:2:2 target of config 4 (UYVY -> I422, csp.c:498), High 4:2:2 AQ chroma; rc-lookahead 40
+    full for 20 decisions."""
+    types = run_config(3840, 2160, 60, "uyvy", UYVY, 6, 2, "medium", {"keyint_max": 50, "keyint_min": 5}, cuts=(33,), flash=20, flash_len=2)
+    assert types[0] == "I" and types[33] in "Ii"
 
 
 def test_config4_2160p_uyvy_to_i444_extension():
     """UYVY -> I444 has no reference path (csp.c:501-504); extension = I422 samples, chroma doubled."""
-    types = run_config(3840, 2160, 6, "uyvy", UYVY, 0xc, 3, "medium", {}, ext=2)
+    types = run_config(3840, 2160, 8, "uyvy", UYVY, 0xc, 3, "medium", {}, ext=2, cuts=(5,), flash=None)
     assert types[0] == "I"
+
+
+# ---- config 5: 8 concurrent independent 1080p RGB32 streams, one session + one native host thread each ----
+C5_STREAMS, C5_FRAMES, C5_STEP = 8, 80, 16
+_c5_cache = {}
+
+
+def _c5_inputs():
+    """Clips (one per stream id) and the checker's decisions for them, computed once per test run."""
+    if not _c5_cache:
+        w, h = 1920, 1080
+        clips = [make_packed(w, h, C5_FRAMES, "bgra", stream_id=s, cuts=(30 + 3 * s,), flash=55 + s, flash_len=2) for s in range(C5_STREAMS)]
+        po = ol.la_params("medium", w, h)
+
+        def one(s):
+            planes = [ol.oracle_convert(p, BGRA | FLIP, 2, 2, 0, w, h) for p in clips[s]]
+            return oracle_session(po, planes), planes[-1]
+
+        with ThreadPoolExecutor(max_workers=C5_STREAMS) as ex:
+            want = list(ex.map(one, range(C5_STREAMS)))
+        _c5_cache.update(clips=clips, want=[w_[0] for w_ in want], last_planes=[w_[1] for w_ in want])
+    return _c5_cache
+
+
+@pytest.mark.parametrize("mode", ["resident", "host"])
+def test_config5_eight_concurrent_1080p_streams_match_the_checker(mode):
+    """The configuration bench.py times: 8 sessions, preset medium, rc-lookahead 40, driven by
+    harness_run_streams (one native thread per stream, 16 frames per step) with adaptive speculation, side
+    streams and recycled frame slots all live.  "resident" = packed clips in HBM (bench `value`), "host" = pinned
+    host frames in, conv_pic out (bench `e2e`).  Every stream's decisions, costs and qp-offset arrays (by hash) must
+    be the checker's."""
+    import torch
+    from x264vfw_b200 import lookahead
+    from x264vfw_b200.harness import StreamSet
+    c5 = _c5_inputs()
+    w, h = 1920, 1080
+    sessions = [lookahead.Lookahead(lookahead.params_preset("medium", w, h), in_csp=BGRA | FLIP, out_csp=2, device=0) for _ in range(C5_STREAMS)]
+    try:
+        if mode == "resident":
+            dev = [[torch.from_numpy(f).cuda() for f in clip] for clip in c5["clips"]]
+            torch.cuda.synchronize()
+            frames, conv, on_device = [[t.data_ptr() for t in clip] for clip in dev], None, 2
+        else:
+            frames = [[torch.from_numpy(f).pin_memory().numpy() for f in clip] for clip in c5["clips"]]
+            conv = [[torch.empty(w * h * 3 // 2, dtype=torch.uint8).pin_memory().numpy() for _ in range(4)] for _ in range(C5_STREAMS)]
+            on_device = 0
+        ss = StreamSet(sessions, frames, on_device, conv, log_decisions=C5_FRAMES)
+        for _ in range(C5_FRAMES // C5_STEP):
+            ss.run(C5_STEP)
+        if conv:
+            for s in range(C5_STREAMS):       # conv_pic of the last frame == the reference conversion
+                assert np.array_equal(conv[s][(C5_FRAMES - 1) % 4], c5["last_planes"][s]), s
+        ss.flush()
+        logs = [ss.log(s) for s in range(C5_STREAMS)]
+        ss.close()
+    finally:
+        for la in sessions:
+            la.close()
+    for s in range(C5_STREAMS):
+        got, want = logs[s], c5["want"][s]
+        assert len(got) == C5_FRAMES, (s, len(got))
+        for a, b in zip(got, want):
+            for k in ("i_frame", "i_type", "b_keyframe", "i_bframes", "i_cost_est", "i_cost_est_aq", "i_intra_mbs"):
+                assert a[k] == b[k], (s, k, a["i_frame"], a[k], b[k])
+            assert a["qp_fnv"] == ol.fnv(b["qp_offset"].view(np.uint8)), (s, a["i_frame"])
+            assert a["qp_aq_fnv"] == ol.fnv(b["qp_offset_aq"].view(np.uint8)), (s, a["i_frame"])

@@ -38,7 +38,7 @@ def test_native_stream_runner_matches_the_python_driver():
     the same clips frame by frame from Python."""
     import numpy as np
     from x264vfw_b200 import lookahead
-    from x264vfw_b200.clipgen import SyntheticClip
+    from clipgen import SyntheticClip
     from x264vfw_b200.harness import StreamSet
     build()
     w, h, n = 256, 144, 36

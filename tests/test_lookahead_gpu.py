@@ -14,7 +14,7 @@ BGRA_FLIP = 9 | 0x1000
 
 
 def make_clip(w, h, n, **kw):
-    from x264vfw_b200.clipgen import SyntheticClip
+    from clipgen import SyntheticClip
     clip = SyntheticClip(w, h, n_frames=n, **kw)
     return [clip.packed(i, "bgra") for i in range(n)]
 
@@ -36,7 +36,7 @@ def open_pair(preset, w, h, keep=True, in_csp=0, **over):
 
 def test_params_presets_agree_with_oracle():
     from x264vfw_b200 import lookahead
-    for preset in ("ultrafast", "superfast", "veryfast", "faster", "fast", "medium", "slow", "slower", "veryslow"):
+    for preset in ("ultrafast", "superfast", "veryfast", "faster", "fast", "medium", "slow", "slower", "veryslow", "placebo"):
         a, b = ol.la_params(preset, 1920, 1080), lookahead.params_preset(preset, 1920, 1080)
         for name, _ in a._fields_:
             assert getattr(a, name) == getattr(b, name), (preset, name)
@@ -58,6 +58,23 @@ def test_tunes_only_touch_the_documented_fields():
             assert (abs(got - exp) < 1e-6) if isinstance(exp, float) else got == exp, (tune, name, got, exp)
     with pytest.raises(ValueError):
         lookahead.params_tune(lookahead.params_preset("medium", 64, 64), "nosuchtune")
+    # the reference joins the dialog's tunings with commas (codec.c:1430-1445)
+    p = lookahead.params_tune(lookahead.params_preset("medium", 1920, 1080), "film,fastdecode,zerolatency")
+    assert (p.weightb, p.weightp, p.rc_lookahead, p.bframes, p.b_mbtree) == (0, 0, 0, 0, 0)
+    with pytest.raises(ValueError):
+        lookahead.params_tune(lookahead.params_preset("medium", 64, 64), "film,nosuchtune")
+
+
+def test_open_refuses_what_is_not_restated():
+    """Kept-RGB encoder formats and lookaheadless mb-tree fail loudly instead of returning other numbers."""
+    from x264vfw_b200 import lookahead
+    from x264vfw_b200._lib import CudaError
+    p = lookahead.params_preset("medium", 64, 64)
+    for out_csp in (0xe, 0xf):
+        with pytest.raises(CudaError, match="kept-RGB"):
+            lookahead.Lookahead(p, in_csp=9, out_csp=out_csp, device=0)
+    with pytest.raises(CudaError, match="rc-lookahead 0"):
+        lookahead.Lookahead(lookahead.params_preset("medium", 64, 64, rc_lookahead=0), device=0)
 
 
 @pytest.mark.parametrize("size,over", [((128, 96), {}), ((320, 192), {}), ((330, 186), {}),
@@ -170,6 +187,30 @@ def test_frame_cost_with_fade_exercises_weights():
         orc.close(); gpu.close()
 
 
+def fade_clip(w, h, n, step=30):
+    base = make_clip(w, h, n, cuts=(), flash=None)
+    return [((f.astype(np.int32) * (256 - step * i)) >> 8).astype(np.uint8) for i, f in enumerate(base)]
+
+
+def test_weightp_fake_on_a_fade():
+    """tune fastdecode (weightp 0) with mb-tree and psy is X264_WEIGHTP_FAKE: the lookahead still analyses and
+    uses luma weights, and macroblock_tree_finish consumes f_weighted_cost_delta."""
+    w, h = 320, 192
+    frames = to_i420(fade_clip(w, h, 6), w, h)
+    orc, gpu = open_pair("medium", w, h, rc_lookahead=20, weightp=0, weightb=0)
+    try:
+        for f in frames:
+            orc.put_i420(f)
+            gpu.put_frame(f)
+        seen = 0
+        for (p0, p1, b) in [(0, 1, 1), (1, 2, 2), (0, 2, 2), (0, 2, 1), (2, 3, 3), (3, 5, 5), (3, 5, 4)]:
+            compare_cost(orc, gpu, p0, p1, b)
+            seen += orc.weight(b)["on"]
+        assert seen > 0, "fade clip did not trigger the weight analysis under X264_WEIGHTP_FAKE"
+    finally:
+        orc.close(); gpu.close()
+
+
 def run_session(la, frames, put):
     out = []
     for f in frames:
@@ -225,6 +266,51 @@ def test_session_decisions_match_oracle(preset, over):
     """Whole sessions: frame types, coded order, rate-control costs and per-MB qp offsets."""
     types = compare_sessions(preset, 320, 192, 48, dict(cuts=(25,), flash=36, flash_len=1), over)
     assert types[0] == "I"
+
+
+def test_session_fastdecode_fade_matches_oracle():
+    """Whole session under X264_WEIGHTP_FAKE on a fading clip: the qp offsets carry the weight delta."""
+    w, h, n = 320, 192, 40
+    frames = to_i420(fade_clip(w, h, n, step=5), w, h)
+    over = {"rc_lookahead": 12, "keyint_max": 50, "keyint_min": 5, "weightp": 0, "weightb": 0}
+    orc, gpu = open_pair("medium", w, h, keep=False, **over)
+    try:
+        do = run_session(orc, frames, lambda la, f: la.put_i420(f))
+        dg = run_session(gpu, frames, lambda la, f: la.put_frame(f))
+    finally:
+        orc.close(); gpu.close()
+    assert [(d["i_frame"], d["i_type"], d["i_cost_est"], d["i_cost_est_aq"]) for d in dg] == \
+           [(d["i_frame"], d["i_type"], d["i_cost_est"], d["i_cost_est_aq"]) for d in do]
+    for a, b in zip(dg, do):
+        assert np.array_equal(a["qp_offset"].view(np.uint32), b["qp_offset"].view(np.uint32)), a["i_frame"]
+
+
+def test_nv12_session_uses_the_chroma_planes():
+    """NV12 in -> NV12 out (csp.c:490-492): the AQ energies include U and V read out of the interleaved plane,
+    so every decision equals the I420 session's on the same samples."""
+    from x264vfw_b200 import lookahead
+    w, h, n = 320, 192, 30
+    i420 = to_i420(make_clip(w, h, n, cuts=(17,), flash=None), w, h)
+    nv12 = []
+    for f in i420:
+        y, u, v = f[:w * h], f[w * h:w * h * 5 // 4], f[w * h * 5 // 4:]
+        uv = np.empty(w * h // 2, dtype=np.uint8)
+        uv[0::2] = u; uv[1::2] = v
+        nv12.append(np.concatenate([y, uv]))
+    over = {"rc_lookahead": 10, "keyint_max": 50, "keyint_min": 5}
+    po, pg = params_pair("medium", w, h, **over)
+    orc = ol.OracleLookahead(po)
+    gpu = lookahead.Lookahead(pg, in_csp=5, out_csp=4, device=0)
+    try:
+        do = run_session(orc, i420, lambda la, f: la.put_i420(f))
+        dg = run_session(gpu, nv12, lambda la, f: la.put_frame(f))
+    finally:
+        orc.close(); gpu.close()
+    assert [(d["i_frame"], d["i_type"], d["i_cost_est"], d["i_cost_est_aq"]) for d in dg] == \
+           [(d["i_frame"], d["i_type"], d["i_cost_est"], d["i_cost_est_aq"]) for d in do]
+    for a, b in zip(dg, do):
+        assert np.array_equal(a["qp_offset_aq"].view(np.uint32), b["qp_offset_aq"].view(np.uint32)), a["i_frame"]
+        assert np.array_equal(a["qp_offset"].view(np.uint32), b["qp_offset"].view(np.uint32)), a["i_frame"]
 
 
 def test_session_with_device_csp_front_end_matches_oracle():

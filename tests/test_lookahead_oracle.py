@@ -180,7 +180,7 @@ def test_behavioural_anchors_of_the_decision_logic():
     there are no B-frames; decisions come out in coded order (every B after the P/I that closes its mini-GOP)."""
     import numpy as np
     import oracle_lib as ol
-    from x264vfw_b200.clipgen import SyntheticClip
+    from clipgen import SyntheticClip
     BGRA_FLIP = 9 | 0x1000
     w, h = 128, 96
 
@@ -246,7 +246,7 @@ def test_behavioural_anchors_of_the_qp_offsets():
     below the AQ offset, and the last P-frame of the clip (nothing references it) keeps the AQ offset."""
     import numpy as np
     import oracle_lib as ol
-    from x264vfw_b200.clipgen import SyntheticClip
+    from clipgen import SyntheticClip
     w, h, n = 128, 96, 12
     f = ol.oracle_convert(SyntheticClip(w, h, n_frames=1, cuts=(), flash=None).packed(0, "bgra"), 9 | 0x1000, 2, 2, 0, w, h)
 
@@ -326,7 +326,7 @@ def test_aq_offsets_against_a_numpy_formulation():
     point is the energy (blocks, replication, chroma) rather than the last bit."""
     import numpy as np
     import oracle_lib as ol
-    from x264vfw_b200.clipgen import SyntheticClip
+    from clipgen import SyntheticClip
     w, h = 136, 88                                      # not multiples of 16: the replicated part counts
     f = ol.oracle_convert(SyntheticClip(w, h, n_frames=1, cuts=(), flash=None).packed(0, "bgra"), 9 | 0x1000, 2, 2, 0, w, h)
     p = ol.la_params("medium", w, h)
@@ -430,7 +430,7 @@ def test_frame_sums_are_the_sums_of_the_per_mb_results():
     cost with each MB scaled by its inv_qscale (+128 >> 8), row sums over all macroblocks."""
     import numpy as np
     import oracle_lib as ol
-    from x264vfw_b200.clipgen import SyntheticClip
+    from clipgen import SyntheticClip
     w, h = 160, 112
     clip = SyntheticClip(w, h, n_frames=2, cuts=(), flash=None)
     la = ol.OracleLookahead(ol.la_params("medium", w, h))
@@ -451,3 +451,45 @@ def test_frame_sums_are_the_sums_of_the_per_mb_results():
         assert 0 < (used == 0).sum() < mbw * mbh or (used == 1).all()
     finally:
         la.close()
+
+
+def test_weightp_fake_is_analysed_and_feeds_the_tree_finish():
+    """[x264] validate_parameters turns weightp 0 into X264_WEIGHTP_FAKE when mb-tree and psy are on (tune
+    fastdecode on the default presets): the lookahead still finds a weight on a fade, searches with it, and
+    macroblock_tree_finish lowers log2_ratio by 1 - minscore/origscore.  With psy off there is no analysis at all."""
+    import numpy as np
+    import oracle_lib as ol
+    from clipgen import SyntheticClip
+    w, h, n = 128, 96, 16
+    clip = SyntheticClip(w, h, n_frames=n, cuts=(), flash=None)
+    base = [ol.oracle_convert(clip.packed(i, "bgra"), 9 | 0x1000, 2, 2, 0, w, h) for i in range(n)]
+    fade = [((f.astype(np.int32) * (256 - 12 * i)) >> 8).astype(np.uint8) for i, f in enumerate(base)]
+
+    def run(**over):
+        la = ol.OracleLookahead(ol.la_params("medium", w, h, rc_lookahead=8, keyint_max=250, keyint_min=5, bframes=0, **over))
+        out = []
+        try:
+            for f in fade:
+                la.put_i420(f)
+                out += la.decisions()
+            weights = [la.weight(i)["on"] for i in range(n)]
+            la.flush()
+            out += la.decisions()
+        finally:
+            la.close()
+        return {d["i_frame"]: d for d in out}, weights
+
+    fake, w_fake = run(weightp=0)
+    real, w_real = run(weightp=2)
+    none, w_none = run(weightp=0, b_psy=0)
+    assert sum(w_fake) > 0 and w_fake == w_real            # the same analysis as with real weighted prediction
+    assert sum(w_none) == 0
+    # fake and real share the costs (the weight is used in the lookahead either way) ...
+    assert [fake[i]["i_cost_est"] for i in range(n)] == [real[i]["i_cost_est"] for i in range(n)]
+    # ... but only the fake mode hands the gain to the tree finish: offsets differ from the real mode's on weighted frames
+    differ = [i for i in range(n) if not np.array_equal(fake[i]["qp_offset"], real[i]["qp_offset"])]
+    assert differ and all(w_fake[i] for i in differ), (differ, w_fake)
+    # log2_ratio grows by weightdelta = 1 - minscore/origscore > 0 on every MB: the offsets drop by 5 (1 - qcomp) weightdelta
+    i = differ[0]
+    drop = real[i]["qp_offset"] - fake[i]["qp_offset"]
+    assert (drop > 0).all() and np.allclose(drop, drop[0], atol=1e-5) and 0 < drop[0] < 2.0 * 0.5

@@ -50,6 +50,7 @@ int convert_device_public(cudaStream_t st, int out_csp, int colmatrix, int fullr
 #define AUTO_OR_I(t) ((t) == T_AUTO || IS_I(t))
 #define AUTO_OR_B(t) ((t) == T_AUTO || IS_B(t))
 #define COST_MAX64 (1ULL << 60)
+#define WEIGHTP_FAKE (-1)      // X264_WEIGHTP_FAKE of x264.h
 #define PENDING (-2)
 
 #define ME_SIDE 2
@@ -515,6 +516,8 @@ static int weights_analyse(La *la, Frame *fenc, Frame *ref)
     while (mindenom > 0 && !(minscale & 1)) { mindenom--; minscale >>= 1; }
     if (!found || (minscale == 1 << mindenom && minoff == 0) || (float)minscore / origscore > 0.998f) return 0;
     fenc->weight = WeightDev{1, minscale, mindenom, minoff};
+    // X264_WEIGHTP_FAKE: what the weight gained is kept for macroblock_tree_finish
+    if (la->p.weightp == WEIGHTP_FAKE) fenc->weighted_cost_delta[fenc->i_frame - ref->i_frame - 1] = (float)minscore / origscore;
     // x264_weight_scale_plane: the whole padded plane 0 of the reference
     { ProfScope ps(la, K_WEIGHT); if (launch_weight_plane(la->st, la->g, la->d_weight_buf, ref->lowres, fenc->weight) < 0) return -1; }
     la->n_launch++;
@@ -1352,6 +1355,39 @@ static int decide_and_shift(La *la)
     return la->fail ? -1 : 0;
 }
 
+// [x264] x264_adaptive_quant_frame + x264_frame_init_lowres of frame f from the converted planes
+// (device, encoder csp).  NV12 sessions hand the interleaved chroma plane to the AQ kernel, which
+// reads U and V out of it: libx264 computes the same 4:2:0 energies on its internal NV12 frame.
+static int frame_prep(La *la, Frame *f, const x264vfw_cuda_image_t &planes)
+{
+    const int w = la->p.width, hgt = la->p.height;
+    // ---- [x264] x264_adaptive_quant_frame ----
+    const bool planar_yuv = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_I422 || la->out_csp == X264VFW_CUDA_OUT_I444;
+    const bool nv12 = la->out_csp == X264VFW_CUDA_OUT_NV12;
+    const bool aq_on = la->p.aq_mode != 0 && la->p.aq_strength != 0;
+    AqJob aq;
+    aq.y = planes.plane[0]; aq.y_stride = planes.i_stride[0];
+    aq.u = planar_yuv || nv12 ? planes.plane[1] : nullptr; aq.v = planar_yuv ? planes.plane[2] : nv12 ? planes.plane[1] + 1 : nullptr;
+    aq.c_stride = planes.i_stride[1]; aq.c_step = nv12 ? 2 : 1;
+    aq.chroma_format = planar_yuv ? la->p.chroma_format : nv12 ? 1 : 0;
+    aq.aq_on = aq_on; aq.strength = la->p.aq_strength * 1.0397f;
+    aq.aq_mode = la->p.aq_mode; aq.aq_strength = la->p.aq_strength;
+    aq.qp_offset = f->qp_offset; aq.qp_offset_aq = f->qp_offset_aq; aq.inv_qscale = f->inv_qscale;
+    aq.stats = f->stats; aq.log2_lut = la->d_log2_lut; aq.exp2_lut = la->d_exp2_lut;
+    { ProfScope ps(la, K_AQ); if (launch_aq(la->st, la->g, aq) < 0) return -1; }
+    XV_CUDA_OK(cudaMemcpyAsync(f->h_stats, f->stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, la->st));
+    XV_CUDA_OK(cudaEventRecord(f->ev_stats, la->st));
+    // ---- [x264] x264_frame_init_lowres ----
+    LowresJob lj;
+    lj.y = planes.plane[0]; lj.y_stride = planes.i_stride[0]; lj.w = w; lj.h = hgt; lj.dst = f->lowres;
+    lj.luma_w = la->g.luma_w; lj.luma_h = la->g.luma_h; lj.lw = la->g.lw; lj.lh = la->g.lh;
+    lj.lstride = la->g.lstride; lj.lplane_bytes = la->g.lplane; lj.lorigin = la->g.lorigin;
+    lj.src_frame_bytes = 0; lj.dst_frame_bytes = 0;
+    { ProfScope ps(la, K_LOWRES); if (launch_lowres_init(la->st, lj, 1) < 0) return -1; }
+    la->n_launch += 2;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Session worker.  put_frame only moves the caller's buffers (H2D, conversion, D2H on the I/O
 // stream) and queues the frame; everything that touches the lookahead state -- frame slot, AQ,
@@ -1372,28 +1408,7 @@ static int process_frame(La *la, Frame *f, const x264vfw_cuda_image_t &planes, c
         if (cudaEventQuery(ev_csp) != cudaSuccess) { const double t0 = now_s(); if (wait_event(la, ev_csp) < 0) return -1; la->t_csp_wait += now_s() - t0; }
         XV_CUDA_OK(cudaStreamWaitEvent(la->st, ev_csp, 0));
     }
-    // ---- [x264] x264_adaptive_quant_frame ----
-    const bool planar_yuv = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_I422 || la->out_csp == X264VFW_CUDA_OUT_I444;
-    const bool aq_on = la->p.aq_mode != 0 && la->p.aq_strength != 0;
-    AqJob aq;
-    aq.y = planes.plane[0]; aq.y_stride = planes.i_stride[0];
-    aq.u = planar_yuv ? planes.plane[1] : nullptr; aq.v = planar_yuv ? planes.plane[2] : nullptr; aq.c_stride = planes.i_stride[1];
-    aq.chroma_format = planar_yuv ? la->p.chroma_format : 0;
-    aq.aq_on = aq_on; aq.strength = la->p.aq_strength * 1.0397f;
-    aq.aq_mode = la->p.aq_mode; aq.aq_strength = la->p.aq_strength;
-    aq.qp_offset = f->qp_offset; aq.qp_offset_aq = f->qp_offset_aq; aq.inv_qscale = f->inv_qscale;
-    aq.stats = f->stats; aq.log2_lut = la->d_log2_lut; aq.exp2_lut = la->d_exp2_lut;
-    { ProfScope ps(la, K_AQ); if (launch_aq(la->st, la->g, aq) < 0) return -1; }
-    XV_CUDA_OK(cudaMemcpyAsync(f->h_stats, f->stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, la->st));
-    XV_CUDA_OK(cudaEventRecord(f->ev_stats, la->st));
-    // ---- [x264] x264_frame_init_lowres ----
-    LowresJob lj;
-    lj.y = planes.plane[0]; lj.y_stride = planes.i_stride[0]; lj.w = w; lj.h = hgt; lj.dst = f->lowres;
-    lj.luma_w = la->g.luma_w; lj.luma_h = la->g.luma_h; lj.lw = la->g.lw; lj.lh = la->g.lh;
-    lj.lstride = la->g.lstride; lj.lplane_bytes = la->g.lplane; lj.lorigin = la->g.lorigin;
-    lj.src_frame_bytes = 0; lj.dst_frame_bytes = 0;
-    { ProfScope ps(la, K_LOWRES); if (launch_lowres_init(la->st, lj, 1) < 0) return -1; }
-    la->n_launch += 2;
+    if (frame_prep(la, f, planes) < 0) return -1;
     XV_CUDA_OK(cudaEventRecord(ev_free, la->st));           // the planes may be overwritten again
     {   // every frame's intra costs are needed sooner or later and only depend on its lowres plane
         IntraJob ij;
@@ -1498,15 +1513,15 @@ int x264vfw_cuda_la_params_preset(x264vfw_cuda_la_params *p, const char *preset,
         p->me_method = 2; p->subme = 9; p->frame_reference = 8; p->b_adapt = 2; p->rc_lookahead = 60;
     } else if (!strcmp(preset, "veryslow")) {
         p->me_method = 2; p->subme = 10; p->me_range = 24; p->frame_reference = 16; p->b_adapt = 2; p->bframes = 8; p->rc_lookahead = 60;
+    } else if (!strcmp(preset, "placebo")) {
+        // config.c:1493 / [x264] x264_param_apply_preset: bframes 16, b-adapt 2, me tesa, merange 24, ref 16, subme 11, rc-lookahead 60
+        p->me_method = 4; p->subme = 11; p->me_range = 24; p->frame_reference = 16; p->b_adapt = 2; p->bframes = 16; p->rc_lookahead = 60;
     } else { set_error("unknown preset %s", preset); return -1; }
     return 0;
 }
 
-int x264vfw_cuda_la_params_tune(x264vfw_cuda_la_params *p, const char *tune)
+static int apply_one_tune(x264vfw_cuda_la_params *p, const char *tune)
 {
-    // [x264] x264_param_apply_tune reduced to the fields the lookahead reads (the tunings x264vfw
-    // offers in its configuration dialog, config.c "Tuning"); apply after the preset
-    if (!p || !tune) return -1;
     if (!strcmp(tune, "film") || !strcmp(tune, "none") || !*tune) {
     } else if (!strcmp(tune, "animation")) {
         p->frame_reference = p->frame_reference > 1 ? p->frame_reference * 2 : 1;
@@ -1527,6 +1542,27 @@ int x264vfw_cuda_la_params_tune(x264vfw_cuda_la_params *p, const char *tune)
         p->frame_reference = p->frame_reference > 1 ? p->frame_reference * 2 : 1;
         p->aq_strength = 1.3f;
     } else { set_error("unknown tune %s", tune); return -1; }
+    return 0;
+}
+
+int x264vfw_cuda_la_params_tune(x264vfw_cuda_la_params *p, const char *tune)
+{
+    // [x264] x264_param_apply_tune reduced to the fields the lookahead reads (the tunings x264vfw
+    // offers in its configuration dialog, config.c "Tuning"); apply after the preset.  Like upstream
+    // the string may hold several names separated by ',', '.', '/', '-', '+' or blanks -- the
+    // reference passes e.g. "film,fastdecode,zerolatency" (codec.c:1430-1445).
+    if (!p || !tune) return -1;
+    char buf[128];
+    size_t n = strlen(tune);
+    if (n >= sizeof(buf)) { set_error("tune string too long"); return -1; }
+    memcpy(buf, tune, n + 1);
+    char *save = nullptr;
+    int seen = 0;
+    for (char *t = strtok_r(buf, ",./-+ ", &save); t; t = strtok_r(nullptr, ",./-+ ", &save)) {
+        if (apply_one_tune(p, t) < 0) return -1;
+        seen++;
+    }
+    if (!seen && apply_one_tune(p, "") < 0) return -1;
     if (p->bframes > BMAX) p->bframes = BMAX;
     return 0;
 }
@@ -1551,11 +1587,28 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (p.rc_lookahead > LMAX) p.rc_lookahead = LMAX;
     if (p.keyint_min <= 0) { int fps = p.fps_num / (p.fps_den > 0 ? p.fps_den : 1); p.keyint_min = p.keyint_max / 10 < fps ? p.keyint_max / 10 : fps; }
     if (p.chroma_format < 0 || p.chroma_format > 3) { set_error("bad chroma_format"); delete la; return -1; }
+    // [x264] validate_parameters: weightp off + mb-tree + psy => X264_WEIGHTP_FAKE: the lookahead still
+    // analyses (and uses) luma weights and records f_weighted_cost_delta for macroblock_tree_finish
+    if (!p.weightp && p.b_mbtree && p.b_psy) p.weightp = WEIGHTP_FAKE;
+    // [x264] macroblock_tree has a separate extrapolation branch for rc-lookahead 0 (no BASELINE
+    // configuration uses it; the presets that set rc-lookahead 0 also switch mb-tree off): not
+    // restated, so the combination is refused instead of answered with different qp offsets
+    if (p.b_mbtree && p.rc_lookahead <= 0) { set_error("mb-tree with rc-lookahead 0 (lookaheadless mb-tree) is not supported: set rc_lookahead >= 1 or b_mbtree = 0"); delete la; return -1; }
     if (p.aq_mode < 0 || p.aq_mode > 3) { set_error("bad aq_mode %d (0 off, 1 variance, 2 auto-variance, 3 auto-variance biased)", p.aq_mode); delete la; return -1; }
     la->device = device; la->in_csp = in_csp; la->out_csp = out_csp; la->colmatrix = colmatrix; la->fullrange = fullrange;
     la->keep_frames = keep_frames;
     if (((in_csp & X264VFW_CUDA_CSP_MASK) == X264VFW_CUDA_CSP_YUYV || (in_csp & X264VFW_CUDA_CSP_MASK) == X264VFW_CUDA_CSP_UYVY) && out_csp == X264VFW_CUDA_OUT_I444)
         la->ext = X264VFW_CUDA_EXT_422_TO_I444;
+    // "RGB24/32 -> NV12" (BASELINE config 3) is the documented extension conversion as well (csp.c:490-492 has no such pair)
+    if (((in_csp & X264VFW_CUDA_CSP_MASK) == X264VFW_CUDA_CSP_BGR || (in_csp & X264VFW_CUDA_CSP_MASK) == X264VFW_CUDA_CSP_BGRA) && out_csp == X264VFW_CUDA_OUT_NV12)
+        la->ext = X264VFW_CUDA_EXT_RGB_TO_NV12;
+    // Kept-RGB sessions (codec.c:293-297 -> X264_CSP_BGR/BGRA): libx264 analyses the G plane of its internal
+    // planar GBR frame with 4:4:4 AQ energies; that frame is not built here, so refuse instead of analysing the
+    // packed bytes as if they were luma.
+    if (out_csp == X264VFW_CUDA_OUT_BGR || out_csp == X264VFW_CUDA_OUT_BGRA) {
+        set_error("lookahead sessions on kept-RGB encoder formats (X264_CSP_BGR/BGRA) are not supported: convert to a YUV encoder csp");
+        delete la; return -1;
+    }
     if (const char *e = getenv("X264VFW_CUDA_DECIDE_LAG")) { la->decide_lag = atoi(e); if (la->decide_lag < 0) la->decide_lag = 0; if (la->decide_lag > 4) la->decide_lag = 4; }
     if (const char *e = getenv("X264VFW_CUDA_SPECULATE")) la->speculate = atoi(e) != 0;
     if (const char *e = getenv("X264VFW_CUDA_SPEC_THRESHOLD")) la->spec_threshold = atof(e);
@@ -1758,6 +1811,11 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     x264vfw_cuda_image_t planes = la->planes_img;           // device, tight, encoder csp
     const bool host_src = !src_on_device && in != X264VFW_CUDA_CSP_NONE;
     const bool borrowed = conv_pic || !src_on_device;
+    // A device source is borrowed for the call like a host one (src_on_device == 1: its last reader, the
+    // conversion or the plane copy, has finished when the call returns) unless the caller declares it
+    // RESIDENT (src_on_device == 2: it stays unmodified until x264vfw_cuda_la_flush / _close, e.g. a clip
+    // that lives in HBM) -- then nothing waits.
+    const bool wait_dev_src = src_on_device == 1 && !conv_pic;
     auto chroma_rows = [&](int csp_is_420, int i) { return (i && csp_is_420) ? hgt / 2 : hgt; };
 
     if (borrowed && !la->st_io) {
@@ -1827,6 +1885,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
             { ProfScope ps(la, K_CSP, st1); if (convert_device_public(st1, la->out_csp, la->colmatrix, la->fullrange, la->ext, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
             la->n_launch++;
         }
+        if (!(borrowed || async)) XV_CUDA_OK(cudaEventRecord(ev_csp, st1));      // device source on the main stream
         if (borrowed || async) {
             XV_CUDA_OK(cudaEventRecord(ev_csp, la->st_io));
             if (iop) cudaEventRecord(la->io_ev[3], la->st_io);
@@ -1864,6 +1923,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         la->n_put++;
         la->t_put += now_s() - t_begin;
         if (borrowed) { const double t0 = now_s(); if (wait_event(la, la->ev_io) < 0) return -1; la->t_io += now_s() - t0; }
+        else if (wait_dev_src) { const double t0 = now_s(); if (wait_event(la, ev_csp) < 0) return -1; la->t_io += now_s() - t0; }
         if (borrowed && la->d_me_stats && la->io_ev[0]) {
             for (int k = 0; k < 4; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, la->io_ev[k], la->io_ev[k + 1]) == cudaSuccess) la->io_ms[k] += ms; }
             la->io_n++;
@@ -1885,29 +1945,8 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     if (!borrowed) { if (stage1() < 0) return -1; }
     else XV_CUDA_OK(cudaStreamWaitEvent(la->st, la->ev_csp, 0));
 
-    // ---- 4. [x264] x264_adaptive_quant_frame ----
-    const bool planar_yuv = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_I422 || la->out_csp == X264VFW_CUDA_OUT_I444;
-    const bool aq_on = la->p.aq_mode != 0 && la->p.aq_strength != 0;
-    AqJob aq;
-    aq.y = planes.plane[0]; aq.y_stride = planes.i_stride[0];
-    aq.u = planar_yuv ? planes.plane[1] : nullptr; aq.v = planar_yuv ? planes.plane[2] : nullptr; aq.c_stride = planes.i_stride[1];
-    aq.chroma_format = planar_yuv ? la->p.chroma_format : 0;
-    aq.aq_on = aq_on; aq.strength = la->p.aq_strength * 1.0397f;
-    aq.aq_mode = la->p.aq_mode; aq.aq_strength = la->p.aq_strength;
-    aq.qp_offset = f->qp_offset; aq.qp_offset_aq = f->qp_offset_aq; aq.inv_qscale = f->inv_qscale;
-    aq.stats = f->stats; aq.log2_lut = la->d_log2_lut; aq.exp2_lut = la->d_exp2_lut;
-    { ProfScope ps(la, K_AQ); if (launch_aq(la->st, la->g, aq) < 0) return -1; }
-    XV_CUDA_OK(cudaMemcpyAsync(f->h_stats, f->stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, la->st));
-    XV_CUDA_OK(cudaEventRecord(f->ev_stats, la->st));
-
-    // ---- 5. [x264] x264_frame_init_lowres ----
-    LowresJob lj;
-    lj.y = planes.plane[0]; lj.y_stride = planes.i_stride[0]; lj.w = w; lj.h = hgt; lj.dst = f->lowres;
-    lj.luma_w = la->g.luma_w; lj.luma_h = la->g.luma_h; lj.lw = la->g.lw; lj.lh = la->g.lh;
-    lj.lstride = la->g.lstride; lj.lplane_bytes = la->g.lplane; lj.lorigin = la->g.lorigin;
-    lj.src_frame_bytes = 0; lj.dst_frame_bytes = 0;
-    { ProfScope ps(la, K_LOWRES); if (launch_lowres_init(la->st, lj, 1) < 0) return -1; }
-    la->n_launch += 2;
+    // ---- 4./5. [x264] x264_adaptive_quant_frame, x264_frame_init_lowres ----
+    if (frame_prep(la, f, planes) < 0) return -1;
     XV_CUDA_OK(cudaEventRecord(la->ev_planes_free, la->st));
     la->planes_busy = true;
 
@@ -1923,6 +1962,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     la->t_decide += t_dec;
     la->t_put += (la->decide_lag == 0 ? t_mid - t_begin : now_s() - t_begin - t_dec);
     if (borrowed) { const double t0 = now_s(); if (wait_event(la, la->ev_io) < 0) return -1; la->t_io += now_s() - t0; }
+    else if (wait_dev_src) { const double t0 = now_s(); if (wait_event(la, ev_csp) < 0) return -1; la->t_io += now_s() - t0; }
     if (borrowed && la->d_me_stats && la->io_ev[0]) {
         for (int k = 0; k < 4; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, la->io_ev[k], la->io_ev[k + 1]) == cudaSuccess) la->io_ms[k] += ms; }
         la->io_n++;

@@ -47,22 +47,31 @@ __device__ __forceinline__ int dev_exp2fix8(const uint8_t *lut, float x)
     return (lut[i & 63] + 256) << (i >> 6) >> 8;
 }
 
-// sum and sum of squares of rows [ya, yb) of the bw x bh block at (x0, y0)
+// sum and sum of squares of rows [ya, yb) of the bw x bh block at (x0, y0); samples are `step`
+// bytes apart (2 = one component of an interleaved NV12 chroma plane)
 __device__ __forceinline__ void block_sums_dev(const uint8_t *p, int stride, int pw, int ph, int x0, int y0,
-                                               int bw, int ya, int yb, uint32_t &sum, uint32_t &ssd)
+                                               int bw, int ya, int yb, uint32_t &sum, uint32_t &ssd, int step = 1)
 {
     sum = 0; ssd = 0;
     const bool fast = (x0 + bw <= pw) && (((uintptr_t)p | (unsigned)stride) & 15) == 0 && (x0 & 15) == 0 && (bw & 7) == 0;
+    // interleaved pair: p points at the component's first byte (U: even, V: odd address)
+    const bool fast2 = step == 2 && (x0 + bw <= pw) && ((((uintptr_t)p & ~(uintptr_t)1) | (unsigned)stride) & 15) == 0 && (x0 & 7) == 0 && bw == 8;
+    const unsigned sh2 = ((uintptr_t)p & 1) * 8;
     for (int y = ya; y < yb; y++) {
         const uint8_t *r = p + (size_t)min(y0 + y, ph - 1) * stride;
-        if (fast) {
+        if (step == 1 && fast) {
             for (int x = 0; x < bw; x += 8) {
                 uint2 v = *(const uint2 *)(r + x0 + x);
                 sum = __dp4a(v.x, 0x01010101u, sum); sum = __dp4a(v.y, 0x01010101u, sum);
                 ssd = __dp4a(v.x, v.x, ssd); ssd = __dp4a(v.y, v.y, ssd);
             }
+        } else if (fast2) {
+            const uint4 v = *(const uint4 *)((const uint8_t *)((uintptr_t)r & ~(uintptr_t)1) + 2 * x0);
+            const uint32_t a = (v.x >> sh2) & 0x00ff00ffu, b = (v.y >> sh2) & 0x00ff00ffu, c = (v.z >> sh2) & 0x00ff00ffu, d = (v.w >> sh2) & 0x00ff00ffu;
+            sum = __dp4a(a, 0x01010101u, sum); sum = __dp4a(b, 0x01010101u, sum); sum = __dp4a(c, 0x01010101u, sum); sum = __dp4a(d, 0x01010101u, sum);
+            ssd = __dp4a(a, a, ssd); ssd = __dp4a(b, b, ssd); ssd = __dp4a(c, c, ssd); ssd = __dp4a(d, d, ssd);
         } else {
-            for (int x = 0; x < bw; x++) { uint32_t v = r[min(x0 + x, pw - 1)]; sum += v; ssd += v * v; }
+            for (int x = 0; x < bw; x++) { uint32_t v = r[min(x0 + x, pw - 1) * step]; sum += v; ssd += v * v; }
         }
     }
 }
@@ -85,8 +94,8 @@ aq_kernel(LaGeom g, AqJob job)
         const int mx = idx % g.mb_w, my = idx / g.mb_w;
         block_sums_dev(job.y, job.y_stride, w, h, 16 * mx, 16 * my, 16, part * 16 / AQ_PARTS, (part + 1) * 16 / AQ_PARTS, s[0], q[0]);
         if (cf) {
-            block_sums_dev(job.u, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, part * cbh / AQ_PARTS, (part + 1) * cbh / AQ_PARTS, s[1], q[1]);
-            block_sums_dev(job.v, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, part * cbh / AQ_PARTS, (part + 1) * cbh / AQ_PARTS, s[2], q[2]);
+            block_sums_dev(job.u, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, part * cbh / AQ_PARTS, (part + 1) * cbh / AQ_PARTS, s[1], q[1], job.c_step);
+            block_sums_dev(job.v, job.c_stride, cw, ch, cbw * mx, cbh * my, cbw, part * cbh / AQ_PARTS, (part + 1) * cbh / AQ_PARTS, s[2], q[2], job.c_step);
         }
     }
 #pragma unroll

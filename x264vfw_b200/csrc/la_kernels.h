@@ -18,6 +18,7 @@ struct WeightDev { int on, scale, denom, offset; };
 // ---- adaptive quant statistics ([x264] x264_adaptive_quant_frame) -------------------------
 struct AqJob {
     const uint8_t *y, *u, *v; int y_stride, c_stride;
+    int c_step;                   // bytes between chroma samples: 1 planar, 2 interleaved (NV12: v = u + 1)
     int chroma_format;            // 1: 4:2:0, 2: 4:2:2, 3: 4:4:4; 0: luma only
     int aq_on; float strength;    // strength: aq-mode 1 (already * 1.0397)
     int aq_mode; float aq_strength; // aq-mode 2 / 3 (auto-variance): raw rc.f_aq_strength

@@ -18,7 +18,17 @@ class _Stream(C.Structure):
                 ("in_csp", C.c_int), ("out_csp", C.c_int), ("width", C.c_int), ("height", C.c_int),
                 ("conv", C.POINTER(C.c_void_p)), ("n_conv", C.c_int),
                 ("pos", C.c_long), ("decided", C.c_long), ("checksum", C.c_double),
-                ("mb_count", C.c_int), ("error", C.c_int), ("qp", C.c_void_p), ("qp_aq", C.c_void_p), ("count", C.c_int)]
+                ("mb_count", C.c_int), ("error", C.c_int), ("qp", C.c_void_p), ("qp_aq", C.c_void_p), ("count", C.c_int),
+                ("log", C.c_void_p), ("log_cap", C.c_int), ("log_n", C.c_int)]
+
+
+class _Decision(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("i_frame", "i_type", "b_keyframe", "i_bframes", "i_cost_est", "i_cost_est_aq",
+                                       "i_intra_mbs", "mb_count")]
+
+
+class _LogRec(C.Structure):
+    _fields_ = [("d", _Decision), ("qp_fnv", C.c_uint64), ("qp_aq_fnv", C.c_uint64)]
 
 
 def _load():
@@ -28,6 +38,8 @@ def _load():
     lib.harness_run_streams.restype = C.c_int
     lib.harness_run_streams.argtypes = [C.POINTER(_Stream), C.c_int, C.c_int]
     lib.harness_stream_free.argtypes = [C.POINTER(_Stream)]
+    lib.harness_flush_streams.restype = C.c_int
+    lib.harness_flush_streams.argtypes = [C.POINTER(_Stream), C.c_int]
     return lib
 
 
@@ -36,7 +48,10 @@ class StreamSet:
     addresses (on_device) or uint8 numpy buffers (host); conv[s]: optional list of host numpy
     buffers that receive conv_pic."""
 
-    def __init__(self, sessions, frames, on_device, conv=None):
+    def __init__(self, sessions, frames, on_device, conv=None, log_decisions=0):
+        """on_device: 0 host buffers, 1 device buffers borrowed for the call, 2 device buffers that stay
+        resident and unmodified (x264vfw_cuda.h: X264VFW_CUDA_SRC_*).  log_decisions: keep up to that many
+        decisions per stream (frame, type, costs, FNV-1a-64 of the qp offset arrays) for parity tests."""
         self.lib = _load()
         self.n = len(sessions)
         self.arr = (_Stream * self.n)()
@@ -57,12 +72,37 @@ class StreamSet:
                 self._keep.append(ca)
                 st.conv = ca
                 st.n_conv = len(conv[s])
+            if log_decisions:
+                buf = (_LogRec * log_decisions)()
+                self._keep.append(buf)
+                st.log = C.cast(buf, C.c_void_p)
+                st.log_cap = log_decisions
+        self._logs = log_decisions
 
     def run(self, count: int) -> None:
         """Feed `count` frames to every stream concurrently (native threads; returns when all did)."""
         if self.lib.harness_run_streams(self.arr, self.n, count) < 0:
             from ._lib import last_error
             raise RuntimeError("harness_run_streams failed: " + last_error())
+
+    def flush(self) -> None:
+        """x264vfw_cuda_la_flush on every session, decisions drained into the counters / the log."""
+        if self.lib.harness_flush_streams(self.arr, self.n) < 0:
+            from ._lib import last_error
+            raise RuntimeError("harness_flush_streams failed: " + last_error())
+
+    def log(self, s):
+        """Logged decisions of stream s in coded order: dicts with the decision fields and the two hashes."""
+        st = self.arr[s]
+        recs = C.cast(st.log, C.POINTER(_LogRec))
+        out = []
+        for i in range(st.log_n):
+            r = recs[i]
+            d = {n: int(getattr(r.d, n)) for n, _ in _Decision._fields_}
+            d["qp_fnv"] = "%016x" % r.qp_fnv
+            d["qp_aq_fnv"] = "%016x" % r.qp_aq_fnv
+            out.append(d)
+        return out
 
     @property
     def decided(self):

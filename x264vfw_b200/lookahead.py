@@ -213,20 +213,17 @@ class Lookahead:
                     put_us=int(c[4]), decide_us=int(c[5]), sync_us=int(c[6]), frames=int(c[7]))
 
 
-def smoke_check(ctx=None):
-    """Tiny end-to-end lookahead run on cuda:0; __graft_entry__.smoke() checks the returned
-    decisions against its CPU checker."""
-    from .clipgen import SyntheticClip
-    w, h = 128, 96
-    clip = SyntheticClip(w, h, n_frames=12, cuts=(7,), flash=None)
+def smoke_check(frames, w=128, h=96):
+    """Tiny end-to-end lookahead run on cuda:0 over packed bottom-up BGRA frames;
+    __graft_entry__.smoke() checks the returned decisions against its CPU checker."""
     p = params_preset("medium", w, h, rc_lookahead=6, keyint_max=50, keyint_min=2)
     la = Lookahead(p, in_csp=_csp.X264VFW_CSP_BGRA | _csp.X264VFW_CSP_VFLIP, device=0)
     out = []
-    for n in range(12):
-        la.put_frame(clip.packed(n, "bgra"))
+    for f in frames:
+        la.put_frame(f)
         out += la.decisions()
     la.flush()
     out += la.decisions()
     la.close()
-    assert sorted(d["i_frame"] for d in out) == list(range(12))
+    assert sorted(d["i_frame"] for d in out) == list(range(len(frames)))
     return out
