@@ -326,6 +326,13 @@ void x264vfw_cuda_la_counters( x264vfw_cuda_la *la, uint64_t out[8] );
  * on/off and resets the totals, -1 only reads. */
 int x264vfw_cuda_la_profile( x264vfw_cuda_la *la, int enable, double ms[16], uint64_t count[16] );
 
+/* Work counters of the search kernels and the mb-tree, counted on the device while x264vfw_cuda_la_profile
+ * is enabled (reset when it is switched on): [0] MBs whose speculative result the ordered verification kept,
+ * [1] MBs it searched again in order, [2..5] MBs searched by parallel pass 0..3, [6] SAD 8x8 evaluations,
+ * [7] SATD 8x8 evaluations (all search kernels), [8] mb-tree steps run by tree_chain_kernel, [9] mb-tree walks,
+ * [10] searches launched speculatively, [11] searches launched on demand, [12] on-demand launches.  Returns 0 / -1. */
+int x264vfw_cuda_la_stats( x264vfw_cuda_la *la, uint64_t out[16] );
+
 const char *x264vfw_cuda_last_error( void );
 /* "x264vfw_cuda <version> sm_100a"; also proves the library loaded. */
 const char *x264vfw_cuda_version( void );

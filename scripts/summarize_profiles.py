@@ -48,6 +48,60 @@ def raw_metrics(rep, dst, title):
                     f.write(f"{k:78s} {r[hdr.index(k)]} {rows[1][hdr.index(k)]}\n")
 
 
+def metrics_json(tag):
+    """profiles/ncu_metrics_<tag>.json: the static per-kernel numbers bench.py quotes (instructions per MB search,
+    DRAM bytes per search) computed from the captured launches, never typed in."""
+    import json
+    out = {}
+    for kern in ("me_pass_kernel", "me_verify_kernel", "tree_chain_kernel"):
+        rep = os.path.join(GP, f"{kern}_{tag}.ncu-rep")
+        if not os.path.exists(rep):
+            continue
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr = rows[0]
+
+        def col(r, k):
+            try:
+                return float(r[hdr.index(k)].replace(",", ""))
+            except Exception:
+                return None
+
+        def to_bytes(r, k):
+            v, unit = col(r, k), rows[1][hdr.index(k)]
+            return None if v is None else v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+        launches = []
+        for r in rows[2:]:
+            launches.append({"grid": col(r, "launch__grid_size"), "inst": col(r, "smsp__inst_executed.sum"),
+                             "dur_us": col(r, "gpu__time_duration.sum"), "issue_pct": col(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                             "warps_active_pct": col(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                             "dram": (to_bytes(r, "dram__bytes_read.sum") or 0) + (to_bytes(r, "dram__bytes_write.sum") or 0),
+                             "regs": col(r, "launch__registers_per_thread")})
+        if kern == "me_pass_kernel":
+            big = max(launches, key=lambda l: l["inst"] or 0)          # pass 0 of its batch: every MB is searched
+            searches = round(big["grid"] / 2040)
+            out[kern] = {"captured": "pass 0 of a %d-search batch at 1080p (scripts/profile_la.py, kernel alone on the GPU)" % searches,
+                         "warp_inst": big["inst"], "mb_searches": searches * 8160, "warp_inst_per_mb_search": big["inst"] / (searches * 8160),
+                         "duration_us": big["dur_us"], "issue_active_pct": big["issue_pct"], "warps_active_pct": big["warps_active_pct"],
+                         "registers": big["regs"], "dram_bytes_per_search": big["dram"] / searches,
+                         "other_passes": [{"warp_inst": l["inst"], "duration_us": l["dur_us"]} for l in launches if l is not big]}
+        elif kern == "me_verify_kernel":
+            l = launches[0]
+            searches = round(l["grid"] / 5) if l["grid"] and l["grid"] >= 5 else 1
+            out[kern] = {"captured": "verification of a batch (grid %d) at 1080p" % int(l["grid"] or 0), "warp_inst": l["inst"], "duration_us": l["dur_us"],
+                         "issue_active_pct": l["issue_pct"], "registers": l["regs"], "searches": searches, "dram_bytes_per_search": l["dram"] / max(1, searches),
+                         "all": [{"grid": x["grid"], "duration_us": x["dur_us"], "warp_inst": x["inst"]} for x in launches]}
+        else:
+            l = launches[0]
+            out[kern] = {"warp_inst": l["inst"], "duration_us": l["dur_us"], "issue_active_pct": l["issue_pct"], "grid": l["grid"], "dram_bytes": l["dram"]}
+    if out:
+        json.dump(out, open(os.path.join(OUT, f"ncu_metrics_{tag}.json"), "w"), indent=1)
+    return out
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
@@ -72,6 +126,14 @@ if __name__ == "__main__":
             ("hpel_c.ncu-rep", f"ncu_hpel_{tag}_v3_compact_loop.txt", "hpel_kernel, one row per loop trip (6 KB loop body), one warp per block; an EXIT inside the loop still waits for the prefetched loads"),
             ("hpel_e.ncu-rep", f"ncu_hpel_{tag}_v4_no_exit.txt", "hpel_kernel without the EXIT in the loop, register double buffer: the copy pre[0]=pre[1] of a register still being loaded holds 25 % of the stall samples"),
             ("hpel_f.ncu-rep", f"ncu_hpel_{tag}.txt", "hpel_kernel as measured at the end of the round: rows prefetched three trips ahead through a per-lane cp.async ring in shared memory; 48 frames of 1920x1088 per launch")]
+    if tag != "r1":
+        jobs = [(f"launches_bench_{tag}.csv", f"launches_bench_{tag}.txt", "bench.py --steps 2 --warmup 3 --streams 2 --frames-per-step 24 --clip-frames 60 --no-e2e --no-cpu-baseline --no-worst-case (launches 4000..8000)")]
+        for src, dst, title in jobs:
+            if os.path.exists(os.path.join(GP, src)):
+                launch_list(os.path.join(GP, src), os.path.join(OUT, dst), title)
+        reps = [(f"{k}_{tag}.ncu-rep", f"ncu_{k.replace('_kernel', '')}_{tag}.txt", f"{k}, scripts/profile_la.py 60 (one 1080p stream, preset medium), kernel alone on the GPU")
+                for k in ("me_pass_kernel", "me_verify_kernel", "tree_chain_kernel", "frontend_kernel", "intra_kernel", "finalize_kernel")]
+        print(metrics_json(tag))
     for src, dst, title in reps:
         if os.path.exists(os.path.join(GP, src)):
             raw_metrics(os.path.join(GP, src), os.path.join(OUT, dst), title)

@@ -7,8 +7,9 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
-REF_CSP_SO = os.path.join(ROOT, "oracle", "_ref", "libref_csp.so")
+# bench.py's CPU arms point these at the -march=native builds made on the box (oracle/Makefile: native)
+ORACLE_SO = os.environ.get("X264VFW_ORACLE_SO") or os.path.join(ROOT, "oracle", "liboracle.so")
+REF_CSP_SO = os.environ.get("X264VFW_REF_CSP_SO") or os.path.join(ROOT, "oracle", "_ref", "libref_csp.so")
 
 
 class OrcImage(C.Structure):

@@ -87,28 +87,48 @@ __device__ __forceinline__ int sad8x8_rows(const uint2 a[8], const uint2 b[8])
 
 __device__ __forceinline__ int px_of(uint2 v, int i) { return (int)(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 0xff); }
 
+// ---- SATD building blocks -------------------------------------------------------------------------------------
+// Row transform of a 4x4 block WITHOUT extracting bytes: coefficient k of the row of differences a - b is
+//   t_k = dp4a(a, H_k) + dp4a(b, -H_k)      (IDP.4A, unsigned pixels x signed Hadamard row)
+// two dot products per coefficient instead of 8 byte extractions, 4 subtractions and 8 butterfly adds per row.
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void hadamard_row4(uint32_t a, uint32_t b, int t[4])
+{
+    t[0] = dp4a_us(a, 0x01010101, dp4a_us(b, (int)0xffffffffu, 0));      // + + + +
+    t[1] = dp4a_us(a, (int)0xffff0101u, dp4a_us(b, 0x0101ffff, 0));      // + + - -
+    t[2] = dp4a_us(a, 0x01ffff01, dp4a_us(b, (int)0xff0101ffu, 0));      // + - - +
+    t[3] = dp4a_us(a, (int)0xff01ff01u, dp4a_us(b, 0x01ff01ff, 0));      // + - + -
+}
+// Column transform + sum of magnitudes of one coefficient column (v0..v3 = that coefficient of the 4 rows), HALVED:
+// |s+t| + |s-t| = 2 max(|s|, |t|), so the last butterfly stage and the final >> 1 of x264_pixel_satd_8x4 fold into
+// two maxima (exact in integers: every pair sum is even).
+__device__ __forceinline__ int hadamard_col4_half(int v0, int v1, int v2, int v3)
+{
+    const int s01 = v0 + v1, e01 = v0 - v1, s23 = v2 + v3, e23 = v2 - v3;
+    return max(abs(s01), abs(s23)) + max(abs(e01), abs(e23));
+}
+// one 4x4 block given its four rows as packed words: SATD contribution already halved
+__device__ __forceinline__ int satd4x4_half(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                            uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3)
+{
+    int t0[4], t1[4], t2[4], t3[4];
+    hadamard_row4(a0, b0, t0); hadamard_row4(a1, b1, t1); hadamard_row4(a2, b2, t2); hadamard_row4(a3, b3, t3);
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) sum += hadamard_col4_half(t0[k], t1[k], t2[k], t3[k]);
+    return sum;
+}
+
 // [x264] x264_pixel_satd_8x4 on rows r0..r0+3
 __device__ __forceinline__ int satd8x4_rows(const uint2 a[8], const uint2 b[8], int r0)
 {
-    int sum = 0;
-#pragma unroll
-    for (int blk = 0; blk < 2; blk++) {
-        int t[4][4];
-#pragma unroll
-        for (int y = 0; y < 4; y++) {
-            uint32_t wa = blk ? a[r0 + y].y : a[r0 + y].x, wb = blk ? b[r0 + y].y : b[r0 + y].x;
-            int d0 = (int)(wa & 0xff) - (int)(wb & 0xff), d1 = (int)((wa >> 8) & 0xff) - (int)((wb >> 8) & 0xff);
-            int d2 = (int)((wa >> 16) & 0xff) - (int)((wb >> 16) & 0xff), d3 = (int)(wa >> 24) - (int)(wb >> 24);
-            int s01 = d0 + d1, e01 = d0 - d1, s23 = d2 + d3, e23 = d2 - d3;
-            t[y][0] = s01 + s23; t[y][1] = s01 - s23; t[y][2] = e01 + e23; t[y][3] = e01 - e23;
-        }
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            int s01 = t[0][x] + t[1][x], e01 = t[0][x] - t[1][x], s23 = t[2][x] + t[3][x], e23 = t[2][x] - t[3][x];
-            sum += abs(s01 + s23) + abs(s01 - s23) + abs(e01 + e23) + abs(e01 - e23);
-        }
-    }
-    return sum >> 1;
+    return satd4x4_half(a[r0].x, a[r0 + 1].x, a[r0 + 2].x, a[r0 + 3].x, b[r0].x, b[r0 + 1].x, b[r0 + 2].x, b[r0 + 3].x) +
+           satd4x4_half(a[r0].y, a[r0 + 1].y, a[r0 + 2].y, a[r0 + 3].y, b[r0].y, b[r0 + 1].y, b[r0 + 2].y, b[r0 + 3].y);
 }
 __device__ __forceinline__ int satd8x8_rows(const uint2 a[8], const uint2 b[8])
 {
@@ -127,21 +147,9 @@ __device__ __forceinline__ int satd_rows4(uint2 fe0, uint2 fe1, uint2 a0, uint2 
     int s[8], d[8];
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const uint32_t f0 = half ? fe0.y : fe0.x, f1 = half ? fe1.y : fe1.x;
-        const uint32_t r0 = half ? a0.y : a0.x, r1 = half ? a1.y : a1.x;
         int t0[4], t1[4];
-        {
-            int e0 = (int)(f0 & 0xff) - (int)(r0 & 0xff), e1 = (int)((f0 >> 8) & 0xff) - (int)((r0 >> 8) & 0xff);
-            int e2 = (int)((f0 >> 16) & 0xff) - (int)((r0 >> 16) & 0xff), e3 = (int)(f0 >> 24) - (int)(r0 >> 24);
-            int s01 = e0 + e1, d01 = e0 - e1, s23 = e2 + e3, d23 = e2 - e3;
-            t0[0] = s01 + s23; t0[1] = s01 - s23; t0[2] = d01 + d23; t0[3] = d01 - d23;
-        }
-        {
-            int e0 = (int)(f1 & 0xff) - (int)(r1 & 0xff), e1 = (int)((f1 >> 8) & 0xff) - (int)((r1 >> 8) & 0xff);
-            int e2 = (int)((f1 >> 16) & 0xff) - (int)((r1 >> 16) & 0xff), e3 = (int)(f1 >> 24) - (int)(r1 >> 24);
-            int s01 = e0 + e1, d01 = e0 - e1, s23 = e2 + e3, d23 = e2 - e3;
-            t1[0] = s01 + s23; t1[1] = s01 - s23; t1[2] = d01 + d23; t1[3] = d01 - d23;
-        }
+        hadamard_row4(half ? fe0.y : fe0.x, half ? a0.y : a0.x, t0);
+        hadamard_row4(half ? fe1.y : fe1.x, half ? a1.y : a1.x, t1);
 #pragma unroll
         for (int k = 0; k < 4; k++) { s[half * 4 + k] = t0[k] + t1[k]; d[half * 4 + k] = t0[k] - t1[k]; }
     }

@@ -122,6 +122,8 @@ struct La {
     int me_rows = 0;         // warps per search in the wavefront kernel
     int me_variant = 1;      // 0: plain wavefront, 1: speculative parallel passes + verification wavefront
     int me_passes = 3;       // parallel passes of the speculative search
+    int me_force_miss = 0;   // diagnostics (X264VFW_CUDA_ME_FORCE_MISS): the verification keeps nothing = cost at a 0 % hit rate
+    uint64_t n_tree_steps = 0, n_tree_walks = 0;
     int *d_me_stats = nullptr;
     int stats_verbose = 0; std::string dbg_jobs; int dbg_prev[8] = {0};
     // searches the decision logic asked for during the current decision, and the ones predicted
@@ -533,6 +535,7 @@ static void me_params_init(La *la, MeParams &mp)
     mp.cost_mv = la->d_cost_mv + la->cost_mv_half;
     mp.rows_in_flight = la->me_rows;
     mp.variant = la->me_variant; mp.npasses = la->me_passes; mp.stats = la->d_me_stats;
+    mp.force_miss = la->me_force_miss;
 }
 
 static void me_add_job(La *la, MeParams &mp, int eng, Frame *fenc, Frame *ref, int list, int dist, const WeightDev *w)
@@ -908,6 +911,7 @@ static int tree_run(La *la)
     LA_CUDA(cudaEventRecord(la->ev_tree[slot], la->st));
     z.clear(); t.clear();
     la->n_launch++;
+    la->n_tree_steps += n; la->n_tree_walks++;
     ProfScope ps(la, K_TREE);
     return launch_tree_chain(la->st, la->g, la->d_tree[slot], (int)n, la->d_log2_lut);
 }
@@ -1618,6 +1622,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_ME_VARIANT")) la->me_variant = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ME_PASSES")) { la->me_passes = atoi(e); if (la->me_passes < 1) la->me_passes = 1; if (la->me_passes > 4) la->me_passes = 4; }
     if (const char *e = getenv("X264VFW_CUDA_ME_GUESS")) la->me_guess = atoi(e);
+    if (const char *e = getenv("X264VFW_CUDA_ME_FORCE_MISS")) la->me_force_miss = atoi(e) != 0;
     if (const char *e = getenv("X264VFW_CUDA_ASYNC")) la->async = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_SYNC")) {      // spin (default) | yield | block | hybrid | hybrid:<microseconds>
         la->yielding = !strcmp(e, "yield");
@@ -1761,13 +1766,13 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     }
     if (la->st) cudaStreamSynchronize(la->st);
     for (int e = 1; e <= ME_SIDE; e++) if (la->st_me[e]) cudaStreamSynchronize(la->st_me[e]);
-    if (la->d_me_stats) {
+    if (la->d_me_stats && getenv("X264VFW_CUDA_STATS")) {
         int v[8] = {0};
         cudaMemcpy(v, la->d_me_stats, sizeof(v), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[x264vfw_cuda] speculative search: kept %d, re-searched in order %d (%.2f%%); searched per pass: %d %d %d %d\n",
                 v[0], v[1], 100.0 * v[1] / (v[0] + v[1] > 0 ? v[0] + v[1] : 1), v[2], v[3], v[4], v[5]);
-        cudaFree(la->d_me_stats);
     }
+    cudaFree(la->d_me_stats);
     prof_resolve(la);
     for (cudaEvent_t e : la->prof.pool) cudaEventDestroy(e);
     for (Frame *f : la->pool) frame_free(f);
@@ -2092,7 +2097,31 @@ int x264vfw_cuda_la_profile(x264vfw_cuda_la *h, int enable, double ms[16], uint6
     if (enable >= 0) {
         la->prof.on = enable != 0;
         for (int i = 0; i < K_N; i++) { la->prof.ms[i] = 0; la->prof.n[i] = 0; }
+        // the search kernels count their work while profiling is on (x264vfw_cuda_la_stats)
+        if (enable && !la->d_me_stats) {
+            XV_CUDA_OK(cudaMalloc((void **)&la->d_me_stats, 8 * sizeof(int)));
+        }
+        if (enable) { XV_CUDA_OK(cudaMemset(la->d_me_stats, 0, 8 * sizeof(int))); la->n_tree_steps = la->n_tree_walks = 0; }
     }
+    return 0;
+}
+
+int x264vfw_cuda_la_stats(x264vfw_cuda_la *h, uint64_t out[16])
+{
+    La *la = (La *)h;
+    if (!la || !out) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    if (worker_join(la) < 0) return -1;
+    if (la_sync(la) < 0) return -1;
+    for (int e = 1; e <= la->me_side; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
+    for (int i = 0; i < 16; i++) out[i] = 0;
+    if (la->d_me_stats) {
+        int v[8];
+        XV_CUDA_OK(cudaMemcpy(v, la->d_me_stats, sizeof(v), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 8; i++) out[i] = (uint64_t)(unsigned)v[i];
+    }
+    out[8] = la->n_tree_steps; out[9] = la->n_tree_walks;
+    out[10] = la->n_spec_jobs; out[11] = la->n_ondemand_jobs; out[12] = la->n_ondemand;
     return 0;
 }
 

@@ -104,25 +104,9 @@ template <int LPS> __device__ __forceinline__ int mvcost2(const Mb<LPS> &m, int 
 // ---- SATD of this lane's rows ([x264] x264_pixel_satd_8x4 per 4 rows: two 4x4 Hadamards) ----
 __device__ __forceinline__ int satd_8x4_regs(const uint2 *a, const uint2 *b)
 {
-    int sum = 0;
-#pragma unroll
-    for (int blk = 0; blk < 2; blk++) {
-        int t[4][4];
-#pragma unroll
-        for (int y = 0; y < 4; y++) {
-            const uint32_t wa = blk ? a[y].y : a[y].x, wb = blk ? b[y].y : b[y].x;
-            const int d0 = (int)(wa & 0xff) - (int)(wb & 0xff), d1 = (int)((wa >> 8) & 0xff) - (int)((wb >> 8) & 0xff);
-            const int d2 = (int)((wa >> 16) & 0xff) - (int)((wb >> 16) & 0xff), d3 = (int)(wa >> 24) - (int)(wb >> 24);
-            const int s01 = d0 + d1, e01 = d0 - d1, s23 = d2 + d3, e23 = d2 - d3;
-            t[y][0] = s01 + s23; t[y][1] = s01 - s23; t[y][2] = e01 + e23; t[y][3] = e01 - e23;
-        }
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            const int s01 = t[0][x] + t[1][x], e01 = t[0][x] - t[1][x], s23 = t[2][x] + t[3][x], e23 = t[2][x] - t[3][x];
-            sum += abs(s01 + s23) + abs(s01 - s23) + abs(e01 + e23) + abs(e01 - e23);
-        }
-    }
-    return sum >> 1;
+    // dp4a row transform + max-folded column transform (la_common.cuh)
+    return satd4x4_half(a[0].x, a[1].x, a[2].x, a[3].x, b[0].x, b[1].x, b[2].x, b[3].x) +
+           satd4x4_half(a[0].y, a[1].y, a[2].y, a[3].y, b[0].y, b[1].y, b[2].y, b[3].y);
 }
 template <int LPS> __device__ __forceinline__ int satd_rows(const Mb<LPS> &m, const uint2 *a)
 {
@@ -323,9 +307,16 @@ __device__ __forceinline__ void sub_load(Mb<LPS> &m, GroupSmem &sm, bool on, int
 // samples waiting for instructions).  The sub-pel part is one loop of two rounds.
 enum { S_PRED, S_RZ, S_HEX1, S_HEXIT, S_SQUARE, S_DIA, S_DONE };
 
+// n_sad / n_satd: 8x8 block metrics evaluated by the warp (counted only when P.stats is set; every lane holds the
+// same totals, the caller adds them once per warp)
+template <int LPS> __device__ __forceinline__ int count_cands(const Mb<LPS> &m, bool a)
+{
+    return __popc(__ballot_sync(FULL, a && (m.gl % LPS) == 0));
+}
 template <int LPS, bool QPRED>
 __device__ __forceinline__ MeResult2 me_search_mb2(Mb<LPS> &m, GroupSmem &sm, const LaGeom &g, const MeParams &P, const bool on,
-                                                   const int mvc[4][2], int i_mvc, int min_sx, int max_sx, int min_sy, int max_sy)
+                                                   const int mvc[4][2], int i_mvc, int min_sx, int max_sx, int min_sy, int max_sy,
+                                                   int &n_sad, int &n_satd)
 {
     const int mv_x_min = min_sx >> 2, mv_x_max = max_sx >> 2, mv_y_min = min_sy >> 2, mv_y_max = max_sy >> 2;
     const int grp = m.slot;
@@ -356,6 +347,7 @@ __device__ __forceinline__ MeResult2 me_search_mb2(Mb<LPS> &m, GroupSmem &sm, co
             }
         }
         active = active && on;
+        if (P.stats) n_sad += count_cands(m, active);
         const int c = cand_qpel<LPS, false>(m, cx, cy, active, false);
         win_commit();
         m.win = sm.win; m.wx0 = wx0; m.wy0 = wy0;
@@ -415,6 +407,7 @@ __device__ __forceinline__ MeResult2 me_search_mb2(Mb<LPS> &m, GroupSmem &sm, co
         else if (st == S_DIA) { mx = bmx + (grp == 2 ? -1 : grp == 3 ? 1 : 0); my = bmy + (grp == 0 ? -1 : grp == 1 ? 1 : 0); tag = grp + 1; a = grp < 4; }
         else if (QPRED && st == S_RZ) { mx = grp == 0 ? bmx : 0; my = grp == 0 ? bmy : 0; a = (grp == 0 && subpel) || (grp == 1 && need_zero); }
         else if (!QPRED && st == S_PRED) { mx = pcx; my = pcy; tag = grp; a = pact; }
+        if (P.stats) n_sad += count_cands(m, a);
         int c = cand_fpel(m, mx, my, a);
         if (!QPRED && st == S_PRED) {
             if (grp == 0) c -= mvcost2(m, mx * 4, my * 4);
@@ -488,6 +481,7 @@ __device__ __forceinline__ MeResult2 me_search_mb2(Mb<LPS> &m, GroupSmem &sm, co
         const int mx = clip3i(m.mvp_x, min_sx + 2, max_sx - 2), my = clip3i(m.mvp_y, min_sy + 2, max_sy - 2);
         const bool want = on && (((mx - bmx) | (my - bmy)) != 0);
         if (__any_sync(FULL, want)) {
+            if (P.stats) n_sad += count_cands(m, want && grp == 0);
             const int c = g_bcast<LPS>(cand_qpel<LPS, false>(m, mx, my, want && grp == 0, false), 0);
             if (want && c < bcost) { bcost = c; bmx = mx; bmy = my; }
         }
@@ -506,6 +500,7 @@ __device__ __forceinline__ MeResult2 me_search_mb2(Mb<LPS> &m, GroupSmem &sm, co
             dx = grp == 3 ? -1 : grp == 4 ? 1 : 0; dy = grp == 1 ? -1 : grp == 2 ? 1 : 0;
             a = on && (grp == 0 || (do_qpel && grp < 5));
         }
+        if (P.stats) { if (round == 1) n_satd += count_cands(m, a); else n_sad += count_cands(m, a); }
         const int c = cand_qpel<LPS, true>(m, bmx + dx, bmy + dy, a, round == 1);
         const int c_s0 = g_bcast<LPS>(c, 0);
         if (round == 0) {
@@ -626,9 +621,11 @@ __device__ __forceinline__ void pass_search_store(const LaGeom &g, const MeParam
     mv_limits(mb_x, mb_y, g.mb_w, g.mb_h, P.mv_range2, min_sx, max_sx, min_sy, max_sy);
 
     int out_mv = 0, out_cost = 0;
+    int n_sad = 0, n_satd = 0;
     bool skip = false;
     const bool ztest = need && !(m.mvp_x | m.mvp_y);
     if (__any_sync(FULL, ztest)) {
+        if (P.stats) { const int n = __popc(__ballot_sync(FULL, ztest && m.gl == 0)); if (P.satd) n_satd += n; else n_sad += n; }
         // fast skip: mbcmp at mv 0 on the UNWEIGHTED plane 0 (every lane scores its rows)
         uint2 a[RPL];
 #pragma unroll
@@ -642,7 +639,7 @@ __device__ __forceinline__ void pass_search_store(const LaGeom &g, const MeParam
     }
     const bool on = need && !skip;
     if (__any_sync(FULL, on)) {
-        MeResult2 r = me_search_mb2<LPS, QPRED>(m, sm, g, P, on, mvc, i_mvc, min_sx, max_sx, min_sy, max_sy);
+        MeResult2 r = me_search_mb2<LPS, QPRED>(m, sm, g, P, on, mvc, i_mvc, min_sx, max_sx, min_sy, max_sy, n_sad, n_satd);
         if (on) {
             int cost = r.cost - (int)__ldg(P.cost_mv);      // remove mvcost from skip mbs
             if (r.mvx | r.mvy) cost += 5;
@@ -653,7 +650,10 @@ __device__ __forceinline__ void pass_search_store(const LaGeom &g, const MeParam
         job.mvs[q.mb_xy] = out_mv;
         job.mv_costs[q.mb_xy] = out_cost;
         job.assumed[q.mb_xy] = in;
-        if (P.stats) atomicAdd(P.stats + 2 + min(pass, 3), 1);
+    }
+    if (P.stats) {     // one set of atomics per warp
+        const int n_mb = __popc(__ballot_sync(FULL, need && m.gl == 0));
+        if (lane == 0) { atomicAdd(P.stats + 2 + min(pass, 3), n_mb); atomicAdd(P.stats + 6, n_sad); atomicAdd(P.stats + 7, n_satd); }
     }
 }
 
@@ -797,7 +797,7 @@ me_verify_kernel(LaGeom g, MeParams P)
     int right_mv = 0;               // final MV of (x+1, y); zero before the first MB
     int c0 = 0, c1 = 0;             // final MVs of the row below at columns x and x+1
     if (has_below) { c1 = below_wait(start_x + 1); c0 = below_wait(start_x); }
-    int n_hit = 0, n_miss = 0;
+    int n_hit = 0, n_miss = 0, n_sad = 0, n_satd = 0;
     unsigned ns = 32;
     while (x >= end_x) {
         // ---- load a chunk: lane i examines MB xi = x - i ----
@@ -828,7 +828,7 @@ me_verify_kernel(LaGeom g, MeParams P)
             const bool below_ok = cond && A.y == in_b && A.z == in_bl && A.w == in_br;
             const int Gr = __shfl_up_sync(FULLM, G, 1);
             const int in_r = has_r ? (lane == p ? rm : Gr) : 0;
-            const bool hit = lane >= p && below_ok && A.x == in_r;
+            const bool hit = lane >= p && below_ok && A.x == in_r && !P.force_miss;
             const unsigned hb = __ballot_sync(FULLM, hit) >> p;
             int n = __ffs(~hb) - 1;
             if (n < 0) n = 32;
@@ -883,10 +883,11 @@ me_verify_kernel(LaGeom g, MeParams P)
                 const int pel = m.pel + m.r0 * g.lstride;
                 const uint2 a[2] = {load8u(job.fref[0] + pel), load8u(job.fref[0] + pel + g.lstride)};
                 const int cz = P.satd ? satd_rows(m, a) : part_sum<4>(sad_rows(m, a));
+                if (P.satd) n_satd++; else n_sad++;
                 if (cz < 64) { skip = true; out_mv = 0; out_cost = cz; }
             }
             if (!skip) {
-                MeResult2 r = me_search_mb2<4, QPRED>(m, sm, g, P, true, mvc, i_mvc, min_sx, max_sx, min_sy, max_sy);
+                MeResult2 r = me_search_mb2<4, QPRED>(m, sm, g, P, true, mvc, i_mvc, min_sx, max_sx, min_sy, max_sy, n_sad, n_satd);
                 int cost = r.cost - (int)__ldg(P.cost_mv);      // remove mvcost from skip mbs
                 if (r.mvx | r.mvy) cost += 5;
                 out_mv = mv_pack(r.mvx, r.mvy); out_cost = cost;
@@ -910,7 +911,7 @@ me_verify_kernel(LaGeom g, MeParams P)
             x -= p; ns = 32;
         } else { __nanosleep(below_local ? 20 : ns); if (ns < 256) ns <<= 1; }
     }
-    if (P.stats && lane == 0) { atomicAdd(P.stats, n_hit); atomicAdd(P.stats + 1, n_miss); }
+    if (P.stats && lane == 0) { atomicAdd(P.stats, n_hit); atomicAdd(P.stats + 1, n_miss); atomicAdd(P.stats + 6, n_sad); atomicAdd(P.stats + 7, n_satd); }
   }
 }
 

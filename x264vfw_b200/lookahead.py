@@ -55,6 +55,8 @@ lib.x264vfw_cuda_la_counters.restype = None
 lib.x264vfw_cuda_la_counters.argtypes = [C.c_void_p, _P(C.c_uint64)]
 
 
+lib.x264vfw_cuda_la_stats.restype = C.c_int
+lib.x264vfw_cuda_la_stats.argtypes = [C.c_void_p, _P(C.c_uint64)]
 lib.x264vfw_cuda_la_profile.restype = C.c_int
 lib.x264vfw_cuda_la_profile.argtypes = [C.c_void_p, C.c_int, _P(C.c_double), _P(C.c_uint64)]
 KERNEL_CLASSES = ("csp", "aq", "lowres", "intra", "me", "finalize", "weights", "mbtree", "me_pass")
@@ -205,6 +207,15 @@ class Lookahead:
         if lib.x264vfw_cuda_la_profile(self.h, enable, ms, n) < 0:
             raise CudaError(last_error())
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+    def stats(self):
+        """Device-side work counters, valid while profile(1) is on (x264vfw_cuda_la_stats)."""
+        c = (C.c_uint64 * 16)()
+        if lib.x264vfw_cuda_la_stats(self.h, c) < 0:
+            raise CudaError(last_error())
+        names = ("kept", "researched", "pass0", "pass1", "pass2", "pass3", "sad8x8", "satd8x8", "tree_steps", "tree_walks",
+                 "spec_jobs", "ondemand_jobs", "ondemand_launches")
+        return {k: int(c[i]) for i, k in enumerate(names)}
 
     def counters(self):
         c = (C.c_uint64 * 8)()
