@@ -160,6 +160,21 @@ int x264vfw_cuda_lowres_init( x264vfw_cuda_ctx *ctx, uint8_t *dst_dev, const uin
                               int y_stride, int i_width, int i_height,
                               size_t src_frame_bytes, size_t dst_frame_bytes, int n_frames );
 
+/* Fused front end of a frame: ONE kernel (TMA-staged tiles of the packed rows) that replaces, for packed RGB32
+ * sources and a 4:2:0 target, the sequence csp.convert[] (codec.c:1774, RGB_TO_I420 csp.c:299-388) ->
+ * [x264] x264_adaptive_quant_frame (aq-mode 1: f_qp_offset_aq, i_inv_qscale_factor, i_pixel_sum / i_pixel_ssd before
+ * mean removal) -> x264_frame_init_lowres incl. border, which x264_encoder_encode runs on every input picture
+ * (codec.c:1693).  The lookahead session uses it for every eligible frame; this entry runs it on n_frames
+ * device-resident frames in one launch (roofline probe, parity tests).  src_dev: X264VFW_CUDA_CSP_BGRA (| VFLIP)
+ * image, rows 16-byte aligned; dst_dev: tight I420 planes; lowres_dev: 4 * lplane_bytes per frame;
+ * qp_offset_aq_dev / inv_qscale_dev: mb_w * mb_h per frame; stats_dev: 6 uint64 per frame (sum[3], ssd[3]).
+ * Needs i_width % 16 == 0; returns -1 (with a message) when the frame is not eligible. */
+int x264vfw_cuda_frontend_batch( x264vfw_cuda_ctx *ctx, int i_colmatrix, int b_fullrange,
+                                 const x264vfw_cuda_image_t *dst_dev, const x264vfw_cuda_image_t *src_dev,
+                                 uint8_t *lowres_dev, float *qp_offset_aq_dev, uint16_t *inv_qscale_dev,
+                                 unsigned long long *stats_dev, float aq_strength,
+                                 int i_width, int i_height, size_t src_frame_bytes, size_t dst_frame_bytes, int n_frames );
+
 /* ---- half-pel reference planes of a reconstructed frame ------------------
  * [x264] x264_frame_expand_border + x264_frame_filter (x264_mc_functions_t.hpel_filter) +
  * x264_frame_expand_border_filtered for a progressive 8-bit luma plane: what libx264 runs on every
@@ -321,7 +336,8 @@ void x264vfw_cuda_la_counters( x264vfw_cuda_la *la, uint64_t out[8] );
 /* Per-kernel-class device time of this session, measured with CUDA events on the session's
  * stream around every launch: [0] csp [1] aq [2] lowres [3] intra [4] motion search
  * (ordered part: verification wavefront) [5] cost selection [6] weights [7] mb-tree
- * [8] motion search (speculative parallel passes) [9..15] reserved.  Returns the totals
+ * [8] motion search (speculative parallel passes) [9] fused front end (csp + adaptive quant + lowres in one kernel)
+ * [10..15] reserved.  Returns the totals
  * accumulated so far in ms[16] / count[16] (may be NULL); enable = 1/0 switches measurement
  * on/off and resets the totals, -1 only reads. */
 int x264vfw_cuda_la_profile( x264vfw_cuda_la *la, int enable, double ms[16], uint64_t count[16] );

@@ -82,7 +82,7 @@ def metrics_json(tag):
                              "regs": col(r, "launch__registers_per_thread")})
         if kern == "me_pass_kernel":
             big = max(launches, key=lambda l: l["inst"] or 0)          # pass 0 of its batch: every MB is searched
-            searches = round(big["grid"] / 2040)
+            searches = round(big["grid"] / 1020)          # 2040 warps per 1080p search, 2 warps per block
             out[kern] = {"captured": "pass 0 of a %d-search batch at 1080p (scripts/profile_la.py, kernel alone on the GPU)" % searches,
                          "warp_inst": big["inst"], "mb_searches": searches * 8160, "warp_inst_per_mb_search": big["inst"] / (searches * 8160),
                          "duration_us": big["dur_us"], "issue_active_pct": big["issue_pct"], "warps_active_pct": big["warps_active_pct"],

@@ -5,7 +5,11 @@
 // describes the borrowed input buffer; conv_pic comes from [x264] x264_picture_alloc
 // (codec.c:1673).  Here the same decisions select a CUDA kernel + launch descriptor.
 #include "common.cuh"
+#include <mutex>
+#include <math.h>
 #include "csp_kernels.h"
+#include "frontend.h"
+#include "rgb_math.cuh"
 #define XV_DEVICE static inline      /* host view of hpel_kernel.cuh: the job descriptor only */
 #define XV_HPEL_HOST_ONLY
 #include "hpel_kernel.cuh"
@@ -228,6 +232,30 @@ static int table_entry(x264vfw_cuda_image_t *dst, x264vfw_cuda_image_t *src, int
 }
 static int table_fail(x264vfw_cuda_image_t *, x264vfw_cuda_image_t *, int, int) { return -1; }   // csp.c:93-97
 
+const RgbCoef &rgb_coef(int colmatrix, int fullrange) { return k_rgb_coef[(colmatrix == 1 ? 2 : 0) + (fullrange ? 1 : 0)]; }
+
+// x264_log2_lut / x264_exp2_lut on the device, one copy per device, for the context-level front end
+// (a lookahead session has its own)
+int frontend_luts(int device, const float **log2_lut, const uint8_t **exp2_lut)
+{
+    static std::mutex mu;
+    static float *d_l2[64] = {nullptr};
+    static uint8_t *d_e2[64] = {nullptr};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64) return -1;
+    if (!d_l2[device]) {
+        float l2[128]; uint8_t e2[64];
+        for (int i = 0; i < 128; i++) l2[i] = (float)(round(log2(1.0 + i / 128.0) * 100000.0) / 100000.0);
+        for (int i = 0; i < 64; i++) e2[i] = (uint8_t)lround(256.0 * (pow(2.0, i / 64.0) - 1.0));
+        XV_CUDA_OK(cudaMalloc((void **)&d_l2[device], sizeof(l2)));
+        XV_CUDA_OK(cudaMalloc((void **)&d_e2[device], 64));
+        XV_CUDA_OK(cudaMemcpy(d_l2[device], l2, sizeof(l2), cudaMemcpyHostToDevice));
+        XV_CUDA_OK(cudaMemcpy(d_e2[device], e2, 64, cudaMemcpyHostToDevice));
+    }
+    *log2_lut = d_l2[device]; *exp2_lut = d_e2[device];
+    return 0;
+}
+
 } // namespace xv
 
 using namespace xv;
@@ -448,6 +476,38 @@ int x264vfw_cuda_chroma_nv12_pad(x264vfw_cuda_ctx *ctx, uint8_t *dst, int dst_st
     j.u = u; j.v = v; j.c_stride = c_stride; j.w = w; j.h = h; j.dst = dst; j.dst_stride = dst_stride;
     j.luma_w = g.luma_w; j.luma_h = g.luma_h; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
     return launch_chroma_nv12_pad(c->stream, j, n_frames);
+}
+
+int x264vfw_cuda_frontend_batch(x264vfw_cuda_ctx *ctx, int colmatrix, int fullrange, const x264vfw_cuda_image_t *dst, const x264vfw_cuda_image_t *src,
+                                uint8_t *lowres, float *qp_offset_aq, uint16_t *inv_qscale, unsigned long long *stats, float aq_strength,
+                                int w, int h, size_t sfb, size_t dfb, int n_frames)
+{
+    if (!ctx || !dst || !src || !lowres || !qp_offset_aq || !inv_qscale || !stats) { set_error("null argument"); return -1; }
+    Ctx *c = (Ctx *)ctx;
+    XV_CUDA_OK(cudaSetDevice(c->device));
+    if ((src->i_csp & X264VFW_CUDA_CSP_MASK) != X264VFW_CUDA_CSP_BGRA) { set_error("fused front end: BGRA sources only"); return -1; }
+    if (!frontend_eligible(src->plane[0], src->i_stride[0], sfb, w, h, n_frames, dst->plane[0], dst->i_stride[0], dst->plane[1], dst->plane[2],
+                           dst->i_stride[1], dfb) || dst->i_stride[1] != dst->i_stride[2]) {
+        set_error("fused front end: needs width %% 16 == 0, 16-byte aligned packed rows, 4-byte aligned luma rows");
+        return -1;
+    }
+    x264vfw_cuda_lowres_geom g;
+    x264vfw_cuda_lowres_geometry(&g, w, h);
+    FrontendJob j;
+    memset(&j, 0, sizeof(j));
+    j.dst_y = dst->plane[0]; j.dst_u = dst->plane[1]; j.dst_v = dst->plane[2]; j.y_stride = dst->i_stride[0]; j.c_stride = dst->i_stride[1];
+    j.dst_frame_bytes = dfb;
+    j.lowres = lowres; j.lowres_frame_bytes = (size_t)4 * g.lplane_bytes; j.lw = g.lw; j.lh = g.lh; j.lstride = g.lstride;
+    j.lplane_bytes = g.lplane_bytes; j.lorigin = g.lorigin;
+    // f_qp_offset == f_qp_offset_aq at this point of [x264] x264_adaptive_quant_frame: one array serves both
+    j.qp_offset = qp_offset_aq; j.qp_offset_aq = qp_offset_aq; j.inv_qscale = inv_qscale; j.stats = stats;
+    j.mb_frame_stride = (size_t)g.mb_w * g.mb_h;
+    j.aq_on = aq_strength != 0.f; j.aq_mode = 1; j.strength = aq_strength * 1.0397f;
+    if (frontend_luts(c->device, &j.log2_lut, &j.exp2_lut) < 0) return -1;
+    j.w = w; j.h = h; j.mb_w = g.mb_w; j.mb_h = g.mb_h; j.luma_h = g.luma_h; j.flip = (src->i_csp & X264VFW_CUDA_CSP_VFLIP) != 0;
+    j.k = make_rgb_kernel_coef(rgb_coef(colmatrix, fullrange));
+    XV_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)n_frames * 6 * sizeof(unsigned long long), c->stream));
+    return launch_frontend(c->stream, j, src->plane[0], src->i_stride[0], sfb, n_frames);
 }
 
 void x264vfw_cuda_hpel_geometry(x264vfw_cuda_hpel_geom *g, int w, int h)

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "csp_kernels.h"
 #include "la_kernels.h"
+#include "frontend.h"
+#include "rgb_math.cuh"
 #include "../../include/x264vfw_cuda.h"
 #include <math.h>
 #include <string.h>
@@ -32,6 +34,7 @@
 
 namespace xv {
 
+const RgbCoef &rgb_coef(int colmatrix, int fullrange);
 int convert_device_public(cudaStream_t st, int out_csp, int colmatrix, int fullrange, int ext,
                           const x264vfw_cuda_image_t *dst, const x264vfw_cuda_image_t *src,
                           int w, int h, size_t sfb, size_t dfb, int n_frames);
@@ -95,7 +98,7 @@ struct PendingResult { Frame *f; int d0, d1; int slot; bool is_b; bool intra; };
 
 // Optional per-kernel-class device timing: CUDA events recorded on the session's stream around
 // each launch, resolved at the next synchronisation (bench.py reads the totals).
-enum KClass { K_CSP, K_AQ, K_LOWRES, K_INTRA, K_ME, K_FINALIZE, K_WEIGHT, K_TREE, K_ME_PASS, K_N };
+enum KClass { K_CSP, K_AQ, K_LOWRES, K_INTRA, K_ME, K_FINALIZE, K_WEIGHT, K_TREE, K_ME_PASS, K_FRONTEND, K_N };
 struct ProfRec { int cls; cudaEvent_t a, b; };
 struct Prof {
     bool on = false;
@@ -184,7 +187,7 @@ struct La {
     // Same decisions, one put later -- deterministic, like decide_lag.
     std::thread worker; std::mutex mu; std::condition_variable cv;
     bool wstop = false;
-    std::deque<std::array<long, 2>> jobs;       // {frame number, planes ring slot} submitted, not yet taken
+    std::deque<std::array<long, 3>> jobs;       // {frame number, planes ring slot, fused front end ran} submitted, not yet taken
     long n_put = 0;                             // frames submitted by the caller
     long processed = 0;                         // frames the worker is done with (incl. the decisions they made due)
     std::deque<std::pair<long, Decision>> doneq; // decisions tagged with the frame whose arrival produced them
@@ -196,6 +199,13 @@ struct La {
     int io_depth = 2;                           // planes ring: frames the caller may run ahead of the worker
     uint8_t *d_planes_ring[4] = {nullptr}; x264vfw_cuda_image_t planes_ring[4];
     cudaEvent_t ev_csp_ring[4] = {nullptr}, ev_free_ring[4] = {nullptr};
+    // Fused front end (frontend_kernel.cu: csp + AQ + lowres in one pass over the packed rows).  It runs on the I/O
+    // stream inside put_frame and writes straight into the frame's arrays, so the frame slot of put n is chosen
+    // ahead of time by the worker (when it is done with frame n - io_depth) and handed over through ring_frame[];
+    // ev_frame_ready orders the kernel after the slot's reset on the main stream.
+    int fused = 1;
+    Frame *ring_frame[4] = {nullptr};
+    cudaEvent_t ev_frame_ready[4] = {nullptr};
     std::mutex prof_mu;
     int n_input = 0;
     uint64_t n_frame_cost = 0, n_mb_search = 0, n_sync = 0;
@@ -1359,6 +1369,48 @@ static int decide_and_shift(La *la)
     return la->fail ? -1 : 0;
 }
 
+// The fused front end for frame f: packed BGRA rows at `src` (device) -> converted planes + AQ arrays + lowres
+// planes of f, on stream st.  Returns 1 when it ran, 0 when the frame is not eligible (the separate kernels run
+// instead), -1 on error.
+static int fused_eligible(const La *la, const x264vfw_cuda_image_t &planes, const uint8_t *src, long long stride)
+{
+    if (!la->fused || (la->in_csp & X264VFW_CUDA_CSP_MASK) != X264VFW_CUDA_CSP_BGRA || la->out_csp != X264VFW_CUDA_OUT_I420) return 0;
+    if (la->p.chroma_format != 1 || planes.i_stride[1] != planes.i_stride[2]) return 0;
+    return frontend_eligible(src, stride, 0, la->p.width, la->p.height, 1, planes.plane[0], planes.i_stride[0], planes.plane[1], planes.plane[2],
+                             planes.i_stride[1], 0) ? 1 : 0;
+}
+
+static int launch_fused(La *la, cudaStream_t st, Frame *f, const x264vfw_cuda_image_t &planes, const uint8_t *src, long long stride)
+{
+    const bool aq_on = la->p.aq_mode != 0 && la->p.aq_strength != 0;
+    FrontendJob j;
+    memset(&j, 0, sizeof(j));
+    j.dst_y = planes.plane[0]; j.dst_u = planes.plane[1]; j.dst_v = planes.plane[2];
+    j.y_stride = planes.i_stride[0]; j.c_stride = planes.i_stride[1]; j.dst_frame_bytes = 0;
+    j.lowres = f->lowres; j.lowres_frame_bytes = 0; j.lw = la->g.lw; j.lh = la->g.lh; j.lstride = la->g.lstride;
+    j.lplane_bytes = la->g.lplane; j.lorigin = la->g.lorigin;
+    j.qp_offset = f->qp_offset; j.qp_offset_aq = f->qp_offset_aq; j.inv_qscale = f->inv_qscale; j.stats = f->stats; j.mb_frame_stride = 0;
+    j.aq_on = aq_on; j.aq_mode = la->p.aq_mode; j.strength = la->p.aq_strength * 1.0397f;
+    j.log2_lut = la->d_log2_lut; j.exp2_lut = la->d_exp2_lut;
+    j.w = la->p.width; j.h = la->p.height; j.mb_w = la->g.mb_w; j.mb_h = la->g.mb_h; j.luma_h = la->g.luma_h;
+    j.flip = (la->in_csp & X264VFW_CUDA_CSP_VFLIP) != 0;
+    j.k = make_rgb_kernel_coef(rgb_coef(la->colmatrix, la->fullrange));
+    { ProfScope ps(la, K_FRONTEND, st); if (launch_frontend(st, j, src, stride, 0, 1) < 0) return -1; }
+    la->n_launch++;
+    if (aq_on && la->p.aq_mode >= 2) {
+        AqJob aq;
+        memset(&aq, 0, sizeof(aq));
+        aq.aq_on = 1; aq.aq_mode = la->p.aq_mode; aq.aq_strength = la->p.aq_strength;
+        aq.qp_offset = f->qp_offset; aq.qp_offset_aq = f->qp_offset_aq; aq.inv_qscale = f->inv_qscale; aq.exp2_lut = la->d_exp2_lut;
+        ProfScope ps(la, K_AQ, st);
+        if (launch_aq_auto(st, la->g, aq) < 0) return -1;
+        la->n_launch++;
+    }
+    XV_CUDA_OK(cudaMemcpyAsync(f->h_stats, f->stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    XV_CUDA_OK(cudaEventRecord(f->ev_stats, st));
+    return 1;
+}
+
 // [x264] x264_adaptive_quant_frame + x264_frame_init_lowres of frame f from the converted planes
 // (device, encoder csp).  NV12 sessions hand the interleaved chroma plane to the AQ kernel, which
 // reads U and V out of it: libx264 computes the same 4:2:0 energies on its internal NV12 frame.
@@ -1403,7 +1455,7 @@ static int frame_prep(La *la, Frame *f, const x264vfw_cuda_image_t &planes)
 // ------------------------------------------------------------------------------------------
 // Frame f has been converted into `planes` (signalled by ev_csp on the I/O stream): [x264]
 // x264_adaptive_quant_frame, x264_frame_init_lowres, then the searches this frame enables.
-static int process_frame(La *la, Frame *f, const x264vfw_cuda_image_t &planes, cudaEvent_t ev_csp, cudaEvent_t ev_free)
+static int process_frame(La *la, Frame *f, const x264vfw_cuda_image_t &planes, cudaEvent_t ev_csp, cudaEvent_t ev_free, bool fused)
 {
     const int w = la->p.width, hgt = la->p.height;
     if (ev_csp) {
@@ -1412,7 +1464,7 @@ static int process_frame(La *la, Frame *f, const x264vfw_cuda_image_t &planes, c
         if (cudaEventQuery(ev_csp) != cudaSuccess) { const double t0 = now_s(); if (wait_event(la, ev_csp) < 0) return -1; la->t_csp_wait += now_s() - t0; }
         XV_CUDA_OK(cudaStreamWaitEvent(la->st, ev_csp, 0));
     }
-    if (frame_prep(la, f, planes) < 0) return -1;
+    if (!fused && frame_prep(la, f, planes) < 0) return -1;   // the fused front end already produced AQ arrays and lowres planes
     XV_CUDA_OK(cudaEventRecord(ev_free, la->st));           // the planes may be overwritten again
     {   // every frame's intra costs are needed sooner or later and only depend on its lowres plane
         IntraJob ij;
@@ -1440,7 +1492,7 @@ static void worker_main(La *la)
 {
     cudaSetDevice(la->device);
     for (;;) {
-        std::array<long, 2> job;
+        std::array<long, 3> job;
         {
             std::unique_lock<std::mutex> lk(la->mu);
             la->cv.wait(lk, [&] { return la->wstop || !la->jobs.empty(); });
@@ -1454,12 +1506,20 @@ static void worker_main(La *la)
         // (When the conversion is already done -- device-resident sources -- the frame goes first,
         // so that its searches start as early as possible.)
         int rc = 0;
-        Frame *f = frame_get(la, (int)job[0]);
-        if (!f) rc = -1;
+        const bool fused = job[2] != 0;
+        Frame *f = la->ring_frame[slot];                       // chosen io_depth frames ago (see La::ring_frame)
+        if (!f || f->i_frame != (int)job[0]) { set_error("lookahead worker: frame slot hand-over out of step"); rc = -1; }
         const bool converted = rc == 0 && cudaEventQuery(la->ev_csp_ring[slot]) == cudaSuccess;
-        if (rc == 0 && converted) rc = process_frame(la, f, la->planes_ring[slot], la->ev_csp_ring[slot], la->ev_free_ring[slot]);
+        if (rc == 0 && converted) rc = process_frame(la, f, la->planes_ring[slot], la->ev_csp_ring[slot], la->ev_free_ring[slot], fused);
         if (rc == 0) { la->n_input = (int)job[0] + 1; la->next.push_back(f); rc = run_due_decisions(la); }
-        if (rc == 0 && !converted) rc = process_frame(la, f, la->planes_ring[slot], la->ev_csp_ring[slot], la->ev_free_ring[slot]);
+        if (rc == 0 && !converted) rc = process_frame(la, f, la->planes_ring[slot], la->ev_csp_ring[slot], la->ev_free_ring[slot], fused);
+        if (rc == 0) {
+            // the slot of put (n + io_depth), which re-uses this ring position
+            Frame *nf = frame_get(la, (int)job[0] + la->io_depth);
+            if (!nf) rc = -1;
+            else if (cudaEventRecord(la->ev_frame_ready[slot], la->st) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = -1; }
+            la->ring_frame[slot] = nf;
+        }
         std::lock_guard<std::mutex> lk(la->mu);
         if (rc < 0 && !la->werr) { la->werr = -1; la->werr_msg = x264vfw_cuda_last_error(); }
         while (!la->outq.empty()) { la->doneq.emplace_back(job[0], la->outq.front()); la->outq.pop_front(); }
@@ -1624,6 +1684,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_ME_GUESS")) la->me_guess = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ME_FORCE_MISS")) la->me_force_miss = atoi(e) != 0;
     if (const char *e = getenv("X264VFW_CUDA_ASYNC")) la->async = atoi(e);
+    if (const char *e = getenv("X264VFW_CUDA_FUSED")) la->fused = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_SYNC")) {      // spin (default) | yield | block | hybrid | hybrid:<microseconds>
         la->yielding = !strcmp(e, "yield");
         la->blocking = strcmp(e, "spin") != 0 && !la->yielding;
@@ -1714,9 +1775,13 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
         }
         if (!ok) { if (!*x264vfw_cuda_last_error()) set_error("lookahead allocation failed"); x264vfw_cuda_la_close((x264vfw_cuda_la *)la); return -1; }
     }
+    // ev_frame_ready[0] for the synchronous path (keep_frames / X264VFW_CUDA_ASYNC=0); the ring creates its own below
+    if (!(la->async && la->decide_lag >= 1 && !keep_frames) && cudaEventCreateWithFlags(&la->ev_frame_ready[0], cudaEventDisableTiming) != cudaSuccess) {
+        set_error("cudaEventCreate failed"); x264vfw_cuda_la_close((x264vfw_cuda_la *)la); return -1;
+    }
     // pre-allocate the frame pool: allocation is slow and serialises across sessions
     if (!keep_frames) {
-        const int want = la->slicetype_length + p.bframes + 6 + la->decide_lag;
+        const int want = la->slicetype_length + p.bframes + 6 + la->decide_lag + la->io_depth;
         for (int i = 0; i < want; i++) {
             Frame *f = frame_alloc(la);
             if (!f) { x264vfw_cuda_la_close((x264vfw_cuda_la *)la); return -1; }
@@ -1727,12 +1792,17 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (la->async && la->decide_lag >= 1 && !keep_frames) {
         bool ok = cudaStreamCreateWithPriority(&la->st_io, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
         for (int k = 0; k < la->io_depth && ok; k++) {
-            ok = cudaMalloc((void **)&la->d_planes_ring[k], la->d_planes_bytes + 256) == cudaSuccess &&
+            ok = cudaEventCreateWithFlags(&la->ev_frame_ready[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaMalloc((void **)&la->d_planes_ring[k], la->d_planes_bytes + 256) == cudaSuccess &&
                  cudaEventCreateWithFlags(&la->ev_csp_ring[k], cudaEventDisableTiming | (la->blocking ? cudaEventBlockingSync : 0)) == cudaSuccess &&
                  cudaEventCreateWithFlags(&la->ev_free_ring[k], cudaEventDisableTiming) == cudaSuccess;
             if (ok) x264vfw_cuda_picture_layout(&la->planes_ring[k], la->d_planes_ring[k], out_csp, p.width, p.height);
         }
-        if (!ok) { set_error("lookahead allocation failed"); x264vfw_cuda_la_close((x264vfw_cuda_la *)la); return -1; }
+        for (int k = 0; k < la->io_depth && ok; k++) {
+            la->ring_frame[k] = frame_get(la, k);
+            ok = la->ring_frame[k] && cudaEventRecord(la->ev_frame_ready[k], la->st) == cudaSuccess;
+        }
+        if (!ok) { if (!*x264vfw_cuda_last_error()) set_error("lookahead allocation failed"); x264vfw_cuda_la_close((x264vfw_cuda_la *)la); return -1; }
         la->worker = std::thread(worker_main, la);
     }
     *pla = (x264vfw_cuda_la *)la;
@@ -1779,7 +1849,7 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     for (Decision &d : la->outq) if (d.h_qp) cudaFreeHost(d.h_qp);
     for (Decision &d : la->pubq) if (d.h_qp) cudaFreeHost(d.h_qp);
     for (auto &pd : la->doneq) if (pd.second.h_qp) cudaFreeHost(pd.second.h_qp);
-    for (int k = 0; k < 4; k++) { cudaFree(la->d_planes_ring[k]); if (la->ev_csp_ring[k]) cudaEventDestroy(la->ev_csp_ring[k]); if (la->ev_free_ring[k]) cudaEventDestroy(la->ev_free_ring[k]); }
+    for (int k = 0; k < 4; k++) { if (la->ev_frame_ready[k]) cudaEventDestroy(la->ev_frame_ready[k]); cudaFree(la->d_planes_ring[k]); if (la->ev_csp_ring[k]) cudaEventDestroy(la->ev_csp_ring[k]); if (la->ev_free_ring[k]) cudaEventDestroy(la->ev_free_ring[k]); }
     for (float *q : la->qp_free) cudaFreeHost(q);
     cudaFree(la->d_cost_mv); cudaFree(la->d_log2_lut); cudaFree(la->d_exp2_lut); cudaFree(la->d_weight_buf);
     for (int e = 0; e <= ME_SIDE; e++) {
@@ -1844,7 +1914,10 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         f = frame_get(la, la->n_input);
         if (!f) return -1;
         la->n_input++;
+        if (la->ev_frame_ready[0]) XV_CUDA_OK(cudaEventRecord(la->ev_frame_ready[0], la->st));   // the slot's reset is queued on the main stream
     }
+    Frame *ff = async ? la->ring_frame[slot] : f;           // the frame slot this put fills (fused front end writes into it)
+    bool did_fuse = false;
 
     const int out420 = la->out_csp == X264VFW_CUDA_OUT_I420 || la->out_csp == X264VFW_CUDA_OUT_NV12;
     x264vfw_cuda_image_t geo_out;
@@ -1886,6 +1959,11 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
             for (int i = 0; i < geo_out.i_plane; i++)
                 XV_CUDA_OK(cudaMemcpy2DAsync(planes.plane[i], planes.i_stride[i], src->plane[i], src->i_stride[i], geo_out.i_stride[i], chroma_rows(out420, i),
                                              src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st1));
+        } else if (ff && fused_eligible(la, planes, dsrc.plane[0], dsrc.i_stride[0])) {
+            // one kernel: converted planes + AQ arrays + lowres planes of the frame slot
+            if (st1 != la->st) XV_CUDA_OK(cudaStreamWaitEvent(st1, la->ev_frame_ready[slot], 0));
+            if (launch_fused(la, st1, ff, planes, dsrc.plane[0], dsrc.i_stride[0]) < 0) return -1;
+            did_fuse = true;
         } else {
             { ProfScope ps(la, K_CSP, st1); if (convert_device_public(st1, la->out_csp, la->colmatrix, la->fullrange, la->ext, &planes, &dsrc, w, hgt, 0, 0, 1) < 0) return -1; }
             la->n_launch++;
@@ -1922,7 +2000,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         // hand the frame to the session worker; wait for the borrowed buffers only
         {
             std::lock_guard<std::mutex> lk(la->mu);
-            la->jobs.push_back({n, (long)slot});
+            la->jobs.push_back({n, (long)slot, (long)did_fuse});
             la->cv.notify_all();
         }
         la->n_put++;
@@ -1950,8 +2028,8 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     if (!borrowed) { if (stage1() < 0) return -1; }
     else XV_CUDA_OK(cudaStreamWaitEvent(la->st, la->ev_csp, 0));
 
-    // ---- 4./5. [x264] x264_adaptive_quant_frame, x264_frame_init_lowres ----
-    if (frame_prep(la, f, planes) < 0) return -1;
+    // ---- 4./5. [x264] x264_adaptive_quant_frame, x264_frame_init_lowres (unless the fused front end produced them) ----
+    if (!did_fuse && frame_prep(la, f, planes) < 0) return -1;
     XV_CUDA_OK(cudaEventRecord(la->ev_planes_free, la->st));
     la->planes_busy = true;
 

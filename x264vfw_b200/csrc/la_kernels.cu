@@ -169,14 +169,20 @@ aq_auto_kernel(LaGeom g, AqJob job)
     }
 }
 
+int launch_aq_auto(cudaStream_t st, const LaGeom &g, const AqJob &job);
 int launch_aq(cudaStream_t st, const LaGeom &g, const AqJob &job)
 {
     aq_kernel<<<(g.mb_count + 31) / 32, 32 * AQ_PARTS, 0, st>>>(g, job);
     XV_LAUNCH_CHECK();
-    if (job.aq_on && job.aq_mode >= 2) {
-        aq_auto_kernel<<<1, 1024, 0, st>>>(g, job);
-        XV_LAUNCH_CHECK();
-    }
+    if (job.aq_on && job.aq_mode >= 2) return launch_aq_auto(st, g, job);
+    return 0;
+}
+
+// second half of the auto-variance modes on its own (the fused front end produces the first half)
+int launch_aq_auto(cudaStream_t st, const LaGeom &g, const AqJob &job)
+{
+    aq_auto_kernel<<<1, 1024, 0, st>>>(g, job);
+    XV_LAUNCH_CHECK();
     return 0;
 }
 

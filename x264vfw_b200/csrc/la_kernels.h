@@ -27,6 +27,7 @@ struct AqJob {
     const float *log2_lut; const uint8_t *exp2_lut;
 };
 int launch_aq(cudaStream_t st, const LaGeom &g, const AqJob &job);
+int launch_aq_auto(cudaStream_t st, const LaGeom &g, const AqJob &job);   // second loop of aq-mode 2 / 3 only
 
 // ---- intra cost ([x264] slicetype_mb_cost, lowres_intra_mb) --------------------------------
 struct IntraJob {

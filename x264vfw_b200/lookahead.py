@@ -59,7 +59,7 @@ lib.x264vfw_cuda_la_stats.restype = C.c_int
 lib.x264vfw_cuda_la_stats.argtypes = [C.c_void_p, _P(C.c_uint64)]
 lib.x264vfw_cuda_la_profile.restype = C.c_int
 lib.x264vfw_cuda_la_profile.argtypes = [C.c_void_p, C.c_int, _P(C.c_double), _P(C.c_uint64)]
-KERNEL_CLASSES = ("csp", "aq", "lowres", "intra", "me", "finalize", "weights", "mbtree", "me_pass")
+KERNEL_CLASSES = ("csp", "aq", "lowres", "intra", "me", "finalize", "weights", "mbtree", "me_pass", "frontend")
 
 
 lib.x264vfw_cuda_la_params_tune.restype = C.c_int
