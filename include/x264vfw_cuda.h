@@ -342,6 +342,66 @@ void x264vfw_cuda_la_counters( x264vfw_cuda_la *la, uint64_t out[8] );
  * on/off and resets the totals, -1 only reads. */
 int x264vfw_cuda_la_profile( x264vfw_cuda_la *la, int enable, double ms[16], uint64_t count[16] );
 
+/* ------------------------------------------------------------------------------------
+ * B3: upstream libx264's own function-table shapes on DEVICE pointers.  libx264 is not part of the
+ * reference tree (Makefile:21-23,109; entered at codec.c:1693); these mirror the C functions behind
+ * x264_mc_functions_t / x264_pixel_function_t ([x264] common/mc.c, common/pixel.c) argument for argument, so that
+ * a patch that points those table entries at the GPU is mechanical.  Differences are only what a device call
+ * needs: the context (stream) in front, device pointers, a float instead of float*, and batches (offset arrays)
+ * where upstream calls the function once per block.  All calls are asynchronous on the context's stream.
+ * ---------------------------------------------------------------------------------- */
+/* mc.frame_init_lowres_core( src0, dst0, dsth, dstv, dstc, src_stride, dst_stride, width, height ): width x height
+ * lowres pixels, reads src rows 0 .. 2*height and columns 0 .. 2*width (the caller provides the duplicated last
+ * row / column, as upstream's x264_frame_init_lowres does); no border. */
+int x264vfw_cuda_frame_init_lowres_core( x264vfw_cuda_ctx *ctx, const uint8_t *src0, uint8_t *dst0, uint8_t *dsth,
+                                         uint8_t *dstv, uint8_t *dstc, intptr_t src_stride, intptr_t dst_stride,
+                                         int width, int height );
+/* mc.mbtree_propagate_cost( dst, propagate_in, intra_costs, inter_costs, inv_qscales, fps_factor, len ) */
+int x264vfw_cuda_mbtree_propagate_cost( x264vfw_cuda_ctx *ctx, int16_t *dst, const uint16_t *propagate_in,
+                                        const uint16_t *intra_costs, const uint16_t *inter_costs,
+                                        const uint16_t *inv_qscales, float fps_factor, int len );
+/* mc.mbtree_propagate_list( h, ref_costs, mvs, propagate_amount, lowres_costs, bipred_weight, mb_y, len, list ):
+ * one MB row; mvs / propagate_amount / lowres_costs point at that row, ref_costs at the whole frame; h->mb.i_mb_width /
+ * i_mb_height travel as the last two arguments.  Saturating 16-bit adds (32767) like upstream. */
+int x264vfw_cuda_mbtree_propagate_list( x264vfw_cuda_ctx *ctx, uint16_t *ref_costs, const int16_t (*mvs)[2],
+                                        const int16_t *propagate_amount, const uint16_t *lowres_costs,
+                                        int bipred_weight, int mb_y, int len, int list, int mb_width, int mb_height );
+/* pixf.sad[PIXEL_8x8] / pixf.satd[PIXEL_8x8]( pix1, stride1, pix2, stride2 ) for n block pairs: pair i compares the
+ * blocks at pix1 + off1[i] and pix2 + off2[i]; scores[i] receives the result. */
+int x264vfw_cuda_pixel_cmp_8x8( x264vfw_cuda_ctx *ctx, int b_satd, const uint8_t *pix1, intptr_t stride1,
+                                const uint8_t *pix2, intptr_t stride2, const int *off1, const int *off2,
+                                int *scores, int n );
+/* pixf.sad_x3 / sad_x4[PIXEL_8x8]( fenc, pix0..pix3, stride, scores ) for n source blocks: block i at
+ * fenc + off_fenc[i] against n_ref (3 or 4) candidates at ref + off_ref[i * n_ref + k]; scores[i * n_ref + k]. */
+int x264vfw_cuda_pixel_sad_xn_8x8( x264vfw_cuda_ctx *ctx, int n_ref, const uint8_t *fenc, intptr_t fenc_stride,
+                                   const int *off_fenc, const uint8_t *ref, intptr_t ref_stride,
+                                   const int *off_ref, int *scores, int n );
+/* pixf.intra_mbcmp_x3_8x8c( fenc, fdec, res ) for every 8x8 block of a plane: predict_8x8c_{dc,h,v} from the block's
+ * neighbours inside the plane (row above, column to the left must be valid memory: the lookahead's padded lowres
+ * plane), scored with SAD or SATD; res[3 * (mx + my * mb_w) + {0,1,2}] = {DC, H, V}. */
+int x264vfw_cuda_intra_mbcmp_x3_8x8c( x264vfw_cuda_ctx *ctx, int b_satd, const uint8_t *plane, int stride,
+                                      int mb_w, int mb_h, int *res );
+
+/* [x264] encoder/slicetype-cl.c hook names: what a libx264 patched at its HAVE_OPENCL sites (slicetype_frame_cost,
+ * x264_slicetype_analyse) would call, here on a COST-ENGINE session: x264vfw_cuda_la_open with keep_frames = 1 and
+ * params.rc_lookahead = X264VFW_CUDA_LOOKAHEAD_MAX, so that the session never decides anything itself and libx264's own
+ * decision code keeps the control flow.  Frames are addressed by display index = order of the lowres_init calls.
+ *   x264_opencl_lowres_init( h, fenc, lambda )                        -> _opencl_lowres_init: returns the frame's index
+ *   x264_opencl_motionsearch( h, frames, b, ref, b_islist1, lambda, w ) -> _opencl_motionsearch: enqueues the search
+ *   x264_opencl_finalize_cost( h, lambda, frames, p0, p1, b, dsf )    -> _opencl_finalize_cost: slicetype_frame_cost(p0,p1,b)
+ *                                                                        incl. the weight analysis; cost_out = {i_cost_est,
+ *                                                                        i_cost_est_aq, i_intra_mbs}; returns the score
+ *   x264_opencl_flush( h )                                            -> _opencl_flush
+ *   x264_opencl_slicetype_prep( h, frames, num_frames, lambda )       -> _opencl_slicetype_prep( first, num_frames ): batches
+ *                                                                        every search of the window up to bframes away
+ *   x264_opencl_slicetype_end( h )                                    -> _opencl_slicetype_end */
+int x264vfw_cuda_opencl_lowres_init( x264vfw_cuda_la *la, const x264vfw_cuda_image_t *src, int src_on_device );
+int x264vfw_cuda_opencl_motionsearch( x264vfw_cuda_la *la, int b, int ref, int b_islist1 );
+int x264vfw_cuda_opencl_finalize_cost( x264vfw_cuda_la *la, int p0, int p1, int b, int cost_out[3] );
+int x264vfw_cuda_opencl_flush( x264vfw_cuda_la *la );
+int x264vfw_cuda_opencl_slicetype_prep( x264vfw_cuda_la *la, int first, int num_frames );
+int x264vfw_cuda_opencl_slicetype_end( x264vfw_cuda_la *la );
+
 /* Work counters of the search kernels and the mb-tree, counted on the device while x264vfw_cuda_la_profile
  * is enabled (reset when it is switched on): [0] MBs whose speculative result the ordered verification kept,
  * [1] MBs it searched again in order, [2..5] MBs searched by parallel pass 0..3, [6] SAD 8x8 evaluations,

@@ -52,14 +52,68 @@ __device__ __forceinline__ void hphase4(uint32_t lo, uint32_t hi, uint32_t tail,
     ph = avg4(o, n);
 }
 
-__global__ void __launch_bounds__(256)
+// conversion of the thread's two row pairs (4 pixels wide each, same macroblock).  EDGE: the tile crosses the right or
+// bottom picture edge (bounds checks, replicated rows count with their multiplicity); interior tiles skip all of that.
+template <bool FLIP, bool EDGE>
+__device__ __forceinline__ void fe_convert(const FrontendJob &job, FeSmem &sm, int tid, int x0, int y0, uint8_t *Y, uint8_t *U, uint8_t *V)
+{
+    unsigned s[6] = {0, 0, 0, 0, 0, 0};
+    const int c = tid & 31, p0 = 2 * (tid >> 5);
+    const int x = x0 + 4 * c;
+    // byte offsets inside the frame fit 32 bits
+    uint8_t *py = Y + (unsigned)((y0 + 2 * p0) * job.y_stride + x);
+    uint8_t *pu = U + (unsigned)(((y0 >> 1) + p0) * job.c_stride + (x >> 1));
+    uint8_t *pv = V + (unsigned)(((y0 >> 1) + p0) * job.c_stride + (x >> 1));
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int p = p0 + it, y = y0 + 2 * p;
+        if (!EDGE || (x < job.w && y < job.h)) {
+            const int ra = FLIP ? FE_LH - 2 * p : 2 * p, rb = FLIP ? ra - 1 : ra + 1;
+            const uint4 t = *(const uint4 *)&sm.rgb[ra][4 * c], b = *(const uint4 *)&sm.rgb[rb][4 * c];
+            const uint32_t yt = __byte_perm(__byte_perm(luma16(job.k, t.x), luma16(job.k, t.y), 0x0073),
+                                            __byte_perm(luma16(job.k, t.z), luma16(job.k, t.w), 0x0073), 0x5410);
+            const uint32_t yb = __byte_perm(__byte_perm(luma16(job.k, b.x), luma16(job.k, b.y), 0x0073),
+                                            __byte_perm(luma16(job.k, b.z), luma16(job.k, b.w), 0x0073), 0x5410);
+            uint32_t u0, v0, u1, v1;
+            chroma_quad(job.k, t.x, b.x, t.y, b.y, u0, v0);
+            chroma_quad(job.k, t.z, b.z, t.w, b.w, u1, v1);
+            *(uint32_t *)(py + it * 2 * job.y_stride) = yt;
+            *(uint32_t *)(py + (it * 2 + 1) * job.y_stride) = yb;
+            *(uint16_t *)(pu + it * job.c_stride) = (uint16_t)(u0 | (u1 << 8));
+            *(uint16_t *)(pv + it * job.c_stride) = (uint16_t)(v0 | (v1 << 8));
+            *(uint32_t *)&sm.y[2 * p][4 * c] = yt;
+            *(uint32_t *)&sm.y[2 * p + 1][4 * c] = yb;
+            // macroblock sums; the rows below the picture replicate its last row ([x264] expand_border_mod16):
+            // that row counts 1 + (luma_h - h) times, the last chroma row 1 + (8 mb_h - h/2) times
+            unsigned my = 1u, mc = 1u;
+            if (EDGE && y + 2 == job.h) { my += (unsigned)(job.luma_h - job.h); mc += (unsigned)(8 * job.mb_h - job.h / 2); }
+            s[0] += __dp4a(yt, 0x01010101u, 0u) + my * __dp4a(yb, 0x01010101u, 0u);
+            s[3] += __dp4a(yt, yt, 0u) + my * __dp4a(yb, yb, 0u);
+            s[1] += mc * (u0 + u1); s[4] += mc * (u0 * u0 + u1 * u1);
+            s[2] += mc * (v0 + v1); s[5] += mc * (v0 * v0 + v1 * v1);
+        }
+    }
+    // the 4 lanes of a macroblock column meet by shuffle, one of them adds to the MB's accumulators
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        s[k] += __shfl_xor_sync(0xffffffffu, s[k], 1);
+        s[k] += __shfl_xor_sync(0xffffffffu, s[k], 2);
+    }
+    if ((c & 3) == 0) {
+        unsigned int *acc = sm.mb[(tid >> 7) * 8 + (c >> 2)];
+#pragma unroll
+        for (int k = 0; k < 6; k++) if (s[k]) atomicAdd(acc + k, s[k]);
+    }
+}
+
+template <bool FLIP>
+__global__ void __launch_bounds__(256, 8)
 frontend_kernel(const __grid_constant__ FrontendJob job)
 {
     __shared__ FeSmem sm;
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * FE_LW, y0 = blockIdx.y * FE_LH;
     const size_t f = blockIdx.z;
-    const int flip = job.flip;
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.mbar)) : "memory");
@@ -69,7 +123,7 @@ frontend_kernel(const __grid_constant__ FrontendJob job)
     __syncthreads();
     if (tid == 0) {
         // tile rows y0 .. y0+32 are source rows h-1-y0-32 .. h-1-y0 of a bottom-up DIB (csp.c:310-314)
-        const int row0 = flip ? job.h - 1 - y0 - FE_LH : y0;
+        const int row0 = FLIP ? job.h - 1 - y0 - FE_LH : y0;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&sm.mbar)), "r"((uint32_t)sizeof(sm.rgb)) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                      :: "r"(smem_u32(&sm.rgb[0][0])), "l"((uint64_t)&job.tmap), "r"(x0), "r"(row0), "r"((int)f), "r"(smem_u32(&sm.mbar)) : "memory");
@@ -80,53 +134,14 @@ frontend_kernel(const __grid_constant__ FrontendJob job)
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                          : "=r"(done) : "r"(smem_u32(&sm.mbar)) : "memory");
     }
-    auto srow = [&](int j) { return flip ? FE_LH - j : j; };      // shared-memory row of tile row j
+    auto srow = [&](int j) { return FLIP ? FE_LH - j : j; };      // shared-memory row of tile row j
     const int rmax = min(FE_LH, job.h - 1 - y0);                   // last tile row / column inside the picture
     const int cmax = min(FE_LW, job.w - 1 - x0);
 
     // ---- conversion: thread = 4 pixels x a row pair, two such items per thread ----
     uint8_t *Y = job.dst_y + f * job.dst_frame_bytes, *U = job.dst_u + f * job.dst_frame_bytes, *V = job.dst_v + f * job.dst_frame_bytes;
-#pragma unroll
-    for (int it = 0; it < 2; it++) {
-        const int item = tid + it * 256, c = item & 31, p = item >> 5;
-        const int x = x0 + 4 * c, y = y0 + 2 * p;
-        unsigned s[6] = {0, 0, 0, 0, 0, 0};
-        if (x < job.w && y < job.h) {
-            const uint4 t = *(const uint4 *)&sm.rgb[srow(2 * p)][4 * c], b = *(const uint4 *)&sm.rgb[srow(2 * p + 1)][4 * c];
-            const uint32_t yt = __byte_perm(__byte_perm(luma16(job.k, t.x), luma16(job.k, t.y), 0x0073),
-                                            __byte_perm(luma16(job.k, t.z), luma16(job.k, t.w), 0x0073), 0x5410);
-            const uint32_t yb = __byte_perm(__byte_perm(luma16(job.k, b.x), luma16(job.k, b.y), 0x0073),
-                                            __byte_perm(luma16(job.k, b.z), luma16(job.k, b.w), 0x0073), 0x5410);
-            uint32_t u0, v0, u1, v1;
-            chroma_quad(job.k, t.x, b.x, t.y, b.y, u0, v0);
-            chroma_quad(job.k, t.z, b.z, t.w, b.w, u1, v1);
-            *(uint32_t *)(Y + (size_t)y * job.y_stride + x) = yt;
-            *(uint32_t *)(Y + (size_t)(y + 1) * job.y_stride + x) = yb;
-            *(uint16_t *)(U + (size_t)(y >> 1) * job.c_stride + (x >> 1)) = (uint16_t)(u0 | (u1 << 8));
-            *(uint16_t *)(V + (size_t)(y >> 1) * job.c_stride + (x >> 1)) = (uint16_t)(v0 | (v1 << 8));
-            *(uint32_t *)&sm.y[2 * p][4 * c] = yt;
-            *(uint32_t *)&sm.y[2 * p + 1][4 * c] = yb;
-            // macroblock sums; the rows below the picture replicate its last row ([x264] expand_border_mod16):
-            // that row counts 1 + (luma_h - h) times, the last chroma row 1 + (8 mb_h - h/2) times
-            const unsigned my = (y + 2 == job.h) ? 1u + (unsigned)(job.luma_h - job.h) : 1u;
-            const unsigned mc = (y + 2 == job.h) ? 1u + (unsigned)(8 * job.mb_h - job.h / 2) : 1u;
-            s[0] = __dp4a(yt, 0x01010101u, 0u) + my * __dp4a(yb, 0x01010101u, 0u);
-            s[3] = __dp4a(yt, yt, 0u) + my * __dp4a(yb, yb, 0u);
-            s[1] = mc * (u0 + u1); s[4] = mc * (u0 * u0 + u1 * u1);
-            s[2] = mc * (v0 + v1); s[5] = mc * (v0 * v0 + v1 * v1);
-        }
-        // the 4 lanes of a macroblock column meet by shuffle, one of them adds to the MB's accumulators
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            s[k] += __shfl_xor_sync(0xffffffffu, s[k], 1);
-            s[k] += __shfl_xor_sync(0xffffffffu, s[k], 2);
-        }
-        if ((c & 3) == 0) {
-            unsigned int *acc = sm.mb[(p >> 3) * 8 + (c >> 2)];
-#pragma unroll
-            for (int k = 0; k < 6; k++) if (s[k]) atomicAdd(acc + k, s[k]);
-        }
-    }
+    if (x0 + FE_LW <= job.w && y0 + FE_LH <= job.h) fe_convert<FLIP, false>(job, sm, tid, x0, y0, Y, U, V);
+    else fe_convert<FLIP, true>(job, sm, tid, x0, y0, Y, U, V);
     // halo: luma of tile column 128 (rows 0..32) and of tile row 32 (columns 0..127), where inside the picture
     for (int i = tid; i < FE_BOXH + FE_LW; i += 256) {
         const int j = i < FE_BOXH ? i : FE_LH, cx = i < FE_BOXH ? FE_LW : i - FE_BOXH;
@@ -270,7 +285,8 @@ int launch_frontend(cudaStream_t st, FrontendJob &job, const uint8_t *src, long 
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)rc); return -1; }
     const dim3 grid((unsigned)((job.w + FE_LW - 1) / FE_LW), (unsigned)((job.luma_h + FE_LH - 1) / FE_LH), (unsigned)n_frames);
-    frontend_kernel<<<grid, 256, 0, st>>>(job);
+    if (job.flip) frontend_kernel<true><<<grid, 256, 0, st>>>(job);
+    else frontend_kernel<false><<<grid, 256, 0, st>>>(job);
     XV_LAUNCH_CHECK();
     return 0;
 }

@@ -2203,6 +2203,92 @@ int x264vfw_cuda_la_stats(x264vfw_cuda_la *h, uint64_t out[16])
     return 0;
 }
 
+// ---- [x264] encoder/slicetype-cl.c hook names on a cost-engine session --------------------------
+static int hook_frames(La *la, int a, int b)
+{
+    if (!la->keep_frames) { set_error("opencl-style hooks need a session opened with keep_frames"); return -1; }
+    for (int i = a; i <= b; i++)
+        if (i < 0 || i >= (int)la->by_index.size() || !la->by_index[i] || !la->by_index[i]->ready) { set_error("hook: frame %d is not resident", i); return -1; }
+    return 0;
+}
+
+// enqueue the unweighted search of frame b towards `ref` unless its result exists already (mp collects a batch)
+static int hook_add_search(La *la, MeParams &mp, int b, int ref, int list)
+{
+    const int dist = list ? ref - b : b - ref;
+    if (dist < 1 || dist > la->p.bframes + 1) { set_error("hook: distance %d outside 1..%d", dist, la->p.bframes + 1); return -1; }
+    Frame *fenc = la->by_index[b], *fref = la->by_index[ref];
+    if (fenc->spec[list][dist - 1] || fenc->searched[list][dist - 1]) return 0;
+    me_add_job(la, mp, 0, fenc, fref, list, dist, nullptr);
+    fenc->spec[list][dist - 1] = true; fenc->spec_eng[list][dist - 1] = 0;
+    if (mp.njobs == XV_ME_MAX_JOBS) { if (me_launch(la, mp, 0) < 0) return -1; me_params_init(la, mp); }
+    return 0;
+}
+
+int x264vfw_cuda_opencl_lowres_init(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *src, int src_on_device)
+{
+    La *la = (La *)h;
+    if (!la || !la->keep_frames) { set_error("opencl-style hooks need a session opened with keep_frames"); return -1; }
+    if (x264vfw_cuda_la_put_frame(h, src, src_on_device, nullptr) < 0) return -1;
+    return la->n_input - 1;
+}
+
+int x264vfw_cuda_opencl_motionsearch(x264vfw_cuda_la *h, int b, int ref, int b_islist1)
+{
+    La *la = (La *)h;
+    if (!la) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    if (hook_frames(la, b < ref ? b : ref, b < ref ? ref : b) < 0) return -1;
+    MeParams mp;
+    me_params_init(la, mp);
+    if (hook_add_search(la, mp, b, ref, b_islist1 != 0) < 0) return -1;
+    return me_launch(la, mp, 0);
+}
+
+int x264vfw_cuda_opencl_finalize_cost(x264vfw_cuda_la *h, int p0, int p1, int b, int cost_out[3])
+{
+    La *la = (La *)h;
+    if (!la) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    if (p0 > b || b > p1 || hook_frames(la, p0, p1) < 0) { if (p0 > b || b > p1) set_error("finalize_cost: need p0 <= b <= p1"); return -1; }
+    if (b - p0 > la->p.bframes + 1 || p1 - b > la->p.bframes + 1) { set_error("finalize_cost: distance too large"); return -1; }
+    const int score = frame_cost(la, la->by_index.data(), p0, p1, b, true);
+    if (score < 0) return -1;
+    Frame *f = la->by_index[b];
+    if (cost_out) { cost_out[0] = f->cost_est[b - p0][p1 - b]; cost_out[1] = f->cost_est_aq[b - p0][p1 - b]; cost_out[2] = f->intra_mbs[b - p0]; }
+    return score;
+}
+
+int x264vfw_cuda_opencl_flush(x264vfw_cuda_la *h)
+{
+    La *la = (La *)h;
+    if (!la) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    if (la_sync(la) < 0) return -1;
+    for (int e = 1; e <= la->me_side; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
+    return 0;
+}
+
+int x264vfw_cuda_opencl_slicetype_prep(x264vfw_cuda_la *h, int first, int num_frames)
+{
+    // upstream precomputes, for trellis B-adapt, the searches of every frame of the window towards the frames up to
+    // bframes away in both directions; here that is one or a few batched launches for any b-adapt
+    La *la = (La *)h;
+    if (!la) return -1;
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    if (hook_frames(la, first, first + num_frames) < 0) return -1;
+    MeParams mp;
+    me_params_init(la, mp);
+    for (int b = first; b <= first + num_frames; b++)
+        for (int j = 1; j <= la->p.bframes; j++) {
+            if (b - j >= first && hook_add_search(la, mp, b, b - j, 0) < 0) return -1;
+            if (b + j <= first + num_frames && hook_add_search(la, mp, b, b + j, 1) < 0) return -1;
+        }
+    return me_launch(la, mp, 0);
+}
+
+int x264vfw_cuda_opencl_slicetype_end(x264vfw_cuda_la *h) { return x264vfw_cuda_opencl_flush(h); }
+
 void x264vfw_cuda_la_counters(x264vfw_cuda_la *h, uint64_t out[8])
 {
     La *la = (La *)h;
