@@ -50,6 +50,25 @@ WORKLOAD = ("C5: 1080p RGB32 bottom-up DIB -> I420 + x264 lookahead preset mediu
             "SURVEY 8(d) clip (300 frames, cuts at 100/200, 2-frame flash at 150) played back and forth")
 
 
+def bind_to_gpu_numa(index):
+    """Run this rank (its session threads, its pinned buffers by first touch) on the CPUs NVML reports as local to the
+    GPU: at N > 1 a rank whose threads or pinned memory sit on the other socket pays for every copy twice."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hnd, n)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -407,6 +426,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 and os.environ.get("X264VFW_BENCH_NUMA", "1") != "0" else None
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -555,7 +575,10 @@ def main():
                 "integer": integer,
                 "speculation": {"kept_fraction": kept, "mbs_kept": stats["kept"], "mbs_researched_in_order": stats["researched"],
                                 "mbs_searched_by_pass": [stats["pass0"], stats["pass1"], stats["pass2"], stats["pass3"]],
-                                "searches_speculative": stats["spec_jobs"], "searches_on_demand": stats["ondemand_jobs"]},
+                                "searches_speculative": stats["spec_jobs"], "searches_on_demand": stats["ondemand_jobs"],
+                                "searches_the_decision_logic_asked_for": stats["searches_asked_for"],
+                                "wasted_speculation": 1.0 - stats["searches_asked_for"] / max(1, stats["spec_jobs"] + stats["ondemand_jobs"]),
+                                "note": "search counts since the sessions were opened (prefill and warm-up included)"},
                 "note": "dominant kernels by device time; their bound is neither HBM nor tensor (SURVEY 8(d)): algorithmic traffic is ~2.7 MB per search "
                         "against 8160 MB searches with a dependent chain, so the GB/s figure is tiny by construction -- the integer roofline (issue slots) "
                         "is in `integer`, the HBM-bound kernels of the path are in `stage1`."}
@@ -589,7 +612,7 @@ def main():
     line = {"metric": "1080p frames/sec through csp+lookahead", "value": value, "unit": "frames/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
-            "run": {"host_wait": os.environ.get("X264VFW_CUDA_SYNC", "spin"),
+            "run": {"host_wait": os.environ.get("X264VFW_CUDA_SYNC", "spin"), "rank0_cpu_affinity": (f"{len(numa_cpus)} CPUs local to the GPU" if numa_cpus else "unrestricted"),
                     "l2_policy": f"inputs larger than L2: {S * F * SRC_BYTES / 1e6:.0f} MB of packed frames per step per GPU",
                     "timed_region_s": main_r["ms_per_step"] * args.steps * 1e-3,
                     "frames_fed": main_r["frames_fed"], "decisions_drained": main_r["decisions_drained"],

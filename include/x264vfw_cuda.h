@@ -406,7 +406,9 @@ int x264vfw_cuda_opencl_slicetype_end( x264vfw_cuda_la *la );
  * is enabled (reset when it is switched on): [0] MBs whose speculative result the ordered verification kept,
  * [1] MBs it searched again in order, [2..5] MBs searched by parallel pass 0..3, [6] SAD 8x8 evaluations,
  * [7] SATD 8x8 evaluations (all search kernels), [8] mb-tree steps run by tree_chain_kernel, [9] mb-tree walks,
- * [10] searches launched speculatively, [11] searches launched on demand, [12] on-demand launches.  Returns 0 / -1. */
+ * [10] searches launched speculatively, [11] searches launched on demand, [12] on-demand launches ([10]..[14] count
+ * since the session was opened), [13] searches the decision logic actually asked for (upstream's count), [14] frames
+ * put.  Returns 0 / -1. */
 int x264vfw_cuda_la_stats( x264vfw_cuda_la *la, uint64_t out[16] );
 
 const char *x264vfw_cuda_last_error( void );

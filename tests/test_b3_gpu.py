@@ -58,7 +58,7 @@ def test_mbtree_propagate_cost_and_list(ctx):
     try:
         for i in range(n):
             orc.put_i420(ol.oracle_convert(clip.packed(i, "bgra"), 9 | 0x1000, 2, 2, 0, w, h))
-        orc.mbtree([0, 1, 2], [3, 5, 3], 0)                       # types P B P: evaluates (0,2,2) and (0,2,1)
+        orc.mbtree([0, 1, 2], [1, 5, 3], 1)                       # types I B P, keyframe walk: evaluates (0,2,2) and (0,2,1)
         intra, invq, lc = orc.intra_cost(1), orc.inv_qscale(1), orc.lowres_costs(1, 1, 1)
         mv0, mv1 = orc.mvs(1, 0, 1), orc.mvs(1, 1, 1)
     finally:
@@ -127,20 +127,23 @@ def test_pixel_sad_satd_and_xn(ctx):
     off2 = (ys2[:, 0] * w + xs2[:, 0]).astype(np.int32)
     offr = (ys2 * w + xs2).astype(np.int32)
     da, db, d1, d2, dr = dev(a), dev(b), dev(off1), dev(off2), dev(offr)
-    blk = lambda p, y, x: np.ascontiguousarray(p[y:y + 8, x:x + 8])
+    def score(fn, p, y, x, q, y2, x2):
+        b1, b2 = np.ascontiguousarray(p[y:y + 8, x:x + 8]), np.ascontiguousarray(q[y2:y2 + 8, x2:x2 + 8])      # both stay alive for the call
+        return fn(b1.ctypes.data, b2.ctypes.data)
+
     for satd in (0, 1):
         sc = torch.zeros(n, dtype=torch.int32, device="cuda")
         b3.pixel_cmp_8x8(ctx, satd, da.data_ptr(), w, db.data_ptr(), w, d1.data_ptr(), d2.data_ptr(), sc.data_ptr(), n)
         ctx.sync()
         fn = o.orc_test_satd_8x8 if satd else o.orc_test_sad_8x8
-        want = [fn(blk(a, ys[i], xs[i]).ctypes.data, blk(b, ys2[i, 0], xs2[i, 0]).ctypes.data) for i in range(n)]
+        want = [score(fn, a, ys[i], xs[i], b, ys2[i, 0], xs2[i, 0]) for i in range(n)]
         assert sc.cpu().numpy().tolist() == want, satd
     for nref in (3, 4):
         sc = torch.zeros(n * nref, dtype=torch.int32, device="cuda")
         dro = dev(np.ascontiguousarray(offr[:, :nref]))
         b3.pixel_sad_xn_8x8(ctx, nref, da.data_ptr(), w, d1.data_ptr(), db.data_ptr(), w, dro.data_ptr(), sc.data_ptr(), n)
         ctx.sync()
-        want = [o.orc_test_sad_8x8(blk(a, ys[i], xs[i]).ctypes.data, blk(b, ys2[i, k], xs2[i, k]).ctypes.data) for i in range(n) for k in range(nref)]
+        want = [score(o.orc_test_sad_8x8, a, ys[i], xs[i], b, ys2[i, k], xs2[i, k]) for i in range(n) for k in range(nref)]
         assert sc.cpu().numpy().tolist() == want, nref
 
 

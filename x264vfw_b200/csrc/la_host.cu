@@ -133,7 +133,7 @@ struct La {
     // for the next decision (same pattern, shifted by the mini-GOP just emitted): {frame, list, dist}
     std::vector<std::array<int, 3>> asked_now, wanted;
     int predict = 1;
-    double spec_threshold = 0.4;   // speculate a (list,distance) pair when at least this share of frames asked for it
+    double spec_threshold = 0.7;   // speculate a (list,distance) pair when at least this share of frames asked for it
     int decide_lag = 1;      // run the decision due at put(n) during put(n+lag): same decisions, searches overlap
     bool flushing = false;
     int la_me_hex, la_subpel_refine, la_satd, do_edges;
@@ -204,6 +204,7 @@ struct La {
     // ahead of time by the worker (when it is done with frame n - io_depth) and handed over through ring_frame[];
     // ev_frame_ready orders the kernel after the slot's reset on the main stream.
     int fused = 1;
+    int caller_block = 1;    // yield mode: the caller sleeps on the interrupt while its copies run (X264VFW_CUDA_CALLER_BLOCK=0: polls)
     Frame *ring_frame[4] = {nullptr};
     cudaEvent_t ev_frame_ready[4] = {nullptr};
     std::mutex prof_mu;
@@ -217,6 +218,7 @@ struct La {
     int sync_kind = 0; double t_sync_kind[3] = {0, 0, 0}; uint64_t n_sync_kind[3] = {0, 0, 0};   // host wall-clock seconds (diagnostics)
     uint64_t n_ondemand = 0, n_ondemand_jobs = 0, n_spec_jobs = 0;
     uint64_t n_logical[2][BMAX + 1] = {{0}};      // searches upstream's control flow actually asked for, by list/distance
+    uint64_t n_launched[2][BMAX + 1] = {{0}};     // searches launched (speculative + on demand), by list/distance
     Prof prof;
 };
 
@@ -253,6 +255,15 @@ static int wait_event(La *la, cudaEvent_t ev)
     }
     LA_CUDA(cudaEventSynchronize(ev));
     return 0;
+}
+
+// The CALLER's wait for its borrowed buffers (a whole H2D -> conversion -> D2H chain, ~1 ms with several streams on
+// the link): on a node with fewer cores than session threads (yield mode) it sleeps on the interrupt instead of
+// polling -- the session worker, whose waits are short and latency-critical, keeps the core.
+static int wait_event_caller(La *la, cudaEvent_t ev)
+{
+    if (la->yielding && la->caller_block) { LA_CUDA(cudaEventSynchronize(ev)); return 0; }
+    return wait_event(la, ev);
 }
 
 static cudaEvent_t prof_event(La *la)
@@ -586,6 +597,7 @@ static void me_add_job(La *la, MeParams &mp, int eng, Frame *fenc, Frame *ref, i
     }
     mp.njobs++;
     la->n_mb_search += la->g.mb_count;
+    la->n_launched[list][dist - 1]++;
     if (la->stats_verbose) { char b[96]; snprintf(b, sizeof(b), " [f%d l%d d%d%s%s]", fenc->i_frame, list, dist, w ? " W" : "", j.guess ? "" : " noguess"); la->dbg_jobs += b; }
 }
 
@@ -1685,6 +1697,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_ME_FORCE_MISS")) la->me_force_miss = atoi(e) != 0;
     if (const char *e = getenv("X264VFW_CUDA_ASYNC")) la->async = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_FUSED")) la->fused = atoi(e);
+    if (const char *e = getenv("X264VFW_CUDA_CALLER_BLOCK")) la->caller_block = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_SYNC")) {      // spin (default) | yield | block | hybrid | hybrid:<microseconds>
         la->yielding = !strcmp(e, "yield");
         la->blocking = strcmp(e, "spin") != 0 && !la->yielding;
@@ -1740,7 +1753,7 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
                   cudaMemcpy(la->d_exp2_lut, e2, 64, cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&la->d_weight_buf, g.lplane + 64) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&la->ev_io, cudaEventDisableTiming | (la->blocking ? cudaEventBlockingSync : 0)) == cudaSuccess &&
+             cudaEventCreateWithFlags(&la->ev_io, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&la->ev_csp, cudaEventDisableTiming) == cudaSuccess &&
@@ -1822,6 +1835,8 @@ void x264vfw_cuda_la_close(x264vfw_cuda_la *h)
     if (getenv("X264VFW_CUDA_STATS")) {
         fprintf(stderr, "[x264vfw_cuda] frames %d searches asked for by (list,dist):", la->n_input);
         for (int l = 0; l < 2; l++) for (int d = 0; d <= la->p.bframes; d++) fprintf(stderr, " l%d/d%d=%llu", l, d + 1, (unsigned long long)la->n_logical[l][d]);
+        fprintf(stderr, "  | launched:");
+        for (int l = 0; l < 2; l++) for (int d = 0; d <= la->p.bframes; d++) fprintf(stderr, " l%d/d%d=%llu", l, d + 1, (unsigned long long)la->n_launched[l][d]);
         fprintf(stderr, "  | speculative jobs %llu, on-demand launches %llu (%llu jobs)\n", (unsigned long long)la->n_spec_jobs,
                 (unsigned long long)la->n_ondemand, (unsigned long long)la->n_ondemand_jobs);
         if (la->io_n) fprintf(stderr, "[x264vfw_cuda] I/O stream us per frame: wait for planes %.0f, H2D %.0f, conversion %.0f, D2H %.0f\n",
@@ -2005,7 +2020,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
         }
         la->n_put++;
         la->t_put += now_s() - t_begin;
-        if (borrowed) { const double t0 = now_s(); if (wait_event(la, la->ev_io) < 0) return -1; la->t_io += now_s() - t0; }
+        if (borrowed) { const double t0 = now_s(); if (wait_event_caller(la, la->ev_io) < 0) return -1; la->t_io += now_s() - t0; }
         else if (wait_dev_src) { const double t0 = now_s(); if (wait_event(la, ev_csp) < 0) return -1; la->t_io += now_s() - t0; }
         if (borrowed && la->d_me_stats && la->io_ev[0]) {
             for (int k = 0; k < 4; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, la->io_ev[k], la->io_ev[k + 1]) == cudaSuccess) la->io_ms[k] += ms; }
@@ -2044,7 +2059,7 @@ int x264vfw_cuda_la_put_frame(x264vfw_cuda_la *h, const x264vfw_cuda_image_t *sr
     }
     la->t_decide += t_dec;
     la->t_put += (la->decide_lag == 0 ? t_mid - t_begin : now_s() - t_begin - t_dec);
-    if (borrowed) { const double t0 = now_s(); if (wait_event(la, la->ev_io) < 0) return -1; la->t_io += now_s() - t0; }
+    if (borrowed) { const double t0 = now_s(); if (wait_event_caller(la, la->ev_io) < 0) return -1; la->t_io += now_s() - t0; }
     else if (wait_dev_src) { const double t0 = now_s(); if (wait_event(la, ev_csp) < 0) return -1; la->t_io += now_s() - t0; }
     if (borrowed && la->d_me_stats && la->io_ev[0]) {
         for (int k = 0; k < 4; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, la->io_ev[k], la->io_ev[k + 1]) == cudaSuccess) la->io_ms[k] += ms; }
@@ -2200,6 +2215,8 @@ int x264vfw_cuda_la_stats(x264vfw_cuda_la *h, uint64_t out[16])
     }
     out[8] = la->n_tree_steps; out[9] = la->n_tree_walks;
     out[10] = la->n_spec_jobs; out[11] = la->n_ondemand_jobs; out[12] = la->n_ondemand;
+    for (int l = 0; l < 2; l++) for (int d = 0; d <= BMAX; d++) out[13] += la->n_logical[l][d];
+    out[14] = (uint64_t)la->n_input;
     return 0;
 }
 

@@ -23,9 +23,18 @@
 namespace xv {
 
 #define BIG_COST 0x3fffffff
-#define WIN_W 64
-#define WIN_H 40
-#define WIN_R 16
+// Full-pel window staged in shared memory: the block itself + WIN_R pixels around the search centre, x origin
+// aligned down to 16 bytes (cp.async chunks): 2 * WIN_R + 8 + 15 <= WIN_W, 2 * WIN_R + 8 <= WIN_H.  Candidates that
+// leave the window (the hexagon may walk up to me_range + 1 = 17 pixels) are scored from global memory instead --
+// same result, rarer than 1 in 100 on the bench clip -- so the window radius is a pure occupancy knob.
+#ifndef WIN_R
+#define WIN_R 12
+#endif
+#define WIN_W ((2 * WIN_R + 8 + 15 + 15) & ~15)
+#define WIN_H (2 * WIN_R + 8)
+#ifndef PASS_BLOCKS_PER_SM
+#define PASS_BLOCKS_PER_SM 12
+#endif
 #define SUB_W 32
 #define SUB_H 12
 
@@ -251,14 +260,15 @@ __device__ __forceinline__ void win_issue(const Mb<LPS> &m, GroupSmem &sm, const
     const uint8_t *base = m.fref_w + wy0 * m.stride + wx0;
     __syncwarp();                                        // previous readers of the window are done
     if (on) {
-        // lane gl copies chunk (row, col16) = (gl/4 + (GL/4) k, gl%4)
-        const uint8_t *src = base + (m.gl >> 2) * m.stride + (m.gl & 3) * 16;
-        uint8_t *dst = sm.win + (m.gl >> 2) * WIN_W + (m.gl & 3) * 16;
-        const int sstep = (GL / 4) * m.stride;
+        // the window is WIN_H rows of WIN_W / 16 chunks of 16 bytes; lane gl copies chunks gl, gl + GL, ...
+        constexpr int CPR = WIN_W / 16, NCH = WIN_H * CPR;
 #pragma unroll
-        for (int k = 0; k < (WIN_H * 4) / GL; k++) {
-            cpa16(dst, src);
-            src += sstep; dst += (GL / 4) * WIN_W;
+        for (int k = 0; k < (NCH + GL - 1) / GL; k++) {
+            const int c = m.gl + k * GL;
+            if (NCH % GL == 0 || c < NCH) {
+                const int row = c / CPR, col = c - row * CPR;
+                cpa16(sm.win + row * WIN_W + col * 16, base + row * m.stride + col * 16);
+            }
         }
     }
 }
@@ -662,7 +672,7 @@ __device__ __forceinline__ void pass_search_store(const LaGeom &g, const MeParam
 // inputs change.  (Collecting the MBs to re-search per 256-MB tile and searching them with a
 // small grid was tried: same frame rate within noise, longer when they cluster, so not kept.)
 template <int LPS, bool QPRED>
-__global__ void __launch_bounds__(32 * PASS_WARPS, 10)
+__global__ void __launch_bounds__(32 * PASS_WARPS, PASS_BLOCKS_PER_SM)
 me_pass_kernel(LaGeom g, MeParams P, int pass)
 {
     constexpr int GL = Mb<LPS>::GL, NG = 32 / GL;
@@ -732,8 +742,14 @@ __device__ __forceinline__ void sts_rec(int2 *p, int mv, int epoch)
     asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" :: "r"((unsigned)__cvta_generic_to_shared(p)), "r"(mv), "r"(epoch) : "memory");
 }
 
+// Register budget: the band's 16 warps hold their registers for the whole walk although most of the time they only
+// poll; at the compiler's own choice (123 registers) one band fills an SM's register file and nothing else -- no
+// block of the parallel passes of another stream -- can run beside it.
+#ifndef VERIFY_MAXREG
+#define VERIFY_MAXREG 128
+#endif
 template <bool QPRED>
-__global__ void __launch_bounds__(32 * VERIFY_ROWS, 1)
+__global__ void __maxnreg__(VERIFY_MAXREG)
 me_verify_kernel(LaGeom g, MeParams P)
 {
     extern __shared__ __align__(16) uint8_t vsm[];

@@ -214,7 +214,7 @@ class Lookahead:
         if lib.x264vfw_cuda_la_stats(self.h, c) < 0:
             raise CudaError(last_error())
         names = ("kept", "researched", "pass0", "pass1", "pass2", "pass3", "sad8x8", "satd8x8", "tree_steps", "tree_walks",
-                 "spec_jobs", "ondemand_jobs", "ondemand_launches")
+                 "spec_jobs", "ondemand_jobs", "ondemand_launches", "searches_asked_for", "frames_since_open")
         return {k: int(c[i]) for i, k in enumerate(names)}
 
     def counters(self):
