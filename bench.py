@@ -459,12 +459,14 @@ def main():
     dev_frames = [[None] * args.clip_frames for _ in range(S)]
     pin_frames = [[None] * e2e_frames for _ in range(S)]
 
+    dev = torch.device("cuda", local_rank)
+
     def sink(k, n, f):
         t = torch.from_numpy(f)
         if n < e2e_frames:
             t = t.pin_memory()
             pin_frames[k][n] = t.numpy()
-        dev_frames[k][n] = t.cuda()
+        dev_frames[k][n] = t.to(dev)          # explicit device: the generator threads' current CUDA device is not this rank's
 
     generate_clips(my_streams, args.clip_frames, sink)
     dev_ptrs = [[t.data_ptr() for t in clip] for clip in dev_frames]

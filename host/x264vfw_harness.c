@@ -179,6 +179,14 @@ static void stream_drain(harness_stream *s)
     }
 }
 
+/* the library's error string is per thread: keep the first failure of a stream thread where the caller can read it */
+static char g_harness_error[512];
+static void keep_error(void)
+{
+    if (!g_harness_error[0]) { strncpy(g_harness_error, x264vfw_cuda_last_error(), sizeof(g_harness_error) - 1); }
+}
+const char *harness_last_error(void) { return g_harness_error; }
+
 static void *stream_thread(void *arg)
 {
     harness_stream *s = (harness_stream *)arg;
@@ -193,12 +201,12 @@ static void *stream_thread(void *arg)
         int k = n > 1 ? (int)(s->pos % (2 * n - 2)) : 0;
         if (k >= n) k = 2 * n - 2 - k;
         x264vfw_cuda_image_t pic, conv_pic, *cp = NULL;
-        if (x264vfw_cuda_img_fill(&pic, (uint8_t *)s->frames[k], s->in_csp, s->width, s->height) < 0) { s->error = 1; break; }
+        if (x264vfw_cuda_img_fill(&pic, (uint8_t *)s->frames[k], s->in_csp, s->width, s->height) < 0) { keep_error(); s->error = 1; break; }
         if (s->conv) {
             x264vfw_cuda_picture_layout(&conv_pic, s->conv[s->pos % s->n_conv], s->out_csp, s->width, s->height);
             cp = &conv_pic;
         }
-        if (x264vfw_cuda_la_put_frame(s->la, &pic, s->on_device, cp) < 0) { s->error = 1; break; }
+        if (x264vfw_cuda_la_put_frame(s->la, &pic, s->on_device, cp) < 0) { keep_error(); s->error = 1; break; }
         stream_drain(s);
         s->pos++;
     }
@@ -223,7 +231,7 @@ int harness_flush_streams(harness_stream *streams, int n)
     for (int i = 0; i < n; i++) {
         harness_stream *s = &streams[i];
         if (!s->qp) continue;
-        if (x264vfw_cuda_la_flush(s->la) < 0) { s->error = 1; rc = -1; continue; }
+        if (x264vfw_cuda_la_flush(s->la) < 0) { keep_error(); s->error = 1; rc = -1; continue; }
         stream_drain(s);
     }
     return rc;

@@ -38,6 +38,7 @@ def _load():
     lib.harness_run_streams.restype = C.c_int
     lib.harness_run_streams.argtypes = [C.POINTER(_Stream), C.c_int, C.c_int]
     lib.harness_stream_free.argtypes = [C.POINTER(_Stream)]
+    lib.harness_last_error.restype = C.c_char_p
     lib.harness_flush_streams.restype = C.c_int
     lib.harness_flush_streams.argtypes = [C.POINTER(_Stream), C.c_int]
     return lib
@@ -83,13 +84,13 @@ class StreamSet:
         """Feed `count` frames to every stream concurrently (native threads; returns when all did)."""
         if self.lib.harness_run_streams(self.arr, self.n, count) < 0:
             from ._lib import last_error
-            raise RuntimeError("harness_run_streams failed: " + last_error())
+            raise RuntimeError("harness_run_streams failed: " + (self.lib.harness_last_error() or b"").decode() + " " + last_error())
 
     def flush(self) -> None:
         """x264vfw_cuda_la_flush on every session, decisions drained into the counters / the log."""
         if self.lib.harness_flush_streams(self.arr, self.n) < 0:
             from ._lib import last_error
-            raise RuntimeError("harness_flush_streams failed: " + last_error())
+            raise RuntimeError("harness_flush_streams failed: " + (self.lib.harness_last_error() or b"").decode() + " " + last_error())
 
     def log(self, s):
         """Logged decisions of stream s in coded order: dicts with the decision fields and the two hashes."""
