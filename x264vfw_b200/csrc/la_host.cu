@@ -195,7 +195,7 @@ struct La {
     int async = 1;
     // host waits: spin (lowest latency; one busy core per waiting thread) or block on an interrupt
     // (X264VFW_CUDA_SYNC=block: for hosts with fewer cores than session threads)
-    bool blocking = false, yielding = false; int spin_us = 60; cudaEvent_t ev_sync = nullptr;   // default: spin; hybrid: spin for spin_us, then block
+    bool blocking = false, yielding = false, notify = false; int spin_us = 60; cudaEvent_t ev_sync = nullptr;   // default: spin; hybrid: spin for spin_us, then block
     int io_depth = 2;                           // planes ring: frames the caller may run ahead of the worker
     uint8_t *d_planes_ring[4] = {nullptr}; x264vfw_cuda_image_t planes_ring[4];
     cudaEvent_t ev_csp_ring[4] = {nullptr}, ev_free_ring[4] = {nullptr};
@@ -230,11 +230,63 @@ static int la_sync(La *la);
 static int wait_engine(La *la, int eng, uint64_t seq);
 
 static inline double now_s();
+
+// ---- one polling thread per process (X264VFW_CUDA_SYNC=notify) -------------------------------------------------
+// On a node with fewer cores than session threads every polling waiter steals the core of a thread that has work to
+// do.  In this mode a waiter registers its event and SLEEPS on a condition variable; a single notifier thread polls
+// all registered events and wakes the owners (a few microseconds of wake-up latency instead of a scheduler
+// quantum).  At 8 ranks x 8 streams that leaves 8 pollers instead of 128.
+struct Notifier {
+    struct Item { cudaEvent_t ev; int device; std::condition_variable *cv; bool *done; cudaError_t *err; };
+    std::mutex mu;
+    std::condition_variable cv_work;
+    std::vector<Item> items;
+    bool started = false;
+    void run()
+    {
+        int cur = -1;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_work.wait(lk, [&] { return !items.empty(); });
+            for (size_t i = 0; i < items.size();) {
+                Item &it = items[i];
+                if (it.device != cur) { cudaSetDevice(it.device); cur = it.device; }
+                const cudaError_t q = cudaEventQuery(it.ev);
+                if (q == cudaErrorNotReady) { i++; continue; }
+                *it.err = q; *it.done = true;
+                it.cv->notify_one();
+                items[i] = items.back(); items.pop_back();
+            }
+            lk.unlock();
+            sched_yield();
+        }
+    }
+    int wait(int device, cudaEvent_t ev)
+    {
+        std::condition_variable cv;
+        bool done = false;
+        cudaError_t err = cudaSuccess;
+        std::unique_lock<std::mutex> lk(mu);
+        if (!started) { started = true; std::thread([this] { run(); }).detach(); }
+        items.push_back(Item{ev, device, &cv, &done, &err});
+        cv_work.notify_one();
+        cv.wait(lk, [&] { return done; });
+        if (err != cudaSuccess) { set_error("cudaEventQuery failed: %s", cudaGetErrorString(err)); return -1; }
+        return 0;
+    }
+};
+// heap-allocated and never destroyed: its thread is detached and may be waiting on the condition variable at exit
+static Notifier &g_notifier = *new Notifier();
+
 // Host wait for an event: poll for a short while (most waits are for a few light kernels), then
 // block on the interrupt so that long waits (a search batch, a frame's copies) do not hold a core
 // -- a node runs 2 threads per stream, usually more than it has cores once several GPUs are used.
 static int wait_event(La *la, cudaEvent_t ev)
 {
+    if (la->notify) {
+        if (cudaEventQuery(ev) == cudaSuccess) return 0;       // already there: no round trip through the notifier
+        return g_notifier.wait(la->device, ev);
+    }
     if (la->yielding) {
         // poll, but give the core away between polls: for nodes with more session threads than cores
         for (;;) {
@@ -263,6 +315,7 @@ static int wait_event(La *la, cudaEvent_t ev)
 static int wait_event_caller(La *la, cudaEvent_t ev)
 {
     if (la->yielding && la->caller_block) { LA_CUDA(cudaEventSynchronize(ev)); return 0; }
+    // notify mode: wait_event already sleeps
     return wait_event(la, ev);
 }
 
@@ -406,7 +459,7 @@ static int la_sync(La *la)
     struct Acc { La *l; double t; ~Acc() { l->t_sync += now_s() - t; } } acc{la, t0};
     if (!la->pending.empty())
         LA_CUDA(cudaMemcpyAsync(la->h_results, la->d_results, RESULT_SLOTS * 4 * sizeof(int), cudaMemcpyDeviceToHost, la->st));
-    if (la->blocking || la->yielding) { LA_CUDA(cudaEventRecord(la->ev_sync, la->st)); if (wait_event(la, la->ev_sync) < 0) return -1; }
+    if (la->blocking || la->yielding || la->notify) { LA_CUDA(cudaEventRecord(la->ev_sync, la->st)); if (wait_event(la, la->ev_sync) < 0) return -1; }
     else LA_CUDA(cudaStreamSynchronize(la->st));
     la->n_sync++;
     la->t_sync_kind[la->sync_kind] += now_s() - t0; la->n_sync_kind[la->sync_kind]++; la->sync_kind = 0;
@@ -1698,9 +1751,10 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_ASYNC")) la->async = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_FUSED")) la->fused = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_CALLER_BLOCK")) la->caller_block = atoi(e);
-    if (const char *e = getenv("X264VFW_CUDA_SYNC")) {      // spin (default) | yield | block | hybrid | hybrid:<microseconds>
+    if (const char *e = getenv("X264VFW_CUDA_SYNC")) {      // spin (default) | yield | notify | block | hybrid | hybrid:<microseconds>
         la->yielding = !strcmp(e, "yield");
-        la->blocking = strcmp(e, "spin") != 0 && !la->yielding;
+        la->notify = !strcmp(e, "notify");
+        la->blocking = strcmp(e, "spin") != 0 && !la->yielding && !la->notify;
         if (!strcmp(e, "block")) la->spin_us = 0;
         else if (!strncmp(e, "hybrid:", 7)) la->spin_us = atoi(e + 7);
     }
