@@ -76,7 +76,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=8, help="independent streams per GPU")
-    ap.add_argument("--frames-per-step", type=int, default=128, help="frames per stream per step (timed region >= 2 s at the default 20 steps)")
+    ap.add_argument("--frames-per-step", type=int, default=160, help="frames per stream per step (timed region >= 2 s at the default 20 steps)")
     ap.add_argument("--clip-frames", type=int, default=CLIP_FRAMES)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -124,7 +124,8 @@ struct La {
     int ext = X264VFW_CUDA_EXT_NONE;   // packed 4:2:2 -> I444 uses the documented extension conversion
     int me_rows = 0;         // warps per search in the wavefront kernel
     int me_variant = 1;      // 0: plain wavefront, 1: speculative parallel passes + verification wavefront
-    int me_passes = 3;       // parallel passes of the speculative search
+    int me_passes = 3;       // parallel (Jacobi) passes of the speculative search: pass 0 = every MB from the guessed field
+    int me_relax = 0;        // row-relaxation passes after them (X264VFW_CUDA_ME_RELAX; measured slower than Jacobi passes: profiles/README.md)
     int me_force_miss = 0;   // diagnostics (X264VFW_CUDA_ME_FORCE_MISS): the verification keeps nothing = cost at a 0 % hit rate
     uint64_t n_tree_steps = 0, n_tree_walks = 0;
     int *d_me_stats = nullptr;
@@ -608,7 +609,7 @@ static void me_params_init(La *la, MeParams &mp)
     mp.subpel_refine = la->la_subpel_refine; mp.satd = la->la_satd; mp.me_range = la->p.me_range;
     mp.cost_mv = la->d_cost_mv + la->cost_mv_half;
     mp.rows_in_flight = la->me_rows;
-    mp.variant = la->me_variant; mp.npasses = la->me_passes; mp.stats = la->d_me_stats;
+    mp.variant = la->me_variant; mp.npasses = la->me_passes; mp.nrelax = la->me_relax; mp.stats = la->d_me_stats;
     mp.force_miss = la->me_force_miss;
 }
 
@@ -676,8 +677,10 @@ static int me_kernels(La *la, cudaStream_t st, const MeParams &mp, bool prof)
         ProfScope ps(la, prof ? K_ME_PASS : -1, st);
         for (int pass = 0; pass < mp.npasses; pass++)
             if (launch_me_pass(st, la->g, mp, pass) < 0) return -1;
+        for (int r = 0; r < mp.nrelax; r++)
+            if (launch_me_verify(st, la->g, mp, mp.npasses + r) < 0) return -1;
     }
-    la->n_launch += mp.npasses;
+    la->n_launch += mp.npasses + mp.nrelax;
     ProfScope ps(la, prof ? K_ME : -1, st);
     return launch_me_verify(st, la->g, mp);
 }
@@ -1746,6 +1749,8 @@ int x264vfw_cuda_la_open(x264vfw_cuda_la **pla, const x264vfw_cuda_la_params *pa
     if (const char *e = getenv("X264VFW_CUDA_ME_SIDE")) { la->me_side = atoi(e); if (la->me_side < 1) la->me_side = 1; if (la->me_side > ME_SIDE) la->me_side = ME_SIDE; }
     if (const char *e = getenv("X264VFW_CUDA_ME_VARIANT")) la->me_variant = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ME_PASSES")) { la->me_passes = atoi(e); if (la->me_passes < 1) la->me_passes = 1; if (la->me_passes > 4) la->me_passes = 4; }
+    if (const char *e = getenv("X264VFW_CUDA_ME_RELAX")) { la->me_relax = atoi(e); if (la->me_relax < 0) la->me_relax = 0; if (la->me_relax > 3) la->me_relax = 3; }
+    if (la->me_passes + la->me_relax > 4) la->me_relax = 4 - la->me_passes;
     if (const char *e = getenv("X264VFW_CUDA_ME_GUESS")) la->me_guess = atoi(e);
     if (const char *e = getenv("X264VFW_CUDA_ME_FORCE_MISS")) la->me_force_miss = atoi(e) != 0;
     if (const char *e = getenv("X264VFW_CUDA_ASYNC")) la->async = atoi(e);

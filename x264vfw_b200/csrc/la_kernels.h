@@ -67,14 +67,15 @@ struct MeParams {
     int me_range;
     const uint16_t *cost_mv;      // centred table
     int variant;                  // 0: plain wavefront (me_wavefront_kernel); 1: speculative parallel passes + verification wavefront
-    int npasses;                  // variant 1: parallel passes before the verification
+    int npasses;                  // variant 1: parallel (Jacobi) passes before the verification
+    int nrelax;                   // variant 1: row-relaxation passes after them (la_me2_kernel.cu: RELAX)
     int *stats;                   // optional device counters: [0] kept, [1] re-searched in order, [2..5] searched in pass 0..3,
                                   // [6] SAD 8x8 evaluations, [7] SATD 8x8 evaluations
     int force_miss;               // diagnostics: the verification keeps nothing (every MB re-searched in order) = 0 % hit rate
 };
 int launch_me(cudaStream_t st, const LaGeom &g, const MeParams &p);                    // plain wavefront
 int launch_me_pass(cudaStream_t st, const LaGeom &g, const MeParams &p, int pass);     // one speculative parallel pass
-int launch_me_verify(cudaStream_t st, const LaGeom &g, const MeParams &p);             // exact verification wavefront
+int launch_me_verify(cudaStream_t st, const LaGeom &g, const MeParams &p, int relax_pass = -1);   // exact verification wavefront (relax_pass >= 1: a row-relaxation pass)
 
 // ---- per-MB cost selection + frame accumulators ([x264] rest of slicetype_mb_cost) ---------
 struct FinalizeJob {

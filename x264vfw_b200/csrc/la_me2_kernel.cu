@@ -748,9 +748,14 @@ __device__ __forceinline__ void sts_rec(int2 *p, int mv, int epoch)
 #ifndef VERIFY_MAXREG
 #define VERIFY_MAXREG 128
 #endif
-template <bool QPRED>
+// RELAX = row relaxation: the same walk along every row, but WITHOUT waiting for the row below -- each row takes the
+// row below as it currently is (the previous pass's results, possibly already updated by that row's own warp; whatever
+// it reads is what it records as "assumed"), all rows run at once.  One such launch resolves every dependency chain
+// that runs along a row (the right neighbour is the first predictor candidate, so most chains do), which a Jacobi
+// pass advances by only one MB.  The exact, ordered launch afterwards finds far fewer MBs to search again.
+template <bool QPRED, bool RELAX>
 __global__ void __maxnreg__(VERIFY_MAXREG)
-me_verify_kernel(LaGeom g, MeParams P)
+me_verify_kernel(LaGeom g, MeParams P, int relax_pass)
 {
     extern __shared__ __align__(16) uint8_t vsm[];
     const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
@@ -760,12 +765,13 @@ me_verify_kernel(LaGeom g, MeParams P)
     const MeJob &job = P.job[blockIdx.y];
     const unsigned FULLM = 0xffffffffu;
     const int nbands = (g.mb_h + VERIFY_ROWS - 1) / VERIFY_ROWS;
-  for (;;) {
+  for (int round = 0;; round++) {
+    if (RELAX && round) return;                            // relaxation: one band per block, no hand-over
     __syncthreads();                                       // everybody is done with the previous band's records
-    if (threadIdx.x == 0) s_ticket = atomicAdd(job.ticket, 1);
+    if (!RELAX && threadIdx.x == 0) s_ticket = atomicAdd(job.ticket, 1);
     for (int i = lane; i < g.mb_w; i += 32) srec[wrow * g.mb_w + i] = make_int2(0, 0);   // epoch is never 0
     __syncthreads();
-    const int ticket = s_ticket;
+    const int ticket = RELAX ? (int)blockIdx.x : s_ticket;
     if (ticket >= nbands) return;
     const int mb_y = g.mb_h - 1 - (ticket * VERIFY_ROWS + wrow);   // bottom band first, warp 0 = its bottom row
     if (mb_y < 0) continue;
@@ -788,8 +794,12 @@ me_verify_kernel(LaGeom g, MeParams P)
     int2 *mine_s = srec + wrow * g.mb_w;
     const bool top = wrow == VERIFY_ROWS - 1;              // read by another block: publish to global memory too
     const int row0 = mb_y * g.mb_w;
-    auto ld_below = [&](int p) -> uint2 { return below_local ? lds_rec(below + p) : ld_rec2(below + p); };
-    auto publish = [&](int xcol, int mv) { sts_rec(mine_s + xcol, mv, epoch); if (top) st_rec2(mine + xcol, mv, epoch); };
+    const int *below_mvs = job.mvs + (mb_y + 1) * g.mb_w;  // RELAX: the row below as it is right now
+    auto ld_below = [&](int p) -> uint2 {
+        if (RELAX) return make_uint2((unsigned)__ldcg(below_mvs + p), (unsigned)epoch);
+        return below_local ? lds_rec(below + p) : ld_rec2(below + p);
+    };
+    auto publish = [&](int xcol, int mv) { if (RELAX) return; sts_rec(mine_s + xcol, mv, epoch); if (top) st_rec2(mine + xcol, mv, epoch); };
 
     Mb<4> m;                                               // the whole warp on one MB: 8 candidates x 4 lanes
     m.gl = lane; m.slot = lane >> 2; m.r0 = (lane & 3) * 2;
@@ -911,6 +921,8 @@ me_verify_kernel(LaGeom g, MeParams P)
             if (lane == 0) {
                 job.mvs[mb_xy] = out_mv;
                 job.mv_costs[mb_xy] = out_cost;
+                // a relaxation pass records what it searched from, for the ordered launch to check
+                if (RELAX) job.assumed[mb_xy] = make_int4(mhas_r ? rm : 0, has_below ? b_0 : 0, has_bl ? b_m1 : 0, has_br ? b_p1 : 0);
                 publish(mb_x, out_mv);
             }
             if (lane == p) G = out_mv;                     // the next lane's right neighbour
@@ -927,12 +939,17 @@ me_verify_kernel(LaGeom g, MeParams P)
             x -= p; ns = 32;
         } else { __nanosleep(below_local ? 20 : ns); if (ns < 256) ns <<= 1; }
     }
-    if (P.stats && lane == 0) { atomicAdd(P.stats, n_hit); atomicAdd(P.stats + 1, n_miss); atomicAdd(P.stats + 6, n_sad); atomicAdd(P.stats + 7, n_satd); }
+    if (P.stats && lane == 0) {
+        if (RELAX) atomicAdd(P.stats + 2 + min(relax_pass, 3), n_miss);       // counted with the parallel passes
+        else { atomicAdd(P.stats, n_hit); atomicAdd(P.stats + 1, n_miss); }
+        atomicAdd(P.stats + 6, n_sad); atomicAdd(P.stats + 7, n_satd);
+    }
   }
 }
 
 
-int launch_me_verify(cudaStream_t st, const LaGeom &g, const MeParams &p)
+// relax_pass < 0: the exact ordered verification; >= 1: a row-relaxation pass (counted as parallel pass `relax_pass`)
+int launch_me_verify(cudaStream_t st, const LaGeom &g, const MeParams &p, int relax_pass)
 {
     if (p.njobs <= 0) return 0;
     // every band of a search resident at once: the row pipeline is up to mb_w/2 rows deep
@@ -940,13 +957,21 @@ int launch_me_verify(cudaStream_t st, const LaGeom &g, const MeParams &p)
     const size_t smem = VERIFY_ROWS * sizeof(GroupSmem) + (size_t)VERIFY_ROWS * g.mb_w * sizeof(int2);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(me_verify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(me_verify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(me_verify_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(me_verify_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(me_verify_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(me_verify_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_done = true;
     }
     if (smem > 160 * 1024) { set_error("frame too wide for the verification kernel (%d MBs)", g.mb_w); return -1; }
-    if (p.subpel_refine >= 3) me_verify_kernel<true><<<grid, 32 * VERIFY_ROWS, smem, st>>>(g, p);
-    else me_verify_kernel<false><<<grid, 32 * VERIFY_ROWS, smem, st>>>(g, p);
+    const bool q = p.subpel_refine >= 3;
+    if (relax_pass >= 1) {
+        if (q) me_verify_kernel<true, true><<<grid, 32 * VERIFY_ROWS, smem, st>>>(g, p, relax_pass);
+        else me_verify_kernel<false, true><<<grid, 32 * VERIFY_ROWS, smem, st>>>(g, p, relax_pass);
+    } else {
+        if (q) me_verify_kernel<true, false><<<grid, 32 * VERIFY_ROWS, smem, st>>>(g, p, 0);
+        else me_verify_kernel<false, false><<<grid, 32 * VERIFY_ROWS, smem, st>>>(g, p, 0);
+    }
     XV_LAUNCH_CHECK();
     return 0;
 }
