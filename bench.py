@@ -599,7 +599,7 @@ def main():
                          "dependency order after the parallel passes; identical decisions"}
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and n_gpus == 1:        # reported at N = 1 only (the --impl reference arm covers every N)
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True)
         cores = os.cpu_count() or 1
         clips = host_clips(S, 96, args.clip_frames)
