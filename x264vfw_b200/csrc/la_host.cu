@@ -840,7 +840,9 @@ static int frame_cost(La *la, Frame **frames, int p0, int p1, int b, bool need_v
                 const int ni = l ? fenc->i_frame - 1 : fenc->i_frame + 1;      // display index of the neighbour
                 Frame *nf = (ni >= 0 && ni < (int)la->by_index.size()) ? la->by_index[ni] : nullptr;
                 const int nd_max = l ? la->p.bframes : la->p.bframes + 1;
-                if (nf && nf->ready && nf != (l ? fref1 : fref0) && nd <= nd_max && !nf->spec[l][nd - 1] && !nf->searched[l][nd - 1]) {
+                // ... unless the decision logic (almost) never asks for that (list, distance) on this content
+                const bool asked_sometimes = la->n_input < 24 || (double)la->n_logical[l][nd - 1 < BMAX ? nd - 1 : BMAX] >= 0.1 * (double)la->n_input;
+                if (nf && nf->ready && nf != (l ? fref1 : fref0) && nd <= nd_max && asked_sometimes && !nf->spec[l][nd - 1] && !nf->searched[l][nd - 1]) {
                     me_add_job(la, mp, 0, nf, l ? fref1 : fref0, l, nd, nullptr);
                     nf->spec[l][nd - 1] = true; nf->spec_eng[l][nd - 1] = 0;
                 }
