@@ -76,7 +76,7 @@ namespace xv {
 // on 72 registers without a spill -- 28 warps per SM all the same; asking for 28 (cap 72) spills the trip counter.
 // The byte-gather instantiation (unaligned planes) needs more registers and is bound by its loads anyway.
 template <bool ALIGNED>
-__global__ void __launch_bounds__(32, ALIGNED ? 32 : 20)
+__global__ void __launch_bounds__(32, ALIGNED ? 25 : 20)
 hpel_kernel(HpelJob job)
 {
     hpel_unit_any<ALIGNED>(job, blockIdx.x, blockIdx.y, threadIdx.x);
