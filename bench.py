@@ -435,12 +435,16 @@ def main():
     n_gpus = world
     S, F = args.streams, args.frames_per_step
 
-    # one caller thread + one session worker per stream; they spin while they wait (lowest latency).
-    # On a node with fewer cores than such threads (8 ranks x 16 threads on 32 cores) the pollers
-    # yield the core between polls instead.
+    # one caller thread + one session worker per stream; they spin while they wait (lowest latency).  On a node with fewer
+    # cores than such threads: first the CALLERS stop polling (they sleep on the interrupt while their copies run; with
+    # resident clips they sleep on a condition variable anyway), and when even the workers alone outnumber the cores the
+    # workers yield the core between polls.
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    if "X264VFW_CUDA_SYNC" not in os.environ and local_world * S * 2 > (os.cpu_count() or 1):
-        os.environ["X264VFW_CUDA_SYNC"] = "yield"
+    cores = os.cpu_count() or 1
+    if "X264VFW_CUDA_SYNC" not in os.environ and local_world * S * 2 > cores:
+        os.environ.setdefault("X264VFW_CUDA_CALLER_BLOCK", "1")
+        if local_world * (S + 2) > cores:
+            os.environ["X264VFW_CUDA_SYNC"] = "yield"
     from x264vfw_b200.sharding import streams_of_rank
     my_streams = streams_of_rank(S * world, rank, world)   # global stream ids of this rank (S per GPU)
     assert len(my_streams) == S
@@ -614,7 +618,7 @@ def main():
     line = {"metric": "1080p frames/sec through csp+lookahead", "value": value, "unit": "frames/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
-            "run": {"host_wait": os.environ.get("X264VFW_CUDA_SYNC", "spin"), "rank0_cpu_affinity": (f"{len(numa_cpus)} CPUs local to the GPU" if numa_cpus else "unrestricted"),
+            "run": {"host_wait": os.environ.get("X264VFW_CUDA_SYNC", "spin") + ("+callers block" if os.environ.get("X264VFW_CUDA_CALLER_BLOCK") == "1" else ""), "rank0_cpu_affinity": (f"{len(numa_cpus)} CPUs local to the GPU" if numa_cpus else "unrestricted"),
                     "l2_policy": f"inputs larger than L2: {S * F * SRC_BYTES / 1e6:.0f} MB of packed frames per step per GPU",
                     "timed_region_s": main_r["ms_per_step"] * args.steps * 1e-3,
                     "frames_fed": main_r["frames_fed"], "decisions_drained": main_r["decisions_drained"],

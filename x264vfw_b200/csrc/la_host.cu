@@ -205,7 +205,8 @@ struct La {
     // ahead of time by the worker (when it is done with frame n - io_depth) and handed over through ring_frame[];
     // ev_frame_ready orders the kernel after the slot's reset on the main stream.
     int fused = 1;
-    int caller_block = 1;    // yield mode: the caller sleeps on the interrupt while its copies run (X264VFW_CUDA_CALLER_BLOCK=0: polls)
+    int caller_block = -1;   // the caller sleeps on the interrupt while its copies run: -1 = in yield mode only, 0 never, 1 always
+                             // (X264VFW_CUDA_CALLER_BLOCK; for nodes where the workers fit the cores but workers + callers do not)
     Frame *ring_frame[4] = {nullptr};
     cudaEvent_t ev_frame_ready[4] = {nullptr};
     std::mutex prof_mu;
@@ -315,7 +316,7 @@ static int wait_event(La *la, cudaEvent_t ev)
 // polling -- the session worker, whose waits are short and latency-critical, keeps the core.
 static int wait_event_caller(La *la, cudaEvent_t ev)
 {
-    if (la->yielding && la->caller_block) { LA_CUDA(cudaEventSynchronize(ev)); return 0; }
+    if (la->caller_block > 0 || (la->caller_block < 0 && la->yielding)) { LA_CUDA(cudaEventSynchronize(ev)); return 0; }
     // notify mode: wait_event already sleeps
     return wait_event(la, ev);
 }
