@@ -411,3 +411,43 @@ class OracleLookahead:
         c = (C.c_uint64 * 4)()
         self.o.orc_la_counters(self.h, c)
         return dict(mb_cost=c[0], searches=c[1], sad=c[2], satd=c[3])
+
+
+# ---- f4: decoder-side output conversion (oracle/decode_oracle.c) ---------------------------------------------
+def decode_picture_size(out_csp, w, h):
+    o = oracle()
+    o.orc_decode_picture_size.restype = C.c_int64
+    o.orc_decode_picture_size.argtypes = [C.c_int, C.c_int, C.c_int]
+    return int(o.orc_decode_picture_size(out_csp, w, h))
+
+
+def oracle_decode_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0):
+    """y, u, v: 2-D uint8 planes of one decoded yuv420p picture (any row stride).  Returns the output DIB bytes, or
+    None where the checker refuses (-1)."""
+    o = oracle()
+    o.orc_decode_convert.restype = C.c_int
+    o.orc_decode_convert.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                     C.c_int, C.c_int]
+    h, w = y.shape
+    size = decode_picture_size(out_csp, w, h)
+    if size < 0:
+        return None
+    out = np.zeros(size, np.uint8)
+    src = (C.c_void_p * 3)(y.ctypes.data, u.ctypes.data, v.ctypes.data)
+    ss = (C.c_int * 3)(y.strides[0], u.strides[0], v.strides[0])
+    if o.orc_decode_convert(out_csp, out.ctypes.data, src, ss, w, h, avcol_spc, fullrange) != 0:
+        return None
+    return out
+
+
+def decode_source(w, h, seed=0, pad=0):
+    """Seeded yuv420p picture (SURVEY A.4 byte generator, seed folded into the generator's size arguments); rows
+    carry `pad` spare bytes so that strides differ from widths like a decoder's AVFrame linesize."""
+    cw, ch = w // 2, h // 2
+    raw = lcg_bytes((w + pad) * h + 2 * (cw + pad) * ch, w + 7 * seed, h + 13 * seed)
+    y = raw[:(w + pad) * h].reshape(h, w + pad)[:, :w]
+    o = (w + pad) * h
+    u = raw[o:o + (cw + pad) * ch].reshape(ch, cw + pad)[:, :cw]
+    o += (cw + pad) * ch
+    v = raw[o:o + (cw + pad) * ch].reshape(ch, cw + pad)[:, :cw]
+    return y, u, v
