@@ -283,6 +283,21 @@ def stage1_roofline(torch, args):
     rec = torch.randint(0, 256, (hn * W * 1088,), dtype=torch.uint8, device="cuda")
     hp = torch.empty(hn * 4 * hg.plane_bytes, dtype=torch.uint8, device="cuda")
     leg("hpel_filter", HPEL_ALGO_BYTES, hn, lambda: hpel.hpel_filter(ctx, hp.data_ptr(), rec.data_ptr(), W, W, 1088, W * 1088, 4 * hg.plane_bytes, hn))
+    # decoder-side output conversion: decoded yuv420p pictures -> bottom-up RGB32 DIBs, the default VfW
+    # decompress target; algorithmic bytes = 1.5 read + 4 written per pixel.  `dst` doubles as the yuv420p source.
+    try:
+        from x264vfw_b200 import decode
+        dn = max(1, nf // 2)
+        dd = decode.Decompressor(csp.X264VFW_CSP_BGRA | csp.X264VFW_CSP_VFLIP, W, H, decode.AVCOL_SPC_BT709, False, ctx=ctx)
+        dib = torch.empty(dn * W * H * 4, dtype=torch.uint8, device="cuda")
+        yuv = torch.randint(0, 256, (dn * dfb,), dtype=torch.uint8, device="cuda")
+        b0 = yuv.data_ptr()
+        leg("decode_yuv420p_to_bgra", W * H * 3 // 2 + W * H * 4, dn,
+            lambda: dd.decompress_batch(dib.data_ptr(), W * H * 4, (b0, b0 + W * H, b0 + W * H * 5 // 4), (W, W // 2, W // 2), dfb, dn))
+        ctx.sync()
+        dd.close()
+    except Exception as e:
+        out["decode_yuv420p_to_bgra"] = {"error": f"{type(e).__name__}: {e}"}
     try:
         ctx.close()
     except Exception:

@@ -6,4 +6,4 @@ the test / benchmark harness language.  There is no CPU fallback: importing work
 a GPU (symbols can be inspected) but every compute call fails without a CUDA device.
 """
 from ._lib import lib, LibraryMissing, last_error, version, launch_count  # noqa: F401
-from . import csp, lowres, hpel, lookahead  # noqa: F401
+from . import csp, lowres, hpel, lookahead, decode  # noqa: F401

@@ -1,0 +1,566 @@
+// the decoder-side output conversion of x264vfw_decompress (codec.c:2258-2292).
+//
+// The reference hands every decoded yuv420p picture to libswscale's sws_scale() with the context of
+// x264vfw_init_sws_context (codec.c:2075-2152).  What that context computes for a same-size picture
+// is (DESIGN.md 4.5 has the derivation and how it is pinned against libswscale 9.1.100):
+//   luma untouched; chroma kept at half horizontal resolution (SWS_FULL_CHR_H_INT never reaches the
+//   context, codec.c:2097 vs :2110) and interpolated vertically by a 4-tap bicubic with 12-bit
+//   coefficients; rows 0..h-3 go through libswscale's 16-bit "accurate rounding" SIMD writers,
+//   rows h-2 and h-1 (and every row of UYVY) through its table-driven C writers; I420 / YV12 / NV12
+//   are plane copies.
+//
+// Device formulation: one thread owns 8 pixels x DEC_RT rows.  The four chroma lines a row needs are
+// loaded as 32-bit words (4 chroma samples each), transposed with PRMT so that one register holds
+// the 4 vertical taps of one chroma column, and the filter is two DP2A (s16 coefficient pair x u8
+// sample pair) per sample; pixels are packed with saturating I2IP (cvt.pack.sat.u8.s32) and leave
+// as 128-bit stores.  HBM traffic per pixel is 1.5 bytes in + 2..4 bytes out; the kernel is bounded
+// by instruction issue, like the RGB->I420 direction.
+#include "common.cuh"
+#include "../../include/x264vfw_cuda.h"
+#include <vector>
+#include <string.h>
+#include <stdlib.h>
+
+namespace xv {
+
+enum { DEC_BGRA = 0, DEC_BGR = 1, DEC_YUYV = 2, DEC_UYVY = 3 };
+#define DEC_RT 4            // rows per thread; tiles start at row -1 so that rows (2k-1, 2k) share their chroma window
+
+struct DecRow {             // one output row of the vertical chroma filter
+    int pos;                // first of the 4 chroma lines
+    int c01, c23;           // coefficient pairs (s16 | s16 << 16) as the writer of this row sees them
+    int c_writer;           // 1: libswscale's C writer (last two rows, UYVY), 0: its SIMD writer
+};
+
+struct DecConst {
+    // SIMD writers: Yv = (y * yc + ykf) >> 13, chroma deltas = ((s >> 9) * coeff + coeff0) >> 16 with coeff0 = -1020 * coeff
+    int yc, ykf, vr, ub, vg, ug, vr0, ub0, vg0, ug0;
+    // C writers: component = clip8((idx * cy + bias) >> 16), idx = Y + ((C * cxx) >> 16) - (cxx >> 9) ...
+    int cy, bias, crv, cbu, cgu, cgv, crv9, cbu9, cgu9, cgv9;
+};
+
+struct DecJob {
+    const uint8_t *y, *u, *v;
+    int ys, us, vs;
+    uint8_t *dst;
+    long long dst_stride;   // negative for a bottom-up DIB (x264vfw_picture_vflip, codec.c:510-527)
+    int w, h;
+    size_t src_frame_bytes, dst_frame_bytes;
+    const DecRow *rows;
+    DecConst k;
+};
+
+__device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// (sat_u8(a) << 8 | sat_u8(b)) | c << 16
+__device__ __forceinline__ uint32_t pack_sat(int a, int b, uint32_t c)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
+
+// 4 bytes of a chroma line starting at column c0 (zeros past the line's end)
+template <bool VEC>
+__device__ __forceinline__ uint32_t load_c4(const uint8_t *line, int c0, int cw)
+{
+    if (VEC) return __ldg((const uint32_t *)(line + c0));
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (c0 + i < cw) r |= (uint32_t)__ldg(line + c0 + i) << (8 * i);
+    return r;
+}
+
+template <int FMT, bool VEC>
+__global__ void __launch_bounds__(256) dec_packed_kernel(const DecJob j)
+{
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+    if (x0 >= j.w) return;
+    const int cw = j.w >> 1, c0 = x0 >> 1;
+    const int npx = min(8, j.w - x0);
+    const size_t fo = (size_t)blockIdx.z * j.src_frame_bytes;
+    const uint8_t *Y = j.y + fo, *U = j.u + fo, *V = j.v + fo;
+    uint8_t *D = j.dst + (size_t)blockIdx.z * j.dst_frame_bytes;
+    const DecConst &K = j.k;
+
+    const int r0 = (blockIdx.y * 8 + threadIdx.y) * DEC_RT - 1;
+    int cur = -1;
+    uint32_t uc[4], vc[4];                      // per chroma column: its 4 vertical taps, one byte each
+#pragma unroll
+    for (int i = 0; i < DEC_RT; i++) {
+        const int r = r0 + i;
+        if (r < 0 || r >= j.h) continue;
+        const int4 t4 = __ldg((const int4 *)(j.rows + r));
+        const DecRow t = {t4.x, t4.y, t4.z, t4.w};
+        if (t.pos != cur) {
+            cur = t.pos;
+            uint32_t l[4], m[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                l[q] = load_c4<VEC>(U + (ptrdiff_t)(cur + q) * j.us, c0, cw);
+                m[q] = load_c4<VEC>(V + (ptrdiff_t)(cur + q) * j.vs, c0, cw);
+            }
+            uint32_t a0 = __byte_perm(l[0], l[1], 0x5140), a1 = __byte_perm(l[0], l[1], 0x7362);
+            uint32_t a2 = __byte_perm(l[2], l[3], 0x5140), a3 = __byte_perm(l[2], l[3], 0x7362);
+            uc[0] = __byte_perm(a0, a2, 0x5410); uc[1] = __byte_perm(a0, a2, 0x7632);
+            uc[2] = __byte_perm(a1, a3, 0x5410); uc[3] = __byte_perm(a1, a3, 0x7632);
+            a0 = __byte_perm(m[0], m[1], 0x5140); a1 = __byte_perm(m[0], m[1], 0x7362);
+            a2 = __byte_perm(m[2], m[3], 0x5140); a3 = __byte_perm(m[2], m[3], 0x7362);
+            vc[0] = __byte_perm(a0, a2, 0x5410); vc[1] = __byte_perm(a0, a2, 0x7632);
+            vc[2] = __byte_perm(a1, a3, 0x5410); vc[3] = __byte_perm(a1, a3, 0x7632);
+        }
+        // luma: 8 bytes
+        uint32_t yw[2];
+        const uint8_t *yrow = Y + (ptrdiff_t)r * j.ys + x0;
+        if (VEC) {
+            const uint2 t2 = ldg_stream64(yrow);
+            yw[0] = t2.x; yw[1] = t2.y;
+        } else {
+            yw[0] = yw[1] = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (q < npx) yw[q >> 2] |= (uint32_t)__ldg(yrow + q) << (8 * (q & 3));
+        }
+
+        uint32_t px[8];                         // BGRA/BGR: one word per pixel (B | G<<8 | R<<16 | 255<<24); 4:2:2: one per pixel pair
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            // vertical filter: sum of sample * coefficient (the reference's 15-bit intermediates are sample << 7)
+            const int su = dp2a_hi_su(t.c23, uc[c], dp2a_lo_su(t.c01, uc[c], 0));
+            const int sv = dp2a_hi_su(t.c23, vc[c], dp2a_lo_su(t.c01, vc[c], 0));
+            const uint32_t ywc = yw[c >> 1];
+            if (FMT == DEC_YUYV || FMT == DEC_UYVY) {
+                const int ya = (ywc >> (16 * (c & 1))) & 0xff, yb = (ywc >> (16 * (c & 1) + 8)) & 0xff;
+                int Uo, Vo;
+                if (t.c_writer) { Uo = (su + 2048) >> 12; Vo = (sv + 2048) >> 12; }       // (acc + (1 << 18)) >> 19
+                else            { Uo = ((su >> 9) + 4) >> 3; Vo = ((sv >> 9) + 4) >> 3; } // psrad 16, +rounder, psraw 3
+                px[c] = FMT == DEC_YUYV ? pack_sat(Uo, ya, pack_sat(Vo, yb, 0)) : pack_sat(ya, Uo, pack_sat(yb, Vo, 0));
+            } else if (t.c_writer) {
+                const int ya = (ywc >> (16 * (c & 1))) & 0xff, yb = (ywc >> (16 * (c & 1) + 8)) & 0xff;
+                const int Uc = clip8((su + 2048) >> 12), Vc = clip8((sv + 2048) >> 12);
+                const int dr = ((Vc * K.crv) >> 16) - K.crv9;
+                const int db = ((Uc * K.cbu) >> 16) - K.cbu9;
+                const int dg = ((Uc * K.cgu) >> 16) - K.cgu9 + ((Vc * K.cgv) >> 16) - K.cgv9;
+                px[2 * c]     = pack_sat(((ya + dg) * K.cy + K.bias) >> 16, ((ya + db) * K.cy + K.bias) >> 16,
+                                         pack_sat(255, ((ya + dr) * K.cy + K.bias) >> 16, 0));
+                px[2 * c + 1] = pack_sat(((yb + dg) * K.cy + K.bias) >> 16, ((yb + db) * K.cy + K.bias) >> 16,
+                                         pack_sat(255, ((yb + dr) * K.cy + K.bias) >> 16, 0));
+            } else {
+                // 16-bit SIMD writer: chroma = (s >> 9) + 4 - (128 << 3); delta = chroma * coeff >> 16 (constants folded);
+                // luma = ((y << 3) + 4 - y_offset) * y_coeff >> 16, as one DP2A on the packed bytes and one shift
+                const int uq = su >> 9, vq = sv >> 9;
+                const int ub = (uq * K.ub + K.ub0) >> 16, vr = (vq * K.vr + K.vr0) >> 16;
+                const int g = ((uq * K.ug + K.ug0) >> 16) + ((vq * K.vg + K.vg0) >> 16);
+                const int y0v = ((c & 1) ? dp2a_hi_su(K.yc, ywc, K.ykf) : dp2a_lo_su(K.yc, ywc, K.ykf)) >> 13;
+                const int y1v = ((c & 1) ? dp2a_hi_su(K.yc << 16, ywc, K.ykf) : dp2a_lo_su(K.yc << 16, ywc, K.ykf)) >> 13;
+                px[2 * c]     = pack_sat(y0v + g, y0v + ub, pack_sat(255, y0v + vr, 0));
+                px[2 * c + 1] = pack_sat(y1v + g, y1v + ub, pack_sat(255, y1v + vr, 0));
+            }
+        }
+
+        uint8_t *o = D + (ptrdiff_t)r * j.dst_stride;
+        if (FMT == DEC_BGRA) {
+            o += (size_t)x0 * 4;
+            if (VEC) {
+                ((uint4 *)o)[0] = make_uint4(px[0], px[1], px[2], px[3]);
+                ((uint4 *)o)[1] = make_uint4(px[4], px[5], px[6], px[7]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (q < npx) *(uint32_t *)(o + 4 * q) = px[q];      // DIB rows are 4-byte aligned by construction
+            }
+        } else if (FMT == DEC_BGR) {
+            o += (size_t)x0 * 3;
+            if (VEC) {
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const uint32_t p0 = px[4 * q], p1 = px[4 * q + 1], p2 = px[4 * q + 2], p3 = px[4 * q + 3];
+                    ((uint32_t *)o)[3 * q]     = __byte_perm(p0, p1, 0x4210);      // B0 G0 R0 B1
+                    ((uint32_t *)o)[3 * q + 1] = __byte_perm(p1, p2, 0x5421);      // G1 R1 B2 G2
+                    ((uint32_t *)o)[3 * q + 2] = __byte_perm(p2, p3, 0x6542);      // R2 B3 G3 R3
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (q < npx) { o[3 * q] = px[q]; o[3 * q + 1] = px[q] >> 8; o[3 * q + 2] = px[q] >> 16; }
+            }
+        } else {
+            o += (size_t)x0 * 2;
+            if (VEC)
+                *(uint4 *)o = make_uint4(px[0], px[1], px[2], px[3]);
+            else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (2 * q < npx) *(uint32_t *)(o + 4 * q) = px[q];
+            }
+        }
+    }
+}
+
+// I420 / YV12 / NV12 targets: plane copies (libswscale's planarCopyWrapper / planarToNv12Wrapper); YV12 arrives
+// here with the destination U/V pointers already swapped (codec.c:2263-2274).
+struct DecPlanarJob {
+    const uint8_t *y, *u, *v;
+    int ys, us, vs;
+    uint8_t *dy, *du, *dv;      // dv == nullptr: NV12 (du rows hold U,V interleaved)
+    int w, h;
+    size_t src_frame_bytes, dst_frame_bytes;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) dec_planar_kernel(const DecPlanarJob j)
+{
+    const int xb = (blockIdx.x * 256 + threadIdx.x) * 16;
+    const int row = blockIdx.y;
+    const size_t so = (size_t)blockIdx.z * j.src_frame_bytes, dof = (size_t)blockIdx.z * j.dst_frame_bytes;
+    const int cw = j.w >> 1;
+    if (row < j.h) {
+        if (xb >= j.w) return;
+        const uint8_t *s = j.y + so + (ptrdiff_t)row * j.ys + xb;
+        uint8_t *d = j.dy + dof + (size_t)row * j.w + xb;
+        if (VEC) *(uint4 *)d = ldg_stream128(s);
+        else for (int q = 0; q < 16 && xb + q < j.w; q++) d[q] = __ldg(s + q);
+        return;
+    }
+    const int r = row - j.h;
+    const uint8_t *su = j.u + so + (ptrdiff_t)r * j.us, *sv = j.v + so + (ptrdiff_t)r * j.vs;
+    if (!j.dv) {                                            // NV12: 16 output bytes = 8 U + 8 V
+        if (xb >= j.w) return;
+        uint8_t *d = j.du + dof + (size_t)r * j.w + xb;
+        if (VEC) {
+            const uint2 a = ldg_stream64(su + (xb >> 1)), b = ldg_stream64(sv + (xb >> 1));
+            *(uint4 *)d = make_uint4(__byte_perm(a.x, b.x, 0x5140), __byte_perm(a.x, b.x, 0x7362),
+                                     __byte_perm(a.y, b.y, 0x5140), __byte_perm(a.y, b.y, 0x7362));
+        } else
+            for (int q = 0; q < 8 && (xb >> 1) + q < cw; q++) { d[2 * q] = __ldg(su + (xb >> 1) + q); d[2 * q + 1] = __ldg(sv + (xb >> 1) + q); }
+        return;
+    }
+    if (xb >= cw) return;
+    uint8_t *du = j.du + dof + (size_t)r * cw + xb, *dv = j.dv + dof + (size_t)r * cw + xb;
+    if (VEC) { *(uint4 *)du = ldg_stream128(su + xb); *(uint4 *)dv = ldg_stream128(sv + xb); }
+    else for (int q = 0; q < 16 && xb + q < cw; q++) { du[q] = __ldg(su + xb + q); dv[q] = __ldg(sv + xb + q); }
+}
+
+// ---- host side: the context x264vfw_init_sws_context builds, as numbers --------------------------------------
+
+// The vertical chroma filter libswscale's initFilter() [libswscale/utils.c] yields for this context: bicubic
+// (B = 0, C = 0.6), src_n -> 2 * src_n, both chroma sitings 128, coefficients normalised to 1 << 12, at most 4 taps
+// after near-zero taps are dropped, out-of-picture taps folded onto the edge line.
+static bool vertical_chroma_filter(int src_n, std::vector<DecRow> &rows, bool c_writer_everywhere)
+{
+    const int dst_n = 2 * src_n, one = 1 << 12;
+    if (src_n < 5) return false;
+    const int taps = src_n - 2 < 5 ? src_n - 2 : 5;            // 1 + sizeFactor(bicubic), capped by the source height
+    const long long inc = (((long long)src_n << 16) + (dst_n >> 1)) / dst_n;        // 1 << 15
+    const long long Cq = (long long)(0.6 * (1 << 24));
+    std::vector<long long> f((size_t)dst_n * taps);
+    std::vector<int> pos(dst_n);
+    long long at = ((128 * inc) >> 7) - ((128 * 0x10000LL) >> 7);
+    for (int i = 0; i < dst_n; i++, at += 2 * inc) {
+        int xx = (int)((at - (long long)(taps - 2) * (1LL << 16)) / (1 << 17));
+        pos[i] = xx;
+        for (int t = 0; t < taps; t++, xx++) {
+            const long long d = llabs((long long)xx * (1 << 17) - at) << 13;
+            long long c = 0;
+            if (d < (1LL << 31)) {
+                const long long dd = (d * d) >> 30, ddd = (dd * d) >> 30;
+                c = d < (1LL << 30)
+                        ? (12 * (1 << 24) - 6 * Cq) * ddd + (-18 * (1 << 24) + 6 * Cq) * dd + 6LL * (1 << 24) * (1LL << 30)
+                        : -6 * Cq * ddd + 30 * Cq * dd - 48 * Cq * d + 24 * Cq * (1LL << 30);
+            }
+            f[(size_t)i * taps + t] = c;
+        }
+    }
+    // drop near-zero leading taps (keeping positions monotonic), measure the longest remaining support
+    const double cut = 0.002 * 18014398509481984.0;      // SWS_MAX_REDUCE_CUTOFF * 2^54
+    int support = 0;
+    for (int i = dst_n - 1; i >= 0; i--) {
+        long long *fi = &f[(size_t)i * taps];
+        long long acc = 0;
+        for (int t = 0; t < taps; t++) {
+            acc += llabs(fi[0]);
+            if ((double)acc > cut || (i < dst_n - 1 && pos[i] >= pos[i + 1])) break;
+            memmove(fi, fi + 1, (taps - 1) * sizeof(*fi));
+            fi[taps - 1] = 0;
+            pos[i]++;
+        }
+        int n = taps;
+        acc = 0;
+        for (int t = taps - 1; t > 0; t--) {
+            acc += llabs(fi[t]);
+            if ((double)acc > cut) break;
+            n--;
+        }
+        support = n > support ? n : support;
+    }
+    const int size = (support + 1) & ~1;                   // vertical filterAlign of the x86 build: 2
+    if (size != 4) return false;                          // the kernel reads 4 lines per row
+    rows.resize(dst_n);
+    for (int i = 0; i < dst_n; i++) {
+        long long t[4] = {0, 0, 0, 0};
+        for (int q = 0; q < size && q < taps; q++) t[q] = f[(size_t)i * taps + q];
+        if (pos[i] < 0) {
+            for (int q = 1; q < size; q++) { const int to = q + pos[i] > 0 ? q + pos[i] : 0; t[to] += t[q]; t[q] = 0; }
+            pos[i] = 0;
+        }
+        if (pos[i] + size > src_n) {
+            const int shift = pos[i] + size - src_n;       // src_n >= 5 > taps kept
+            long long acc = 0;
+            for (int q = size - 1; q >= 0; q--) if (pos[i] + q >= src_n) { acc += t[q]; t[q] = 0; }
+            for (int q = size - 1; q >= 0; q--) t[q] = q < shift ? 0 : t[q - shift];
+            pos[i] -= shift;
+            t[src_n - 1 - pos[i]] += acc;
+        }
+        long long sum = 0, err = 0;
+        for (int q = 0; q < 4; q++) sum += t[q];
+        sum = (sum + one / 2) / one;
+        if (!sum) sum = 1;
+        int c[4];
+        for (int q = 0; q < 4; q++) {
+            const long long v = t[q] + err;
+            const long long iv = v >= 0 ? (v + (sum >> 1)) / sum : (v - (sum >> 1)) / sum;
+            c[q] = (int)iv;
+            err = v - iv * sum;
+        }
+        const bool cwr = c_writer_everywhere || i >= dst_n - 2;    // libswscale leaves SIMD for the last two lines
+        if (!cwr)          // ff_updateMMXDitherTables packs f[q] + f[q+1] * 65536 into ONE int: a negative f[q] borrows
+            for (int q = 0; q < 4; q += 2) if (c[q] < 0) c[q + 1] = (int16_t)(c[q + 1] - 1);
+        rows[i].pos = pos[i];
+        rows[i].c01 = (c[0] & 0xffff) | (int)((uint32_t)c[1] << 16);
+        rows[i].c23 = (c[2] & 0xffff) | (int)((uint32_t)c[3] << 16);
+        rows[i].c_writer = cwr;
+    }
+    return true;
+}
+
+static int to_int16(long long f)
+{
+    long long r = (f + (1 << 15)) >> 16;
+    return (int)(r < -0x7FFF ? -0x7FFF : r > 0x7FFF ? 0x7FFF : r);
+}
+
+// ff_yuv2rgb_c_init_tables [libswscale/yuv2rgb.c] for brightness 0, contrast = saturation = 1.0 (codec.c:2141-2144)
+static void colour_constants(DecConst &k, int avcol_spc, int fullrange)
+{
+    // sws_getCoefficients(): {crv, cbu, cgu, cgv}; the switch of codec.c:2114-2140
+    static const int coeffs[5][4] = {
+        {104597, 132201, 25675, 53279},     // ITU601 / SMPTE170M / default
+        {117489, 138438, 13975, 34925},     // ITU709
+        {104448, 132798, 24759, 53109},     // FCC
+        {117579, 136230, 16907, 35559},     // SMPTE240M
+        {110013, 140363, 12277, 42626},     // BT2020
+    };
+    int row = 0;
+    switch (avcol_spc) {
+    case 1: row = 1; break;                 // AVCOL_SPC_BT709
+    case 4: row = 2; break;                 // AVCOL_SPC_FCC
+    case 7: row = 3; break;                 // AVCOL_SPC_SMPTE240M
+    case 9: case 10: row = 4; break;        // AVCOL_SPC_BT2020_NCL / _CL
+    default: row = 0;                       // BT470BG, SMPTE170M, anything else -> SWS_CS_DEFAULT
+    }
+    long long crv = coeffs[row][0], cbu = coeffs[row][1], cgu = -coeffs[row][2], cgv = -coeffs[row][3];
+    long long cy = 1 << 16, oy = 0;
+    if (!fullrange) { cy = (cy * 255) / 219; oy = 16 << 16; }
+    else { crv = crv * 224 / 255; cbu = cbu * 224 / 255; cgu = cgu * 224 / 255; cgv = cgv * 224 / 255; }
+    const int y_coeff = to_int16(cy << 13), y_off = to_int16(oy << 3);
+    // ((y << 3) + 4 - y_off) * y_coeff >> 16 == (y * y_coeff + floor((4 - y_off) * y_coeff / 8)) >> 13 for integer y
+    const int yk = (4 - y_off) * y_coeff;
+    k.yc = y_coeff; k.ykf = yk >= 0 ? yk / 8 : -((-yk + 7) / 8);
+    k.vr = to_int16(crv * 8192); k.ub = to_int16(cbu * 8192); k.vg = to_int16(cgv * 8192); k.ug = to_int16(cgu * 8192);
+    k.vr0 = -1020 * k.vr; k.ub0 = -1020 * k.ub; k.vg0 = -1020 * k.vg; k.ug0 = -1020 * k.ug;
+    crv = (crv * 65536 + 0x8000) / cy; cbu = (cbu * 65536 + 0x8000) / cy;
+    cgu = (cgu * 65536 + 0x8000) / cy; cgv = (cgv * 65536 + 0x8000) / cy;
+    k.cy = (int)cy;
+    k.bias = (int)((fullrange ? 384 : 326) * cy - (384LL << 16) - oy + 0x8000);
+    k.crv = (int)crv; k.cbu = (int)cbu; k.cgu = (int)cgu; k.cgv = (int)cgv;
+    k.crv9 = (int)(crv >> 9); k.cbu9 = (int)(cbu >> 9); k.cgu9 = (int)(cgu >> 9); k.cgv9 = (int)(cgv >> 9);
+}
+
+struct Dec {
+    Ctx *ctx;
+    int csp, flip, w, h;
+    DecConst k;
+    DecRow *d_rows = nullptr;
+    // staging of the host-buffer entry
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    size_t src_bytes = 0, dst_bytes = 0;
+};
+
+static inline bool al(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+static inline bool als(long long v, long long a) { return (v & (a - 1)) == 0; }
+
+static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src[3], const int ss[3], size_t sfb, int n)
+{
+    cudaStream_t st = d->ctx->stream;
+    const int w = d->w, h = d->h, cw = w / 2, ch = h / 2;
+    if (n <= 0) return 0;
+    if (n > 65535) { set_error("at most 65535 pictures per launch"); return -1; }
+    if (d->csp == X264VFW_CUDA_CSP_I420 || d->csp == X264VFW_CUDA_CSP_YV12 || d->csp == X264VFW_CUDA_CSP_NV12) {
+        DecPlanarJob j;
+        j.y = src[0]; j.u = src[1]; j.v = src[2]; j.ys = ss[0]; j.us = ss[1]; j.vs = ss[2];
+        j.w = w; j.h = h; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
+        j.dy = dst;
+        uint8_t *p1 = dst + (size_t)w * h, *p2 = p1 + (size_t)cw * ch;             // x264vfw_picture_fill, codec.c:425-439,469-480
+        if (d->csp == X264VFW_CUDA_CSP_NV12) { j.du = p1; j.dv = nullptr; }
+        else if (d->csp == X264VFW_CUDA_CSP_YV12) { j.du = p2; j.dv = p1; }          // codec.c:2263-2274
+        else { j.du = p1; j.dv = p2; }
+        const bool vec = als(w, 32) && al(dst, 16) && als((long long)dfb, 16) && als((long long)sfb, 16) &&
+                         al(src[0], 16) && al(src[1], 16) && al(src[2], 16) && als(ss[0], 16) && als(ss[1], 16) && als(ss[2], 16) &&
+                         als((long long)cw * ch, 16);
+        dim3 grid((w + 4095) / 4096, h + ch, n);
+        if (vec) dec_planar_kernel<true><<<grid, 256, 0, st>>>(j);
+        else     dec_planar_kernel<false><<<grid, 256, 0, st>>>(j);
+        XV_LAUNCH_CHECK();
+        return 0;
+    }
+    DecJob j;
+    j.y = src[0]; j.u = src[1]; j.v = src[2]; j.ys = ss[0]; j.us = ss[1]; j.vs = ss[2];
+    j.w = w; j.h = h; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
+    j.rows = d->d_rows; j.k = d->k;
+    long long stride = d->csp == X264VFW_CUDA_CSP_BGR ? ((w * 3 + 3) & ~3) : d->csp == X264VFW_CUDA_CSP_BGRA ? w * 4 : w * 2;
+    j.dst = dst; j.dst_stride = stride;
+    if (d->flip) { j.dst = dst + stride * (h - 1); j.dst_stride = -stride; }       // codec.c:515-518
+    const size_t da = d->csp == X264VFW_CUDA_CSP_BGR ? 4 : 16;
+    const bool vec = als(w, 8) && al(dst, da) && als(stride, da) && als((long long)dfb, da) && als((long long)sfb, 8) &&
+                     al(src[0], 8) && als(ss[0], 8) && al(src[1], 4) && al(src[2], 4) && als(ss[1], 4) && als(ss[2], 4);
+    if (!al(dst, 4) || !als((long long)dfb, 4)) { set_error("output picture must be 4-byte aligned"); return -1; }
+    dim3 block(32, 8), grid((w + 255) / 256, (h + 1 + 8 * DEC_RT - 1) / (8 * DEC_RT), n);
+#define DEC_GO(F) do { if (vec) dec_packed_kernel<F, true><<<grid, block, 0, st>>>(j); \
+                       else     dec_packed_kernel<F, false><<<grid, block, 0, st>>>(j); } while (0)
+    switch (d->csp) {
+    case X264VFW_CUDA_CSP_BGRA: DEC_GO(DEC_BGRA); break;
+    case X264VFW_CUDA_CSP_BGR:  DEC_GO(DEC_BGR); break;
+    case X264VFW_CUDA_CSP_YUYV: DEC_GO(DEC_YUYV); break;
+    default:                    DEC_GO(DEC_UYVY); break;
+    }
+#undef DEC_GO
+    XV_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace xv
+
+using namespace xv;
+
+extern "C" {
+
+int64_t x264vfw_cuda_dec_picture_size(int i_out_csp, int w, int h)
+{
+    // x264vfw_picture_get_size (codec.c:505-508) for the formats below
+    switch (i_out_csp & X264VFW_CUDA_CSP_MASK) {
+    case X264VFW_CUDA_CSP_I420: case X264VFW_CUDA_CSP_YV12: case X264VFW_CUDA_CSP_NV12:
+        return (int64_t)w * h + 2 * (int64_t)(w / 2) * (h / 2);
+    case X264VFW_CUDA_CSP_YUYV: case X264VFW_CUDA_CSP_UYVY: return (int64_t)w * 2 * h;
+    case X264VFW_CUDA_CSP_BGR:  return (int64_t)((w * 3 + 3) & ~3) * h;
+    case X264VFW_CUDA_CSP_BGRA: return (int64_t)w * 4 * h;
+    default: return -1;
+    }
+}
+
+int x264vfw_cuda_dec_open(x264vfw_cuda_dec **pdec, x264vfw_cuda_ctx *ctx, int i_out_csp, int w, int h,
+                          int i_avcol_spc, int b_fullrange)
+{
+    if (!pdec || !ctx) { set_error("null argument"); return -1; }
+    *pdec = nullptr;
+    const int csp = i_out_csp & X264VFW_CUDA_CSP_MASK, flip = (i_out_csp & X264VFW_CUDA_CSP_VFLIP) != 0;
+    if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) { set_error("width/height must be positive and even (codec.c:1950-1954)"); return -1; }
+    if (x264vfw_cuda_dec_picture_size(csp, w, h) < 0) { set_error("output csp %d is not covered (YV16/YV24 outputs are not)", csp); return -1; }
+    const bool rgb = csp == X264VFW_CUDA_CSP_BGR || csp == X264VFW_CUDA_CSP_BGRA;
+    if (flip && !rgb) { set_error("only RGB output can be bottom-up (codec.c:510-527)"); return -1; }
+    const bool planar = csp == X264VFW_CUDA_CSP_I420 || csp == X264VFW_CUDA_CSP_YV12 || csp == X264VFW_CUDA_CSP_NV12;
+    Ctx *c = (Ctx *)ctx;
+    XV_CUDA_OK(cudaSetDevice(c->device));
+    Dec *d = new Dec;
+    d->ctx = c; d->csp = csp; d->flip = flip; d->w = w; d->h = h;
+    colour_constants(d->k, i_avcol_spc, b_fullrange != 0);
+    if (!planar) {
+        std::vector<DecRow> rows;
+        if (!vertical_chroma_filter(h / 2, rows, csp == X264VFW_CUDA_CSP_UYVY)) {
+            set_error("pictures below 10 rows are not covered");
+            delete d;
+            return -1;
+        }
+        if (cudaMalloc((void **)&d->d_rows, rows.size() * sizeof(DecRow)) != cudaSuccess ||
+            cudaMemcpy(d->d_rows, rows.data(), rows.size() * sizeof(DecRow), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("row table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (d->d_rows) cudaFree(d->d_rows);
+            delete d;
+            return -1;
+        }
+    }
+    *pdec = (x264vfw_cuda_dec *)d;
+    return 0;
+}
+
+void x264vfw_cuda_dec_close(x264vfw_cuda_dec *dec)
+{
+    Dec *d = (Dec *)dec;
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    if (d->d_rows) cudaFree(d->d_rows);
+    if (d->d_src) cudaFree(d->d_src);
+    if (d->d_dst) cudaFree(d->d_dst);
+    delete d;
+}
+
+int x264vfw_cuda_dec_convert_batch(x264vfw_cuda_dec *dec, uint8_t *dst_dev, size_t dst_frame_bytes,
+                                   const uint8_t *const src_dev[3], const int src_stride[3], size_t src_frame_bytes,
+                                   int n_frames)
+{
+    Dec *d = (Dec *)dec;
+    if (!d || !dst_dev || !src_dev || !src_stride || !src_dev[0] || !src_dev[1] || !src_dev[2]) { set_error("null argument"); return -1; }
+    XV_CUDA_OK(cudaSetDevice(d->ctx->device));
+    return dec_launch(d, dst_dev, dst_frame_bytes, src_dev, src_stride, src_frame_bytes, n_frames);
+}
+
+int x264vfw_cuda_dec_convert(x264vfw_cuda_dec *dec, uint8_t *dst_host, const uint8_t *const src_host[3], const int src_stride[3])
+{
+    Dec *d = (Dec *)dec;
+    if (!d || !dst_host || !src_host || !src_stride || !src_host[0] || !src_host[1] || !src_host[2]) { set_error("null argument"); return -1; }
+    for (int i = 0; i < 3; i++) if (src_stride[i] < (i ? d->w / 2 : d->w)) { set_error("source stride below the row width"); return -1; }
+    XV_CUDA_OK(cudaSetDevice(d->ctx->device));
+    cudaStream_t st = d->ctx->stream;
+    const int w = d->w, h = d->h, cw = w / 2, ch = h / 2;
+    // device staging: tight planes with 16-byte aligned rows; the picture is gathered by 2-D copies so that the
+    // decoder's linesize padding never crosses the bus
+    const int ys = (w + 15) & ~15, cs = (cw + 15) & ~15;
+    const size_t sneed = (size_t)ys * h + 2 * (size_t)cs * ch, dneed = (size_t)x264vfw_cuda_dec_picture_size(d->csp, w, h);
+    if (d->src_bytes < sneed) {
+        if (d->d_src) cudaFree(d->d_src);
+        d->d_src = nullptr; d->src_bytes = 0;
+        XV_CUDA_OK(cudaMalloc((void **)&d->d_src, sneed));
+        d->src_bytes = sneed;
+    }
+    if (d->dst_bytes < dneed) {
+        if (d->d_dst) cudaFree(d->d_dst);
+        d->d_dst = nullptr; d->dst_bytes = 0;
+        XV_CUDA_OK(cudaMalloc((void **)&d->d_dst, dneed));
+        XV_CUDA_OK(cudaMemsetAsync(d->d_dst, 0, dneed, st));      // BGR24 row padding is never written: keep it defined
+        d->dst_bytes = dneed;
+    }
+    uint8_t *py = d->d_src, *pu = py + (size_t)ys * h, *pv = pu + (size_t)cs * ch;
+    XV_CUDA_OK(cudaMemcpy2DAsync(py, ys, src_host[0], src_stride[0], w, h, cudaMemcpyHostToDevice, st));
+    XV_CUDA_OK(cudaMemcpy2DAsync(pu, cs, src_host[1], src_stride[1], cw, ch, cudaMemcpyHostToDevice, st));
+    XV_CUDA_OK(cudaMemcpy2DAsync(pv, cs, src_host[2], src_stride[2], cw, ch, cudaMemcpyHostToDevice, st));
+    const uint8_t *sp[3] = {py, pu, pv};
+    const int ss[3] = {ys, cs, cs};
+    if (dec_launch(d, d->d_dst, 0, sp, ss, 0, 1) < 0) return -1;
+    XV_CUDA_OK(cudaMemcpyAsync(dst_host, d->d_dst, dneed, cudaMemcpyDeviceToHost, st));
+    XV_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+} // extern "C"
