@@ -424,7 +424,7 @@ int x264vfw_cuda_la_stats( x264vfw_cuda_la *la, uint64_t out[16] );
  * driven that way -- including that SWS_FULL_CHR_H_INT never reaches the context (codec.c:2097 vs :2110), so RGB output
  * shares one chroma sample per pixel pair -- except that exactly width pixels per row are written (libswscale's SIMD
  * writers store groups of 8).  Not covered (open returns -1): YV16/YV24 outputs, 4:2:2/4:4:4 decoder output, pictures
- * below 10 rows. */
+ * below 12 rows. */
 typedef struct x264vfw_cuda_dec x264vfw_cuda_dec;
 int  x264vfw_cuda_dec_open( x264vfw_cuda_dec **pdec, x264vfw_cuda_ctx *ctx, int i_out_csp, int i_width, int i_height,
                             int i_avcol_spc, int b_fullrange );

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libx264vfw_cuda.so")
+LIB_PATH = os.environ.get("X264VFW_CUDA_LIB") or os.path.join(_HERE, "libx264vfw_cuda.so")
 
 
 class LibraryMissing(RuntimeError):

@@ -9,7 +9,7 @@
 //   rows h-2 and h-1 (and every row of UYVY) through its table-driven C writers; I420 / YV12 / NV12
 //   are plane copies.
 //
-// Device formulation: one thread owns 8 pixels x DEC_RT rows.  The four chroma lines a row needs are
+// Device formulation: one thread owns 8 pixels x the row pair (2k-1, 2k), whose chroma windows coincide.  The four chroma lines a row needs are
 // loaded as 32-bit words (4 chroma samples each), transposed with PRMT so that one register holds
 // the 4 vertical taps of one chroma column, and the filter is two DP2A (s16 coefficient pair x u8
 // sample pair) per sample; pixels are packed with saturating I2IP (cvt.pack.sat.u8.s32) and leave
@@ -18,13 +18,15 @@
 #include "common.cuh"
 #include "../../include/x264vfw_cuda.h"
 #include <vector>
+#include <algorithm>
 #include <string.h>
 #include <stdlib.h>
 
 namespace xv {
 
 enum { DEC_BGRA = 0, DEC_BGR = 1, DEC_YUYV = 2, DEC_UYVY = 3 };
-#define DEC_RT 4            // rows per thread; tiles start at row -1 so that rows (2k-1, 2k) share their chroma window
+// resident blocks per SM the register allocation aims at: measured best per format on B200 (profiles/README.md R2.6)
+#define DEC_BLOCKS_PER_SM(FMT) ((FMT) == DEC_BGRA ? 6 : 8)
 
 struct DecRow {             // one output row of the vertical chroma filter
     int pos;                // first of the 4 chroma lines
@@ -83,130 +85,141 @@ __device__ __forceinline__ uint32_t load_c4(const uint8_t *line, int c0, int cw)
     return r;
 }
 
+// One output row of 8 pixels: filter the 4 chroma columns, convert, store.
+template <int FMT, bool VEC, bool CW>
+__device__ __forceinline__ void dec_row_impl(const DecJob &j, const DecRow t, const uint32_t (&uc)[4], const uint32_t (&vc)[4],
+                                             const uint8_t *yrow, uint8_t *o, int npx)
+{
+    const DecConst &K = j.k;
+    uint32_t yw[2];
+    if (VEC) {
+        const uint2 t2 = ldg_stream64(yrow);
+        yw[0] = t2.x; yw[1] = t2.y;
+    } else {
+        yw[0] = yw[1] = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (q < npx) yw[q >> 2] |= (uint32_t)__ldg(yrow + q) << (8 * (q & 3));
+    }
+    uint32_t px[8];                             // BGRA/BGR: one word per pixel (B | G<<8 | R<<16 | 255<<24); 4:2:2: one per pixel pair
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        // vertical filter: sum of sample * coefficient (the reference's 15-bit intermediates are sample << 7)
+        const int su = dp2a_hi_su(t.c23, uc[c], dp2a_lo_su(t.c01, uc[c], 0));
+        const int sv = dp2a_hi_su(t.c23, vc[c], dp2a_lo_su(t.c01, vc[c], 0));
+        const uint32_t ywc = yw[c >> 1];
+        if (FMT == DEC_YUYV || FMT == DEC_UYVY) {
+            const int ya = (ywc >> (16 * (c & 1))) & 0xff, yb = (ywc >> (16 * (c & 1) + 8)) & 0xff;
+            int Uo, Vo;
+            if (CW) { Uo = (su + 2048) >> 12; Vo = (sv + 2048) >> 12; }               // (acc + (1 << 18)) >> 19
+            else            { Uo = ((su >> 9) + 4) >> 3; Vo = ((sv >> 9) + 4) >> 3; } // psrad 16, +rounder, psraw 3
+            px[c] = FMT == DEC_YUYV ? pack_sat(Uo, ya, pack_sat(Vo, yb, 0)) : pack_sat(ya, Uo, pack_sat(yb, Vo, 0));
+        } else if (CW) {
+            const int ya = (ywc >> (16 * (c & 1))) & 0xff, yb = (ywc >> (16 * (c & 1) + 8)) & 0xff;
+            const int Uc = clip8((su + 2048) >> 12), Vc = clip8((sv + 2048) >> 12);
+            const int dr = ((Vc * K.crv) >> 16) - K.crv9;
+            const int db = ((Uc * K.cbu) >> 16) - K.cbu9;
+            const int dg = ((Uc * K.cgu) >> 16) - K.cgu9 + ((Vc * K.cgv) >> 16) - K.cgv9;
+            px[2 * c]     = pack_sat(((ya + dg) * K.cy + K.bias) >> 16, ((ya + db) * K.cy + K.bias) >> 16,
+                                     pack_sat(255, ((ya + dr) * K.cy + K.bias) >> 16, 0));
+            px[2 * c + 1] = pack_sat(((yb + dg) * K.cy + K.bias) >> 16, ((yb + db) * K.cy + K.bias) >> 16,
+                                     pack_sat(255, ((yb + dr) * K.cy + K.bias) >> 16, 0));
+        } else {
+            // 16-bit SIMD writer: chroma = (s >> 9) + 4 - (128 << 3); delta = chroma * coeff >> 16 (constants folded);
+            // luma = ((y << 3) + 4 - y_offset) * y_coeff >> 16, as one DP2A on the packed bytes and one shift
+            const int uq = su >> 9, vq = sv >> 9;
+            const int ub = (uq * K.ub + K.ub0) >> 16, vr = (vq * K.vr + K.vr0) >> 16;
+            const int g = ((uq * K.ug + K.ug0) >> 16) + ((vq * K.vg + K.vg0) >> 16);
+            const int y0v = ((c & 1) ? dp2a_hi_su(K.yc, ywc, K.ykf) : dp2a_lo_su(K.yc, ywc, K.ykf)) >> 13;
+            const int y1v = ((c & 1) ? dp2a_hi_su(K.yc << 16, ywc, K.ykf) : dp2a_lo_su(K.yc << 16, ywc, K.ykf)) >> 13;
+            px[2 * c]     = pack_sat(y0v + g, y0v + ub, pack_sat(255, y0v + vr, 0));
+            px[2 * c + 1] = pack_sat(y1v + g, y1v + ub, pack_sat(255, y1v + vr, 0));
+        }
+    }
+    if (FMT == DEC_BGRA) {
+        if (VEC) {
+            ((uint4 *)o)[0] = make_uint4(px[0], px[1], px[2], px[3]);
+            ((uint4 *)o)[1] = make_uint4(px[4], px[5], px[6], px[7]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (q < npx) *(uint32_t *)(o + 4 * q) = px[q];          // DIB rows are 4-byte aligned by construction
+        }
+    } else if (FMT == DEC_BGR) {
+        if (VEC) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const uint32_t p0 = px[4 * q], p1 = px[4 * q + 1], p2 = px[4 * q + 2], p3 = px[4 * q + 3];
+                ((uint32_t *)o)[3 * q]     = __byte_perm(p0, p1, 0x4210);          // B0 G0 R0 B1
+                ((uint32_t *)o)[3 * q + 1] = __byte_perm(p1, p2, 0x5421);          // G1 R1 B2 G2
+                ((uint32_t *)o)[3 * q + 2] = __byte_perm(p2, p3, 0x6542);          // R2 B3 G3 R3
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (q < npx) { o[3 * q] = px[q]; o[3 * q + 1] = px[q] >> 8; o[3 * q + 2] = px[q] >> 16; }
+        }
+    } else {
+        if (VEC)
+            *(uint4 *)o = make_uint4(px[0], px[1], px[2], px[3]);
+        else {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (2 * q < npx) *(uint32_t *)(o + 4 * q) = px[q];
+        }
+    }
+}
+
 template <int FMT, bool VEC>
-__global__ void __launch_bounds__(256) dec_packed_kernel(const DecJob j)
+__device__ __forceinline__ void dec_row(const DecJob &j, const DecRow t, const uint32_t (&uc)[4], const uint32_t (&vc)[4],
+                                        const uint8_t *yrow, uint8_t *o, int npx)
+{
+    if (FMT == DEC_UYVY || t.c_writer) dec_row_impl<FMT, VEC, true>(j, t, uc, vc, yrow, o, npx);
+    else                               dec_row_impl<FMT, VEC, false>(j, t, uc, vc, yrow, o, npx);
+}
+
+// The 4 chroma lines starting at `pos`, 4 columns from c0, transposed: word c = the 4 vertical taps of column c0 + c.
+template <bool VEC>
+__device__ __forceinline__ void dec_window(const uint8_t *plane, int stride, int pos, int c0, int cw, uint32_t (&col)[4])
+{
+    uint32_t l[4];
+    const uint8_t *p = plane + (ptrdiff_t)pos * stride;
+#pragma unroll
+    for (int q = 0; q < 4; q++, p += stride) l[q] = load_c4<VEC>(p, c0, cw);
+    const uint32_t a0 = __byte_perm(l[0], l[1], 0x5140), a1 = __byte_perm(l[0], l[1], 0x7362);
+    const uint32_t a2 = __byte_perm(l[2], l[3], 0x5140), a3 = __byte_perm(l[2], l[3], 0x7362);
+    col[0] = __byte_perm(a0, a2, 0x5410); col[1] = __byte_perm(a0, a2, 0x7632);
+    col[2] = __byte_perm(a1, a3, 0x5410); col[3] = __byte_perm(a1, a3, 0x7632);
+}
+
+// Thread = 8 pixels x the row pair (2k-1, 2k): in libswscale's filter those two rows read the same 4 chroma lines
+// (rows -1 and h do not exist).
+template <int FMT, bool VEC>
+__global__ void __launch_bounds__(256, DEC_BLOCKS_PER_SM(FMT)) dec_packed_kernel(const __grid_constant__ DecJob j)
 {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
-    if (x0 >= j.w) return;
+    const int k = blockIdx.y * 8 + threadIdx.y;
+    const int ra = 2 * k - 1, rb = 2 * k;
+    if (x0 >= j.w || ra >= j.h) return;
     const int cw = j.w >> 1, c0 = x0 >> 1;
     const int npx = min(8, j.w - x0);
     const size_t fo = (size_t)blockIdx.z * j.src_frame_bytes;
-    const uint8_t *Y = j.y + fo, *U = j.u + fo, *V = j.v + fo;
-    uint8_t *D = j.dst + (size_t)blockIdx.z * j.dst_frame_bytes;
-    const DecConst &K = j.k;
+    const uint8_t *Y = j.y + fo + x0, *U = j.u + fo, *V = j.v + fo;
+    constexpr int BPP2 = FMT == DEC_BGRA ? 8 : FMT == DEC_BGR ? 6 : 4;       // bytes per pixel pair
+    uint8_t *D = j.dst + (size_t)blockIdx.z * j.dst_frame_bytes + (size_t)c0 * BPP2;
 
-    const int r0 = (blockIdx.y * 8 + threadIdx.y) * DEC_RT - 1;
-    int cur = -1;
-    uint32_t uc[4], vc[4];                      // per chroma column: its 4 vertical taps, one byte each
-#pragma unroll
-    for (int i = 0; i < DEC_RT; i++) {
-        const int r = r0 + i;
-        if (r < 0 || r >= j.h) continue;
-        const int4 t4 = __ldg((const int4 *)(j.rows + r));
-        const DecRow t = {t4.x, t4.y, t4.z, t4.w};
-        if (t.pos != cur) {
-            cur = t.pos;
-            uint32_t l[4], m[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                l[q] = load_c4<VEC>(U + (ptrdiff_t)(cur + q) * j.us, c0, cw);
-                m[q] = load_c4<VEC>(V + (ptrdiff_t)(cur + q) * j.vs, c0, cw);
-            }
-            uint32_t a0 = __byte_perm(l[0], l[1], 0x5140), a1 = __byte_perm(l[0], l[1], 0x7362);
-            uint32_t a2 = __byte_perm(l[2], l[3], 0x5140), a3 = __byte_perm(l[2], l[3], 0x7362);
-            uc[0] = __byte_perm(a0, a2, 0x5410); uc[1] = __byte_perm(a0, a2, 0x7632);
-            uc[2] = __byte_perm(a1, a3, 0x5410); uc[3] = __byte_perm(a1, a3, 0x7632);
-            a0 = __byte_perm(m[0], m[1], 0x5140); a1 = __byte_perm(m[0], m[1], 0x7362);
-            a2 = __byte_perm(m[2], m[3], 0x5140); a3 = __byte_perm(m[2], m[3], 0x7362);
-            vc[0] = __byte_perm(a0, a2, 0x5410); vc[1] = __byte_perm(a0, a2, 0x7632);
-            vc[2] = __byte_perm(a1, a3, 0x5410); vc[3] = __byte_perm(a1, a3, 0x7632);
-        }
-        // luma: 8 bytes
-        uint32_t yw[2];
-        const uint8_t *yrow = Y + (ptrdiff_t)r * j.ys + x0;
-        if (VEC) {
-            const uint2 t2 = ldg_stream64(yrow);
-            yw[0] = t2.x; yw[1] = t2.y;
-        } else {
-            yw[0] = yw[1] = 0;
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-                if (q < npx) yw[q >> 2] |= (uint32_t)__ldg(yrow + q) << (8 * (q & 3));
-        }
-
-        uint32_t px[8];                         // BGRA/BGR: one word per pixel (B | G<<8 | R<<16 | 255<<24); 4:2:2: one per pixel pair
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            // vertical filter: sum of sample * coefficient (the reference's 15-bit intermediates are sample << 7)
-            const int su = dp2a_hi_su(t.c23, uc[c], dp2a_lo_su(t.c01, uc[c], 0));
-            const int sv = dp2a_hi_su(t.c23, vc[c], dp2a_lo_su(t.c01, vc[c], 0));
-            const uint32_t ywc = yw[c >> 1];
-            if (FMT == DEC_YUYV || FMT == DEC_UYVY) {
-                const int ya = (ywc >> (16 * (c & 1))) & 0xff, yb = (ywc >> (16 * (c & 1) + 8)) & 0xff;
-                int Uo, Vo;
-                if (t.c_writer) { Uo = (su + 2048) >> 12; Vo = (sv + 2048) >> 12; }       // (acc + (1 << 18)) >> 19
-                else            { Uo = ((su >> 9) + 4) >> 3; Vo = ((sv >> 9) + 4) >> 3; } // psrad 16, +rounder, psraw 3
-                px[c] = FMT == DEC_YUYV ? pack_sat(Uo, ya, pack_sat(Vo, yb, 0)) : pack_sat(ya, Uo, pack_sat(yb, Vo, 0));
-            } else if (t.c_writer) {
-                const int ya = (ywc >> (16 * (c & 1))) & 0xff, yb = (ywc >> (16 * (c & 1) + 8)) & 0xff;
-                const int Uc = clip8((su + 2048) >> 12), Vc = clip8((sv + 2048) >> 12);
-                const int dr = ((Vc * K.crv) >> 16) - K.crv9;
-                const int db = ((Uc * K.cbu) >> 16) - K.cbu9;
-                const int dg = ((Uc * K.cgu) >> 16) - K.cgu9 + ((Vc * K.cgv) >> 16) - K.cgv9;
-                px[2 * c]     = pack_sat(((ya + dg) * K.cy + K.bias) >> 16, ((ya + db) * K.cy + K.bias) >> 16,
-                                         pack_sat(255, ((ya + dr) * K.cy + K.bias) >> 16, 0));
-                px[2 * c + 1] = pack_sat(((yb + dg) * K.cy + K.bias) >> 16, ((yb + db) * K.cy + K.bias) >> 16,
-                                         pack_sat(255, ((yb + dr) * K.cy + K.bias) >> 16, 0));
-            } else {
-                // 16-bit SIMD writer: chroma = (s >> 9) + 4 - (128 << 3); delta = chroma * coeff >> 16 (constants folded);
-                // luma = ((y << 3) + 4 - y_offset) * y_coeff >> 16, as one DP2A on the packed bytes and one shift
-                const int uq = su >> 9, vq = sv >> 9;
-                const int ub = (uq * K.ub + K.ub0) >> 16, vr = (vq * K.vr + K.vr0) >> 16;
-                const int g = ((uq * K.ug + K.ug0) >> 16) + ((vq * K.vg + K.vg0) >> 16);
-                const int y0v = ((c & 1) ? dp2a_hi_su(K.yc, ywc, K.ykf) : dp2a_lo_su(K.yc, ywc, K.ykf)) >> 13;
-                const int y1v = ((c & 1) ? dp2a_hi_su(K.yc << 16, ywc, K.ykf) : dp2a_lo_su(K.yc << 16, ywc, K.ykf)) >> 13;
-                px[2 * c]     = pack_sat(y0v + g, y0v + ub, pack_sat(255, y0v + vr, 0));
-                px[2 * c + 1] = pack_sat(y1v + g, y1v + ub, pack_sat(255, y1v + vr, 0));
-            }
-        }
-
-        uint8_t *o = D + (ptrdiff_t)r * j.dst_stride;
-        if (FMT == DEC_BGRA) {
-            o += (size_t)x0 * 4;
-            if (VEC) {
-                ((uint4 *)o)[0] = make_uint4(px[0], px[1], px[2], px[3]);
-                ((uint4 *)o)[1] = make_uint4(px[4], px[5], px[6], px[7]);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    if (q < npx) *(uint32_t *)(o + 4 * q) = px[q];      // DIB rows are 4-byte aligned by construction
-            }
-        } else if (FMT == DEC_BGR) {
-            o += (size_t)x0 * 3;
-            if (VEC) {
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const uint32_t p0 = px[4 * q], p1 = px[4 * q + 1], p2 = px[4 * q + 2], p3 = px[4 * q + 3];
-                    ((uint32_t *)o)[3 * q]     = __byte_perm(p0, p1, 0x4210);      // B0 G0 R0 B1
-                    ((uint32_t *)o)[3 * q + 1] = __byte_perm(p1, p2, 0x5421);      // G1 R1 B2 G2
-                    ((uint32_t *)o)[3 * q + 2] = __byte_perm(p2, p3, 0x6542);      // R2 B3 G3 R3
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    if (q < npx) { o[3 * q] = px[q]; o[3 * q + 1] = px[q] >> 8; o[3 * q + 2] = px[q] >> 16; }
-            }
-        } else {
-            o += (size_t)x0 * 2;
-            if (VEC)
-                *(uint4 *)o = make_uint4(px[0], px[1], px[2], px[3]);
-            else {
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (2 * q < npx) *(uint32_t *)(o + 4 * q) = px[q];
-            }
-        }
-    }
+    // both rows of the pair read chroma lines pos..pos+3, pos = clamp(k - 2, 0, h/2 - 4) (checked against the filter
+    // table when the context is opened), so every load of this thread can be issued before anything is computed
+    const int pos = min(max(k - 2, 0), (j.h >> 1) - 4);
+    const int4 a4 = __ldg((const int4 *)(j.rows + max(ra, 0))), b4 = __ldg((const int4 *)(j.rows + min(rb, j.h - 1)));
+    const DecRow ta = {a4.x, a4.y, a4.z, a4.w}, tb = {b4.x, b4.y, b4.z, b4.w};
+    uint32_t uc[4], vc[4];
+    dec_window<VEC>(U, j.us, pos, c0, cw, uc);
+    dec_window<VEC>(V, j.vs, pos, c0, cw, vc);
+    if (ra >= 0)
+        dec_row<FMT, VEC>(j, ta, uc, vc, Y + (ptrdiff_t)ra * j.ys, D + (ptrdiff_t)ra * j.dst_stride, npx);
+    if (rb < j.h)
+        dec_row<FMT, VEC>(j, tb, uc, vc, Y + (ptrdiff_t)rb * j.ys, D + (ptrdiff_t)rb * j.dst_stride, npx);
 }
 
 // I420 / YV12 / NV12 targets: plane copies (libswscale's planarCopyWrapper / planarToNv12Wrapper); YV12 arrives
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(256) dec_planar_kernel(const DecPlanarJob j)
 static bool vertical_chroma_filter(int src_n, std::vector<DecRow> &rows, bool c_writer_everywhere)
 {
     const int dst_n = 2 * src_n, one = 1 << 12;
-    if (src_n < 5) return false;
+    if (src_n < 6) return false;                               // below that the tap positions stop following the kernel's rule
     const int taps = src_n - 2 < 5 ? src_n - 2 : 5;            // 1 + sizeFactor(bicubic), capped by the source height
     const long long inc = (((long long)src_n << 16) + (dst_n >> 1)) / dst_n;        // 1 << 15
     const long long Cq = (long long)(0.6 * (1 << 24));
@@ -337,6 +350,7 @@ static bool vertical_chroma_filter(int src_n, std::vector<DecRow> &rows, bool c_
         const bool cwr = c_writer_everywhere || i >= dst_n - 2;    // libswscale leaves SIMD for the last two lines
         if (!cwr)          // ff_updateMMXDitherTables packs f[q] + f[q+1] * 65536 into ONE int: a negative f[q] borrows
             for (int q = 0; q < 4; q += 2) if (c[q] < 0) c[q + 1] = (int16_t)(c[q + 1] - 1);
+        if (pos[i] != std::min(std::max(((i + 1) >> 1) - 2, 0), src_n - 4)) return false;   // the kernel derives it
         rows[i].pos = pos[i];
         rows[i].c01 = (c[0] & 0xffff) | (int)((uint32_t)c[1] << 16);
         rows[i].c23 = (c[2] & 0xffff) | (int)((uint32_t)c[3] << 16);
@@ -436,7 +450,7 @@ static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src
     const bool vec = als(w, 8) && al(dst, da) && als(stride, da) && als((long long)dfb, da) && als((long long)sfb, 8) &&
                      al(src[0], 8) && als(ss[0], 8) && al(src[1], 4) && al(src[2], 4) && als(ss[1], 4) && als(ss[2], 4);
     if (!al(dst, 4) || !als((long long)dfb, 4)) { set_error("output picture must be 4-byte aligned"); return -1; }
-    dim3 block(32, 8), grid((w + 255) / 256, (h + 1 + 8 * DEC_RT - 1) / (8 * DEC_RT), n);
+    dim3 block(32, 8), grid((w + 255) / 256, (h / 2 + 1 + 7) / 8, n);
 #define DEC_GO(F) do { if (vec) dec_packed_kernel<F, true><<<grid, block, 0, st>>>(j); \
                        else     dec_packed_kernel<F, false><<<grid, block, 0, st>>>(j); } while (0)
     switch (d->csp) {
@@ -488,7 +502,7 @@ int x264vfw_cuda_dec_open(x264vfw_cuda_dec **pdec, x264vfw_cuda_ctx *ctx, int i_
     if (!planar) {
         std::vector<DecRow> rows;
         if (!vertical_chroma_filter(h / 2, rows, csp == X264VFW_CUDA_CSP_UYVY)) {
-            set_error("pictures below 10 rows are not covered");
+            set_error("pictures below 12 rows are not covered");
             delete d;
             return -1;
         }
