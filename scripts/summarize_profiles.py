@@ -133,6 +133,8 @@ if __name__ == "__main__":
                 launch_list(os.path.join(GP, src), os.path.join(OUT, dst), title)
         reps = [(f"{k}_{tag}.ncu-rep", f"ncu_{k.replace('_kernel', '')}_{tag}.txt", f"{k}, scripts/profile_la.py 60 (one 1080p stream, preset medium), kernel alone on the GPU")
                 for k in ("me_pass_kernel", "me_verify_kernel", "tree_chain_kernel", "frontend_kernel", "intra_kernel", "finalize_kernel")]
+        reps.append((f"dec_packed_kernel_{tag}.ncu-rep", f"ncu_dec_packed_{tag}.txt",
+                     "dec_packed_kernel<BGRA,vec>, yuv420p -> bottom-up RGB32, 48 pictures of 1080p per launch (scripts/probe_decode.py 48 2 bgra_bottom_up), kernel alone on the GPU"))
         print(metrics_json(tag))
     for src, dst, title in reps:
         if os.path.exists(os.path.join(GP, src)):

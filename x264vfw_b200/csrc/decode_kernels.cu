@@ -71,6 +71,7 @@ __device__ __forceinline__ uint32_t pack_sat(int a, int b, uint32_t c)
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+#define DEC_ST128(p, v) (*(p) = (v))      // __stcs measured the same (profiles/README.md R2.6)
 __device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
 
 // 4 bytes of a chroma line starting at column c0 (zeros past the line's end)
@@ -88,19 +89,9 @@ __device__ __forceinline__ uint32_t load_c4(const uint8_t *line, int c0, int cw)
 // One output row of 8 pixels: filter the 4 chroma columns, convert, store.
 template <int FMT, bool VEC, bool CW>
 __device__ __forceinline__ void dec_row_impl(const DecJob &j, const DecRow t, const uint32_t (&uc)[4], const uint32_t (&vc)[4],
-                                             const uint8_t *yrow, uint8_t *o, int npx)
+                                             const uint32_t (&yw)[2], uint8_t *o, int npx)
 {
     const DecConst &K = j.k;
-    uint32_t yw[2];
-    if (VEC) {
-        const uint2 t2 = ldg_stream64(yrow);
-        yw[0] = t2.x; yw[1] = t2.y;
-    } else {
-        yw[0] = yw[1] = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            if (q < npx) yw[q >> 2] |= (uint32_t)__ldg(yrow + q) << (8 * (q & 3));
-    }
     uint32_t px[8];                             // BGRA/BGR: one word per pixel (B | G<<8 | R<<16 | 255<<24); 4:2:2: one per pixel pair
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -138,8 +129,8 @@ __device__ __forceinline__ void dec_row_impl(const DecJob &j, const DecRow t, co
     }
     if (FMT == DEC_BGRA) {
         if (VEC) {
-            ((uint4 *)o)[0] = make_uint4(px[0], px[1], px[2], px[3]);
-            ((uint4 *)o)[1] = make_uint4(px[4], px[5], px[6], px[7]);
+            DEC_ST128((uint4 *)o, make_uint4(px[0], px[1], px[2], px[3]));
+            DEC_ST128((uint4 *)o + 1, make_uint4(px[4], px[5], px[6], px[7]));
         } else {
 #pragma unroll
             for (int q = 0; q < 8; q++)
@@ -147,13 +138,16 @@ __device__ __forceinline__ void dec_row_impl(const DecJob &j, const DecRow t, co
         }
     } else if (FMT == DEC_BGR) {
         if (VEC) {
+            uint32_t wd[6];
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const uint32_t p0 = px[4 * q], p1 = px[4 * q + 1], p2 = px[4 * q + 2], p3 = px[4 * q + 3];
-                ((uint32_t *)o)[3 * q]     = __byte_perm(p0, p1, 0x4210);          // B0 G0 R0 B1
-                ((uint32_t *)o)[3 * q + 1] = __byte_perm(p1, p2, 0x5421);          // G1 R1 B2 G2
-                ((uint32_t *)o)[3 * q + 2] = __byte_perm(p2, p3, 0x6542);          // R2 B3 G3 R3
+                wd[3 * q]     = __byte_perm(p0, p1, 0x4210);          // B0 G0 R0 B1
+                wd[3 * q + 1] = __byte_perm(p1, p2, 0x5421);          // G1 R1 B2 G2
+                wd[3 * q + 2] = __byte_perm(p2, p3, 0x6542);          // R2 B3 G3 R3
             }
+#pragma unroll
+            for (int q = 0; q < 6; q++) ((uint32_t *)o)[q] = wd[q];
         } else {
 #pragma unroll
             for (int q = 0; q < 8; q++)
@@ -161,7 +155,7 @@ __device__ __forceinline__ void dec_row_impl(const DecJob &j, const DecRow t, co
         }
     } else {
         if (VEC)
-            *(uint4 *)o = make_uint4(px[0], px[1], px[2], px[3]);
+            DEC_ST128((uint4 *)o, make_uint4(px[0], px[1], px[2], px[3]));
         else {
 #pragma unroll
             for (int q = 0; q < 4; q++)
@@ -172,10 +166,25 @@ __device__ __forceinline__ void dec_row_impl(const DecJob &j, const DecRow t, co
 
 template <int FMT, bool VEC>
 __device__ __forceinline__ void dec_row(const DecJob &j, const DecRow t, const uint32_t (&uc)[4], const uint32_t (&vc)[4],
-                                        const uint8_t *yrow, uint8_t *o, int npx)
+                                        const uint32_t (&yw)[2], uint8_t *o, int npx)
 {
-    if (FMT == DEC_UYVY || t.c_writer) dec_row_impl<FMT, VEC, true>(j, t, uc, vc, yrow, o, npx);
-    else                               dec_row_impl<FMT, VEC, false>(j, t, uc, vc, yrow, o, npx);
+    if (FMT == DEC_UYVY || t.c_writer) dec_row_impl<FMT, VEC, true>(j, t, uc, vc, yw, o, npx);
+    else                               dec_row_impl<FMT, VEC, false>(j, t, uc, vc, yw, o, npx);
+}
+
+// 8 luma bytes of a row (zeros past the picture's right edge)
+template <bool VEC>
+__device__ __forceinline__ void dec_luma8(const uint8_t *yrow, int npx, uint32_t (&yw)[2])
+{
+    if (VEC) {
+        const uint2 t2 = ldg_stream64(yrow);
+        yw[0] = t2.x; yw[1] = t2.y;
+    } else {
+        yw[0] = yw[1] = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (q < npx) yw[q >> 2] |= (uint32_t)__ldg(yrow + q) << (8 * (q & 3));
+    }
 }
 
 // The 4 chroma lines starting at `pos`, 4 columns from c0, transposed: word c = the 4 vertical taps of column c0 + c.
@@ -213,13 +222,15 @@ __global__ void __launch_bounds__(256, DEC_BLOCKS_PER_SM(FMT)) dec_packed_kernel
     const int pos = min(max(k - 2, 0), (j.h >> 1) - 4);
     const int4 a4 = __ldg((const int4 *)(j.rows + max(ra, 0))), b4 = __ldg((const int4 *)(j.rows + min(rb, j.h - 1)));
     const DecRow ta = {a4.x, a4.y, a4.z, a4.w}, tb = {b4.x, b4.y, b4.z, b4.w};
-    uint32_t uc[4], vc[4];
+    uint32_t uc[4], vc[4], ya[2], yb[2];
+    dec_luma8<VEC>(Y + (ptrdiff_t)max(ra, 0) * j.ys, npx, ya);             // before any store: a load after a store waits for it
+    dec_luma8<VEC>(Y + (ptrdiff_t)min(rb, j.h - 1) * j.ys, npx, yb);
     dec_window<VEC>(U, j.us, pos, c0, cw, uc);
     dec_window<VEC>(V, j.vs, pos, c0, cw, vc);
     if (ra >= 0)
-        dec_row<FMT, VEC>(j, ta, uc, vc, Y + (ptrdiff_t)ra * j.ys, D + (ptrdiff_t)ra * j.dst_stride, npx);
+        dec_row<FMT, VEC>(j, ta, uc, vc, ya, D + (ptrdiff_t)ra * j.dst_stride, npx);
     if (rb < j.h)
-        dec_row<FMT, VEC>(j, tb, uc, vc, Y + (ptrdiff_t)rb * j.ys, D + (ptrdiff_t)rb * j.dst_stride, npx);
+        dec_row<FMT, VEC>(j, tb, uc, vc, yb, D + (ptrdiff_t)rb * j.dst_stride, npx);
 }
 
 // I420 / YV12 / NV12 targets: plane copies (libswscale's planarCopyWrapper / planarToNv12Wrapper); YV12 arrives
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(256) dec_planar_kernel(const DecPlanarJob j)
         if (xb >= j.w) return;
         const uint8_t *s = j.y + so + (ptrdiff_t)row * j.ys + xb;
         uint8_t *d = j.dy + dof + (size_t)row * j.w + xb;
-        if (VEC) *(uint4 *)d = ldg_stream128(s);
+        if (VEC) DEC_ST128((uint4 *)d, ldg_stream128(s));
         else for (int q = 0; q < 16 && xb + q < j.w; q++) d[q] = __ldg(s + q);
         return;
     }
@@ -254,15 +265,15 @@ __global__ void __launch_bounds__(256) dec_planar_kernel(const DecPlanarJob j)
         uint8_t *d = j.du + dof + (size_t)r * j.w + xb;
         if (VEC) {
             const uint2 a = ldg_stream64(su + (xb >> 1)), b = ldg_stream64(sv + (xb >> 1));
-            *(uint4 *)d = make_uint4(__byte_perm(a.x, b.x, 0x5140), __byte_perm(a.x, b.x, 0x7362),
-                                     __byte_perm(a.y, b.y, 0x5140), __byte_perm(a.y, b.y, 0x7362));
+            DEC_ST128((uint4 *)d, make_uint4(__byte_perm(a.x, b.x, 0x5140), __byte_perm(a.x, b.x, 0x7362),
+                                             __byte_perm(a.y, b.y, 0x5140), __byte_perm(a.y, b.y, 0x7362)));
         } else
             for (int q = 0; q < 8 && (xb >> 1) + q < cw; q++) { d[2 * q] = __ldg(su + (xb >> 1) + q); d[2 * q + 1] = __ldg(sv + (xb >> 1) + q); }
         return;
     }
     if (xb >= cw) return;
     uint8_t *du = j.du + dof + (size_t)r * cw + xb, *dv = j.dv + dof + (size_t)r * cw + xb;
-    if (VEC) { *(uint4 *)du = ldg_stream128(su + xb); *(uint4 *)dv = ldg_stream128(sv + xb); }
+    if (VEC) { DEC_ST128((uint4 *)du, ldg_stream128(su + xb)); DEC_ST128((uint4 *)dv, ldg_stream128(sv + xb)); }
     else for (int q = 0; q < 16 && xb + q < cw; q++) { du[q] = __ldg(su + xb + q); dv[q] = __ldg(sv + xb + q); }
 }
 
