@@ -26,7 +26,7 @@ namespace xv {
 
 enum { DEC_BGRA = 0, DEC_BGR = 1, DEC_YUYV = 2, DEC_UYVY = 3 };
 // resident blocks per SM the register allocation aims at: measured best per format on B200 (profiles/README.md R2.6)
-#define DEC_BLOCKS_PER_SM(FMT) ((FMT) == DEC_BGRA ? 6 : 8)
+#define DEC_BLOCKS_PER_SM(FMT) ((FMT) == DEC_BGRA || (FMT) == DEC_BGR ? 6 : 8)
 
 struct DecRow {             // one output row of the vertical chroma filter
     int pos;                // first of the 4 chroma lines
