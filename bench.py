@@ -296,6 +296,22 @@ def stage1_roofline(torch, args):
             lambda: dd.decompress_batch(dib.data_ptr(), W * H * 4, (b0, b0 + W * H, b0 + W * H * 5 // 4), (W, W // 2, W // 2), dfb, dn))
         ctx.sync()
         dd.close()
+        if "gbs" in out["decode_yuv420p_to_bgra"] and not args.no_cpu_baseline:
+            # the reference's own CPU path for this stage is libswscale (codec.c:2292): time the copy this image carries,
+            # driven like the reference drives it, one thread, five pictures
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+                import numpy as np
+                import swsref
+                if swsref.available():
+                    rng = np.random.default_rng(0)
+                    py, pu, pv = (rng.integers(0, 256, sh, dtype=np.uint8) for sh in ((H, W), (H // 2, W // 2), (H // 2, W // 2)))
+                    tm = []
+                    swsref.decompress_convert(py, pu, pv, 9 | 0x1000, 1, 0, repeat=5, timing=tm)
+                    out["decode_yuv420p_to_bgra"]["cpu_reference"] = {"kind": "libswscale " + swsref.version() + " sws_scale, context built once, 1 thread",
+                                                                      "ms_per_picture": tm[0] * 1e3}
+            except Exception as e:
+                out["decode_yuv420p_to_bgra"]["cpu_reference"] = {"error": f"{type(e).__name__}: {e}"}
     except Exception as e:
         out["decode_yuv420p_to_bgra"] = {"error": f"{type(e).__name__}: {e}"}
     try:

@@ -66,7 +66,7 @@ def picture_size(csp, w, h):
     return ((w * 3 + 3) & ~3) * h if csp == CSP_BGR else w * 4 * h
 
 
-def decompress_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0, pad_tail=64):
+def decompress_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0, pad_tail=64, repeat=1, timing=None):
     """What x264vfw_decompress does with one decoded yuv420p picture (y, u, v: 2-D uint8, any row stride):
     returns the output DIB bytes (picture_size long).  The buffer handed to libswscale carries pad_tail spare bytes
     because its SIMD writers store whole groups of 8 pixels (see oracle/decode_oracle.c header)."""
@@ -106,7 +106,13 @@ def decompress_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0, pad_tail=64):
     ls += [0] * (4 - len(ls))
     src = (C.c_void_p * 4)(y.ctypes.data, u.ctypes.data, v.ctypes.data, None)
     ss = (C.c_int * 4)(y.strides[0], u.strides[0], v.strides[0], 0)
-    r = sws.sws_scale(ctx, src, ss, 0, h, (C.c_void_p * 4)(*data), (C.c_int * 4)(*ls))   # codec.c:2292
+    dp, dl = (C.c_void_p * 4)(*data), (C.c_int * 4)(*ls)
+    import time
+    t0 = time.perf_counter()
+    for _ in range(repeat):                     # repeat > 1: bench.py times the call alone, context built once like codec.c:2282
+        r = sws.sws_scale(ctx, src, ss, 0, h, dp, dl)                                    # codec.c:2292
+    if timing is not None:
+        timing.append((time.perf_counter() - t0) / repeat)
     sws.sws_freeContext(ctx)
     if r != h:
         raise RuntimeError("sws_scale returned %d" % r)
