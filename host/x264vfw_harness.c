@@ -9,6 +9,11 @@
  *                             x264_encoder_encode (:1693) -> here: lookahead put + decisions
  *   harness_compress_end    ~ x264vfw_compress_end (codec.c:1838): flush (:1848-1854), close (:1857)
  *
+ *   harness_decompress_query / _begin / harness_decompress / _end
+ *                           ~ x264vfw_decompress_query (codec.c:1930), _begin (:1982), x264vfw_decompress (:2154,
+ *                             the part after avcodec_receive_frame: picture_fill, U/V swap, vflip, lazy context,
+ *                             sws_scale, :2243-2295), _end (:2298); SURVEY 8(f) row 4
+ *
  * It is a Linux stand-in for the Win32 caller, not a re-implementation of the wrapper: no ICM
  * messages, no registry, no muxers.  Build: make -C host.  Usage: see main() below.
  */
@@ -123,6 +128,66 @@ int harness_compress_end(harness_codec *c, FILE *out)
     free(c->conv_buf); free(c->qp); free(c->qp_aq);                                             /* codec.c:1872 */
     memset(c, 0, sizeof(*c));
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Decompress side.  The H.264 decode (libavcodec, codec.c:2160-2238) is not part
+ * of the path: the harness is handed the decoded picture (AVFrame data[] / linesize[]).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    x264vfw_cuda_ctx *ctx;
+    x264vfw_cuda_dec *dec;               /* codec->sws */
+    int out_csp, width, height;          /* get_csp() of the output header, VFLIP bit included */
+    int colorspace, fullrange;           /* decoder_context->colorspace / color_range (codec.c:2091, :2114) */
+} harness_decoder;
+
+#define HARNESS_ICERR_OK         0
+#define HARNESS_ICERR_BADFORMAT (-2)
+#define HARNESS_ICERR_ERROR     (-100)
+
+int harness_decompress_query(const harness_bih *in, const harness_bih *out, unsigned out_size_image)
+{
+    /* codec.c:1948-1977 (the fourcc check of the INPUT header, :1945, is the caller's: the harness has no bitstream) */
+    if (in->biWidth <= 0 || in->biHeight <= 0) return HARNESS_ICERR_BADFORMAT;
+    if (in->biWidth % 2 || in->biHeight % 2) return HARNESS_ICERR_BADFORMAT;
+    if (!out) return HARNESS_ICERR_OK;
+    if (in->biWidth != out->biWidth || in->biHeight != abs(out->biHeight)) return HARNESS_ICERR_BADFORMAT;
+    int i_csp = get_csp(out);
+    if (i_csp == X264VFW_CUDA_CSP_NONE) return HARNESS_ICERR_BADFORMAT;
+    int64_t size = x264vfw_cuda_dec_picture_size(i_csp, in->biWidth, in->biHeight);
+    if (size < 0) return HARNESS_ICERR_BADFORMAT;      /* csp_to_pix_fmt == NONE there; here also the YV16 / YV24 outputs this library leaves out */
+    if (out_size_image != 0 && out_size_image < (uint64_t)size) return HARNESS_ICERR_BADFORMAT;
+    return HARNESS_ICERR_OK;
+}
+
+int harness_decompress_begin(harness_decoder *d, const harness_bih *in, const harness_bih *out, int colorspace, int fullrange)
+{
+    memset(d, 0, sizeof(*d));
+    if (harness_decompress_query(in, out, 0) != HARNESS_ICERR_OK) return HARNESS_ICERR_BADFORMAT;    /* codec.c:1988 */
+    d->out_csp = get_csp(out);                                                                      /* codec.c:1994-1998 */
+    d->width = in->biWidth; d->height = in->biHeight;
+    d->colorspace = colorspace; d->fullrange = fullrange;
+    if (x264vfw_cuda_ctx_create(&d->ctx, -1) < 0) return HARNESS_ICERR_ERROR;
+    return HARNESS_ICERR_OK;
+}
+
+/* lpOutput: the application's DIB (icd->lpOutput), x264vfw_cuda_dec_picture_size() bytes */
+int harness_decompress(harness_decoder *d, const uint8_t *const data[3], const int linesize[3], uint8_t *lpOutput)
+{
+    if (!d->dec &&                                                                                  /* codec.c:2282-2290 */
+        x264vfw_cuda_dec_open(&d->dec, d->ctx, d->out_csp, d->width, d->height, d->colorspace, d->fullrange) < 0)
+        return HARNESS_ICERR_ERROR;
+    /* picture_fill, the YV12 pointer swap and the bottom-up flip (codec.c:2258-2280) follow from out_csp inside */
+    if (x264vfw_cuda_dec_convert(d->dec, lpOutput, data, linesize) < 0) return HARNESS_ICERR_ERROR; /* codec.c:2292 */
+    return HARNESS_ICERR_OK;
+}
+
+int harness_decompress_end(harness_decoder *d)
+{
+    x264vfw_cuda_dec_close(d->dec);                                                                 /* codec.c:2306 */
+    x264vfw_cuda_ctx_destroy(d->ctx);
+    memset(d, 0, sizeof(*d));
+    return HARNESS_ICERR_OK;
 }
 
 /* ------------------------------------------------------------------------------------------
