@@ -411,6 +411,42 @@ int x264vfw_cuda_opencl_slicetype_end( x264vfw_cuda_la *la );
  * put.  Returns 0 / -1. */
 int x264vfw_cuda_la_stats( x264vfw_cuda_la *la, uint64_t out[16] );
 
+/* ---- SURVEY 8(f) row 3, remainder: the encoder-side weight analysis and the integral image -------------------------
+ * [x264] x264_weights_analyse( h, fenc, ref, 0 ) (encoder/slicetype.c; reached from x264_encoder_encode, codec.c:1693, when a P
+ * frame is about to be coded with weightp >= 1): explicit weights {on, scale, denom, offset} for luma, U and V of `fenc`
+ * against its nearest reference.  Luma is scored on the lowres planes with the reference compensated by the lookahead's list-0
+ * vectors of that distance, chroma at full resolution on NV12 planes; the (scale, offset) window grows with subme.  All
+ * pointers are DEVICE pointers; the two lowres buffers are the 4 padded planes x264vfw_cuda_lowres_init lays out (what
+ * x264vfw_cuda_la_read(LA_LOWRES) returns), the chroma planes what x264vfw_cuda_chroma_nv12_pad writes (mod-16 padded NV12,
+ * 4:2:0), the statistics [x264] i_pixel_sum / i_pixel_ssd (LA_PIXEL_STATS).  lowres_mvs == NULL is upstream's 0x7FFF
+ * sentinel: the lookahead never searched that (frame, distance), the reference is used uncompensated. */
+typedef struct x264vfw_cuda_weights_in
+{
+    int width, height;                 /* display size */
+    const uint8_t  *fenc_lowres, *ref_lowres;
+    const int16_t  *lowres_mvs;        /* int16[mb][2], quarter-pel lowres vectors of (fenc, list 0, fenc - ref), or NULL */
+    const uint16_t *intra_cost;        /* uint16[mb]: fenc->i_intra_cost */
+    const uint8_t  *fenc_uv, *ref_uv;
+    int uv_stride;
+    uint64_t fenc_sum[3], fenc_ssd[3], ref_sum[3], ref_ssd[3];
+    int subme;                         /* analyse.i_subpel_refine: the search window and sad / satd */
+    int weightp;                       /* analyse.i_weighted_pred; -1 (X264_WEIGHTP_FAKE) also reports cost_delta */
+} x264vfw_cuda_weights_in;
+int x264vfw_cuda_weights_analyse( x264vfw_cuda_ctx *ctx, const x264vfw_cuda_weights_in *in, int32_t out[3][4], float *cost_delta );
+/* The same on a lookahead session opened with keep_frames: lowres planes, vectors, intra costs and statistics of display
+ * indices `fenc` and `ref` come from the session, the caller adds the two chroma planes. */
+int x264vfw_cuda_la_weights_analyse( x264vfw_cuda_la *la, int fenc, int ref, const uint8_t *fenc_uv_dev, const uint8_t *ref_uv_dev,
+                                     int uv_stride, int32_t out[3][4], float *cost_delta );
+
+/* [x264] the integral image x264_frame_filter builds behind the half-pel planes for the exhaustive searches (me esa / tesa;
+ * common/mc.c integral_init8h + 8v, and 4h + 4v for the 4x4 plane of --partitions p4x4): for every position of a PADDED
+ * plane (plane_dev = its top-left corner, `rows` rows of `stride` bytes, e.g. plane 0 of x264vfw_cuda_hpel_filter's output)
+ * sum8[y*stride + x] = sum of the 8x8 pixels whose top-left is (x, y), modulo 2^16 like upstream's uint16 arithmetic; sum4
+ * (may be NULL) the same for 4x4.  Written for y <= rows-8 (rows-4), x <= stride-9 (stride-5) -- everything the search can
+ * address; the remaining entries are left untouched.  n_frames planes per launch (+f*plane_bytes / +f*sum_elems). */
+int x264vfw_cuda_integral_init( x264vfw_cuda_ctx *ctx, uint16_t *sum8_dev, uint16_t *sum4_dev, const uint8_t *plane_dev,
+                                int stride, int rows, size_t plane_bytes, size_t sum_elems, int n_frames );
+
 /* ---- B1b: decoder-side output conversion ---------------------------------------------
  * Replaces the libswscale pair of the reference's decompress path: x264vfw_init_sws_context (codec.c:2075-2152,
  * called lazily at codec.c:2282-2290) becomes x264vfw_cuda_dec_open, sws_scale (codec.c:2292) becomes

@@ -1594,6 +1594,246 @@ void orc_la_mbtree(orc_la *la, const int *frame_idx, const int *types, int num_f
     }
     macroblock_tree(la, frames, num_frames, b_intra);
 }
+/* ------------------------------------------------------------------------------------------
+ * SURVEY 8(f) row 3, remainder: [x264] x264_weights_analyse( h, fenc, ref, 0 ) -- the ENCODER-side explicit
+ * weight analysis of a P frame against its nearest reference (called from x264_encoder_encode via
+ * reference_build_list / weighted_reference_duplicate when weightp >= 1), and the helpers it uses in
+ * [x264] encoder/slicetype.c: weight_cost_init_luma, weight_cost_luma, weight_cost_init_chroma,
+ * weight_cost_chroma, weight_slice_header_cost, x264_weight_get_h264; [x264] common/mc.c: mc_chroma;
+ * [x264] common/pixel.c: pixel_asd8.  Restated from upstream as the rest of this file (PARITY UNPINNED).
+ *
+ * What differs from the lookahead's call (b_lookahead = 1, weights_analyse above):
+ *   - luma is still scored on the LOWRES planes, but the reference is first motion compensated with the
+ *     lookahead's own list-0 vectors for that distance (when that search was run), 8x8 by 8x8;
+ *   - both chroma planes are scored at full resolution on the deinterleaved NV12 planes, the reference
+ *     compensated by mc_chroma with the SAME lowres vector of the MB (upstream passes the lowres quarter-pel
+ *     vector where a full-resolution one is expected, i.e. half the displacement: kept), cost = |sum of block
+ *     differences| (asd8: only the DC matters), header cost with 4 x lambda;
+ *   - scale and offset are searched in a window that grows with subme (weight_check_distance);
+ *   - the offset guess is truncated (no + 0.5), chroma shares one denominator.
+ * fenc_uv / ref_uv: NV12 chroma planes of the frames padded to mod 16 (8*mb_w pairs x 8*mb_h rows, 4:2:0);
+ * references past the edge replicate the edge pair, which is what upstream's x264_frame_expand_border_chroma
+ * leaves there.  out[plane] = {on, scale, denom, offset}.
+ * ---------------------------------------------------------------------------------------- */
+static inline int uv_at(const uint8_t *uv, int stride, int cw, int ch, int x, int y, int c)
+{
+    x = x < 0 ? 0 : x >= cw ? cw - 1 : x;
+    y = y < 0 ? 0 : y >= ch ? ch - 1 : y;
+    return uv[(ptrdiff_t)y * stride + 2 * x + c];
+}
+
+/* [x264] mc_chroma for one 8x8 block of component c; (bx, by) = block origin in chroma pixels */
+static void mc_chroma_8x8(uint8_t dst[64], const uint8_t *uv, int stride, int cw, int ch, int bx, int by, int mvx, int mvy, int c)
+{
+    const int d8x = mvx & 7, d8y = mvy & 7;
+    const int cA = (8 - d8x) * (8 - d8y), cB = d8x * (8 - d8y), cC = (8 - d8x) * d8y, cD = d8x * d8y;
+    const int x0 = bx + (mvx >> 3), y0 = by + (mvy >> 3);
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++)
+            dst[y * 8 + x] = (cA * uv_at(uv, stride, cw, ch, x0 + x, y0 + y, c) + cB * uv_at(uv, stride, cw, ch, x0 + x + 1, y0 + y, c) +
+                              cC * uv_at(uv, stride, cw, ch, x0 + x, y0 + y + 1, c) + cD * uv_at(uv, stride, cw, ch, x0 + x + 1, y0 + y + 1, c) + 32) >> 6;
+}
+
+static int weight_header_cost(const weight_t *w, int b_chroma)
+{
+    const int lambda = b_chroma ? 4 : 1;                      /* x264_lambda_tab[X264_LOOKAHEAD_QP] = 1 */
+    const int denom_cost = ue_size(w->denom) * (2 - b_chroma);
+    return lambda * 1 * (10 + denom_cost + 2 * (se_size(w->scale) + se_size(w->offset)));     /* numslices = 1 */
+}
+
+typedef struct {
+    orc_la *la; frame_t *fenc, *ref; int searched, dist;
+    const uint8_t *fenc_uv, *ref_uv; int uv_stride;
+} wfull_t;
+
+static unsigned wfull_cost(wfull_t *c, int plane, const weight_t *w)
+{
+    orc_la *la = c->la;
+    unsigned cost = 0;
+    int i_mb = 0;
+    if (!plane) {
+        const int stride = la->lstride;
+        for (int y = 0; y < la->lh; y += 8)
+            for (int x = 0; x < la->lw; x += 8, i_mb++) {
+                uint8_t buf[64];
+                if (c->searched) {                              /* weight_cost_init_luma */
+                    const int16_t *mv = c->fenc->mvs[0][c->dist][i_mb];
+                    get_ref_8x8(buf, c->ref->lowres, stride, mv[0] + (x << 2), mv[1] + (y << 2), NULL);
+                } else
+                    for (int yy = 0; yy < 8; yy++) memcpy(buf + yy * 8, c->ref->lowres[0] + (y + yy) * stride + x, 8);
+                if (w) for (int i = 0; i < 64; i++) buf[i] = weight_px(w, buf[i]);
+                int cmp = mbcmp(la, buf, 8, c->fenc->lowres[0] + y * stride + x, stride);
+                cost += MIN(cmp, c->fenc->intra_cost[i_mb]);
+            }
+        if (w) cost += weight_header_cost(w, 0);
+        return cost;
+    }
+    const int cw = 8 * la->mb_w, ch = 8 * la->mb_h, comp = plane - 1;
+    for (int y = 0; y < ch; y += 8)
+        for (int x = 0; x < cw; x += 8, i_mb++) {
+            uint8_t buf[64];
+            if (c->searched) {                                  /* weight_cost_init_chroma */
+                const int16_t *mv = c->fenc->mvs[0][c->dist][i_mb];
+                mc_chroma_8x8(buf, c->ref_uv, c->uv_stride, cw, ch, x, y, mv[0], mv[1], comp);    /* 2*mvy >> v_shift, 4:2:0 */
+            } else
+                for (int i = 0; i < 64; i++) buf[i] = c->ref_uv[(ptrdiff_t)(y + (i >> 3)) * c->uv_stride + 2 * (x + (i & 7)) + comp];
+            int sum = 0;                                        /* pixel_asd8 */
+            for (int i = 0; i < 64; i++) {
+                int r = w ? weight_px(w, buf[i]) : buf[i];
+                sum += r - c->fenc_uv[(ptrdiff_t)(y + (i >> 3)) * c->uv_stride + 2 * (x + (i & 7)) + comp];
+            }
+            cost += abs(sum);
+        }
+    if (w) cost += weight_header_cost(w, 1);
+    return cost;
+}
+
+int orc_la_weights_full(orc_la *la, int f_enc, int f_ref, const uint8_t *fenc_uv, const uint8_t *ref_uv, int uv_stride,
+                        int out[3][4], float *cost_delta)
+{
+    static const uint8_t weight_check_distance[][2] = {{0, 0}, {0, 0}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {1, 1}, {1, 1}, {2, 1}, {2, 1}, {4, 2}};
+    if (la->p.chroma_format != 1) return -1;                    /* 4:2:0 only here */
+    frame_t *fenc = la->all[f_enc], *ref = la->all[f_ref];
+    const int dist = fenc->i_frame - ref->i_frame - 1;
+    if (dist < 0 || dist > ORC_BFRAME_MAX) return -1;
+    const float epsilon = 1.f / 128.f;
+    weight_t weights[3] = {{0, 1, 0, 0}, {0, 1, 0, 0}, {0, 1, 0, 0}};
+    float guess_scale[3], fenc_mean[3], ref_mean[3];
+    const int dims[2] = {la->luma_h * la->luma_w, (la->luma_h / 2) * (la->luma_w / 2)};
+    for (int plane = 0; plane < 3; plane++) {
+        int zero_bias = !ref->pixel_ssd[plane];
+        float fenc_var = fenc->pixel_ssd[plane] + zero_bias;
+        float ref_var = ref->pixel_ssd[plane] + zero_bias;
+        guess_scale[plane] = sqrtf(fenc_var / ref_var);
+        fenc_mean[plane] = (float)(fenc->pixel_sum[plane] + zero_bias) / dims[!!plane] / 1;
+        ref_mean[plane] = (float)(ref->pixel_sum[plane] + zero_bias) / dims[!!plane] / 1;
+    }
+    int chroma_denom = 7;
+    while (chroma_denom > 0) {                                   /* make sure both chroma scales fit */
+        float thresh = 127.f / (1 << chroma_denom);
+        if (guess_scale[1] < thresh && guess_scale[2] < thresh) break;
+        chroma_denom--;
+    }
+    wfull_t c = {la, fenc, ref, fenc->mvs_searched[0][dist], dist, fenc_uv, ref_uv, uv_stride};
+    const int subme = la->p.subme < 0 ? 0 : la->p.subme > 11 ? 11 : la->p.subme;
+    if (cost_delta) *cost_delta = 0;
+
+    for (int plane = 0; plane < 3 && !(plane && !weights[0].on); plane++) {
+        if (fabsf(ref_mean[plane] - fenc_mean[plane]) < 0.5f && fabsf(1.f - guess_scale[plane]) < epsilon) {
+            weights[plane] = (weight_t){0, 1, 0, 0};
+            continue;
+        }
+        if (plane) {
+            weights[plane].denom = chroma_denom;
+            weights[plane].scale = clip3((int)round(guess_scale[plane] * (1 << chroma_denom)), 0, 255);
+            if (weights[plane].scale > 127) { weights[1].on = weights[2].on = 0; break; }
+        } else {
+            int scale = (int)round(guess_scale[0] * 128), denom = 7;     /* x264_weight_get_h264 */
+            while (denom > 0 && scale > 127) { denom--; scale >>= 1; }
+            weights[0].scale = MIN(scale, 127); weights[0].denom = denom; weights[0].offset = 0;
+        }
+        int found = 0, mindenom = weights[plane].denom, minscale = weights[plane].scale, minoff = 0;
+        if (!plane && !fenc->b_intra_calculated) { frame_t *one[1] = {fenc}; frame_cost(la, one, 0, 0, 0); }
+        unsigned origscore, minscore;
+        origscore = minscore = wfull_cost(&c, plane, NULL);
+        if (!minscore) continue;
+
+        const int scale_dist = weight_check_distance[subme][0], offset_dist = weight_check_distance[subme][1];
+        const int start_scale = clip3(minscale - scale_dist, 0, 127), end_scale = clip3(minscale + scale_dist, 0, 127);
+        for (int i_scale = start_scale; i_scale <= end_scale; i_scale++) {
+            int cur_scale = i_scale;
+            int cur_offset = fenc_mean[plane] - ref_mean[plane] * cur_scale / (1 << mindenom) + 0.5f * 0;
+            if (cur_offset < -128 || cur_offset > 127) {
+                cur_offset = clip3(cur_offset, -128, 127);
+                cur_scale = clip3f((1 << mindenom) * (fenc_mean[plane] - cur_offset) / ref_mean[plane] + 0.5f, 0, 127);
+            }
+            const int start_offset = clip3(cur_offset - offset_dist, -128, 127), end_offset = clip3(cur_offset + offset_dist, -128, 127);
+            for (int i_off = start_offset; i_off <= end_offset; i_off++) {
+                weight_t w = {1, cur_scale, mindenom, i_off};
+                unsigned sc = wfull_cost(&c, plane, &w);
+                if (sc < minscore) { minscore = sc; minscale = cur_scale; minoff = i_off; found = 1; }
+                /* don't check any more offsets if the previous one had a lower cost than the current one */
+                if (minoff == start_offset && i_off != start_offset) break;
+            }
+        }
+        if (!plane)
+            while (mindenom > 0 && !(minscale & 1)) { mindenom--; minscale >>= 1; }
+        if (!found || (minscale == 1 << mindenom && minoff == 0) || (float)minscore / origscore > 0.998f) {
+            weights[plane] = (weight_t){0, 1, 0, 0};
+            continue;
+        }
+        weights[plane] = (weight_t){1, minscale, mindenom, minoff};
+        if (la->p.weightp == ORC_WEIGHTP_FAKE && !plane && cost_delta) *cost_delta = (float)minscore / origscore;
+    }
+    /* optimise and unify the chroma denominator */
+    if (weights[1].on || weights[2].on) {
+        int denom = weights[1].on ? weights[1].denom : weights[2].denom;
+        const int both = weights[1].on && weights[2].on;
+        while ((!both && denom == 7) ||
+               (denom > 0 && !(weights[1].on && (weights[1].scale & 1)) && !(weights[2].on && (weights[2].scale & 1)))) {
+            denom--;
+            for (int i = 1; i <= 2; i++)
+                if (weights[i].on) { weights[i].scale >>= 1; weights[i].denom = denom; }
+        }
+    }
+    for (int i = 0; i < 3; i++) {
+        if (!weights[i].on) weights[i] = (weight_t){0, 1, 0, 0};      /* weightfn == NULL: the fields are not looked at */
+        out[i][0] = weights[i].on; out[i][1] = weights[i].scale; out[i][2] = weights[i].denom; out[i][3] = weights[i].offset;
+    }
+    return 0;
+}
+
+/* test hook: one score of the analysis above */
+unsigned orc_test_weights_full_cost(orc_la *la, int f_enc, int f_ref, const uint8_t *fenc_uv, const uint8_t *ref_uv, int uv_stride,
+                                    int plane, int weighted, int scale, int denom, int offset)
+{
+    frame_t *fenc = la->all[f_enc], *ref = la->all[f_ref];
+    const int dist = fenc->i_frame - ref->i_frame - 1;
+    wfull_t c = {la, fenc, ref, fenc->mvs_searched[0][dist], dist, fenc_uv, ref_uv, uv_stride};
+    weight_t w = {1, scale, denom, offset};
+    if (!plane && !fenc->b_intra_calculated) { frame_t *one[1] = {fenc}; frame_cost(la, one, 0, 0, 0); }
+    return wfull_cost(&c, plane, weighted ? &w : NULL);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * [x264] the integral image x264_frame_filter builds after the half-pel planes when the encoder searches
+ * exhaustively (me esa / tesa; [x264] common/mc.c integral_init8h / integral_init8v, and 4h / 4v for the
+ * 4x4 plane of --partitions p4x4).  Upstream fills it row by row in place (a horizontal running sum added
+ * to the row above, then a vertical difference 8 rows later), in uint16 arithmetic that wraps.  What the
+ * exhaustive search reads afterwards is, for every position whose 8x8 (4x4) window lies inside the padded
+ * plane:  sum8[y][x] = sum of the 64 pixels of the window with top-left (x, y)   (mod 2^16)
+ * This function runs upstream's row recurrences (running horizontal sum + row above, vertical difference) on a padded plane (pad = the 32-pixel border of the
+ * half-pel planes; plane points at the top-left corner of the PADDED plane, rows = height + 64) so that
+ * the device's direct box sums can be compared against them over exactly that domain.
+ * sum8 / sum4: rows x stride uint16 (sum4 may be NULL).  Valid output rows: 0 .. rows-9 (rows-5 for sum4),
+ * columns 0 .. stride-9.
+ * ---------------------------------------------------------------------------------------- */
+void orc_integral_init(uint16_t *sum8, uint16_t *sum4, const uint8_t *plane, int stride, int rows)
+{
+    /* running buffers laid out like upstream's: row r+1 of `acc` = horizontal sums of pixel row r + row r of acc */
+    uint16_t *acc8 = calloc((size_t)(rows + 1) * stride, sizeof(uint16_t));
+    uint16_t *acc4 = sum4 ? calloc((size_t)(rows + 1) * stride, sizeof(uint16_t)) : NULL;
+    for (int y = 0; y < rows; y++) {
+        const uint8_t *pix = plane + (size_t)y * stride;
+        uint16_t *s = acc8 + (size_t)(y + 1) * stride;
+        int v = pix[0] + pix[1] + pix[2] + pix[3] + pix[4] + pix[5] + pix[6] + pix[7];        /* integral_init8h */
+        for (int x = 0; x < stride - 8; x++) { s[x] = (uint16_t)(v + s[x - stride]); v += pix[x + 8] - pix[x]; }
+        if (acc4) {
+            s = acc4 + (size_t)(y + 1) * stride;
+            v = pix[0] + pix[1] + pix[2] + pix[3];                                            /* integral_init4h */
+            for (int x = 0; x < stride - 4; x++) { s[x] = (uint16_t)(v + s[x - stride]); v += pix[x + 4] - pix[x]; }
+        }
+    }
+    for (int y = 0; y + 8 <= rows; y++)                                                       /* integral_init8v */
+        for (int x = 0; x < stride - 8; x++)
+            sum8[(size_t)y * stride + x] = (uint16_t)(acc8[(size_t)(y + 8) * stride + x] - acc8[(size_t)y * stride + x]);
+    if (sum4)
+        for (int y = 0; y + 4 <= rows; y++)                                                   /* integral_init4v, 4x4 plane */
+            for (int x = 0; x < stride - 4; x++)
+                sum4[(size_t)y * stride + x] = (uint16_t)(acc4[(size_t)(y + 4) * stride + x] - acc4[(size_t)y * stride + x]);
+    free(acc8); free(acc4);
+}
+
 void orc_la_counters(orc_la *la, uint64_t out[4]) { out[0] = la->n_mbcost; out[1] = la->n_search; out[2] = la->n_sad; out[3] = la->n_satd; }
 
 /* ---- test hooks (see lookahead_oracle.h) ---- */

@@ -107,6 +107,13 @@ void orc_la_weight(orc_la *la, int frame, int out[4]);
 const uint16_t *orc_cost_mv_table(int mv_range, int *half_len);
 /* run one mb-tree pass over explicit display indices with explicit types (for kernel parity) */
 void orc_la_mbtree(orc_la *la, const int *frame_idx, const int *types, int num_frames, int b_intra);
+/* [x264] x264_weights_analyse(h, fenc, ref, 0), the encoder-side weight analysis of P frame `fenc`
+ * against display index `ref` (luma on the lowres planes compensated by the lookahead's vectors, chroma at full
+ * resolution on NV12 planes padded to mod 16).  out[plane] = {on, scale, denom, offset}; -1 when not 4:2:0. */
+int orc_la_weights_full(orc_la *la, int fenc, int ref, const uint8_t *fenc_uv, const uint8_t *ref_uv, int uv_stride,
+                        int out[3][4], float *cost_delta);
+/* [x264] integral_init8h/8v (+4h/4v): upstream's recurrences on a padded plane; see the definition for the valid domain */
+void orc_integral_init(uint16_t *sum8, uint16_t *sum4, const uint8_t *plane, int stride, int rows);
 /* counters: number of MB motion searches / SAD / SATD evaluations performed so far */
 void orc_la_counters(orc_la *la, uint64_t out[4]);
 

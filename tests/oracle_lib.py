@@ -355,6 +355,24 @@ class OracleLookahead:
     def frame_cost(self, p0, p1, b):
         return self.o.orc_la_frame_cost(self.h, p0, p1, b)
 
+    def weights_full(self, fenc, ref, fenc_uv: np.ndarray, ref_uv: np.ndarray, uv_stride):
+        """[x264] x264_weights_analyse(h, fenc, ref, 0): ([[on, scale, denom, offset]] * 3, cost_delta) or None (-1)."""
+        out = (C.c_int * 4 * 3)()
+        delta = C.c_float(0)
+        self.o.orc_la_weights_full.restype = C.c_int
+        self.o.orc_la_weights_full.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int * 4 * 3), C.POINTER(C.c_float)]
+        if self.o.orc_la_weights_full(self.h, fenc, ref, fenc_uv.ctypes.data, ref_uv.ctypes.data, uv_stride, C.byref(out), C.byref(delta)) < 0:
+            return None
+        return [[int(out[p][i]) for i in range(4)] for p in range(3)], float(delta.value)
+
+    def weights_full_cost(self, fenc, ref, fenc_uv, ref_uv, uv_stride, plane, weight=None):
+        """One score of that analysis (test hook): weight = (scale, denom, offset) or None for the unweighted score."""
+        self.o.orc_test_weights_full_cost.restype = C.c_uint
+        self.o.orc_test_weights_full_cost.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        w = weight or (0, 0, 0)
+        return int(self.o.orc_test_weights_full_cost(self.h, fenc, ref, fenc_uv.ctypes.data, ref_uv.ctypes.data, uv_stride, plane,
+                                                     int(weight is not None), w[0], w[1], w[2]))
+
     def _arr(self, ptr, n, dtype):
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dtype).itemsize,)).view(dtype).copy()
 
@@ -451,3 +469,16 @@ def decode_source(w, h, seed=0, pad=0):
     o += (cw + pad) * ch
     v = raw[o:o + (cw + pad) * ch].reshape(ch, cw + pad)[:, :cw]
     return y, u, v
+
+
+def oracle_integral_init(plane: np.ndarray, with_sum4=True):
+    """[x264] integral_init8h/8v (+4h/4v) on a padded plane (2-D uint8, contiguous rows): (sum8, sum4 or None), uint16 arrays of the
+    plane's shape; valid where the 8x8 (4x4) window lies inside the plane."""
+    o = oracle()
+    rows, stride = plane.shape
+    plane = np.ascontiguousarray(plane)
+    s8 = np.zeros((rows, stride), np.uint16)
+    s4 = np.zeros((rows, stride), np.uint16) if with_sum4 else None
+    o.orc_integral_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    o.orc_integral_init(s8.ctypes.data, s4.ctypes.data if with_sum4 else None, plane.ctypes.data, stride, rows)
+    return s8, s4

@@ -19,6 +19,19 @@ _sig = {
     "x264vfw_cuda_opencl_slicetype_prep": [_V, _I, _I],
     "x264vfw_cuda_opencl_slicetype_end": [_V],
 }
+
+
+class WeightsIn(C.Structure):
+    """x264vfw_cuda_weights_in: inputs of [x264] x264_weights_analyse(h, fenc, ref, 0) as device pointers."""
+    _fields_ = [("width", _I), ("height", _I), ("fenc_lowres", _V), ("ref_lowres", _V), ("lowres_mvs", _V), ("intra_cost", _V),
+                ("fenc_uv", _V), ("ref_uv", _V), ("uv_stride", _I),
+                ("fenc_sum", C.c_uint64 * 3), ("fenc_ssd", C.c_uint64 * 3), ("ref_sum", C.c_uint64 * 3), ("ref_ssd", C.c_uint64 * 3),
+                ("subme", _I), ("weightp", _I)]
+
+
+_sig["x264vfw_cuda_weights_analyse"] = [_V, C.POINTER(WeightsIn), C.POINTER(C.c_int32 * 4 * 3), C.POINTER(C.c_float)]
+_sig["x264vfw_cuda_la_weights_analyse"] = [_V, _I, _I, _V, _V, _I, C.POINTER(C.c_int32 * 4 * 3), C.POINTER(C.c_float)]
+_sig["x264vfw_cuda_integral_init"] = [_V, _V, _V, _V, _I, _I, C.c_size_t, C.c_size_t, _I]
 for _n, _a in _sig.items():
     getattr(lib, _n).restype = C.c_int
     getattr(lib, _n).argtypes = _a
@@ -82,3 +95,26 @@ class OpenclHooks:
 
     def slicetype_end(self):
         _ck(lib.x264vfw_cuda_opencl_slicetype_end(self.la.h))
+
+
+def weights_analyse(ctx: Context, win: WeightsIn):
+    """[x264] x264_weights_analyse(h, fenc, ref, 0) on device buffers.  Returns ([[on, scale, denom, offset]] * 3, cost_delta)."""
+    out = (C.c_int32 * 4 * 3)()
+    delta = C.c_float(0)
+    _ck(lib.x264vfw_cuda_weights_analyse(ctx.handle, C.byref(win), C.byref(out), C.byref(delta)))
+    return [[int(out[p][i]) for i in range(4)] for p in range(3)], float(delta.value)
+
+
+def la_weights_analyse(la, fenc: int, ref: int, fenc_uv: int, ref_uv: int, uv_stride: int):
+    """The same for display indices of a lookahead session opened with keep_frames; fenc_uv / ref_uv: device addresses of the
+    frames' NV12 chroma planes padded to mod 16 (x264vfw_cuda_chroma_nv12_pad)."""
+    out = (C.c_int32 * 4 * 3)()
+    delta = C.c_float(0)
+    _ck(lib.x264vfw_cuda_la_weights_analyse(la.handle, fenc, ref, fenc_uv, ref_uv, uv_stride, C.byref(out), C.byref(delta)))
+    return [[int(out[p][i]) for i in range(4)] for p in range(3)], float(delta.value)
+
+
+def integral_init(ctx: Context, sum8: int, sum4: int, plane: int, stride: int, rows: int, plane_bytes: int = 0, sum_elems: int = 0,
+                  n_frames: int = 1):
+    """[x264] integral_init8h/8v (+4h/4v): 8x8 (and 4x4) box sums of a padded plane, device addresses."""
+    _ck(lib.x264vfw_cuda_integral_init(ctx.handle, sum8, sum4 or None, plane, stride, rows, plane_bytes, sum_elems, n_frames))

@@ -2261,6 +2261,48 @@ int x264vfw_cuda_la_profile(x264vfw_cuda_la *h, int enable, double ms[16], uint6
     return 0;
 }
 
+// [x264] x264_weights_analyse(h, fenc, ref, 0) on a session that kept its frames (la_weights_full.cu)
+int x264vfw_cuda_la_weights_analyse(x264vfw_cuda_la *h, int fenc_i, int ref_i, const uint8_t *fenc_uv, const uint8_t *ref_uv,
+                                    int uv_stride, int32_t out[3][4], float *cost_delta)
+{
+    La *la = (La *)h;
+    if (!la || !fenc_uv || !ref_uv || !out) { set_error("null argument"); return -1; }
+    XV_CUDA_OK(cudaSetDevice(la->device));
+    if (worker_join(la) < 0) return -1;
+    if (la->p.chroma_format != 1) { set_error("weights_analyse: 4:2:0 only"); return -1; }
+    const int n = (int)la->by_index.size();
+    if (fenc_i < 0 || fenc_i >= n || ref_i < 0 || ref_i >= fenc_i || fenc_i - ref_i > la->p.bframes + 1) { set_error("weights_analyse: bad indices"); return -1; }
+    Frame *fenc = la->by_index[fenc_i], *ref = la->by_index[ref_i];
+    if (!fenc || !ref) { set_error("weights_analyse: frame was recycled (open with keep_frames)"); return -1; }
+    if (la_sync(la) < 0) return -1;
+    for (int e = 1; e <= la->me_side; e++) XV_CUDA_OK(cudaStreamSynchronize(la->st_me[e]));
+    if (ensure_stats(la, fenc) < 0 || ensure_stats(la, ref) < 0) return -1;
+    if (!fenc->b_intra_calculated) {                         // "if( !fenc->b_intra_calculated ) slicetype_frame_cost( h, &a, &fenc, 0, 0, 0 )"
+        Frame *one[1] = {fenc};
+        if (frame_cost(la, one, 0, 0, 0, true) < 0) return -1;
+    }
+    const int dist = fenc_i - ref_i - 1;
+    x264vfw_cuda_weights_in in;
+    memset(&in, 0, sizeof(in));
+    in.width = la->g.width; in.height = la->g.height;
+    in.fenc_lowres = fenc->lowres; in.ref_lowres = ref->lowres;
+    in.lowres_mvs = fenc->searched[0][dist] ? (const int16_t *)fenc->mvs[0][dist] : nullptr;
+    in.intra_cost = fenc->intra_cost;
+    in.fenc_uv = fenc_uv; in.ref_uv = ref_uv; in.uv_stride = uv_stride;
+    for (int i = 0; i < 3; i++) {
+        in.fenc_sum[i] = fenc->pixel_sum[i]; in.fenc_ssd[i] = fenc->pixel_ssd[i];
+        in.ref_sum[i] = ref->pixel_sum[i]; in.ref_ssd[i] = ref->pixel_ssd[i];
+    }
+    in.subme = la->p.subme; in.weightp = la->p.weightp;
+    unsigned *d_res = nullptr, *h_res = nullptr;
+    XV_CUDA_OK(cudaMalloc((void **)&d_res, sizeof(unsigned) * 3 * 48));
+    if (cudaMallocHost((void **)&h_res, sizeof(unsigned) * 3 * 48) != cudaSuccess) { cudaFree(d_res); set_error("pinned allocation failed"); return -1; }
+    memset(h_res, 0, sizeof(unsigned) * 3 * 48);
+    const int rc = weights_analyse_full(la->st, la->g, &in, out, cost_delta, d_res, h_res);
+    cudaFree(d_res); cudaFreeHost(h_res);
+    return rc;
+}
+
 int x264vfw_cuda_la_stats(x264vfw_cuda_la *h, uint64_t out[16])
 {
     La *la = (La *)h;

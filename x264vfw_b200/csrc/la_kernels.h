@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+struct x264vfw_cuda_weights_in;     // include/x264vfw_cuda.h
+
 namespace xv {
 
 struct LaGeom {
@@ -114,6 +116,11 @@ struct WeightCostJob {
 };
 int launch_weight_cost(cudaStream_t st, const LaGeom &g, const WeightCostJob &job);
 int launch_weight_plane(cudaStream_t st, const LaGeom &g, uint8_t *dst, const uint8_t *src_plane_base, WeightDev w);
+
+// ---- encoder-side weight analysis ([x264] x264_weights_analyse(..., 0); la_weights_full.cu) ----
+// d_result / h_result: 3 * 48 unsigned each (device / pinned host), h_result zeroed by the caller
+int weights_analyse_full(cudaStream_t st, const LaGeom &g, const ::x264vfw_cuda_weights_in *in, int32_t out[3][4], float *cost_delta,
+                         unsigned *d_result, unsigned *h_result);
 
 // ---- mb-tree ([x264] mbtree_propagate_cost/_list, macroblock_tree_finish) ------------------
 struct PropagateJob {
