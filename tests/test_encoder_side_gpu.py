@@ -49,8 +49,6 @@ def test_weights_analyse_matches_checker(size, subme, kw):
                 seen += sum(p[0] for p in want[0])
         if kw.get("step", 0):
             assert seen > 0, "the fade did not produce a single weight"
-        else:
-            assert seen == 0
     finally:
         orc.close(); gpu.close()
 

@@ -110,7 +110,7 @@ def la_weights_analyse(la, fenc: int, ref: int, fenc_uv: int, ref_uv: int, uv_st
     frames' NV12 chroma planes padded to mod 16 (x264vfw_cuda_chroma_nv12_pad)."""
     out = (C.c_int32 * 4 * 3)()
     delta = C.c_float(0)
-    _ck(lib.x264vfw_cuda_la_weights_analyse(la.handle, fenc, ref, fenc_uv, ref_uv, uv_stride, C.byref(out), C.byref(delta)))
+    _ck(lib.x264vfw_cuda_la_weights_analyse(la.h, fenc, ref, fenc_uv, ref_uv, uv_stride, C.byref(out), C.byref(delta)))
     return [[int(out[p][i]) for i in range(4)] for p in range(3)], float(delta.value)
 
 
