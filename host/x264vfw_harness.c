@@ -138,6 +138,7 @@ typedef struct {
     x264vfw_cuda_ctx *ctx;
     x264vfw_cuda_dec *dec;               /* codec->sws */
     int out_csp, width, height;          /* get_csp() of the output header, VFLIP bit included */
+    int src_chroma;                      /* 1: the decoder delivers yuv420p, 2: yuv422p (decoder_context->pix_fmt, codec.c:2092) */
     int colorspace, fullrange;           /* decoder_context->colorspace / color_range (codec.c:2091, :2114) */
 } harness_decoder;
 
@@ -160,13 +161,13 @@ int harness_decompress_query(const harness_bih *in, const harness_bih *out, unsi
     return HARNESS_ICERR_OK;
 }
 
-int harness_decompress_begin(harness_decoder *d, const harness_bih *in, const harness_bih *out, int colorspace, int fullrange)
+int harness_decompress_begin(harness_decoder *d, const harness_bih *in, const harness_bih *out, int src_chroma, int colorspace, int fullrange)
 {
     memset(d, 0, sizeof(*d));
     if (harness_decompress_query(in, out, 0) != HARNESS_ICERR_OK) return HARNESS_ICERR_BADFORMAT;    /* codec.c:1988 */
     d->out_csp = get_csp(out);                                                                      /* codec.c:1994-1998 */
     d->width = in->biWidth; d->height = in->biHeight;
-    d->colorspace = colorspace; d->fullrange = fullrange;
+    d->src_chroma = src_chroma; d->colorspace = colorspace; d->fullrange = fullrange;
     if (x264vfw_cuda_ctx_create(&d->ctx, -1) < 0) return HARNESS_ICERR_ERROR;
     return HARNESS_ICERR_OK;
 }
@@ -175,7 +176,7 @@ int harness_decompress_begin(harness_decoder *d, const harness_bih *in, const ha
 int harness_decompress(harness_decoder *d, const uint8_t *const data[3], const int linesize[3], uint8_t *lpOutput)
 {
     if (!d->dec &&                                                                                  /* codec.c:2282-2290 */
-        x264vfw_cuda_dec_open(&d->dec, d->ctx, d->out_csp, d->width, d->height, d->colorspace, d->fullrange) < 0)
+        x264vfw_cuda_dec_open(&d->dec, d->ctx, d->out_csp, d->width, d->height, d->src_chroma, d->colorspace, d->fullrange) < 0)
         return HARNESS_ICERR_ERROR;
     /* picture_fill, the YV12 pointer swap and the bottom-up flip (codec.c:2258-2280) follow from out_csp inside */
     if (x264vfw_cuda_dec_convert(d->dec, lpOutput, data, linesize) < 0) return HARNESS_ICERR_ERROR; /* codec.c:2292 */

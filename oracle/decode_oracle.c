@@ -246,18 +246,26 @@ static inline int c_table(const orc_yuv2rgb_t *k, int idx)
 
 /* dst formats: the reference's own output csp codes (csp.h:30-44), as get_csp() returns them for
  * the output header (codec.c:1994-1998) */
-enum { F_I420 = 1, F_YV12 = 2, F_NV12 = 5, F_YUYV = 6, F_UYVY = 7, F_BGR = 8, F_BGRA = 9, F_VFLIP = 0x1000 };
+enum { F_I420 = 1, F_YV12 = 2, F_YV16 = 3, F_NV12 = 5, F_YUYV = 6, F_UYVY = 7, F_BGR = 8, F_BGRA = 9, F_VFLIP = 0x1000 };
 
-int orc_decode_convert(int out_csp, uint8_t *dst, const uint8_t *const src[3], const int src_stride[3],
-                       int w, int h, int avcol_spc, int fullrange)
+/* src_chroma: 1 = the decoder delivers yuv420p, 2 = yuv422p.  A 4:2:2 picture has a chroma line per luma line, so the
+ * vertical filter degenerates to one tap of 1.0 and libswscale picks its single-line writers (yuv2packed1): the SIMD ones
+ * (rows 0..h-3) then add no rounder, (sample << 7) >> 4 instead of (sum >> 16) + 4; the C ones (last two rows) take
+ * (sample << 7 + 64) >> 7 = the sample.  YUY2 / UYVY / YV16 targets are pure (de)interleaves (yuv422pToYuy2Wrapper,
+ * yuv422pToUyvyWrapper, planarCopyWrapper).  Checked against libswscale like the 4:2:0 case. */
+int orc_decode_convert_src(int src_chroma, int out_csp, uint8_t *dst, const uint8_t *const src[3], const int src_stride[3],
+                           int w, int h, int avcol_spc, int fullrange)
 {
     const int fmt = out_csp & 0xff;
     const int flip = (out_csp & F_VFLIP) != 0;
     if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) return -1;        /* codec.c:1950-1954 */
-    const int cw = w / 2, ch = h / 2;
+    if (src_chroma != 1 && src_chroma != 2) return -1;
+    const int v422 = src_chroma == 2;
+    const int cw = w / 2, ch = v422 ? h : h / 2;
+    if ((v422 && (fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12)) || (!v422 && fmt == F_YV16)) return -1;   /* yuv2planeX path: not restated */
 
     /* x264vfw_picture_fill (codec.c:419-503) geometry of the output DIB */
-    if (fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12) {
+    if (fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12 || fmt == F_YV16) {
         if (flip) return -1;                                      /* x264vfw_picture_vflip: RGB only (codec.c:510-527) */
         uint8_t *py = dst, *p1 = dst + (size_t)w * h, *p2 = p1 + (size_t)cw * ch;
         for (int r = 0; r < h; r++) memcpy(py + (size_t)r * w, src[0] + (ptrdiff_t)r * src_stride[0], w);
@@ -268,7 +276,7 @@ int orc_decode_convert(int out_csp, uint8_t *dst, const uint8_t *const src[3], c
                     p1[(size_t)r * w + 2 * x + 1] = src[2][(ptrdiff_t)r * src_stride[2] + x];
                 }
         } else {
-            uint8_t *pu = fmt == F_YV12 ? p2 : p1, *pv = fmt == F_YV12 ? p1 : p2;   /* codec.c:2263-2274 */
+            uint8_t *pu = fmt != F_I420 ? p2 : p1, *pv = fmt != F_I420 ? p1 : p2;   /* YV12 / YV16: codec.c:2263-2274 */
             for (int r = 0; r < ch; r++) {
                 memcpy(pu + (size_t)r * cw, src[1] + (ptrdiff_t)r * src_stride[1], cw);
                 memcpy(pv + (size_t)r * cw, src[2] + (ptrdiff_t)r * src_stride[2], cw);
@@ -278,7 +286,7 @@ int orc_decode_convert(int out_csp, uint8_t *dst, const uint8_t *const src[3], c
     }
     if (fmt != F_BGR && fmt != F_BGRA && fmt != F_YUYV && fmt != F_UYVY) return -1;
     if (flip && fmt != F_BGR && fmt != F_BGRA) return -1;
-    if (ch < 5) return -1;                       /* below this initFilter degenerates (fewer taps); not restated */
+    if (h < 10) return -1;                       /* below this initFilter degenerates (fewer taps); not restated */
 
     ptrdiff_t stride = fmt == F_BGR ? ((w * 3 + 3) & ~3) : fmt == F_BGRA ? w * 4 : w * 2;
     if (flip) { dst += stride * (h - 1); stride = -stride; }      /* codec.c:515-518 */
@@ -287,8 +295,13 @@ int orc_decode_convert(int out_csp, uint8_t *dst, const uint8_t *const src[3], c
     int *pos = malloc(sizeof(int) * h);
     if (!coef || !pos) { free(coef); free(pos); return -1; }
     /* vertical chroma filter: filterAlign 2 (x86), one = 1<<12, both sitings 128 */
-    int n = orc_sws_bicubic_filter(ch, h, 2, 1 << 12, 128, 128, coef, pos);
-    if (n != 4) { free(coef); free(pos); return -1; }
+    if (v422) {
+        for (int r = 0; r < h; r++) { pos[r] = r < h - 3 ? r : h - 4; for (int j = 0; j < 4; j++) coef[r][j] = j == r - pos[r] ? 4096 : 0; }
+    } else {
+        int n = orc_sws_bicubic_filter(ch, h, 2, 1 << 12, 128, 128, coef, pos);
+        if (n != 4) { free(coef); free(pos); return -1; }
+    }
+    const int rnd = v422 ? 0 : 4;                                 /* the rounder of the vertical-filter SIMD writers */
 
     orc_yuv2rgb_t k;
     yuv2rgb_setup(&k, avcol_spc, fullrange);
@@ -320,8 +333,8 @@ int orc_decode_convert(int out_csp, uint8_t *dst, const uint8_t *const src[3], c
                     U = clip_u8((au + (1 << 18)) >> 19);
                     V = clip_u8((av + (1 << 18)) >> 19);
                 } else {                                          /* psrad 16, packssdw, paddw rounder, psraw 3, packuswb */
-                    int u16 = wrap16((int)(au >> 16 < -32768 ? -32768 : au >> 16 > 32767 ? 32767 : au >> 16) + 4);
-                    int v16 = wrap16((int)(av >> 16 < -32768 ? -32768 : av >> 16 > 32767 ? 32767 : av >> 16) + 4);
+                    int u16 = wrap16((int)(au >> 16 < -32768 ? -32768 : au >> 16 > 32767 ? 32767 : au >> 16) + rnd);
+                    int v16 = wrap16((int)(av >> 16 < -32768 ? -32768 : av >> 16 > 32767 ? 32767 : av >> 16) + rnd);
                     U = clip_u8(u16 >> 3);
                     V = clip_u8(v16 >> 3);
                 }
@@ -344,12 +357,12 @@ int orc_decode_convert(int out_csp, uint8_t *dst, const uint8_t *const src[3], c
                 int64_t su = au >> 16, sv = av >> 16;
                 su = su < -32768 ? -32768 : su > 32767 ? 32767 : su;
                 sv = sv < -32768 ? -32768 : sv > 32767 ? 32767 : sv;
-                const int ud = wrap16(wrap16((int)su + 4) - 0x400), vd = wrap16(wrap16((int)sv + 4) - 0x400);
+                const int ud = wrap16(wrap16((int)su + rnd) - 0x400), vd = wrap16(wrap16((int)sv + rnd) - 0x400);
                 const int ug = (ud * k.ug_coeff) >> 16, vg = (vd * k.vg_coeff) >> 16;
                 const int ub = (ud * k.ub_coeff) >> 16, vr = (vd * k.vr_coeff) >> 16;
                 const int g = wrap16(ug + vg);
                 for (int p = 0; p < 2; p++) {
-                    const int y16 = wrap16(((p ? y1 : y0) << 3) + 4);
+                    const int y16 = wrap16(((p ? y1 : y0) << 3) + rnd);
                     const int yv = (wrap16(y16 - k.y_offset) * k.y_coeff) >> 16;
                     Bv[p] = clip_u8(wrap16(yv + ub)); Gv[p] = clip_u8(wrap16(yv + g)); Rv[p] = clip_u8(wrap16(yv + vr));
                 }
@@ -366,12 +379,18 @@ int orc_decode_convert(int out_csp, uint8_t *dst, const uint8_t *const src[3], c
     return 0;
 }
 
+int orc_decode_convert(int out_csp, uint8_t *dst, const uint8_t *const src[3], const int src_stride[3],
+                       int w, int h, int avcol_spc, int fullrange)
+{
+    return orc_decode_convert_src(1, out_csp, dst, src, src_stride, w, h, avcol_spc, fullrange);
+}
+
 /* size of the output DIB: x264vfw_picture_get_size (codec.c:505-508) */
 int64_t orc_decode_picture_size(int out_csp, int w, int h)
 {
     switch (out_csp & 0xff) {
     case F_I420: case F_YV12: case F_NV12: return (int64_t)w * h + 2 * (int64_t)(w / 2) * (h / 2);
-    case F_YUYV: case F_UYVY: return (int64_t)w * 2 * h;
+    case F_YV16: case F_YUYV: case F_UYVY: return (int64_t)w * 2 * h;
     case F_BGR:  return (int64_t)((w * 3 + 3) & ~3) * h;
     case F_BGRA: return (int64_t)w * 4 * h;
     default: return -1;

@@ -31,6 +31,21 @@ def pixel_bytes(out, csp, w, h):
     return out
 
 
+def cases_422():
+    """High 4:2:2 decoder pictures (what "keep input colorspace" makes of YUY2 / UYVY input): the outputs that keep or raise the
+    chroma height."""
+    for w, h in [(16, 12), (70, 38), (72, 40), (320, 240), (1920, 1080)]:
+        for csp in [sr.CSP_YV16, sr.CSP_YUYV, sr.CSP_UYVY, sr.CSP_BGR, sr.CSP_BGRA, sr.CSP_BGRA | sr.CSP_VFLIP, sr.CSP_BGR | sr.CSP_VFLIP]:
+            if (csp & sr.CSP_VFLIP) and w % 8:
+                continue
+            for spc, full in MATRICES:
+                if w >= 320 and (spc, full) not in ((2, 0), (1, 0)):
+                    continue
+                if csp & 0xff in (sr.CSP_YV16, sr.CSP_YUYV, sr.CSP_UYVY) and (spc, full) != (2, 0):
+                    continue
+                yield w, h, csp, spc, full
+
+
 def cases():
     for w, h in SIZES:
         for csp in FORMATS:
@@ -50,6 +65,11 @@ def main():
         y, u, v = ol.decode_source(w, h, seed=spc + full, pad=24)
         dib = sr.decompress_convert(y, u, v, csp, spc, full)
         out["cases"].append({"w": w, "h": h, "csp": csp, "spc": spc, "full": full,
+                             "fnv": ol.fnv(pixel_bytes(dib, csp, w, h))})
+    for w, h, csp, spc, full in cases_422():
+        y, u, v = ol.decode_source(w, h, seed=spc + full, pad=24, src_chroma=2)
+        dib = sr.decompress_convert(y, u, v, csp, spc, full, src_chroma=2)
+        out["cases"].append({"w": w, "h": h, "csp": csp, "spc": spc, "full": full, "src": 2,
                              "fnv": ol.fnv(pixel_bytes(dib, csp, w, h))})
     # one small picture in full, for debugging a mismatch by eye
     y, u, v = ol.decode_source(16, 10, seed=2, pad=24)

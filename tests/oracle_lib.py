@@ -439,13 +439,13 @@ def decode_picture_size(out_csp, w, h):
     return int(o.orc_decode_picture_size(out_csp, w, h))
 
 
-def oracle_decode_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0):
-    """y, u, v: 2-D uint8 planes of one decoded yuv420p picture (any row stride).  Returns the output DIB bytes, or
-    None where the checker refuses (-1)."""
+def oracle_decode_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0, src_chroma=1):
+    """y, u, v: 2-D uint8 planes of one decoded yuv420p (src_chroma 1) or yuv422p (2) picture (any row stride).  Returns the
+    output DIB bytes, or None where the checker refuses (-1)."""
     o = oracle()
-    o.orc_decode_convert.restype = C.c_int
-    o.orc_decode_convert.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int,
-                                     C.c_int, C.c_int]
+    o.orc_decode_convert_src.restype = C.c_int
+    o.orc_decode_convert_src.argtypes = [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                         C.c_int, C.c_int]
     h, w = y.shape
     size = decode_picture_size(out_csp, w, h)
     if size < 0:
@@ -453,15 +453,15 @@ def oracle_decode_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0):
     out = np.zeros(size, np.uint8)
     src = (C.c_void_p * 3)(y.ctypes.data, u.ctypes.data, v.ctypes.data)
     ss = (C.c_int * 3)(y.strides[0], u.strides[0], v.strides[0])
-    if o.orc_decode_convert(out_csp, out.ctypes.data, src, ss, w, h, avcol_spc, fullrange) != 0:
+    if o.orc_decode_convert_src(src_chroma, out_csp, out.ctypes.data, src, ss, w, h, avcol_spc, fullrange) != 0:
         return None
     return out
 
 
-def decode_source(w, h, seed=0, pad=0):
-    """Seeded yuv420p picture (SURVEY A.4 byte generator, seed folded into the generator's size arguments); rows
+def decode_source(w, h, seed=0, pad=0, src_chroma=1):
+    """Seeded yuv420p / yuv422p picture (SURVEY A.4 byte generator, seed folded into the generator's size arguments); rows
     carry `pad` spare bytes so that strides differ from widths like a decoder's AVFrame linesize."""
-    cw, ch = w // 2, h // 2
+    cw, ch = w // 2, (h if src_chroma == 2 else h // 2)
     raw = lcg_bytes((w + pad) * h + 2 * (cw + pad) * ch, w + 7 * seed, h + 13 * seed)
     y = raw[:(w + pad) * h].reshape(h, w + pad)[:, :w]
     o = (w + pad) * h

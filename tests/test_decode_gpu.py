@@ -32,8 +32,9 @@ def test_every_libswscale_fixture_is_reproduced_on_the_device(dec):
     for c in GOLDEN["cases"]:
         if c["h"] < 12:
             continue                   # the device path starts at 12 rows (the checker and libswscale go down to 10)
-        y, u, v = ol.decode_source(c["w"], c["h"], seed=c["spc"] + c["full"], pad=24)
-        d = dec.Decompressor(c["csp"], c["w"], c["h"], c["spc"], c["full"], ctx=ctx)
+        src = c.get("src", 1)
+        y, u, v = ol.decode_source(c["w"], c["h"], seed=c["spc"] + c["full"], pad=24, src_chroma=src)
+        d = dec.Decompressor(c["csp"], c["w"], c["h"], c["spc"], c["full"], ctx=ctx, src_chroma=src)
         dib = d.decompress(y, u, v)
         d.close()
         assert ol.fnv(pixel_bytes(dib, c["csp"], c["w"], c["h"])) == c["fnv"], c
@@ -54,6 +55,25 @@ def test_device_matches_checker_on_fresh_inputs(dec, w, h):
             for spc, full in ((2, 0), (1, 1), (9, 0)):
                 want = ol.oracle_decode_convert(y, u, v, csp, spc, full)
                 d = dec.Decompressor(csp, w, h, spc, full)
+                got = d.decompress(y, u, v)
+                d.close()
+                assert (got == want).all(), (w, h, hex(csp), spc, full, kind, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("w,h", [(16, 12), (70, 38), (258, 66), (1920, 1080), (1288, 728)])
+def test_device_matches_checker_on_422_pictures(dec, w, h):
+    """High 4:2:2 decoder pictures: no vertical chroma filter; YUY2 / UYVY / YV16 are (de)interleaves, RGB uses the single-line writers."""
+    rng = np.random.default_rng(w * 3 + h)
+    for kind in range(2):
+        if kind == 0:
+            y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((h, w + 9), (h, w // 2 + 5), (h, w // 2 + 5)))
+        else:
+            y, u, v = (rng.choice(np.array([0, 255], np.uint8), s) for s in ((h, w + 64), (h, w // 2 + 32), (h, w // 2 + 32)))
+        y, u, v = y[:, :w], u[:, :w // 2], v[:, :w // 2]
+        for csp in (3, CSP_YUYV, CSP_UYVY, CSP_BGR, CSP_BGRA, CSP_BGR | VFLIP, CSP_BGRA | VFLIP):
+            for spc, full in ((2, 0), (1, 1), (9, 0)):
+                want = ol.oracle_decode_convert(y, u, v, csp, spc, full, src_chroma=2)
+                d = dec.Decompressor(csp, w, h, spc, full, src_chroma=2)
                 got = d.decompress(y, u, v)
                 d.close()
                 assert (got == want).all(), (w, h, hex(csp), spc, full, kind, int((got != want).sum()))
@@ -94,10 +114,15 @@ def test_batch_entry_on_resident_pictures(dec, csp):
 def test_refusals_and_geometry(dec):
     from x264vfw_b200._lib import CudaError
     assert dec.picture_get_size(CSP_BGR, 70, 38) == 212 * 38
-    assert dec.picture_get_size(3, 64, 32) == -1                      # YV16 output: not covered
-    for args in ((CSP_YUYV | VFLIP, 64, 32), (3, 64, 32), (CSP_BGRA, 64, 8), (CSP_BGRA, 64, 10), (CSP_BGRA, 63, 32), (CSP_BGRA, 64, 0)):
+    assert dec.picture_get_size(4, 64, 32) == -1                      # YV24 output: not covered
+    for args in ((CSP_YUYV | VFLIP, 64, 32), (4, 64, 32), (3, 64, 32), (CSP_BGRA, 64, 8), (CSP_BGRA, 64, 10), (CSP_BGRA, 63, 32), (CSP_BGRA, 64, 0)):
         with pytest.raises(CudaError):
-            dec.Decompressor(*args)
+            dec.Decompressor(*args)                                   # (3 = YV16 from a 4:2:0 picture: another chroma height)
+    for csp in (CSP_I420, CSP_YV12, CSP_NV12):
+        with pytest.raises(CudaError):
+            dec.Decompressor(csp, 64, 32, src_chroma=2)
+    with pytest.raises(CudaError):
+        dec.Decompressor(CSP_BGRA, 64, 32, src_chroma=3)              # 4:4:4 decoder pictures: not covered
     # codec.c:1930-1980
     from x264vfw_b200.csp import fourcc
     assert dec.decompress_query(64, 32, 0, 32, 64, 32) == dec.ICERR_OK

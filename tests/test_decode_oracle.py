@@ -18,7 +18,7 @@ GOLDEN = json.load(open(os.path.join(HERE, "golden", "decode_golden.json")))
 
 
 def case_id(c):
-    return "%dx%d-csp%x-spc%d-%s" % (c["w"], c["h"], c["csp"], c["spc"], "pc" if c["full"] else "tv")
+    return "%dx%d-%s-csp%x-spc%d-%s" % (c["w"], c["h"], "422" if c.get("src", 1) == 2 else "420", c["csp"], c["spc"], "pc" if c["full"] else "tv")
 
 
 SMALL = [c for c in GOLDEN["cases"] if c["w"] <= 320]
@@ -27,16 +27,18 @@ LARGE = [c for c in GOLDEN["cases"] if c["w"] > 320]
 
 @pytest.mark.parametrize("c", SMALL, ids=case_id)
 def test_checker_reproduces_libswscale_fixture(c):
-    y, u, v = ol.decode_source(c["w"], c["h"], seed=c["spc"] + c["full"], pad=24)
-    dib = ol.oracle_decode_convert(y, u, v, c["csp"], c["spc"], c["full"])
+    src = c.get("src", 1)
+    y, u, v = ol.decode_source(c["w"], c["h"], seed=c["spc"] + c["full"], pad=24, src_chroma=src)
+    dib = ol.oracle_decode_convert(y, u, v, c["csp"], c["spc"], c["full"], src_chroma=src)
     assert dib is not None
     assert ol.fnv(pixel_bytes(dib, c["csp"], c["w"], c["h"])) == c["fnv"]
 
 
 def test_checker_reproduces_libswscale_fixture_full_sizes():
     for c in LARGE:
-        y, u, v = ol.decode_source(c["w"], c["h"], seed=c["spc"] + c["full"], pad=24)
-        dib = ol.oracle_decode_convert(y, u, v, c["csp"], c["spc"], c["full"])
+        src = c.get("src", 1)
+        y, u, v = ol.decode_source(c["w"], c["h"], seed=c["spc"] + c["full"], pad=24, src_chroma=src)
+        dib = ol.oracle_decode_convert(y, u, v, c["csp"], c["spc"], c["full"], src_chroma=src)
         assert ol.fnv(pixel_bytes(dib, c["csp"], c["w"], c["h"])) == c["fnv"], case_id(c)
 
 
@@ -62,6 +64,22 @@ def test_checker_against_the_live_library_on_fresh_inputs():
                     assert (pixel_bytes(a, csp, w, h) == pixel_bytes(b, csp, w, h)).all(), (w, h, hex(csp), spc, full)
 
 
+@pytest.mark.skipif(not sr.available(), reason="libswscale 9 (opencv wheel) not importable here")
+def test_checker_against_the_live_library_on_422_pictures():
+    rng = np.random.default_rng(422)
+    for w, h in ((24, 18), (88, 50)):
+        y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((h, w), (h, w // 2), (h, w // 2)))
+        for csp in (sr.CSP_BGRA, sr.CSP_BGR, sr.CSP_YUYV, sr.CSP_UYVY, sr.CSP_YV16, sr.CSP_BGRA | sr.CSP_VFLIP):
+            for spc, full in ((2, 0), (1, 1), (9, 0)):
+                a = sr.decompress_convert(y, u, v, csp, spc, full, src_chroma=2)
+                b = ol.oracle_decode_convert(y, u, v, csp, spc, full, src_chroma=2)
+                assert (pixel_bytes(a, csp, w, h) == pixel_bytes(b, csp, w, h)).all(), (w, h, hex(csp), spc, full)
+    # planar outputs of another chroma height go through libswscale's yuv2planeX path: refused, not approximated
+    assert ol.oracle_decode_convert(y, u, v, sr.CSP_I420, src_chroma=2) is None
+    y0, u0, v0 = ol.decode_source(64, 32)
+    assert ol.oracle_decode_convert(y0, u0, v0, sr.CSP_YV16) is None
+
+
 def test_reference_context_never_gets_full_chroma_interpolation():
     """codec.c:2097 hands `flags` to the context BEFORE codec.c:2110-2111 adds SWS_FULL_CHR_H_INT to the local, so
     RGB output keeps one chroma sample per pixel pair: with flat luma, pixels 2x and 2x+1 of a row are equal."""
@@ -76,6 +94,6 @@ def test_geometry_and_refusals():
     assert ol.decode_picture_size(sr.CSP_NV12, 64, 32) == 64 * 32 * 3 // 2
     y, u, v = ol.decode_source(64, 32)
     assert ol.oracle_decode_convert(y, u, v, sr.CSP_YUYV | sr.CSP_VFLIP) is None   # only RGB can be flipped (codec.c:510-527)
-    assert ol.oracle_decode_convert(y, u, v, 3) is None                          # YV16: not covered
+    assert ol.oracle_decode_convert(y, u, v, 4) is None                          # YV24: not covered
     y, u, v = ol.decode_source(64, 8)
     assert ol.oracle_decode_convert(y, u, v, sr.CSP_BGRA) is None                # fewer than 5 chroma rows: not restated

@@ -86,7 +86,7 @@ def _harness_lib():
     build()
     lib = C.CDLL(os.path.join(ROOT, "host", "libx264vfw_harness.so"))
     lib.harness_decompress_query.argtypes = [C.POINTER(_Bih), C.POINTER(_Bih), C.c_uint]
-    lib.harness_decompress_begin.argtypes = [C.c_void_p, C.POINTER(_Bih), C.POINTER(_Bih), C.c_int, C.c_int]
+    lib.harness_decompress_begin.argtypes = [C.c_void_p, C.POINTER(_Bih), C.POINTER(_Bih), C.c_int, C.c_int, C.c_int]
     lib.harness_decompress.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_void_p]
     lib.harness_decompress_end.argtypes = [C.c_void_p]
     return lib
@@ -121,7 +121,7 @@ def test_harness_decompress_matches_the_checker():
     inp = _Bih(w, h, 24, fcc("H264"))
     for out, csp in ((_Bih(w, h, 32, 0), 9 | 0x1000), (_Bih(w, -h, 24, 0), 8), (_Bih(w, h, 12, fcc("YV12")), 2), (_Bih(w, h, 16, fcc("UYVY")), 7)):
         dec = C.create_string_buffer(256)
-        assert lib.harness_decompress_begin(dec, C.byref(inp), C.byref(out), 1, 0) == 0
+        assert lib.harness_decompress_begin(dec, C.byref(inp), C.byref(out), 1, 1, 0) == 0
         dib = np.zeros(ol.decode_picture_size(csp, w, h), np.uint8)
         data = (C.c_void_p * 3)(y.ctypes.data, u.ctypes.data, v.ctypes.data)
         ls = (C.c_int * 3)(y.strides[0], u.strides[0], v.strides[0])

@@ -35,7 +35,7 @@ struct DecRow {             // one output row of the vertical chroma filter
 };
 
 struct DecConst {
-    // SIMD writers: Yv = (y * yc + ykf) >> 13, chroma deltas = ((s >> 9) * coeff + coeff0) >> 16 with coeff0 = -1020 * coeff
+    // SIMD writers: Yv = (y * yc + ykf) >> 13, chroma deltas = ((s >> 9) * coeff + coeff0) >> 16 with coeff0 = (rounder - 1024) * coeff
     int yc, ykf, vr, ub, vg, ug, vr0, ub0, vg0, ug0;
     // C writers: component = clip8((idx * cy + bias) >> 16), idx = Y + ((C * cxx) >> 16) - (cxx >> 9) ...
     int cy, bias, crv, cbu, cgu, cgv, crv9, cbu9, cgu9, cgv9;
@@ -47,6 +47,7 @@ struct DecJob {
     uint8_t *dst;
     long long dst_stride;   // negative for a bottom-up DIB (x264vfw_picture_vflip, codec.c:510-527)
     int w, h;
+    int v422;               // decoder picture is 4:2:2: every luma row has its own chroma line (no vertical filter)
     size_t src_frame_bytes, dst_frame_bytes;
     const DecRow *rows;
     DecConst k;
@@ -219,7 +220,8 @@ __global__ void __launch_bounds__(256, DEC_BLOCKS_PER_SM(FMT)) dec_packed_kernel
 
     // both rows of the pair read chroma lines pos..pos+3, pos = clamp(k - 2, 0, h/2 - 4) (checked against the filter
     // table when the context is opened), so every load of this thread can be issued before anything is computed
-    const int pos = min(max(k - 2, 0), (j.h >> 1) - 4);
+    // (4:2:2 pictures: the pair's two chroma lines 2k-1, 2k lie in the window that starts at clamp(2k - 1, 0, h - 4))
+    const int pos = j.v422 ? min(max(2 * k - 1, 0), j.h - 4) : min(max(k - 2, 0), (j.h >> 1) - 4);
     const int4 a4 = __ldg((const int4 *)(j.rows + max(ra, 0))), b4 = __ldg((const int4 *)(j.rows + min(rb, j.h - 1)));
     const DecRow ta = {a4.x, a4.y, a4.z, a4.w}, tb = {b4.x, b4.y, b4.z, b4.w};
     uint32_t uc[4], vc[4], ya[2], yb[2];
@@ -239,7 +241,7 @@ struct DecPlanarJob {
     const uint8_t *y, *u, *v;
     int ys, us, vs;
     uint8_t *dy, *du, *dv;      // dv == nullptr: NV12 (du rows hold U,V interleaved)
-    int w, h;
+    int w, h;                   // (chroma rows follow from the grid: rows h .. gridDim.y - 1)
     size_t src_frame_bytes, dst_frame_bytes;
 };
 
@@ -377,7 +379,7 @@ static int to_int16(long long f)
 }
 
 // ff_yuv2rgb_c_init_tables [libswscale/yuv2rgb.c] for brightness 0, contrast = saturation = 1.0 (codec.c:2141-2144)
-static void colour_constants(DecConst &k, int avcol_spc, int fullrange)
+static void colour_constants(DecConst &k, int avcol_spc, int fullrange, int rounder)
 {
     // sws_getCoefficients(): {crv, cbu, cgu, cgv}; the switch of codec.c:2114-2140
     static const int coeffs[5][4] = {
@@ -401,10 +403,12 @@ static void colour_constants(DecConst &k, int avcol_spc, int fullrange)
     else { crv = crv * 224 / 255; cbu = cbu * 224 / 255; cgu = cgu * 224 / 255; cgv = cgv * 224 / 255; }
     const int y_coeff = to_int16(cy << 13), y_off = to_int16(oy << 3);
     // ((y << 3) + 4 - y_off) * y_coeff >> 16 == (y * y_coeff + floor((4 - y_off) * y_coeff / 8)) >> 13 for integer y
-    const int yk = (4 - y_off) * y_coeff;
+    // rounder: the +4 (0.5 in 1/8 units) the vertical-filter writers add; the single-line writers of 4:2:2 pictures do not
+    const int yk = (rounder - y_off) * y_coeff;
     k.yc = y_coeff; k.ykf = yk >= 0 ? yk / 8 : -((-yk + 7) / 8);
     k.vr = to_int16(crv * 8192); k.ub = to_int16(cbu * 8192); k.vg = to_int16(cgv * 8192); k.ug = to_int16(cgu * 8192);
-    k.vr0 = -1020 * k.vr; k.ub0 = -1020 * k.ub; k.vg0 = -1020 * k.vg; k.ug0 = -1020 * k.ug;
+    const int c0 = rounder - 1024;
+    k.vr0 = c0 * k.vr; k.ub0 = c0 * k.ub; k.vg0 = c0 * k.vg; k.ug0 = c0 * k.ug;
     crv = (crv * 65536 + 0x8000) / cy; cbu = (cbu * 65536 + 0x8000) / cy;
     cgu = (cgu * 65536 + 0x8000) / cy; cgv = (cgv * 65536 + 0x8000) / cy;
     k.cy = (int)cy;
@@ -415,7 +419,7 @@ static void colour_constants(DecConst &k, int avcol_spc, int fullrange)
 
 struct Dec {
     Ctx *ctx;
-    int csp, flip, w, h;
+    int csp, flip, w, h, v422;
     DecConst k;
     DecRow *d_rows = nullptr;
     // staging of the host-buffer entry
@@ -429,17 +433,17 @@ static inline bool als(long long v, long long a) { return (v & (a - 1)) == 0; }
 static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src[3], const int ss[3], size_t sfb, int n)
 {
     cudaStream_t st = d->ctx->stream;
-    const int w = d->w, h = d->h, cw = w / 2, ch = h / 2;
+    const int w = d->w, h = d->h, cw = w / 2, ch = d->v422 ? h : h / 2;
     if (n <= 0) return 0;
     if (n > 65535) { set_error("at most 65535 pictures per launch"); return -1; }
-    if (d->csp == X264VFW_CUDA_CSP_I420 || d->csp == X264VFW_CUDA_CSP_YV12 || d->csp == X264VFW_CUDA_CSP_NV12) {
+    if (d->csp == X264VFW_CUDA_CSP_I420 || d->csp == X264VFW_CUDA_CSP_YV12 || d->csp == X264VFW_CUDA_CSP_NV12 || d->csp == X264VFW_CUDA_CSP_YV16) {
         DecPlanarJob j;
         j.y = src[0]; j.u = src[1]; j.v = src[2]; j.ys = ss[0]; j.us = ss[1]; j.vs = ss[2];
         j.w = w; j.h = h; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
         j.dy = dst;
         uint8_t *p1 = dst + (size_t)w * h, *p2 = p1 + (size_t)cw * ch;             // x264vfw_picture_fill, codec.c:425-439,469-480
         if (d->csp == X264VFW_CUDA_CSP_NV12) { j.du = p1; j.dv = nullptr; }
-        else if (d->csp == X264VFW_CUDA_CSP_YV12) { j.du = p2; j.dv = p1; }          // codec.c:2263-2274
+        else if (d->csp == X264VFW_CUDA_CSP_YV12 || d->csp == X264VFW_CUDA_CSP_YV16) { j.du = p2; j.dv = p1; }   // codec.c:2263-2274
         else { j.du = p1; j.dv = p2; }
         const bool vec = als(w, 32) && al(dst, 16) && als((long long)dfb, 16) && als((long long)sfb, 16) &&
                          al(src[0], 16) && al(src[1], 16) && al(src[2], 16) && als(ss[0], 16) && als(ss[1], 16) && als(ss[2], 16) &&
@@ -452,7 +456,7 @@ static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src
     }
     DecJob j;
     j.y = src[0]; j.u = src[1]; j.v = src[2]; j.ys = ss[0]; j.us = ss[1]; j.vs = ss[2];
-    j.w = w; j.h = h; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
+    j.w = w; j.h = h; j.v422 = d->v422; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
     j.rows = d->d_rows; j.k = d->k;
     long long stride = d->csp == X264VFW_CUDA_CSP_BGR ? ((w * 3 + 3) & ~3) : d->csp == X264VFW_CUDA_CSP_BGRA ? w * 4 : w * 2;
     j.dst = dst; j.dst_stride = stride;
@@ -487,7 +491,7 @@ int64_t x264vfw_cuda_dec_picture_size(int i_out_csp, int w, int h)
     switch (i_out_csp & X264VFW_CUDA_CSP_MASK) {
     case X264VFW_CUDA_CSP_I420: case X264VFW_CUDA_CSP_YV12: case X264VFW_CUDA_CSP_NV12:
         return (int64_t)w * h + 2 * (int64_t)(w / 2) * (h / 2);
-    case X264VFW_CUDA_CSP_YUYV: case X264VFW_CUDA_CSP_UYVY: return (int64_t)w * 2 * h;
+    case X264VFW_CUDA_CSP_YV16: case X264VFW_CUDA_CSP_YUYV: case X264VFW_CUDA_CSP_UYVY: return (int64_t)w * 2 * h;
     case X264VFW_CUDA_CSP_BGR:  return (int64_t)((w * 3 + 3) & ~3) * h;
     case X264VFW_CUDA_CSP_BGRA: return (int64_t)w * 4 * h;
     default: return -1;
@@ -495,24 +499,40 @@ int64_t x264vfw_cuda_dec_picture_size(int i_out_csp, int w, int h)
 }
 
 int x264vfw_cuda_dec_open(x264vfw_cuda_dec **pdec, x264vfw_cuda_ctx *ctx, int i_out_csp, int w, int h,
-                          int i_avcol_spc, int b_fullrange)
+                          int i_src_chroma, int i_avcol_spc, int b_fullrange)
 {
     if (!pdec || !ctx) { set_error("null argument"); return -1; }
     *pdec = nullptr;
     const int csp = i_out_csp & X264VFW_CUDA_CSP_MASK, flip = (i_out_csp & X264VFW_CUDA_CSP_VFLIP) != 0;
     if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) { set_error("width/height must be positive and even (codec.c:1950-1954)"); return -1; }
-    if (x264vfw_cuda_dec_picture_size(csp, w, h) < 0) { set_error("output csp %d is not covered (YV16/YV24 outputs are not)", csp); return -1; }
+    if (i_src_chroma != 1 && i_src_chroma != 2) { set_error("decoder pictures must be 4:2:0 (1) or 4:2:2 (2); 4:4:4 is not covered"); return -1; }
+    if (x264vfw_cuda_dec_picture_size(csp, w, h) < 0) { set_error("output csp %d is not covered", csp); return -1; }
+    const bool v422 = i_src_chroma == 2;
+    const bool out420 = csp == X264VFW_CUDA_CSP_I420 || csp == X264VFW_CUDA_CSP_YV12 || csp == X264VFW_CUDA_CSP_NV12;
+    // a change of the vertical chroma resolution between planar formats is libswscale's yuv2planeX path: not covered
+    if ((v422 && out420) || (!v422 && csp == X264VFW_CUDA_CSP_YV16)) { set_error("planar output with another chroma height than the decoder picture is not covered"); return -1; }
     const bool rgb = csp == X264VFW_CUDA_CSP_BGR || csp == X264VFW_CUDA_CSP_BGRA;
     if (flip && !rgb) { set_error("only RGB output can be bottom-up (codec.c:510-527)"); return -1; }
-    const bool planar = csp == X264VFW_CUDA_CSP_I420 || csp == X264VFW_CUDA_CSP_YV12 || csp == X264VFW_CUDA_CSP_NV12;
+    const bool planar = out420 || csp == X264VFW_CUDA_CSP_YV16;
     Ctx *c = (Ctx *)ctx;
     XV_CUDA_OK(cudaSetDevice(c->device));
     Dec *d = new Dec;
-    d->ctx = c; d->csp = csp; d->flip = flip; d->w = w; d->h = h;
-    colour_constants(d->k, i_avcol_spc, b_fullrange != 0);
+    d->ctx = c; d->csp = csp; d->flip = flip; d->w = w; d->h = h; d->v422 = v422;
+    colour_constants(d->k, i_avcol_spc, b_fullrange != 0, v422 ? 0 : 4);
     if (!planar) {
         std::vector<DecRow> rows;
-        if (!vertical_chroma_filter(h / 2, rows, csp == X264VFW_CUDA_CSP_UYVY)) {
+        if (v422 && h >= 12) {
+            // no vertical filter (libswscale's yuv2packed1 writers; plain interleave for 4:2:2 output): one tap of 1.0 on the
+            // row's own chroma line, addressed inside the 4-line window the kernel loads for the row pair
+            rows.resize(h);
+            for (int r = 0; r < h; r++) {
+                const int k = (r + 1) >> 1, pos = std::min(std::max(2 * k - 1, 0), h - 4), t = r - pos;
+                rows[r].pos = pos;
+                rows[r].c01 = t == 0 ? 4096 : t == 1 ? (4096 << 16) : 0;
+                rows[r].c23 = t == 2 ? 4096 : t == 3 ? (4096 << 16) : 0;
+                rows[r].c_writer = csp == X264VFW_CUDA_CSP_UYVY || r >= h - 2;
+            }
+        } else if (v422 || !vertical_chroma_filter(h / 2, rows, csp == X264VFW_CUDA_CSP_UYVY)) {
             set_error("pictures below 12 rows are not covered");
             delete d;
             return -1;
@@ -558,7 +578,7 @@ int x264vfw_cuda_dec_convert(x264vfw_cuda_dec *dec, uint8_t *dst_host, const uin
     for (int i = 0; i < 3; i++) if (src_stride[i] < (i ? d->w / 2 : d->w)) { set_error("source stride below the row width"); return -1; }
     XV_CUDA_OK(cudaSetDevice(d->ctx->device));
     cudaStream_t st = d->ctx->stream;
-    const int w = d->w, h = d->h, cw = w / 2, ch = h / 2;
+    const int w = d->w, h = d->h, cw = w / 2, ch = d->v422 ? h : h / 2;
     // device staging: tight planes with 16-byte aligned rows; the picture is gathered by 2-D copies so that the
     // decoder's linesize padding never crosses the bus
     const int ys = (w + 15) & ~15, cs = (cw + 15) & ~15;

@@ -25,7 +25,7 @@ ICERR_OK, ICERR_BADFORMAT, ICERR_ERROR = 0, -2, -100
 
 _P = C.POINTER
 lib.x264vfw_cuda_dec_open.restype = C.c_int
-lib.x264vfw_cuda_dec_open.argtypes = [_P(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+lib.x264vfw_cuda_dec_open.argtypes = [_P(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
 lib.x264vfw_cuda_dec_close.restype = None
 lib.x264vfw_cuda_dec_close.argtypes = [C.c_void_p]
 lib.x264vfw_cuda_dec_picture_size.restype = C.c_int64
@@ -62,19 +62,21 @@ class Decompressor:
     (codec.c:1994): its VFLIP bit makes RGB bottom-up, YV12 swaps U and V (codec.c:1995-1998)."""
 
     def __init__(self, i_csp: int, width: int, height: int, colorspace: int = AVCOL_SPC_UNSPECIFIED,
-                 fullrange: bool = False, ctx: Context = None):
+                 fullrange: bool = False, ctx: Context = None, src_chroma: int = 1):
+        """src_chroma: 1 = the decoder delivers yuv420p, 2 = yuv422p (High 4:2:2 streams)."""
         self.ctx = ctx or Context()
-        self.i_csp, self.width, self.height = i_csp, width, height
+        self.i_csp, self.width, self.height, self.src_chroma = i_csp, width, height, src_chroma
         self.picture_size = picture_get_size(i_csp, width, height)
         h = C.c_void_p()
-        if lib.x264vfw_cuda_dec_open(C.byref(h), self.ctx.handle, i_csp, width, height, colorspace, int(bool(fullrange))) < 0:
+        if lib.x264vfw_cuda_dec_open(C.byref(h), self.ctx.handle, i_csp, width, height, src_chroma, colorspace, int(bool(fullrange))) < 0:
             raise CudaError(last_error())
         self.handle = h
 
     def decompress(self, y: np.ndarray, u: np.ndarray, v: np.ndarray, out: np.ndarray = None) -> np.ndarray:
         """The sws_scale call of codec.c:2292 on one decoded yuv420p picture held in HOST memory (2-D uint8 arrays,
         any row stride, like AVFrame data[]/linesize[]).  Returns the output DIB bytes."""
-        if y.shape != (self.height, self.width) or u.shape != (self.height // 2, self.width // 2) or v.shape != u.shape:
+        ch = self.height if self.src_chroma == 2 else self.height // 2
+        if y.shape != (self.height, self.width) or u.shape != (ch, self.width // 2) or v.shape != u.shape:
             raise ValueError("plane shapes do not match the context")
         for p in (y, u, v):
             if p.dtype != np.uint8 or p.strides[1] != 1:
