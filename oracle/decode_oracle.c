@@ -246,7 +246,7 @@ static inline int c_table(const orc_yuv2rgb_t *k, int idx)
 
 /* dst formats: the reference's own output csp codes (csp.h:30-44), as get_csp() returns them for
  * the output header (codec.c:1994-1998) */
-enum { F_I420 = 1, F_YV12 = 2, F_YV16 = 3, F_NV12 = 5, F_YUYV = 6, F_UYVY = 7, F_BGR = 8, F_BGRA = 9, F_VFLIP = 0x1000 };
+enum { F_I420 = 1, F_YV12 = 2, F_YV16 = 3, F_YV24 = 4, F_NV12 = 5, F_YUYV = 6, F_UYVY = 7, F_BGR = 8, F_BGRA = 9, F_VFLIP = 0x1000 };
 
 /* src_chroma: 1 = the decoder delivers yuv420p, 2 = yuv422p.  A 4:2:2 picture has a chroma line per luma line, so the
  * vertical filter degenerates to one tap of 1.0 and libswscale picks its single-line writers (yuv2packed1): the SIMD ones
@@ -259,13 +259,18 @@ int orc_decode_convert_src(int src_chroma, int out_csp, uint8_t *dst, const uint
     const int fmt = out_csp & 0xff;
     const int flip = (out_csp & F_VFLIP) != 0;
     if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) return -1;        /* codec.c:1950-1954 */
-    if (src_chroma != 1 && src_chroma != 2) return -1;
-    const int v422 = src_chroma == 2;
-    const int cw = w / 2, ch = v422 ? h : h / 2;
-    if ((v422 && (fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12)) || (!v422 && fmt == F_YV16)) return -1;   /* yuv2planeX path: not restated */
+    if (src_chroma < 1 || src_chroma > 3) return -1;
+    const int v422 = src_chroma == 2, v444 = src_chroma == 3;
+    const int cw = v444 ? w : w / 2, ch = v422 || v444 ? h : h / 2;
+    {   /* a YUV output of another chroma resolution is libswscale's resampling path (yuv2planeX, hscale + dither): not restated */
+        const int out420 = fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12;
+        const int out_chroma = out420 ? 1 : fmt == F_YV16 || fmt == F_YUYV || fmt == F_UYVY ? 2 : fmt == F_YV24 ? 3 : 0;
+        const int planar_out = out420 || fmt == F_YV16 || fmt == F_YV24;
+        if ((planar_out && out_chroma != src_chroma) || (v444 && out_chroma == 2)) return -1;
+    }
 
     /* x264vfw_picture_fill (codec.c:419-503) geometry of the output DIB */
-    if (fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12 || fmt == F_YV16) {
+    if (fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12 || fmt == F_YV16 || fmt == F_YV24) {
         if (flip) return -1;                                      /* x264vfw_picture_vflip: RGB only (codec.c:510-527) */
         uint8_t *py = dst, *p1 = dst + (size_t)w * h, *p2 = p1 + (size_t)cw * ch;
         for (int r = 0; r < h; r++) memcpy(py + (size_t)r * w, src[0] + (ptrdiff_t)r * src_stride[0], w);
@@ -286,6 +291,37 @@ int orc_decode_convert_src(int src_chroma, int out_csp, uint8_t *dst, const uint
     }
     if (fmt != F_BGR && fmt != F_BGRA && fmt != F_YUYV && fmt != F_UYVY) return -1;
     if (flip && fmt != F_BGR && fmt != F_BGRA) return -1;
+    if (v444) {
+        /* 4:4:4 pictures: libswscale switches full chroma interpolation on by itself and EVERY row goes through the portable
+         * writer yuv2rgb_full_1_c -> yuv2rgb_write_full [libswscale/output.c]: per pixel, on the 15-bit intermediates * 4,
+         *   Y = ((y << 9) - y_offset) * y_coeff + (1 << 21),  R = Y + V * v2r,  G = Y + V * v2g + U * u2g,  B = Y + U * u2b
+         * in 32-bit arithmetic that wraps (the products are unsigned in the source), all three clipped to 30 bits when any of
+         * them has one of the top two bits set (== clipping each on its own), >> 22.  Coefficients: the 13-bit ones of the SIMD
+         * writers; y_offset = round16(oy << 9). */
+        orc_yuv2rgb_t k;
+        yuv2rgb_setup(&k, avcol_spc, fullrange);
+        const int y_off9 = round_to_int16(k.oy * (1 << 9));
+        const int bpp = fmt == F_BGRA ? 4 : 3;
+        ptrdiff_t stride = fmt == F_BGR ? ((w * 3 + 3) & ~3) : w * 4;
+        if (flip) { dst += stride * (h - 1); stride = -stride; }
+        for (int r = 0; r < h; r++)
+            for (int x = 0; x < w; x++) {
+                const int32_t Y = (int32_t)((uint32_t)(((src[0][(ptrdiff_t)r * src_stride[0] + x] << 9) - y_off9) * k.y_coeff) + (1u << 21));
+                const int32_t U = (src[1][(ptrdiff_t)r * src_stride[1] + x] - 128) << 9, V = (src[2][(ptrdiff_t)r * src_stride[2] + x] - 128) << 9;
+                int32_t R = (int32_t)((uint32_t)Y + (uint32_t)V * (uint32_t)k.vr_coeff);
+                int32_t G = (int32_t)((uint32_t)Y + (uint32_t)V * (uint32_t)k.vg_coeff + (uint32_t)U * (uint32_t)k.ug_coeff);
+                int32_t B = (int32_t)((uint32_t)Y + (uint32_t)U * (uint32_t)k.ub_coeff);
+                if ((R | G | B) & 0xC0000000) {
+                    R = R < 0 ? 0 : R > 0x3FFFFFFF ? 0x3FFFFFFF : R;
+                    G = G < 0 ? 0 : G > 0x3FFFFFFF ? 0x3FFFFFFF : G;
+                    B = B < 0 ? 0 : B > 0x3FFFFFFF ? 0x3FFFFFFF : B;
+                }
+                uint8_t *q = dst + r * stride + (size_t)x * bpp;
+                q[0] = B >> 22; q[1] = G >> 22; q[2] = R >> 22;
+                if (bpp == 4) q[3] = 255;
+            }
+        return 0;
+    }
     if (h < 10) return -1;                       /* below this initFilter degenerates (fewer taps); not restated */
 
     ptrdiff_t stride = fmt == F_BGR ? ((w * 3 + 3) & ~3) : fmt == F_BGRA ? w * 4 : w * 2;
@@ -391,6 +427,7 @@ int64_t orc_decode_picture_size(int out_csp, int w, int h)
     switch (out_csp & 0xff) {
     case F_I420: case F_YV12: case F_NV12: return (int64_t)w * h + 2 * (int64_t)(w / 2) * (h / 2);
     case F_YV16: case F_YUYV: case F_UYVY: return (int64_t)w * 2 * h;
+    case F_YV24: return (int64_t)w * 3 * h;
     case F_BGR:  return (int64_t)((w * 3 + 3) & ~3) * h;
     case F_BGRA: return (int64_t)w * 4 * h;
     default: return -1;

@@ -46,6 +46,18 @@ def cases_422():
                 yield w, h, csp, spc, full
 
 
+def cases_444():
+    """High 4:4:4 decoder pictures: RGB output (libswscale's full-chroma writer) and the YV24 plane copy."""
+    for w, h in [(16, 12), (70, 38), (72, 40), (320, 240), (1920, 1080)]:
+        for csp in [sr.CSP_YV24, sr.CSP_BGR, sr.CSP_BGRA, sr.CSP_BGRA | sr.CSP_VFLIP, sr.CSP_BGR | sr.CSP_VFLIP]:
+            for spc, full in MATRICES:
+                if w >= 320 and (spc, full) not in ((2, 0), (1, 0)):
+                    continue
+                if csp == sr.CSP_YV24 and (spc, full) != (2, 0):
+                    continue
+                yield w, h, csp, spc, full
+
+
 def cases():
     for w, h in SIZES:
         for csp in FORMATS:
@@ -70,6 +82,11 @@ def main():
         y, u, v = ol.decode_source(w, h, seed=spc + full, pad=24, src_chroma=2)
         dib = sr.decompress_convert(y, u, v, csp, spc, full, src_chroma=2)
         out["cases"].append({"w": w, "h": h, "csp": csp, "spc": spc, "full": full, "src": 2,
+                             "fnv": ol.fnv(pixel_bytes(dib, csp, w, h))})
+    for w, h, csp, spc, full in cases_444():
+        y, u, v = ol.decode_source(w, h, seed=spc + full, pad=24, src_chroma=3)
+        dib = sr.decompress_convert(y, u, v, csp, spc, full, src_chroma=3)
+        out["cases"].append({"w": w, "h": h, "csp": csp, "spc": spc, "full": full, "src": 3,
                              "fnv": ol.fnv(pixel_bytes(dib, csp, w, h))})
     # one small picture in full, for debugging a mismatch by eye
     y, u, v = ol.decode_source(16, 10, seed=2, pad=24)

@@ -10,10 +10,10 @@ import numpy as np
 
 SWS_BICUBIC, SWS_FULL_CHR_H_INT, SWS_FULL_CHR_H_INP, SWS_ACCURATE_RND = 4, 0x2000, 0x4000, 0x40000
 # AVPixelFormat values of libavutil 60
-PIX = {"yuv420p": 0, "yuyv": 1, "bgr": 3, "yuv422p": 4, "uyvy": 15, "nv12": 23, "bgra": 28}
+PIX = {"yuv420p": 0, "yuyv": 1, "bgr": 3, "yuv422p": 4, "yuv444p": 5, "uyvy": 15, "nv12": 23, "bgra": 28}
 # output csp codes of the reference (csp.h:30-44) -> (AVPixelFormat, swap U/V of the output picture)
-CSP_I420, CSP_YV12, CSP_YV16, CSP_NV12, CSP_YUYV, CSP_UYVY, CSP_BGR, CSP_BGRA, CSP_VFLIP = 1, 2, 3, 5, 6, 7, 8, 9, 0x1000
-CSP_TO_PIX = {CSP_I420: "yuv420p", CSP_YV12: "yuv420p", CSP_YV16: "yuv422p", CSP_NV12: "nv12", CSP_YUYV: "yuyv", CSP_UYVY: "uyvy",
+CSP_I420, CSP_YV12, CSP_YV16, CSP_YV24, CSP_NV12, CSP_YUYV, CSP_UYVY, CSP_BGR, CSP_BGRA, CSP_VFLIP = 1, 2, 3, 4, 5, 6, 7, 8, 9, 0x1000
+CSP_TO_PIX = {CSP_I420: "yuv420p", CSP_YV12: "yuv420p", CSP_YV16: "yuv422p", CSP_YV24: "yuv444p", CSP_NV12: "nv12", CSP_YUYV: "yuyv", CSP_UYVY: "uyvy",
               CSP_BGR: "bgr", CSP_BGRA: "bgra"}
 # codec.c:2114-2140: AVCOL_SPC_* -> SWS_CS_*
 SPC_TO_CS = {1: 1, 4: 4, 5: 5, 6: 6, 7: 7, 9: 9, 10: 9}
@@ -63,11 +63,13 @@ def picture_size(csp, w, h):
         return w * h + 2 * (w // 2) * (h // 2)
     if csp in (CSP_YV16, CSP_YUYV, CSP_UYVY):
         return w * 2 * h
+    if csp == CSP_YV24:
+        return w * 3 * h
     return ((w * 3 + 3) & ~3) * h if csp == CSP_BGR else w * 4 * h
 
 
 def decompress_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0, pad_tail=64, repeat=1, timing=None, src_chroma=1):
-    """What x264vfw_decompress does with one decoded yuv420p (src_chroma 1) / yuv422p (2) picture (y, u, v: 2-D uint8, any row stride):
+    """What x264vfw_decompress does with one decoded yuv420p (src_chroma 1) / yuv422p (2) / yuv444p (3) picture (y, u, v: 2-D uint8, any row stride):
     returns the output DIB bytes (picture_size long).  The buffer handed to libswscale carries pad_tail spare bytes
     because its SIMD writers store whole groups of 8 pixels (see oracle/decode_oracle.c header)."""
     sws, avu = libs()
@@ -75,7 +77,7 @@ def decompress_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0, pad_tail=64, 
     fmt, flip = out_csp & 0xff, bool(out_csp & CSP_VFLIP)
     ctx = sws.sws_alloc_context()
     flags = SWS_BICUBIC | SWS_FULL_CHR_H_INP | SWS_ACCURATE_RND                      # codec.c:2081-2082
-    for k, val in ((b"sws_flags", flags), (b"srcw", w), (b"srch", h), (b"src_format", PIX["yuv420p" if src_chroma == 1 else "yuv422p"]),
+    for k, val in ((b"sws_flags", flags), (b"srcw", w), (b"srch", h), (b"src_format", PIX[{1: "yuv420p", 2: "yuv422p", 3: "yuv444p"}[src_chroma]]),
                    (b"src_range", fullrange), (b"dstw", w), (b"dsth", h), (b"dst_format", PIX[CSP_TO_PIX[fmt]]),
                    (b"dst_range", fullrange)):                                     # codec.c:2097-2107
         avu.av_opt_set_int(ctx, k, val, 0)
@@ -95,6 +97,8 @@ def decompress_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0, pad_tail=64, 
             data[1], data[2] = data[2], data[1]
     elif fmt == CSP_YV16:                                                            # codec.c:441-454, swapped like YV12
         data, ls = [base, base + w * h + cw * h, base + w * h], [w, cw, cw]
+    elif fmt == CSP_YV24:                                                            # codec.c:456-467, swapped like YV12
+        data, ls = [base, base + 2 * w * h, base + w * h], [w, w, w]
     elif fmt == CSP_NV12:
         data, ls = [base, base + w * h], [w, w]
     elif fmt in (CSP_YUYV, CSP_UYVY):

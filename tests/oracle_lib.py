@@ -440,7 +440,7 @@ def decode_picture_size(out_csp, w, h):
 
 
 def oracle_decode_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0, src_chroma=1):
-    """y, u, v: 2-D uint8 planes of one decoded yuv420p (src_chroma 1) or yuv422p (2) picture (any row stride).  Returns the
+    """y, u, v: 2-D uint8 planes of one decoded yuv420p (src_chroma 1), yuv422p (2) or yuv444p (3) picture (any row stride).  Returns the
     output DIB bytes, or None where the checker refuses (-1)."""
     o = oracle()
     o.orc_decode_convert_src.restype = C.c_int
@@ -459,9 +459,9 @@ def oracle_decode_convert(y, u, v, out_csp, avcol_spc=2, fullrange=0, src_chroma
 
 
 def decode_source(w, h, seed=0, pad=0, src_chroma=1):
-    """Seeded yuv420p / yuv422p picture (SURVEY A.4 byte generator, seed folded into the generator's size arguments); rows
+    """Seeded yuv420p / yuv422p / yuv444p (src_chroma 1 / 2 / 3) picture (SURVEY A.4 byte generator, seed folded into the generator's size arguments); rows
     carry `pad` spare bytes so that strides differ from widths like a decoder's AVFrame linesize."""
-    cw, ch = w // 2, (h if src_chroma == 2 else h // 2)
+    cw, ch = (w if src_chroma == 3 else w // 2), (h if src_chroma >= 2 else h // 2)
     raw = lcg_bytes((w + pad) * h + 2 * (cw + pad) * ch, w + 7 * seed, h + 13 * seed)
     y = raw[:(w + pad) * h].reshape(h, w + pad)[:, :w]
     o = (w + pad) * h

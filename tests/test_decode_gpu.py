@@ -79,6 +79,26 @@ def test_device_matches_checker_on_422_pictures(dec, w, h):
                 assert (got == want).all(), (w, h, hex(csp), spc, full, kind, int((got != want).sum()))
 
 
+@pytest.mark.parametrize("w,h", [(16, 12), (70, 38), (258, 66), (1920, 1080), (1284, 724)])
+def test_device_matches_checker_on_444_pictures(dec, w, h):
+    """High 4:4:4 decoder pictures: libswscale's per-pixel full-chroma writer (32-bit arithmetic that wraps on saturated colours) and the
+    YV24 plane copy."""
+    rng = np.random.default_rng(w * 5 + h)
+    for kind in range(2):
+        if kind == 0:
+            y, u, v = (rng.integers(0, 256, (h, w + 12), dtype=np.uint8) for _ in range(3))
+        else:
+            y, u, v = (rng.choice(np.array([0, 255], np.uint8), (h, w + 64)) for _ in range(3))
+        y, u, v = y[:, :w], u[:, :w], v[:, :w]
+        for csp in (4, CSP_BGR, CSP_BGRA, CSP_BGR | VFLIP, CSP_BGRA | VFLIP):
+            for spc, full in ((2, 0), (1, 1), (9, 0)):
+                want = ol.oracle_decode_convert(y, u, v, csp, spc, full, src_chroma=3)
+                d = dec.Decompressor(csp, w, h, spc, full, src_chroma=3)
+                got = d.decompress(y, u, v)
+                d.close()
+                assert (got == want).all(), (w, h, hex(csp), spc, full, kind, int((got != want).sum()))
+
+
 @pytest.mark.parametrize("csp", ALL)
 def test_batch_entry_on_resident_pictures(dec, csp):
     """x264vfw_cuda_dec_convert_batch: N pictures in device memory, one launch; every picture equals the checker's."""
@@ -114,15 +134,18 @@ def test_batch_entry_on_resident_pictures(dec, csp):
 def test_refusals_and_geometry(dec):
     from x264vfw_b200._lib import CudaError
     assert dec.picture_get_size(CSP_BGR, 70, 38) == 212 * 38
-    assert dec.picture_get_size(4, 64, 32) == -1                      # YV24 output: not covered
+    assert dec.picture_get_size(4, 64, 32) == 64 * 32 * 3 and dec.picture_get_size(10, 64, 32) == -1
     for args in ((CSP_YUYV | VFLIP, 64, 32), (4, 64, 32), (3, 64, 32), (CSP_BGRA, 64, 8), (CSP_BGRA, 64, 10), (CSP_BGRA, 63, 32), (CSP_BGRA, 64, 0)):
         with pytest.raises(CudaError):
-            dec.Decompressor(*args)                                   # (3 = YV16 from a 4:2:0 picture: another chroma height)
-    for csp in (CSP_I420, CSP_YV12, CSP_NV12):
+            dec.Decompressor(*args)                                   # (3 / 4 = YV16 / YV24 from a 4:2:0 picture: another chroma resolution)
+    for csp in (CSP_I420, CSP_YV12, CSP_NV12, 4):
         with pytest.raises(CudaError):
             dec.Decompressor(csp, 64, 32, src_chroma=2)
+    for csp in (CSP_I420, CSP_NV12, 3, CSP_YUYV, CSP_UYVY):
+        with pytest.raises(CudaError):
+            dec.Decompressor(csp, 64, 32, src_chroma=3)               # 4:4:4 -> subsampled YUV: libswscale resamples the chroma
     with pytest.raises(CudaError):
-        dec.Decompressor(CSP_BGRA, 64, 32, src_chroma=3)              # 4:4:4 decoder pictures: not covered
+        dec.Decompressor(CSP_BGRA, 64, 32, src_chroma=4)
     # codec.c:1930-1980
     from x264vfw_b200.csp import fourcc
     assert dec.decompress_query(64, 32, 0, 32, 64, 32) == dec.ICERR_OK

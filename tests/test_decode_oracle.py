@@ -18,7 +18,7 @@ GOLDEN = json.load(open(os.path.join(HERE, "golden", "decode_golden.json")))
 
 
 def case_id(c):
-    return "%dx%d-%s-csp%x-spc%d-%s" % (c["w"], c["h"], "422" if c.get("src", 1) == 2 else "420", c["csp"], c["spc"], "pc" if c["full"] else "tv")
+    return "%dx%d-%s-csp%x-spc%d-%s" % (c["w"], c["h"], {1: "420", 2: "422", 3: "444"}[c.get("src", 1)], c["csp"], c["spc"], "pc" if c["full"] else "tv")
 
 
 SMALL = [c for c in GOLDEN["cases"] if c["w"] <= 320]
@@ -65,7 +65,7 @@ def test_checker_against_the_live_library_on_fresh_inputs():
 
 
 @pytest.mark.skipif(not sr.available(), reason="libswscale 9 (opencv wheel) not importable here")
-def test_checker_against_the_live_library_on_422_pictures():
+def test_checker_against_the_live_library_on_422_and_444_pictures():
     rng = np.random.default_rng(422)
     for w, h in ((24, 18), (88, 50)):
         y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((h, w), (h, w // 2), (h, w // 2)))
@@ -74,6 +74,16 @@ def test_checker_against_the_live_library_on_422_pictures():
                 a = sr.decompress_convert(y, u, v, csp, spc, full, src_chroma=2)
                 b = ol.oracle_decode_convert(y, u, v, csp, spc, full, src_chroma=2)
                 assert (pixel_bytes(a, csp, w, h) == pixel_bytes(b, csp, w, h)).all(), (w, h, hex(csp), spc, full)
+    for w, h in ((24, 18), (90, 50)):                                    # High 4:4:4 pictures: RGB and the YV24 copy
+        for y, u, v in ((rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (h, w), dtype=np.uint8)),
+                        tuple(rng.choice(np.array([0, 255], np.uint8), (h, w)) for _ in range(3))):
+            for csp in (sr.CSP_BGRA, sr.CSP_BGR, sr.CSP_YV24, sr.CSP_BGR | sr.CSP_VFLIP):
+                for spc, full in ((2, 0), (1, 1), (9, 0), (7, 1)):
+                    a = sr.decompress_convert(y, u, v, csp, spc, full, src_chroma=3)
+                    b = ol.oracle_decode_convert(y, u, v, csp, spc, full, src_chroma=3)
+                    assert (pixel_bytes(a, csp, w, h) == pixel_bytes(b, csp, w, h)).all(), (w, h, hex(csp), spc, full)
+    assert ol.oracle_decode_convert(y, u, v, sr.CSP_YUYV, src_chroma=3) is None      # 4:4:4 -> 4:2:2 resamples chroma: not restated
+    y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((18, 24), (18, 12), (18, 12)))
     # planar outputs of another chroma height go through libswscale's yuv2planeX path: refused, not approximated
     assert ol.oracle_decode_convert(y, u, v, sr.CSP_I420, src_chroma=2) is None
     y0, u0, v0 = ol.decode_source(64, 32)
@@ -94,6 +104,6 @@ def test_geometry_and_refusals():
     assert ol.decode_picture_size(sr.CSP_NV12, 64, 32) == 64 * 32 * 3 // 2
     y, u, v = ol.decode_source(64, 32)
     assert ol.oracle_decode_convert(y, u, v, sr.CSP_YUYV | sr.CSP_VFLIP) is None   # only RGB can be flipped (codec.c:510-527)
-    assert ol.oracle_decode_convert(y, u, v, 4) is None                          # YV24: not covered
+    assert ol.oracle_decode_convert(y, u, v, 4) is None                          # YV24 from a 4:2:0 picture: another chroma resolution
     y, u, v = ol.decode_source(64, 8)
     assert ol.oracle_decode_convert(y, u, v, sr.CSP_BGRA) is None                # fewer than 5 chroma rows: not restated

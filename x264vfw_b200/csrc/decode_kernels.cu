@@ -39,6 +39,8 @@ struct DecConst {
     int yc, ykf, vr, ub, vg, ug, vr0, ub0, vg0, ug0;
     // C writers: component = clip8((idx * cy + bias) >> 16), idx = Y + ((C * cxx) >> 16) - (cxx >> 9) ...
     int cy, bias, crv, cbu, cgu, cgv, crv9, cbu9, cgu9, cgv9;
+    // 4:4:4 pictures (libswscale's full-chroma C writer): X = (y << 9) * fy + fy0 + ((u - 128) << 9) * fu.. + ..., >> 22
+    int fy, fy0, fvr, fvg, fug, fub;
 };
 
 struct DecJob {
@@ -235,13 +237,53 @@ __global__ void __launch_bounds__(256, DEC_BLOCKS_PER_SM(FMT)) dec_packed_kernel
         dec_row<FMT, VEC>(j, tb, uc, vc, yb, D + (ptrdiff_t)rb * j.dst_stride, npx);
 }
 
+// 4:4:4 decoder pictures -> RGB: libswscale turns full chroma interpolation on by itself and every row goes through its C writer
+// yuv2rgb_full_1_c / yuv2rgb_write_full: per pixel, 32-bit integer arithmetic that wraps, clip to 30 bits, >> 22.
+template <bool BGRA, bool VEC>
+__global__ void __launch_bounds__(256) dec_444_kernel(const __grid_constant__ DecJob j)
+{
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, r = blockIdx.y * 8 + threadIdx.y;
+    if (x0 >= j.w || r >= j.h) return;
+    const size_t fo = (size_t)blockIdx.z * j.src_frame_bytes;
+    const uint8_t *py = j.y + fo + (ptrdiff_t)r * j.ys + x0, *pu = j.u + fo + (ptrdiff_t)r * j.us + x0, *pv = j.v + fo + (ptrdiff_t)r * j.vs + x0;
+    const int npx = min(4, j.w - x0);
+    uint32_t yw = 0, uw = 0, vw = 0;
+    if (VEC) { yw = ldg_stream32(py); uw = ldg_stream32(pu); vw = ldg_stream32(pv); }
+    else
+        for (int q = 0; q < npx; q++) { yw |= (uint32_t)__ldg(py + q) << (8 * q); uw |= (uint32_t)__ldg(pu + q) << (8 * q); vw |= (uint32_t)__ldg(pv + q) << (8 * q); }
+    const DecConst &K = j.k;
+    uint32_t px[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int Y = (int)(((yw >> (8 * q)) & 0xff) << 9) * K.fy + K.fy0;
+        const int U = ((int)((uw >> (8 * q)) & 0xff) - 128) << 9, V = ((int)((vw >> (8 * q)) & 0xff) - 128) << 9;
+        // unsigned wrap-around like the C writer's (unsigned) products; a sum past 2^31 turns negative and clips to 0
+        const int R = (int)((unsigned)Y + (unsigned)V * (unsigned)K.fvr);
+        const int G = (int)((unsigned)Y + (unsigned)V * (unsigned)K.fvg + (unsigned)U * (unsigned)K.fug);
+        const int B = (int)((unsigned)Y + (unsigned)U * (unsigned)K.fub);
+        const int lim = (1 << 30) - 1;
+        px[q] = (uint32_t)(min(max(B, 0), lim) >> 22) | ((uint32_t)(min(max(G, 0), lim) >> 22) << 8) |
+                ((uint32_t)(min(max(R, 0), lim) >> 22) << 16) | 0xff000000u;
+    }
+    uint8_t *o = j.dst + (size_t)blockIdx.z * j.dst_frame_bytes + (ptrdiff_t)r * j.dst_stride + (size_t)x0 * (BGRA ? 4 : 3);
+    if (BGRA) {
+        if (VEC) *(uint4 *)o = make_uint4(px[0], px[1], px[2], px[3]);
+        else for (int q = 0; q < npx; q++) *(uint32_t *)(o + 4 * q) = px[q];
+    } else if (VEC) {
+        ((uint32_t *)o)[0] = __byte_perm(px[0], px[1], 0x4210);
+        ((uint32_t *)o)[1] = __byte_perm(px[1], px[2], 0x5421);
+        ((uint32_t *)o)[2] = __byte_perm(px[2], px[3], 0x6542);
+    } else
+        for (int q = 0; q < npx; q++) { o[3 * q] = px[q]; o[3 * q + 1] = px[q] >> 8; o[3 * q + 2] = px[q] >> 16; }
+}
+
 // I420 / YV12 / NV12 targets: plane copies (libswscale's planarCopyWrapper / planarToNv12Wrapper); YV12 arrives
 // here with the destination U/V pointers already swapped (codec.c:2263-2274).
 struct DecPlanarJob {
     const uint8_t *y, *u, *v;
     int ys, us, vs;
     uint8_t *dy, *du, *dv;      // dv == nullptr: NV12 (du rows hold U,V interleaved)
-    int w, h;                   // (chroma rows follow from the grid: rows h .. gridDim.y - 1)
+    int w, h, cw;               // cw: chroma plane width (w / 2, or w for 4:4:4); chroma rows follow from the grid: rows h .. gridDim.y - 1
     size_t src_frame_bytes, dst_frame_bytes;
 };
 
@@ -251,7 +293,7 @@ __global__ void __launch_bounds__(256) dec_planar_kernel(const DecPlanarJob j)
     const int xb = (blockIdx.x * 256 + threadIdx.x) * 16;
     const int row = blockIdx.y;
     const size_t so = (size_t)blockIdx.z * j.src_frame_bytes, dof = (size_t)blockIdx.z * j.dst_frame_bytes;
-    const int cw = j.w >> 1;
+    const int cw = j.cw;
     if (row < j.h) {
         if (xb >= j.w) return;
         const uint8_t *s = j.y + so + (ptrdiff_t)row * j.ys + xb;
@@ -415,11 +457,15 @@ static void colour_constants(DecConst &k, int avcol_spc, int fullrange, int roun
     k.bias = (int)((fullrange ? 384 : 326) * cy - (384LL << 16) - oy + 0x8000);
     k.crv = (int)crv; k.cbu = (int)cbu; k.cgu = (int)cgu; k.cgv = (int)cgv;
     k.crv9 = (int)(crv >> 9); k.cbu9 = (int)(cbu >> 9); k.cgu9 = (int)(cgu >> 9); k.cgv9 = (int)(cgv >> 9);
+    // yuv2rgb_write_full: Y = ((y << 9) - y_offset) * y_coeff + (1 << 21), y_offset = to_int16(oy << 9); chroma terms (c - 128) << 9 times
+    // the same 13-bit coefficients
+    k.fy = y_coeff; k.fy0 = (1 << 21) - to_int16(oy << 9) * y_coeff;
+    k.fvr = k.vr; k.fvg = k.vg; k.fug = k.ug; k.fub = k.ub;
 }
 
 struct Dec {
     Ctx *ctx;
-    int csp, flip, w, h, v422;
+    int csp, flip, w, h, v422, v444;
     DecConst k;
     DecRow *d_rows = nullptr;
     // staging of the host-buffer entry
@@ -433,17 +479,18 @@ static inline bool als(long long v, long long a) { return (v & (a - 1)) == 0; }
 static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src[3], const int ss[3], size_t sfb, int n)
 {
     cudaStream_t st = d->ctx->stream;
-    const int w = d->w, h = d->h, cw = w / 2, ch = d->v422 ? h : h / 2;
+    const int w = d->w, h = d->h, cw = d->v444 ? w : w / 2, ch = d->v422 || d->v444 ? h : h / 2;
     if (n <= 0) return 0;
     if (n > 65535) { set_error("at most 65535 pictures per launch"); return -1; }
-    if (d->csp == X264VFW_CUDA_CSP_I420 || d->csp == X264VFW_CUDA_CSP_YV12 || d->csp == X264VFW_CUDA_CSP_NV12 || d->csp == X264VFW_CUDA_CSP_YV16) {
+    if (d->csp == X264VFW_CUDA_CSP_I420 || d->csp == X264VFW_CUDA_CSP_YV12 || d->csp == X264VFW_CUDA_CSP_NV12 || d->csp == X264VFW_CUDA_CSP_YV16 ||
+        d->csp == X264VFW_CUDA_CSP_YV24) {
         DecPlanarJob j;
         j.y = src[0]; j.u = src[1]; j.v = src[2]; j.ys = ss[0]; j.us = ss[1]; j.vs = ss[2];
-        j.w = w; j.h = h; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
+        j.w = w; j.h = h; j.cw = cw; j.src_frame_bytes = sfb; j.dst_frame_bytes = dfb;
         j.dy = dst;
         uint8_t *p1 = dst + (size_t)w * h, *p2 = p1 + (size_t)cw * ch;             // x264vfw_picture_fill, codec.c:425-439,469-480
         if (d->csp == X264VFW_CUDA_CSP_NV12) { j.du = p1; j.dv = nullptr; }
-        else if (d->csp == X264VFW_CUDA_CSP_YV12 || d->csp == X264VFW_CUDA_CSP_YV16) { j.du = p2; j.dv = p1; }   // codec.c:2263-2274
+        else if (d->csp != X264VFW_CUDA_CSP_I420) { j.du = p2; j.dv = p1; }             // YV12 / YV16 / YV24: codec.c:2263-2274
         else { j.du = p1; j.dv = p2; }
         const bool vec = als(w, 32) && al(dst, 16) && als((long long)dfb, 16) && als((long long)sfb, 16) &&
                          al(src[0], 16) && al(src[1], 16) && al(src[2], 16) && als(ss[0], 16) && als(ss[1], 16) && als(ss[2], 16) &&
@@ -461,6 +508,18 @@ static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src
     long long stride = d->csp == X264VFW_CUDA_CSP_BGR ? ((w * 3 + 3) & ~3) : d->csp == X264VFW_CUDA_CSP_BGRA ? w * 4 : w * 2;
     j.dst = dst; j.dst_stride = stride;
     if (d->flip) { j.dst = dst + stride * (h - 1); j.dst_stride = -stride; }       // codec.c:515-518
+    if (d->v444) {
+        const bool bgra = d->csp == X264VFW_CUDA_CSP_BGRA;
+        const size_t a = bgra ? 16 : 4;
+        const bool v4 = als(w, 4) && al(dst, a) && als(stride, a) && als((long long)dfb, a) && als((long long)sfb, 4) &&
+                        al(src[0], 4) && al(src[1], 4) && al(src[2], 4) && als(ss[0], 4) && als(ss[1], 4) && als(ss[2], 4);
+        if (!al(dst, 4) || !als((long long)dfb, 4)) { set_error("output picture must be 4-byte aligned"); return -1; }
+        dim3 blk(32, 8), grd((w + 127) / 128, (h + 7) / 8, n);
+        if (bgra) { if (v4) dec_444_kernel<true, true><<<grd, blk, 0, st>>>(j); else dec_444_kernel<true, false><<<grd, blk, 0, st>>>(j); }
+        else      { if (v4) dec_444_kernel<false, true><<<grd, blk, 0, st>>>(j); else dec_444_kernel<false, false><<<grd, blk, 0, st>>>(j); }
+        XV_LAUNCH_CHECK();
+        return 0;
+    }
     const size_t da = d->csp == X264VFW_CUDA_CSP_BGR ? 4 : 16;
     const bool vec = als(w, 8) && al(dst, da) && als(stride, da) && als((long long)dfb, da) && als((long long)sfb, 8) &&
                      al(src[0], 8) && als(ss[0], 8) && al(src[1], 4) && al(src[2], 4) && als(ss[1], 4) && als(ss[2], 4);
@@ -492,6 +551,7 @@ int64_t x264vfw_cuda_dec_picture_size(int i_out_csp, int w, int h)
     case X264VFW_CUDA_CSP_I420: case X264VFW_CUDA_CSP_YV12: case X264VFW_CUDA_CSP_NV12:
         return (int64_t)w * h + 2 * (int64_t)(w / 2) * (h / 2);
     case X264VFW_CUDA_CSP_YV16: case X264VFW_CUDA_CSP_YUYV: case X264VFW_CUDA_CSP_UYVY: return (int64_t)w * 2 * h;
+    case X264VFW_CUDA_CSP_YV24: return (int64_t)w * 3 * h;
     case X264VFW_CUDA_CSP_BGR:  return (int64_t)((w * 3 + 3) & ~3) * h;
     case X264VFW_CUDA_CSP_BGRA: return (int64_t)w * 4 * h;
     default: return -1;
@@ -505,19 +565,25 @@ int x264vfw_cuda_dec_open(x264vfw_cuda_dec **pdec, x264vfw_cuda_ctx *ctx, int i_
     *pdec = nullptr;
     const int csp = i_out_csp & X264VFW_CUDA_CSP_MASK, flip = (i_out_csp & X264VFW_CUDA_CSP_VFLIP) != 0;
     if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) { set_error("width/height must be positive and even (codec.c:1950-1954)"); return -1; }
-    if (i_src_chroma != 1 && i_src_chroma != 2) { set_error("decoder pictures must be 4:2:0 (1) or 4:2:2 (2); 4:4:4 is not covered"); return -1; }
+    if (i_src_chroma < 1 || i_src_chroma > 3) { set_error("decoder pictures must be 4:2:0 (1), 4:2:2 (2) or 4:4:4 (3)"); return -1; }
     if (x264vfw_cuda_dec_picture_size(csp, w, h) < 0) { set_error("output csp %d is not covered", csp); return -1; }
-    const bool v422 = i_src_chroma == 2;
+    const bool v422 = i_src_chroma == 2, v444 = i_src_chroma == 3;
     const bool out420 = csp == X264VFW_CUDA_CSP_I420 || csp == X264VFW_CUDA_CSP_YV12 || csp == X264VFW_CUDA_CSP_NV12;
-    // a change of the vertical chroma resolution between planar formats is libswscale's yuv2planeX path: not covered
-    if ((v422 && out420) || (!v422 && csp == X264VFW_CUDA_CSP_YV16)) { set_error("planar output with another chroma height than the decoder picture is not covered"); return -1; }
+    // a change of chroma resolution between YUV formats is libswscale's resampling path (yuv2planeX / hscale + dither): not covered
+    const int out_chroma = out420 ? 1 : csp == X264VFW_CUDA_CSP_YV16 || csp == X264VFW_CUDA_CSP_YUYV || csp == X264VFW_CUDA_CSP_UYVY ? 2 :
+                           csp == X264VFW_CUDA_CSP_YV24 ? 3 : 0;
+    const bool planar_out = out420 || csp == X264VFW_CUDA_CSP_YV16 || csp == X264VFW_CUDA_CSP_YV24;
+    if ((planar_out && out_chroma != i_src_chroma) || (v444 && out_chroma == 2)) {
+        set_error("YUV output with another chroma resolution than the decoder picture is not covered");
+        return -1;
+    }
     const bool rgb = csp == X264VFW_CUDA_CSP_BGR || csp == X264VFW_CUDA_CSP_BGRA;
     if (flip && !rgb) { set_error("only RGB output can be bottom-up (codec.c:510-527)"); return -1; }
-    const bool planar = out420 || csp == X264VFW_CUDA_CSP_YV16;
+    const bool planar = planar_out || v444;               // no row table: plane copies, and the per-pixel 4:4:4 writer
     Ctx *c = (Ctx *)ctx;
     XV_CUDA_OK(cudaSetDevice(c->device));
     Dec *d = new Dec;
-    d->ctx = c; d->csp = csp; d->flip = flip; d->w = w; d->h = h; d->v422 = v422;
+    d->ctx = c; d->csp = csp; d->flip = flip; d->w = w; d->h = h; d->v422 = v422; d->v444 = v444;
     colour_constants(d->k, i_avcol_spc, b_fullrange != 0, v422 ? 0 : 4);
     if (!planar) {
         std::vector<DecRow> rows;
@@ -575,10 +641,10 @@ int x264vfw_cuda_dec_convert(x264vfw_cuda_dec *dec, uint8_t *dst_host, const uin
 {
     Dec *d = (Dec *)dec;
     if (!d || !dst_host || !src_host || !src_stride || !src_host[0] || !src_host[1] || !src_host[2]) { set_error("null argument"); return -1; }
-    for (int i = 0; i < 3; i++) if (src_stride[i] < (i ? d->w / 2 : d->w)) { set_error("source stride below the row width"); return -1; }
+    for (int i = 0; i < 3; i++) if (src_stride[i] < (i && !d->v444 ? d->w / 2 : d->w)) { set_error("source stride below the row width"); return -1; }
     XV_CUDA_OK(cudaSetDevice(d->ctx->device));
     cudaStream_t st = d->ctx->stream;
-    const int w = d->w, h = d->h, cw = w / 2, ch = d->v422 ? h : h / 2;
+    const int w = d->w, h = d->h, cw = d->v444 ? w : w / 2, ch = d->v422 || d->v444 ? h : h / 2;
     // device staging: tight planes with 16-byte aligned rows; the picture is gathered by 2-D copies so that the
     // decoder's linesize padding never crosses the bus
     const int ys = (w + 15) & ~15, cs = (cw + 15) & ~15;

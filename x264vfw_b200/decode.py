@@ -63,7 +63,7 @@ class Decompressor:
 
     def __init__(self, i_csp: int, width: int, height: int, colorspace: int = AVCOL_SPC_UNSPECIFIED,
                  fullrange: bool = False, ctx: Context = None, src_chroma: int = 1):
-        """src_chroma: 1 = the decoder delivers yuv420p, 2 = yuv422p (High 4:2:2 streams)."""
+        """src_chroma: 1 = the decoder delivers yuv420p, 2 = yuv422p (High 4:2:2 streams), 3 = yuv444p (High 4:4:4 Predictive)."""
         self.ctx = ctx or Context()
         self.i_csp, self.width, self.height, self.src_chroma = i_csp, width, height, src_chroma
         self.picture_size = picture_get_size(i_csp, width, height)
@@ -75,8 +75,9 @@ class Decompressor:
     def decompress(self, y: np.ndarray, u: np.ndarray, v: np.ndarray, out: np.ndarray = None) -> np.ndarray:
         """The sws_scale call of codec.c:2292 on one decoded yuv420p picture held in HOST memory (2-D uint8 arrays,
         any row stride, like AVFrame data[]/linesize[]).  Returns the output DIB bytes."""
-        ch = self.height if self.src_chroma == 2 else self.height // 2
-        if y.shape != (self.height, self.width) or u.shape != (ch, self.width // 2) or v.shape != u.shape:
+        ch = self.height if self.src_chroma >= 2 else self.height // 2
+        cw = self.width if self.src_chroma == 3 else self.width // 2
+        if y.shape != (self.height, self.width) or u.shape != (ch, cw) or v.shape != u.shape:
             raise ValueError("plane shapes do not match the context")
         for p in (y, u, v):
             if p.dtype != np.uint8 or p.strides[1] != 1:
