@@ -16,15 +16,26 @@ st = torch.cuda.ExternalStream(ctx.stream)
 sfb = W * H * 3 // 2
 src = torch.randint(0, 256, (nf * sfb,), dtype=torch.uint8, device="cuda")
 b0 = src.data_ptr()
-FORMATS = {"bgra_bottom_up": 9 | 0x1000, "bgra": 9, "bgr24_bottom_up": 8 | 0x1000, "yuyv": 6, "uyvy": 7, "nv12": 5, "yv12": 2}
+FORMATS = {"bgra_bottom_up": (9 | 0x1000, 1), "bgra": (9, 1), "bgr24_bottom_up": (8 | 0x1000, 1), "yuyv": (6, 1), "uyvy": (7, 1), "nv12": (5, 1),
+           "yv12": (2, 1), "422_to_bgra_bottom_up": (9 | 0x1000, 2), "422_to_yuyv": (6, 2), "444_to_bgra_bottom_up": (9 | 0x1000, 3),
+           "444_to_bgr24_bottom_up": (8 | 0x1000, 3)}
 res = {}
-for name, csp in FORMATS.items():
+src444 = torch.randint(0, 256, (nf * W * H * 3,), dtype=torch.uint8, device="cuda")
+for name, (csp, chroma) in FORMATS.items():
     if only and name not in only:
         continue
-    d = decode.Decompressor(csp, W, H, decode.AVCOL_SPC_BT709, False, ctx=ctx)
+    d = decode.Decompressor(csp, W, H, decode.AVCOL_SPC_BT709, False, ctx=ctx, src_chroma=chroma)
     dfb = (d.picture_size + 255) & ~255
     dst = torch.empty(nf * dfb, dtype=torch.uint8, device="cuda")
-    run = lambda: d.decompress_batch(dst.data_ptr(), dfb, (b0, b0 + W * H, b0 + W * H * 5 // 4), (W, W // 2, W // 2), sfb, nf)
+    if chroma == 1:
+        fb, planes, strides = sfb, (b0, b0 + W * H, b0 + W * H * 5 // 4), (W, W // 2, W // 2)
+    elif chroma == 2:
+        b4 = src444.data_ptr()
+        fb, planes, strides = W * H * 2, (b4, b4 + W * H, b4 + W * H * 3 // 2), (W, W // 2, W // 2)
+    else:
+        b4 = src444.data_ptr()
+        fb, planes, strides = W * H * 3, (b4, b4 + W * H, b4 + 2 * W * H), (W, W, W)
+    run = lambda: d.decompress_batch(dst.data_ptr(), dfb, planes, strides, fb, nf)
     for _ in range(3):
         run()
     ctx.sync()
@@ -35,7 +46,7 @@ for name, csp in FORMATS.items():
     b.record(st)
     b.synchronize()
     t = a.elapsed_time(b) / iters * 1e-3
-    algo = sfb + d.picture_size
+    algo = fb + d.picture_size
     res[name] = {"us_per_frame": t * 1e6 / nf, "algorithmic_bytes_per_frame": algo, "gbs": algo * nf / t / 1e9}
     if name == "bgra_bottom_up" and not only:
         # host entry: pageable numpy planes in, DIB out, synchronous (what one ICM_DECOMPRESS call costs)
