@@ -242,21 +242,27 @@ __global__ void __launch_bounds__(256, DEC_BLOCKS_PER_SM(FMT)) dec_packed_kernel
 template <bool BGRA, bool VEC>
 __global__ void __launch_bounds__(256) dec_444_kernel(const __grid_constant__ DecJob j)
 {
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, r = blockIdx.y * 8 + threadIdx.y;
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8, r = blockIdx.y * 8 + threadIdx.y;       // thread = 8 pixels of a row
     if (x0 >= j.w || r >= j.h) return;
     const size_t fo = (size_t)blockIdx.z * j.src_frame_bytes;
     const uint8_t *py = j.y + fo + (ptrdiff_t)r * j.ys + x0, *pu = j.u + fo + (ptrdiff_t)r * j.us + x0, *pv = j.v + fo + (ptrdiff_t)r * j.vs + x0;
-    const int npx = min(4, j.w - x0);
-    uint32_t yw = 0, uw = 0, vw = 0;
-    if (VEC) { yw = ldg_stream32(py); uw = ldg_stream32(pu); vw = ldg_stream32(pv); }
-    else
-        for (int q = 0; q < npx; q++) { yw |= (uint32_t)__ldg(py + q) << (8 * q); uw |= (uint32_t)__ldg(pu + q) << (8 * q); vw |= (uint32_t)__ldg(pv + q) << (8 * q); }
+    const int npx = min(8, j.w - x0);
+    uint32_t yw[2] = {0, 0}, uw[2] = {0, 0}, vw[2] = {0, 0};
+    if (VEC) {
+        const uint2 a = ldg_stream64(py), b = ldg_stream64(pu), c = ldg_stream64(pv);
+        yw[0] = a.x; yw[1] = a.y; uw[0] = b.x; uw[1] = b.y; vw[0] = c.x; vw[1] = c.y;
+    } else
+        for (int q = 0; q < npx; q++) {
+            yw[q >> 2] |= (uint32_t)__ldg(py + q) << (8 * (q & 3)); uw[q >> 2] |= (uint32_t)__ldg(pu + q) << (8 * (q & 3));
+            vw[q >> 2] |= (uint32_t)__ldg(pv + q) << (8 * (q & 3));
+        }
     const DecConst &K = j.k;
-    uint32_t px[4];
+    uint32_t px[8];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int Y = (int)(((yw >> (8 * q)) & 0xff) << 9) * K.fy + K.fy0;
-        const int U = ((int)((uw >> (8 * q)) & 0xff) - 128) << 9, V = ((int)((vw >> (8 * q)) & 0xff) - 128) << 9;
+    for (int q = 0; q < 8; q++) {
+        const int sh = 8 * (q & 3);
+        const int Y = (int)(((yw[q >> 2] >> sh) & 0xff) << 9) * K.fy + K.fy0;
+        const int U = ((int)((uw[q >> 2] >> sh) & 0xff) - 128) << 9, V = ((int)((vw[q >> 2] >> sh) & 0xff) - 128) << 9;
         // unsigned wrap-around like the C writer's (unsigned) products; a sum past 2^31 turns negative and clips to 0
         const int R = (int)((unsigned)Y + (unsigned)V * (unsigned)K.fvr);
         const int G = (int)((unsigned)Y + (unsigned)V * (unsigned)K.fvg + (unsigned)U * (unsigned)K.fug);
@@ -267,12 +273,15 @@ __global__ void __launch_bounds__(256) dec_444_kernel(const __grid_constant__ De
     }
     uint8_t *o = j.dst + (size_t)blockIdx.z * j.dst_frame_bytes + (ptrdiff_t)r * j.dst_stride + (size_t)x0 * (BGRA ? 4 : 3);
     if (BGRA) {
-        if (VEC) *(uint4 *)o = make_uint4(px[0], px[1], px[2], px[3]);
+        if (VEC) { ((uint4 *)o)[0] = make_uint4(px[0], px[1], px[2], px[3]); ((uint4 *)o)[1] = make_uint4(px[4], px[5], px[6], px[7]); }
         else for (int q = 0; q < npx; q++) *(uint32_t *)(o + 4 * q) = px[q];
     } else if (VEC) {
-        ((uint32_t *)o)[0] = __byte_perm(px[0], px[1], 0x4210);
-        ((uint32_t *)o)[1] = __byte_perm(px[1], px[2], 0x5421);
-        ((uint32_t *)o)[2] = __byte_perm(px[2], px[3], 0x6542);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            ((uint32_t *)o)[3 * q]     = __byte_perm(px[4 * q], px[4 * q + 1], 0x4210);
+            ((uint32_t *)o)[3 * q + 1] = __byte_perm(px[4 * q + 1], px[4 * q + 2], 0x5421);
+            ((uint32_t *)o)[3 * q + 2] = __byte_perm(px[4 * q + 2], px[4 * q + 3], 0x6542);
+        }
     } else
         for (int q = 0; q < npx; q++) { o[3 * q] = px[q]; o[3 * q + 1] = px[q] >> 8; o[3 * q + 2] = px[q] >> 16; }
 }
@@ -511,10 +520,10 @@ static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src
     if (d->v444) {
         const bool bgra = d->csp == X264VFW_CUDA_CSP_BGRA;
         const size_t a = bgra ? 16 : 4;
-        const bool v4 = als(w, 4) && al(dst, a) && als(stride, a) && als((long long)dfb, a) && als((long long)sfb, 4) &&
-                        al(src[0], 4) && al(src[1], 4) && al(src[2], 4) && als(ss[0], 4) && als(ss[1], 4) && als(ss[2], 4);
+        const bool v4 = als(w, 8) && al(dst, a) && als(stride, a) && als((long long)dfb, a) && als((long long)sfb, 8) &&
+                        al(src[0], 8) && al(src[1], 8) && al(src[2], 8) && als(ss[0], 8) && als(ss[1], 8) && als(ss[2], 8);
         if (!al(dst, 4) || !als((long long)dfb, 4)) { set_error("output picture must be 4-byte aligned"); return -1; }
-        dim3 blk(32, 8), grd((w + 127) / 128, (h + 7) / 8, n);
+        dim3 blk(32, 8), grd((w + 255) / 256, (h + 7) / 8, n);
         if (bgra) { if (v4) dec_444_kernel<true, true><<<grd, blk, 0, st>>>(j); else dec_444_kernel<true, false><<<grd, blk, 0, st>>>(j); }
         else      { if (v4) dec_444_kernel<false, true><<<grd, blk, 0, st>>>(j); else dec_444_kernel<false, false><<<grd, blk, 0, st>>>(j); }
         XV_LAUNCH_CHECK();
