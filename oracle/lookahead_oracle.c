@@ -1783,6 +1783,21 @@ int orc_la_weights_full(orc_la *la, int f_enc, int f_ref, const uint8_t *fenc_uv
     return 0;
 }
 
+/* test hook: a whole chroma picture compensated by mc_chroma with one vector (luma quarter-sample units, what mc_chroma
+ * takes), 8x8 block by 8x8 block -- pinned against the H.264 decoder's chroma prediction in tests/test_h264_pins.py */
+void orc_test_mc_chroma_picture(uint8_t *out_u, uint8_t *out_v, const uint8_t *uv, int stride, int cw, int ch, int mvx, int mvy)
+{
+    for (int by = 0; by < ch; by += 8)
+        for (int bx = 0; bx < cw; bx += 8)
+            for (int c = 0; c < 2; c++) {
+                uint8_t blk[64];
+                mc_chroma_8x8(blk, uv, stride, cw, ch, bx, by, mvx, mvy, c);
+                uint8_t *o = c ? out_v : out_u;
+                for (int y = 0; y < 8 && by + y < ch; y++)
+                    for (int x = 0; x < 8 && bx + x < cw; x++) o[(by + y) * cw + bx + x] = blk[y * 8 + x];
+            }
+}
+
 /* test hook: one score of the analysis above */
 unsigned orc_test_weights_full_cost(orc_la *la, int f_enc, int f_ref, const uint8_t *fenc_uv, const uint8_t *ref_uv, int uv_stride,
                                     int plane, int weighted, int scale, int denom, int offset)

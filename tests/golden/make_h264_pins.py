@@ -14,7 +14,8 @@ import h264_pins as hp  # noqa: E402
 def main():
     out = {"source": "libavcodec h264 decoder (opencv_python_headless wheel, avcodec 62.11), bitstreams from h264_mini.py",
            "mc": {"w": hp.MC_W, "h": hp.MC_H, "mvs": [list(m) for m in hp.MC_MVS],
-                  "pictures": {k: hp.decoder_mc_hashes(k) for k in hp.MC_KINDS}},
+                  "pictures": {k: hp.decoder_mc_hashes(k) for k in hp.MC_KINDS},
+                  "chroma": {k: hp.decoder_mc_chroma_hashes(k) for k in hp.MC_KINDS}},
            "hd": {"w": hp.HD_W, "h": hp.HD_H, "mvs": [list(m) for m in hp.HD_MVS], "pictures": hp.decoder_hd_hashes()},
            "wp": {"cases": [[list(m), list(w)] for m, w in hp.WP_CASES], "pictures": hp.decoder_wp_hashes()},
            "bi": {"cases": [[c[0], c[1], list(c[2]), list(c[3]), c[4]] for c in hp.BI_CASES], "pictures": hp.decoder_bi_hashes()},

@@ -162,6 +162,29 @@ def checker_mc_hashes(kind, planes=None):
     return [fnv(predict_from_planes(planes, MC_W, MC_H, g["stride"], mx, my)) for mx, my in MC_MVS]
 
 
+def checker_mc_chroma_hashes(kind):
+    """[x264] mc_chroma (the checker's, used by the encoder-side weight analysis) on the picture's chroma planes, one hash per
+    vector over U then V: H.264 8.4.2.2.2, the chroma vector is the luma vector in eighth samples."""
+    _, u, v = mc_picture(kind)
+    ch, cw = u.shape
+    uv = np.empty((ch, 2 * cw), np.uint8)
+    uv[:, 0::2], uv[:, 1::2] = u, v
+    o = ol.oracle()
+    o.orc_test_mc_chroma_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5
+    out = []
+    for mx, my in MC_MVS:
+        pu, pv = np.zeros((ch, cw), np.uint8), np.zeros((ch, cw), np.uint8)
+        o.orc_test_mc_chroma_picture(pu.ctypes.data, pv.ctypes.data, uv.ctypes.data, 2 * cw, cw, ch, mx, my)
+        out.append(fnv(np.concatenate([pu.ravel(), pv.ravel()])))
+    return out
+
+
+def decoder_mc_chroma_hashes(kind):
+    import avdec
+    pics = avdec.decode_h264(mc_stream(kind))
+    return [fnv(np.concatenate([p[1].ravel(), p[2].ravel()])) for p in pics[1:]]
+
+
 def checker_wp_hashes():
     y, _, _ = mc_picture("noise")
     g = ol.hpel_geometry(MC_W, MC_H)

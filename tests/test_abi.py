@@ -98,3 +98,21 @@ def test_product_does_not_reference_the_oracle():
                     if re.search(r"oracle", open(os.path.join(dp, fn), errors="ignore").read()):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_decompress_query_and_picture_sizes_without_a_device():
+    """codec.c:1930-1980 and x264vfw_picture_get_size (codec.c:505-508) through the Python mirror: pure host logic of the library."""
+    from x264vfw_b200 import decode
+    from x264vfw_b200.csp import fourcc
+    assert decode.picture_get_size(8, 70, 38) == 212 * 38                    # BGR24 rows padded to 4 bytes (codec.c:489-492)
+    assert decode.picture_get_size(9, 64, 32) == 64 * 32 * 4
+    assert decode.picture_get_size(5, 64, 32) == decode.picture_get_size(1, 64, 32) == 64 * 32 * 3 // 2
+    assert decode.picture_get_size(6, 64, 32) == decode.picture_get_size(3, 64, 32) == 64 * 32 * 2
+    assert decode.picture_get_size(4, 64, 32) == 64 * 32 * 3 and decode.picture_get_size(0, 64, 32) == -1
+    ok, bad = decode.ICERR_OK, decode.ICERR_BADFORMAT
+    assert decode.decompress_query(64, 32, 0, 32, 64, 32) == ok and decode.decompress_query(64, 32, 0, 24, 64, -32) == ok
+    assert decode.decompress_query(64, 32, fourcc("YV12"), 12, 64, 32) == ok and decode.decompress_query(64, 32, fourcc("UYVY"), 16, 64, 32) == ok
+    assert decode.decompress_query(64, 32, 0, 32, 32, 32) == bad            # output size must equal the stream's
+    assert decode.decompress_query(64, 32, 0, 16, 64, 32) == bad            # no csp for 16-bit RGB
+    assert decode.decompress_query(64, 33, 0, 32, 64, 33) == bad            # odd height
+    assert decode.decompress_query(64, 32, 0, 32, 64, 32, out_size_image=64 * 32 * 4 - 1) == bad

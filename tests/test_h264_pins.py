@@ -31,6 +31,16 @@ def test_checker_hpel_planes_and_get_ref_equal_the_decoders_motion_compensation(
     assert not bad, bad
 
 
+@pytest.mark.parametrize("kind", hp.MC_KINDS)
+def test_checker_mc_chroma_equals_the_decoders_chroma_prediction(kind):
+    """[x264] mc_chroma as restated for the encoder-side weight analysis: both chroma planes of the same 22
+    pictures -- every eighth-sample phase the 16 quarter-sample luma vectors produce, and vectors far outside the picture."""
+    got = hp.checker_mc_chroma_hashes(kind)
+    want = GOLD["mc"]["chroma"][kind]
+    bad = [hp.MC_MVS[i] for i in range(len(want)) if got[i] != want[i]]
+    assert not bad, bad
+
+
 def test_checker_equals_the_decoder_at_1080p():
     """1920x1088 (BASELINE's frame padded to whole macroblocks), six vectors."""
     assert (GOLD["hd"]["w"], GOLD["hd"]["h"], [tuple(m) for m in GOLD["hd"]["mvs"]]) == (hp.HD_W, hp.HD_H, hp.HD_MVS)
