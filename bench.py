@@ -283,6 +283,17 @@ def stage1_roofline(torch, args):
     rec = torch.randint(0, 256, (hn * W * 1088,), dtype=torch.uint8, device="cuda")
     hp = torch.empty(hn * 4 * hg.plane_bytes, dtype=torch.uint8, device="cuda")
     leg("hpel_filter", HPEL_ALGO_BYTES, hn, lambda: hpel.hpel_filter(ctx, hp.data_ptr(), rec.data_ptr(), W, W, 1088, W * 1088, 4 * hg.plane_bytes, hn))
+    # integral image behind the half-pel planes (me esa / tesa): 8x8 box sums of the padded plane 0 just produced
+    try:
+        from x264vfw_b200 import b3
+        prow = hg.plane_bytes // hg.stride
+        s8 = torch.empty(hn * prow * hg.stride, dtype=torch.int16, device="cuda")
+        leg("integral_init8", prow * hg.stride * 3, hn,
+            lambda: b3.integral_init(ctx, s8.data_ptr(), 0, hp.data_ptr(), hg.stride, prow, 4 * hg.plane_bytes, prow * hg.stride, hn))
+        ctx.sync()
+        del s8
+    except Exception as e:
+        out["integral_init8"] = {"error": f"{type(e).__name__}: {e}"}
     # decoder-side output conversion: decoded yuv420p pictures -> bottom-up RGB32 DIBs, the default VfW
     # decompress target; algorithmic bytes = 1.5 read + 4 written per pixel.  `dst` doubles as the yuv420p source.
     try:
