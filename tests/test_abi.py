@@ -116,3 +116,19 @@ def test_decompress_query_and_picture_sizes_without_a_device():
     assert decode.decompress_query(64, 32, 0, 16, 64, 32) == bad            # no csp for 16-bit RGB
     assert decode.decompress_query(64, 33, 0, 32, 64, 33) == bad            # odd height
     assert decode.decompress_query(64, 32, 0, 32, 64, 32, out_size_image=64 * 32 * 4 - 1) == bad
+
+
+def test_new_entry_points_reject_null_arguments_without_a_device():
+    """Argument checks of the round-2 entry points happen before any CUDA call: -1 and a message, no crash, no device needed."""
+    import ctypes as C
+    from x264vfw_b200 import lib, last_error
+    from x264vfw_b200 import decode, b3  # noqa: F401  (registers the signatures)
+    h = C.c_void_p()
+    assert lib.x264vfw_cuda_dec_open(C.byref(h), None, 9, 64, 32, 1, 2, 0) == -1 and "null" in last_error()
+    assert lib.x264vfw_cuda_dec_convert(None, None, None, None) == -1
+    assert lib.x264vfw_cuda_dec_convert_batch(None, None, 0, None, None, 0, 1) == -1
+    lib.x264vfw_cuda_dec_close(None)                                        # like sws_freeContext(NULL)
+    out = (C.c_int32 * 4 * 3)()
+    assert lib.x264vfw_cuda_weights_analyse(None, None, C.byref(out), None) == -1
+    assert lib.x264vfw_cuda_la_weights_analyse(None, 1, 0, None, None, 0, C.byref(out), None) == -1
+    assert lib.x264vfw_cuda_integral_init(None, None, None, None, 64, 64, 0, 0, 1) == -1
