@@ -18,7 +18,8 @@ def open_pair(w, h, **over):
 
 @pytest.mark.parametrize("size,subme,kw", [((320, 192), 7, dict(step=28, chroma_step=24)), ((320, 192), 11, dict(step=33, offset=3)),
                                            ((330, 186), 2, dict(step=20, chroma_step=30)), ((320, 192), 9, dict(step=-20, chroma_step=-25)),
-                                           ((1280, 720), 7, dict(step=30, chroma_step=20)), ((320, 192), 7, dict(step=0))])
+                                           ((1280, 720), 7, dict(step=30, chroma_step=20)), ((320, 192), 7, dict(step=0)),
+                                           ((320, 192), 1, dict(step=30, chroma_step=20)), ((320, 192), 0, dict(step=25))])
 def test_weights_analyse_matches_checker(size, subme, kw):
     """Every (P frame, reference) pair of a fading clip, with the lookahead's vectors present (after slicetype_frame_cost) and absent:
     the three weights and the X264_WEIGHTP_FAKE ratio are identical."""
