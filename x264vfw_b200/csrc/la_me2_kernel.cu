@@ -730,7 +730,9 @@ int launch_me_pass(cudaStream_t st, const LaGeom &g, const MeParams &p, int pass
 // trip of ~1500 on the chain), only the top row of a band publishes to global memory for the
 // band above.  Bands are handed out bottom-first by an atomic ticket, so a block only ever
 // waits on bands that already started (no co-residency assumption between blocks).
+#ifndef VERIFY_ROWS
 #define VERIFY_ROWS 16
+#endif
 __device__ __forceinline__ uint2 lds_rec(const int2 *p)
 {
     uint2 v;
