@@ -39,13 +39,21 @@ __device__ __forceinline__ uint32_t filt(uint32_t a, uint32_t b, uint32_t c, uin
     return (((a + b + 1) >> 1) + ((c + d + 1) >> 1) + 1) >> 1;
 }
 
-// One padded lowres row of 8 pixels from three source rows (generic path: borders, odd geometry).
-__device__ __forceinline__ void lowres_row_generic(const LowresJob &job, const uint8_t *Y, int prow, int lx, uint8_t *d)
+__global__ void __launch_bounds__(128)
+lowres_init_kernel(LowresJob job)
 {
+    const int pchunk = blockIdx.x * blockDim.x + threadIdx.x;       // 8-px chunk of the padded row
+    const int prow = blockIdx.y * blockDim.y + threadIdx.y;          // padded row
+    if (pchunk >= ((job.lw + 2 * LOWRES_PAD) >> 3) || prow >= job.lh + 2 * LOWRES_PAD) return;
+    const size_t f = blockIdx.z;
+    const uint8_t *Y = job.y + f * job.src_frame_bytes;
     const int ys = job.y_stride, w = job.w, h = job.h;
+
     const int ly = min(max(prow - LOWRES_PAD, 0), job.lh - 1);   // clamped lowres row
+    const int lx = (pchunk << 3) - LOWRES_PAD;                    // first lowres x of this chunk
     const int r0 = min(2 * ly, h - 1), r1 = min(2 * ly + 1, h - 1), r2 = min(2 * ly + 2, h - 1);
     const uint8_t *s0 = Y + (size_t)r0 * ys, *s1 = Y + (size_t)r1 * ys, *s2 = Y + (size_t)r2 * ys;
+
     uint2 o0, oh, ov, oc;
     const int sx = 2 * lx;
     if (lx >= 0 && lx + 8 <= job.lw && sx + 16 <= w && ((ys | (int)(uintptr_t)Y) & 15) == 0) {
@@ -79,53 +87,11 @@ __device__ __forceinline__ void lowres_row_generic(const LowresJob &job, const u
         o0 = make_uint2(r[0][0], r[0][1]); oh = make_uint2(r[1][0], r[1][1]);
         ov = make_uint2(r[2][0], r[2][1]); oc = make_uint2(r[3][0], r[3][1]);
     }
+    uint8_t *d = job.dst + f * job.dst_frame_bytes + (size_t)prow * job.lstride + (pchunk << 3);
     *(uint2 *)(d) = o0;
     *(uint2 *)(d + (size_t)job.lplane_bytes) = oh;
     *(uint2 *)(d + 2 * (size_t)job.lplane_bytes) = ov;
     *(uint2 *)(d + 3 * (size_t)job.lplane_bytes) = oc;
-}
-
-// Thread = 8 lowres pixels x TWO padded rows (2k, 2k+1): in the interior they need source rows 4j .. 4j+4, five instead of
-// twice three, and all five are requested before the first store.
-__global__ void __launch_bounds__(128)
-lowres_init_kernel(LowresJob job)
-{
-    const int pchunk = blockIdx.x * blockDim.x + threadIdx.x;       // 8-px chunk of the padded row
-    const int prow = 2 * (blockIdx.y * blockDim.y + threadIdx.y);   // first of the two padded rows
-    const int prows = job.lh + 2 * LOWRES_PAD;
-    if (pchunk >= ((job.lw + 2 * LOWRES_PAD) >> 3) || prow >= prows) return;
-    const size_t f = blockIdx.z;
-    const uint8_t *Y = job.y + f * job.src_frame_bytes;
-    const int ys = job.y_stride, w = job.w, h = job.h;
-    const int lx = (pchunk << 3) - LOWRES_PAD;                    // first lowres x of this chunk
-    uint8_t *d = job.dst + f * job.dst_frame_bytes + (size_t)prow * job.lstride + (pchunk << 3);
-    const int ly = prow - LOWRES_PAD, sx = 2 * lx;
-    // fast path: both rows inside the picture (no vertical clamping), chunk inside the row, aligned plane
-    if (ly >= 0 && ly + 1 < job.lh && 2 * ly + 4 <= h - 1 && prow + 1 < prows &&
-        lx >= 0 && lx + 8 <= job.lw && sx + 16 <= w && ((ys | (int)(uintptr_t)Y) & 15) == 0) {
-        const uint8_t *s = Y + (size_t)(2 * ly) * ys + sx;
-        const int tx = min(sx + 16, w - 1) - sx;
-        uint4 r[5]; uint32_t t[5];
-#pragma unroll
-        for (int i = 0; i < 5; i++) { r[i] = *(const uint4 *)(s + (size_t)i * ys); t[i] = s[(size_t)i * ys + tx]; }
-        uint2 o0, oh, ov, oc;
-        hphase(avg16(r[0], r[1]), (t[0] + t[1] + 1) >> 1, o0, oh);
-        hphase(avg16(r[1], r[2]), (t[1] + t[2] + 1) >> 1, ov, oc);
-        *(uint2 *)(d) = o0;
-        *(uint2 *)(d + (size_t)job.lplane_bytes) = oh;
-        *(uint2 *)(d + 2 * (size_t)job.lplane_bytes) = ov;
-        *(uint2 *)(d + 3 * (size_t)job.lplane_bytes) = oc;
-        hphase(avg16(r[2], r[3]), (t[2] + t[3] + 1) >> 1, o0, oh);
-        hphase(avg16(r[3], r[4]), (t[3] + t[4] + 1) >> 1, ov, oc);
-        d += job.lstride;
-        *(uint2 *)(d) = o0;
-        *(uint2 *)(d + (size_t)job.lplane_bytes) = oh;
-        *(uint2 *)(d + 2 * (size_t)job.lplane_bytes) = ov;
-        *(uint2 *)(d + 3 * (size_t)job.lplane_bytes) = oc;
-        return;
-    }
-    lowres_row_generic(job, Y, prow, lx, d);
-    if (prow + 1 < prows) lowres_row_generic(job, Y, prow + 1, lx, d + job.lstride);
 }
 
 int launch_lowres_init(cudaStream_t st, const LowresJob &job, int n_frames)
@@ -134,8 +100,7 @@ int launch_lowres_init(cudaStream_t st, const LowresJob &job, int n_frames)
     if (chunks <= 0 || rows <= 0 || n_frames <= 0) return 0;
     // block = (chunks of one row rounded to a warp multiple, up to 128) x (rows to reach 128 threads)
     const int bx = ((chunks < 128 ? chunks : 128) + 31) & ~31, by = bx >= 128 ? 1 : 128 / bx;
-    const int row_pairs = (rows + 1) / 2;                   // a thread writes two padded rows
-    dim3 block(bx, by), grid((unsigned)((chunks + bx - 1) / bx), (unsigned)((row_pairs + by - 1) / by), (unsigned)n_frames);
+    dim3 block(bx, by), grid((unsigned)((chunks + bx - 1) / bx), (unsigned)((rows + by - 1) / by), (unsigned)n_frames);
     lowres_init_kernel<<<grid, block, 0, st>>>(job);
     XV_LAUNCH_CHECK();
     return 0;
