@@ -455,7 +455,7 @@ int x264vfw_cuda_integral_init( x264vfw_cuda_ctx *ctx, uint16_t *sum8_dev, uint1
  * 4:2:2 streams, what "keep input colorspace" makes of YUY2 / UYVY input), 3 for YUV444P / YUVJ444P (High 4:4:4 Predictive,
  * what it makes of YV24 input).  Destination: the output DIB
  * laid out by x264vfw_picture_fill (codec.c:419-503), i_out_csp = what get_csp() returns for the OUTPUT header
- * (codec.c:1994-1998): X264VFW_CUDA_CSP_{I420,YV12,NV12,YUYV,UYVY,BGR,BGRA} (YV16 from 4:2:2, YV24 from 4:4:4 pictures), | X264VFW_CUDA_CSP_VFLIP for bottom-up
+ * (codec.c:1994-1998): X264VFW_CUDA_CSP_{I420,YV12,YV16,YV24,NV12,YUYV,UYVY,BGR,BGRA}, | X264VFW_CUDA_CSP_VFLIP for bottom-up
  * RGB (x264vfw_picture_vflip, codec.c:510-527); the YV12 U/V swap of codec.c:2263-2274 is applied inside.
  * i_avcol_spc: decoder_context->colorspace (AVCOL_SPC_*, the switch of codec.c:2114-2140); b_fullrange: color_range ==
  * AVCOL_RANGE_JPEG or a YUVJ pixel format (codec.c:2091-2095).  Results are byte-identical to libswscale 9.1.100 (x86-64)
@@ -463,8 +463,10 @@ int x264vfw_cuda_integral_init( x264vfw_cuda_ctx *ctx, uint16_t *sum8_dev, uint1
  * shares one chroma sample per pixel pair -- except that exactly width pixels per row are written (libswscale's SIMD
  * writers store groups of 8).  4:2:2 pictures have no vertical chroma filter: YUY2 / UYVY / YV16 are plain (de)interleaves,
  * RGB uses libswscale's single-line writers; for 4:4:4 pictures libswscale interpolates nothing and converts pixel by pixel
- * (its full-chroma C writer), YV24 is a plane copy.  Not covered (open returns -1): a YUV output whose chroma resolution differs
- * from the decoder picture's other than 4:2:0 -> YUY2 / UYVY (libswscale resamples and dithers there), pictures below 12 rows. */
+ * (its full-chroma C writer), YV24 is a plane copy.  Planar outputs with MORE chroma than the picture (4:2:0 -> YV16 / YV24,
+ * 4:2:2 -> YV24) run libswscale's 4-tap bicubic chroma up-sampling.  Not covered (open returns -1): a YUV output with LESS chroma
+ * than the decoder picture (4:2:2 -> I420 / YV12 / NV12, 4:4:4 -> anything subsampled: libswscale's 8-tap down-sampling filters),
+ * pictures below 12 rows (12 columns where chroma is up-sampled horizontally). */
 typedef struct x264vfw_cuda_dec x264vfw_cuda_dec;
 int  x264vfw_cuda_dec_open( x264vfw_cuda_dec **pdec, x264vfw_cuda_ctx *ctx, int i_out_csp, int i_width, int i_height,
                             int i_src_chroma, int i_avcol_spc, int b_fullrange );

@@ -262,11 +262,54 @@ int orc_decode_convert_src(int src_chroma, int out_csp, uint8_t *dst, const uint
     if (src_chroma < 1 || src_chroma > 3) return -1;
     const int v422 = src_chroma == 2, v444 = src_chroma == 3;
     const int cw = v444 ? w : w / 2, ch = v422 || v444 ? h : h / 2;
-    {   /* a YUV output of another chroma resolution is libswscale's resampling path (yuv2planeX, hscale + dither): not restated */
-        const int out420 = fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12;
-        const int out_chroma = out420 ? 1 : fmt == F_YV16 || fmt == F_YUYV || fmt == F_UYVY ? 2 : fmt == F_YV24 ? 3 : 0;
-        const int planar_out = out420 || fmt == F_YV16 || fmt == F_YV24;
-        if ((planar_out && out_chroma != src_chroma) || (v444 && out_chroma == 2)) return -1;
+    const int out420 = fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12;
+    const int out_chroma = out420 ? 1 : fmt == F_YV16 || fmt == F_YUYV || fmt == F_UYVY ? 2 : fmt == F_YV24 ? 3 : 0;
+    const int planar_out = out420 || fmt == F_YV16 || fmt == F_YV24;
+    /* a YUV output with LESS chroma than the decoder picture is libswscale's down-sampling path (8-tap filters): not restated */
+    if ((planar_out && out_chroma < src_chroma) || (v444 && out_chroma == 2)) return -1;
+    if (planar_out && out_chroma > src_chroma) {
+        /* planar output with MORE chroma than the picture (4:2:0 -> YV16 / YV24, 4:2:2 -> YV24): libswscale's general scaler on
+         * the chroma planes -- horizontal 2x bicubic (initFilter, 4 taps, 14-bit coefficients, filterAlign 4) into 15-bit
+         * intermediates  c15 = min((sum tap * sample) >> 7, 32767)  [hScale8To15], then the vertical filter of this file's
+         * header (4 taps, 12-bit; identity when the heights agree) and the 8-bit plane writer
+         *   out = clip8((sum tap * c15 + (64 << 12)) >> 19)          [yuv2planeX_8 / yuv2plane1_8 with the flat dither 64]
+         * in every row (the SIMD plane writers are bit-exact with the C ones); luma is copied.  YV16 / YV24: planes swapped. */
+        if (flip) return -1;
+        const int ocw = fmt == F_YV24 ? w : w / 2, och = h;              /* output chroma plane */
+        const int hup = ocw != cw, vup = och != ch;
+        if ((hup && cw < 6) || (vup && ch < 5)) return -1;               /* below this initFilter degenerates; not restated */
+        int16_t (*hc)[4] = malloc(sizeof(int16_t[4]) * ocw), (*vc)[4] = malloc(sizeof(int16_t[4]) * och);
+        int *hp = malloc(sizeof(int) * ocw), *vp = malloc(sizeof(int) * och);
+        int ok = hc && vc && hp && vp;
+        if (ok && hup) ok = orc_sws_bicubic_filter(cw, ocw, 4, 1 << 14, 128, 128, hc, hp) == 4;
+        if (ok && vup) ok = orc_sws_bicubic_filter(ch, och, 2, 1 << 12, 128, 128, vc, vp) == 4;
+        if (!ok) { free(hc); free(vc); free(hp); free(vp); return -1; }
+        uint8_t *py = dst, *p1 = dst + (size_t)w * h, *p2 = p1 + (size_t)ocw * och;
+        for (int r = 0; r < h; r++) memcpy(py + (size_t)r * w, src[0] + (ptrdiff_t)r * src_stride[0], w);
+        for (int c = 0; c < 2; c++) {
+            uint8_t *o = c ? p1 : p2;                                     /* YV16 / YV24: V first (codec.c:2263-2274) */
+            const uint8_t *sp = src[1 + c];
+            const int st = src_stride[1 + c];
+            for (int r = 0; r < och; r++)
+                for (int x = 0; x < ocw; x++) {
+                    int64_t acc = 0;
+                    for (int j = 0; j < (vup ? 4 : 1); j++) {
+                        const uint8_t *line = sp + (ptrdiff_t)(vup ? vp[r] + j : r) * st;
+                        int c15;
+                        if (hup) {
+                            int a = 0;
+                            for (int i = 0; i < 4; i++) a += line[hp[x] + i] * hc[x][i];
+                            c15 = a >> 7;
+                            if (c15 > 32767) c15 = 32767;
+                        } else
+                            c15 = line[x] << 7;
+                        acc += (int64_t)c15 * (vup ? vc[r][j] : 4096);
+                    }
+                    o[(size_t)r * ocw + x] = clip_u8((acc + (64 << 12)) >> 19);
+                }
+        }
+        free(hc); free(vc); free(hp); free(vp);
+        return 0;
     }
 
     /* x264vfw_picture_fill (codec.c:419-503) geometry of the output DIB */

@@ -58,6 +58,14 @@ def cases_444():
                 yield w, h, csp, spc, full
 
 
+def cases_up():
+    """Planar outputs with MORE chroma than the decoder picture: 4:2:0 -> YV16 / YV24, 4:2:2 -> YV24 (libswscale's scaler on the
+    chroma planes)."""
+    for w, h in [(16, 12), (70, 38), (72, 40), (320, 240), (1920, 1080)]:
+        for src, csp in ((1, sr.CSP_YV16), (1, sr.CSP_YV24), (2, sr.CSP_YV24)):
+            yield w, h, csp, src
+
+
 def cases():
     for w, h in SIZES:
         for csp in FORMATS:
@@ -88,6 +96,10 @@ def main():
         dib = sr.decompress_convert(y, u, v, csp, spc, full, src_chroma=3)
         out["cases"].append({"w": w, "h": h, "csp": csp, "spc": spc, "full": full, "src": 3,
                              "fnv": ol.fnv(pixel_bytes(dib, csp, w, h))})
+    for w, h, csp, src in cases_up():
+        y, u, v = ol.decode_source(w, h, seed=2, pad=24, src_chroma=src)
+        dib = sr.decompress_convert(y, u, v, csp, 2, 0, src_chroma=src)
+        out["cases"].append({"w": w, "h": h, "csp": csp, "spc": 2, "full": 0, "src": src, "fnv": ol.fnv(dib)})
     # one small picture in full, for debugging a mismatch by eye
     y, u, v = ol.decode_source(16, 10, seed=2, pad=24)
     out["sample_16x10_bgra"] = sr.decompress_convert(y, u, v, sr.CSP_BGRA, 2, 0).tolist()

@@ -99,6 +99,27 @@ def test_device_matches_checker_on_444_pictures(dec, w, h):
                 assert (got == want).all(), (w, h, hex(csp), spc, full, kind, int((got != want).sum()))
 
 
+@pytest.mark.parametrize("w,h", [(16, 12), (70, 38), (258, 66), (1920, 1080)])
+def test_device_matches_checker_on_planar_outputs_with_more_chroma(dec, w, h):
+    """4:2:0 -> YV16 / YV24 and 4:2:2 -> YV24: libswscale's 4-tap bicubic chroma up-sampling (horizontal into 15-bit intermediates,
+    then vertical), luma copied."""
+    rng = np.random.default_rng(w + 9 * h)
+    for src, csps in ((1, (3, 4)), (2, (4,))):
+        ch = h if src == 2 else h // 2
+        for kind in range(2):
+            if kind == 0:
+                y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((h, w + 9), (ch, w // 2 + 5), (ch, w // 2 + 5)))
+            else:
+                y, u, v = (rng.choice(np.array([0, 255], np.uint8), s) for s in ((h, w + 64), (ch, w // 2 + 32), (ch, w // 2 + 32)))
+            y, u, v = y[:, :w], u[:, :w // 2], v[:, :w // 2]
+            for csp in csps:
+                want = ol.oracle_decode_convert(y, u, v, csp, 2, 0, src_chroma=src)
+                d = dec.Decompressor(csp, w, h, 2, 0, src_chroma=src)
+                got = d.decompress(y, u, v)
+                d.close()
+                assert (got == want).all(), (w, h, src, csp, kind, int((got != want).sum()))
+
+
 @pytest.mark.parametrize("csp", ALL)
 def test_batch_entry_on_resident_pictures(dec, csp):
     """x264vfw_cuda_dec_convert_batch: N pictures in device memory, one launch; every picture equals the checker's."""
@@ -135,12 +156,12 @@ def test_refusals_and_geometry(dec):
     from x264vfw_b200._lib import CudaError
     assert dec.picture_get_size(CSP_BGR, 70, 38) == 212 * 38
     assert dec.picture_get_size(4, 64, 32) == 64 * 32 * 3 and dec.picture_get_size(10, 64, 32) == -1
-    for args in ((CSP_YUYV | VFLIP, 64, 32), (4, 64, 32), (3, 64, 32), (CSP_BGRA, 64, 8), (CSP_BGRA, 64, 10), (CSP_BGRA, 63, 32), (CSP_BGRA, 64, 0)):
+    for args in ((CSP_YUYV | VFLIP, 64, 32), (4 | VFLIP, 64, 32), (4, 8, 32), (CSP_BGRA, 64, 8), (CSP_BGRA, 64, 10), (CSP_BGRA, 63, 32), (CSP_BGRA, 64, 0)):
         with pytest.raises(CudaError):
-            dec.Decompressor(*args)                                   # (3 / 4 = YV16 / YV24 from a 4:2:0 picture: another chroma resolution)
-    for csp in (CSP_I420, CSP_YV12, CSP_NV12, 4):
+            dec.Decompressor(*args)
+    for csp in (CSP_I420, CSP_YV12, CSP_NV12):
         with pytest.raises(CudaError):
-            dec.Decompressor(csp, 64, 32, src_chroma=2)
+            dec.Decompressor(csp, 64, 32, src_chroma=2)               # less chroma than the picture: libswscale down-samples
     for csp in (CSP_I420, CSP_NV12, 3, CSP_YUYV, CSP_UYVY):
         with pytest.raises(CudaError):
             dec.Decompressor(csp, 64, 32, src_chroma=3)               # 4:4:4 -> subsampled YUV: libswscale resamples the chroma

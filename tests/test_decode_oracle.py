@@ -82,12 +82,19 @@ def test_checker_against_the_live_library_on_422_and_444_pictures():
                     a = sr.decompress_convert(y, u, v, csp, spc, full, src_chroma=3)
                     b = ol.oracle_decode_convert(y, u, v, csp, spc, full, src_chroma=3)
                     assert (pixel_bytes(a, csp, w, h) == pixel_bytes(b, csp, w, h)).all(), (w, h, hex(csp), spc, full)
-    assert ol.oracle_decode_convert(y, u, v, sr.CSP_YUYV, src_chroma=3) is None      # 4:4:4 -> 4:2:2 resamples chroma: not restated
+    assert ol.oracle_decode_convert(y, u, v, sr.CSP_YUYV, src_chroma=3) is None      # 4:4:4 -> 4:2:2 down-samples chroma: not restated
     y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((18, 24), (18, 12), (18, 12)))
-    # planar outputs of another chroma height go through libswscale's yuv2planeX path: refused, not approximated
-    assert ol.oracle_decode_convert(y, u, v, sr.CSP_I420, src_chroma=2) is None
-    y0, u0, v0 = ol.decode_source(64, 32)
-    assert ol.oracle_decode_convert(y0, u0, v0, sr.CSP_YV16) is None
+    assert ol.oracle_decode_convert(y, u, v, sr.CSP_I420, src_chroma=2) is None      # 4:2:2 -> 4:2:0 likewise
+    # planar outputs with MORE chroma than the picture: libswscale's 4-tap scaler on the chroma planes
+    for w, h in ((24, 18), (90, 50), (12, 10)):
+        for src, csps in ((1, (sr.CSP_YV16, sr.CSP_YV24)), (2, (sr.CSP_YV24,))):
+            ch = h if src == 2 else h // 2
+            for y, u, v in ((rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (ch, w // 2), dtype=np.uint8), rng.integers(0, 256, (ch, w // 2), dtype=np.uint8)),
+                            (rng.choice(np.array([0, 255], np.uint8), (h, w)), rng.choice(np.array([0, 255], np.uint8), (ch, w // 2)), rng.choice(np.array([0, 255], np.uint8), (ch, w // 2)))):
+                for csp in csps:
+                    a = sr.decompress_convert(y, u, v, csp, 2, 0, src_chroma=src)
+                    b = ol.oracle_decode_convert(y, u, v, csp, 2, 0, src_chroma=src)
+                    assert (a == b).all(), (w, h, src, csp)
 
 
 def test_reference_context_never_gets_full_chroma_interpolation():
@@ -104,6 +111,6 @@ def test_geometry_and_refusals():
     assert ol.decode_picture_size(sr.CSP_NV12, 64, 32) == 64 * 32 * 3 // 2
     y, u, v = ol.decode_source(64, 32)
     assert ol.oracle_decode_convert(y, u, v, sr.CSP_YUYV | sr.CSP_VFLIP) is None   # only RGB can be flipped (codec.c:510-527)
-    assert ol.oracle_decode_convert(y, u, v, 4) is None                          # YV24 from a 4:2:0 picture: another chroma resolution
+    assert ol.oracle_decode_convert(y, u, v, 10) is None                         # no such csp
     y, u, v = ol.decode_source(64, 8)
     assert ol.oracle_decode_convert(y, u, v, sr.CSP_BGRA) is None                # fewer than 5 chroma rows: not restated

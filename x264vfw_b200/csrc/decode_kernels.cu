@@ -330,14 +330,59 @@ __global__ void __launch_bounds__(256) dec_planar_kernel(const DecPlanarJob j)
     else for (int q = 0; q < 16 && xb + q < cw; q++) { du[q] = __ldg(su + xb + q); dv[q] = __ldg(sv + xb + q); }
 }
 
+// Planar output with MORE chroma than the decoder picture (4:2:0 -> YV16 / YV24, 4:2:2 -> YV24): libswscale's general scaler
+// on a chroma plane -- horizontal 2x bicubic into 15-bit intermediates, c15 = min((sum tap * sample) >> 7, 32767), then the
+// vertical filter and the 8-bit plane writer, out = clip8((sum tap * c15 + (64 << 12)) >> 19).  Where a direction is not scaled
+// its table holds one tap of 1.0 (16384 / 4096), which makes the same expression the identity.  Thread = one output sample of
+// both planes; a rare path, kept simple.
+struct DecUpJob {
+    const uint8_t *u, *v; int us, vs;
+    uint8_t *du, *dv;
+    int ocw, och;                   // output chroma plane
+    const DecRow *cols, *rows;      // horizontal / vertical taps per output column / row (pos, c01, c23)
+    size_t src_frame_bytes, dst_frame_bytes;
+};
+
+__global__ void __launch_bounds__(256) dec_upchroma_kernel(const DecUpJob j)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
+    if (x >= j.ocw || r >= j.och) return;
+    const int4 hc = __ldg((const int4 *)(j.cols + x)), vc = __ldg((const int4 *)(j.rows + r));
+    const int hcoef[4] = {(short)(hc.y & 0xffff), hc.y >> 16, (short)(hc.z & 0xffff), hc.z >> 16};
+    const int vcoef[4] = {(short)(vc.y & 0xffff), vc.y >> 16, (short)(vc.z & 0xffff), vc.z >> 16};
+    const size_t so = (size_t)blockIdx.z * j.src_frame_bytes, dof = (size_t)blockIdx.z * j.dst_frame_bytes;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const uint8_t *sp = (c ? j.v : j.u) + so + hc.x;
+        const int st = c ? j.vs : j.us;
+        int acc = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (!vcoef[q]) continue;                       // also keeps the loads inside the plane: padding taps are zero
+            const uint8_t *line = sp + (ptrdiff_t)(vc.x + q) * st;
+            int a = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (hcoef[i]) a += (int)__ldg(line + i) * hcoef[i];
+            acc += min(a >> 7, 32767) * vcoef[q];
+        }
+        ((c ? j.dv : j.du) + dof)[(size_t)r * j.ocw + x] = (uint8_t)clip8((acc + (64 << 12)) >> 19);
+    }
+}
+
 // ---- host side: the context x264vfw_init_sws_context builds, as numbers --------------------------------------
 
 // The vertical chroma filter libswscale's initFilter() [libswscale/utils.c] yields for this context: bicubic
 // (B = 0, C = 0.6), src_n -> 2 * src_n, both chroma sitings 128, coefficients normalised to 1 << 12, at most 4 taps
 // after near-zero taps are dropped, out-of-picture taps folded onto the edge line.
+static bool bicubic_2x_filter(int src_n, std::vector<DecRow> &rows, bool c_writer_everywhere, int one, int align, bool kernel_pos_rule);
 static bool vertical_chroma_filter(int src_n, std::vector<DecRow> &rows, bool c_writer_everywhere)
 {
-    const int dst_n = 2 * src_n, one = 1 << 12;
+    return bicubic_2x_filter(src_n, rows, c_writer_everywhere, 1 << 12, 2, true);
+}
+
+static bool bicubic_2x_filter(int src_n, std::vector<DecRow> &rows, bool c_writer_everywhere, int one, int align, bool kernel_pos_rule)
+{
+    const int dst_n = 2 * src_n;
     if (src_n < 6) return false;                               // below that the tap positions stop following the kernel's rule
     const int taps = src_n - 2 < 5 ? src_n - 2 : 5;            // 1 + sizeFactor(bicubic), capped by the source height
     const long long inc = (((long long)src_n << 16) + (dst_n >> 1)) / dst_n;        // 1 << 15
@@ -382,7 +427,7 @@ static bool vertical_chroma_filter(int src_n, std::vector<DecRow> &rows, bool c_
         }
         support = n > support ? n : support;
     }
-    const int size = (support + 1) & ~1;                   // vertical filterAlign of the x86 build: 2
+    const int size = (support + align - 1) & ~(align - 1);   // filterAlign of the x86 build: 2 vertical, 4 horizontal
     if (size != 4) return false;                          // the kernel reads 4 lines per row
     rows.resize(dst_n);
     for (int i = 0; i < dst_n; i++) {
@@ -414,7 +459,7 @@ static bool vertical_chroma_filter(int src_n, std::vector<DecRow> &rows, bool c_
         const bool cwr = c_writer_everywhere || i >= dst_n - 2;    // libswscale leaves SIMD for the last two lines
         if (!cwr)          // ff_updateMMXDitherTables packs f[q] + f[q+1] * 65536 into ONE int: a negative f[q] borrows
             for (int q = 0; q < 4; q += 2) if (c[q] < 0) c[q + 1] = (int16_t)(c[q + 1] - 1);
-        if (pos[i] != std::min(std::max(((i + 1) >> 1) - 2, 0), src_n - 4)) return false;   // the kernel derives it
+        if (kernel_pos_rule && pos[i] != std::min(std::max(((i + 1) >> 1) - 2, 0), src_n - 4)) return false;   // dec_packed_kernel derives it
         rows[i].pos = pos[i];
         rows[i].c01 = (c[0] & 0xffff) | (int)((uint32_t)c[1] << 16);
         rows[i].c23 = (c[2] & 0xffff) | (int)((uint32_t)c[3] << 16);
@@ -475,8 +520,9 @@ static void colour_constants(DecConst &k, int avcol_spc, int fullrange, int roun
 struct Dec {
     Ctx *ctx;
     int csp, flip, w, h, v422, v444;
+    int up = 0;                 // planar output with more chroma than the picture: dec_upchroma_kernel (d_rows + d_cols)
     DecConst k;
-    DecRow *d_rows = nullptr;
+    DecRow *d_rows = nullptr, *d_cols = nullptr;
     // staging of the host-buffer entry
     uint8_t *d_src = nullptr, *d_dst = nullptr;
     size_t src_bytes = 0, dst_bytes = 0;
@@ -491,6 +537,28 @@ static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src
     const int w = d->w, h = d->h, cw = d->v444 ? w : w / 2, ch = d->v422 || d->v444 ? h : h / 2;
     if (n <= 0) return 0;
     if (n > 65535) { set_error("at most 65535 pictures per launch"); return -1; }
+    if (d->up) {
+        // luma: plane copy (the planar kernel with no chroma rows in its grid); chroma: the up-sampling kernel
+        const int ocw = d->csp == X264VFW_CUDA_CSP_YV24 ? w : w / 2, och = h;
+        DecPlanarJob pj;
+        pj.y = src[0]; pj.u = src[1]; pj.v = src[2]; pj.ys = ss[0]; pj.us = ss[1]; pj.vs = ss[2];
+        pj.w = w; pj.h = h; pj.cw = cw; pj.src_frame_bytes = sfb; pj.dst_frame_bytes = dfb;
+        pj.dy = dst; pj.du = pj.dv = nullptr;
+        const bool vec = als(w, 16) && al(dst, 16) && als((long long)dfb, 16) && als((long long)sfb, 16) && al(src[0], 16) && als(ss[0], 16);
+        dim3 grid((w + 4095) / 4096, h, n);
+        if (vec) dec_planar_kernel<true><<<grid, 256, 0, st>>>(pj);
+        else     dec_planar_kernel<false><<<grid, 256, 0, st>>>(pj);
+        XV_LAUNCH_CHECK();
+        DecUpJob uj;
+        uj.u = src[1]; uj.v = src[2]; uj.us = ss[1]; uj.vs = ss[2];
+        uint8_t *p1 = dst + (size_t)w * h, *p2 = p1 + (size_t)ocw * och;
+        uj.du = p2; uj.dv = p1;                                                       // YV16 / YV24: codec.c:2263-2274
+        uj.ocw = ocw; uj.och = och; uj.cols = d->d_cols; uj.rows = d->d_rows;
+        uj.src_frame_bytes = sfb; uj.dst_frame_bytes = dfb;
+        dec_upchroma_kernel<<<dim3((ocw + 31) / 32, (och + 7) / 8, n), dim3(32, 8), 0, st>>>(uj);
+        XV_LAUNCH_CHECK();
+        return 0;
+    }
     if (d->csp == X264VFW_CUDA_CSP_I420 || d->csp == X264VFW_CUDA_CSP_YV12 || d->csp == X264VFW_CUDA_CSP_NV12 || d->csp == X264VFW_CUDA_CSP_YV16 ||
         d->csp == X264VFW_CUDA_CSP_YV24) {
         DecPlanarJob j;
@@ -582,19 +650,47 @@ int x264vfw_cuda_dec_open(x264vfw_cuda_dec **pdec, x264vfw_cuda_ctx *ctx, int i_
     const int out_chroma = out420 ? 1 : csp == X264VFW_CUDA_CSP_YV16 || csp == X264VFW_CUDA_CSP_YUYV || csp == X264VFW_CUDA_CSP_UYVY ? 2 :
                            csp == X264VFW_CUDA_CSP_YV24 ? 3 : 0;
     const bool planar_out = out420 || csp == X264VFW_CUDA_CSP_YV16 || csp == X264VFW_CUDA_CSP_YV24;
-    if ((planar_out && out_chroma != i_src_chroma) || (v444 && out_chroma == 2)) {
-        set_error("YUV output with another chroma resolution than the decoder picture is not covered");
+    if ((planar_out && out_chroma < i_src_chroma) || (v444 && out_chroma == 2)) {
+        set_error("YUV output with less chroma than the decoder picture is not covered (libswscale's down-sampling filters)");
         return -1;
     }
+    const bool up = planar_out && out_chroma > i_src_chroma;      // 4:2:0 -> YV16 / YV24, 4:2:2 -> YV24
+    if (up && (h < 12 || w < 12)) { set_error("pictures below 12 rows / columns are not covered"); return -1; }
     const bool rgb = csp == X264VFW_CUDA_CSP_BGR || csp == X264VFW_CUDA_CSP_BGRA;
     if (flip && !rgb) { set_error("only RGB output can be bottom-up (codec.c:510-527)"); return -1; }
     const bool planar = planar_out || v444;               // no row table: plane copies, and the per-pixel 4:4:4 writer
     Ctx *c = (Ctx *)ctx;
     XV_CUDA_OK(cudaSetDevice(c->device));
     Dec *d = new Dec;
-    d->ctx = c; d->csp = csp; d->flip = flip; d->w = w; d->h = h; d->v422 = v422; d->v444 = v444;
+    d->ctx = c; d->csp = csp; d->flip = flip; d->w = w; d->h = h; d->v422 = v422; d->v444 = v444; d->up = up;
     colour_constants(d->k, i_avcol_spc, b_fullrange != 0, v422 ? 0 : 4);
-    if (!planar) {
+    if (up) {
+        const int cw = w / 2, ch = v422 ? h : h / 2, ocw = csp == X264VFW_CUDA_CSP_YV24 ? w : w / 2, och = h;
+        std::vector<DecRow> rows, cols;
+        auto identity = [](int n, int one, std::vector<DecRow> &t) {          // one tap of 1.0 on the sample itself, inside a 4-sample window
+            t.resize(n);
+            for (int i = 0; i < n; i++) {
+                const int pos = std::min(i, n - 4), k = i - pos;
+                t[i].pos = pos;
+                t[i].c01 = k == 0 ? one : k == 1 ? (int)((unsigned)one << 16) : 0;
+                t[i].c23 = k == 2 ? one : k == 3 ? (int)((unsigned)one << 16) : 0;
+                t[i].c_writer = 1;
+            }
+        };
+        bool ok = true;
+        if (och != ch) ok = bicubic_2x_filter(ch, rows, true, 1 << 12, 2, false); else identity(och, 1 << 12, rows);
+        if (ok) { if (ocw != cw) ok = bicubic_2x_filter(cw, cols, true, 1 << 14, 4, false); else identity(ocw, 1 << 14, cols); }
+        if (!ok || cudaMalloc((void **)&d->d_rows, rows.size() * sizeof(DecRow)) != cudaSuccess ||
+            cudaMalloc((void **)&d->d_cols, cols.size() * sizeof(DecRow)) != cudaSuccess ||
+            cudaMemcpy(d->d_rows, rows.data(), rows.size() * sizeof(DecRow), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(d->d_cols, cols.data(), cols.size() * sizeof(DecRow), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error(ok ? "filter table upload failed" : "picture too small for libswscale's 4-tap chroma filters");
+            if (d->d_rows) cudaFree(d->d_rows);
+            if (d->d_cols) cudaFree(d->d_cols);
+            delete d;
+            return -1;
+        }
+    } else if (!planar) {
         std::vector<DecRow> rows;
         if (v422 && h >= 12) {
             // no vertical filter (libswscale's yuv2packed1 writers; plain interleave for 4:2:2 output): one tap of 1.0 on the
@@ -631,6 +727,7 @@ void x264vfw_cuda_dec_close(x264vfw_cuda_dec *dec)
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
     if (d->d_rows) cudaFree(d->d_rows);
+    if (d->d_cols) cudaFree(d->d_cols);
     if (d->d_src) cudaFree(d->d_src);
     if (d->d_dst) cudaFree(d->d_dst);
     delete d;
