@@ -463,10 +463,11 @@ int x264vfw_cuda_integral_init( x264vfw_cuda_ctx *ctx, uint16_t *sum8_dev, uint1
  * shares one chroma sample per pixel pair -- except that exactly width pixels per row are written (libswscale's SIMD
  * writers store groups of 8).  4:2:2 pictures have no vertical chroma filter: YUY2 / UYVY / YV16 are plain (de)interleaves,
  * RGB uses libswscale's single-line writers; for 4:4:4 pictures libswscale interpolates nothing and converts pixel by pixel
- * (its full-chroma C writer), YV24 is a plane copy.  Planar outputs with MORE chroma than the picture (4:2:0 -> YV16 / YV24,
- * 4:2:2 -> YV24) run libswscale's 4-tap bicubic chroma up-sampling.  Not covered (open returns -1): a YUV output with LESS chroma
- * than the decoder picture (4:2:2 -> I420 / YV12 / NV12, 4:4:4 -> anything subsampled: libswscale's 8-tap down-sampling filters),
- * pictures below 12 rows (12 columns where chroma is up-sampled horizontally). */
+ * (its full-chroma C writer), YV24 is a plane copy.  A YUV output whose chroma resolution differs from the picture's (4:2:0 ->
+ * YV16 / YV24, 4:2:2 -> I420 / YV12 / NV12 / YV24, 4:4:4 -> I420 / YV12 / NV12 / YV16 / YUY2 / UYVY) runs libswscale's bicubic chroma
+ * scaler (4 taps for 2x up, 8 taps for 2:1 down).  Every (picture format, output csp) pair of 8-bit 4:2:0 / 4:2:2 / 4:4:4 pictures
+ * is covered.  Not covered (open returns -1): pictures below 12 rows; chroma planes below 12 (6) samples in a direction that is
+ * halved (doubled). */
 typedef struct x264vfw_cuda_dec x264vfw_cuda_dec;
 int  x264vfw_cuda_dec_open( x264vfw_cuda_dec **pdec, x264vfw_cuda_ctx *ctx, int i_out_csp, int i_width, int i_height,
                             int i_src_chroma, int i_avcol_spc, int b_fullrange );

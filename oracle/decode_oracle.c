@@ -51,16 +51,20 @@ static int64_t rounded_div(int64_t a, int64_t b)
     return a >= 0 ? (a + (b >> 1)) / b : (a - (b >> 1)) / b;
 }
 
-/* Fills coef[dst_n][4] (zero padded) and pos[dst_n]; returns the filter size (<= 4) or -1. */
-int orc_sws_bicubic_filter(int src_n, int dst_n, int filter_align, int one, int src_pos, int dst_pos,
-                           int16_t (*coef)[4], int *pos)
+/* initFilter() for the two bicubic cases this context meets: 2x upscale (xInc <= 1<<16: 1 + 4 taps before the cut) and 2:1
+ * downscale (xInc > 1<<16: 1 + 4 * srcW / dstW = 9 taps before the cut, distances scaled by dstW / srcW, fone halved).
+ * Fills coef[dst_n][8] (zero padded) and pos[dst_n]; returns the filter size (<= 8) or -1. */
+int orc_sws_filter(int src_n, int dst_n, int filter_align, int one, int src_pos, int dst_pos, int16_t (*coef)[8], int *pos)
 {
-    const int64_t fone = (int64_t)1 << 54;                 /* av_log2(srcW/dstW) == 0 on an upscale */
     const int x_inc = (int)((((int64_t)src_n << 16) + (dst_n >> 1)) / dst_n);
-    int size = 1 + 4;                                      /* "upscale": 1 + sizeFactor(bicubic = 4) */
+    const int down = x_inc > (1 << 16);
+    int lg = 0;                                             /* av_log2(srcW / dstW), capped at 8 */
+    for (int q = src_n / dst_n; q > 1; q >>= 1) lg++;
+    const int64_t fone = (int64_t)1 << (54 - (lg < 8 ? lg : 8));
+    int size = down ? 1 + (4 * src_n + dst_n - 1) / dst_n : 1 + 4;
     if (size > src_n - 2) size = src_n - 2;
     if (size < 1) size = 1;
-    if (x_inc > (1 << 16) || llabs((long long)x_inc - 0x10000) < 10) return -1;   /* other initFilter branches */
+    if (llabs((long long)x_inc - 0x10000) < 10 || size > 9) return -1;                     /* other initFilter branches */
 
     int64_t *f = calloc((size_t)dst_n * size, sizeof(*f));
     if (!f) return -1;
@@ -72,6 +76,7 @@ int orc_sws_bicubic_filter(int src_n, int dst_n, int filter_align, int one, int 
         for (int j = 0; j < size; j++) {
             int64_t d = llabs((int64_t)xx * (1 << 17) - x_dst_in_src) << 13;
             int64_t c;
+            if (down) d = d * dst_n / src_n;
             if (d >= 1LL << 31)
                 c = 0;
             else {
@@ -113,10 +118,10 @@ int orc_sws_bicubic_filter(int src_n, int dst_n, int filter_align, int one, int 
         if (mn > min_size) min_size = mn;
     }
     int out_size = (min_size + (filter_align - 1)) & ~(filter_align - 1);
-    if (out_size > 4) { free(f); return -1; }
+    if (out_size > 8 || out_size > src_n) { free(f); return -1; }
 
     for (int i = 0; i < dst_n; i++) {
-        int64_t t[4] = {0, 0, 0, 0};
+        int64_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int j = 0; j < out_size && j < size; j++) t[j] = f[(size_t)i * size + j];
         /* borders: fold taps that fall outside [0, src_n) onto the edge sample */
         if (pos[i] < 0) {
@@ -142,7 +147,7 @@ int orc_sws_bicubic_filter(int src_n, int dst_n, int filter_align, int one, int 
         for (int j = 0; j < out_size; j++) sum += t[j];
         sum = (sum + one / 2) / one;
         if (!sum) sum = 1;
-        for (int j = 0; j < 4; j++) coef[i][j] = 0;
+        for (int j = 0; j < 8; j++) coef[i][j] = 0;
         for (int j = 0; j < out_size; j++) {
             int64_t v = t[j] + err;
             int64_t iv = rounded_div(v, sum);
@@ -152,6 +157,20 @@ int orc_sws_bicubic_filter(int src_n, int dst_n, int filter_align, int one, int 
     }
     free(f);
     return out_size;
+}
+
+/* the 2x upscale with at most 4 taps, as the packed writers use it: coef[dst_n][4] */
+int orc_sws_bicubic_filter(int src_n, int dst_n, int filter_align, int one, int src_pos, int dst_pos,
+                           int16_t (*coef)[4], int *pos)
+{
+    if (dst_n != 2 * src_n) return -1;
+    int16_t (*c8)[8] = malloc(sizeof(int16_t[8]) * dst_n);
+    if (!c8) return -1;
+    int n = orc_sws_filter(src_n, dst_n, filter_align, one, src_pos, dst_pos, c8, pos);
+    if (n > 4) n = -1;
+    if (n > 0) for (int i = 0; i < dst_n; i++) for (int j = 0; j < 4; j++) coef[i][j] = c8[i][j];
+    free(c8);
+    return n;
 }
 
 /* ---- colour constants: ff_yuv2rgb_c_init_tables() of libswscale/yuv2rgb.c ------------------ */
@@ -265,50 +284,83 @@ int orc_decode_convert_src(int src_chroma, int out_csp, uint8_t *dst, const uint
     const int out420 = fmt == F_I420 || fmt == F_YV12 || fmt == F_NV12;
     const int out_chroma = out420 ? 1 : fmt == F_YV16 || fmt == F_YUYV || fmt == F_UYVY ? 2 : fmt == F_YV24 ? 3 : 0;
     const int planar_out = out420 || fmt == F_YV16 || fmt == F_YV24;
-    /* a YUV output with LESS chroma than the decoder picture is libswscale's down-sampling path (8-tap filters): not restated */
-    if ((planar_out && out_chroma < src_chroma) || (v444 && out_chroma == 2)) return -1;
-    if (planar_out && out_chroma > src_chroma) {
-        /* planar output with MORE chroma than the picture (4:2:0 -> YV16 / YV24, 4:2:2 -> YV24): libswscale's general scaler on
-         * the chroma planes -- horizontal 2x bicubic (initFilter, 4 taps, 14-bit coefficients, filterAlign 4) into 15-bit
-         * intermediates  c15 = min((sum tap * sample) >> 7, 32767)  [hScale8To15], then the vertical filter of this file's
-         * header (4 taps, 12-bit; identity when the heights agree) and the 8-bit plane writer
-         *   out = clip8((sum tap * c15 + (64 << 12)) >> 19)          [yuv2planeX_8 / yuv2plane1_8 with the flat dither 64]
-         * in every row (the SIMD plane writers are bit-exact with the C ones); luma is copied.  YV16 / YV24: planes swapped. */
+    if (planar_out && out_chroma != src_chroma) {
+        /* planar output with another chroma resolution than the picture (4:2:0 -> YV16 / YV24, 4:2:2 -> I420 / YV12 / NV12 / YV24,
+         * 4:4:4 -> I420 / YV12 / NV12 / YV16): libswscale's general scaler on the chroma planes -- horizontal bicubic (initFilter:
+         * 4 taps for 2x up, 8 taps for 2:1 down; 14-bit coefficients, filterAlign 4) into 15-bit intermediates
+         *   c15 = min((sum tap * sample) >> 7, 32767)                [hScale8To15],
+         * then the vertical filter (4 / 8 taps, 12-bit, filterAlign 2; identity when the heights agree) and the 8-bit plane writer
+         *   out = clip8((sum tap * c15 + (64 << 12)) >> 19)          [yuv2planeX_8 / yuv2plane1_8 / yuv2nv12cX, flat dither 64]
+         * in every row (the SIMD plane writers are bit-exact with the C ones); luma is copied.  YV12 / YV16 / YV24: planes swapped. */
         if (flip) return -1;
-        const int ocw = fmt == F_YV24 ? w : w / 2, och = h;              /* output chroma plane */
-        const int hup = ocw != cw, vup = och != ch;
-        if ((hup && cw < 6) || (vup && ch < 5)) return -1;               /* below this initFilter degenerates; not restated */
-        int16_t (*hc)[4] = malloc(sizeof(int16_t[4]) * ocw), (*vc)[4] = malloc(sizeof(int16_t[4]) * och);
+        const int ocw = fmt == F_YV24 ? w : w / 2, och = out420 ? h / 2 : h;          /* output chroma plane */
+        const int hs = ocw != cw, vs = och != ch;
+        int16_t (*hc)[8] = malloc(sizeof(int16_t[8]) * ocw), (*vc)[8] = malloc(sizeof(int16_t[8]) * och);
         int *hp = malloc(sizeof(int) * ocw), *vp = malloc(sizeof(int) * och);
-        int ok = hc && vc && hp && vp;
-        if (ok && hup) ok = orc_sws_bicubic_filter(cw, ocw, 4, 1 << 14, 128, 128, hc, hp) == 4;
-        if (ok && vup) ok = orc_sws_bicubic_filter(ch, och, 2, 1 << 12, 128, 128, vc, vp) == 4;
+        int ok = hc && vc && hp && vp, hn = 1, vn = 1;
+        if (ok && hs) ok = (hn = orc_sws_filter(cw, ocw, 4, 1 << 14, 128, 128, hc, hp)) > 0;
+        if (ok && vs) ok = (vn = orc_sws_filter(ch, och, 2, 1 << 12, 128, 128, vc, vp)) > 0;
+        /* below these sizes initFilter cuts its tap count to the picture: not restated */
+        if (ok && ((hs && (ocw > cw ? cw < 6 : cw < 12)) || (vs && (och > ch ? ch < 5 : ch < 12)))) ok = 0;
         if (!ok) { free(hc); free(vc); free(hp); free(vp); return -1; }
         uint8_t *py = dst, *p1 = dst + (size_t)w * h, *p2 = p1 + (size_t)ocw * och;
         for (int r = 0; r < h; r++) memcpy(py + (size_t)r * w, src[0] + (ptrdiff_t)r * src_stride[0], w);
         for (int c = 0; c < 2; c++) {
-            uint8_t *o = c ? p1 : p2;                                     /* YV16 / YV24: V first (codec.c:2263-2274) */
+            uint8_t *o; int ostep, ostride;
+            if (fmt == F_NV12) { o = p1 + c; ostep = 2; ostride = w; }
+            else { o = (fmt == F_I420) == (c == 0) ? p1 : p2; ostep = 1; ostride = ocw; }   /* YV12 / YV16 / YV24: V first (codec.c:2263-2274) */
             const uint8_t *sp = src[1 + c];
             const int st = src_stride[1 + c];
             for (int r = 0; r < och; r++)
                 for (int x = 0; x < ocw; x++) {
                     int64_t acc = 0;
-                    for (int j = 0; j < (vup ? 4 : 1); j++) {
-                        const uint8_t *line = sp + (ptrdiff_t)(vup ? vp[r] + j : r) * st;
+                    for (int j = 0; j < (vs ? vn : 1); j++) {
+                        const uint8_t *line = sp + (ptrdiff_t)(vs ? vp[r] + j : r) * st;
                         int c15;
-                        if (hup) {
+                        if (hs) {
                             int a = 0;
-                            for (int i = 0; i < 4; i++) a += line[hp[x] + i] * hc[x][i];
+                            for (int i = 0; i < hn; i++) a += line[hp[x] + i] * hc[x][i];
                             c15 = a >> 7;
                             if (c15 > 32767) c15 = 32767;
                         } else
                             c15 = line[x] << 7;
-                        acc += (int64_t)c15 * (vup ? vc[r][j] : 4096);
+                        acc += (int64_t)c15 * (vs ? vc[r][j] : 4096);
                     }
-                    o[(size_t)r * ocw + x] = clip_u8((acc + (64 << 12)) >> 19);
+                    o[(size_t)r * ostride + (size_t)x * ostep] = clip_u8((acc + (64 << 12)) >> 19);
                 }
         }
         free(hc); free(vc); free(hp); free(vp);
+        return 0;
+    }
+    if (v444 && out_chroma == 2) {
+        /* 4:4:4 picture -> YUY2 / UYVY: chroma down-sampled horizontally as above (8 taps), then libswscale's single-line packed
+         * writers: yuv2yuyv422_1 SIMD in rows 0..h-3 (c15 >> 7), the C writer in the last two rows and in every row of UYVY
+         * ((c15 + 64) >> 7); luma passes through. */
+        if (flip || w < 24) return -1;
+        const int ocw = w / 2;
+        int16_t (*hc)[8] = malloc(sizeof(int16_t[8]) * ocw);
+        int *hp = malloc(sizeof(int) * ocw);
+        int hn = hc && hp ? orc_sws_filter(cw, ocw, 4, 1 << 14, 128, 128, hc, hp) : -1;
+        if (hn <= 0) { free(hc); free(hp); return -1; }
+        for (int r = 0; r < h; r++) {
+            const int c_writer = fmt == F_UYVY || r >= h - 2;
+            uint8_t *o = dst + (size_t)r * 2 * w;
+            for (int x = 0; x < ocw; x++) {
+                int cv[2];
+                for (int c = 0; c < 2; c++) {
+                    const uint8_t *line = src[1 + c] + (ptrdiff_t)r * src_stride[1 + c];
+                    int a = 0;
+                    for (int i = 0; i < hn; i++) a += line[hp[x] + i] * hc[x][i];
+                    int c15 = a >> 7;
+                    if (c15 > 32767) c15 = 32767;
+                    cv[c] = clip_u8(c_writer ? (c15 + 64) >> 7 : c15 >> 7);
+                }
+                const int y0 = src[0][(ptrdiff_t)r * src_stride[0] + 2 * x], y1 = src[0][(ptrdiff_t)r * src_stride[0] + 2 * x + 1];
+                if (fmt == F_YUYV) { o[4 * x] = y0; o[4 * x + 1] = cv[0]; o[4 * x + 2] = y1; o[4 * x + 3] = cv[1]; }
+                else               { o[4 * x] = cv[0]; o[4 * x + 1] = y0; o[4 * x + 2] = cv[1]; o[4 * x + 3] = y1; }
+            }
+        }
+        free(hc); free(hp);
         return 0;
     }
 

@@ -13,10 +13,12 @@ from test_encoder_side_oracle import fade_frames, nv12
 
 ctx = xv._lib.Context(0)
 n = 0
-for src, csps in ((1, (1, 2, 3, 4, 5, 6, 7, 8, 9, 8 | 0x1000, 9 | 0x1000)), (2, (3, 4, 6, 7, 8, 9 | 0x1000)), (3, (4, 8, 9, 9 | 0x1000))):
+for src, csps in ((1, (1, 2, 3, 4, 5, 6, 7, 8, 9, 8 | 0x1000, 9 | 0x1000)), (2, (1, 2, 3, 4, 5, 6, 7, 8, 9 | 0x1000)), (3, (1, 2, 3, 4, 5, 6, 7, 8, 9, 9 | 0x1000))):
     for w, h in ((64, 32), (70, 38), (16, 12)):
         y, u, v = ol.decode_source(w, h, seed=src, pad=8, src_chroma=src)
         for csp in csps:
+            if ol.oracle_decode_convert(y, u, v, csp, 1, 0, src_chroma=src) is None:
+                continue                                    # too small for libswscale's full tap count: refused on both sides
             d = decode.Decompressor(csp, w, h, 1, 0, ctx=ctx, src_chroma=src)
             got = d.decompress(y, u, v)
             d.close()

@@ -59,11 +59,14 @@ def cases_444():
 
 
 def cases_up():
-    """Planar outputs with MORE chroma than the decoder picture: 4:2:0 -> YV16 / YV24, 4:2:2 -> YV24 (libswscale's scaler on the
-    chroma planes)."""
-    for w, h in [(16, 12), (70, 38), (72, 40), (320, 240), (1920, 1080)]:
-        for src, csp in ((1, sr.CSP_YV16), (1, sr.CSP_YV24), (2, sr.CSP_YV24)):
-            yield w, h, csp, src
+    """YUV outputs with ANOTHER chroma resolution than the decoder picture (libswscale's scaler on the chroma planes: 4 taps up, 8 taps
+    down), packed 4:2:2 from 4:4:4 included."""
+    for w, h in [(24, 24), (70, 38), (72, 40), (320, 240), (1920, 1080)]:
+        for src, csps in ((1, (sr.CSP_YV16, sr.CSP_YV24)),
+                          (2, (sr.CSP_I420, sr.CSP_YV12, sr.CSP_NV12, sr.CSP_YV24)),
+                          (3, (sr.CSP_I420, sr.CSP_YV12, sr.CSP_NV12, sr.CSP_YV16, sr.CSP_YUYV, sr.CSP_UYVY))):
+            for csp in csps:
+                yield w, h, csp, src
 
 
 def cases():

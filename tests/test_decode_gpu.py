@@ -99,21 +99,24 @@ def test_device_matches_checker_on_444_pictures(dec, w, h):
                 assert (got == want).all(), (w, h, hex(csp), spc, full, kind, int((got != want).sum()))
 
 
-@pytest.mark.parametrize("w,h", [(16, 12), (70, 38), (258, 66), (1920, 1080)])
-def test_device_matches_checker_on_planar_outputs_with_more_chroma(dec, w, h):
-    """4:2:0 -> YV16 / YV24 and 4:2:2 -> YV24: libswscale's 4-tap bicubic chroma up-sampling (horizontal into 15-bit intermediates,
-    then vertical), luma copied."""
+@pytest.mark.parametrize("w,h", [(24, 24), (70, 38), (258, 66), (1920, 1080)])
+def test_device_matches_checker_where_the_chroma_resolution_changes(dec, w, h):
+    """Every YUV output whose chroma resolution differs from the decoder picture's: libswscale's bicubic chroma scaler (4 taps for 2x up,
+    8 taps for 2:1 down; horizontal into 15-bit intermediates, then vertical), luma copied; 4:4:4 -> YUY2 / UYVY through the single-line
+    packed writers."""
     rng = np.random.default_rng(w + 9 * h)
-    for src, csps in ((1, (3, 4)), (2, (4,))):
-        ch = h if src == 2 else h // 2
+    combos = ((1, (3, 4)), (2, (CSP_I420, CSP_YV12, CSP_NV12, 4)), (3, (CSP_I420, CSP_YV12, CSP_NV12, 3, CSP_YUYV, CSP_UYVY)))
+    for src, csps in combos:
+        cw, ch = (w if src == 3 else w // 2), (h if src >= 2 else h // 2)
         for kind in range(2):
             if kind == 0:
-                y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((h, w + 9), (ch, w // 2 + 5), (ch, w // 2 + 5)))
+                y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((h, w + 9), (ch, cw + 5), (ch, cw + 5)))
             else:
-                y, u, v = (rng.choice(np.array([0, 255], np.uint8), s) for s in ((h, w + 64), (ch, w // 2 + 32), (ch, w // 2 + 32)))
-            y, u, v = y[:, :w], u[:, :w // 2], v[:, :w // 2]
+                y, u, v = (rng.choice(np.array([0, 255], np.uint8), s) for s in ((h, w + 64), (ch, cw + 32), (ch, cw + 32)))
+            y, u, v = y[:, :w], u[:, :cw], v[:, :cw]
             for csp in csps:
                 want = ol.oracle_decode_convert(y, u, v, csp, 2, 0, src_chroma=src)
+                assert want is not None
                 d = dec.Decompressor(csp, w, h, 2, 0, src_chroma=src)
                 got = d.decompress(y, u, v)
                 d.close()
@@ -159,12 +162,8 @@ def test_refusals_and_geometry(dec):
     for args in ((CSP_YUYV | VFLIP, 64, 32), (4 | VFLIP, 64, 32), (4, 8, 32), (CSP_BGRA, 64, 8), (CSP_BGRA, 64, 10), (CSP_BGRA, 63, 32), (CSP_BGRA, 64, 0)):
         with pytest.raises(CudaError):
             dec.Decompressor(*args)
-    for csp in (CSP_I420, CSP_YV12, CSP_NV12):
-        with pytest.raises(CudaError):
-            dec.Decompressor(csp, 64, 32, src_chroma=2)               # less chroma than the picture: libswscale down-samples
-    for csp in (CSP_I420, CSP_NV12, 3, CSP_YUYV, CSP_UYVY):
-        with pytest.raises(CudaError):
-            dec.Decompressor(csp, 64, 32, src_chroma=3)               # 4:4:4 -> subsampled YUV: libswscale resamples the chroma
+    with pytest.raises(CudaError):
+        dec.Decompressor(CSP_I420, 16, 10, src_chroma=2)              # 10 chroma rows cannot be halved with libswscale's full 8 taps
     with pytest.raises(CudaError):
         dec.Decompressor(CSP_BGRA, 64, 32, src_chroma=4)
     # codec.c:1930-1980

@@ -82,19 +82,20 @@ def test_checker_against_the_live_library_on_422_and_444_pictures():
                     a = sr.decompress_convert(y, u, v, csp, spc, full, src_chroma=3)
                     b = ol.oracle_decode_convert(y, u, v, csp, spc, full, src_chroma=3)
                     assert (pixel_bytes(a, csp, w, h) == pixel_bytes(b, csp, w, h)).all(), (w, h, hex(csp), spc, full)
-    assert ol.oracle_decode_convert(y, u, v, sr.CSP_YUYV, src_chroma=3) is None      # 4:4:4 -> 4:2:2 down-samples chroma: not restated
-    y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((18, 24), (18, 12), (18, 12)))
-    assert ol.oracle_decode_convert(y, u, v, sr.CSP_I420, src_chroma=2) is None      # 4:2:2 -> 4:2:0 likewise
-    # planar outputs with MORE chroma than the picture: libswscale's 4-tap scaler on the chroma planes
-    for w, h in ((24, 18), (90, 50), (12, 10)):
-        for src, csps in ((1, (sr.CSP_YV16, sr.CSP_YV24)), (2, (sr.CSP_YV24,))):
-            ch = h if src == 2 else h // 2
-            for y, u, v in ((rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (ch, w // 2), dtype=np.uint8), rng.integers(0, 256, (ch, w // 2), dtype=np.uint8)),
-                            (rng.choice(np.array([0, 255], np.uint8), (h, w)), rng.choice(np.array([0, 255], np.uint8), (ch, w // 2)), rng.choice(np.array([0, 255], np.uint8), (ch, w // 2)))):
-                for csp in csps:
+    # every YUV output of every picture format: where the chroma resolution changes, libswscale's scaler runs on the chroma planes
+    # (4 taps up, 8 taps down), packed 4:2:2 from 4:4:4 adds the single-line packed writers
+    for w, h in ((24, 24), (90, 50), (64, 32)):
+        for src in (1, 2, 3):
+            cw, ch = (w if src == 3 else w // 2), (h if src >= 2 else h // 2)
+            for y, u, v in ((rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (ch, cw), dtype=np.uint8), rng.integers(0, 256, (ch, cw), dtype=np.uint8)),
+                            (rng.choice(np.array([0, 255], np.uint8), (h, w)), rng.choice(np.array([0, 255], np.uint8), (ch, cw)), rng.choice(np.array([0, 255], np.uint8), (ch, cw)))):
+                for csp in (sr.CSP_I420, sr.CSP_YV12, sr.CSP_YV16, sr.CSP_YV24, sr.CSP_NV12, sr.CSP_YUYV, sr.CSP_UYVY):
                     a = sr.decompress_convert(y, u, v, csp, 2, 0, src_chroma=src)
                     b = ol.oracle_decode_convert(y, u, v, csp, 2, 0, src_chroma=src)
-                    assert (a == b).all(), (w, h, src, csp)
+                    assert b is not None and (a == b).all(), (w, h, src, csp)
+    # too small for libswscale's full tap count: refused, not approximated
+    y, u, v = (rng.integers(0, 256, s, dtype=np.uint8) for s in ((10, 16), (10, 8), (10, 8)))
+    assert ol.oracle_decode_convert(y, u, v, sr.CSP_I420, src_chroma=2) is None
 
 
 def test_reference_context_never_gets_full_chroma_interpolation():

@@ -330,43 +330,87 @@ __global__ void __launch_bounds__(256) dec_planar_kernel(const DecPlanarJob j)
     else for (int q = 0; q < 16 && xb + q < cw; q++) { du[q] = __ldg(su + xb + q); dv[q] = __ldg(sv + xb + q); }
 }
 
-// Planar output with MORE chroma than the decoder picture (4:2:0 -> YV16 / YV24, 4:2:2 -> YV24): libswscale's general scaler
-// on a chroma plane -- horizontal 2x bicubic into 15-bit intermediates, c15 = min((sum tap * sample) >> 7, 32767), then the
-// vertical filter and the 8-bit plane writer, out = clip8((sum tap * c15 + (64 << 12)) >> 19).  Where a direction is not scaled
-// its table holds one tap of 1.0 (16384 / 4096), which makes the same expression the identity.  Thread = one output sample of
-// both planes; a rare path, kept simple.
+// YUV output with ANOTHER chroma resolution than the decoder picture (4:2:0 -> YV16 / YV24, 4:2:2 -> I420 / YV12 / NV12 / YV24,
+// 4:4:4 -> I420 / YV12 / NV12 / YV16): libswscale's general scaler on a chroma plane -- horizontal bicubic (4 taps for 2x up, 8 for
+// 2:1 down, 14-bit) into 15-bit intermediates, c15 = min((sum tap * sample) >> 7, 32767), then the vertical filter (4 / 8 taps,
+// 12-bit) and the 8-bit plane writer, out = clip8((sum tap * c15 + (64 << 12)) >> 19).  Where a direction is not scaled its table
+// holds one tap of 1.0 (16384 / 4096), which makes the same expression the identity.  Thread = one output sample of both
+// planes; rare paths, kept simple (zero taps are skipped, which also keeps every load inside the plane).
+struct DecTap8 { int pos; int c[4]; int pad[3]; };          // first sample + 8 coefficients as s16 pairs
+
 struct DecUpJob {
     const uint8_t *u, *v; int us, vs;
-    uint8_t *du, *dv;
+    uint8_t *du, *dv;               // first output sample of each plane
+    int ostride, ostep;             // bytes between output rows / samples (NV12: w, 2; planar: chroma width, 1)
     int ocw, och;                   // output chroma plane
-    const DecRow *cols, *rows;      // horizontal / vertical taps per output column / row (pos, c01, c23)
+    const DecTap8 *cols, *rows;     // horizontal / vertical taps per output column / row
     size_t src_frame_bytes, dst_frame_bytes;
 };
 
-__global__ void __launch_bounds__(256) dec_upchroma_kernel(const DecUpJob j)
+__device__ __forceinline__ int dec_tap(const int4 &a, const int4 &b, int i)
+{
+    // a = {pos, c01, c23, c45}, b.x = c67
+    const int w = i < 2 ? a.y : i < 4 ? a.z : i < 6 ? a.w : b.x;
+    return (i & 1) ? w >> 16 : (int)(short)(w & 0xffff);
+}
+
+// 15-bit intermediate of one chroma line at the output column whose taps are (ha, hb): hScale8To15
+__device__ __forceinline__ int dec_hscale(const uint8_t *line, const int4 &ha, const int4 &hb)
+{
+    int a = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int c = dec_tap(ha, hb, i);
+        if (c) a += (int)__ldg(line + ha.x + i) * c;
+    }
+    return min(a >> 7, 32767);
+}
+
+__global__ void __launch_bounds__(256) dec_resample_kernel(const DecUpJob j)
 {
     const int x = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
     if (x >= j.ocw || r >= j.och) return;
-    const int4 hc = __ldg((const int4 *)(j.cols + x)), vc = __ldg((const int4 *)(j.rows + r));
-    const int hcoef[4] = {(short)(hc.y & 0xffff), hc.y >> 16, (short)(hc.z & 0xffff), hc.z >> 16};
-    const int vcoef[4] = {(short)(vc.y & 0xffff), vc.y >> 16, (short)(vc.z & 0xffff), vc.z >> 16};
+    const int4 ha = __ldg((const int4 *)(j.cols + x)), hb = __ldg((const int4 *)(j.cols + x) + 1);
+    const int4 va = __ldg((const int4 *)(j.rows + r)), vb = __ldg((const int4 *)(j.rows + r) + 1);
     const size_t so = (size_t)blockIdx.z * j.src_frame_bytes, dof = (size_t)blockIdx.z * j.dst_frame_bytes;
 #pragma unroll
     for (int c = 0; c < 2; c++) {
-        const uint8_t *sp = (c ? j.v : j.u) + so + hc.x;
+        const uint8_t *sp = (c ? j.v : j.u) + so;
         const int st = c ? j.vs : j.us;
         int acc = 0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (!vcoef[q]) continue;                       // also keeps the loads inside the plane: padding taps are zero
-            const uint8_t *line = sp + (ptrdiff_t)(vc.x + q) * st;
-            int a = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) if (hcoef[i]) a += (int)__ldg(line + i) * hcoef[i];
-            acc += min(a >> 7, 32767) * vcoef[q];
+        for (int q = 0; q < 8; q++) {
+            const int vcoef = dec_tap(va, vb, q);
+            if (vcoef) acc += dec_hscale(sp + (ptrdiff_t)(va.x + q) * st, ha, hb) * vcoef;
         }
-        ((c ? j.dv : j.du) + dof)[(size_t)r * j.ocw + x] = (uint8_t)clip8((acc + (64 << 12)) >> 19);
+        ((c ? j.dv : j.du) + dof)[(size_t)r * j.ostride + (size_t)x * j.ostep] = (uint8_t)clip8((acc + (64 << 12)) >> 19);
     }
+}
+
+// 4:4:4 picture -> YUY2 / UYVY: chroma down-sampled horizontally as above, then libswscale's single-line packed writers:
+// yuv2yuyv422_1 SIMD in rows 0..h-3 (c15 >> 7), the C writer in the last two rows and in every row of UYVY ((c15 + 64) >> 7).
+// Thread = one pixel pair.
+struct Dec444PackedJob {
+    const uint8_t *y, *u, *v; int ys, us, vs;
+    uint8_t *dst;
+    int w, h, uyvy;
+    const DecTap8 *cols;
+    size_t src_frame_bytes, dst_frame_bytes;
+};
+
+__global__ void __launch_bounds__(256) dec_444_packed_kernel(const Dec444PackedJob j)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
+    if (2 * x >= j.w || r >= j.h) return;
+    const int4 ha = __ldg((const int4 *)(j.cols + x)), hb = __ldg((const int4 *)(j.cols + x) + 1);
+    const size_t so = (size_t)blockIdx.z * j.src_frame_bytes;
+    const int cu = dec_hscale(j.u + so + (ptrdiff_t)r * j.us, ha, hb), cv = dec_hscale(j.v + so + (ptrdiff_t)r * j.vs, ha, hb);
+    const bool c_writer = j.uyvy || r >= j.h - 2;
+    const int U = clip8(c_writer ? (cu + 64) >> 7 : cu >> 7), V = clip8(c_writer ? (cv + 64) >> 7 : cv >> 7);
+    const uint8_t *yp = j.y + so + (ptrdiff_t)r * j.ys + 2 * x;
+    const int y0 = __ldg(yp), y1 = __ldg(yp + 1);
+    const uint32_t px = j.uyvy ? (uint32_t)U | (y0 << 8) | (V << 16) | (y1 << 24) : (uint32_t)y0 | (U << 8) | (y1 << 16) | (V << 24);
+    *(uint32_t *)(j.dst + (size_t)blockIdx.z * j.dst_frame_bytes + (size_t)r * 2 * j.w + 4 * (size_t)x) = px;
 }
 
 // ---- host side: the context x264vfw_init_sws_context builds, as numbers --------------------------------------
@@ -468,6 +512,96 @@ static bool bicubic_2x_filter(int src_n, std::vector<DecRow> &rows, bool c_write
     return true;
 }
 
+// Tap tables of dec_resample_kernel: libswscale's initFilter() for the bicubic cases this context meets -- 2x up-sampling (1 + 4
+// taps before the cut), 2:1 down-sampling (1 + 4 * src / dst = 9 taps before the cut, distances scaled by dst / src, unit halved) --
+// or one tap of 1.0 when the sizes agree.  At most 8 taps survive the cut; out-of-plane taps are folded onto the edge sample.
+static bool resample_taps(int src_n, int dst_n, int one, int align, std::vector<DecTap8> &out)
+{
+    out.assign(dst_n, DecTap8{0, {0, 0, 0, 0}, {0, 0, 0}});
+    auto put = [&](int i, int k, int c) { out[i].c[k >> 1] |= (k & 1) ? (int)((unsigned)(c & 0xffff) << 16) : (c & 0xffff); };
+    if (src_n == dst_n) {
+        for (int i = 0; i < dst_n; i++) { out[i].pos = i; put(i, 0, one); }
+        return true;
+    }
+    const bool down = src_n == 2 * dst_n;
+    if (!down && dst_n != 2 * src_n) return false;
+    if (down ? src_n < 12 : src_n < 6) return false;            // below that libswscale cuts its tap count to the plane: not covered
+    const long long inc = (((long long)src_n << 16) + (dst_n >> 1)) / dst_n;
+    const long long unit = 1LL << (down ? 53 : 54);              // fone = 1 << (54 - av_log2(src / dst))
+    const int taps = std::min(down ? 9 : 5, src_n - 2);           // capped by the plane
+    const long long Cq = (long long)(0.6 * (1 << 24));
+    std::vector<long long> f((size_t)dst_n * taps);
+    std::vector<int> pos(dst_n);
+    long long at = ((128 * inc) >> 7) - ((128 * 0x10000LL) >> 7);
+    for (int i = 0; i < dst_n; i++, at += 2 * inc) {
+        int xx = (int)((at - (long long)(taps - 2) * (1LL << 16)) / (1 << 17));
+        pos[i] = xx;
+        for (int t = 0; t < taps; t++, xx++) {
+            long long d = llabs((long long)xx * (1 << 17) - at) << 13;
+            if (down) d = d * dst_n / src_n;
+            long long c = 0;
+            if (d < (1LL << 31)) {
+                const long long dd = (d * d) >> 30, ddd = (dd * d) >> 30;
+                c = d < (1LL << 30)
+                        ? (12 * (1 << 24) - 6 * Cq) * ddd + (-18 * (1 << 24) + 6 * Cq) * dd + 6LL * (1 << 24) * (1LL << 30)
+                        : -6 * Cq * ddd + 30 * Cq * dd - 48 * Cq * d + 24 * Cq * (1LL << 30);
+            }
+            f[(size_t)i * taps + t] = c / ((1LL << 54) / unit);
+        }
+    }
+    const double cut = 0.002 * (double)unit;
+    int support = 0;
+    for (int i = dst_n - 1; i >= 0; i--) {
+        long long *fi = &f[(size_t)i * taps];
+        long long acc = 0;
+        for (int t = 0; t < taps; t++) {
+            acc += llabs(fi[0]);
+            if ((double)acc > cut || (i < dst_n - 1 && pos[i] >= pos[i + 1])) break;
+            memmove(fi, fi + 1, (taps - 1) * sizeof(*fi));
+            fi[taps - 1] = 0;
+            pos[i]++;
+        }
+        int n = taps;
+        acc = 0;
+        for (int t = taps - 1; t > 0; t--) {
+            acc += llabs(fi[t]);
+            if ((double)acc > cut) break;
+            n--;
+        }
+        support = n > support ? n : support;
+    }
+    const int size = (support + align - 1) & ~(align - 1);
+    if (size > 8 || size > src_n) return false;
+    for (int i = 0; i < dst_n; i++) {
+        long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < size && q < taps; q++) t[q] = f[(size_t)i * taps + q];
+        if (pos[i] < 0) {
+            for (int q = 1; q < size; q++) { const int to = q + pos[i] > 0 ? q + pos[i] : 0; t[to] += t[q]; t[q] = 0; }
+            pos[i] = 0;
+        }
+        if (pos[i] + size > src_n) {
+            const int shift = pos[i] + size - src_n;
+            long long acc = 0;
+            for (int q = size - 1; q >= 0; q--) if (pos[i] + q >= src_n) { acc += t[q]; t[q] = 0; }
+            for (int q = size - 1; q >= 0; q--) t[q] = q < shift ? 0 : t[q - shift];
+            pos[i] -= shift;
+            t[src_n - 1 - pos[i]] += acc;
+        }
+        long long sum = 0, err = 0;
+        for (int q = 0; q < size; q++) sum += t[q];
+        sum = (sum + one / 2) / one;
+        if (!sum) sum = 1;
+        out[i].pos = pos[i];
+        for (int q = 0; q < size; q++) {
+            const long long v = t[q] + err;
+            const long long iv = v >= 0 ? (v + (sum >> 1)) / sum : (v - (sum >> 1)) / sum;
+            put(i, q, (int)iv);
+            err = v - iv * sum;
+        }
+    }
+    return true;
+}
+
 static int to_int16(long long f)
 {
     long long r = (f + (1 << 15)) >> 16;
@@ -520,9 +654,10 @@ static void colour_constants(DecConst &k, int avcol_spc, int fullrange, int roun
 struct Dec {
     Ctx *ctx;
     int csp, flip, w, h, v422, v444;
-    int up = 0;                 // planar output with more chroma than the picture: dec_upchroma_kernel (d_rows + d_cols)
+    int up = 0;                 // 1: planar output with another chroma resolution (dec_resample_kernel), 2: 4:4:4 -> YUY2 / UYVY
     DecConst k;
-    DecRow *d_rows = nullptr, *d_cols = nullptr;
+    DecRow *d_rows = nullptr;
+    DecTap8 *d_cols = nullptr, *d_vtaps = nullptr;
     // staging of the host-buffer entry
     uint8_t *d_src = nullptr, *d_dst = nullptr;
     size_t src_bytes = 0, dst_bytes = 0;
@@ -537,9 +672,20 @@ static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src
     const int w = d->w, h = d->h, cw = d->v444 ? w : w / 2, ch = d->v422 || d->v444 ? h : h / 2;
     if (n <= 0) return 0;
     if (n > 65535) { set_error("at most 65535 pictures per launch"); return -1; }
+    if (d->up == 2) {
+        Dec444PackedJob pj;
+        pj.y = src[0]; pj.u = src[1]; pj.v = src[2]; pj.ys = ss[0]; pj.us = ss[1]; pj.vs = ss[2];
+        pj.dst = dst; pj.w = w; pj.h = h; pj.uyvy = d->csp == X264VFW_CUDA_CSP_UYVY; pj.cols = d->d_cols;
+        pj.src_frame_bytes = sfb; pj.dst_frame_bytes = dfb;
+        if (!al(dst, 4) || !als((long long)dfb, 4)) { set_error("output picture must be 4-byte aligned"); return -1; }
+        dec_444_packed_kernel<<<dim3((w / 2 + 31) / 32, (h + 7) / 8, n), dim3(32, 8), 0, st>>>(pj);
+        XV_LAUNCH_CHECK();
+        return 0;
+    }
     if (d->up) {
-        // luma: plane copy (the planar kernel with no chroma rows in its grid); chroma: the up-sampling kernel
-        const int ocw = d->csp == X264VFW_CUDA_CSP_YV24 ? w : w / 2, och = h;
+        // luma: plane copy (the planar kernel with no chroma rows in its grid); chroma: the resampling kernel
+        const bool o420 = d->csp == X264VFW_CUDA_CSP_I420 || d->csp == X264VFW_CUDA_CSP_YV12 || d->csp == X264VFW_CUDA_CSP_NV12;
+        const int ocw = d->csp == X264VFW_CUDA_CSP_YV24 ? w : w / 2, och = o420 ? h / 2 : h;
         DecPlanarJob pj;
         pj.y = src[0]; pj.u = src[1]; pj.v = src[2]; pj.ys = ss[0]; pj.us = ss[1]; pj.vs = ss[2];
         pj.w = w; pj.h = h; pj.cw = cw; pj.src_frame_bytes = sfb; pj.dst_frame_bytes = dfb;
@@ -552,10 +698,14 @@ static int dec_launch(Dec *d, uint8_t *dst, size_t dfb, const uint8_t *const src
         DecUpJob uj;
         uj.u = src[1]; uj.v = src[2]; uj.us = ss[1]; uj.vs = ss[2];
         uint8_t *p1 = dst + (size_t)w * h, *p2 = p1 + (size_t)ocw * och;
-        uj.du = p2; uj.dv = p1;                                                       // YV16 / YV24: codec.c:2263-2274
-        uj.ocw = ocw; uj.och = och; uj.cols = d->d_cols; uj.rows = d->d_rows;
+        if (d->csp == X264VFW_CUDA_CSP_NV12) { uj.du = p1; uj.dv = p1 + 1; uj.ostride = w; uj.ostep = 2; }
+        else {
+            uj.ostride = ocw; uj.ostep = 1;
+            if (d->csp == X264VFW_CUDA_CSP_I420) { uj.du = p1; uj.dv = p2; } else { uj.du = p2; uj.dv = p1; }   // YV12 / YV16 / YV24: codec.c:2263-2274
+        }
+        uj.ocw = ocw; uj.och = och; uj.cols = d->d_cols; uj.rows = d->d_vtaps;
         uj.src_frame_bytes = sfb; uj.dst_frame_bytes = dfb;
-        dec_upchroma_kernel<<<dim3((ocw + 31) / 32, (och + 7) / 8, n), dim3(32, 8), 0, st>>>(uj);
+        dec_resample_kernel<<<dim3((ocw + 31) / 32, (och + 7) / 8, n), dim3(32, 8), 0, st>>>(uj);
         XV_LAUNCH_CHECK();
         return 0;
     }
@@ -650,43 +800,28 @@ int x264vfw_cuda_dec_open(x264vfw_cuda_dec **pdec, x264vfw_cuda_ctx *ctx, int i_
     const int out_chroma = out420 ? 1 : csp == X264VFW_CUDA_CSP_YV16 || csp == X264VFW_CUDA_CSP_YUYV || csp == X264VFW_CUDA_CSP_UYVY ? 2 :
                            csp == X264VFW_CUDA_CSP_YV24 ? 3 : 0;
     const bool planar_out = out420 || csp == X264VFW_CUDA_CSP_YV16 || csp == X264VFW_CUDA_CSP_YV24;
-    if ((planar_out && out_chroma < i_src_chroma) || (v444 && out_chroma == 2)) {
-        set_error("YUV output with less chroma than the decoder picture is not covered (libswscale's down-sampling filters)");
-        return -1;
-    }
-    const bool up = planar_out && out_chroma > i_src_chroma;      // 4:2:0 -> YV16 / YV24, 4:2:2 -> YV24
-    if (up && (h < 12 || w < 12)) { set_error("pictures below 12 rows / columns are not covered"); return -1; }
+    // 1: planar output with another chroma resolution than the picture; 2: 4:4:4 -> YUY2 / UYVY (libswscale resamples the chroma)
+    const int up = planar_out && out_chroma != i_src_chroma ? 1 : v444 && out_chroma == 2 ? 2 : 0;
     const bool rgb = csp == X264VFW_CUDA_CSP_BGR || csp == X264VFW_CUDA_CSP_BGRA;
     if (flip && !rgb) { set_error("only RGB output can be bottom-up (codec.c:510-527)"); return -1; }
-    const bool planar = planar_out || v444;               // no row table: plane copies, and the per-pixel 4:4:4 writer
+    const bool planar = planar_out || v444;               // no packed-writer row table: plane copies, resampled planes, the per-pixel 4:4:4 writer
     Ctx *c = (Ctx *)ctx;
     XV_CUDA_OK(cudaSetDevice(c->device));
     Dec *d = new Dec;
     d->ctx = c; d->csp = csp; d->flip = flip; d->w = w; d->h = h; d->v422 = v422; d->v444 = v444; d->up = up;
     colour_constants(d->k, i_avcol_spc, b_fullrange != 0, v422 ? 0 : 4);
     if (up) {
-        const int cw = w / 2, ch = v422 ? h : h / 2, ocw = csp == X264VFW_CUDA_CSP_YV24 ? w : w / 2, och = h;
-        std::vector<DecRow> rows, cols;
-        auto identity = [](int n, int one, std::vector<DecRow> &t) {          // one tap of 1.0 on the sample itself, inside a 4-sample window
-            t.resize(n);
-            for (int i = 0; i < n; i++) {
-                const int pos = std::min(i, n - 4), k = i - pos;
-                t[i].pos = pos;
-                t[i].c01 = k == 0 ? one : k == 1 ? (int)((unsigned)one << 16) : 0;
-                t[i].c23 = k == 2 ? one : k == 3 ? (int)((unsigned)one << 16) : 0;
-                t[i].c_writer = 1;
-            }
-        };
-        bool ok = true;
-        if (och != ch) ok = bicubic_2x_filter(ch, rows, true, 1 << 12, 2, false); else identity(och, 1 << 12, rows);
-        if (ok) { if (ocw != cw) ok = bicubic_2x_filter(cw, cols, true, 1 << 14, 4, false); else identity(ocw, 1 << 14, cols); }
-        if (!ok || cudaMalloc((void **)&d->d_rows, rows.size() * sizeof(DecRow)) != cudaSuccess ||
-            cudaMalloc((void **)&d->d_cols, cols.size() * sizeof(DecRow)) != cudaSuccess ||
-            cudaMemcpy(d->d_rows, rows.data(), rows.size() * sizeof(DecRow), cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(d->d_cols, cols.data(), cols.size() * sizeof(DecRow), cudaMemcpyHostToDevice) != cudaSuccess) {
-            set_error(ok ? "filter table upload failed" : "picture too small for libswscale's 4-tap chroma filters");
-            if (d->d_rows) cudaFree(d->d_rows);
+        const int cw = v444 ? w : w / 2, ch = v422 || v444 ? h : h / 2;
+        const int ocw = csp == X264VFW_CUDA_CSP_YV24 ? w : w / 2, och = up == 2 || !out420 ? h : h / 2;
+        std::vector<DecTap8> cols, rows;
+        const bool ok = resample_taps(cw, ocw, 1 << 14, 4, cols) && resample_taps(ch, och, 1 << 12, 2, rows);
+        if (!ok || cudaMalloc((void **)&d->d_cols, cols.size() * sizeof(DecTap8)) != cudaSuccess ||
+            cudaMalloc((void **)&d->d_vtaps, rows.size() * sizeof(DecTap8)) != cudaSuccess ||
+            cudaMemcpy(d->d_cols, cols.data(), cols.size() * sizeof(DecTap8), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(d->d_vtaps, rows.data(), rows.size() * sizeof(DecTap8), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error(ok ? "filter table upload failed" : "picture too small for libswscale's chroma filters (12 samples to halve, 6 to double)");
             if (d->d_cols) cudaFree(d->d_cols);
+            if (d->d_vtaps) cudaFree(d->d_vtaps);
             delete d;
             return -1;
         }
@@ -728,6 +863,7 @@ void x264vfw_cuda_dec_close(x264vfw_cuda_dec *dec)
     cudaStreamSynchronize(d->ctx->stream);
     if (d->d_rows) cudaFree(d->d_rows);
     if (d->d_cols) cudaFree(d->d_cols);
+    if (d->d_vtaps) cudaFree(d->d_vtaps);
     if (d->d_src) cudaFree(d->d_src);
     if (d->d_dst) cudaFree(d->d_dst);
     delete d;
