@@ -456,7 +456,7 @@ int x264vfw_cuda_integral_init( x264vfw_cuda_ctx *ctx, uint16_t *sum8_dev, uint1
  * what it makes of YV24 input).  Destination: the output DIB
  * laid out by x264vfw_picture_fill (codec.c:419-503), i_out_csp = what get_csp() returns for the OUTPUT header
  * (codec.c:1994-1998): X264VFW_CUDA_CSP_{I420,YV12,YV16,YV24,NV12,YUYV,UYVY,BGR,BGRA}, | X264VFW_CUDA_CSP_VFLIP for bottom-up
- * RGB (x264vfw_picture_vflip, codec.c:510-527); the YV12 U/V swap of codec.c:2263-2274 is applied inside.
+ * RGB (x264vfw_picture_vflip, codec.c:510-527); the U/V swap of codec.c:2263-2274 (YV12 / YV16 / YV24) is applied inside.
  * i_avcol_spc: decoder_context->colorspace (AVCOL_SPC_*, the switch of codec.c:2114-2140); b_fullrange: color_range ==
  * AVCOL_RANGE_JPEG or a YUVJ pixel format (codec.c:2091-2095).  Results are byte-identical to libswscale 9.1.100 (x86-64)
  * driven that way -- including that SWS_FULL_CHR_H_INT never reaches the context (codec.c:2097 vs :2110), so RGB output
@@ -478,7 +478,7 @@ int64_t x264vfw_cuda_dec_picture_size( int i_out_csp, int i_width, int i_height 
  * dst_host holds x264vfw_cuda_dec_picture_size() bytes.  0 / -1. */
 int x264vfw_cuda_dec_convert( x264vfw_cuda_dec *dec, uint8_t *dst_host, const uint8_t *const src_host[3],
                               const int src_stride[3] );
-/* n_frames pictures, DEVICE buffers, one launch, asynchronous on the context's stream: picture f reads its planes at
+/* n_frames pictures, DEVICE buffers, one launch (two where the chroma resolution changes), asynchronous on the context's stream: picture f reads its planes at
  * src_dev[i] + f*src_frame_bytes and writes its DIB at dst_dev + f*dst_frame_bytes.  The entry the roofline number of
  * this stage is measured on. */
 int x264vfw_cuda_dec_convert_batch( x264vfw_cuda_dec *dec, uint8_t *dst_dev, size_t dst_frame_bytes,
