@@ -485,6 +485,15 @@ int x264vfw_cuda_dec_convert_batch( x264vfw_cuda_dec *dec, uint8_t *dst_dev, siz
                                     const uint8_t *const src_dev[3], const int src_stride[3], size_t src_frame_bytes,
                                     int n_frames );
 
+/* Host-only views of the tables those kernels are handed (no device needed; the CPU test suite holds them against the checker):
+ * the tap table of a chroma plane resampled from src_n to dst_n samples (dst_n = 2 src_n, src_n = 2 dst_n or equal; one = 1 << 14
+ * with align 4 horizontally, 1 << 12 with align 2 vertically) as pos[dst_n] + coef[dst_n][8]; and the per-row table of the
+ * packed writers for a 4:2:0 picture with chroma_rows chroma lines: pos[2n], coef[2n][4] as the writer of that row sees them
+ * (libswscale's SIMD writers pack coefficient pairs into one int, so a negative even tap borrows 1 from the odd one), and which
+ * rows take the C writer.  0 / -1 (sizes the kernels do not cover). */
+int x264vfw_cuda_dec_filter_taps( int src_n, int dst_n, int one, int align, int32_t *pos, int16_t *coef );
+int x264vfw_cuda_dec_packed_rows( int chroma_rows, int b_uyvy, int32_t *pos, int16_t *coef, int32_t *c_writer );
+
 const char *x264vfw_cuda_last_error( void );
 /* "x264vfw_cuda <version> sm_100a"; also proves the library loaded. */
 const char *x264vfw_cuda_version( void );

@@ -132,3 +132,50 @@ def test_new_entry_points_reject_null_arguments_without_a_device():
     assert lib.x264vfw_cuda_weights_analyse(None, None, C.byref(out), None) == -1
     assert lib.x264vfw_cuda_la_weights_analyse(None, 1, 0, None, None, 0, C.byref(out), None) == -1
     assert lib.x264vfw_cuda_integral_init(None, None, None, None, 64, 64, 0, 0, 1) == -1
+
+
+def test_decoder_filter_tables_of_the_product_equal_the_checkers():
+    """Host logic of the decoder-side conversion without a device: the tap tables the kernels are handed (the product's own initFilter
+    restatement) against the checker's, for 2x up, 2:1 down and identity, both coefficient scales; and the packed writers' row table
+    with libswscale's coefficient-pair borrow and its C-writer rows."""
+    import ctypes as C
+    import numpy as np
+    import oracle_lib as ol
+    from x264vfw_b200 import lib
+    o = ol.oracle()
+    lib.x264vfw_cuda_dec_filter_taps.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    lib.x264vfw_cuda_dec_packed_rows.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    o.orc_sws_filter.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
+    checked = 0
+    for one, align in ((1 << 14, 4), (1 << 12, 2)):
+        for n in (6, 7, 12, 13, 19, 35, 360, 540, 640, 960, 1080):
+            for src, dst in ((n, 2 * n), (2 * n, n)):
+                pos_p, co_p = np.zeros(dst, np.int32), np.zeros((dst, 8), np.int16)
+                pos_o, co_o = np.zeros(dst, np.int32), np.zeros((dst, 8), np.int16)
+                rp = lib.x264vfw_cuda_dec_filter_taps(src, dst, one, align, pos_p.ctypes.data, co_p.ctypes.data)
+                if src > dst and src < 12:
+                    assert rp == -1                                   # too small to halve with the full 8 taps
+                    continue
+                assert rp == 0 and o.orc_sws_filter(src, dst, align, one, 128, 128, co_o.ctypes.data, pos_o.ctypes.data) > 0
+                assert (pos_p == pos_o).all() and (co_p == co_o).all(), (src, dst, one)
+                assert (co_p.sum(1) == one).all()                       # every output sample is a weighted mean
+                checked += 1
+    assert checked >= 40
+    pos, co = np.zeros(8, np.int32), np.zeros((8, 8), np.int16)
+    assert lib.x264vfw_cuda_dec_filter_taps(8, 8, 1 << 14, 4, pos.ctypes.data, co.ctypes.data) == 0
+    assert (pos == np.arange(8)).all() and (co[:, 0] == 1 << 14).all() and not co[:, 1:].any()      # same size: one tap of 1.0
+    assert lib.x264vfw_cuda_dec_filter_taps(8, 24, 1 << 14, 4, pos.ctypes.data, co.ctypes.data) == -1
+    # packed writers, 4:2:0 picture with 540 chroma lines
+    n = 540
+    pos, co, cw = np.zeros(2 * n, np.int32), np.zeros((2 * n, 4), np.int16), np.zeros(2 * n, np.int32)
+    assert lib.x264vfw_cuda_dec_packed_rows(n, 0, pos.ctypes.data, co.ctypes.data, cw.ctypes.data) == 0
+    pos_o, co_o = np.zeros(2 * n, np.int32), np.zeros((2 * n, 8), np.int16)
+    assert o.orc_sws_filter(n, 2 * n, 2, 1 << 12, 128, 128, co_o.ctypes.data, pos_o.ctypes.data) == 4
+    want = co_o[:, :4].astype(np.int32)
+    simd = np.arange(2 * n) < 2 * n - 2                                 # libswscale leaves its SIMD writers for the last two lines
+    for k in (0, 2):
+        want[:, k + 1] -= (simd & (want[:, k] < 0))                     # f[k] + f[k+1] * 65536 as ONE int: the borrow
+    assert (pos == pos_o).all() and (co == want).all() and (cw == ~simd).all()
+    assert (pos == np.clip(((np.arange(2 * n) + 1) >> 1) - 2, 0, n - 4)).all()      # what dec_packed_kernel derives instead of loading
+    assert lib.x264vfw_cuda_dec_packed_rows(n, 1, pos.ctypes.data, co.ctypes.data, cw.ctypes.data) == 0
+    assert cw.all() and (co == co_o[:, :4]).all()                          # UYVY: the C writer everywhere, plain coefficients

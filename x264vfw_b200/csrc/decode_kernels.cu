@@ -771,6 +771,30 @@ using namespace xv;
 
 extern "C" {
 
+// Host-only views of the filter tables (no device needed): what the kernels are handed, for the CPU test suite.
+int x264vfw_cuda_dec_filter_taps(int src_n, int dst_n, int one, int align, int32_t *pos, int16_t *coef)
+{
+    std::vector<DecTap8> t;
+    if (!pos || !coef || src_n <= 0 || dst_n <= 0 || !resample_taps(src_n, dst_n, one, align, t)) return -1;
+    for (int i = 0; i < dst_n; i++) {
+        pos[i] = t[i].pos;
+        for (int k = 0; k < 8; k++) coef[8 * i + k] = (int16_t)((k & 1) ? t[i].c[k >> 1] >> 16 : (t[i].c[k >> 1] & 0xffff));
+    }
+    return 0;
+}
+
+int x264vfw_cuda_dec_packed_rows(int chroma_rows, int b_uyvy, int32_t *pos, int16_t *coef, int32_t *c_writer)
+{
+    std::vector<DecRow> rows;
+    if (!pos || !coef || !c_writer || chroma_rows <= 0 || !vertical_chroma_filter(chroma_rows, rows, b_uyvy != 0)) return -1;
+    for (int i = 0; i < 2 * chroma_rows; i++) {
+        pos[i] = rows[i].pos; c_writer[i] = rows[i].c_writer;
+        coef[4 * i] = (int16_t)(rows[i].c01 & 0xffff); coef[4 * i + 1] = (int16_t)(rows[i].c01 >> 16);
+        coef[4 * i + 2] = (int16_t)(rows[i].c23 & 0xffff); coef[4 * i + 3] = (int16_t)(rows[i].c23 >> 16);
+    }
+    return 0;
+}
+
 int64_t x264vfw_cuda_dec_picture_size(int i_out_csp, int w, int h)
 {
     // x264vfw_picture_get_size (codec.c:505-508) for the formats below
