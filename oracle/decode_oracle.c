@@ -336,7 +336,7 @@ int orc_decode_convert_src(int src_chroma, int out_csp, uint8_t *dst, const uint
         /* 4:4:4 picture -> YUY2 / UYVY: chroma down-sampled horizontally as above (8 taps), then libswscale's single-line packed
          * writers: yuv2yuyv422_1 SIMD in rows 0..h-3 (c15 >> 7), the C writer in the last two rows and in every row of UYVY
          * ((c15 + 64) >> 7); luma passes through. */
-        if (flip || w < 24) return -1;
+        if (flip || w < 12) return -1;                              /* below 12 chroma samples initFilter cuts its tap count to the plane: not restated */
         const int ocw = w / 2;
         int16_t (*hc)[8] = malloc(sizeof(int16_t[8]) * ocw);
         int *hp = malloc(sizeof(int) * ocw);
