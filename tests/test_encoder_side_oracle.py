@@ -184,3 +184,45 @@ def test_weights_full_refuses_other_chroma_formats_and_distances():
     uv = nv12(frames[0], w, h)
     assert orc.weights_full(0, 1, uv, uv, 64) is None                   # reference must precede the frame
     orc.close()
+
+
+# ---- the integral kernel's source on the CPU (lockstep warps, tests/sim/integral_sim.cpp) ------------------------------
+@pytest.fixture(scope="module")
+def integral_sim():
+    import ctypes as C
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "sim", "_build", "libintegral_sim.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    srcs = [os.path.join(here, "sim", "integral_sim.cpp"), os.path.join(here, "sim", "warp_sim.h"),
+            os.path.join(os.path.dirname(here), "x264vfw_b200", "csrc", "integral_kernel.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, srcs[0], "-lpthread"], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.sim_integral.restype = C.c_int
+    lib.sim_integral.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int]
+    return lib
+
+
+@pytest.mark.parametrize("rows,stride,with4", [(8, 16, True), (40, 64, False), (72, 136, True), (150, 260, True), (71, 128, False)])
+def test_integral_kernel_source_on_cpu_matches_checker(integral_sim, rows, stride, with4):
+    """x264vfw_b200/csrc/integral_kernel.cuh compiled by g++, every warp of the grid run as 32 threads in lockstep (shuffles as
+    exchanges): 8x8 / 4x4 box sums of two planes, and nothing written outside the valid domain."""
+    rng = np.random.default_rng(rows * 7 + stride)
+    nf = 2
+    planes = rng.integers(0, 256, (nf, rows, stride), dtype=np.uint8)
+    planes[0, : rows // 2] = 255
+    s8 = np.full((nf, rows, stride), 0x5a5a, np.uint16)
+    s4 = np.full((nf, rows, stride), 0x5a5a, np.uint16)
+    warps = integral_sim.sim_integral(s8.ctypes.data, s4.ctypes.data if with4 else None, planes.ctypes.data, stride, rows, rows * stride, rows * stride, nf)
+    assert warps > 0
+    for f in range(nf):
+        w8, w4 = ol.oracle_integral_init(planes[f], with_sum4=with4)
+        assert (s8[f, : rows - 7, : stride - 8] == w8[: rows - 7, : stride - 8]).all()
+        assert (s8[f, rows - 7:] == 0x5a5a).all() and (s8[f, :, stride - 8:] == 0x5a5a).all()
+        if with4:
+            assert (s4[f, : rows - 3, : stride - 4] == w4[: rows - 3, : stride - 4]).all()
+            assert (s4[f, rows - 3:] == 0x5a5a).all() and (s4[f, :, stride - 4:] == 0x5a5a).all()
+        else:
+            assert (s4[f] == 0x5a5a).all()
